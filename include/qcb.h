@@ -1,0 +1,209 @@
+/*
+ * qcb.h — C ABI of libqucumber_b200.so: B200 (sm_100a) kernels for the RBM hot path of
+ * PIQuIL/QuCumber v1.3.3 (block Gibbs sampling, effective energies and their gradients,
+ * exact enumeration, rotated-basis amplitudes/gradients).
+ *
+ * The reference has no FFI of its own: the seam is the Python object protocol of
+ * qucumber.rbm.BinaryRBM / PurificationRBM as consumed through nn_state.rbm_am / rbm_ph.
+ * Each entry point below names the reference code (file:line, relative to the reference
+ * checkout) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - Every pointer is a CUDA device pointer to contiguous row-major float64 unless stated.
+ *  - W is (nh, N) "weights"; b (N) "visible_bias"; c (nh) "hidden_bias"
+ *    (rbm/binary_rbm.py:48-72).  PurificationRBM adds U (na, N) "weights_U" and d (na)
+ *    "aux_bias" (rbm/purification_rbm.py:89-128).  na == 0 (U, d NULL) means BinaryRBM.
+ *  - Flat gradient order is [W row-major, (U row-major,) b, c, (d)] — the
+ *    parameters_to_vector order of rbm/binary_rbm.py:120 and rbm/purification_rbm.py:185.
+ *  - Visible/hidden states are float64 arrays holding exactly 0.0 or 1.0 (the reference's
+ *    domain).  Energy / gradient / probability entry points accept arbitrary real v.
+ *  - Kernels are enqueued on `stream` (a cudaStream_t) and return immediately; no hidden
+ *    synchronisation, no allocation.  Scratch memory is caller-owned: ask
+ *    qcb_workspace_bytes() and pass a device buffer of at least that size.
+ *  - Return value: QCB_OK or an error class; qcb_last_error() gives a thread-local message.
+ *  - There is no CPU fallback and no other backend: unsupported shapes return
+ *    QCB_ERR_UNSUPPORTED.
+ *
+ * Random numbers (used when `uniforms` is NULL)
+ *  Philox4x32-10.  key = (seed low 32, seed high 32);
+ *  counter = (chain id low 32, chain id high 32, sweep index, stream << 31 | slot / 4),
+ *  word `slot % 4` of the output.  The 53-bit uniform of a unit is
+ *      u = (hi * 2^21 + (lo >> 11)) * 2^-53,   hi from stream 0, lo from stream 1,
+ *  the same grid {m * 2^-53} torch's CPU bernoulli uses.  Slots: hidden unit i -> i,
+ *  auxiliary unit l -> nh + l, visible unit j -> roundup4(nh + na) + j.  Chain ids are
+ *  chain_id0 + row, sweep indices sweep0 + s, so a run sharded over ranks or split into
+ *  several calls draws exactly the same numbers as one call.  A unit is set when u < p.
+ *
+ * Fed uniforms (bit-exact replay of the reference under a given torch seed)
+ *  uniforms is (k, C, nh + na + N): per sweep and chain the hidden block, the auxiliary
+ *  block, then the visible block — the order rbm/binary_rbm.py:224-226 and
+ *  rbm/purification_rbm.py:332-335 consume torch.bernoulli draws.
+ */
+#ifndef QCB_H_
+#define QCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCB_VERSION 100 /* 0.1.0 */
+
+enum {
+  QCB_OK = 0,
+  QCB_ERR_BAD_ARG = 1,
+  QCB_ERR_UNSUPPORTED = 2,
+  QCB_ERR_CUDA = 3
+};
+
+/* Operation ids for qcb_workspace_bytes */
+enum {
+  QCB_OP_GIBBS = 1,
+  QCB_OP_ENERGY = 2,
+  QCB_OP_GRAD_REDUCE = 3,
+  QCB_OP_LOGZ = 4,
+  QCB_OP_EXACT_STATS = 5,
+  QCB_OP_CWF_ROTATED = 6,
+  QCB_OP_DM_ROTATED = 7,
+  QCB_OP_CDK_NEG = 8
+};
+
+int qcb_version(void);
+const char* qcb_last_error(void);
+
+/* Scratch bytes an operation needs for the given sizes (rows = C, B, or 0 when unused). */
+size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows);
+
+/* ---- Block Gibbs sampling ------------------------------------------------------------
+ * k sweeps of (h | v), (a | v), (v | h, a) on C chains, in place on v (C, N).
+ * Replaces BinaryRBM.gibbs_steps / sample_h_given_v / sample_v_given_h
+ * (rbm/binary_rbm.py:170-228) and PurificationRBM.gibbs_steps (rbm/purification_rbm.py:261-337).
+ * uniforms == NULL: in-kernel Philox draws (see above). */
+int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const double* c, const double* d,
+                  int N, int nh, int na, double* v, int64_t C, int k,
+                  uint64_t seed, uint64_t chain_id0, uint64_t sweep0, const double* uniforms,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Conditionals --------------------------------------------------------------------
+ * out (rows, n_out) = clamp(sigmoid(x M^T + bias [+ x2 M2^T]), 0, 1).
+ * prob_h_given_v: M = W (nh, N), transpose_m = 0;  prob_v_given_h: M = W used as (N, nh),
+ * transpose_m = 1 (rbm/binary_rbm.py:129-168; rbm/purification_rbm.py:196-259, where
+ * prob_v_given_ha adds the second term x2 = a, M2 = U).  m_rows/m_cols are the stored shape. */
+int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias,
+                       const double* x, const double* M2, int m2_rows, const double* x2,
+                       int64_t rows, double* out, void* stream);
+
+/* out[i] = (u[i] < p[i]) as 0.0/1.0 — torch.bernoulli(p, out=p) (rbm/binary_rbm.py:182,197)
+ * with u either fed (uniforms != NULL) or Philox slot i of chain `chain_id0`, sweep `sweep0`. */
+int qcb_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed,
+                  uint64_t chain_id0, uint64_t sweep0, double* out, void* stream);
+
+/* ---- Effective energy ----------------------------------------------------------------
+ * E_out[r] = -(b.v_r + sum_i softplus(W_i.v_r + c_i) [+ sum_l softplus(U_l.v_r + d_l)]),
+ * softplus with torch's threshold 20.  Replaces BinaryRBM.effective_energy
+ * (rbm/binary_rbm.py:75-96) and PurificationRBM.effective_energy with a=None
+ * (rbm/purification_rbm.py:131-158). */
+int qcb_rbm_energy(const double* W, const double* U, const double* b, const double* c, const double* d,
+                   int N, int nh, int na, const double* v, int64_t rows, double* E_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Energy gradients ----------------------------------------------------------------
+ * g (G) = [accumulate ? g : 0] + scale * sum_r grad E(v_r), grad E(v) = -[p_h (x) v, (p_a (x) v,) v, p_h (, p_a)].
+ * Replaces effective_energy_gradient(v, reduce=True) (rbm/binary_rbm.py:98-120;
+ * rbm/purification_rbm.py:160-185) and the 1/batch scalings of
+ * nn_states/neural_state.py:383,445. */
+int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const double* c, const double* d,
+                        int N, int nh, int na, const double* v, int64_t rows, double scale,
+                        double* g, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
+/* g_rows (rows, G): per-row gradients, effective_energy_gradient(v, reduce=False)
+ * (rbm/binary_rbm.py:121-126; rbm/purification_rbm.py:186-193). */
+int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const double* c, const double* d,
+                       int N, int nh, int na, const double* v, int64_t rows, double* g_rows, void* stream);
+
+/* Fused CD-k negative phase: k Gibbs sweeps on v (C, N) in place, then
+ * g += scale * sum_chains grad E(v_k)  (nn_states/neural_state.py:443-445 with scale = -1/C). */
+int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const double* c, const double* d,
+                    int N, int nh, int na, double* v, int64_t C, int k,
+                    uint64_t seed, uint64_t chain_id0, uint64_t sweep0, const double* uniforms,
+                    double scale, double* g, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Exact enumeration ---------------------------------------------------------------
+ * Basis states are generated from their index r in [first_state, first_state + count):
+ * visible unit j = (r >> (N-1-j)) & 1 — the row order of generate_hilbert_space
+ * (nn_states/neural_state.py:156-176) — so no (2^N, N) tensor exists anywhere.
+ * out2[0] = m = max_r(-E(r)), out2[1] = sum_r exp(-E(r) - m): log Z over the range is
+ * m + log(out2[1]); ranges combine with a max/sum.  Replaces partition()
+ * (rbm/binary_rbm.py:230-241; rbm/purification_rbm.py:453-463).  N <= 62. */
+int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const double* c, const double* d,
+                       int N, int nh, int na, uint64_t first_state, uint64_t count,
+                       double* out2, void* ws, size_t ws_bytes, void* stream);
+
+/* out2 = (m, s) with logsumexp_i(-E[i]) = m + log(s) for an explicit energy vector — partition()
+ * called with a user-supplied `space` tensor (rbm/binary_rbm.py:240). */
+int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, void* stream);
+
+/* One pass over the same index range with log Z known, for PositiveWaveFunction metrics and
+ * the exact negative phase.  target_re/target_im (may be NULL) point at the entries of the
+ * target state for `first_state` onwards.  out8:
+ *   [0] sum_r t_re(r) * psi(r)        [1] sum_r t_im(r) * psi(r)      psi = exp(-E/2 - logZ/2)
+ *   [2] sum_r p_t(r) * log clamp(p_t(r))   [3] sum_r p_t(r) * log clamp(p(r))
+ *   [4] sum_r p(r)                          [5..7] reserved (0)
+ * with p = exp(-E - logZ), p_t = t_re^2 + t_im^2, clamp to [2^-52, 1 - 2^-52]
+ * (utils/training_statistics.py:57-59, 131-135, 179-183).  If g_exact != NULL it receives
+ * (accumulated) sum_r p(r) * grad E(r), the exact negative phase of
+ * nn_states/neural_state.py:406-413.  BinaryRBM only (U, d NULL, na 0). */
+int qcb_rbm_exact_stats_range(const double* W, const double* b, const double* c, int N, int nh,
+                              uint64_t first_state, uint64_t count, double logZ,
+                              const double* target_re, const double* target_im,
+                              double* out8, double* g_exact, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Rotated-basis amplitude and gradient: ComplexWaveFunction ------------------------
+ * For each sample (row of `samples`, B x N) measured in `basis` (N codes indexing `unitaries`;
+ * code 0 must be the identity / "Z"), expand over the S non-identity sites (2^S states,
+ * expansion bit order of utils/unitaries.py:154-181), with psi = exp(-E_am/2) * exp(-i E_ph/2):
+ *   Upsi[b]  = sum_i Ut[i,b] psi(v_ib)                             -> Upsi (2, B) [re; im]
+ *   g_am    += sum_b Re[ sum_i Ut psi grad E_am(v_ib) / Upsi[b] ]
+ *   g_ph    += sum_b Re[ i sum_i Ut psi grad E_ph(v_ib) / Upsi[b] ]
+ * unitaries is (K, 2, 2, 2) = [code][re/im][row][col] (utils/unitaries.py:36-48).
+ * Replaces rotate_psi_inner_prod (utils/unitaries.py:189-233) and
+ * ComplexWaveFunction.rotated_gradient (nn_states/complex_wavefunction.py:162-211).
+ * g_am / g_ph may be NULL (amplitudes only); both are accumulated into, not overwritten. */
+int qcb_cwf_rotated(const double* W_am, const double* b_am, const double* c_am,
+                    const double* W_ph, const double* b_ph, const double* c_ph, int N, int nh,
+                    const double* samples, int64_t B, const uint8_t* basis, const double* unitaries, int K,
+                    double* Upsi, double* g_am, double* g_ph, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Rotated-basis probability and gradient: DensityMatrix ----------------------------
+ * Two PurificationRBMs (amplitude, phase) with the same (N, nh, na).  For each sample:
+ *   w_ij = Ut_i conj(Ut_j) rho~(v_i, v_j),  P[b] = sum_ij Re w_ij              -> UrhoU (B)
+ *   g_x += - sum_b sum_ij Re[ w_ij dlog rho~(v_i, v_j)/dx ] / (P[b] + 1e-8)
+ * Replaces rotate_rho_probs (utils/unitaries.py:236-283), DensityMatrix.pi / rho / pi_grad /
+ * rotated_gradient (nn_states/density_matrix.py:113-330) and PurificationRBM.gamma /
+ * gamma_grad (rbm/purification_rbm.py:352-451). */
+int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, const double* c_am, const double* d_am,
+                   const double* W_ph, const double* U_ph, const double* b_ph, const double* c_ph, const double* d_ph,
+                   int N, int nh, int na, const double* samples, int64_t B, const uint8_t* basis,
+                   const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Host-buffer convenience (the end-to-end path bench.py times) ---------------------
+ * Same as qcb_rbm_gibbs but v_host / params are HOST pointers (pinned for full speed); the
+ * call copies in, runs, copies out on `stream` using the caller's device scratch
+ * dev_scratch (>= qcb_gibbs_host_scratch_bytes) and synchronises the stream before returning. */
+size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C);
+int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
+                       const double* d_host, int N, int nh, int na, double* v_host, int64_t C, int k,
+                       uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                       void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* Kernel-launch counter (incremented by every kernel this library launches); bench.py reads it
+ * to report gpu_launches. */
+uint64_t qcb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCB_H_ */

@@ -284,14 +284,14 @@ class PurificationRBMOracle:
         return v
 
     def gibbs_steps_philox(self, k, initial_state, seed, chain_id0=0, sweep0=0):
-        """Slots: hidden i -> i, aux l -> round_up4(nh) + l, visible j -> round_up4(nh) + round_up4(na) + j."""
+        """Slots: hidden i -> i, aux l -> nh + l, visible j -> round_up4(nh + na) + j."""
         v = np.array(initial_state, dtype=np.float64, copy=True).reshape(-1, self.n)
         ids = np.arange(chain_id0, chain_id0 + v.shape[0], dtype=np.uint64)
-        h4, a4 = round_up4(self.nh), round_up4(self.na)
+        v0 = round_up4(self.nh + self.na)
         for s in range(k):
             h = (philox_uniforms(seed, ids, sweep0 + s, 0, self.nh) < self.prob_h_given_v(v)).astype(np.float64)
-            a = (philox_uniforms(seed, ids, sweep0 + s, h4, self.na) < self.prob_a_given_v(v)).astype(np.float64)
-            v = (philox_uniforms(seed, ids, sweep0 + s, h4 + a4, self.n) < self.prob_v_given_ha(h, a)).astype(np.float64)
+            a = (philox_uniforms(seed, ids, sweep0 + s, self.nh, self.na) < self.prob_a_given_v(v)).astype(np.float64)
+            v = (philox_uniforms(seed, ids, sweep0 + s, v0, self.n) < self.prob_v_given_ha(h, a)).astype(np.float64)
         return v.reshape(np.shape(initial_state))
 
     def logz_range(self, first=0, count=None, chunk=1 << 16):  # :453-463

@@ -1,0 +1,269 @@
+// extern "C" surface of libqucumber_b200.so (declared in include/qcb.h).
+#include "common.cuh"
+#include <cstring>
+#include <string>
+
+namespace qcb {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return code;
+}
+
+// implemented in the other translation units
+size_t gibbs_workspace_bytes(int N, int nhid);
+int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+              const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st);
+int run_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
+                       const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, cudaStream_t st);
+int run_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                  double* out, cudaStream_t st);
+size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
+int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, double scale, double* g, int accumulate,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+int run_exact_grad_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, double* g, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
+int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double* g_rows, cudaStream_t st);
+size_t enum_workspace_bytes();
+int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int run_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_exact_stats_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, const double* t_re,
+                          const double* t_im, double* out8, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t cwf_workspace_bytes(int N, int nh, int64_t B);
+int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t B,
+                    const uint8_t* basis, const double* unitaries, int K, double* Upsi, double* g_am, double* g_ph,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+size_t dm_workspace_bytes(int N, int nh, int na, int64_t B);
+int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t B,
+                   const uint8_t* basis, const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
+
+static int make_params(StackedParams& p, const double* W, const double* U, const double* b, const double* c,
+                       const double* d, int N, int nh, int na) {
+  if (N < 1 || nh < 1 || na < 0) return fail(QCB_ERR_BAD_ARG, "bad sizes N=%d nh=%d na=%d", N, nh, na);
+  if (W == nullptr || b == nullptr || c == nullptr) return fail(QCB_ERR_BAD_ARG, "W, b, c must not be NULL");
+  if (na > 0 && (U == nullptr || d == nullptr)) return fail(QCB_ERR_BAD_ARG, "na > 0 needs U and d");
+  p.W = W; p.U = U; p.b = b; p.c = c; p.d = d;
+  p.N = N; p.nh = nh; p.na = na;
+  return QCB_OK;
+}
+
+}  // namespace qcb
+
+using namespace qcb;
+
+extern "C" {
+
+int qcb_version(void) { return QCB_VERSION; }
+
+const char* qcb_last_error(void) { return t_last_error.c_str(); }
+
+uint64_t qcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
+  switch (op) {
+    case QCB_OP_GIBBS: return gibbs_workspace_bytes(N, nh + na);
+    case QCB_OP_ENERGY: return 0;
+    case QCB_OP_GRAD_REDUCE: return grad_reduce_workspace_bytes(N, nh + na, rows);
+    case QCB_OP_LOGZ: return enum_workspace_bytes();
+    case QCB_OP_EXACT_STATS: {
+      const size_t a = enum_workspace_bytes(), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      return a > b ? a : b;
+    }
+    case QCB_OP_CWF_ROTATED: return cwf_workspace_bytes(N, nh, rows);
+    case QCB_OP_DM_ROTATED: return dm_workspace_bytes(N, nh, na, rows);
+    case QCB_OP_CDK_NEG: {
+      const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      return a + b;
+    }
+    default: return 0;
+  }
+}
+
+int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                  int na, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                  const double* uniforms, void* ws, size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (C < 0 || k < 0 || (C > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "gibbs: bad C/k/v");
+  return run_gibbs(p, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
+                       const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, void* stream) {
+  if (M == nullptr || x == nullptr || out == nullptr || m_rows < 1 || m_cols < 1 || rows < 0)
+    return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: bad arguments");
+  if ((M2 == nullptr) != (x2 == nullptr)) return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: M2 and x2 go together");
+  return run_linear_sigmoid(M, m_rows, m_cols, transpose_m, bias, x, M2, m2_rows, x2, rows, out, (cudaStream_t)stream);
+}
+
+int qcb_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                  double* out, void* stream) {
+  if (n < 0 || (n > 0 && (p == nullptr || out == nullptr))) return fail(QCB_ERR_BAD_ARG, "bernoulli: bad arguments");
+  return run_bernoulli(p, n, uniforms, seed, chain_id0, sweep0, out, (cudaStream_t)stream);
+}
+
+int qcb_rbm_energy(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                   int na, const double* v, int64_t rows, double* E_out, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (rows < 0 || (rows > 0 && (v == nullptr || E_out == nullptr))) return fail(QCB_ERR_BAD_ARG, "energy: bad rows/v/E_out");
+  return run_energy(p, v, rows, E_out, (cudaStream_t)stream);
+}
+
+int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
+                        int nh, int na, const double* v, int64_t rows, double scale, double* g, int accumulate, void* ws,
+                        size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (rows < 0 || g == nullptr || (rows > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "grad_reduce: bad rows/v/g");
+  return run_grad_reduce(p, v, rows, scale, g, accumulate, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
+                       int nh, int na, const double* v, int64_t rows, double* g_rows, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (rows < 0 || (rows > 0 && (v == nullptr || g_rows == nullptr))) return fail(QCB_ERR_BAD_ARG, "grad_batch: bad rows/v/out");
+  return run_grad_batch(p, v, rows, g_rows, (cudaStream_t)stream);
+}
+
+int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                    int na, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                    const double* uniforms, double scale, double* g, void* ws, size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (C < 0 || k < 0 || g == nullptr || (C > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "cdk_neg: bad arguments");
+  const size_t gb = gibbs_workspace_bytes(N, nh + na);
+  if (ws == nullptr || ws_bytes < gb + grad_reduce_workspace_bytes(N, nh + na, C))
+    return fail(QCB_ERR_BAD_ARG, "cdk_neg: workspace too small");
+  rc = run_gibbs(p, v, C, k, seed, chain_id0, sweep0, uniforms, ws, gb, (cudaStream_t)stream);
+  if (rc != QCB_OK) return rc;
+  return run_grad_reduce(p, v, C, scale, g, 1, static_cast<char*>(ws) + gb, ws_bytes - gb, (cudaStream_t)stream);
+}
+
+int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
+                       int nh, int na, uint64_t first_state, uint64_t count, double* out2, void* ws, size_t ws_bytes,
+                       void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (out2 == nullptr) return fail(QCB_ERR_BAD_ARG, "logz_range: out2 is NULL");
+  return run_logz_range(p, first_state, count, out2, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, void* stream) {
+  if (n < 0 || out2 == nullptr || (n > 0 && E == nullptr)) return fail(QCB_ERR_BAD_ARG, "neg_logsumexp: bad arguments");
+  return run_neg_logsumexp(E, n, out2, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_rbm_exact_stats_range(const double* W, const double* b, const double* c, int N, int nh, uint64_t first_state,
+                              uint64_t count, double logZ, const double* target_re, const double* target_im,
+                              double* out8, double* g_exact, void* ws, size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, nullptr, b, c, nullptr, N, nh, 0);
+  if (rc != QCB_OK) return rc;
+  if (out8 == nullptr) return fail(QCB_ERR_BAD_ARG, "exact_stats: out8 is NULL");
+  rc = run_exact_stats_range(p, first_state, count, logZ, target_re, target_im, out8, ws, ws_bytes, (cudaStream_t)stream);
+  if (rc != QCB_OK || g_exact == nullptr) return rc;
+  return run_exact_grad_range(p, first_state, count, logZ, g_exact, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_cwf_rotated(const double* W_am, const double* b_am, const double* c_am, const double* W_ph, const double* b_ph,
+                    const double* c_ph, int N, int nh, const double* samples, int64_t B, const uint8_t* basis,
+                    const double* unitaries, int K, double* Upsi, double* g_am, double* g_ph, void* ws, size_t ws_bytes,
+                    void* stream) {
+  StackedParams am, ph;
+  int rc = make_params(am, W_am, nullptr, b_am, c_am, nullptr, N, nh, 0);
+  if (rc != QCB_OK) return rc;
+  rc = make_params(ph, W_ph, nullptr, b_ph, c_ph, nullptr, N, nh, 0);
+  if (rc != QCB_OK) return rc;
+  if (B < 0 || basis == nullptr || unitaries == nullptr || K < 1 || (B > 0 && (samples == nullptr || Upsi == nullptr)))
+    return fail(QCB_ERR_BAD_ARG, "cwf_rotated: bad arguments");
+  if ((g_am == nullptr) != (g_ph == nullptr)) return fail(QCB_ERR_BAD_ARG, "cwf_rotated: g_am and g_ph go together");
+  return run_cwf_rotated(am, ph, samples, B, basis, unitaries, K, Upsi, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, const double* c_am, const double* d_am,
+                   const double* W_ph, const double* U_ph, const double* b_ph, const double* c_ph, const double* d_ph,
+                   int N, int nh, int na, const double* samples, int64_t B, const uint8_t* basis, const double* unitaries,
+                   int K, double* UrhoU, double* g_am, double* g_ph, void* ws, size_t ws_bytes, void* stream) {
+  StackedParams am, ph;
+  if (na < 1) return fail(QCB_ERR_BAD_ARG, "dm_rotated: na must be >= 1");
+  int rc = make_params(am, W_am, U_am, b_am, c_am, d_am, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  rc = make_params(ph, W_ph, U_ph, b_ph, c_ph, d_ph, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (B < 0 || basis == nullptr || unitaries == nullptr || K < 1 || (B > 0 && (samples == nullptr || UrhoU == nullptr)))
+    return fail(QCB_ERR_BAD_ARG, "dm_rotated: bad arguments");
+  if ((g_am == nullptr) != (g_ph == nullptr)) return fail(QCB_ERR_BAD_ARG, "dm_rotated: g_am and g_ph go together");
+  return run_dm_rotated(am, ph, samples, B, basis, unitaries, K, UrhoU, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C) {
+  const size_t params = align_up(((size_t)(nh + na) * N + N + nh + na) * sizeof(double), 256);
+  return params + align_up((size_t)C * N * sizeof(double), 256) + gibbs_workspace_bytes(N, nh + na);
+}
+
+int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
+                       const double* d_host, int N, int nh, int na, double* v_host, int64_t C, int k, uint64_t seed,
+                       uint64_t chain_id0, uint64_t sweep0, void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  if (N < 1 || nh < 1 || na < 0 || C < 0 || k < 0) return fail(QCB_ERR_BAD_ARG, "gibbs_host: bad sizes");
+  if (W_host == nullptr || b_host == nullptr || c_host == nullptr || (na > 0 && (U_host == nullptr || d_host == nullptr)) ||
+      (C > 0 && v_host == nullptr))
+    return fail(QCB_ERR_BAD_ARG, "gibbs_host: NULL argument");
+  if (dev_scratch == nullptr || dev_scratch_bytes < qcb_gibbs_host_scratch_bytes(N, nh, na, C))
+    return fail(QCB_ERR_BAD_ARG, "gibbs_host: device scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* dW = static_cast<double*>(dev_scratch);
+  double* dU = dW + (size_t)nh * N;
+  double* db = dU + (size_t)na * N;
+  double* dc = db + N;
+  double* dd = dc + nh;
+  const size_t params = align_up(((size_t)(nh + na) * N + N + nh + na) * sizeof(double), 256);
+  double* dv = reinterpret_cast<double*>(static_cast<char*>(dev_scratch) + params);
+  const size_t vbytes = (size_t)C * N * sizeof(double);
+  void* ws = static_cast<char*>(dev_scratch) + params + align_up(vbytes, 256);
+  QCB_CUDA(cudaMemcpyAsync(dW, W_host, (size_t)nh * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (na > 0) {
+    QCB_CUDA(cudaMemcpyAsync(dU, U_host, (size_t)na * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    QCB_CUDA(cudaMemcpyAsync(dd, d_host, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  QCB_CUDA(cudaMemcpyAsync(db, b_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+  QCB_CUDA(cudaMemcpyAsync(dc, c_host, (size_t)nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (C > 0) QCB_CUDA(cudaMemcpyAsync(dv, v_host, vbytes, cudaMemcpyHostToDevice, st));
+  StackedParams p;
+  int rc = make_params(p, dW, na > 0 ? dU : nullptr, db, dc, na > 0 ? dd : nullptr, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  rc = run_gibbs(p, dv, C, k, seed, chain_id0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
+  if (rc != QCB_OK) return rc;
+  if (C > 0) QCB_CUDA(cudaMemcpyAsync(v_host, dv, vbytes, cudaMemcpyDeviceToHost, st));
+  QCB_CUDA(cudaStreamSynchronize(st));
+  return QCB_OK;
+}
+
+}  // extern "C"

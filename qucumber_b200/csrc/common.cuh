@@ -1,0 +1,138 @@
+// Shared device/host helpers for libqucumber_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include "../../include/qcb.h"
+
+namespace qcb {
+
+// ---- error plumbing (no exception crosses the C ABI) -----------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define QCB_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::qcb::fail(QCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                         __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define QCB_LAUNCH_CHECK()                                                                        \
+  do {                                                                                            \
+    ::qcb::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::qcb::fail(QCB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                        \
+                         cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+  } while (0)
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__host__ __device__ constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ constexpr int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// Stacked "hidden-like" parameter view: rows [0, nh) come from W/c, rows [nh, nh+na) from U/d.
+struct StackedParams {
+  const double* W;
+  const double* U;
+  const double* b;
+  const double* c;
+  const double* d;
+  int N, nh, na;
+  __host__ __device__ int nhid() const { return nh + na; }
+  __device__ __forceinline__ double w(int hid, int vis) const {
+    return hid < nh ? W[(size_t)hid * N + vis] : U[(size_t)(hid - nh) * N + vis];
+  }
+  __device__ __forceinline__ double hbias(int hid) const { return hid < nh ? c[hid] : d[hid - nh]; }
+};
+
+#ifdef __CUDACC__
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double uniform53(uint32_t hi, uint32_t lo) {
+  const uint64_t bits = ((uint64_t)hi << 21) | (uint64_t)(lo >> 11);
+  return (double)bits * 0x1.0p-53;
+}
+
+// torch.sigmoid in float64
+__device__ __forceinline__ double sigmoid_exact(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// F.softplus(beta=1, threshold=20)
+__device__ __forceinline__ double softplus20(double x) { return x > 20.0 ? x : log1p(exp(x)); }
+
+// ---- warp helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared::cta) --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8).  Lane l holds A[l>>2][l&3], B[l&3][l>>2],
+// C[l>>2][2*(l&3) + {0,1}]  (PTX ISA, mma.m8n8k4 .f64 fragment layout).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+#endif  // __CUDACC__
+
+}  // namespace qcb

@@ -1,0 +1,320 @@
+// Exact enumeration over the visible Hilbert space (partition function, fidelity / KL partial sums)
+// for sm_100a.
+//
+// Replaces generate_hilbert_space + partition (nn_states/neural_state.py:156-197,
+// rbm/binary_rbm.py:230-241, rbm/purification_rbm.py:453-463) and the full-space passes of
+// utils/training_statistics.py:27-76,131-183.  The reference materialises a (2^N, N) float64
+// tensor (capped at N = 20) and pushes it through a GEMM; here a basis state is only an index:
+//
+//  * a thread owns an aligned block of 2^m consecutive indices and walks it in Gray-code order,
+//    so consecutive states differ in ONE visible unit and the hidden pre-activations
+//    theta_i = c_i + W_i . v are updated with nh adds per state instead of an N x nh product;
+//  * all threads of a CTA flip the same bit in the same direction at the same step, so the
+//    needed column of W is a shared-memory broadcast;
+//  * -E(v) = b.v + sum_i softplus(theta_i) (torch threshold 20) feeds an online log-sum-exp kept
+//    as (max, sum exp(x - max)); CTAs write partial pairs, a final kernel combines them in a
+//    fixed order.  Index r maps to visible unit j = (r >> (N-1-j)) & 1, the reference's row order.
+#include "common.cuh"
+
+namespace qcb {
+
+constexpr int ENUM_THREADS = 128;
+
+struct EnumArgs {
+  StackedParams p;
+  uint64_t first, count;
+  int m;                 // log2 of states per thread
+  uint64_t nblocks;      // aligned 2^m blocks covering [first, first + count)
+  uint64_t block0;       // index of the first aligned block
+  double logZ;           // stats kernel only
+  const double* t_re;
+  const double* t_im;
+};
+
+struct LSE {
+  double m, s;
+};
+__device__ __forceinline__ void lse_add(LSE& a, double x) {
+  if (x > a.m) {
+    a.s = a.s * exp(a.m - x) + 1.0;  // exp(-inf) = 0 handles the first element
+    a.m = x;
+  } else {
+    a.s += exp(x - a.m);
+  }
+}
+__device__ __forceinline__ LSE lse_merge(LSE a, LSE b) {
+  if (b.m == -INFINITY) return a;
+  if (a.m == -INFINITY) return b;
+  LSE r;
+  r.m = fmax(a.m, b.m);
+  r.s = a.s * exp(a.m - r.m) + b.s * exp(b.m - r.m);
+  return r;
+}
+
+// Shared-memory staging: Wt[j][i] (visible-major, NHT stride), hb[NHT], vb[N]
+template <int NHT>
+__device__ __forceinline__ void stage_enum(const StackedParams& p, double* Wt, double* hb, double* vb) {
+  const int H = p.nhid();
+  for (int idx = threadIdx.x; idx < p.N * NHT; idx += blockDim.x) {
+    const int j = idx / NHT, i = idx - j * NHT;
+    Wt[idx] = i < H ? p.w(i, j) : 0.0;
+  }
+  for (int i = threadIdx.x; i < NHT; i += blockDim.x) hb[i] = i < H ? p.hbias(i) : 0.0;
+  for (int j = threadIdx.x; j < p.N; j += blockDim.x) vb[j] = p.b[j];
+}
+
+// MODE 0: log-sum-exp partials.  MODE 1: statistics partials (5 sums) given logZ.
+template <int NHT, int MODE>
+__global__ void __launch_bounds__(ENUM_THREADS) enum_kernel(const EnumArgs a, double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Wt = reinterpret_cast<double*>(smem_raw);
+  double* hb = Wt + (size_t)a.p.N * NHT;
+  double* vb = hb + NHT;
+  double* red = vb + round_up(a.p.N, 2);  // reduction scratch: 8 doubles per warp
+  stage_enum<NHT>(a.p, Wt, hb, vb);
+  __syncthreads();
+
+  const int N = a.p.N, H = a.p.nhid();
+  const uint64_t last = a.first + a.count;  // exclusive
+  const uint32_t steps = 1u << a.m;
+
+  LSE acc{-INFINITY, 0.0};
+  double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const double eps = 0x1.0p-52;
+
+  for (uint64_t blk = (uint64_t)blockIdx.x * ENUM_THREADS + threadIdx.x; blk < a.nblocks;
+       blk += (uint64_t)gridDim.x * ENUM_THREADS) {
+    const uint64_t base = (a.block0 + blk) << a.m;
+    // theta for the block's first state (gray(0) = 0 -> index = base)
+    double th[NHT];
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) th[i] = hb[i];
+    double bv = 0.0;
+    for (int j = 0; j < N; ++j) {
+      if ((base >> (N - 1 - j)) & 1ull) {
+        const double* col = Wt + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) th[i] += col[i];
+        bv += vb[j];
+      }
+    }
+    for (uint32_t k = 0; k < steps; ++k) {
+      const uint32_t gk = k ^ (k >> 1);
+      const uint64_t idx = base | gk;
+      double x = bv;
+#pragma unroll
+      for (int i = 0; i < NHT; ++i)
+        if (i < H) x += softplus20(th[i]);
+      if (idx >= a.first && idx < last) {
+        if (MODE == 0) {
+          lse_add(acc, x);
+        } else {
+          const double lp = x - a.logZ;
+          const double p = exp(lp);
+          sums[4] += p;
+          if (a.t_re != nullptr) {
+            const double tr = a.t_re[idx - a.first];
+            const double ti = a.t_im != nullptr ? a.t_im[idx - a.first] : 0.0;
+            const double psi = exp(0.5 * lp);
+            sums[0] = fma(tr, psi, sums[0]);
+            sums[1] = fma(ti, psi, sums[1]);
+            const double pt = tr * tr + ti * ti;
+            sums[2] = fma(pt, log(fmin(fmax(pt, eps), 1.0 - eps)), sums[2]);
+            sums[3] = fma(pt, log(fmin(fmax(p, eps), 1.0 - eps)), sums[3]);
+          }
+        }
+      }
+      if (k + 1 < steps) {
+        const uint32_t k1 = k + 1;
+        const int pbit = __ffs(k1) - 1;
+        const uint32_t g1 = k1 ^ (k1 >> 1);
+        const double sgn = ((g1 >> pbit) & 1u) ? 1.0 : -1.0;
+        const int j = N - 1 - pbit;
+        const double* col = Wt + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) th[i] = fma(sgn, col[i], th[i]);
+        bv = fma(sgn, vb[j], bv);
+      }
+    }
+  }
+
+  // CTA reduction -> partials[blockIdx]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (MODE == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      LSE other;
+      other.m = __shfl_xor_sync(0xffffffffu, acc.m, o);
+      other.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+      acc = lse_merge(acc, other);
+    }
+    if (lane == 0) { red[2 * warp] = acc.m; red[2 * warp + 1] = acc.s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      LSE t{red[0], red[1]};
+      for (int w = 1; w < ENUM_THREADS / 32; ++w) t = lse_merge(t, LSE{red[2 * w], red[2 * w + 1]});
+      partials[2 * blockIdx.x] = t.m;
+      partials[2 * blockIdx.x + 1] = t.s;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) sums[q] = warp_sum(sums[q]);
+    if (lane == 0)
+      for (int q = 0; q < 5; ++q) red[8 * warp + q] = sums[q];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      double t = 0.0;
+      for (int w = 0; w < ENUM_THREADS / 32; ++w) t += red[8 * w + threadIdx.x];
+      partials[8 * blockIdx.x + threadIdx.x] = t;
+    }
+  }
+}
+
+__global__ void lse_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  LSE t{-INFINITY, 0.0};
+  for (int i = 0; i < n; ++i) t = lse_merge(t, LSE{partials[2 * i], partials[2 * i + 1]});
+  out2[0] = t.m;
+  out2[1] = t.s;
+}
+
+__global__ void sums_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out8) {
+  const int q = threadIdx.x;
+  if (q >= 8) return;
+  double t = 0.0;
+  if (q < 5)
+    for (int i = 0; i < n; ++i) t += partials[8 * i + q];
+  out8[q] = t;
+}
+
+__global__ void __launch_bounds__(256) neg_lse_kernel(const double* __restrict__ E, int64_t n, double* __restrict__ partials) {
+  __shared__ double red[16];
+  LSE acc{-INFINITY, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) lse_add(acc, -E[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    LSE other;
+    other.m = __shfl_xor_sync(0xffffffffu, acc.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+    acc = lse_merge(acc, other);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[2 * warp] = acc.m; red[2 * warp + 1] = acc.s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LSE t{red[0], red[1]};
+    for (int w = 1; w < 8; ++w) t = lse_merge(t, LSE{red[2 * w], red[2 * w + 1]});
+    partials[2 * blockIdx.x] = t.m;
+    partials[2 * blockIdx.x + 1] = t.s;
+  }
+}
+
+static int pick_nht(int H) {
+  if (H <= 8) return 8;
+  if (H <= 16) return 16;
+  if (H <= 32) return 32;
+  if (H <= 64) return 64;
+  return 0;
+}
+
+static int enum_max_grid() { return sm_count() * 8; }
+
+size_t enum_workspace_bytes() { return align_up((size_t)enum_max_grid() * 8 * sizeof(double), 256); }
+
+template <int NHT, int MODE>
+static int launch_enum(const EnumArgs& a, double* partials, int* grid_out, cudaStream_t st) {
+  const size_t smem = ((size_t)a.p.N * NHT + NHT + round_up(a.p.N, 2) + 8 * (ENUM_THREADS / 32)) * sizeof(double);
+  if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "enumeration: parameters do not fit in shared memory");
+  QCB_CUDA(cudaFuncSetAttribute(enum_kernel<NHT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const uint64_t need = (a.nblocks + ENUM_THREADS - 1) / ENUM_THREADS;
+  const uint64_t cap = (uint64_t)enum_max_grid();
+  const int grid = (int)(need < cap ? need : cap);
+  enum_kernel<NHT, MODE><<<grid, ENUM_THREADS, smem, st>>>(a, partials);
+  QCB_LAUNCH_CHECK();
+  *grid_out = grid;
+  return QCB_OK;
+}
+
+static int setup_enum(const StackedParams& p, uint64_t first, uint64_t count, EnumArgs& a) {
+  if (p.N < 1 || p.N > 62) return fail(QCB_ERR_UNSUPPORTED, "enumeration: N=%d outside [1, 62]", p.N);
+  const uint64_t total = 1ull << p.N;
+  if (first > total || count > total - first) return fail(QCB_ERR_BAD_ARG, "enumeration: range exceeds 2^N states");
+  if (pick_nht(p.nhid()) == 0) return fail(QCB_ERR_UNSUPPORTED, "enumeration: nh + na = %d > 64", p.nhid());
+  a.p = p;
+  a.first = first;
+  a.count = count;
+  // states per thread: enough threads to fill the GPU (>= ~150k threads) but long Gray walks when possible
+  int m = 0;
+  const uint64_t want_threads = (uint64_t)sm_count() * 1024;
+  while (m < 12 && m < p.N && (count >> (m + 1)) >= want_threads) ++m;
+  if (m < 2 && p.N >= 2) m = 2;
+  if (m > p.N) m = p.N;
+  a.m = m;
+  a.block0 = first >> m;
+  a.nblocks = count == 0 ? 0 : (((first + count - 1) >> m) - a.block0 + 1);
+  a.logZ = 0.0;
+  a.t_re = a.t_im = nullptr;
+  return QCB_OK;
+}
+
+#define QCB_ENUM_DISPATCH(MODE, a, partials, gridp, st)                        \
+  switch (pick_nht((a).p.nhid())) {                                            \
+    case 8: rc = launch_enum<8, MODE>(a, partials, gridp, st); break;          \
+    case 16: rc = launch_enum<16, MODE>(a, partials, gridp, st); break;        \
+    case 32: rc = launch_enum<32, MODE>(a, partials, gridp, st); break;        \
+    default: rc = launch_enum<64, MODE>(a, partials, gridp, st); break;        \
+  }
+
+int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  EnumArgs a;
+  int rc = setup_enum(p, first, count, a);
+  if (rc != QCB_OK) return rc;
+  if (ws == nullptr || ws_bytes < enum_workspace_bytes()) return fail(QCB_ERR_BAD_ARG, "logz_range: workspace too small");
+  double* partials = reinterpret_cast<double*>(ws);
+  int grid = 0;
+  if (count > 0) {
+    QCB_ENUM_DISPATCH(0, a, partials, &grid, st)
+    if (rc != QCB_OK) return rc;
+  }
+  lse_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out2);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (ws == nullptr || ws_bytes < enum_workspace_bytes()) return fail(QCB_ERR_BAD_ARG, "neg_logsumexp: workspace too small");
+  double* partials = reinterpret_cast<double*>(ws);
+  int grid = 0;
+  if (n > 0) {
+    const int64_t need = (n + 255) / 256;
+    grid = (int)(need < enum_max_grid() ? need : enum_max_grid());
+    neg_lse_kernel<<<grid, 256, 0, st>>>(E, n, partials);
+    QCB_LAUNCH_CHECK();
+  }
+  lse_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out2);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_exact_stats_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, const double* t_re,
+                          const double* t_im, double* out8, void* ws, size_t ws_bytes, cudaStream_t st) {
+  EnumArgs a;
+  int rc = setup_enum(p, first, count, a);
+  if (rc != QCB_OK) return rc;
+  if (ws == nullptr || ws_bytes < enum_workspace_bytes()) return fail(QCB_ERR_BAD_ARG, "exact_stats: workspace too small");
+  a.logZ = logZ;
+  a.t_re = t_re;
+  a.t_im = t_im;
+  double* partials = reinterpret_cast<double*>(ws);
+  int grid = 0;
+  if (count > 0) {
+    QCB_ENUM_DISPATCH(1, a, partials, &grid, st)
+    if (rc != QCB_OK) return rc;
+  }
+  sums_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out8);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+}  // namespace qcb

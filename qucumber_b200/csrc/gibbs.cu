@@ -1,0 +1,357 @@
+// Fused k-sweep block Gibbs sampler for BinaryRBM / PurificationRBM on sm_100a.
+//
+// Replaces the reference's per-sweep chain of torch ops (rbm/binary_rbm.py:129-228,
+// rbm/purification_rbm.py:196-337: matmul, add_, sigmoid_, clamp_, bernoulli — 10 to 17 launches
+// and two HBM round trips of the chain state per sweep) with ONE launch for all k sweeps:
+//
+//  * a warp owns 8 chains; their visible/hidden states live in registers as bit masks for the
+//    whole call (HBM is touched once to read v0 and once to write v_k);
+//  * the pre-activations x = W v + c and x' = W^T h + b are FP64 tensor-core tiles
+//    (mma.sync m8n8k4 f64, "DMMA"): A = the 8 chains' state bits as 0.0/1.0, B = W fragments
+//    read from shared memory, accumulators start at the bias;
+//  * W lives in shared memory for the whole call in *fragment order* (one conflict-free
+//    LDS.128 per lane feeds two DMMAs).  A tiny pack kernel writes that image once per call into
+//    the caller's workspace; every CTA pulls it with one 1-D TMA bulk copy (cp.async.bulk +
+//    mbarrier complete_tx);
+//  * uniforms are Philox4x32-10 draws made in-kernel (convention in include/qcb.h), or fed by
+//    the caller for bit-exact replay of the reference;
+//  * the Bernoulli decision u < sigmoid(x) is made with an exactness-preserving filter: a float
+//    sigmoid and the top 23 bits of u decide whenever |u - p| > 2^-16; the rare remaining cases
+//    (probability ~3e-5) take the exact FP64 path.  Decisions are identical to evaluating
+//    u < 1/(1+exp(-x)) in FP64 for every unit.
+//
+// The PurificationRBM is the same kernel on the stacked matrix [W; U] with biases [c; d]
+// (h | v and a | v are both "hidden-like"; v | h,a sums both contributions).
+#include "common.cuh"
+
+namespace qcb {
+
+constexpr int GIBBS_THREADS = 256;
+constexpr int GIBBS_WARPS = GIBBS_THREADS / 32;
+constexpr int CHAINS_PER_WARP = 8;
+
+struct GibbsArgs {
+  const double* image;   // packed fragment image in global memory (workspace)
+  uint32_t image_bytes;
+  double* v;             // (C, N) in/out
+  const double* uniforms;  // NULL or (k, C, nhid + N)
+  int64_t C;
+  int N, nhid;
+  int k;
+  uint32_t key0, key1;
+  uint64_t chain_id0;
+  uint32_t sweep0;
+  int64_t num_groups;
+};
+
+// ---- pack kernel: builds the fragment-ordered shared-memory image ------------------------------
+// Layout (doubles): Ih[4*VB][HB][32][2] | Iv[4*HB][VB][32][2] | biasH[16*HB] | biasV[16*VB]
+// Ih feeds h|v: element (kk, gq, lane=(g,t), s) = Wst[hid = 16gq + 4(g/2) + 2s + (g%2)][vis = 4kk + t]
+// Iv feeds v|h: element (kk, gq, lane, s)       = Wst[hid = 4kk + t][vis = 16gq + 4(g/2) + 2s + (g%2)]
+// With this column permutation lane (g,t) ends up owning output units 16gq + 4t + {0,1,2,3} of
+// chain g, i.e. exactly the four words of one Philox call.
+__global__ void gibbs_pack_kernel(StackedParams p, int HB, int VB, double* __restrict__ img) {
+  const int Hpad = 16 * HB, Npad = 16 * VB;
+  const int nIh = Npad * Hpad;
+  const int total = 2 * nIh + Hpad + Npad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    double val = 0.0;
+    if (idx < 2 * nIh) {
+      const bool hside = idx < nIh;
+      const int r = hside ? idx : idx - nIh;
+      const int OB = hside ? HB : VB;
+      const int s = r & 1;
+      const int lane = (r >> 1) & 31;
+      const int gq = (r >> 6) % OB;
+      const int kk = (r >> 6) / OB;
+      const int g = lane >> 2, t = lane & 3;
+      const int outu = 16 * gq + 4 * (g >> 1) + 2 * s + (g & 1);
+      const int inu = 4 * kk + t;
+      const int hid = hside ? outu : inu;
+      const int vis = hside ? inu : outu;
+      if (hid < p.nhid() && vis < p.N) val = p.w(hid, vis);
+    } else if (idx < 2 * nIh + Hpad) {
+      const int hid = idx - 2 * nIh;
+      if (hid < p.nhid()) val = p.hbias(hid);
+    } else {
+      const int vis = idx - 2 * nIh - Hpad;
+      if (vis < p.N) val = p.b[vis];
+    }
+    img[idx] = val;
+  }
+}
+
+// ---- Bernoulli decisions for the four units of one Philox call ----------------------------------
+// Returns a 4-bit mask, bit w set iff u_w < sigmoid(x_w) evaluated exactly in FP64.
+struct RngCtx {
+  uint32_t c0, c1;   // chain id
+  uint32_t key0, key1;
+};
+
+constexpr float FILTER_EPS = 0x1.0p-16f;
+
+__device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const RngCtx& rc, uint32_t sweep, uint32_t q,
+                                                   uint32_t valid) {
+  uint32_t r[4];
+  philox4x32_10(rc.c0, rc.c1, sweep, q, rc.key0, rc.key1, r);
+  uint32_t nib = 0, slow = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float xf = (float)x[w];
+    const float p = __fdividef(1.0f, 1.0f + __expf(-xf));
+    const float uf = __uint_as_float(0x3F800000u | (r[w] >> 9)) - 1.0f;  // u in [uf, uf + 2^-23)
+    if (uf + FILTER_EPS <= p) nib |= 1u << w;
+    else if (!(uf >= p + FILTER_EPS)) slow |= 1u << w;
+  }
+  slow &= valid;
+  if (slow) {
+    uint32_t lo[4];
+    philox4x32_10(rc.c0, rc.c1, sweep, q | 0x80000000u, rc.key0, rc.key1, lo);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (slow & (1u << w)) {
+        const double u = uniform53(r[w], lo[w]);
+        if (u < sigmoid_exact(x[w])) nib |= 1u << w; else nib &= ~(1u << w);
+      }
+    }
+  }
+  return nib & valid;
+}
+
+__device__ __forceinline__ uint32_t decide4_fed(const double (&x)[4], const double* __restrict__ u, uint32_t valid) {
+  uint32_t nib = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if (valid & (1u << w)) {
+      if (u[w] < sigmoid_exact(x[w])) nib |= 1u << w;
+    }
+  }
+  return nib;
+}
+
+// ---- one conditional update (all output units of 8 chains) --------------------------------------
+// KB_IN / OB: number of 16-unit blocks on the input / output side.
+template <int KB_IN, int OB>
+__device__ __forceinline__ void half_sweep(const uint32_t (&min)[(KB_IN + 1) / 2], uint32_t (&mout)[(OB + 1) / 2],
+                                           const double2* __restrict__ img, const double* __restrict__ bias,
+                                           int n_out_real, const RngCtx& rc, uint32_t sweep, uint32_t q0,
+                                           const double* __restrict__ fed /* this chain's block or NULL */,
+                                           int lane) {
+  const int t = lane & 3;
+  double acc[2 * OB][2];
+#pragma unroll
+  for (int gq = 0; gq < OB; ++gq) {
+    const double2 b01 = *reinterpret_cast<const double2*>(bias + 16 * gq + 4 * t);
+    const double2 b23 = *reinterpret_cast<const double2*>(bias + 16 * gq + 4 * t + 2);
+    acc[2 * gq][0] = b01.x; acc[2 * gq][1] = b01.y;
+    acc[2 * gq + 1][0] = b23.x; acc[2 * gq + 1][1] = b23.y;
+  }
+  uint32_t mt[(KB_IN + 1) / 2];
+#pragma unroll
+  for (int w = 0; w < (KB_IN + 1) / 2; ++w) mt[w] = min[w] >> t;
+
+  constexpr int KK = 4 * KB_IN;
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+    const uint32_t bit = (mt[kk / 8] >> (4 * (kk % 8))) & 1u;
+    const double a = __hiloint2double((int)(bit * 0x3FF00000u), 0);
+    const double2* row = img + (size_t)kk * OB * 32 + lane;
+#pragma unroll
+    for (int gq = 0; gq < OB; ++gq) {
+      const double2 bf = row[gq * 32];
+      dmma884(acc[2 * gq][0], acc[2 * gq][1], a, bf.x);
+      dmma884(acc[2 * gq + 1][0], acc[2 * gq + 1][1], a, bf.y);
+    }
+  }
+
+#pragma unroll
+  for (int w = 0; w < (OB + 1) / 2; ++w) mout[w] = 0u;
+#pragma unroll
+  for (int gq = 0; gq < OB; ++gq) {
+    const int unit0 = 16 * gq + 4 * t;
+    const int nvalid = n_out_real - unit0;
+    if (nvalid > 0) {
+      const uint32_t valid = nvalid >= 4 ? 0xFu : ((1u << nvalid) - 1u);
+      const double x[4] = {acc[2 * gq][0], acc[2 * gq][1], acc[2 * gq + 1][0], acc[2 * gq + 1][1]};
+      uint32_t nib;
+      if (fed != nullptr) {
+        double u[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) u[w] = (valid & (1u << w)) ? fed[unit0 + w] : 2.0;
+        nib = decide4_fed(x, u, valid);
+      } else {
+        nib = decide4_philox(x, rc, sweep, q0 + 4 * gq + t, valid);
+      }
+      mout[gq / 2] |= nib << (16 * (gq % 2) + 4 * t);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < (OB + 1) / 2; ++w) {
+    mout[w] |= __shfl_xor_sync(0xffffffffu, mout[w], 1);
+    mout[w] |= __shfl_xor_sync(0xffffffffu, mout[w], 2);
+  }
+}
+
+template <int HB, int VB>
+__global__ void __launch_bounds__(GIBBS_THREADS) gibbs_kernel(const GibbsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  constexpr int Hpad = 16 * HB, Npad = 16 * VB;
+  constexpr int nI = Hpad * Npad;
+  const double2* Ih = reinterpret_cast<const double2*>(smem);
+  const double2* Iv = reinterpret_cast<const double2*>(smem + nI);
+  const double* biasH = smem + 2 * nI;
+  const double* biasV = biasH + Hpad;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * nI + Hpad + Npad);
+
+  // Stage the packed parameters with one TMA bulk copy per <=32 KB chunk.
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(mbar, a.image_bytes);
+    const char* src = reinterpret_cast<const char*>(a.image);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (uint32_t off = 0; off < a.image_bytes; off += 32768u) {
+      const uint32_t n = a.image_bytes - off < 32768u ? a.image_bytes - off : 32768u;
+      tma_bulk_g2s(dst + off, src + off, n, mbar);
+    }
+  }
+  mbar_wait(mbar, 0);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2;
+  constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
+  const int nunits = a.nhid + a.N;
+  const uint32_t qv0 = (uint32_t)(round_up(a.nhid, 4) / 4);
+
+  for (int64_t gi = (int64_t)blockIdx.x * GIBBS_WARPS + warp; gi < a.num_groups; gi += (int64_t)gridDim.x * GIBBS_WARPS) {
+    const int64_t chain_base = gi * CHAINS_PER_WARP;
+    const int64_t my_chain = chain_base + g;
+    const bool my_valid = my_chain < a.C;
+
+    // v0 -> bit masks (coalesced row reads + ballot)
+    uint32_t mv[MV], mh[MH];
+#pragma unroll
+    for (int w = 0; w < MV; ++w) mv[w] = 0u;
+#pragma unroll
+    for (int cc = 0; cc < CHAINS_PER_WARP; ++cc) {
+      const int64_t ch = chain_base + cc;
+#pragma unroll
+      for (int w = 0; w < MV; ++w) {
+        const int j = w * 32 + lane;
+        double val = 0.0;
+        if (ch < a.C && j < a.N) val = a.v[ch * a.N + j];
+        const uint32_t bal = __ballot_sync(0xffffffffu, val != 0.0);
+        if (g == cc) mv[w] = bal;
+      }
+    }
+
+    RngCtx rc;
+    const uint64_t cid = a.chain_id0 + (uint64_t)my_chain;
+    rc.c0 = (uint32_t)cid; rc.c1 = (uint32_t)(cid >> 32);
+    rc.key0 = a.key0; rc.key1 = a.key1;
+
+    for (int s = 0; s < a.k; ++s) {
+      const double* fed_h = nullptr;
+      const double* fed_v = nullptr;
+      if (a.uniforms != nullptr) {
+        const int64_t ch = my_valid ? my_chain : 0;
+        fed_h = a.uniforms + ((int64_t)s * a.C + ch) * nunits;
+        fed_v = fed_h + a.nhid;
+      }
+      const uint32_t sweep = a.sweep0 + (uint32_t)s;
+      half_sweep<VB, HB>(mv, mh, Ih, biasH, a.nhid, rc, sweep, 0u, fed_h, lane);
+      half_sweep<HB, VB>(mh, mv, Iv, biasV, a.N, rc, sweep, qv0, fed_v, lane);
+    }
+
+    // bit masks -> v_k (coalesced row writes)
+#pragma unroll
+    for (int cc = 0; cc < CHAINS_PER_WARP; ++cc) {
+      const int64_t ch = chain_base + cc;
+#pragma unroll
+      for (int w = 0; w < MV; ++w) {
+        const uint32_t word = __shfl_sync(0xffffffffu, mv[w], cc * 4);
+        const int j = w * 32 + lane;
+        if (ch < a.C && j < a.N) a.v[ch * a.N + j] = ((word >> lane) & 1u) ? 1.0 : 0.0;
+      }
+    }
+  }
+}
+
+static size_t gibbs_image_doubles(int HB, int VB) { return (size_t)2 * 256 * HB * VB + 16 * HB + 16 * VB; }
+
+static int pick_blocks(int units) {
+  if (units <= 16) return 1;
+  if (units <= 32) return 2;
+  if (units <= 64) return 4;
+  if (units <= 128) return 8;
+  return 0;
+}
+
+size_t gibbs_workspace_bytes(int N, int nhid) {
+  const int HB = pick_blocks(nhid), VB = pick_blocks(N);
+  if (HB == 0 || VB == 0) return 0;
+  return align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256);
+}
+
+template <int HB, int VB>
+static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
+  const size_t smem = gibbs_image_doubles(HB, VB) * sizeof(double) + 16;
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  if (!configured) {
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_kernel<HB, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_kernel<HB, VB>, GIBBS_THREADS, smem));
+    if (blocks_per_sm < 1) return fail(QCB_ERR_CUDA, "gibbs kernel does not fit on an SM (smem %zu B)", smem);
+    configured = true;
+  }
+  const int64_t need = (a.num_groups + GIBBS_WARPS - 1) / GIBBS_WARPS;
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  const int grid = (int)(need < cap ? need : cap);
+  gibbs_kernel<HB, VB><<<grid, GIBBS_THREADS, smem, st>>>(a);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+              const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int nhid = p.nhid();
+  const int HB = pick_blocks(nhid), VB = pick_blocks(p.N);
+  if (HB == 0 || VB == 0 || (HB == 8 && VB == 8))
+    return fail(QCB_ERR_UNSUPPORTED, "gibbs: N=%d, nh+na=%d exceeds the shared-memory resident limit (<=128 each, not both >64)",
+                p.N, nhid);
+  const size_t need = gibbs_workspace_bytes(p.N, nhid);
+  if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, need);
+  if (C == 0 || k == 0) return QCB_OK;
+
+  double* img = reinterpret_cast<double*>(ws);
+  const int total = (int)gibbs_image_doubles(HB, VB);
+  gibbs_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(p, HB, VB, img);
+  QCB_LAUNCH_CHECK();
+
+  GibbsArgs a;
+  a.image = img;
+  a.image_bytes = (uint32_t)(total * sizeof(double));
+  a.v = v;
+  a.uniforms = uniforms;
+  a.C = C;
+  a.N = p.N;
+  a.nhid = nhid;
+  a.k = k;
+  a.key0 = (uint32_t)seed;
+  a.key1 = (uint32_t)(seed >> 32);
+  a.chain_id0 = chain_id0;
+  a.sweep0 = (uint32_t)sweep0;
+  a.num_groups = (C + CHAINS_PER_WARP - 1) / CHAINS_PER_WARP;
+
+#define QCB_GIBBS_CASE(H, V) \
+  if (HB == H && VB == V) return launch_gibbs<H, V>(a, st);
+  QCB_GIBBS_CASE(1, 1) QCB_GIBBS_CASE(1, 2) QCB_GIBBS_CASE(1, 4) QCB_GIBBS_CASE(1, 8)
+  QCB_GIBBS_CASE(2, 1) QCB_GIBBS_CASE(2, 2) QCB_GIBBS_CASE(2, 4) QCB_GIBBS_CASE(2, 8)
+  QCB_GIBBS_CASE(4, 1) QCB_GIBBS_CASE(4, 2) QCB_GIBBS_CASE(4, 4) QCB_GIBBS_CASE(4, 8)
+  QCB_GIBBS_CASE(8, 1) QCB_GIBBS_CASE(8, 2) QCB_GIBBS_CASE(8, 4)
+#undef QCB_GIBBS_CASE
+  return fail(QCB_ERR_UNSUPPORTED, "gibbs: no kernel for blocks (%d, %d)", HB, VB);
+}
+
+}  // namespace qcb

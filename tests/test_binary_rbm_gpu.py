@@ -1,0 +1,178 @@
+"""GPU parity of the CUDA BinaryRBM against the CPU oracle (same seeded inputs).
+
+Mirrors the reference's tests/test_models_misc.py (aliasing, 1-D inputs, seed replay) and the
+property style of tests/test_grads.py, with the tolerance the north star states: 1e-10 relative
+for energies/gradients/normalisations, bit-exact samples under fed uniforms."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, load_binary, make_binary_params, random_states
+from oracle.rbm_oracle import BinaryRBMOracle
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(10, 10), (64, 64), (4, 9), (20, 17), (33, 70), (100, 40), (1, 1)]
+
+
+def _pair(n, nh, seed, cuda):
+    from qucumber_b200 import BinaryRBM
+
+    W, b, c = make_binary_params(n, nh, seed)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    assert rbm.weights.is_cuda
+    return rbm, BinaryRBMOracle(W, b, c)
+
+
+@pytest.mark.parametrize("n,nh", SHAPES)
+def test_effective_energy(lib, cuda, n, nh):
+    rbm, orc = _pair(n, nh, 1, cuda)
+    v = random_states(257, n, 2)
+    assert_close(rbm.effective_energy(torch.tensor(v, device=cuda)), orc.effective_energy(v), what="energy")
+    # 1-D in -> 0-D out, arbitrary leading dims, real-valued input
+    assert rbm.effective_energy(torch.tensor(v[0], device=cuda)).dim() == 0
+    v3 = np.random.default_rng(3).standard_normal((3, 5, n))
+    assert_close(rbm.effective_energy(torch.tensor(v3, device=cuda)), orc.effective_energy(v3), what="energy 3-D real")
+
+
+def test_softplus_threshold(lib, cuda):
+    """F.softplus switches to the identity above 20 (a -2e-9 jump the energies must reproduce)."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh = 6, 5
+    W, b, c = make_binary_params(n, nh, 5)
+    c = c + np.array([19.9999, 20.0001, 25.0, 0.0, -30.0])
+    W = W * 1e-3
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    v = random_states(64, n, 6)
+    assert_close(rbm.effective_energy(torch.tensor(v, device=cuda)), BinaryRBMOracle(W, b, c).effective_energy(v), rtol=1e-13,
+                 what="energy near threshold")
+
+
+@pytest.mark.parametrize("n,nh", SHAPES)
+def test_conditionals(lib, cuda, n, nh):
+    rbm, orc = _pair(n, nh, 7, cuda)
+    v = random_states(100, n, 8)
+    h = random_states(100, nh, 9)
+    assert_close(rbm.prob_h_given_v(torch.tensor(v, device=cuda)), orc.prob_h_given_v(v), what="prob_h_given_v")
+    assert_close(rbm.prob_v_given_h(torch.tensor(h, device=cuda)), orc.prob_v_given_h(h), what="prob_v_given_h")
+    out = torch.zeros(100, nh, dtype=torch.double, device=cuda)
+    res = rbm.prob_h_given_v(torch.tensor(v, device=cuda), out=out)
+    assert res.data_ptr() == out.data_ptr()
+    assert rbm.prob_h_given_v(torch.tensor(v[0], device=cuda)).shape == (nh,)
+
+
+@pytest.mark.parametrize("n,nh", SHAPES)
+@pytest.mark.parametrize("rows", [1, 100, 1000])
+def test_gradient_reduce(lib, cuda, n, nh, rows):
+    rbm, orc = _pair(n, nh, 11, cuda)
+    v = random_states(rows, n, 12)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), orc.effective_energy_gradient(v),
+                 what="reduced gradient")
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (4, 9), (20, 17)])
+def test_gradient_batch(lib, cuda, n, nh):
+    rbm, orc = _pair(n, nh, 13, cuda)
+    v = random_states(37, n, 14)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda), reduce=False),
+                 orc.effective_energy_gradient(v, reduce=False), what="batch gradient")
+    v3 = random_states(24, n, 15).reshape(4, 6, n)
+    got = rbm.effective_energy_gradient(torch.tensor(v3, device=cuda), reduce=False)
+    assert got.shape == (4, 6, rbm.num_pars)
+    assert_close(got, orc.effective_energy_gradient(v3, reduce=False), what="batch gradient 3-D")
+    g1 = rbm.effective_energy_gradient(torch.tensor(v[0], device=cuda), reduce=False)
+    assert g1.shape == (1, rbm.num_pars)
+
+
+@pytest.mark.parametrize("n,nh", SHAPES)
+@pytest.mark.parametrize("chains,k", [(1, 1), (200, 10), (1000, 3)])
+def test_gibbs_fed_uniforms_bit_exact(lib, cuda, n, nh, chains, k):
+    rbm, orc = _pair(n, nh, 21, cuda)
+    v0 = random_states(chains, n, 22)
+    u = np.random.default_rng(23).random((k, chains, nh + n))
+    got = rbm.gibbs_steps(k, torch.tensor(v0, device=cuda), uniforms=torch.tensor(u, device=cuda))
+    want = orc.gibbs_steps_fed(k, v0, u)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n,nh", SHAPES)
+def test_gibbs_philox_bit_exact(lib, cuda, n, nh):
+    """With its own Philox draws the kernel reproduces the oracle's restatement of the same stream,
+    including chain-id / sweep offsets (what makes sharded runs identical to unsharded ones)."""
+    rbm, orc = _pair(n, nh, 31, cuda)
+    v0 = random_states(333, n, 32)
+    got = rbm.gibbs_steps(4, torch.tensor(v0, device=cuda), seed=0xDEADBEEFCAFE, chain_id0=5, sweep0=7)
+    want = orc.gibbs_steps_philox(4, v0, seed=0xDEADBEEFCAFE, chain_id0=5, sweep0=7)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # split in two calls and in two shards == one call
+    a = rbm.gibbs_steps(3, torch.tensor(v0, device=cuda), seed=99, sweep0=0)
+    a = rbm.gibbs_steps(2, a, seed=99, sweep0=3)
+    b = rbm.gibbs_steps(5, torch.tensor(v0, device=cuda), seed=99)
+    assert torch.equal(a, b)
+    lo = rbm.gibbs_steps(5, torch.tensor(v0[:100], device=cuda), seed=99)
+    hi = rbm.gibbs_steps(5, torch.tensor(v0[100:], device=cuda), seed=99, chain_id0=100)
+    assert torch.equal(torch.cat([lo, hi]), b)
+
+
+def test_gibbs_api_contract(lib, cuda):
+    """overwrite aliasing, 1-D input, seed replay (reference tests/test_models_misc.py:44-76,237-258)."""
+    rbm, _ = _pair(10, 10, 41, cuda)
+    v0 = torch.tensor(random_states(50, 10, 42), device=cuda)
+    keep = v0.clone()
+    out = rbm.gibbs_steps(5, v0, overwrite=False)
+    assert torch.equal(v0, keep) and out.data_ptr() != v0.data_ptr()
+    out = rbm.gibbs_steps(5, v0, overwrite=True)
+    assert out.data_ptr() == v0.data_ptr()
+    one = rbm.gibbs_steps(3, keep[0])
+    assert one.shape == (10,)
+    torch.manual_seed(1234)
+    a = rbm.gibbs_steps(10, keep)
+    torch.manual_seed(1234)
+    b = rbm.gibbs_steps(10, keep)
+    c = rbm.gibbs_steps(10, keep)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    h = rbm.sample_h_given_v(keep[0])
+    assert h.shape == (10,) and set(h.unique().tolist()) <= {0.0, 1.0}
+
+
+def test_gibbs_statistics_vs_exact_distribution(lib, cuda):
+    """Own-RNG samples follow exp(-E)/Z: chi-square of the 2^N-bin histogram (N = 10, 2e6 samples)."""
+    n, nh = 10, 10
+    rbm, orc = _pair(n, nh, 51, cuda)
+    chains = 2_000_000
+    v0 = torch.tensor(random_states(chains, n, 52), device=cuda)
+    vk = rbm.gibbs_steps(50, v0, seed=2024)
+    idx = (vk.to(torch.int64) * (2 ** torch.arange(n - 1, -1, -1, device=cuda))).sum(1)
+    counts = torch.bincount(idx, minlength=1 << n).cpu().numpy().astype(np.float64)
+    from oracle.rbm_oracle import hilbert_rows
+
+    p = np.exp(-orc.effective_energy(hilbert_rows(n)))
+    p /= p.sum()
+    chi2 = float((((counts - chains * p) ** 2) / (chains * p)).sum())
+    dof = (1 << n) - 1
+    # chi2 ~ N(dof, 2 dof): accept within 5 sigma
+    assert abs(chi2 - dof) < 5 * np.sqrt(2 * dof), f"chi2 = {chi2:.1f} for {dof} dof"
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (4, 9), (16, 20), (20, 20)])
+def test_partition(lib, cuda, n, nh):
+    rbm, orc = _pair(n, nh, 61, cuda)
+    want = orc.log_partition()
+    out2 = rbm.log_partition().cpu().numpy()
+    assert abs((out2[0] + np.log(out2[1])) - want) <= 1e-10 * abs(want)
+    assert_close(rbm.partition(), np.float64(np.exp(want)), what="Z from index enumeration")
+    if n <= 16:
+        from qucumber_b200 import HilbertSpace
+
+        space = HilbertSpace(n).tensor(device=cuda)
+        assert_close(rbm.partition(space), np.float64(np.exp(want)), what="Z from explicit space")
+    # ranges combine: sharded == unsharded, ragged boundaries included
+    total = 1 << n
+    cuts = [0, 1, total // 3, total // 2 + 5, total]
+    parts = [rbm.log_partition(a, b - a).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])]
+    m = max(p[0] for p in parts)
+    s = sum(p[1] * np.exp(p[0] - m) for p in parts)
+    assert abs((m + np.log(s)) - want) <= 1e-10 * abs(want)
+    empty = rbm.log_partition(5, 0).cpu().numpy()
+    assert empty[1] == 0.0
