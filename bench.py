@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the RBM hot path on B200 — BASELINE.json metric "Gibbs chain-sweeps/s at N=64,nh=64"
+(plus the two companion figures, exact-Z states/s and TFIM N=10 epoch time, under "extra").
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's torch-CPU path (oracle port)
+
+One step = one pass of the hot path over one batch: k block-Gibbs sweeps of C = 2^20 chains per GPU
+on a synthetic BinaryRBM N = nh = 64 (W = randn/8, biases 0.1 randn, v0 ~ Bernoulli(1/2)).
+Chains shard across ranks with no data-path collective ("weak" scaling: C per GPU is fixed).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_VIS, N_HID = 64, 64
+FLOP_PER_SWEEP = 4 * N_VIS * N_HID  # dense contraction, both half-sweeps
+
+
+def synthetic_rbm():
+    g = torch.Generator().manual_seed(1234)
+    W = torch.randn(N_HID, N_VIS, dtype=torch.double, generator=g) / 8.0
+    b = 0.1 * torch.randn(N_VIS, dtype=torch.double, generator=g)
+    c = 0.1 * torch.randn(N_HID, dtype=torch.double, generator=g)
+    return W, b, c
+
+
+def initial_state(chains, rank):
+    g = torch.Generator().manual_seed(1337 + rank)
+    return (torch.rand(chains, N_VIS, generator=g) < 0.5).to(torch.double)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_baseline_sample(k, chains, reps):
+    """The reference's torch-CPU Gibbs path on a bounded sample of the workload."""
+    from oracle.cpu_path import gibbs_steps_cpu
+
+    W, b, c = synthetic_rbm()
+    v = initial_state(chains, 0)
+    torch.manual_seed(7)
+    gibbs_steps_cpu(W, b, c, 1, v)  # warm-up
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        gibbs_steps_cpu(W, b, c, k, v)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return chains * k / best, times
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle.cpu_path import gibbs_steps_cpu
+
+    chains = args.ref_chains
+    W, b, c = synthetic_rbm()
+    v = initial_state(chains, 0)
+    torch.manual_seed(7)
+    for _ in range(args.warmup):
+        gibbs_steps_cpu(W, b, c, args.k, v)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gibbs_steps_cpu(W, b, c, args.k, v)
+    dt = time.perf_counter() - t0
+    value = chains * args.k * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{chains} chains x k={args.k} sweeps per step (same RBM, N=nh=64, float64)"
+    line = {
+        "impl": "reference", "metric": "gibbs_chain_sweeps_per_s", "value": value, "unit": "chain-sweeps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BinaryRBM N=64 nh=64 block Gibbs, k={args.k} sweeps/step", "chains_per_step": chains,
+                   "k": args.k, "note": "reference torch-CPU operator sequence (oracle port); bounded sample of the GPU workload"},
+        "cpu_baseline": {"value": value, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def extra_metrics(dev, lib_mod):
+    """Companion figures of the BASELINE metric string, measured outside the main timed region."""
+    from qucumber_b200 import BinaryRBM
+
+    out = {}
+    try:
+        n = 28
+        g = torch.Generator().manual_seed(1234)
+        rbm = BinaryRBM(n, n, gpu=True)
+        with torch.no_grad():
+            rbm.weights.copy_(torch.randn(n, n, dtype=torch.double, generator=g) / np.sqrt(n))
+        rbm.log_partition(0, 1 << 20)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out2 = rbm.log_partition()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        out["exact_z"] = {"N": n, "nh": n, "states_per_s": (1 << n) / (ms * 1e-3), "ms": ms,
+                          "logZ": float(out2[0] + out2[1].log())}
+    except Exception as exc:  # pragma: no cover - reported, not hidden
+        out["exact_z"] = {"error": str(exc)}
+    return out
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — qucumber_b200 has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from qucumber_b200 import BinaryRBM, _lib
+
+    lib = _lib.load()
+    W, b, c = synthetic_rbm()
+    rbm = BinaryRBM(N_VIS, N_HID, gpu=True)
+    with torch.no_grad():
+        rbm.weights.copy_(W)
+        rbm.visible_bias.copy_(b)
+        rbm.hidden_bias.copy_(c)
+    C, k = args.chains, args.k
+    chain0 = rank * C  # global chain ids: sharded runs draw the same numbers as one big run
+    v_host = initial_state(C, rank).pin_memory()
+    v = v_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.double, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- device-resident throughput ("value") ----
+    sweep = 0
+    for _ in range(args.warmup):
+        rbm.gibbs_steps(k, v, overwrite=True, seed=args.seed, chain_id0=chain0, sweep0=sweep)
+        sweep += k
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.qcb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rbm.gibbs_steps(k, v, overwrite=True, seed=args.seed, chain_id0=chain0, sweep0=sweep)
+        sweep += k
+    e1.record()
+    barrier()
+    launches = lib.qcb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * C * k / (ms_step * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_step, "site_updates_per_s": value * N_VIS,
+                              "dmma_frac": C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 37.117e12, "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ----
+    scratch_bytes = lib.qcb_gibbs_host_scratch_bytes(N_VIS, N_HID, 0, C)
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+    Wh, bh, ch = W.contiguous().pin_memory(), b.pin_memory(), c.pin_memory()
+    stream = _lib.stream_ptr(dev)
+
+    def e2e_step(sw):
+        _lib.check(lib.qcb_rbm_gibbs_host(_lib.ptr(Wh), None, _lib.ptr(bh), _lib.ptr(ch), None, N_VIS, N_HID, 0,
+                                          _lib.ptr(v_host), C, k, args.seed, chain0, sw, _lib.ptr(scratch), scratch_bytes,
+                                          stream), "qcb_rbm_gibbs_host")
+
+    for i in range(max(1, min(args.warmup, 3))):
+        e2e_step(i * k)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step((i + 10) * k)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * C * k * args.steps / e2e_s
+    param_bytes = (N_HID * N_VIS + N_VIS + N_HID) * 8
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+        peak_tflops, peak_src = 37.1, "fallback: DMMA m8n8k4 peak measured on this pool (profiles/fp64_peaks_r01.json missing)"
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as fh:
+                peak_tflops = json.load(fh)["dmma_m8n8k4_tflops"]
+            peak_src = "measured: FP64 DMMA m8n8k4 peak, tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure"
+        achieved = C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 1e12  # per GPU: one launch processes C*k chain-sweeps
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gibbs_traffic_r01.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        line = {
+            "metric": "gibbs_chain_sweeps_per_s", "value": value, "unit": "chain-sweeps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BinaryRBM N=64 nh=64 block Gibbs, k={k} sweeps/step, {C} chains per GPU",
+                       "chains_per_gpu": C, "k": k, "l2": "inputs larger than L2 (512 MiB chain state per GPU per step)",
+                       "visible_site_updates_per_s": value * N_VIS, "rng": "in-kernel Philox4x32-10"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": "gibbs_kernel<4,4>",
+                         "peak_source": peak_src, "flop_per_chain_sweep": FLOP_PER_SWEEP},
+            "e2e": {"value": e2e_value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": C * N_VIS * 8 + param_bytes,
+                    "d2h_bytes_per_step": C * N_VIS * 8, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "call": "qcb_rbm_gibbs_host (pinned host buffers, copies inside the timed region)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1:
+            cpu_v, cpu_times = cpu_baseline_sample(k, args.ref_chains, 3)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "chain-sweeps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{args.ref_chains} chains x k={k} sweeps, best of 3 ({min(cpu_times):.2f} s), "
+                                              "reference torch-CPU operator sequence (oracle/cpu_path.py)"}
+            line["extra"] = extra_metrics(dev, _lib)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--k", type=int, default=10, help="Gibbs sweeps per step")
+    ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
+    ap.add_argument("--ref-chains", type=int, default=1 << 17, help="chains per step of the CPU reference sample")
+    ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--quick", action="store_true", help="kernel throughput only (skip e2e, CPU baseline and extras)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,25 @@ struct RngCtx {
 
 constexpr float FILTER_EPS = 0x1.0p-16f;
 
+// Cold path, kept out of line so the hot loop stays inside the instruction cache: draws the low
+// words of the flagged units and compares the full 53-bit uniform with the exact FP64 sigmoid.
+__device__ __noinline__ uint32_t decide4_slow(double x0, double x1, double x2, double x3, uint32_t r0, uint32_t r1,
+                                              uint32_t r2, uint32_t r3, uint32_t c0, uint32_t c1, uint32_t key0,
+                                              uint32_t key1, uint32_t sweep, uint32_t q, uint32_t slow, uint32_t nib) {
+  uint32_t lo[4];
+  philox4x32_10(c0, c1, sweep, q | 0x80000000u, key0, key1, lo);
+  const double x[4] = {x0, x1, x2, x3};
+  const uint32_t r[4] = {r0, r1, r2, r3};
+#pragma unroll 1
+  for (int w = 0; w < 4; ++w) {
+    if (slow & (1u << w)) {
+      const double u = uniform53(r[w], lo[w]);
+      if (u < sigmoid_exact(x[w])) nib |= 1u << w; else nib &= ~(1u << w);
+    }
+  }
+  return nib;
+}
+
 __device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const RngCtx& rc, uint32_t sweep, uint32_t q,
                                                    uint32_t valid) {
   uint32_t r[4];
@@ -104,23 +123,15 @@ __device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const R
     else if (!(uf >= p + FILTER_EPS)) slow |= 1u << w;
   }
   slow &= valid;
-  if (slow) {
-    uint32_t lo[4];
-    philox4x32_10(rc.c0, rc.c1, sweep, q | 0x80000000u, rc.key0, rc.key1, lo);
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      if (slow & (1u << w)) {
-        const double u = uniform53(r[w], lo[w]);
-        if (u < sigmoid_exact(x[w])) nib |= 1u << w; else nib &= ~(1u << w);
-      }
-    }
-  }
+  if (slow) nib = decide4_slow(x[0], x[1], x[2], x[3], r[0], r[1], r[2], r[3], rc.c0, rc.c1, rc.key0, rc.key1, sweep, q, slow, nib);
   return nib & valid;
 }
 
-__device__ __forceinline__ uint32_t decide4_fed(const double (&x)[4], const double* __restrict__ u, uint32_t valid) {
+__device__ __noinline__ uint32_t decide4_fed(double x0, double x1, double x2, double x3, const double* __restrict__ u,
+                                             uint32_t valid) {
+  const double x[4] = {x0, x1, x2, x3};
   uint32_t nib = 0;
-#pragma unroll
+#pragma unroll 1
   for (int w = 0; w < 4; ++w) {
     if (valid & (1u << w)) {
       if (u[w] < sigmoid_exact(x[w])) nib |= 1u << w;
@@ -175,10 +186,7 @@ __device__ __forceinline__ void half_sweep(const uint32_t (&min)[(KB_IN + 1) / 2
       const double x[4] = {acc[2 * gq][0], acc[2 * gq][1], acc[2 * gq + 1][0], acc[2 * gq + 1][1]};
       uint32_t nib;
       if (fed != nullptr) {
-        double u[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) u[w] = (valid & (1u << w)) ? fed[unit0 + w] : 2.0;
-        nib = decide4_fed(x, u, valid);
+        nib = decide4_fed(x[0], x[1], x[2], x[3], fed + unit0, valid);
       } else {
         nib = decide4_philox(x, rc, sweep, q0 + 4 * gq + t, valid);
       }
