@@ -595,3 +595,88 @@ def dm_gradient(rbm_am, rbm_ph, samples, bases, unitaries=None):
         else:
             g[0] += rbm_am.effective_energy_gradient(sub)
     return g
+
+
+# --------------------------------------------------------------------------------------------
+# Metrics with measurement bases (utils/training_statistics.py)
+# --------------------------------------------------------------------------------------------
+def KL_complex(rbm_am, rbm_ph, target_by_basis, bases, unitaries=None):
+    """ts.KL for a WaveFunctionBase with bases and a per-basis target dict
+    (utils/training_statistics.py:185-200): rotate the full psi, average the per-basis KL."""
+    space = hilbert_rows(rbm_am.n)
+    Z = rbm_am.partition(space)
+    psi = psi_complex(rbm_am, rbm_ph, space)
+    total = 0.0
+    for basis in bases:
+        psi_r = kron_rotate(basis, psi, unitaries)
+        total += single_basis_KL(np.abs(target_by_basis[basis]) ** 2, np.abs(psi_r) ** 2 / Z)
+    return total / float(len(bases))
+
+
+def NLL_complex(rbm_am, rbm_ph, samples, sample_bases, unitaries=None):
+    """ts.NLL with sample_bases for a wavefunction (utils/training_statistics.py:103-128)."""
+    samples = np.asarray(samples, dtype=np.float64)
+    Z = rbm_am.partition(hilbert_rows(rbm_am.n))
+    uniq, inv = group_by_basis(sample_bases)
+    nll = 0.0
+    for i in range(uniq.shape[0]):
+        sub = samples[inv == i]
+        if np.any(uniq[i] != "Z"):
+            Upsi = rotate_psi_inner_prod(lambda x: psi_complex(rbm_am, rbm_ph, x), uniq[i], sub, unitaries)
+            probs = np.abs(Upsi) ** 2 / Z
+        else:
+            probs = np.exp(-rbm_am.effective_energy(sub)) / Z
+        nll -= probs_to_logits(probs).sum()
+    return float(nll / len(samples))
+
+
+def KL_dm(rbm_am, rbm_ph, target_rho, bases, unitaries=None):
+    """ts.KL for a DensityMatrix with a full target matrix (utils/training_statistics.py:201-216)."""
+    space = hilbert_rows(rbm_am.n)
+    Z = rbm_am.partition(space)
+    idx = basis_index(space)
+    total = 0.0
+    for basis in bases:
+        Ut, v = rotate_basis_state(basis, space, unitaries)
+        Ut2 = np.einsum("ib,jb->ijb", Ut, np.conj(Ut))
+        vi = basis_index(v)  # (2^S, B)
+        t_probs = (Ut2 * target_rho[vi[:, None, :], vi[None, :, :]]).real.sum((0, 1))
+        n_probs = rotate_rho_probs(lambda x: dm_rho(rbm_am, rbm_ph, x), basis, space, unitaries) / Z
+        total += single_basis_KL(t_probs, n_probs)
+    del idx
+    return total / float(len(bases))
+
+
+def NLL_dm(rbm_am, rbm_ph, samples, sample_bases, unitaries=None):
+    samples = np.asarray(samples, dtype=np.float64)
+    Z = rbm_am.partition(hilbert_rows(rbm_am.n))
+    uniq, inv = group_by_basis(sample_bases)
+    nll = 0.0
+    for i in range(uniq.shape[0]):
+        sub = samples[inv == i]
+        if np.any(uniq[i] != "Z"):
+            probs = rotate_rho_probs(lambda x: dm_rho(rbm_am, rbm_ph, x), uniq[i], sub, unitaries) / Z
+        else:
+            probs = np.exp(-rbm_am.effective_energy(sub)) / Z
+        nll -= probs_to_logits(probs).sum()
+    return float(nll / len(samples))
+
+
+def fidelity_dm(rbm_am, rbm_ph, target_rho):
+    """Mixed-state fidelity (utils/training_statistics.py:60-76): (sum sqrt |eig(target rho)|)^2."""
+    space = hilbert_rows(rbm_am.n)
+    rho = dm_rho(rbm_am, rbm_ph, space, space) / rbm_am.partition(space)
+    eig = np.abs(np.linalg.eigvals(target_rho @ rho).real)
+    return float(np.sum(np.sqrt(eig)) ** 2)
+
+
+def exact_gradient_with_bases(kind, rbm_am, rbm_ph, samples, bases, unitaries=None):
+    """compute_exact_gradients with bases (nn_states/neural_state.py:386-415)."""
+    fn = complex_gradient if kind == "complex" else dm_gradient
+    g = fn(rbm_am, rbm_ph, samples, bases, unitaries)
+    g = [x / float(len(samples)) for x in g]
+    space = hilbert_rows(rbm_am.n)
+    probs = np.exp(-rbm_am.effective_energy(space))
+    probs = probs / probs.sum()
+    g[0] = g[0] - rbm_am.effective_energy_gradient(space, reduce=False).T @ probs
+    return g
