@@ -95,6 +95,12 @@ int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m,
                        const double* x, const double* M2, int m2_rows, const double* x2,
                        int64_t rows, double* out, void* stream);
 
+/* out (rows, n_out) = x M^T + bias without the sigmoid — F.linear as used by
+ * PurificationRBM.mixing_term (rbm/purification_rbm.py:340-350) and DensityMatrix.pi
+ * (nn_states/density_matrix.py:130-134).  bias may be NULL. */
+int qcb_linear(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias,
+               const double* x, int64_t rows, double* out, void* stream);
+
 /* out[i] = (u[i] < p[i]) as 0.0/1.0 — torch.bernoulli(p, out=p) (rbm/binary_rbm.py:182,197)
  * with u either fed (uniforms != NULL) or Philox slot i of chain `chain_id0`, sweep `sweep0`. */
 int qcb_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed,
@@ -154,15 +160,15 @@ int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t
  * with p = exp(-E - logZ), p_t = t_re^2 + t_im^2, clamp to [2^-52, 1 - 2^-52]
  * (utils/training_statistics.py:57-59, 131-135, 179-183).  If g_exact != NULL it receives
  * (accumulated) sum_r p(r) * grad E(r), the exact negative phase of
- * nn_states/neural_state.py:406-413.  BinaryRBM only (U, d NULL, na 0). */
-int qcb_rbm_exact_stats_range(const double* W, const double* b, const double* c, int N, int nh,
-                              uint64_t first_state, uint64_t count, double logZ,
+ * nn_states/neural_state.py:406-413. */
+int qcb_rbm_exact_stats_range(const double* W, const double* U, const double* b, const double* c, const double* d,
+                              int N, int nh, int na, uint64_t first_state, uint64_t count, double logZ,
                               const double* target_re, const double* target_im,
                               double* out8, double* g_exact, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Rotated-basis amplitude and gradient: ComplexWaveFunction ------------------------
- * For each sample (row of `samples`, B x N) measured in `basis` (N codes indexing `unitaries`;
- * code 0 must be the identity / "Z"), expand over the S non-identity sites (2^S states,
+ * For each sample (row of `samples`, B x N) measured in `basis` (a HOST array of N codes indexing
+ * `unitaries`; code 0 must be the identity / "Z"), expand over the S non-identity sites (2^S states,
  * expansion bit order of utils/unitaries.py:154-181), with psi = exp(-E_am/2) * exp(-i E_ph/2):
  *   Upsi[b]  = sum_i Ut[i,b] psi(v_ib)                             -> Upsi (2, B) [re; im]
  *   g_am    += sum_b Re[ sum_i Ut psi grad E_am(v_ib) / Upsi[b] ]

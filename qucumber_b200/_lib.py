@@ -25,6 +25,7 @@ SIGNATURES = {
     "qcb_rbm_gibbs": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64, c_uint64,
                               _P, _P, c_size_t, _P]),
     "qcb_linear_sigmoid": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int64, _P, _P]),
+    "qcb_linear": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int64, _P, _P]),
     "qcb_bernoulli": (c_int, [_P, c_int64, _P, c_uint64, c_uint64, c_uint64, _P, _P]),
     "qcb_rbm_energy": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P, c_size_t, _P]),
     "qcb_rbm_grad_reduce": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_double, _P, c_int, _P,
@@ -34,8 +35,8 @@ SIGNATURES = {
                                 _P, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_logz_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, _P, _P, c_size_t, _P]),
     "qcb_neg_logsumexp": (c_int, [_P, c_int64, _P, _P, c_size_t, _P]),
-    "qcb_rbm_exact_stats_range": (c_int, [_P, _P, _P, c_int, c_int, c_uint64, c_uint64, c_double, _P, _P, _P, _P, _P,
-                                          c_size_t, _P]),
+    "qcb_rbm_exact_stats_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, c_double, _P, _P,
+                                          _P, _P, _P, c_size_t, _P]),
     "qcb_cwf_rotated": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, c_int, _P, _P, _P, _P,
                                 c_size_t, _P]),
     "qcb_dm_rotated": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P, c_int,

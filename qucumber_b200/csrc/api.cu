@@ -31,8 +31,8 @@ size_t gibbs_workspace_bytes(int N, int nhid);
 int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st);
-int run_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
-                       const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, cudaStream_t st);
+int run_linear(int mode, const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
+               const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, cudaStream_t st);
 int run_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                   double* out, cudaStream_t st);
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
@@ -113,7 +113,14 @@ int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m,
   if (M == nullptr || x == nullptr || out == nullptr || m_rows < 1 || m_cols < 1 || rows < 0)
     return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: bad arguments");
   if ((M2 == nullptr) != (x2 == nullptr)) return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: M2 and x2 go together");
-  return run_linear_sigmoid(M, m_rows, m_cols, transpose_m, bias, x, M2, m2_rows, x2, rows, out, (cudaStream_t)stream);
+  return run_linear(1, M, m_rows, m_cols, transpose_m, bias, x, M2, m2_rows, x2, rows, out, (cudaStream_t)stream);
+}
+
+int qcb_linear(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x, int64_t rows,
+               double* out, void* stream) {
+  if (M == nullptr || x == nullptr || out == nullptr || m_rows < 1 || m_cols < 1 || rows < 0)
+    return fail(QCB_ERR_BAD_ARG, "linear: bad arguments");
+  return run_linear(2, M, m_rows, m_cols, transpose_m, bias, x, nullptr, 0, nullptr, rows, out, (cudaStream_t)stream);
 }
 
 int qcb_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
@@ -181,11 +188,12 @@ int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t
   return run_neg_logsumexp(E, n, out2, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int qcb_rbm_exact_stats_range(const double* W, const double* b, const double* c, int N, int nh, uint64_t first_state,
-                              uint64_t count, double logZ, const double* target_re, const double* target_im,
-                              double* out8, double* g_exact, void* ws, size_t ws_bytes, void* stream) {
+int qcb_rbm_exact_stats_range(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
+                              int nh, int na, uint64_t first_state, uint64_t count, double logZ, const double* target_re,
+                              const double* target_im, double* out8, double* g_exact, void* ws, size_t ws_bytes,
+                              void* stream) {
   StackedParams p;
-  int rc = make_params(p, W, nullptr, b, c, nullptr, N, nh, 0);
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
   if (out8 == nullptr) return fail(QCB_ERR_BAD_ARG, "exact_stats: out8 is NULL");
   rc = run_exact_stats_range(p, first_state, count, logZ, target_re, target_im, out8, ws, ws_bytes, (cudaStream_t)stream);

@@ -1,14 +1,432 @@
-// placeholder until the rotated-basis kernels land
-#include "common.cuh"
+// Rotated-basis amplitudes / probabilities and their gradients (sm_100a).
+//
+// ComplexWaveFunction (nn_states/complex_wavefunction.py:162-211, utils/unitaries.py:154-233):
+//   a sample measured in a basis with S non-Z sites is expanded over the 2^S basis states v_i it
+//   overlaps with, T_i = Ut_i psi(v_i), D = sum_i T_i, and the gradients are
+//     g_am = sum_b sum_i Re[T_i / D] grad E_am(v_i),   g_ph = sum_b sum_i (-Im[T_i / D]) grad E_ph(v_i)
+//   (grad E is real, so the complex einsums of the reference collapse to two real weights per
+//   expanded state).  Kernel 1 walks each sample's expansion in Gray-code order (one visible unit
+//   flips per step, theta updated with nh adds) and writes T and D; kernel 2 turns them into the
+//   two weights; the weighted outer products are reduced by grad_reduce.cu (ROWS_EXPANDED).
+//   The reference builds v (2^S, B, N) and Ut with NumPy on the host; nothing leaves the GPU here.
+//
+// DensityMatrix (nn_states/density_matrix.py:113-330, rbm/purification_rbm.py:352-451,
+// utils/unitaries.py:236-283): w_ij = Ut_i conj(Ut_j) rho~(v_i, v_j), P = sum_ij Re w_ij.  Using
+// w_ji = conj(w_ij) and S_ji = conj(S_ij) the (2, 2^S, 2^S, B, G) gradient tensors of the
+// reference reduce to per-expanded-state quantities
+//     r_i = sum_j Re w_ij, s_i = sum_j Im w_ij, R_ik = sum_j Re(w_ij S_ijk), I_ik = sum_j Im(w_ij S_ijk)
+// and  g_am = f sum_i [ r_i s_h(v_i) (x) v_i ; R_i (x) v_i ; r_i v_i ; r_i s_h(v_i) ; R_i ],
+//      g_ph = -f sum_i [ s_i s_h'(v_i) (x) v_i ; I_i (x) v_i ; s_i v_i ; s_i s_h'(v_i) ; 0 ],  f = -1/(P + 1e-8),
+// again a weighted outer-product reduction (S_ijk is the complex sigmoid of utils/cplx.py:319-334).
+#include "rows.cuh"
+
 namespace qcb {
-size_t cwf_workspace_bytes(int, int, int64_t) { return 256; }
-size_t dm_workspace_bytes(int, int, int, int64_t) { return 256; }
-int run_cwf_rotated(const StackedParams&, const StackedParams&, const double*, int64_t, const uint8_t*, const double*, int,
-                    double*, double*, double*, void*, size_t, cudaStream_t) {
-  return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: not built yet");
+
+int run_grad_reduce_expanded(const StackedParams& p, const Expansion& ex, int64_t rows, const double* wrow,
+                             const double* aux, int n_aux, int zero_tail, double scale, double* g, void* ws, size_t ws_bytes,
+                             cudaStream_t st);
+size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
+
+constexpr int64_t ROT_MAX_ROWS = (int64_t)1 << 21;  // expanded rows processed per chunk
+constexpr int ROT_MAX_S = 21;
+constexpr int CWF_THREADS = 128;
+
+struct SiteInfo {
+  int S;
+  int8_t site[32];    // rotated site t -> visible unit
+  uint8_t ucode[32];  // rotated site t -> unitary code
+};
+
+__device__ __forceinline__ void cmul(double& ar, double& ai, double br, double bi) {
+  const double r = ar * br - ai * bi;
+  ai = ar * bi + ai * br;
+  ar = r;
 }
-int run_dm_rotated(const StackedParams&, const StackedParams&, const double*, int64_t, const uint8_t*, const double*, int,
-                   double*, double*, double*, void*, size_t, cudaStream_t) {
-  return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: not built yet");
+
+// Ut for expansion index i of a sample whose rotated sites read sigma_t:
+// prod_t U[ucode_t][sigma_t][bit_t(i)]   (utils/unitaries.py:169-176)
+__device__ __forceinline__ void unitary_product(const double* __restrict__ Usm, const SiteInfo& si, uint32_t sigbits,
+                                                uint32_t i, double& re, double& im) {
+  re = 1.0; im = 0.0;
+  for (int t = 0; t < si.S; ++t) {
+    const int row = (sigbits >> t) & 1u;
+    const int col = (i >> (si.S - 1 - t)) & 1u;
+    const double* u = Usm + si.ucode[t] * 8;
+    cmul(re, im, u[row * 2 + col], u[4 + row * 2 + col]);
+  }
 }
+
+// ---- ComplexWaveFunction kernel 1: T_i and D ---------------------------------------------------
+template <int NHT>
+__global__ void __launch_bounds__(CWF_THREADS) cwf_amp_kernel(StackedParams am, StackedParams ph, const double* __restrict__ samples,
+                                                              int64_t b0, int64_t B, SiteInfo si, const double* __restrict__ U, int K,
+                                                              int tps_log2, double2* __restrict__ T, double2* __restrict__ D,
+                                                              double* __restrict__ Upsi, int64_t Btotal) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = am.N, nh = am.nh, S = si.S;
+  double* Wa = reinterpret_cast<double*>(smem_raw);  // [N][NHT]
+  double* Wp = Wa + (size_t)N * NHT;
+  double* ca = Wp + (size_t)N * NHT;                 // [NHT]
+  double* cp = ca + NHT;
+  double* ba = cp + NHT;                             // [N]
+  double* bp = ba + round_up(N, 2);
+  double* Usm = bp + round_up(N, 2);                 // [K][8]
+  double* red = Usm + (size_t)K * 8;                 // [CWF_THREADS][2]
+  for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
+    const int j = idx / NHT, i = idx - j * NHT;
+    Wa[idx] = i < nh ? am.W[(size_t)i * N + j] : 0.0;
+    Wp[idx] = i < nh ? ph.W[(size_t)i * N + j] : 0.0;
+  }
+  for (int i = threadIdx.x; i < NHT; i += blockDim.x) {
+    ca[i] = i < nh ? am.c[i] : 0.0;
+    cp[i] = i < nh ? ph.c[i] : 0.0;
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) { ba[j] = am.b[j]; bp[j] = ph.b[j]; }
+  for (int i = threadIdx.x; i < K * 8; i += blockDim.x) Usm[i] = U[i];
+  __syncthreads();
+
+  const int tps = 1 << tps_log2;            // threads per sample
+  const int m = S - tps_log2;               // log2(states per thread)
+  const int spc = CWF_THREADS >> tps_log2;  // samples per CTA
+  const int sl = threadIdx.x >> tps_log2, tl = threadIdx.x & (tps - 1);
+  const int64_t b = (int64_t)blockIdx.x * spc + sl;  // sample index within this chunk
+  double dr = 0.0, di = 0.0;
+  if (b < B) {
+    const double* srow = samples + (b0 + b) * N;
+    uint32_t sigbits = 0;  // measured values on the rotated sites
+    for (int t = 0; t < S; ++t) sigbits |= (srow[si.site[t]] != 0.0 ? 1u : 0u) << t;
+    const uint32_t ibase = (uint32_t)tl << m;
+    // visible state of the first expanded index of this thread
+    double tha[NHT], thp[NHT];
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) { tha[i] = ca[i]; thp[i] = cp[i]; }
+    double bva = 0.0, bvp = 0.0;
+    for (int j = 0; j < N; ++j) {
+      bool on = srow[j] != 0.0;
+      for (int t = 0; t < S; ++t)
+        if (si.site[t] == j) on = (ibase >> (S - 1 - t)) & 1u;
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) { tha[i] += Wa[j * NHT + i]; thp[i] += Wp[j * NHT + i]; }
+        bva += ba[j]; bvp += bp[j];
+      }
+    }
+    const uint32_t steps = 1u << m;
+    for (uint32_t k = 0; k < steps; ++k) {
+      const uint32_t i_exp = ibase | (k ^ (k >> 1));
+      double xa = bva, xp = bvp;
+#pragma unroll
+      for (int i = 0; i < NHT; ++i)
+        if (i < nh) { xa += softplus20(tha[i]); xp += softplus20(thp[i]); }
+      const double amp = exp(0.5 * xa), phi = 0.5 * xp;  // |psi| = sqrt(exp(-E_am)), phase = -E_ph / 2
+      double sn, cs;
+      sincos(phi, &sn, &cs);
+      double tr, ti;
+      unitary_product(Usm, si, sigbits, i_exp, tr, ti);
+      cmul(tr, ti, amp * cs, amp * sn);
+      T[(b << S) + i_exp] = make_double2(tr, ti);
+      dr += tr; di += ti;
+      if (k + 1 < steps) {
+        const uint32_t k1 = k + 1;
+        const int pbit = __ffs(k1) - 1;
+        const uint32_t g1 = k1 ^ (k1 >> 1);
+        const double sgn = ((g1 >> pbit) & 1u) ? 1.0 : -1.0;
+        const int j = si.site[S - 1 - pbit];
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) { tha[i] = fma(sgn, Wa[j * NHT + i], tha[i]); thp[i] = fma(sgn, Wp[j * NHT + i], thp[i]); }
+        bva = fma(sgn, ba[j], bva);
+        bvp = fma(sgn, bp[j], bvp);
+      }
+    }
+  }
+  red[2 * threadIdx.x] = dr;
+  red[2 * threadIdx.x + 1] = di;
+  __syncthreads();
+  if (tl == 0 && b < B) {
+    double sr = 0.0, sim = 0.0;
+    for (int q = 0; q < tps; ++q) { sr += red[2 * (threadIdx.x + q)]; sim += red[2 * (threadIdx.x + q) + 1]; }
+    D[b] = make_double2(sr, sim);
+    Upsi[b0 + b] = sr;
+    Upsi[Btotal + b0 + b] = sim;
+  }
+}
+
+// ---- ComplexWaveFunction kernel 2: per-row weights Re(T/D), -Im(T/D) -----------------------------
+__global__ void cwf_weights_kernel(const double2* __restrict__ T, const double2* __restrict__ D, int S, int64_t rows,
+                                   double* __restrict__ wa, double* __restrict__ wp) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const double2 t = T[r], d = D[r >> S];
+  const double inv = 1.0 / (d.x * d.x + d.y * d.y);
+  wa[r] = (t.x * d.x + t.y * d.y) * inv;
+  wp[r] = -((t.y * d.x - t.x * d.y) * inv);
+}
+
+static int make_sites(const uint8_t* basis_host, int N, int K, SiteInfo& si, Expansion& ex) {
+  si.S = 0;
+  for (int j = 0; j < N; ++j) {
+    ex.sitepos[j] = -1;
+    if (basis_host[j] >= K) return fail(QCB_ERR_BAD_ARG, "rotated: basis code %d at site %d >= K = %d", basis_host[j], j, K);
+    if (basis_host[j] != 0) {
+      if (si.S >= ROT_MAX_S) return fail(QCB_ERR_UNSUPPORTED, "rotated: more than %d rotated sites", ROT_MAX_S);
+      si.site[si.S] = (int8_t)j;
+      si.ucode[si.S] = basis_host[j];
+      ex.sitepos[j] = (int8_t)si.S;
+      ++si.S;
+    }
+  }
+  ex.N = N;
+  ex.S = si.S;
+  return QCB_OK;
+}
+
+size_t cwf_workspace_bytes(int N, int nh, int64_t B) {
+  return align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)(B > 0 ? B : 1) * 16, 256) + grad_reduce_workspace_bytes(N, nh, 0);
+}
+
+template <int NHT>
+static int launch_cwf_amp(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t b0, int64_t Bc,
+                          const SiteInfo& si, const double* U, int K, double2* T, double2* D, double* Upsi, int64_t Btotal,
+                          cudaStream_t st) {
+  const int N = am.N;
+  const size_t smem = ((size_t)2 * N * NHT + 2 * NHT + 2 * round_up(N, 2) + (size_t)K * 8 + 2 * CWF_THREADS) * sizeof(double);
+  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: parameters do not fit in shared memory");
+  QCB_CUDA(cudaFuncSetAttribute(cwf_amp_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+  int tps_log2 = si.S < 7 ? si.S : 7;
+  const int spc = CWF_THREADS >> tps_log2;
+  const int64_t grid = (Bc + spc - 1) / spc;
+  cwf_amp_kernel<NHT><<<(unsigned)grid, CWF_THREADS, smem, st>>>(am, ph, samples, b0, Bc, si, U, K, tps_log2, T, D, Upsi, Btotal);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t B,
+                    const uint8_t* basis_host, const double* unitaries, int K, double* Upsi, double* g_am, double* g_ph,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int N = am.N, nh = am.nh;
+  if (N > 128) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: N = %d > 128", N);
+  if (nh > 32) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: nh = %d > 32", nh);
+  SiteInfo si{};
+  Expansion ex{};
+  int rc = make_sites(basis_host, N, K, si, ex);
+  if (rc != QCB_OK) return rc;
+  if (B == 0) return QCB_OK;
+  if (ws == nullptr || ws_bytes < cwf_workspace_bytes(N, nh, B)) return fail(QCB_ERR_BAD_ARG, "cwf_rotated: workspace too small");
+  char* base = static_cast<char*>(ws);
+  double2* T = reinterpret_cast<double2*>(base);
+  double* wa = reinterpret_cast<double*>(base + (size_t)ROT_MAX_ROWS * 16);
+  double* wp = wa + ROT_MAX_ROWS;
+  double2* D = reinterpret_cast<double2*>(base + align_up((size_t)ROT_MAX_ROWS * 32, 256));
+  void* gws = base + align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)B * 16, 256);
+  const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh, 0);
+  const int S = si.S;
+  const int64_t chunkB = ROT_MAX_ROWS >> S;
+  for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
+    const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
+    const int64_t rows = Bc << S;
+    if (nh <= 8) rc = launch_cwf_amp<8>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
+    else if (nh <= 16) rc = launch_cwf_amp<16>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
+    else rc = launch_cwf_amp<32>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
+    if (rc != QCB_OK) return rc;
+    if (g_am == nullptr) continue;
+    cwf_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(T, D, S, rows, wa, wp);
+    QCB_LAUNCH_CHECK();
+    ex.samples = samples + b0 * N;
+    rc = run_grad_reduce_expanded(am, ex, rows, wa, nullptr, 0, 0, 1.0, g_am, gws, gws_bytes, st);
+    if (rc != QCB_OK) return rc;
+    rc = run_grad_reduce_expanded(ph, ex, rows, wp, nullptr, 0, 0, 1.0, g_ph, gws, gws_bytes, st);
+    if (rc != QCB_OK) return rc;
+  }
+  return QCB_OK;
+}
+
+// ================================= DensityMatrix =================================================
+constexpr int DM_MAX_NA = 16;
+constexpr int DM_MAX_S = 8;
+
+// per expanded row: [f_am, f_ph, Ut_re, Ut_im, m_am[na], m_ph[na]]
+// f = b.v + sum softplus(W v + c) (rbm/purification_rbm.py:375-381); m_am = U_am v + d_am,
+// m_ph = U_ph v (no bias, nn_states/density_matrix.py:130-134)
+__global__ void __launch_bounds__(256) dm_feat_kernel(StackedParams am, StackedParams ph, Expansion ex, SiteInfo si,
+                                                      const double* __restrict__ U, int64_t rows, double* __restrict__ feat) {
+  const int lane = threadIdx.x & 31;
+  const int N = am.N, nh = am.nh, na = am.na, S = si.S;
+  const int FW = 4 + 2 * na;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    double fa = 0.0, fp = 0.0;
+    for (int j = lane; j < N; j += 32) {
+      const double vj = ex.value(r, j);
+      fa = fma(am.b[j], vj, fa);
+      fp = fma(ph.b[j], vj, fp);
+    }
+    for (int i = lane; i < nh; i += 32) {
+      double ta = am.c[i], tp = ph.c[i];
+      for (int j = 0; j < N; ++j) {
+        const double vj = ex.value(r, j);
+        ta = fma(am.W[(size_t)i * N + j], vj, ta);
+        tp = fma(ph.W[(size_t)i * N + j], vj, tp);
+      }
+      fa += softplus20(ta);
+      fp += softplus20(tp);
+    }
+    fa = warp_sum(fa);
+    fp = warp_sum(fp);
+    double* out = feat + r * FW;
+    for (int k = lane; k < na; k += 32) {
+      double ma = am.d[k], mp = 0.0;
+      for (int j = 0; j < N; ++j) {
+        const double vj = ex.value(r, j);
+        ma = fma(am.U[(size_t)k * N + j], vj, ma);
+        mp = fma(ph.U[(size_t)k * N + j], vj, mp);
+      }
+      out[4 + k] = ma;
+      out[4 + na + k] = mp;
+    }
+    if (lane == 0) {
+      const int64_t b = r >> S;
+      uint32_t sigbits = 0;
+      for (int t = 0; t < S; ++t) sigbits |= (ex.samples[b * N + si.site[t]] != 0.0 ? 1u : 0u) << t;
+      double ur, ui;
+      unitary_product(U, si, sigbits, (uint32_t)(r & (((int64_t)1 << S) - 1)), ur, ui);
+      out[0] = fa; out[1] = fp; out[2] = ur; out[3] = ui;
+    }
+  }
+}
+
+// thread per expanded row i of sample b: loops over the partner index j
+// stats row: [r_i, s_i, R_i[na], I_i[na]]
+__global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__ feat, int na, int S, int64_t rows,
+                                                      double* __restrict__ stats) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  const int64_t b = r >> S;
+  const double* fi = feat + r * FW;
+  double ri = 0.0, si = 0.0;
+  double R[DM_MAX_NA], I[DM_MAX_NA], Sr[DM_MAX_NA], Si[DM_MAX_NA];
+  for (int k = 0; k < na; ++k) { R[k] = 0.0; I[k] = 0.0; }
+  const int nexp = 1 << S;
+  for (int j = 0; j < nexp; ++j) {
+    const double* fj = feat + ((b << S) + j) * FW;
+    const double gp = 0.5 * (fi[0] + fj[0]);   // Gamma+ (amplitude RBM)
+    const double gm = 0.5 * (fi[1] - fj[1]);   // Gamma- (phase RBM)
+    double pre = 0.0, pim = 0.0;
+    for (int k = 0; k < na; ++k) {
+      const double x = 0.5 * (fi[4 + k] + fj[4 + k]);
+      const double y = 0.5 * (fi[4 + na + k] - fj[4 + na + k]);
+      double sn, cs;
+      sincos(y, &sn, &cs);
+      const double ex = exp(x);
+      // Pi (nn_states/density_matrix.py:143-155)
+      pre += log(sqrt(1.0 + 2.0 * ex * cs + exp(2.0 * x)));
+      pim += atan2(ex * sn, 1.0 + ex * cs);
+      // complex sigmoid 1 / (1 + exp(-(x + iy)))  (utils/cplx.py:319-334)
+      const double en = exp(-x);
+      const double dr = 1.0 + en * cs, di = -en * sn;
+      const double inv = 1.0 / (dr * dr + di * di);
+      Sr[k] = dr * inv;
+      Si[k] = -di * inv;
+    }
+    const double ampl = exp(gp + pre), phs = gm + pim;
+    double sn, cs;
+    sincos(phs, &sn, &cs);
+    // w = Ut_i conj(Ut_j) rho~
+    double wr = fi[2], wi = fi[3];
+    cmul(wr, wi, fj[2], -fj[3]);
+    cmul(wr, wi, ampl * cs, ampl * sn);
+    ri += wr;
+    si += wi;
+    for (int k = 0; k < na; ++k) {
+      R[k] += wr * Sr[k] - wi * Si[k];
+      I[k] += wr * Si[k] + wi * Sr[k];
+    }
+  }
+  double* out = stats + r * SW;
+  out[0] = ri;
+  out[1] = si;
+  for (int k = 0; k < na; ++k) { out[2 + k] = R[k]; out[2 + na + k] = I[k]; }
+}
+
+// thread per sample: P_b = sum_i r_i (imaginary parts cancel, utils/unitaries.py:274-276)
+__global__ void dm_prob_kernel(const double* __restrict__ stats, int na, int S, int64_t B, int64_t b0, double* __restrict__ UrhoU) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int SW = 2 + 2 * na;
+  double p = 0.0;
+  for (int i = 0; i < (1 << S); ++i) p += stats[((b << S) + i) * SW];
+  UrhoU[b0 + b] = p;
+}
+
+// per row weights for the two weighted reductions
+__global__ void dm_weights_kernel(const double* __restrict__ stats, const double* __restrict__ UrhoU, int na, int S,
+                                  int64_t rows, int64_t b0, double* __restrict__ wam, double* __restrict__ auxam,
+                                  double* __restrict__ wph, double* __restrict__ auxph) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int SW = 2 + 2 * na;
+  const double f = -1.0 / (UrhoU[b0 + (r >> S)] + 1e-8);  // nn_states/density_matrix.py:296,300
+  const double* s = stats + r * SW;
+  wam[r] = f * s[0];
+  wph[r] = -f * s[1];
+  for (int k = 0; k < na; ++k) {
+    auxam[r * na + k] = f * s[2 + k];
+    auxph[r * na + k] = -f * s[2 + na + k];
+  }
+}
+
+constexpr int64_t DM_MAX_ROWS = (int64_t)1 << 18;
+
+size_t dm_workspace_bytes(int N, int nh, int na, int64_t B) {
+  (void)B;
+  const size_t per_row = (size_t)(4 + 2 * na) + (2 + 2 * na) + (2 + 2 * na);
+  return align_up((size_t)DM_MAX_ROWS * per_row * sizeof(double), 256) + grad_reduce_workspace_bytes(N, nh + na, 0);
+}
+
+int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t B,
+                   const uint8_t* basis_host, const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int N = am.N, nh = am.nh, na = am.na;
+  if (N > 128) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: N = %d > 128", N);
+  if (na > DM_MAX_NA) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: na = %d > %d", na, DM_MAX_NA);
+  SiteInfo si{};
+  Expansion ex{};
+  int rc = make_sites(basis_host, N, K, si, ex);
+  if (rc != QCB_OK) return rc;
+  if (si.S > DM_MAX_S) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: %d rotated sites > %d (4^S pairs per sample)", si.S, DM_MAX_S);
+  if (B == 0) return QCB_OK;
+  if (ws == nullptr || ws_bytes < dm_workspace_bytes(N, nh, na, B)) return fail(QCB_ERR_BAD_ARG, "dm_rotated: workspace too small");
+  const int S = si.S;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  double* feat = static_cast<double*>(ws);
+  double* stats = feat + DM_MAX_ROWS * FW;
+  double* wam = stats + DM_MAX_ROWS * SW;
+  double* wph = wam + DM_MAX_ROWS;
+  double* auxam = wph + DM_MAX_ROWS;
+  double* auxph = auxam + DM_MAX_ROWS * na;
+  const size_t per_row = (size_t)FW + SW + SW;
+  void* gws = static_cast<char*>(ws) + align_up((size_t)DM_MAX_ROWS * per_row * sizeof(double), 256);
+  const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh + na, 0);
+  const int64_t chunkB = DM_MAX_ROWS >> S;
+  for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
+    const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
+    const int64_t rows = Bc << S;
+    ex.samples = samples + b0 * N;
+    const int64_t fgrid = (rows + 7) / 8;
+    dm_feat_kernel<<<(unsigned)(fgrid < 65535 ? fgrid : 65535), 256, 0, st>>>(am, ph, ex, si, unitaries, rows, feat);
+    QCB_LAUNCH_CHECK();
+    dm_pair_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(feat, na, S, rows, stats);
+    QCB_LAUNCH_CHECK();
+    dm_prob_kernel<<<(unsigned)((Bc + 127) / 128), 128, 0, st>>>(stats, na, S, Bc, b0, UrhoU);
+    QCB_LAUNCH_CHECK();
+    if (g_am == nullptr) continue;
+    dm_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, UrhoU, na, S, rows, b0, wam, auxam, wph, auxph);
+    QCB_LAUNCH_CHECK();
+    rc = run_grad_reduce_expanded(am, ex, rows, wam, auxam, na, 0, -1.0, g_am, gws, gws_bytes, st);
+    if (rc != QCB_OK) return rc;
+    rc = run_grad_reduce_expanded(ph, ex, rows, wph, auxph, na, na, -1.0, g_ph, gws, gws_bytes, st);
+    if (rc != QCB_OK) return rc;
+  }
+  return QCB_OK;
+}
+
 }  // namespace qcb

@@ -1,0 +1,99 @@
+// Row-wise affine layer staging shared by the energy / conditional / gradient kernels.
+#pragma once
+#include "common.cuh"
+
+namespace qcb {
+
+constexpr int ROWS_THREADS = 256;
+constexpr int ROWS_WARPS = ROWS_THREADS / 32;
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+
+// Generic "affine rows" operand: out unit o = bias[o] + sum_i Mop[o][i] * xin[i], where the input is
+// the concatenation [x (n_in1) | x2 (n_in2)] and Mop[o][i] is gathered from up to two stored matrices.
+struct AffineSpec {
+  const double* M1; int m1_rows, m1_cols, t1;   // t1 = 1: Mop[o][i] = M1[i][o]
+  const double* M2; int m2_rows, m2_cols, t2;   // second operand (may be NULL)
+  const double* bias1; int nb1;                 // bias for units [0, nb1)
+  const double* bias2;                          // bias for units [nb1, n_out) (may be NULL -> 0)
+  int n_out, n_in1, n_in2;
+  // stacked_units = 1: units [0, m1_rows) are M1 rows, the rest M2 rows; one input x
+  // stacked_units = 0: every unit sees M1^T over x and M2^T over x2 ("stacked inputs")
+  int stacked_units;
+  __device__ __forceinline__ double mop(int o, int i) const {
+    if (stacked_units) {
+      if (o < m1_rows) return M1[(size_t)o * m1_cols + i];
+      return M2[(size_t)(o - m1_rows) * m2_cols + i];
+    }
+    if (i < n_in1) return t1 ? M1[(size_t)i * m1_cols + o] : M1[(size_t)o * m1_cols + i];
+    const int i2 = i - n_in1;
+    return t2 ? M2[(size_t)i2 * m2_cols + o] : M2[(size_t)o * m2_cols + i2];
+  }
+  __device__ __forceinline__ double bias(int o) const {
+    if (o < nb1) return bias1 ? bias1[o] : 0.0;
+    return bias2 ? bias2[o - nb1] : 0.0;
+  }
+  __host__ __device__ int n_in() const { return n_in1 + n_in2; }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void stage_affine(const AffineSpec& s, double* Ws, int LD, double* bs) {
+  const int nin = s.n_in();
+  for (int idx = threadIdx.x; idx < s.n_out * nin; idx += blockDim.x) {
+    const int o = idx / nin, i = idx - o * nin;
+    Ws[o * LD + i] = s.mop(o, i);
+  }
+  for (int o = threadIdx.x; o < s.n_out; o += blockDim.x) bs[o] = s.bias(o);
+}
+#endif
+
+// all hidden-like units of a (Purification)RBM: [W; U] rows with biases [c; d]
+inline AffineSpec stacked_hidden_spec(const StackedParams& p) {
+  AffineSpec s{};
+  s.M1 = p.W; s.m1_rows = p.nh; s.m1_cols = p.N; s.t1 = 0;
+  s.M2 = p.U; s.m2_rows = p.na; s.m2_cols = p.N; s.t2 = 0;
+  s.bias1 = p.c; s.nb1 = p.nh; s.bias2 = p.d;
+  s.n_out = p.nhid(); s.n_in1 = p.N; s.n_in2 = 0;
+  s.stacked_units = 1;
+  return s;
+}
+
+// only the hidden units (W, c) of a (Purification)RBM
+inline AffineSpec hidden_only_spec(const StackedParams& p) {
+  AffineSpec s{};
+  s.M1 = p.W; s.m1_rows = p.nh; s.m1_cols = p.N; s.t1 = 0;
+  s.M2 = nullptr; s.m2_rows = 0; s.m2_cols = p.N; s.t2 = 0;
+  s.bias1 = p.c; s.nb1 = p.nh; s.bias2 = nullptr;
+  s.n_out = p.nh; s.n_in1 = p.N; s.n_in2 = 0;
+  s.stacked_units = 1;
+  return s;
+}
+
+// Expansion of measured samples over their rotated sites (utils/unitaries.py:154-181): row
+// r = b * 2^S + i is sample b with rotated site number t set to bit (i >> (S-1-t)) & 1.
+struct Expansion {
+  const double* samples;   // (B, N)
+  int N, S;
+  int8_t sitepos[128];     // visible unit -> index among the rotated sites, or -1
+  __device__ __forceinline__ double value(int64_t row, int j) const {
+    const int64_t b = row >> S;
+    const int t = sitepos[j];
+    if (t < 0) return samples[b * N + j];
+    const uint32_t i = (uint32_t)(row & (((int64_t)1 << S) - 1));
+    return ((i >> (S - 1 - t)) & 1u) ? 1.0 : 0.0;
+  }
+};
+
+// Where the rows of a reduced-gradient pass come from, and how they are weighted.
+enum { ROWS_EXPLICIT = 0, ROWS_ENUM = 1, ROWS_EXPANDED = 2 };
+struct RowSrc {
+  const double* v;       // ROWS_EXPLICIT: (rows, N)
+  uint64_t first;        // ROWS_ENUM: index of row 0; weight = exp(-E - logZ)
+  double logZ;
+  const double* vb;      // ROWS_ENUM: visible bias
+  Expansion ex;          // ROWS_EXPANDED
+  const double* wrow;    // ROWS_EXPANDED: per-row weight (multiplies p_h and v)
+  const double* aux;     // ROWS_EXPANDED: optional (rows, n_aux) features appended after p_h (already weighted)
+  int n_aux;
+};
+
+}  // namespace qcb

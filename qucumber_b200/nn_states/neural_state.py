@@ -1,0 +1,321 @@
+"""Host-side mirror of ``qucumber.nn_states.NeuralStateBase`` (reference:
+qucumber/nn_states/neural_state.py:30-636) driving the CUDA RBMs.
+
+The class keeps the reference's public surface (fit / sample / gradient / compute_batch_gradients /
+compute_exact_gradients / normalization / save / load ...) and control flow (shuffling, optimizer,
+callbacks), and routes every numeric step to libqucumber_b200.so:
+
+* negative phase of CD-k: one fused call (k Gibbs sweeps + gradient reduction, qcb_rbm_cdk_neg);
+* positive phase: qcb_rbm_grad_reduce (scaled by 1/batch in-kernel) or the fused rotated-basis
+  kernels, accumulated straight into the gradient vectors;
+* normalisation / exact gradients: index-generated enumeration (no Hilbert-space tensor).
+"""
+import abc
+from itertools import chain
+from math import ceil
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..hilbert import HilbertSpace
+from ..rng import next_seed
+from ..utils import cplx
+from ..utils.data import extract_refbasis_samples
+from ..utils.gradients_utils import vector_to_grads
+
+
+class _Callbacks:
+    """Minimal dispatcher for the reference's callback protocol (on_train_start, on_epoch_start,
+    on_batch_start, on_batch_end, on_epoch_end, on_train_end); any object implementing a subset of
+    those hooks — e.g. the reference's own CallbackBase subclasses — can be passed to fit()."""
+
+    HOOKS = ("on_train_start", "on_train_end", "on_epoch_start", "on_epoch_end", "on_batch_start", "on_batch_end")
+
+    def __init__(self, callbacks):
+        self.callbacks = list(callbacks or [])
+
+    def fire(self, hook, *args):
+        for cb in self.callbacks:
+            fn = getattr(cb, hook, None)
+            if fn is not None:
+                fn(*args)
+
+
+class NeuralStateBase(abc.ABC):
+    """Abstract base class for neural-network quantum states backed by CUDA RBMs."""
+
+    _stop_training = False
+
+    @property
+    def stop_training(self):
+        """If True, training stops at the end of the current batch/epoch (neural_state.py:33-50)."""
+        return self._stop_training
+
+    @stop_training.setter
+    def stop_training(self, new_val):
+        if isinstance(new_val, bool):
+            self._stop_training = new_val
+        else:
+            raise ValueError("stop_training must be a boolean value!")
+
+    @property
+    def max_size(self):
+        """Largest Hilbert space that generate_hilbert_space will materialise as a tensor."""
+        return 20
+
+    @property
+    @abc.abstractmethod
+    def networks(self):
+        """Names of the internal RBMs."""
+
+    @property
+    @abc.abstractmethod
+    def rbm_am(self):
+        """The RBM that models the amplitude."""
+
+    @property
+    @abc.abstractmethod
+    def device(self):
+        """The device the model lives on."""
+
+    def reinitialize_parameters(self):
+        for net in self.networks:
+            getattr(self, net).initialize_parameters()
+
+    def __getattr__(self, attr):
+        return getattr(self.rbm_am, attr)
+
+    # ---- probabilities, sampling, enumeration -------------------------------------------------
+    def probability(self, v, Z=1.0):
+        """exp(-E(v)) / Z in the computational basis (neural_state.py:90-105)."""
+        v = v.to(device=self.device, dtype=torch.double)
+        return (-self.rbm_am.effective_energy(v)).exp() / Z
+
+    def sample(self, k, num_samples=1, initial_state=None, overwrite=False):
+        """k block-Gibbs sweeps from a random (or given) state (neural_state.py:107-131)."""
+        if initial_state is None:
+            dist = torch.distributions.Bernoulli(probs=0.5)
+            initial_state = dist.sample(torch.Size((num_samples, self.num_visible))).to(device=self.device, dtype=torch.double)
+        return self.rbm_am.gibbs_steps(k, initial_state, overwrite=overwrite)
+
+    def subspace_vector(self, num, size=None, device=None):
+        """Basis state number ``num`` (MSB first) as a vector (neural_state.py:133-154)."""
+        device = device if device is not None else self.device
+        size = size if size else self.num_visible
+        bits = [(num >> (size - 1 - j)) & 1 for j in range(size)]
+        return torch.tensor(bits, dtype=torch.double, device=device)
+
+    def generate_hilbert_space(self, size=None, device=None):
+        """All 2^size basis states, row r = binary digits of r, column 0 most significant
+        (neural_state.py:156-176). Raises ValueError above ``max_size`` like the reference; use
+        :meth:`hilbert_space` for a lazy, size-unlimited handle the CUDA kernels understand."""
+        device = device if device is not None else self.device
+        size = size if size else self.rbm_am.num_visible
+        if size > self.max_size:
+            raise ValueError("Size of the Hilbert space is too large!")
+        return HilbertSpace(size, device).tensor()
+
+    def hilbert_space(self):
+        """Lazy handle on the full visible space: accepted wherever a ``space`` tensor is."""
+        return HilbertSpace(self.rbm_am.num_visible, self.device)
+
+    def normalization(self, space=None):
+        """Partition function / trace of the unnormalised state (neural_state.py:178-197)."""
+        return self.rbm_am.partition(space)
+
+    def compute_normalization(self, space=None):
+        return self.normalization(space)
+
+    # ---- checkpointing (same file format as the reference) -------------------------------------
+    def save(self, location, metadata=None):
+        """torch.save of {net: state_dict, **metadata} (neural_state.py:199-226)."""
+        metadata = dict(metadata) if metadata else {}
+        if hasattr(self, "unitary_dict"):
+            if "unitary_dict" in metadata:
+                raise ValueError("Invalid key in metadata; unitary_dict cannot be a key!")
+            metadata["unitary_dict"] = self.unitary_dict
+        for net in self.networks:
+            if net in metadata:
+                raise ValueError(f"Invalid key in metadata; '{net}' cannot be a key!")
+        data = {net: getattr(self, net).state_dict() for net in self.networks}
+        data.update(**metadata)
+        torch.save(data, location)
+
+    def load(self, location):
+        """Load parameters saved by this class or by stock QuCumber (neural_state.py:228-246)."""
+        state_dict = torch.load(location, map_location=self.device, weights_only=False)
+        for net in self.networks:
+            getattr(self, net).load_state_dict(state_dict[net])
+        if hasattr(self, "unitary_dict") and "unitary_dict" in state_dict:
+            self.unitary_dict = state_dict["unitary_dict"]
+
+    @abc.abstractmethod
+    def importance_sampling_numerator(self, vp, v):
+        """Numerator of the importance-sampling weight of vp w.r.t. v."""
+
+    @abc.abstractmethod
+    def importance_sampling_denominator(self, v):
+        """Denominator of the importance-sampling weight."""
+
+    def importance_sampling_weight(self, vp, v):
+        return cplx.elementwise_division(self.importance_sampling_numerator(vp, v), self.importance_sampling_denominator(v))
+
+    # ---- gradients ------------------------------------------------------------------------------
+    def _accumulate_plain_gradient(self, rbm, samples, scale, g):
+        """g += scale * sum_rows grad E(row) with one reduction kernel."""
+        lib = _lib.load()
+        args, keep = rbm._param_args()
+        rows = samples.contiguous()
+        na = getattr(rbm, "num_aux", 0)
+        ws = _lib.workspace(rows.device, lib.qcb_workspace_bytes(_lib.OP_GRAD_REDUCE, rbm.num_visible, rbm.num_hidden, na, rows.shape[0]))
+        _lib.check(lib.qcb_rbm_grad_reduce(*args, _lib.ptr(rows), rows.shape[0], float(scale), _lib.ptr(g), 1, _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr(rows.device)), "qcb_rbm_grad_reduce")
+
+    def _accumulate_rotated_gradient(self, basis, samples, g_am, g_ph):
+        """Subclasses with measurement bases accumulate the rotated-basis gradient of ``samples``."""
+        raise NotImplementedError
+
+    def gradient(self, samples, bases=None):
+        """Summed gradients of a batch measured in the given bases (neural_state.py:326-369)."""
+        samples = samples.to(device=self.device, dtype=torch.double)
+        grad = [torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device) for net in self.networks]
+        if bases is None:
+            s2 = samples.unsqueeze(0) if samples.dim() < 2 else samples
+            self._accumulate_plain_gradient(self.rbm_am, s2, 1.0, grad[0])
+            return grad
+        if samples.dim() < 2:
+            samples = samples.unsqueeze(0)
+            bases = np.array(list(bases)).reshape(1, -1)
+        unique_bases, indices = np.unique(bases, axis=0, return_inverse=True)
+        indices = torch.as_tensor(np.asarray(indices).reshape(-1), device=samples.device)
+        for i in range(unique_bases.shape[0]):
+            basis = unique_bases[i, :]
+            sub = samples[indices == i, :]
+            if np.any(basis != "Z"):
+                self._accumulate_rotated_gradient(basis, sub, grad[0], grad[1])
+            else:
+                self._accumulate_plain_gradient(self.rbm_am, sub, 1.0, grad[0])
+        return grad
+
+    def positive_phase_gradients(self, samples_batch, bases_batch=None):
+        """Data-driven part of the gradient, averaged over the batch (neural_state.py:371-384)."""
+        grad = self.gradient(samples_batch, bases=bases_batch)
+        return [gr / float(samples_batch.shape[0]) for gr in grad]
+
+    def compute_exact_gradients(self, samples_batch, space=None, bases_batch=None):
+        """Positive phase minus the exact negative phase sum_sigma p(sigma) grad E(sigma)
+        (neural_state.py:386-415); the sum runs over index-generated states on the GPU."""
+        grad = self.positive_phase_gradients(samples_batch, bases_batch=bases_batch)
+        rbm = self.rbm_am
+        if space is not None and not isinstance(space, HilbertSpace) and space.shape[0] != (1 << rbm.num_visible):
+            probs = self.probability(space, Z=1.0)
+            probs = probs / probs.sum()
+            all_grads = rbm.effective_energy_gradient(space, reduce=False)
+            grad[0] -= torch.mv(all_grads.t(), probs)
+            return grad
+        lib = _lib.load()
+        args, keep = rbm._param_args()
+        out2 = rbm.log_partition()
+        logZ = float(out2[0] + out2[1].log())
+        na = getattr(rbm, "num_aux", 0)
+        count = 1 << rbm.num_visible
+        neg = torch.zeros(rbm.num_pars, dtype=torch.double, device=self.device)
+        out8 = torch.empty(8, dtype=torch.double, device=self.device)
+        ws = _lib.workspace(self.device, lib.qcb_workspace_bytes(_lib.OP_EXACT_STATS, rbm.num_visible, rbm.num_hidden, na, count))
+        _lib.check(lib.qcb_rbm_exact_stats_range(*args, 0, count, logZ, None, None, _lib.ptr(out8), _lib.ptr(neg), _lib.ptr(ws),
+                                                 ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_exact_stats_range")
+        grad[0] -= neg
+        return grad
+
+    def compute_batch_gradients(self, k, samples_batch, neg_batch, bases_batch=None):
+        """CD-k gradient of one batch (neural_state.py:417-447): positive phase from the data, negative
+        phase from k Gibbs sweeps started at ``neg_batch`` — Gibbs and the gradient of v_k are one
+        fused call, v_k never round-trips through Python."""
+        grad = self.positive_phase_gradients(samples_batch, bases_batch=bases_batch)
+        rbm = self.rbm_am
+        lib = _lib.load()
+        args, keep = rbm._param_args()
+        vk = neg_batch.to(device=self.device, dtype=torch.double).clone().contiguous()
+        C = vk.shape[0]
+        na = getattr(rbm, "num_aux", 0)
+        ws = _lib.workspace(self.device, lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, rbm.num_visible, rbm.num_hidden, na, C))
+        _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, int(k), next_seed(), 0, 0, None, -1.0 / float(C), _lib.ptr(grad[0]),
+                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_cdk_neg")
+        return grad
+
+    # ---- training loop --------------------------------------------------------------------------
+    def _shuffle_data(self, pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples):
+        """Per-epoch batching (neural_state.py:449-498): positive batches are a permutation of the
+        data; negative batches reuse it when the sizes match, otherwise they are drawn with
+        replacement (from the all-Z samples when bases are given)."""
+        pos_perm = torch.randperm(train_samples.shape[0])
+        pos = train_samples[pos_perm]
+        if input_bases is None:
+            if neg_batch_size == pos_batch_size:
+                neg_perm = pos_perm
+            else:
+                neg_perm = torch.randint(train_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long)
+            neg = train_samples[neg_perm]
+        else:
+            neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long)
+            neg = z_samples[neg_perm]
+        pos_batches = [pos[s:s + pos_batch_size] for s in range(0, len(pos), pos_batch_size)]
+        neg_batches = [neg[s:s + neg_batch_size] for s in range(0, len(neg), neg_batch_size)]
+        if input_bases is not None:
+            pos_bases = input_bases[pos_perm]
+            bases_batches = [pos_bases[s:s + pos_batch_size] for s in range(0, len(train_samples), pos_batch_size)]
+            return zip(pos_batches, neg_batches, bases_batches)
+        return zip(pos_batches, neg_batches)
+
+    def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1e-3, input_bases=None, progbar=False,
+            starting_epoch=1, time=False, callbacks=None, optimizer=torch.optim.SGD, optimizer_args=None, scheduler=None,
+            scheduler_args=None, **kwargs):
+        """Train with contrastive divergence (neural_state.py:500-636). Same arguments and hook
+        order as the reference; ``progbar`` accepts True/"notebook" when tqdm is installed."""
+        if self.stop_training:
+            return
+        cbs = _Callbacks(callbacks)
+        if time:
+            from ..callbacks import Timer
+
+            cbs.callbacks.append(Timer())
+        neg_batch_size = neg_batch_size if neg_batch_size else pos_batch_size
+        if isinstance(data, torch.Tensor):
+            train_samples = data.clone().detach().to(device=self.device, dtype=torch.double)
+        else:
+            train_samples = torch.tensor(data, device=self.device, dtype=torch.double)
+        all_params = list(chain(*[getattr(self, net).parameters() for net in self.networks]))
+        optimizer = optimizer(all_params, lr=lr, **(optimizer_args or {}))
+        if scheduler is not None:
+            scheduler = scheduler(optimizer, **(scheduler_args or {}))
+        z_samples = None
+        if input_bases is not None:
+            z_samples = extract_refbasis_samples(train_samples, input_bases).to(device=self.device)
+
+        cbs.fire("on_train_start", self)
+        num_batches = ceil(train_samples.shape[0] / pos_batch_size)
+        epoch_iter = range(starting_epoch, epochs + 1)
+        if progbar:
+            from tqdm import tqdm, tqdm_notebook
+
+            epoch_iter = (tqdm_notebook if progbar == "notebook" else tqdm)(epoch_iter, desc="Epochs ")
+        for ep in epoch_iter:
+            batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
+            cbs.fire("on_epoch_start", self, ep)
+            for b, batch in enumerate(batches):
+                cbs.fire("on_batch_start", self, ep, b)
+                all_grads = self.compute_batch_gradients(k, *batch)
+                optimizer.zero_grad()
+                for i, net in enumerate(self.networks):
+                    vector_to_grads(all_grads[i], getattr(self, net).parameters())
+                optimizer.step()
+                cbs.fire("on_batch_end", self, ep, b)
+                if self.stop_training:
+                    break
+            if scheduler is not None:
+                scheduler.step()
+            cbs.fire("on_epoch_end", self, ep)
+            if self.stop_training:
+                break
+        cbs.fire("on_train_end", self)

@@ -1,0 +1,151 @@
+"""Exact-enumeration metrics (reference: qucumber/utils/training_statistics.py): fidelity, KL and NLL.
+
+For a PositiveWaveFunction measured in the computational basis, fidelity and KL are ONE
+enumeration pass on the GPU (qcb_rbm_exact_stats_range): basis states are generated from their
+index, exp(-E) is normalised by the log-partition function from a first pass, and the overlap
+and both KL sums come back as five numbers. The other cases (bases, density matrices) follow the
+reference's structure on top of the CUDA-backed state classes.
+"""
+import numpy as np
+import torch
+from torch.distributions.utils import probs_to_logits
+
+from .. import _lib
+from ..hilbert import HilbertSpace
+from . import cplx
+from .unitaries import rotate_psi, rotate_psi_inner_prod, rotate_rho_probs
+
+
+def _is_full_space(nn_state, space):
+    return space is None or isinstance(space, HilbertSpace) or space.shape[0] == (1 << nn_state.num_visible)
+
+
+def _positive_stats(nn_state, target):
+    """(logZ, out8) for a PositiveWaveFunction over the full space; target is (2, 2^N) or None."""
+    from ..nn_states import PositiveWaveFunction
+
+    assert isinstance(nn_state, PositiveWaveFunction)
+    rbm = nn_state.rbm_am
+    lib = _lib.load()
+    out2 = rbm.log_partition()
+    logZ = float(out2[0] + out2[1].log())
+    args, keep = rbm._param_args()
+    count = 1 << rbm.num_visible
+    t_re = t_im = None
+    if target is not None:
+        target = target.to(device=nn_state.device, dtype=torch.double)
+        t_re, t_im = target[0].contiguous(), target[1].contiguous()
+    out8 = torch.empty(8, dtype=torch.double, device=nn_state.device)
+    ws = _lib.workspace(nn_state.device, lib.qcb_workspace_bytes(_lib.OP_EXACT_STATS, rbm.num_visible, rbm.num_hidden, 0, count))
+    _lib.check(lib.qcb_rbm_exact_stats_range(*args, 0, count, logZ, _lib.ptr(t_re), _lib.ptr(t_im), _lib.ptr(out8), None,
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(nn_state.device)),
+               "qcb_rbm_exact_stats_range")
+    return logZ, out8
+
+
+def fidelity(nn_state, target, space=None, **kwargs):
+    """|<target|psi>|^2 for pure states; (tr sqrt(sqrt(rho) sigma sqrt(rho)))^2 for mixed states
+    (training_statistics.py:27-76)."""
+    from ..nn_states import PositiveWaveFunction, WaveFunctionBase
+
+    if "target_psi" in kwargs or "target_rho" in kwargs:
+        target = kwargs.get("target_psi", kwargs.get("target_rho"))
+    target = target.to(nn_state.device)
+    if isinstance(nn_state, PositiveWaveFunction) and _is_full_space(nn_state, space):
+        assert target.dim() == 2, "target must be a complex vector!"
+        _, out8 = _positive_stats(nn_state, target)
+        o = out8.cpu()
+        return float(o[0] ** 2 + o[1] ** 2)
+    space = space if space is not None else nn_state.generate_hilbert_space()
+    if isinstance(space, HilbertSpace):
+        space = space.tensor(device=nn_state.device)
+    Z = nn_state.normalization(space)
+    if isinstance(nn_state, WaveFunctionBase):
+        assert target.dim() == 2, "target must be a complex vector!"
+        psi = nn_state.psi(space) / Z.sqrt()
+        F = cplx.inner_prod(target, psi)
+        return cplx.absolute_value(F).pow_(2).item()
+    assert target.dim() == 3, "target must be a complex matrix!"
+    rho = nn_state.rho(space, space) / Z
+    prod = np.matmul(cplx.numpy(target), cplx.numpy(rho))
+    eigvals = np.abs(np.linalg.eigvals(prod).real)  # the tiny negative ones are round-off
+    return float(np.sum(np.sqrt(eigvals)) ** 2)
+
+
+def NLL(nn_state, samples, space=None, sample_bases=None, **kwargs):
+    """Negative log-likelihood of the samples (training_statistics.py:79-128)."""
+    from ..nn_states import WaveFunctionBase
+
+    samples = samples.to(device=nn_state.device, dtype=torch.double)
+    Z = nn_state.normalization(space if not isinstance(space, HilbertSpace) else None)
+    if sample_bases is None:
+        return -torch.mean(probs_to_logits(nn_state.probability(samples, Z))).item()
+    total = 0.0
+    unique_bases, indices = np.unique(sample_bases, axis=0, return_inverse=True)
+    indices = torch.as_tensor(np.asarray(indices).reshape(-1), device=samples.device)
+    for i in range(unique_bases.shape[0]):
+        basis = unique_bases[i, :]
+        sub = samples[indices == i, :]
+        if np.any(basis != "Z"):
+            if isinstance(nn_state, WaveFunctionBase):
+                nn_probs = (cplx.absolute_value(rotate_psi_inner_prod(nn_state, basis, sub)) ** 2) / Z
+            else:
+                nn_probs = rotate_rho_probs(nn_state, basis, sub) / Z
+        else:
+            nn_probs = nn_state.probability(sub, Z)
+        total -= torch.sum(probs_to_logits(nn_probs))
+    return (total / float(len(samples))).item()
+
+
+def _single_basis_KL(target_probs, nn_probs):
+    return torch.sum(target_probs * probs_to_logits(target_probs)) - torch.sum(target_probs * probs_to_logits(nn_probs))
+
+
+def KL(nn_state, target, space=None, bases=None, **kwargs):
+    """KL divergence between target and model distributions, averaged over the given bases
+    (training_statistics.py:138-218)."""
+    from ..nn_states import PositiveWaveFunction, WaveFunctionBase
+
+    if "target_psi" in kwargs or "target_rho" in kwargs:
+        target = kwargs.get("target_psi", kwargs.get("target_rho"))
+    if bases is None and not isinstance(target, dict) and isinstance(nn_state, PositiveWaveFunction) and _is_full_space(nn_state, space):
+        _, out8 = _positive_stats(nn_state, target)
+        o = out8.cpu()
+        return float(o[2] - o[3])
+    space = space if space is not None else nn_state.generate_hilbert_space()
+    if isinstance(space, HilbertSpace):
+        space = space.tensor(device=nn_state.device)
+    Z = nn_state.normalization(space)
+    if isinstance(target, dict):
+        target = {k: v.to(nn_state.device) for k, v in target.items()}
+        if bases is None:
+            bases = list(target.keys())
+        else:
+            assert set(bases) == set(target.keys()), "Given bases must match the keys of the target_psi dictionary."
+    else:
+        target = target.to(nn_state.device)
+    kl = 0.0
+    if bases is None:
+        kl += _single_basis_KL(cplx.absolute_value(target) ** 2, nn_state.probability(space, Z))
+    elif isinstance(nn_state, WaveFunctionBase):
+        for basis in bases:
+            if isinstance(target, dict):
+                target_psi_r = target[basis]
+            else:
+                target_psi_r = rotate_psi(nn_state, basis, space, psi=target)
+            assert target_psi_r.dim() == 2, "target must be a complex vector!"
+            psi_r = rotate_psi(nn_state, basis, space)
+            kl += _single_basis_KL(cplx.absolute_value(target_psi_r) ** 2, (cplx.absolute_value(psi_r) ** 2) / Z)
+        kl /= float(len(bases))
+    else:
+        for basis in bases:
+            if isinstance(target, dict):
+                target_rho_r = target[basis]
+                assert target_rho_r.dim() == 3, "target must be a complex matrix!"
+                target_probs_r = torch.diagonal(cplx.real(target_rho_r))
+            else:
+                assert target.dim() == 3, "target must be a complex matrix!"
+                target_probs_r = rotate_rho_probs(nn_state, basis, space, rho=target)
+            kl += _single_basis_KL(target_probs_r, rotate_rho_probs(nn_state, basis, space) / Z)
+        kl /= float(len(bases))
+    return kl.item()

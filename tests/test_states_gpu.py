@@ -1,0 +1,344 @@
+"""GPU parity of PurificationRBM, the rotated-basis kernels and the nn_states mirror against the CPU
+oracle and the golden vectors produced by the reference (tests/golden/make_golden.py).
+Mirrors reference tests/test_grads.py, tests/test_models_misc.py:148-234,300-384."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, load_binary, load_purification, make_binary_params, make_purification_params, random_states
+from oracle import rbm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def split_bases(arr):
+    return np.array([list(str(s)) for s in arr])
+
+
+def cpx(t):
+    t = t.detach().cpu().numpy()
+    return t[0] + 1j * t[1]
+
+
+# ------------------------------------------------------------------------------- PurificationRBM
+@pytest.mark.parametrize("n,nh,na", [(5, 4, 3), (2, 2, 2), (10, 10, 10), (33, 20, 17), (64, 40, 24)])
+def test_purification_rbm(lib, cuda, n, nh, na):
+    from qucumber_b200 import PurificationRBM
+
+    W, U, b, c, d = make_purification_params(n, nh, na, 3)
+    rbm = load_purification(PurificationRBM(n, nh, na, gpu=True), W, U, b, c, d)
+    o = orc.PurificationRBMOracle(W, U, b, c, d)
+    v, vp = random_states(60, n, 4), random_states(60, n, 5)
+    h, a = random_states(60, nh, 6), random_states(60, na, 7)
+    tv, tvp, th, ta = (torch.tensor(x, device=cuda) for x in (v, vp, h, a))
+    assert_close(rbm.effective_energy(tv), o.effective_energy(v), what="energy")
+    assert_close(rbm.effective_energy(tv, ta), o.effective_energy(v, a), what="energy(v, a)")
+    assert_close(rbm.prob_h_given_v(tv), o.prob_h_given_v(v), what="prob_h")
+    assert_close(rbm.prob_a_given_v(tv), o.prob_a_given_v(v), what="prob_a")
+    assert_close(rbm.prob_v_given_ha(th, ta), o.prob_v_given_ha(h, a), what="prob_v")
+    assert_close(rbm.effective_energy_gradient(tv), o.effective_energy_gradient(v), what="grad reduce")
+    assert_close(rbm.effective_energy_gradient(tv[:7], reduce=False), o.effective_energy_gradient(v[:7], reduce=False), what="grad batch")
+    assert_close(rbm.mixing_term(tv), o.mixing_term(v), what="mixing_term")
+    assert_close(rbm.gamma(tv[:6], tvp[:5], eta=+1, expand=True), o.gamma(v[:6], vp[:5], +1, True), what="gamma+")
+    assert_close(rbm.gamma(tv, tvp, eta=-1, expand=False), o.gamma(v, vp, -1, False), rtol=1e-9, what="gamma- (differences of O(10) terms)")
+    assert_close(rbm.gamma_grad(tv[:4], tvp[:3], eta=+1, expand=True)[0], o.gamma_grad(v[:4], vp[:3], +1, True), what="gamma_grad")
+    k = 3
+    u = np.random.default_rng(8).random((k, 60, nh + na + n))
+    got = rbm.gibbs_steps(k, tv, uniforms=torch.tensor(u, device=cuda))
+    assert np.array_equal(got.cpu().numpy(), o.gibbs_steps_fed(k, v, u))
+    got = rbm.gibbs_steps(k, tv, seed=77, chain_id0=3, sweep0=2)
+    assert np.array_equal(got.cpu().numpy(), o.gibbs_steps_philox(k, v, 77, 3, 2))
+    if n <= 12:
+        assert_close(rbm.partition(), np.float64(o.partition()), what="Z")
+
+
+def test_purification_golden(lib, cuda):
+    from qucumber_b200 import PurificationRBM
+
+    g = gold("purification_rbm.npz")
+    rbm = load_purification(PurificationRBM(5, 4, 3, gpu=True), g["weights_W"], g["weights_U"], g["visible_bias"], g["hidden_bias"],
+                            g["aux_bias"])
+    tv = torch.tensor(g["v"], device=cuda)
+    assert_close(rbm.effective_energy(tv), g["energy"], what="energy")
+    assert_close(rbm.effective_energy_gradient(tv), g["grad_reduce"], what="grad")
+    got = rbm.gibbs_steps(int(g["gibbs_k"]), tv, uniforms=torch.tensor(g["gibbs_uniforms"], device=cuda))
+    assert np.array_equal(got.cpu().numpy(), g["gibbs_vk"])
+    assert_close(rbm.partition(), np.float64(g["Z"]), what="Z")
+
+
+# ------------------------------------------------------------------------------- golden BinaryRBM
+@pytest.mark.parametrize("name,n,nh", [("binary_rbm_tfim10.npz", 10, 10), ("binary_rbm_n64.npz", 64, 64), ("binary_rbm_n7.npz", 7, 12)])
+def test_binary_golden_seed_replay(lib, cuda, name, n, nh):
+    """The reference's gibbs_steps under torch.manual_seed, replayed bit-exactly from its uniforms."""
+    from qucumber_b200 import BinaryRBM
+
+    g = gold(name)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), g["weights"], g["visible_bias"], g["hidden_bias"])
+    tv = torch.tensor(g["states"], device=cuda)
+    assert_close(rbm.effective_energy(tv), g["energy"], what="energy")
+    got = rbm.gibbs_steps(int(g["gibbs_k"]), tv, uniforms=torch.tensor(g["gibbs_uniforms"], device=cuda))
+    assert np.array_equal(got.cpu().numpy(), g["gibbs_vk"])
+
+
+def test_positive_wavefunction_metrics_golden(lib, cuda):
+    """Z, fidelity, KL, NLL, exact gradients on the Tutorial-1 data from the reference's fixed initial
+    parameters (tests/data/test_training_init_pos_params.npz)."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("binary_rbm_tfim10.npz")
+    nn = PositiveWaveFunction(10, 10, gpu=True)
+    load_binary(nn.rbm_am, g["weights"], g["visible_bias"], g["hidden_bias"])
+    train = torch.tensor(np.unpackbits(g["train_packed"], axis=1)[:, :10].astype(np.float64), device=cuda)
+    target = torch.tensor(np.stack([g["target"].real, g["target"].imag]), device=cuda)
+    space = nn.generate_hilbert_space()
+    assert_close(nn.normalization(space), np.float64(g["Z"]), what="Z (explicit space)")
+    assert_close(nn.normalization(), np.float64(g["Z"]), what="Z (index enumeration)")
+    assert abs(ts.fidelity(nn, target, space) - g["fidelity"]) <= 1e-10 * g["fidelity"]
+    assert abs(ts.KL(nn, target, space) - g["KL"]) <= 1e-10 * g["KL"]
+    assert abs(ts.NLL(nn, train, space) - g["NLL"]) <= 1e-10 * g["NLL"]
+    assert_close(cpx(nn.psi(space)), g["psi_space"], what="psi")
+    assert_close(nn.gradient(train)[0], g["grad_reduce_train"], what="gradient(train)")
+    assert_close(nn.compute_exact_gradients(train[:100], space)[0], g["exact_grad_100"], what="exact gradient")
+    with pytest.raises(ValueError):
+        PositiveWaveFunction(21, 2, gpu=True).generate_hilbert_space()
+
+
+# ------------------------------------------------------------------------------- ComplexWaveFunction
+def _load_cwf(g, n, nh):
+    from qucumber_b200 import ComplexWaveFunction
+
+    nn = ComplexWaveFunction(n, nh, gpu=True)
+    load_binary(nn.rbm_am, g["am_weights"], g["am_visible_bias"], g["am_hidden_bias"])
+    load_binary(nn.rbm_ph, g["ph_weights"], g["ph_visible_bias"], g["ph_hidden_bias"])
+    return nn
+
+
+def test_complex_rotated_golden(lib, cuda):
+    from qucumber_b200.utils import unitaries as un
+
+    g = gold("complex_wavefunction.npz")
+    nn = _load_cwf(g, 5, 4)
+    basis = np.array(list(str(g["basis"])))
+    samples = torch.tensor(g["samples"], device=cuda)
+    assert_close(cpx(un.rotate_psi_inner_prod(nn, basis, samples)), g["Upsi"], what="Upsi (fused)")
+    Upsi, Upsi_v, v = un.rotate_psi_inner_prod(nn, basis, samples, include_extras=True)
+    assert np.array_equal(v.cpu().numpy(), g["v_expanded"])
+    assert_close(cpx(Upsi_v), g["Upsi_v"], what="Upsi_v")
+    rg = nn.rotated_gradient(basis, samples)
+    assert_close(rg[0], g["rot_grad_am"], what="rotated grad (amplitude)")
+    assert_close(rg[1], g["rot_grad_ph"], what="rotated grad (phase)")
+    gm = nn.gradient(samples, split_bases(g["bases_mixed"]))
+    assert_close(gm[0], g["grad_mixed_am"], what="gradient with mixed bases (amplitude)")
+    assert_close(gm[1], g["grad_mixed_ph"], what="gradient with mixed bases (phase)")
+    space = nn.generate_hilbert_space()
+    assert_close(cpx(nn.psi(space)), g["psi_space"], what="psi")
+    assert_close(cpx(un.rotate_psi(nn, basis, space)), g["psi_rotated_full"], what="rotate_psi")
+    assert_close(cpx(un.rotate_psi_inner_prod(nn, basis, space)), g["psi_rotated_full"], what="inner-prod over full space == rotate_psi")
+
+
+@pytest.mark.parametrize("n,nh,basis", [(6, 6, "XYZZYX"), (12, 9, "ZZXZZYZZXZZY"), (20, 20, "XYXYXYXYZZZZZZZZZZXY"), (3, 3, "XXX"), (9, 32, "ZZZZXZZZZ")])
+def test_complex_rotated_vs_oracle(lib, cuda, n, nh, basis):
+    from qucumber_b200 import ComplexWaveFunction
+
+    nn = ComplexWaveFunction(n, nh, gpu=True)
+    pa = make_binary_params(n, nh, 21, bias_scale=0.3)
+    pp = make_binary_params(n, nh, 22, bias_scale=0.3)
+    load_binary(nn.rbm_am, *pa)
+    load_binary(nn.rbm_ph, *pp)
+    am, ph = orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp)
+    samples = random_states(19, n, 23)
+    rg = nn.rotated_gradient(np.array(list(basis)), torch.tensor(samples, device=cuda))
+    ga, gp = orc.complex_rotated_gradient(am, ph, list(basis), samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude)")
+    assert_close(rg[1], gp, what="rotated grad (phase)")
+
+
+def test_complex_2qubits_reference_fixture(lib, cuda):
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("complex_2qubits.npz")
+    nn = _load_cwf(g, 2, 2)
+    bases = [str(b) for b in g["bases"]]
+    tdict = {b: torch.tensor(np.stack([g["target_by_basis"][i].real, g["target_by_basis"][i].imag]), device=cuda) for i, b in enumerate(bases)}
+    space = nn.generate_hilbert_space()
+    samples = torch.tensor(g["train_samples"], device=cuda)
+    tb = split_bases(g["train_bases"])
+    assert abs(ts.KL(nn, tdict, space, bases=bases) - g["KL"]) <= 1e-10 * abs(g["KL"])
+    assert abs(ts.NLL(nn, samples, space, sample_bases=tb) - g["NLL"]) <= 1e-10 * abs(g["NLL"])
+    ge = nn.compute_exact_gradients(samples, space, bases_batch=tb)
+    assert_close(ge[0], g["exact_grad_am"], what="exact grad (amplitude)")
+    assert_close(ge[1], g["exact_grad_ph"], what="exact grad (phase)")
+
+
+# ------------------------------------------------------------------------------- DensityMatrix
+def _load_dm(g, n, nh, na):
+    from qucumber_b200 import DensityMatrix
+
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    for tag, r in (("am", nn.rbm_am), ("ph", nn.rbm_ph)):
+        load_purification(r, g[f"{tag}_weights_W"], g[f"{tag}_weights_U"], g[f"{tag}_visible_bias"], g[f"{tag}_hidden_bias"],
+                          g[f"{tag}_aux_bias"])
+    return nn
+
+
+def test_density_matrix_golden(lib, cuda):
+    from qucumber_b200.utils import unitaries as un
+
+    g = gold("density_matrix.npz")
+    nn = _load_dm(g, 4, 3, 5)
+    basis = np.array(list(str(g["basis"])))
+    samples = torch.tensor(g["samples"], device=cuda)
+    space = nn.generate_hilbert_space()
+    assert_close(cpx(nn.pi(space, space)), g["pi_space"], what="pi")
+    rho = nn.rho(space, space)
+    assert_close(cpx(rho), g["rho_space"], what="rho")
+    Z = nn.normalization(space)
+    assert_close(Z, np.float64(g["Z"]), what="Z")
+    assert abs(float(torch.trace(rho[0]) / Z) - 1.0) <= 1e-12
+    assert_close(un.rotate_rho_probs(nn, basis, samples), g["UrhoU"], what="UrhoU (fused)")
+    _, UrhoU_v, _ = un.rotate_rho_probs(nn, basis, samples, include_extras=True)
+    assert_close(cpx(UrhoU_v), g["UrhoU_v"], what="UrhoU_v")
+    assert_close(cpx(nn.pi_grad(space[:5], space[3:7], phase=False, expand=True)), g["pi_grad_am"], what="pi_grad am")
+    assert_close(cpx(nn.pi_grad(space[:5], space[3:7], phase=True, expand=True)), g["pi_grad_ph"], what="pi_grad ph")
+    rg = nn.rotated_gradient(basis, samples)
+    assert_close(rg[0], g["rot_grad_am"], what="rotated grad (amplitude)")
+    assert_close(rg[1], g["rot_grad_ph"], what="rotated grad (phase)")
+    gm = nn.gradient(samples, split_bases(g["bases_mixed"]))
+    assert_close(gm[0], g["grad_mixed_am"], what="gradient with mixed bases (amplitude)")
+    assert_close(gm[1], g["grad_mixed_ph"], what="gradient with mixed bases (phase)")
+
+
+@pytest.mark.parametrize("n,nh,na,basis", [(6, 5, 4, "XZYXZZ"), (2, 2, 2, "XY"), (8, 8, 8, "ZZZYZZZX"), (5, 3, 16, "XXZYY")])
+def test_density_rotated_vs_oracle(lib, cuda, n, nh, na, basis):
+    from qucumber_b200 import DensityMatrix
+
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    pa = make_purification_params(n, nh, na, 31, bias_scale=0.3)
+    pp = make_purification_params(n, nh, na, 32, bias_scale=0.3)
+    load_purification(nn.rbm_am, *pa)
+    load_purification(nn.rbm_ph, *pp)
+    am, ph = orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp)
+    samples = random_states(11, n, 33)
+    rg = nn.rotated_gradient(np.array(list(basis)), torch.tensor(samples, device=cuda))
+    ga, gp = orc.dm_rotated_gradient(am, ph, list(basis), samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude)")
+    assert_close(rg[1], gp, rtol=1e-9, what="rotated grad (phase)")
+
+
+def test_density_2qubits_reference_fixture(lib, cuda):
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("density_2qubits.npz")
+    nn = _load_dm(g, 2, 2, 2)
+    bases = [str(b) for b in g["bases"]]
+    trho = torch.tensor(np.stack([g["target_rho"].real, g["target_rho"].imag]), device=cuda)
+    space = nn.generate_hilbert_space()
+    samples = torch.tensor(g["train_samples"], device=cuda)
+    tb = split_bases(g["train_bases"])
+    assert abs(ts.KL(nn, trho, space, bases=bases) - g["KL"]) <= 1e-10 * abs(g["KL"])
+    assert abs(ts.NLL(nn, samples, space, sample_bases=tb) - g["NLL"]) <= 1e-10 * abs(g["NLL"])
+    assert abs(ts.fidelity(nn, trho, space) - g["fidelity"]) <= 1e-9 * abs(g["fidelity"])
+    ge = nn.compute_exact_gradients(samples, space, bases_batch=tb)
+    assert_close(ge[0], g["exact_grad_am"], what="exact grad (amplitude)")
+    assert_close(ge[1], g["exact_grad_ph"], rtol=1e-9, what="exact grad (phase)")
+
+
+# ------------------------------------------------------------------------------- training loop
+def test_cd_gradient_matches_oracle_with_fed_uniforms(lib, cuda):
+    """compute_batch_gradients = positive phase / B - grad E(v_k) / C, v_k from the same draws."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, B, C, k = 10, 10, 100, 200, 10
+    W, b, c = make_binary_params(n, nh, 41)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = orc.BinaryRBMOracle(W, b, c)
+    pos, neg = random_states(B, n, 42), random_states(C, n, 43)
+    u = np.random.default_rng(44).random((k, C, nh + n))
+    want = o.effective_energy_gradient(pos) / B - o.effective_energy_gradient(o.gibbs_steps_fed(k, neg, u)) / C
+    g = rbm.effective_energy_gradient(torch.tensor(pos, device=cuda)) / B
+    lib_ = _lib.load()
+    args, keep = rbm._param_args()
+    vk = torch.tensor(neg, device=cuda)
+    ut = torch.tensor(u, device=cuda)
+    ws = _lib.workspace(cuda, lib_.qcb_workspace_bytes(_lib.OP_CDK_NEG, n, nh, 0, C))
+    _lib.check(lib_.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, k, 0, 0, 0, _lib.ptr(ut), -1.0 / C, _lib.ptr(g), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr(cuda)), "cdk_neg")
+    assert_close(g, want, what="CD-k gradient")
+
+
+def test_fit_trains_tutorial1_like(lib, cuda):
+    """5 epochs of CD-10 from the reference's fixed initial parameters reach the reference's own
+    statistical target (tests/test_training.py:165-166: fidelity 0.85 +- 0.02... one run: loose gate)."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("binary_rbm_tfim10.npz")
+    train = torch.tensor(np.unpackbits(g["train_packed"], axis=1)[:, :10].astype(np.float64))
+    target = torch.tensor(np.stack([g["target"].real, g["target"].imag]), device=cuda)
+    fids, kls = [], []
+    for run in range(4):
+        torch.manual_seed(1000 + run)
+        nn = PositiveWaveFunction(10, 10, gpu=True)
+        load_binary(nn.rbm_am, g["weights"], g["visible_bias"], g["hidden_bias"])
+        calls = []
+
+        class Hook:
+            def on_epoch_end(self, s, ep):
+                calls.append(ep)
+
+        nn.fit(train, epochs=5, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.1, callbacks=[Hook()])
+        assert calls == [1, 2, 3, 4, 5]
+        fids.append(ts.fidelity(nn, target))
+        kls.append(ts.KL(nn, target))
+    assert abs(np.mean(fids) - 0.85) < 0.03, fids
+    assert abs(np.mean(kls) - 0.29) < 0.03, kls
+
+
+def test_fit_complex_and_density_smoke(lib, cuda):
+    """Parameters move after one epoch with mixed bases (reference tests/test_training.py:40-70)."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+    g = gold("complex_2qubits.npz")
+    nn = ComplexWaveFunction(2, 2, gpu=True)
+    before = [p.clone() for p in nn.rbm_am.parameters()] + [p.clone() for p in nn.rbm_ph.parameters()]
+    nn.fit(torch.tensor(g["train_samples"]), epochs=1, pos_batch_size=50, neg_batch_size=10, k=5, lr=0.1,
+           input_bases=split_bases(g["train_bases"]))
+    after = list(nn.rbm_am.parameters()) + list(nn.rbm_ph.parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(after, before))
+    with pytest.raises(ValueError):
+        nn.fit(torch.tensor(g["train_samples"]), epochs=1)
+    gd = gold("density_2qubits.npz")
+    dm = DensityMatrix(2, 2, 2, gpu=True)
+    before = [p.clone() for p in dm.rbm_am.parameters()] + [p.clone() for p in dm.rbm_ph.parameters()]
+    dm.fit(torch.tensor(gd["train_samples"]), epochs=1, pos_batch_size=100, neg_batch_size=10, k=5, lr=0.1,
+           input_bases=split_bases(gd["train_bases"]))
+    after = list(dm.rbm_am.parameters()) + list(dm.rbm_ph.parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(after, before))
+    assert torch.equal(dm.rbm_ph.aux_bias, torch.zeros_like(dm.rbm_ph.aux_bias))  # never receives a gradient
+
+
+def test_save_load_sample_determinism(lib, cuda, tmp_path):
+    """save -> autoload -> identical sample(k=10) under the same seed (reference tests/test_models_misc.py:44-76)."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix, PositiveWaveFunction
+
+    for cls, args in ((PositiveWaveFunction, (10, 8)), (ComplexWaveFunction, (6, 6)), (DensityMatrix, (4, 4, 3))):
+        nn = cls(*args, gpu=True)
+        path = str(tmp_path / f"{cls.__name__}.pt")
+        nn.save(path)
+        nn2 = cls.autoload(path, gpu=True)
+        torch.manual_seed(5)
+        a = nn.sample(k=10, num_samples=64)
+        torch.manual_seed(5)
+        b = nn2.sample(k=10, num_samples=64)
+        assert torch.equal(a.to(torch.uint8), b.to(torch.uint8))
+        keys = set(torch.load(path, weights_only=False)["rbm_am"].keys())
+        assert keys == ({"weights", "visible_bias", "hidden_bias"} if cls is not DensityMatrix else
+                        {"weights_W", "weights_U", "visible_bias", "hidden_bias", "aux_bias"})
