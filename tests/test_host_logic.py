@@ -1,0 +1,170 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/qcb.h
+declares, the Python mirror's host logic, and the multi-rank combine logic on gloo (world_size 2)."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from qucumber_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "qcb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(qcb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in qcb.h but not exported"
+    assert lib.qcb_version() == 100
+    assert lib.qcb_workspace_bytes(_lib.OP_GIBBS, 64, 64, 0, 1) > 2 * 64 * 64 * 8
+    assert lib.qcb_workspace_bytes(_lib.OP_GIBBS, 200, 200, 0, 1) == 0  # unsupported shape
+
+
+def test_no_cpu_fallback():
+    from qucumber_b200 import BinaryRBM, PositiveWaveFunction, PurificationRBM
+
+    rbm = BinaryRBM(4, 3, gpu=False)
+    assert set(rbm.state_dict()) == {"weights", "visible_bias", "hidden_bias"} and rbm.num_pars == 4 * 3 + 4 + 3
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rbm.effective_energy(torch.zeros(2, 4, dtype=torch.double))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rbm.gibbs_steps(1, torch.zeros(2, 4, dtype=torch.double))
+    p = PurificationRBM(4, 3, 2, gpu=False)
+    assert set(p.state_dict()) == {"weights_W", "weights_U", "visible_bias", "hidden_bias", "aux_bias"}
+    assert p.num_pars == 4 * 3 + 4 * 2 + 4 + 3 + 2
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        PositiveWaveFunction(4, gpu=False).sample(k=1, num_samples=2)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "qucumber_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in text
+
+
+def test_host_helpers(tmp_path):
+    from qucumber_b200 import HilbertSpace
+    from qucumber_b200.utils import auto_unsqueeze_args, cplx, unitaries
+    from qucumber_b200.utils.data import extract_refbasis_samples, load_data
+    from qucumber_b200.utils.gradients_utils import vector_to_grads
+    from oracle.rbm_oracle import default_unitaries, hilbert_rows
+
+    assert np.array_equal(HilbertSpace(5).tensor().numpy(), hilbert_rows(5))
+    assert np.array_equal(HilbertSpace(6).tensor(9, 11).numpy(), hilbert_rows(6, 9, 11))
+
+    class M:
+        @auto_unsqueeze_args()
+        def f(self, v):
+            assert v.dim() == 2
+            return v * 2
+
+    assert M().f(torch.ones(3)).shape == (3,) and M().f(torch.ones(2, 3)).shape == (2, 3)
+    lin = torch.nn.Linear(3, 2)
+    vec = torch.arange(8.0)
+    vector_to_grads(vec, lin.parameters())
+    assert torch.equal(lin.weight.grad, vec[:6].view(2, 3)) and torch.equal(lin.bias.grad, vec[6:])
+    d = unitaries.create_dict()
+    for name, u in default_unitaries().items():
+        assert np.allclose(cplx.numpy(d[name]), u, atol=0, rtol=1e-15)
+    codes, names = unitaries.encode_basis(list("XZYZ"), d)
+    assert names[0] == "Z" and [names[c] for c in codes] == list("XZYZ")
+    a = cplx.make_complex(torch.tensor([1.0, 2.0]), torch.tensor([3.0, -1.0]))
+    b = cplx.make_complex(torch.tensor([0.5, -2.0]), torch.tensor([1.0, 4.0]))
+    assert np.allclose(cplx.numpy(cplx.scalar_mult(a, b)), cplx.numpy(a) * cplx.numpy(b))
+    assert np.allclose(cplx.numpy(cplx.inner_prod(a, b)), np.vdot(cplx.numpy(a), cplx.numpy(b)))
+    assert np.allclose(cplx.numpy(cplx.inverse(a)), 1 / cplx.numpy(a))
+    assert np.allclose(cplx.numpy(cplx.einsum("i,i->", a, b)), np.sum(cplx.numpy(a) * cplx.numpy(b)))
+    # full-space rotation == explicit Kronecker product
+    rng = np.random.default_rng(0)
+    psi = rng.standard_normal(8) + 1j * rng.standard_normal(8)
+    U = np.kron(np.kron(default_unitaries()["X"], default_unitaries()["Z"]), default_unitaries()["Y"])
+
+    class S:
+        unitary_dict = d
+        device = torch.device("cpu")
+
+    got = cplx.numpy(unitaries.rotate_psi(S(), "XZY", None, psi=cplx.make_complex(psi)))
+    assert np.allclose(got, U @ psi, atol=1e-14)
+    samples = tmp_path / "s.txt"
+    samples.write_text("1 0\n0 1\n1 1\n")
+    bases = tmp_path / "b.txt"
+    bases.write_text("Z Z\nX Z\nZ Z\n")
+    s, bs = load_data(str(samples), tr_bases_path=str(bases))
+    assert s.dtype == torch.double and s.shape == (3, 2) and bs.shape == (3, 2)
+    assert extract_refbasis_samples(s, bs).tolist() == [[1.0, 0.0], [1.0, 1.0]]
+
+
+def test_shard_range_covers_everything():
+    from qucumber_b200.distributed import shard_range
+
+    for total in (0, 1, 7, 1 << 20, (1 << 32) + 5):
+        for ws in (1, 2, 3, 8):
+            pieces = [shard_range(total, r, ws) for r in range(ws)]
+            assert pieces[0][0] == 0 and sum(c for _, c in pieces) == total
+            for (f0, c0), (f1, _) in zip(pieces[:-1], pieces[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in pieces) - min(c for _, c in pieces) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world_size, port, out_dir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_binary_params, random_states
+    from oracle.rbm_oracle import BinaryRBMOracle
+    from qucumber_b200 import distributed as qd
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world_size)
+    n, nh = 9, 6
+    W, b, c = make_binary_params(n, nh, 3)
+    orc = BinaryRBMOracle(W, b, c)
+    # exact enumeration: each rank's (m, s) over its index range, merged by all-gather
+    first, count = qd.shard_range(1 << n)
+    m, s = orc.logz_range(first, count)
+    logz = qd.combine_logz(torch.tensor([m, s], dtype=torch.double))
+    assert abs(float(logz) - orc.log_partition()) <= 1e-12 * abs(orc.log_partition())
+    # CD gradient: partial sums scaled by global sizes + one allreduce == full-batch gradient
+    pos = random_states(50, n, 4)
+    f, cnt = qd.shard_range(50)
+    part = torch.tensor(orc.effective_energy_gradient(pos[f:f + cnt]) / 50.0)
+    extra = torch.tensor([float(rank + 1)], dtype=torch.double)
+    qd.allreduce_sum_([part, extra])
+    assert np.allclose(part.numpy(), orc.effective_energy_gradient(pos) / 50.0, rtol=1e-13, atol=0)
+    assert float(extra) == sum(range(1, world_size + 1))
+    # Philox draws keyed by global chain id: shards concatenate to the single-process run
+    v0 = random_states(20, n, 5)
+    f, cnt = qd.shard_range(20)
+    mine = orc.gibbs_steps_philox(3, v0[f:f + cnt], seed=11, chain_id0=f)
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, mine)
+    assert np.array_equal(np.concatenate(gathered), orc.gibbs_steps_philox(3, v0, seed=11))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_combine_logic_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
