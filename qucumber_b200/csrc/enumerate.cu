@@ -65,7 +65,9 @@ __device__ __forceinline__ void stage_enum(const StackedParams& p, double* Wt, d
 
 // MODE 0: log-sum-exp partials.  MODE 1: statistics partials (5 sums) given logZ.
 template <int NHT, int MODE>
-__global__ void __launch_bounds__(ENUM_THREADS) enum_kernel(const EnumArgs a, double* __restrict__ partials) {
+__global__ void __launch_bounds__(ENUM_THREADS) enum_kernel(const EnumArgs a, double* __restrict__ partials,
+                                                            const int* __restrict__ flags) {
+  if (flags != nullptr && flags[0] != 0) return;  // the product-form kernel handles this launch
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Wt = reinterpret_cast<double*>(smem_raw);
   double* hb = Wt + (size_t)a.p.N * NHT;
@@ -170,6 +172,160 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_kernel(const EnumArgs a, do
   }
 }
 
+
+// ---- product-form fast path for log Z ------------------------------------------------------------
+// sum_v exp(-E(v)) = sum_v e^{b.v} prod_i f_i(theta_i),  f_i = theta_i > 20 ? e^{theta_i} : 1 + e^{theta_i}
+// (the branch reproduces torch's softplus threshold exactly).  t_i = e^{theta_i} is carried along
+// the Gray-code walk multiplicatively: a flip of visible unit j multiplies t_i by e^{+-W_ij} (tables
+// in shared memory, broadcast), so a state costs ~3 nh FP64 operations and no exp/log at all.
+// Each thread re-synchronises t_i from an exact evaluation at the start of its 2^m-state block
+// (m <= 12), which bounds the multiplicative drift to ~1e-13 relative.
+// Only used when a pre-pass proves that nothing can overflow or underflow (enum_bounds_kernel);
+// otherwise the log-domain kernel above runs.  flags[0] = eligible, flags[1] = no pre-activation can
+// exceed the softplus threshold (the select is skipped).
+__global__ void enum_bounds_kernel(StackedParams p, int* __restrict__ flags) {
+  __shared__ double red[4][32];
+  const int H = p.nhid(), N = p.N;
+  double sum_sp = 0.0, max_th = -INFINITY, max_abs = 0.0;
+  int bad = 0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    double hi = p.hbias(i), lo = hi;
+    for (int j = 0; j < N; ++j) {
+      const double w = p.w(i, j);
+      if (!(fabs(w) < 1e300)) bad = 1;
+      hi += fmax(w, 0.0);
+      lo += fmin(w, 0.0);
+    }
+    if (!(fabs(hi) < 1e300) || !(fabs(lo) < 1e300)) bad = 1;
+    sum_sp += fmax(hi, 0.0) + 0.6931471805599453;
+    max_th = fmax(max_th, hi);
+    max_abs = fmax(max_abs, fmax(fabs(hi), fabs(lo)));
+  }
+  double bpos = 0.0, bneg = 0.0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const double b = p.b[j];
+    if (!(fabs(b) < 1e300)) bad = 1;
+    bpos += fmax(b, 0.0);
+    bneg += fmin(b, 0.0);
+  }
+  sum_sp = warp_sum(sum_sp);
+  bpos = warp_sum(bpos);
+  bneg = warp_sum(bneg);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    max_th = fmax(max_th, __shfl_xor_sync(0xffffffffu, max_th, o));
+    max_abs = fmax(max_abs, __shfl_xor_sync(0xffffffffu, max_abs, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = sum_sp; red[1][warp] = bpos; red[2][warp] = bneg; red[3][warp] = max_th; }
+  __shared__ double red2[32];
+  __shared__ int redb[32];
+  if (lane == 0) { red2[warp] = max_abs; redb[warp] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0, bp = 0, bn = 0, mt = -INFINITY, ma = 0; int b = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      s += red[0][w]; bp += red[1][w]; bn += red[2][w]; mt = fmax(mt, red[3][w]); ma = fmax(ma, red2[w]); b |= redb[w];
+    }
+    const bool ok = !b && (s + bp < 650.0) && (bn > -650.0) && (ma < 650.0);
+    flags[0] = ok ? 1 : 0;
+    flags[1] = (mt <= 19.99) ? 1 : 0;
+  }
+}
+
+template <int NHT>
+__global__ void __launch_bounds__(ENUM_THREADS) enum_fast_kernel(const EnumArgs a, double* __restrict__ partials,
+                                                                 const int* __restrict__ flags) {
+  if (flags[0] == 0) return;
+  const bool no_thresh = flags[1] != 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = a.p.N, H = a.p.nhid();
+  double* Wt = reinterpret_cast<double*>(smem_raw);   // [N][NHT]      W_ij      (block re-synchronisation)
+  double* Ep = Wt + (size_t)N * NHT;                  // [N][NHT]  exp(+W_ij)
+  double* Em = Ep + (size_t)N * NHT;                  // [N][NHT]  exp(-W_ij)
+  double* hb = Em + (size_t)N * NHT;                  // [NHT]
+  double* vb = hb + NHT;                              // [N]
+  double* ebp = vb + round_up(N, 2);                  // [N] exp(+b_j)
+  double* ebm = ebp + round_up(N, 2);                 // [N] exp(-b_j)
+  double* red = ebm + round_up(N, 2);
+  stage_enum<NHT>(a.p, Wt, hb, vb);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
+    const int i = idx % NHT;
+    Ep[idx] = i < H ? exp(Wt[idx]) : 1.0;
+    Em[idx] = i < H ? exp(-Wt[idx]) : 1.0;
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) { ebp[j] = exp(vb[j]); ebm[j] = exp(-vb[j]); }
+  __syncthreads();
+
+  const uint64_t last = a.first + a.count;
+  const uint32_t steps = 1u << a.m;
+  const double E20 = 485165195.40979028;  // e^20
+  double S = 0.0;
+  for (uint64_t blk = (uint64_t)blockIdx.x * ENUM_THREADS + threadIdx.x; blk < a.nblocks;
+       blk += (uint64_t)gridDim.x * ENUM_THREADS) {
+    const uint64_t base = (a.block0 + blk) << a.m;
+    double t[NHT];
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) t[i] = hb[i];
+    double bv = 0.0;
+    for (int j = 0; j < N; ++j) {
+      if ((base >> (N - 1 - j)) & 1ull) {
+        const double* col = Wt + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) t[i] += col[i];
+        bv += vb[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) t[i] = i < H ? exp(t[i]) : 0.0;   // padded units contribute a factor 1
+    double eb = exp(bv);
+    for (uint32_t k = 0; k < steps; ++k) {
+      const uint64_t idx = base | (uint64_t)(k ^ (k >> 1));
+      double p0 = eb, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+      if (no_thresh) {
+#pragma unroll
+        for (int i = 0; i < NHT; i += 4) {
+          p0 *= 1.0 + t[i]; p1 *= 1.0 + t[i + 1]; p2 *= 1.0 + t[i + 2]; p3 *= 1.0 + t[i + 3];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NHT; i += 4) {
+          p0 *= t[i] > E20 ? t[i] : 1.0 + t[i];
+          p1 *= t[i + 1] > E20 ? t[i + 1] : 1.0 + t[i + 1];
+          p2 *= t[i + 2] > E20 ? t[i + 2] : 1.0 + t[i + 2];
+          p3 *= t[i + 3] > E20 ? t[i + 3] : 1.0 + t[i + 3];
+        }
+      }
+      const double P = (p0 * p1) * (p2 * p3);
+      if (idx >= a.first && idx < last) S += P;
+      if (k + 1 < steps) {
+        const uint32_t k1 = k + 1;
+        const int pbit = __ffs(k1) - 1;
+        const uint32_t g1 = k1 ^ (k1 >> 1);
+        const bool up = (g1 >> pbit) & 1u;
+        const int j = N - 1 - pbit;
+        const double* col = (up ? Ep : Em) + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) t[i] *= col[i];
+        eb *= up ? ebp[j] : ebm[j];
+      }
+    }
+  }
+  S = warp_sum(S);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = S;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < ENUM_THREADS / 32; ++w) tot += red[w];
+    // (m, s) pair in the common format: log-sum = m + log(s)
+    partials[2 * blockIdx.x] = tot > 0.0 ? 0.0 : -INFINITY;
+    partials[2 * blockIdx.x + 1] = tot;
+  }
+}
+
 __global__ void lse_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   LSE t{-INFINITY, 0.0};
@@ -219,19 +375,35 @@ static int pick_nht(int H) {
 
 static int enum_max_grid() { return sm_count() * 8; }
 
-size_t enum_workspace_bytes() { return align_up((size_t)enum_max_grid() * 8 * sizeof(double), 256); }
+static size_t enum_partials_bytes() { return align_up((size_t)enum_max_grid() * 8 * sizeof(double), 256); }
+
+size_t enum_workspace_bytes() { return enum_partials_bytes() + 256; }  // + flags
 
 template <int NHT, int MODE>
-static int launch_enum(const EnumArgs& a, double* partials, int* grid_out, cudaStream_t st) {
+static int launch_enum(const EnumArgs& a, double* partials, int* grid_out, cudaStream_t st, const int* flags = nullptr) {
   const size_t smem = ((size_t)a.p.N * NHT + NHT + round_up(a.p.N, 2) + 8 * (ENUM_THREADS / 32)) * sizeof(double);
   if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "enumeration: parameters do not fit in shared memory");
   QCB_CUDA(cudaFuncSetAttribute(enum_kernel<NHT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const uint64_t need = (a.nblocks + ENUM_THREADS - 1) / ENUM_THREADS;
   const uint64_t cap = (uint64_t)enum_max_grid();
   const int grid = (int)(need < cap ? need : cap);
-  enum_kernel<NHT, MODE><<<grid, ENUM_THREADS, smem, st>>>(a, partials);
+  enum_kernel<NHT, MODE><<<grid, ENUM_THREADS, smem, st>>>(a, partials, flags);
   QCB_LAUNCH_CHECK();
   *grid_out = grid;
+  return QCB_OK;
+}
+
+template <int NHT>
+static int launch_enum_fast(const EnumArgs& a, double* partials, const int* flags, cudaStream_t st) {
+  const int N = a.p.N;
+  const size_t smem = ((size_t)3 * N * NHT + NHT + 3 * round_up(N, 2) + 8) * sizeof(double);
+  if (smem > 200 * 1024) return QCB_OK;  // the general kernel covers it (flags stay as computed; see caller)
+  QCB_CUDA(cudaFuncSetAttribute(enum_fast_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const uint64_t need = (a.nblocks + ENUM_THREADS - 1) / ENUM_THREADS;
+  const uint64_t cap = (uint64_t)enum_max_grid();
+  const int grid = (int)(need < cap ? need : cap);
+  enum_fast_kernel<NHT><<<grid, ENUM_THREADS, smem, st>>>(a, partials, flags);
+  QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
 
@@ -272,9 +444,32 @@ int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, doubl
   if (rc != QCB_OK) return rc;
   if (ws == nullptr || ws_bytes < enum_workspace_bytes()) return fail(QCB_ERR_BAD_ARG, "logz_range: workspace too small");
   double* partials = reinterpret_cast<double*>(ws);
+  int* flags = reinterpret_cast<int*>(static_cast<char*>(ws) + enum_partials_bytes());
   int grid = 0;
   if (count > 0) {
-    QCB_ENUM_DISPATCH(0, a, partials, &grid, st)
+    const int nht = pick_nht(p.nhid());
+    const bool fast_fits = ((size_t)3 * p.N * nht + nht + 3 * round_up(p.N, 2) + 8) * sizeof(double) <= 200 * 1024;
+    const int* gflags = nullptr;
+    if (fast_fits) {
+      // pre-pass decides on the device (no host sync) whether the product form is safe; exactly one of
+      // the two enumeration kernels then does the work, the other returns at once
+      enum_bounds_kernel<<<1, 128, 0, st>>>(p, flags);
+      QCB_LAUNCH_CHECK();
+      switch (nht) {
+        case 8: rc = launch_enum_fast<8>(a, partials, flags, st); break;
+        case 16: rc = launch_enum_fast<16>(a, partials, flags, st); break;
+        case 32: rc = launch_enum_fast<32>(a, partials, flags, st); break;
+        default: rc = launch_enum_fast<64>(a, partials, flags, st); break;
+      }
+      if (rc != QCB_OK) return rc;
+      gflags = flags;
+    }
+    switch (nht) {
+      case 8: rc = launch_enum<8, 0>(a, partials, &grid, st, gflags); break;
+      case 16: rc = launch_enum<16, 0>(a, partials, &grid, st, gflags); break;
+      case 32: rc = launch_enum<32, 0>(a, partials, &grid, st, gflags); break;
+      default: rc = launch_enum<64, 0>(a, partials, &grid, st, gflags); break;
+    }
     if (rc != QCB_OK) return rc;
   }
   lse_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out2);

@@ -176,3 +176,27 @@ def test_partition(lib, cuda, n, nh):
     assert abs((m + np.log(s)) - want) <= 1e-10 * abs(want)
     empty = rbm.log_partition(5, 0).cpu().numpy()
     assert empty[1] == 0.0
+
+
+@pytest.mark.parametrize("case", ["plain", "threshold", "fallback", "wide"])
+def test_partition_kernel_paths(lib, cuda, case):
+    """log Z through the product-form kernel (with and without pre-activations above torch's softplus
+    threshold) and through the log-domain kernel it falls back to when the product could overflow."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh = (12, 12) if case != "wide" else (14, 40)
+    W, b, c = make_binary_params(n, nh, 71, bias_scale=0.5)
+    if case == "threshold":
+        c = c + np.where(np.arange(nh) % 3 == 0, 21.0, 0.0)
+    if case == "fallback":
+        W, b, c = W * 60.0, b * 60.0, c * 60.0
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    want = BinaryRBMOracle(W, b, c).log_partition()
+    out2 = rbm.log_partition().cpu().numpy()
+    got = out2[0] + np.log(out2[1])
+    assert abs(got - want) <= 1e-10 * abs(want), (case, got, want)
+    lo = rbm.log_partition(0, 1000).cpu().numpy()
+    hi = rbm.log_partition(1000, (1 << n) - 1000).cpu().numpy()
+    m = max(lo[0], hi[0])
+    both = m + np.log(lo[1] * np.exp(lo[0] - m) + hi[1] * np.exp(hi[0] - m))
+    assert abs(both - want) <= 1e-10 * abs(want)
