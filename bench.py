@@ -153,28 +153,99 @@ def run_reference(args):
 
 
 def extra_metrics(dev, lib_mod):
-    """Companion figures of the BASELINE metric string, measured outside the main timed region."""
-    from qucumber_b200 import BinaryRBM
+    """Companion figures of the BASELINE metric string (exact-Z states/s, TFIM N=10 epoch time) and the
+    CD-k training step at the benchmark shape, each measured outside the main timed region with the
+    reference's torch-CPU path timed beside it on a bounded sample."""
+    import time as _time
+
+    from oracle import cpu_path
+    from qucumber_b200 import BinaryRBM, PositiveWaveFunction
 
     out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        return best, res
+
+    # ---- exact Z (metric 2): states generated from their index, N = nh = 32 -> 2^32 states
     try:
-        n = 28
+        n = 32
         g = torch.Generator().manual_seed(1234)
+        Wn = torch.randn(n, n, dtype=torch.double, generator=g) / np.sqrt(n)
         rbm = BinaryRBM(n, n, gpu=True)
         with torch.no_grad():
-            rbm.weights.copy_(torch.randn(n, n, dtype=torch.double, generator=g) / np.sqrt(n))
-        rbm.log_partition(0, 1 << 20)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out2 = rbm.log_partition()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
+            rbm.weights.copy_(Wn)
+        ms, out2 = timed(lambda: rbm.log_partition())
+        n_cpu = 20  # the reference's max_size: the largest space it can enumerate at all
+        Wc = torch.randn(n_cpu, n_cpu, dtype=torch.double, generator=g) / np.sqrt(n_cpu)
+        zb, zc = torch.zeros(n_cpu, dtype=torch.double), torch.zeros(n_cpu, dtype=torch.double)
+        cpu_path.partition_cpu(Wc, zb, zc, n_cpu)
+        t0 = _time.perf_counter()
+        cpu_path.partition_cpu(Wc, zb, zc, n_cpu)
+        cpu_s = _time.perf_counter() - t0
         out["exact_z"] = {"N": n, "nh": n, "states_per_s": (1 << n) / (ms * 1e-3), "ms": ms,
-                          "logZ": float(out2[0] + out2[1].log())}
+                          "logZ": float(out2[0] + out2[1].log()),
+                          "fp64_ops_per_state": 3 * n + 3, "fp64_issue_frac_of_measured_peak":
+                              (1 << n) * (3 * n + 3) / (ms * 1e-3) / 18.4e12,
+                          "cpu_reference": {"N": n_cpu, "states_per_s": (1 << n_cpu) / cpu_s, "cores": torch.get_num_threads(),
+                                            "note": "generate_hilbert_space + partition at the reference's max_size=20"}}
     except Exception as exc:  # pragma: no cover - reported, not hidden
         out["exact_z"] = {"error": str(exc)}
+
+    # ---- epoch time TFIM N=10 (metric 3): Tutorial-1 data, pos 100 / neg 200, CD-10, SGD lr 0.01, no callbacks
+    try:
+        gpath = os.path.join(ROOT, "tests", "golden", "binary_rbm_tfim10.npz")
+        gold = np.load(gpath)
+        train = torch.tensor(np.unpackbits(gold["train_packed"], axis=1)[:, :10].astype(np.float64))
+        nn_state = PositiveWaveFunction(10, 10, gpu=True)
+        torch.manual_seed(0)
+        nn_state.fit(train, epochs=1, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+        torch.cuda.synchronize(dev)
+        epochs = 5
+        t0 = _time.perf_counter()
+        nn_state.fit(train, epochs=epochs, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+        torch.cuda.synchronize(dev)
+        ms_epoch = (_time.perf_counter() - t0) / epochs * 1e3
+        # the reference's CPU path for the same step: positive grad, k Gibbs sweeps, negative grad, SGD
+        Wc = torch.tensor(gold["weights"]); bc = torch.tensor(gold["visible_bias"]); cc = torch.tensor(gold["hidden_bias"])
+        torch.manual_seed(0)
+        steps = 100
+        t0 = _time.perf_counter()
+        for i in range(steps):
+            pos = train[(i * 100) % 9900:(i * 100) % 9900 + 100]
+            neg = train[(i * 37) % 9800:(i * 37) % 9800 + 200].clone()
+            gpos = cpu_path.grad_reduce_cpu(Wc, bc, cc, pos) / 100.0
+            vk = cpu_path.gibbs_steps_cpu(Wc, bc, cc, 10, neg)
+            gr = gpos - cpu_path.grad_reduce_cpu(Wc, bc, cc, vk) / 200.0
+            Wc = Wc - 0.01 * gr[:100].view(10, 10); bc = bc - 0.01 * gr[100:110]; cc = cc - 0.01 * gr[110:]
+        cpu_ms_epoch = (_time.perf_counter() - t0) / steps * 100 * 1e3
+        out["tfim_epoch"] = {"ms_per_epoch": ms_epoch, "steps_per_epoch": 100, "config": "N=nh=10, 10k samples, pos 100 / neg 200, CD-10, SGD",
+                             "cpu_reference_ms_per_epoch": cpu_ms_epoch, "cores": torch.get_num_threads(),
+                             "note": "wall clock through PositiveWaveFunction.fit (launch-latency bound)"}
+    except Exception as exc:  # pragma: no cover
+        out["tfim_epoch"] = {"error": str(exc)}
+
+    # ---- CD-k training step at the benchmark shape (config 4): pos grad + k sweeps + neg grad, C = B = 2^20
+    try:
+        W, b, c = synthetic_rbm()
+        nn_state = PositiveWaveFunction(N_VIS, N_HID, gpu=True)
+        with torch.no_grad():
+            nn_state.rbm_am.weights.copy_(W); nn_state.rbm_am.visible_bias.copy_(b); nn_state.rbm_am.hidden_bias.copy_(c)
+        data = initial_state(1 << 20, 0).to(dev)
+        ms, _ = timed(lambda: nn_state.compute_batch_gradients(10, data, data))
+        out["cdk_step"] = {"ms": ms, "pos_batch": 1 << 20, "chains": 1 << 20, "k": 10,
+                           "chain_sweeps_per_s": (1 << 20) * 10 / (ms * 1e-3)}
+    except Exception as exc:  # pragma: no cover
+        out["cdk_step"] = {"error": str(exc)}
     return out
 
 

@@ -263,13 +263,51 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
   }
   QCB_CUDA(cudaMemcpyAsync(db, b_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
   QCB_CUDA(cudaMemcpyAsync(dc, c_host, (size_t)nh * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (C > 0) QCB_CUDA(cudaMemcpyAsync(dv, v_host, vbytes, cudaMemcpyHostToDevice, st));
   StackedParams p;
   int rc = make_params(p, dW, na > 0 ? dU : nullptr, db, dc, na > 0 ? dd : nullptr, N, nh, na);
   if (rc != QCB_OK) return rc;
-  rc = run_gibbs(p, dv, C, k, seed, chain_id0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
-  if (rc != QCB_OK) return rc;
-  if (C > 0) QCB_CUDA(cudaMemcpyAsync(v_host, dv, vbytes, cudaMemcpyDeviceToHost, st));
+  // The chains are independent, so the call is pipelined in slices: slice i+1 travels host->device
+  // and slice i-1 device->host (PCIe is full duplex, two copy engines) while slice i is sampled.
+  // Philox draws are keyed by global chain id, so slicing does not change any sample.
+  static cudaStream_t s_in = nullptr, s_out = nullptr;
+  constexpr int MAX_SLICES = 16;
+  static cudaEvent_t ev_in[MAX_SLICES], ev_k[MAX_SLICES], ev_params, ev_done;
+  if (s_in == nullptr) {
+    QCB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    QCB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_SLICES; ++i) {
+      QCB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      QCB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+    }
+    QCB_CUDA(cudaEventCreateWithFlags(&ev_params, cudaEventDisableTiming));
+    QCB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+  }
+  if (C > 0) {
+    int nslices = (int)(vbytes / ((size_t)32 << 20));  // ~32 MiB per slice
+    nslices = nslices < 1 ? 1 : (nslices > MAX_SLICES ? MAX_SLICES : nslices);
+    const int64_t per = ((C + nslices - 1) / nslices + 15) / 16 * 16;
+    QCB_CUDA(cudaEventRecord(ev_params, st));
+    QCB_CUDA(cudaStreamWaitEvent(s_in, ev_params, 0));
+    int used = 0;
+    for (int i = 0; i < nslices; ++i) {
+      const int64_t c0 = (int64_t)i * per;
+      if (c0 >= C) break;
+      const int64_t cn = C - c0 < per ? C - c0 : per;
+      const size_t off = (size_t)c0 * N, nb = (size_t)cn * N * sizeof(double);
+      QCB_CUDA(cudaMemcpyAsync(dv + off, v_host + off, nb, cudaMemcpyHostToDevice, s_in));
+      QCB_CUDA(cudaEventRecord(ev_in[i], s_in));
+      QCB_CUDA(cudaStreamWaitEvent(st, ev_in[i], 0));
+      rc = run_gibbs(p, dv + off, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
+      if (rc != QCB_OK) return rc;
+      QCB_CUDA(cudaEventRecord(ev_k[i], st));
+      QCB_CUDA(cudaStreamWaitEvent(s_out, ev_k[i], 0));
+      QCB_CUDA(cudaMemcpyAsync(v_host + off, dv + off, nb, cudaMemcpyDeviceToHost, s_out));
+      used = i + 1;
+    }
+    (void)used;
+    QCB_CUDA(cudaEventRecord(ev_done, s_out));
+    QCB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
+  }
   QCB_CUDA(cudaStreamSynchronize(st));
   return QCB_OK;
 }

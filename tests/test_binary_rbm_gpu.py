@@ -200,3 +200,22 @@ def test_partition_kernel_paths(lib, cuda, case):
     m = max(lo[0], hi[0])
     both = m + np.log(lo[1] * np.exp(lo[0] - m) + hi[1] * np.exp(hi[0] - m))
     assert abs(both - want) <= 1e-10 * abs(want)
+
+
+def test_gibbs_host_buffers_pipelined(lib, cuda):
+    """The host-buffer entry point (sliced H2D / sample / D2H pipeline) returns exactly what the
+    device-resident call returns for the same seed."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, C, k = 64, 64, 300_001, 3
+    W, b, c = make_binary_params(n, nh, 81)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    v0 = torch.tensor(random_states(C, n, 82))
+    want = rbm.gibbs_steps(k, v0.to(cuda), seed=4242, chain_id0=7, sweep0=1).cpu()
+    vh = v0.clone().pin_memory()
+    Wh, bh, ch = (torch.tensor(x).contiguous().pin_memory() for x in (W, b, c))
+    nbytes = lib.qcb_gibbs_host_scratch_bytes(n, nh, 0, C)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=cuda)
+    _lib.check(lib.qcb_rbm_gibbs_host(_lib.ptr(Wh), None, _lib.ptr(bh), _lib.ptr(ch), None, n, nh, 0, _lib.ptr(vh), C, k, 4242, 7, 1,
+                                      _lib.ptr(scratch), nbytes, _lib.stream_ptr(cuda)), "qcb_rbm_gibbs_host")
+    assert torch.equal(vh, want)
