@@ -67,7 +67,8 @@ enum {
   QCB_OP_EXACT_STATS = 5,
   QCB_OP_CWF_ROTATED = 6,
   QCB_OP_DM_ROTATED = 7,
-  QCB_OP_CDK_NEG = 8
+  QCB_OP_CDK_NEG = 8,
+  QCB_OP_CD_STEP = 9
 };
 
 int qcb_version(void);
@@ -135,6 +136,14 @@ int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const dou
                     int N, int nh, int na, double* v, int64_t C, int k,
                     uint64_t seed, uint64_t chain_id0, uint64_t sweep0, const double* uniforms,
                     double scale, double* g, void* ws, size_t ws_bytes, void* stream);
+
+/* Whole CD-k gradient of one batch in one call (compute_batch_gradients, nn_states/neural_state.py:417-447):
+ * g = pos_scale * sum_rows grad E(pos) + neg_scale * sum_chains grad E(v_k), v_k = k Gibbs sweeps from
+ * neg (not modified; v_k lives in the workspace).  The reference uses pos_scale = 1/B, neg_scale = -1/C. */
+int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const double* c, const double* d,
+                    int N, int nh, int na, const double* pos, int64_t B, const double* neg, int64_t C, int k,
+                    uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale,
+                    double* g, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Exact enumeration ---------------------------------------------------------------
  * Basis states are generated from their index r in [first_state, first_state + count):

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqucumber_b200.so")
 
 QCB_OK = 0
-OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG = range(1, 9)
+OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP = range(1, 10)
 
 # name -> (restype, argtypes); must list every symbol declared in include/qcb.h
 _P = c_void_p
@@ -33,6 +33,8 @@ SIGNATURES = {
     "qcb_rbm_grad_batch": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "qcb_rbm_cdk_neg": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64, c_uint64,
                                 _P, c_double, _P, _P, c_size_t, _P]),
+    "qcb_rbm_cd_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_uint64, c_uint64,
+                                c_uint64, c_double, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_logz_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, _P, _P, c_size_t, _P]),
     "qcb_neg_logsumexp": (c_int, [_P, c_int64, _P, _P, c_size_t, _P]),
     "qcb_rbm_exact_stats_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, c_double, _P, _P,
@@ -82,8 +84,29 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+def _raw_stream(device):
+    """Raw cudaStream_t (int) of torch's current stream on ``device`` — the cheap C accessor, since the
+    training loop asks several times per step."""
+    idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def stream_ptr(device):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return c_void_p(_raw_stream(device))
+
+
+_ws_bytes_cache = {}
+
+
+def workspace_bytes(op, n, nh, na, rows):
+    """qcb_workspace_bytes with a host-side cache (the training loop asks the same question every step)."""
+    key = (op, n, nh, na, rows)
+    val = _ws_bytes_cache.get(key)
+    if val is None:
+        val = _ws_bytes_cache[key] = load().qcb_workspace_bytes(op, n, nh, na, rows)
+    return val
 
 
 _workspaces = {}
@@ -91,7 +114,7 @@ _workspaces = {}
 
 def workspace(device, nbytes):
     """A per-(device, stream) scratch tensor of at least nbytes (grown geometrically, owned by torch)."""
-    key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index if isinstance(device, torch.device) else torch.device(device).index, _raw_stream(device))
     buf = _workspaces.get(key)
     nbytes = max(int(nbytes), 256)
     if buf is None or buf.numel() < nbytes:

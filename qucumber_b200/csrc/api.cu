@@ -28,7 +28,7 @@ int fail(int code, const char* fmt, ...) {
 
 // implemented in the other translation units
 size_t gibbs_workspace_bytes(int N, int nhid);
-int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st);
 int run_linear(int mode, const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
@@ -90,6 +90,10 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
     }
     case QCB_OP_CWF_ROTATED: return cwf_workspace_bytes(N, nh, rows);
     case QCB_OP_DM_ROTATED: return dm_workspace_bytes(N, nh, na, rows);
+    case QCB_OP_CD_STEP: {
+      const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      return a + b + align_up((size_t)(rows > 0 ? rows : 0) * N * sizeof(double), 256);
+    }
     case QCB_OP_CDK_NEG: {
       const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b;
@@ -105,7 +109,7 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
   if (C < 0 || k < 0 || (C > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "gibbs: bad C/k/v");
-  return run_gibbs(p, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, (cudaStream_t)stream);
+  return run_gibbs(p, v, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
@@ -168,9 +172,32 @@ int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const dou
   const size_t gb = gibbs_workspace_bytes(N, nh + na);
   if (ws == nullptr || ws_bytes < gb + grad_reduce_workspace_bytes(N, nh + na, C))
     return fail(QCB_ERR_BAD_ARG, "cdk_neg: workspace too small");
-  rc = run_gibbs(p, v, C, k, seed, chain_id0, sweep0, uniforms, ws, gb, (cudaStream_t)stream);
+  rc = run_gibbs(p, v, v, C, k, seed, chain_id0, sweep0, uniforms, ws, gb, (cudaStream_t)stream);
   if (rc != QCB_OK) return rc;
   return run_grad_reduce(p, v, C, scale, g, 1, static_cast<char*>(ws) + gb, ws_bytes - gb, (cudaStream_t)stream);
+}
+
+int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                    int na, const double* pos, int64_t B, const double* neg, int64_t C, int k, uint64_t seed,
+                    uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale, double* g, void* ws,
+                    size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (B < 0 || C < 0 || k < 0 || g == nullptr || (B > 0 && pos == nullptr) || (C > 0 && neg == nullptr))
+    return fail(QCB_ERR_BAD_ARG, "cd_step: bad arguments");
+  const size_t gb = gibbs_workspace_bytes(N, nh + na);
+  const size_t rb = grad_reduce_workspace_bytes(N, nh + na, B > C ? B : C);
+  const size_t vb = align_up((size_t)C * N * sizeof(double), 256);
+  if (ws == nullptr || ws_bytes < gb + rb + vb) return fail(QCB_ERR_BAD_ARG, "cd_step: workspace too small");
+  char* base = static_cast<char*>(ws);
+  double* vk = reinterpret_cast<double*>(base + gb + rb);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_grad_reduce(p, pos, B, pos_scale, g, 0, base + gb, rb, st);
+  if (rc != QCB_OK) return rc;
+  rc = run_gibbs(p, neg, vk, C, k, seed, chain_id0, sweep0, nullptr, base, gb, st);
+  if (rc != QCB_OK) return rc;
+  return run_grad_reduce(p, vk, C, neg_scale, g, 1, base + gb, rb, st);
 }
 
 int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
@@ -297,7 +324,7 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
       QCB_CUDA(cudaMemcpyAsync(dv + off, v_host + off, nb, cudaMemcpyHostToDevice, s_in));
       QCB_CUDA(cudaEventRecord(ev_in[i], s_in));
       QCB_CUDA(cudaStreamWaitEvent(st, ev_in[i], 0));
-      rc = run_gibbs(p, dv + off, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
+      rc = run_gibbs(p, dv + off, dv + off, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
       if (rc != QCB_OK) return rc;
       QCB_CUDA(cudaEventRecord(ev_k[i], st));
       QCB_CUDA(cudaStreamWaitEvent(s_out, ev_k[i], 0));

@@ -33,7 +33,8 @@ constexpr int CHAINS_PER_WARP = 8;
 struct GibbsArgs {
   const double* image;   // packed fragment image in global memory (workspace)
   uint32_t image_bytes;
-  double* v;             // (C, N) in/out
+  const double* v_in;    // (C, N) initial states (may alias v)
+  double* v;             // (C, N) final states
   const double* uniforms;  // NULL or (k, C, nhid + N)
   int64_t C;
   int N, nhid;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(GIBBS_THREADS) gibbs_kernel(const GibbsArgs a)
   constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
   const int nunits = a.nhid + a.N;
   const uint32_t qv0 = (uint32_t)(round_up(a.nhid, 4) / 4);
-  const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v);
+  const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v_in);
 
   // every warp runs the same number of iterations (groups past the end are dummies) so that the
   // ping-pong partners stay in lock step; role-1 warps let their partners start first
@@ -352,7 +353,7 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
   return QCB_OK;
 }
 
-int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int nhid = p.nhid();
   const int HB = pick_blocks(nhid), VB = pick_blocks(p.N);
@@ -371,6 +372,7 @@ int run_gibbs(const StackedParams& p, double* v, int64_t C, int k, uint64_t seed
   GibbsArgs a;
   a.image = img;
   a.image_bytes = (uint32_t)(total * sizeof(double));
+  a.v_in = v_in;
   a.v = v;
   a.uniforms = uniforms;
   a.C = C;

@@ -228,19 +228,49 @@ class NeuralStateBase(abc.ABC):
         grad[0] -= neg
         return grad
 
+    _cd_seed = None   # Philox key of the current fit() call (None: draw a fresh key per call)
+    _cd_sweep = 0     # sweeps consumed under that key
+
+    def _next_cd_stream(self, k):
+        """(seed, sweep0) for the next k Gibbs sweeps: inside fit() one key serves the whole run and the
+        sweep counter advances, so no per-step host RNG call is needed; outside, a fresh key per call."""
+        if self._cd_seed is None:
+            return next_seed(), 0
+        sweep0 = self._cd_sweep
+        self._cd_sweep += int(k)
+        if self._cd_sweep >= (1 << 31):
+            self._cd_seed, self._cd_sweep = next_seed(), 0
+        return self._cd_seed, sweep0
+
     def compute_batch_gradients(self, k, samples_batch, neg_batch, bases_batch=None):
         """CD-k gradient of one batch (neural_state.py:417-447): positive phase from the data, negative
-        phase from k Gibbs sweeps started at ``neg_batch`` — Gibbs and the gradient of v_k are one
-        fused call, v_k never round-trips through Python."""
-        grad = self.positive_phase_gradients(samples_batch, bases_batch=bases_batch)
+        phase from k Gibbs sweeps started at ``neg_batch``. Without bases the whole thing is ONE call
+        (qcb_rbm_cd_step: gradient reduction, k fused sweeps, gradient reduction); v_k never leaves
+        the device workspace."""
         rbm = self.rbm_am
         lib = _lib.load()
-        args, keep = rbm._param_args()
-        vk = neg_batch.to(device=self.device, dtype=torch.double).clone().contiguous()
-        C = vk.shape[0]
         na = getattr(rbm, "num_aux", 0)
-        ws = _lib.workspace(self.device, lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, rbm.num_visible, rbm.num_hidden, na, C))
-        _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, int(k), next_seed(), 0, 0, None, -1.0 / float(C), _lib.ptr(grad[0]),
+        seed, sweep0 = self._next_cd_stream(k)
+        neg = neg_batch.to(device=self.device, dtype=torch.double).contiguous()
+        C = neg.shape[0]
+        if bases_batch is None:
+            pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
+            B = pos.shape[0]
+            args, keep = rbm._param_args()
+            g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
+            ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CD_STEP, rbm.num_visible, rbm.num_hidden, na, max(B, C)))
+            _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), B, _lib.ptr(neg), C, int(k), seed, 0, sweep0, 1.0 / float(B),
+                                           -1.0 / float(C), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)),
+                       "qcb_rbm_cd_step")
+            grad = [g]
+            for net in self.networks[1:]:
+                grad.append(torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device))
+            return grad
+        grad = self.positive_phase_gradients(samples_batch, bases_batch=bases_batch)
+        args, keep = rbm._param_args()
+        vk = neg.clone()
+        ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CDK_NEG, rbm.num_visible, rbm.num_hidden, na, C))
+        _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, int(k), seed, 0, sweep0, None, -1.0 / float(C), _lib.ptr(grad[0]),
                                        _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_cdk_neg")
         return grad
 
@@ -289,10 +319,18 @@ class NeuralStateBase(abc.ABC):
         optimizer = optimizer(all_params, lr=lr, **(optimizer_args or {}))
         if scheduler is not None:
             scheduler = scheduler(optimizer, **(scheduler_args or {}))
+        # plain SGD without callbacks (nobody can observe .grad or optimizer hooks): fused update path
+        pg = optimizer.param_groups
+        plain_sgd = (type(optimizer) is torch.optim.SGD and len(pg) == 1 and not cbs.callbacks and scheduler is None
+                     and pg[0].get("momentum", 0) == 0 and pg[0].get("weight_decay", 0) == 0
+                     and pg[0].get("dampening", 0) == 0 and not pg[0].get("nesterov", False)
+                     and not pg[0].get("maximize", False))
+        net_params = [list(getattr(self, net).parameters()) for net in self.networks]
         z_samples = None
         if input_bases is not None:
             z_samples = extract_refbasis_samples(train_samples, input_bases).to(device=self.device)
 
+        self._cd_seed, self._cd_sweep = next_seed(), 0
         cbs.fire("on_train_start", self)
         num_batches = ceil(train_samples.shape[0] / pos_batch_size)
         epoch_iter = range(starting_epoch, epochs + 1)
@@ -306,10 +344,21 @@ class NeuralStateBase(abc.ABC):
             for b, batch in enumerate(batches):
                 cbs.fire("on_batch_start", self, ep, b)
                 all_grads = self.compute_batch_gradients(k, *batch)
-                optimizer.zero_grad()
-                for i, net in enumerate(self.networks):
-                    vector_to_grads(all_grads[i], getattr(self, net).parameters())
-                optimizer.step()
+                if plain_sgd:
+                    # vanilla SGD (the reference's default optimizer): p -= lr * g as one fused multi-tensor
+                    # update on views of the flat gradient vectors; same arithmetic as optimizer.step()
+                    views = []
+                    for i, net in enumerate(self.networks):
+                        offset = 0
+                        for prm in net_params[i]:
+                            views.append(all_grads[i][offset:offset + prm.numel()].view(prm.size()))
+                            offset += prm.numel()
+                    torch._foreach_add_(all_params, views, alpha=-optimizer.param_groups[0]["lr"])
+                else:
+                    optimizer.zero_grad()
+                    for i, net in enumerate(self.networks):
+                        vector_to_grads(all_grads[i], getattr(self, net).parameters())
+                    optimizer.step()
                 cbs.fire("on_batch_end", self, ep, b)
                 if self.stop_training:
                     break
@@ -318,4 +367,5 @@ class NeuralStateBase(abc.ABC):
             cbs.fire("on_epoch_end", self, ep)
             if self.stop_training:
                 break
+        self._cd_seed = None
         cbs.fire("on_train_end", self)
