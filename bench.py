@@ -304,7 +304,10 @@ def run_ours(args):
     barrier()
     launches = lib.qcb_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    if os.environ.get("QCB_BENCH_DEBUG"):
+        print(f"[rank {rank}] local ms/step {ms_local / args.steps:.3f}", file=sys.stderr, flush=True)
+    ms_total = max_over_ranks(ms_local)
     ms_step = ms_total / args.steps
     value = world * C * k / (ms_step * 1e-3)
 
