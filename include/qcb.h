@@ -26,13 +26,19 @@
  *
  * Random numbers (used when `uniforms` is NULL)
  *  Philox4x32-10.  key = (seed low 32, seed high 32);
- *  counter = (chain id low 32, chain id high 32, sweep index, stream << 31 | slot / 4),
- *  word `slot % 4` of the output.  The 53-bit uniform of a unit is
- *      u = (hi * 2^21 + (lo >> 11)) * 2^-53,   hi from stream 0, lo from stream 1,
- *  the same grid {m * 2^-53} torch's CPU bernoulli uses.  Slots: hidden unit i -> i,
- *  auxiliary unit l -> nh + l, visible unit j -> roundup4(nh + na) + j.  Chain ids are
- *  chain_id0 + row, sweep indices sweep0 + s, so a run sharded over ranks or split into
- *  several calls draws exactly the same numbers as one call.  A unit is set when u < p.
+ *  counter = (chain id low 32, chain id high 32, sweep index, stream << 29 | q).
+ *  The hidden-like units form one layer [h; a] of nh + na units whose first call is q0 = 0; the
+ *  visible layer starts at q0 = 4 * ceil((nh + na) / 32).  Unit u of a layer uses call
+ *  q = q0 + 4 (u / 32) + (u % 16) / 4, output word u % 4 and 16-bit half (u / 16) % 2 of that word
+ *  (half 0 = high bits), so one call serves eight units.  Its 53-bit uniform is
+ *      u53 = (h16 * 2^37 + lo_a * 2^5 + (lo_b >> 27)) * 2^-53,
+ *  h16 from stream 0, lo_a from stream 1 + 2 half, lo_b from stream 2 + 2 half — the same grid
+ *  {m * 2^-53} torch's CPU bernoulli uses.  A unit is set when u53 < p.  The kernel decides from
+ *  h16 whenever that is already conclusive and evaluates the remaining bits only otherwise; the
+ *  outcome is always that of the full comparison.  Chain ids are chain_id0 + row and sweep
+ *  indices sweep0 + s, so a run sharded over ranks or split into several calls draws exactly the
+ *  same numbers as one call.  (qcb_bernoulli, the single-step sampler, uses slot s -> call s / 4,
+ *  word s % 4, u = (hi * 2^21 + (lo >> 11)) * 2^-53 with lo from counter word q | 2^31.)
  *
  * Fed uniforms (bit-exact replay of the reference under a given torch seed)
  *  uniforms is (k, C, nh + na + N): per sweep and chain the hidden block, the auxiliary

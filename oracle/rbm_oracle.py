@@ -92,17 +92,46 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def round_up4(n):
-    return (int(n) + 3) & ~3
+def layer_uniforms(seed, chain_ids, sweep, q0, count):
+    """53-bit uniforms of the `count` units of one layer for every chain in ``chain_ids`` at global
+    sweep index ``sweep`` — the convention of qcb_rbm_gibbs when no uniforms are fed (include/qcb.h):
+
+    unit u uses Philox call q = q0 + 4 (u // 32) + (u % 16) // 4, output word w = u % 4 and
+    half = (u // 16) % 2 of that word (half 0 = the high 16 bits). Counter = (chain id low 32,
+    chain id high 32, sweep, stream << 29 | q), key = the 64-bit seed split low/high, and
+        u53 = (h16 * 2^37 + lo_a * 2^5 + (lo_b >> 27)) * 2^-53
+    with h16 from stream 0, lo_a from stream 1 + 2 half and lo_b from stream 2 + 2 half."""
+    chain_ids = np.asarray(chain_ids, dtype=np.uint64)
+    u = np.arange(count, dtype=np.uint64)
+    q = (np.uint64(q0) + np.uint64(4) * (u // np.uint64(32)) + (u % np.uint64(16)) // np.uint64(4))[None, :]
+    w = (u % np.uint64(4)).astype(np.int64)
+    half = ((u // np.uint64(16)) % np.uint64(2))
+    c0 = (chain_ids & _MASK32)[:, None]
+    c1 = (chain_ids >> np.uint64(32))[:, None]
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+
+    def words(stream):
+        ctr = (np.asarray(stream, dtype=np.uint64) << np.uint64(29)) | q
+        out4 = np.stack(philox4x32_10(c0, c1, np.uint64(sweep), ctr, k0, k1), axis=-1)
+        sel = np.broadcast_to(w[None, :, None], out4.shape[:2] + (1,))
+        return np.take_along_axis(out4, sel, axis=-1)[..., 0].astype(np.uint64)
+
+    hi = words(np.zeros_like(half)[None, :])
+    la = words((np.uint64(1) + np.uint64(2) * half)[None, :])
+    lb = words((np.uint64(2) + np.uint64(2) * half)[None, :])
+    h16 = (hi >> (np.uint64(16) * (np.uint64(1) - half))[None, :]) & np.uint64(0xFFFF)
+    bits = (h16 << np.uint64(37)) | (la << np.uint64(5)) | (lb >> np.uint64(27))
+    return bits.astype(np.float64) * (2.0 ** -53)
+
+
+def visible_q0(nhid):
+    """First Philox call of the visible layer: the hidden-like layer occupies 4 calls per 32 units."""
+    return 4 * ((int(nhid) + 31) // 32)
 
 
 def philox_uniforms(seed, chain_ids, sweep, slot0, count):
-    """53-bit uniforms u = (hi * 2^21 + (lo >> 11)) * 2^-53 for unit slots [slot0, slot0+count) of
-    every chain in ``chain_ids`` at global sweep index ``sweep``.
-
-    Counter = (chain id low 32, chain id high 32, sweep, stream << 31 | slot // 4), key = the 64-bit
-    seed split low/high; the 32-bit word used is output word ``slot % 4``; ``hi`` comes from
-    stream 0 and ``lo`` from stream 1. Matches qcb_rbm_gibbs when no uniforms are fed."""
+    """Uniforms of qcb_bernoulli (single conditional steps): slot s uses call s // 4, word s % 4,
+    u = (hi * 2^21 + (lo >> 11)) * 2^-53 with hi from counter word q and lo from q | 2^31."""
     chain_ids = np.asarray(chain_ids, dtype=np.uint64)
     slots = np.arange(slot0, slot0 + count, dtype=np.uint64)
     q = (slots >> np.uint64(2))[None, :]
@@ -171,15 +200,14 @@ class BinaryRBMOracle:
         return v
 
     def gibbs_steps_philox(self, k, initial_state, seed, chain_id0=0, sweep0=0):
-        """Same sweeps with the kernel's own counter-based draws: hidden unit i uses slot i,
-        visible unit j uses slot round_up4(nh) + j."""
+        """Same sweeps with the kernel's own counter-based draws (layer_uniforms)."""
         v = np.array(initial_state, dtype=np.float64, copy=True).reshape(-1, self.n)
         ids = np.arange(chain_id0, chain_id0 + v.shape[0], dtype=np.uint64)
-        h4 = round_up4(self.nh)
+        qv = visible_q0(self.nh)
         for s in range(k):
-            uh = philox_uniforms(seed, ids, sweep0 + s, 0, self.nh)
+            uh = layer_uniforms(seed, ids, sweep0 + s, 0, self.nh)
             h = (uh < self.prob_h_given_v(v)).astype(np.float64)
-            uv = philox_uniforms(seed, ids, sweep0 + s, h4, self.n)
+            uv = layer_uniforms(seed, ids, sweep0 + s, qv, self.n)
             v = (uv < self.prob_v_given_h(h)).astype(np.float64)
         return v.reshape(np.shape(initial_state))
 
@@ -284,14 +312,15 @@ class PurificationRBMOracle:
         return v
 
     def gibbs_steps_philox(self, k, initial_state, seed, chain_id0=0, sweep0=0):
-        """Slots: hidden i -> i, aux l -> nh + l, visible j -> round_up4(nh + na) + j."""
+        """Hidden and auxiliary units form one stacked layer [h; a] of nh + na units (layer_uniforms)."""
         v = np.array(initial_state, dtype=np.float64, copy=True).reshape(-1, self.n)
         ids = np.arange(chain_id0, chain_id0 + v.shape[0], dtype=np.uint64)
-        v0 = round_up4(self.nh + self.na)
+        qv = visible_q0(self.nh + self.na)
         for s in range(k):
-            h = (philox_uniforms(seed, ids, sweep0 + s, 0, self.nh) < self.prob_h_given_v(v)).astype(np.float64)
-            a = (philox_uniforms(seed, ids, sweep0 + s, self.nh, self.na) < self.prob_a_given_v(v)).astype(np.float64)
-            v = (philox_uniforms(seed, ids, sweep0 + s, v0, self.n) < self.prob_v_given_ha(h, a)).astype(np.float64)
+            uha = layer_uniforms(seed, ids, sweep0 + s, 0, self.nh + self.na)
+            h = (uha[:, : self.nh] < self.prob_h_given_v(v)).astype(np.float64)
+            a = (uha[:, self.nh:] < self.prob_a_given_v(v)).astype(np.float64)
+            v = (layer_uniforms(seed, ids, sweep0 + s, qv, self.n) < self.prob_v_given_ha(h, a)).astype(np.float64)
         return v.reshape(np.shape(initial_state))
 
     def logz_range(self, first=0, count=None, chunk=1 << 16):  # :453-463

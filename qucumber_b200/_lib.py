@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_voi
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqucumber_b200.so")
+LIB_PATH = os.environ.get("QCB_LIB_PATH") or os.path.join(_HERE, "libqucumber_b200.so")  # override: kernel experiments only
 
 QCB_OK = 0
 OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP = range(1, 10)

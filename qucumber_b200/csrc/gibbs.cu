@@ -89,42 +89,55 @@ struct RngCtx {
   uint32_t key0, key1;
 };
 
-constexpr float FILTER_EPS = 0x1.0p-16f;
+// Uniform convention (include/qcb.h): unit u of a layer whose first Philox call is q0 uses call
+// q = q0 + 4 (u / 32) + (u % 16) / 4, output word u % 4 and half (u / 16) % 2 of that word:
+//   h16  = 16-bit half of stream 0            (the only bits the fast path needs)
+//   lo_a = word of stream 1 + 2 half,  lo_b = word of stream 2 + 2 half   (cold path only)
+//   u53  = (h16 * 2^37 + lo_a * 2^5 + (lo_b >> 27)) * 2^-53
+// so one Philox call serves EIGHT decisions.  The filter decides from h16 alone unless p lies within
+// 2^-17 of the 2^-16-wide cell [h16, h16 + 1) * 2^-16 (probability 3e-5 per decision).
+constexpr float FILTER_EPS = 0x1.0p-17f;
+constexpr float CELL = 0x1.0p-16f;
 
-// Cold path, kept out of line so the hot loop stays inside the instruction cache: draws the low
-// words of the flagged units and compares the full 53-bit uniform with the exact FP64 sigmoid.
-__device__ __noinline__ uint32_t decide4_slow(double x0, double x1, double x2, double x3, uint32_t r0, uint32_t r1,
-                                              uint32_t r2, uint32_t r3, uint32_t c0, uint32_t c1, uint32_t key0,
-                                              uint32_t key1, uint32_t sweep, uint32_t q, uint32_t slow, uint32_t nib) {
-  uint32_t lo[4];
-  philox4x32_10(c0, c1, sweep, q | 0x80000000u, key0, key1, lo);
+__device__ __forceinline__ uint32_t stream_ctr(uint32_t stream, uint32_t q) { return (stream << 29) | q; }
+
+// Cold path, kept out of line so the hot loop stays inside the instruction cache: rebuilds the full
+// 53-bit uniforms of the flagged units and compares them with the exact FP64 sigmoid.
+__device__ __noinline__ uint32_t decide4_slow(double x0, double x1, double x2, double x3, uint32_t c0, uint32_t c1,
+                                              uint32_t key0, uint32_t key1, uint32_t sweep, uint32_t q, uint32_t half,
+                                              uint32_t slow, uint32_t nib) {
+  uint32_t hi[4], la[4], lb[4];
+  philox4x32_10(c0, c1, sweep, stream_ctr(0u, q), key0, key1, hi);
+  philox4x32_10(c0, c1, sweep, stream_ctr(1u + 2u * half, q), key0, key1, la);
+  philox4x32_10(c0, c1, sweep, stream_ctr(2u + 2u * half, q), key0, key1, lb);
   const double x[4] = {x0, x1, x2, x3};
-  const uint32_t r[4] = {r0, r1, r2, r3};
 #pragma unroll 1
   for (int w = 0; w < 4; ++w) {
     if (slow & (1u << w)) {
-      const double u = uniform53(r[w], lo[w]);
+      const uint64_t h16 = (hi[w] >> (16u * (1u - half))) & 0xFFFFu;
+      const uint64_t bits = (h16 << 37) | ((uint64_t)la[w] << 5) | (uint64_t)(lb[w] >> 27);
+      const double u = (double)bits * 0x1.0p-53;
       if (u < sigmoid_exact(x[w])) nib |= 1u << w; else nib &= ~(1u << w);
     }
   }
   return nib;
 }
 
-__device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const RngCtx& rc, uint32_t sweep, uint32_t q,
-                                                   uint32_t valid) {
-  uint32_t r[4];
-  philox4x32_10(rc.c0, rc.c1, sweep, q, rc.key0, rc.key1, r);
+// Decisions for the four units that use half `half` of the words r[0..3] of call q.
+__device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const uint32_t (&r)[4], uint32_t half,
+                                                   const RngCtx& rc, uint32_t sweep, uint32_t q, uint32_t valid) {
   uint32_t nib = 0, slow = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const float xf = (float)x[w];
     const float p = __fdividef(1.0f, 1.0f + __expf(-xf));
-    const float uf = __uint_as_float(0x3F800000u | (r[w] >> 9)) - 1.0f;  // u in [uf, uf + 2^-23)
-    if (uf + FILTER_EPS <= p) nib |= 1u << w;
+    const uint32_t h16 = half ? (r[w] & 0xFFFFu) : (r[w] >> 16);
+    const float uf = __uint_as_float(0x3F800000u | (h16 << 7)) - 1.0f;  // u in [uf, uf + 2^-16)
+    if (uf + (CELL + FILTER_EPS) <= p) nib |= 1u << w;
     else if (!(uf >= p + FILTER_EPS)) slow |= 1u << w;
   }
   slow &= valid;
-  if (slow) nib = decide4_slow(x[0], x[1], x[2], x[3], r[0], r[1], r[2], r[3], rc.c0, rc.c1, rc.key0, rc.key1, sweep, q, slow, nib);
+  if (slow) nib = decide4_slow(x[0], x[1], x[2], x[3], rc.c0, rc.c1, rc.key0, rc.key1, sweep, q, half, slow, nib);
   return nib & valid;
 }
 
@@ -203,19 +216,29 @@ __device__ __forceinline__ void half_sweep(const uint32_t (&min)[(KB_IN + 1) / 2
 #pragma unroll
   for (int w = 0; w < (OB + 1) / 2; ++w) mout[w] = 0u;
 #pragma unroll
-  for (int gq = 0; gq < OB; ++gq) {
-    const int unit0 = 16 * gq + 4 * t;
-    const int nvalid = n_out_real - unit0;
-    if (nvalid > 0) {
-      const uint32_t valid = nvalid >= 4 ? 0xFu : ((1u << nvalid) - 1u);
-      const double x[4] = {acc[2 * gq][0], acc[2 * gq][1], acc[2 * gq + 1][0], acc[2 * gq + 1][1]};
-      uint32_t nib;
-      if (fed != nullptr) {
-        nib = decide4_fed(x[0], x[1], x[2], x[3], fed + unit0, valid);
-      } else {
-        nib = decide4_philox(x, rc, sweep, q0 + 4 * gq + t, valid);
+  for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
+    // one Philox call per pair of 16-unit blocks: its four words carry two 16-bit uniforms each
+    const uint32_t q = q0 + 4 * pq + t;
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    if (fed == nullptr && 32 * pq + 4 * t < n_out_real) philox4x32_10(rc.c0, rc.c1, sweep, stream_ctr(0u, q), rc.key0, rc.key1, r);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int gq = 2 * pq + half;
+      if (gq < OB) {
+        const int unit0 = 16 * gq + 4 * t;
+        const int nvalid = n_out_real - unit0;
+        if (nvalid > 0) {
+          const uint32_t valid = nvalid >= 4 ? 0xFu : ((1u << nvalid) - 1u);
+          const double x[4] = {acc[2 * gq][0], acc[2 * gq][1], acc[2 * gq + 1][0], acc[2 * gq + 1][1]};
+          uint32_t nib;
+          if (fed != nullptr) {
+            nib = decide4_fed(x[0], x[1], x[2], x[3], fed + unit0, valid);
+          } else {
+            nib = decide4_philox(x, r, (uint32_t)half, rc, sweep, q, valid);
+          }
+          mout[gq / 2] |= nib << (16 * (gq % 2) + 4 * t);
+        }
       }
-      mout[gq / 2] |= nib << (16 * (gq % 2) + 4 * t);
     }
   }
 #pragma unroll
@@ -255,7 +278,7 @@ __global__ void __launch_bounds__(GIBBS_THREADS) gibbs_kernel(const GibbsArgs a)
   const int g = lane >> 2;
   constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
   const int nunits = a.nhid + a.N;
-  const uint32_t qv0 = (uint32_t)(round_up(a.nhid, 4) / 4);
+  const uint32_t qv0 = (uint32_t)(4 * ((a.nhid + 31) / 32));  // first Philox call of the visible layer
   const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v_in);
 
   // every warp runs the same number of iterations (groups past the end are dummies) so that the

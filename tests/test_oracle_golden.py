@@ -85,6 +85,14 @@ def test_philox_known_answers():
     u = orc.philox_uniforms(12345, np.arange(4), 3, 8, 6)
     assert u.shape == (4, 6) and np.all((u >= 0) & (u < 1))
     assert np.all(u * 2.0 ** 53 == np.floor(u * 2.0 ** 53))
+    # layer convention of the Gibbs kernel: 53-bit grid, eight units per call, all units distinct streams
+    lu = orc.layer_uniforms(77, np.arange(3), 5, orc.visible_q0(40), 70)
+    assert lu.shape == (3, 70) and np.all((lu >= 0) & (lu < 1)) and np.all(lu * 2.0 ** 53 == np.floor(lu * 2.0 ** 53))
+    assert len(np.unique(lu)) == lu.size
+    hi = np.stack(orc.philox4x32_10(np.uint64(1), np.uint64(0), np.uint64(5), np.uint64(orc.visible_q0(40) + 4 * 1 + 2), 77, 0), -1)
+    # unit 32*1 + 16*1 + 4*2 + 3 = 59 of chain 1: call q0 + 4*1 + 2, word 3, low half
+    assert int(lu[1, 59] * 2.0 ** 53) >> 37 == int(hi[3]) & 0xFFFF
+    assert orc.visible_q0(64) == 8 and orc.visible_q0(10) == 4 and orc.visible_q0(33) == 8
 
 
 def test_purification():
