@@ -101,55 +101,64 @@ constexpr float CELL = 0x1.0p-16f;
 
 __device__ __forceinline__ uint32_t stream_ctr(uint32_t stream, uint32_t q) { return (stream << 29) | q; }
 
-// Cold path, kept out of line so the hot loop stays inside the instruction cache: rebuilds the full
-// 53-bit uniforms of the flagged units and compares them with the exact FP64 sigmoid.
-__device__ __noinline__ uint32_t decide4_slow(double x0, double x1, double x2, double x3, uint32_t c0, uint32_t c1,
-                                              uint32_t key0, uint32_t key1, uint32_t sweep, uint32_t q, uint32_t half,
-                                              uint32_t slow, uint32_t nib) {
-  uint32_t hi[4], la[4], lb[4];
-  philox4x32_10(c0, c1, sweep, stream_ctr(0u, q), key0, key1, hi);
-  philox4x32_10(c0, c1, sweep, stream_ctr(1u + 2u * half, q), key0, key1, la);
-  philox4x32_10(c0, c1, sweep, stream_ctr(2u + 2u * half, q), key0, key1, lb);
-  const double x[4] = {x0, x1, x2, x3};
+// Cold path, kept out of line (one call site per half sweep) so the hot loop stays small: rebuilds
+// the full 53-bit uniforms of the flagged units and compares them with the exact FP64 sigmoid.
+// xs holds the lane's pre-activations (4 per 16-unit block), nibw its decisions (4 bits per block),
+// slowmask the undecided ones.
+__device__ __noinline__ uint32_t fixup_slow(const double* __restrict__ xs, uint32_t nibw, uint32_t slowmask, uint32_t c0,
+                                            uint32_t c1, uint32_t key0, uint32_t key1, uint32_t sweep, uint32_t q0, int t) {
+  while (slowmask != 0u) {
+    const int bitpos = __ffs(slowmask) - 1;
+    const int gq = bitpos >> 2;
+    const uint32_t sb = (slowmask >> (4 * gq)) & 0xFu;
+    slowmask &= ~(0xFu << (4 * gq));
+    const uint32_t half = (uint32_t)(gq & 1), q = q0 + 4u * (uint32_t)(gq >> 1) + (uint32_t)t;
+    uint32_t hi[4], la[4], lb[4];
+    philox4x32_10(c0, c1, sweep, stream_ctr(0u, q), key0, key1, hi);
+    philox4x32_10(c0, c1, sweep, stream_ctr(1u + 2u * half, q), key0, key1, la);
+    philox4x32_10(c0, c1, sweep, stream_ctr(2u + 2u * half, q), key0, key1, lb);
 #pragma unroll 1
-  for (int w = 0; w < 4; ++w) {
-    if (slow & (1u << w)) {
-      const uint64_t h16 = (hi[w] >> (16u * (1u - half))) & 0xFFFFu;
-      const uint64_t bits = (h16 << 37) | ((uint64_t)la[w] << 5) | (uint64_t)(lb[w] >> 27);
-      const double u = (double)bits * 0x1.0p-53;
-      if (u < sigmoid_exact(x[w])) nib |= 1u << w; else nib &= ~(1u << w);
+    for (int w = 0; w < 4; ++w) {
+      if (sb & (1u << w)) {
+        const uint64_t h16 = (hi[w] >> (16u * (1u - half))) & 0xFFFFu;
+        const uint64_t bits = (h16 << 37) | ((uint64_t)la[w] << 5) | (uint64_t)(lb[w] >> 27);
+        const double u = (double)bits * 0x1.0p-53;
+        const uint32_t m = 1u << (4 * gq + w);
+        if (u < sigmoid_exact(xs[4 * gq + w])) nibw |= m; else nibw &= ~m;
+      }
     }
   }
-  return nib;
+  return nibw;
 }
 
-// Decisions for the four units that use half `half` of the words r[0..3] of call q.
-__device__ __forceinline__ uint32_t decide4_philox(const double (&x)[4], const uint32_t (&r)[4], uint32_t half,
-                                                   const RngCtx& rc, uint32_t sweep, uint32_t q, uint32_t valid) {
-  uint32_t nib = 0, slow = 0;
+// Fed-uniform mode (bit-exact replay of the reference): every decision is the exact FP64 comparison.
+__device__ __noinline__ uint32_t decide_fed(const double* __restrict__ xs, const double* __restrict__ fed, int nblocks,
+                                            int n_out_real, int t) {
+  uint32_t nibw = 0u;
+  for (int gq = 0; gq < nblocks; ++gq) {
+    for (int w = 0; w < 4; ++w) {
+      const int unit = 16 * gq + 4 * t + w;
+      if (unit < n_out_real && fed[unit] < sigmoid_exact(xs[4 * gq + w])) nibw |= 1u << (4 * gq + w);
+    }
+  }
+  return nibw;
+}
+
+// Fast decisions for the four units that use half `half` of the words r[0..3]: bit w of the result is
+// set when u < p is certain, bit w of `slow` when the 16-bit cell cannot decide.
+__device__ __forceinline__ uint32_t decide4_fast(const double (&x)[4], const uint32_t (&r)[4], uint32_t half, uint32_t& slow) {
+  uint32_t nib = 0;
+  slow = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const float xf = (float)x[w];
     const float p = __fdividef(1.0f, 1.0f + __expf(-xf));
     const uint32_t h16 = half ? (r[w] & 0xFFFFu) : (r[w] >> 16);
     const float uf = __uint_as_float(0x3F800000u | (h16 << 7)) - 1.0f;  // u in [uf, uf + 2^-16)
-    if (uf + (CELL + FILTER_EPS) <= p) nib |= 1u << w;
-    else if (!(uf >= p + FILTER_EPS)) slow |= 1u << w;
-  }
-  slow &= valid;
-  if (slow) nib = decide4_slow(x[0], x[1], x[2], x[3], rc.c0, rc.c1, rc.key0, rc.key1, sweep, q, half, slow, nib);
-  return nib & valid;
-}
-
-__device__ __noinline__ uint32_t decide4_fed(double x0, double x1, double x2, double x3, const double* __restrict__ u,
-                                             uint32_t valid) {
-  const double x[4] = {x0, x1, x2, x3};
-  uint32_t nib = 0;
-#pragma unroll 1
-  for (int w = 0; w < 4; ++w) {
-    if (valid & (1u << w)) {
-      if (u[w] < sigmoid_exact(x[w])) nib |= 1u << w;
-    }
+    const bool sure1 = uf + (CELL + FILTER_EPS) <= p;
+    const bool sure0 = uf >= p + FILTER_EPS;
+    nib |= (sure1 ? 1u : 0u) << w;
+    slow |= ((sure1 || sure0) ? 0u : 1u) << w;
   }
   return nib;
 }
@@ -213,34 +222,44 @@ __device__ __forceinline__ void half_sweep(const uint32_t (&min)[(KB_IN + 1) / 2
   }
   pipe_release(lane_warp);
 
+  // Bernoulli decisions: nibw collects 4 bits per 16-unit block, slowmask the undecided ones
+  uint32_t nibw = 0u, slowmask = 0u;
+  if (fed == nullptr) {
 #pragma unroll
-  for (int w = 0; w < (OB + 1) / 2; ++w) mout[w] = 0u;
+    for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
+      // one Philox call per pair of 16-unit blocks: its four words carry two 16-bit uniforms each
+      uint32_t r[4];
+      philox4x32_10(rc.c0, rc.c1, sweep, stream_ctr(0u, q0 + 4 * pq + t), rc.key0, rc.key1, r);
 #pragma unroll
-  for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
-    // one Philox call per pair of 16-unit blocks: its four words carry two 16-bit uniforms each
-    const uint32_t q = q0 + 4 * pq + t;
-    uint32_t r[4] = {0u, 0u, 0u, 0u};
-    if (fed == nullptr && 32 * pq + 4 * t < n_out_real) philox4x32_10(rc.c0, rc.c1, sweep, stream_ctr(0u, q), rc.key0, rc.key1, r);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int gq = 2 * pq + half;
-      if (gq < OB) {
-        const int unit0 = 16 * gq + 4 * t;
-        const int nvalid = n_out_real - unit0;
-        if (nvalid > 0) {
-          const uint32_t valid = nvalid >= 4 ? 0xFu : ((1u << nvalid) - 1u);
+      for (int half = 0; half < 2; ++half) {
+        const int gq = 2 * pq + half;
+        if (gq < OB) {
+          int nvalid = n_out_real - (16 * gq + 4 * t);
+          nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+          const uint32_t valid = (1u << nvalid) - 1u;
           const double x[4] = {acc[2 * gq][0], acc[2 * gq][1], acc[2 * gq + 1][0], acc[2 * gq + 1][1]};
-          uint32_t nib;
-          if (fed != nullptr) {
-            nib = decide4_fed(x[0], x[1], x[2], x[3], fed + unit0, valid);
-          } else {
-            nib = decide4_philox(x, r, (uint32_t)half, rc, sweep, q, valid);
-          }
-          mout[gq / 2] |= nib << (16 * (gq % 2) + 4 * t);
+          uint32_t slow;
+          const uint32_t nib = decide4_fast(x, r, (uint32_t)half, slow);
+          nibw |= (nib & valid) << (4 * gq);
+          slowmask |= (slow & valid) << (4 * gq);
         }
       }
     }
   }
+  if (fed != nullptr || slowmask != 0u) {  // rare (probability ~3e-5 per decision) unless uniforms are fed
+    double xs[4 * OB];
+#pragma unroll
+    for (int gq = 0; gq < OB; ++gq) {
+      xs[4 * gq] = acc[2 * gq][0]; xs[4 * gq + 1] = acc[2 * gq][1];
+      xs[4 * gq + 2] = acc[2 * gq + 1][0]; xs[4 * gq + 3] = acc[2 * gq + 1][1];
+    }
+    if (fed != nullptr) nibw = decide_fed(xs, fed, OB, n_out_real, t);
+    else nibw = fixup_slow(xs, nibw, slowmask, rc.c0, rc.c1, rc.key0, rc.key1, sweep, q0, t);
+  }
+#pragma unroll
+  for (int w = 0; w < (OB + 1) / 2; ++w) mout[w] = 0u;
+#pragma unroll
+  for (int gq = 0; gq < OB; ++gq) mout[gq / 2] |= ((nibw >> (4 * gq)) & 0xFu) << (16 * (gq % 2) + 4 * t);
 #pragma unroll
   for (int w = 0; w < (OB + 1) / 2; ++w) {
     mout[w] |= __shfl_xor_sync(0xffffffffu, mout[w], 1);
