@@ -246,6 +246,30 @@ def extra_metrics(dev, lib_mod):
                            "chain_sweeps_per_s": (1 << 20) * 10 / (ms * 1e-3)}
     except Exception as exc:  # pragma: no cover
         out["cdk_step"] = {"error": str(exc)}
+    # ---- rotated-basis gradient (config 5): ComplexWaveFunction N = nh = 20, S = 10 rotated sites
+    try:
+        from oracle import rbm_oracle as orc
+        from qucumber_b200 import ComplexWaveFunction
+
+        n, S, B = 20, 10, 4096
+        rng = np.random.default_rng(7)
+        cw = ComplexWaveFunction(n, n, gpu=True)
+        sites = np.sort(rng.choice(n, S, replace=False))
+        basis = np.array(["Z"] * n)
+        basis[sites] = rng.choice(["X", "Y"], S)
+        samples = torch.tensor((rng.random((B, n)) < 0.5).astype(np.float64), device=dev)
+        ms, _ = timed(lambda: cw.rotated_gradient(basis, samples))
+        Bc = 8
+        am = orc.BinaryRBMOracle(cw.rbm_am.weights.cpu().numpy(), cw.rbm_am.visible_bias.cpu().numpy(), cw.rbm_am.hidden_bias.cpu().numpy())
+        ph = orc.BinaryRBMOracle(cw.rbm_ph.weights.cpu().numpy(), cw.rbm_ph.visible_bias.cpu().numpy(), cw.rbm_ph.hidden_bias.cpu().numpy())
+        t0 = _time.perf_counter()
+        orc.complex_rotated_gradient(am, ph, list(basis), samples[:Bc].cpu().numpy())
+        cpu_s = _time.perf_counter() - t0
+        out["cwf_rotated_gradient"] = {"N": n, "nh": n, "S": S, "B": B, "ms": ms, "expanded_states_per_s": B * (1 << S) / (ms * 1e-3),
+                                       "cpu_port_expanded_states_per_s": Bc * (1 << S) / cpu_s,
+                                       "cpu_note": f"numpy oracle restatement on {Bc} samples (the reference itself measured 0.9-2.9e5/s, SURVEY.md)"}
+    except Exception as exc:  # pragma: no cover
+        out["cwf_rotated_gradient"] = {"error": str(exc)}
     return out
 
 
