@@ -19,6 +19,9 @@ namespace qcb {
 
 constexpr int GR = 32;  // rows per tile
 
+int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
+                         int* grid_out, cudaStream_t st);
+
 template <int TPT, int SRC>  // TPT = 4x4 tiles per thread
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s, RowSrc src, int64_t rows,
                                                                    double* __restrict__ partials) {
@@ -189,9 +192,17 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
   if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: layer %d x %d does not fit in shared memory", H, N);
   const size_t need = grad_reduce_workspace_bytes(N, H, rows);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "grad_reduce: workspace too small (%zu < %zu)", ws_bytes, need);
-  const int grid = grad_reduce_grid(rows);
+  int grid = grad_reduce_grid(rows);
   double* partials = reinterpret_cast<double*>(ws);
+  int grid_dmma = 0;
   if (rows > 0) {
+    // large batches of explicit / expanded rows run on the FP64 tensor cores (grad_reduce_dmma.cu)
+    const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * 2, &grid_dmma, st);
+    if (rc != QCB_OK) return rc;
+  }
+  if (grid_dmma > 0) {
+    grid = grid_dmma;
+  } else if (rows > 0) {
     const int ntiles = (round_up(H, 4) / 4) * (round_up(N, 4) / 4);
     const int tpt = (ntiles + ROWS_THREADS - 1) / ROWS_THREADS;
 #define QCB_GR_CASE(T)                                                                                                       \

@@ -1,0 +1,219 @@
+// Reduced energy gradient on the FP64 tensor cores (large batches).
+//
+// g_partial = sum_rows [ p_r (x) v_r ; w_r v_r ; p_r ],  p_r = w_r * sigmoid(Wst v_r + hb)   (rbm/binary_rbm.py:113-120)
+// Both contractions are DMMA (mma.sync m8n8k4 f64) tiles:
+//   phase 1  Theta(64 rows x H) = V(64 x N) . Wst^T          A = V tile (shared memory), B = W fragments
+//   phase 2  G(H x N)          += P^T(H x 64) . V(64 x N)     A = P tile, B = V tile, accumulators in registers
+// A CTA of 8 warps walks tiles of 64 rows (persistent grid).  In phase 1 warp w owns rows 8w..8w+7 and
+// applies the exact FP64 sigmoid to its accumulator fragments; in phase 2 warp w owns the 8-row
+// blocks {w, w+8} of G, which stay in registers for the whole kernel.  Per-CTA partials go to the
+// workspace in the same [Wst | vb | hb] layout as the FMA kernel and are summed by
+// grad_finalize_kernel in a fixed order (deterministic).  Shapes that do not fit, tiny batches and
+// index-generated rows keep using grad_reduce_kernel (grad_reduce.cu).
+#include "rows.cuh"
+
+namespace qcb {
+
+constexpr int GD_THREADS = 256;
+constexpr int GD_WARPS = 8;
+constexpr int GD_TR = 64;  // rows per tile
+
+// NB8: 8-column blocks of the visible layer, HB8: 8-unit blocks of all hidden-like features (computed + aux)
+template <int NB8, int HB8>
+__global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec s, RowSrc src, int mode, int64_t rows,
+                                                                      double* __restrict__ partials) {
+  constexpr int Npad = 8 * NB8, Hpad = 8 * HB8;
+  constexpr int KN4 = 2 * NB8;            // k-steps of phase 1
+  constexpr int LDV = Npad + 4, LDP = Hpad + 4;
+  constexpr int MB = (HB8 + GD_WARPS - 1) / GD_WARPS;  // G row blocks per warp
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Wf = reinterpret_cast<double*>(smem_raw);     // [KN4][HB8][32] B fragments of phase 1
+  double* hb = Wf + (size_t)KN4 * HB8 * 32;             // [Hpad]
+  double* Vt = hb + Hpad;                               // [GD_TR][LDV]
+  double* Pt = Vt + (size_t)GD_TR * LDV;                // [GD_TR][LDP]
+  double* wts = Pt + (size_t)GD_TR * LDP;               // [GD_TR]
+
+  const int N = s.n_in1, Hc = s.n_out;                  // Hc units are computed here, the rest are aux features
+  const int n_aux = mode == ROWS_EXPANDED ? src.n_aux : 0;
+  const int H = Hc + n_aux;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // stage W fragments: element (kk, nb, lane) = Wst[hid = 8 nb + g][vis = 4 kk + t]
+  for (int idx = threadIdx.x; idx < KN4 * HB8 * 32; idx += GD_THREADS) {
+    const int l = idx & 31, nb = (idx >> 5) % HB8, kk = (idx >> 5) / HB8;
+    const int hid = 8 * nb + (l >> 2), vis = 4 * kk + (l & 3);
+    Wf[idx] = (hid < Hc && vis < N) ? s.mop(hid, vis) : 0.0;
+  }
+  for (int i = threadIdx.x; i < Hpad; i += GD_THREADS) hb[i] = i < Hc ? s.bias(i) : 0.0;
+  for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
+  for (int i = threadIdx.x; i < GD_TR * LDP; i += GD_THREADS) Pt[i] = 0.0;
+  __syncthreads();
+
+  double G[MB][NB8][2];
+  double hsum[MB], vsum[(NB8 + GD_WARPS - 1) / GD_WARPS];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    hsum[m] = 0.0;
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb) { G[m][nb][0] = 0.0; G[m][nb][1] = 0.0; }
+  }
+#pragma unroll
+  for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) vsum[i] = 0.0;
+
+  const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * GD_TR;
+    // ---- fill the V tile, the row weights and the aux columns of the P tile
+    for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
+      const int rr = idx / N, j = idx - rr * N;
+      const int64_t r = r0 + rr;
+      double val = 0.0;
+      if (r < rows) val = mode == ROWS_EXPANDED ? src.ex.value(r, j) : src.v[r * N + j];
+      Vt[rr * LDV + j] = val;
+    }
+    for (int rr = threadIdx.x; rr < GD_TR; rr += GD_THREADS) {
+      const int64_t r = r0 + rr;
+      wts[rr] = r < rows ? (mode == ROWS_EXPANDED ? src.wrow[r] : 1.0) : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < GD_TR * n_aux; idx += GD_THREADS) {
+      const int rr = idx / n_aux, o = idx - rr * n_aux;
+      const int64_t r = r0 + rr;
+      Pt[rr * LDP + Hc + o] = r < rows ? src.aux[r * n_aux + o] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- phase 1: theta for rows 8 warp .. 8 warp + 7, p = w * sigmoid(theta) -> P tile
+    {
+      double acc[HB8][2];
+#pragma unroll
+      for (int nb = 0; nb < HB8; ++nb) {
+        acc[nb][0] = hb[8 * nb + 2 * t];
+        acc[nb][1] = hb[8 * nb + 2 * t + 1];
+      }
+      const double* arow = Vt + (8 * warp + g) * LDV + t;
+#pragma unroll 4
+      for (int kk = 0; kk < KN4; ++kk) {
+        const double a = arow[4 * kk];
+        const double* bf = Wf + (size_t)kk * HB8 * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < HB8; ++nb) dmma884(acc[nb][0], acc[nb][1], a, bf[nb * 32]);
+      }
+      const double wr = wts[8 * warp + g];
+      double* prow = Pt + (8 * warp + g) * LDP;
+#pragma unroll
+      for (int nb = 0; nb < HB8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int unit = 8 * nb + 2 * t + e;
+          if (unit < Hc) prow[unit] = wr * fmin(fmax(sigmoid_exact(acc[nb][e]), 0.0), 1.0);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: G += P^T V for this warp's row blocks of G; column sums for the bias gradients
+#pragma unroll 2
+    for (int kk = 0; kk < GD_TR / 4; ++kk) {
+      const double* vrow = Vt + (4 * kk + t) * LDV + g;
+      const double* prow = Pt + (4 * kk + t) * LDP + g;
+      double b[NB8];
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb) b[nb] = vrow[8 * nb];
+      const double wk = wts[4 * kk + t];
+#pragma unroll
+      for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) {
+        const int nb = warp + GD_WARPS * i;
+        if (nb < NB8) vsum[i] = fma(wk, vrow[8 * nb], vsum[i]);
+      }
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const int mb = warp + GD_WARPS * m;
+        if (mb < HB8) {
+          const double a = prow[8 * mb];
+          hsum[m] += a;
+#pragma unroll
+          for (int nb = 0; nb < NB8; ++nb) dmma884(G[m][nb][0], G[m][nb][1], a, b[nb]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write this CTA's partial in flat order [Wst (H x N) | vb (N) | hb (H)]
+  double* out = partials + (size_t)blockIdx.x * ((size_t)H * N + N + H);
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    const int mb = warp + GD_WARPS * m;
+    if (mb < HB8) {
+      const int hid = 8 * mb + g;
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int vis = 8 * nb + 2 * t + e;
+          if (hid < H && vis < N) out[(size_t)hid * N + vis] = G[m][nb][e];
+        }
+      double hs = hsum[m];
+      hs += __shfl_xor_sync(0xffffffffu, hs, 1);
+      hs += __shfl_xor_sync(0xffffffffu, hs, 2);
+      if (t == 0 && hid < H) out[(size_t)H * N + N + hid] = hs;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) {
+    const int nb = warp + GD_WARPS * i;
+    double vs = vsum[i];
+    vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+    vs += __shfl_xor_sync(0xffffffffu, vs, 2);
+    const int vis = 8 * nb + g;
+    if (nb < NB8 && t == 0 && vis < N) out[(size_t)H * N + vis] = vs;
+  }
+}
+
+static int pick8(int units) {
+  if (units <= 16) return 2;
+  if (units <= 32) return 4;
+  if (units <= 64) return 8;
+  if (units <= 128) return 16;
+  return 0;
+}
+
+static size_t gd_smem(int NB8, int HB8) {
+  const size_t Npad = 8 * NB8, Hpad = 8 * HB8;
+  return ((size_t)2 * NB8 * HB8 * 32 + Hpad + (size_t)GD_TR * (Npad + 4) + (size_t)GD_TR * (Hpad + 4) + GD_TR) * sizeof(double);
+}
+
+template <int NB8, int HB8>
+static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int grid, cudaStream_t st) {
+  const size_t smem = gd_smem(NB8, HB8);
+  QCB_CUDA(cudaFuncSetAttribute(grad_reduce_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  grad_reduce_dmma_kernel<NB8, HB8><<<grid, GD_THREADS, smem, st>>>(s, src, mode, rows, partials);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+// Returns QCB_OK and sets *grid_out (> 0) when the tensor-core path took the batch; *grid_out = 0 means
+// "not applicable, use the FMA kernel".  H = computed + aux hidden-like units.
+int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
+                         int* grid_out, cudaStream_t st) {
+  *grid_out = 0;
+  if (mode == ROWS_ENUM || rows < 2048) return QCB_OK;
+  const int NB8 = pick8(s.n_in1), HB8 = pick8(H);
+  if (NB8 == 0 || HB8 == 0 || gd_smem(NB8, HB8) > SMEM_LIMIT) return QCB_OK;
+  const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
+  const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
+  int rc = QCB_OK;
+#define QCB_GD_CASE(NB, HBx) \
+  if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx>(s, src, mode, rows, partials, grid, st); else
+  QCB_GD_CASE(2, 2) QCB_GD_CASE(2, 4) QCB_GD_CASE(2, 8) QCB_GD_CASE(2, 16)
+  QCB_GD_CASE(4, 2) QCB_GD_CASE(4, 4) QCB_GD_CASE(4, 8) QCB_GD_CASE(4, 16)
+  QCB_GD_CASE(8, 2) QCB_GD_CASE(8, 4) QCB_GD_CASE(8, 8) QCB_GD_CASE(8, 16)
+  QCB_GD_CASE(16, 2) QCB_GD_CASE(16, 4) QCB_GD_CASE(16, 8)
+  return QCB_OK;  // (16, 16) does not fit: FMA kernel
+#undef QCB_GD_CASE
+  if (rc == QCB_OK) *grid_out = grid;
+  return rc;
+}
+
+}  // namespace qcb

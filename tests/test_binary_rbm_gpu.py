@@ -219,3 +219,16 @@ def test_gibbs_host_buffers_pipelined(lib, cuda):
     _lib.check(lib.qcb_rbm_gibbs_host(_lib.ptr(Wh), None, _lib.ptr(bh), _lib.ptr(ch), None, n, nh, 0, _lib.ptr(vh), C, k, 4242, 7, 1,
                                       _lib.ptr(scratch), nbytes, _lib.stream_ptr(cuda)), "qcb_rbm_gibbs_host")
     assert torch.equal(vh, want)
+
+
+@pytest.mark.parametrize("n,nh", SHAPES + [(128, 60), (17, 128)])
+def test_gradient_reduce_large_batch_tensor_core_path(lib, cuda, n, nh):
+    """Batches of >= 2048 rows take the DMMA reduction (grad_reduce_dmma.cu); same 1e-10 gate,
+    binary and real-valued rows, ragged last tile."""
+    rbm, orc = _pair(n, nh, 91, cuda)
+    v = random_states(5003, n, 92)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), orc.effective_energy_gradient(v),
+                 what="reduced gradient (large batch)")
+    vr = np.random.default_rng(93).standard_normal((2048, n))
+    assert_close(rbm.effective_energy_gradient(torch.tensor(vr, device=cuda)), orc.effective_energy_gradient(vr),
+                 what="reduced gradient (large batch, real rows)")

@@ -342,3 +342,32 @@ def test_save_load_sample_determinism(lib, cuda, tmp_path):
         keys = set(torch.load(path, weights_only=False)["rbm_am"].keys())
         assert keys == ({"weights", "visible_bias", "hidden_bias"} if cls is not DensityMatrix else
                         {"weights_W", "weights_U", "visible_bias", "hidden_bias", "aux_bias"})
+
+
+def test_purification_gradient_large_batch(lib, cuda):
+    from qucumber_b200 import PurificationRBM
+
+    n, nh, na = 40, 30, 20
+    W, U, b, c, d = make_purification_params(n, nh, na, 95)
+    rbm = load_purification(PurificationRBM(n, nh, na, gpu=True), W, U, b, c, d)
+    o = orc.PurificationRBMOracle(W, U, b, c, d)
+    v = random_states(4100, n, 96)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), o.effective_energy_gradient(v), what="grad reduce (large)")
+
+
+def test_density_rotated_large_expansion(lib, cuda):
+    """Enough expanded rows (B * 2^S >= 2048) for the weighted DMMA reduction with aux features."""
+    from qucumber_b200 import DensityMatrix
+
+    n, nh, na, basis = 8, 6, 5, "XYZXYZXY"
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    pa = make_purification_params(n, nh, na, 97, bias_scale=0.3)
+    pp = make_purification_params(n, nh, na, 98, bias_scale=0.3)
+    load_purification(nn.rbm_am, *pa)
+    load_purification(nn.rbm_ph, *pp)
+    am, ph = orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp)
+    samples = random_states(40, n, 99)
+    rg = nn.rotated_gradient(np.array(list(basis)), torch.tensor(samples, device=cuda))
+    ga, gp = orc.dm_rotated_gradient(am, ph, list(basis), samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude)")
+    assert_close(rg[1], gp, rtol=1e-9, what="rotated grad (phase)")
