@@ -72,6 +72,12 @@ __global__ void __launch_bounds__(CWF_THREADS) cwf_amp_kernel(StackedParams am, 
   double* bp = ba + round_up(N, 2);
   double* Usm = bp + round_up(N, 2);                 // [K][8]
   double* red = Usm + (size_t)K * 8;                 // [CWF_THREADS][2]
+  double* EaP = red + 2 * CWF_THREADS;               // [N][NHT] exp(+W_am), exp(-W_am), exp(+W_ph), exp(-W_ph)
+  double* EaM = EaP + (size_t)N * NHT;
+  double* EpP = EaM + (size_t)N * NHT;
+  double* EpM = EpP + (size_t)N * NHT;
+  double* eb = EpM + (size_t)N * NHT;                // [4][N] exp(+-b_am), exp(+-b_ph)
+  __shared__ int fast_ok;
   for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
     const int j = idx / NHT, i = idx - j * NHT;
     Wa[idx] = i < nh ? am.W[(size_t)i * N + j] : 0.0;
@@ -83,7 +89,38 @@ __global__ void __launch_bounds__(CWF_THREADS) cwf_amp_kernel(StackedParams am, 
   }
   for (int j = threadIdx.x; j < N; j += blockDim.x) { ba[j] = am.b[j]; bp[j] = ph.b[j]; }
   for (int i = threadIdx.x; i < K * 8; i += blockDim.x) Usm[i] = U[i];
+  if (threadIdx.x == 0) fast_ok = 1;
   __syncthreads();
+  // Product form (see enumerate.cu): exp(theta_i) is carried multiplicatively along the Gray walk and
+  // -E = log( e^{b.v} prod_i f_i ), so a state costs one sqrt, one log and one sincos instead of 2 nh
+  // softplus evaluations.  Used only when no product can leave the double range for any state.
+  for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
+    const int i = idx % NHT;
+    EaP[idx] = i < nh ? exp(Wa[idx]) : 1.0; EaM[idx] = i < nh ? exp(-Wa[idx]) : 1.0;
+    EpP[idx] = i < nh ? exp(Wp[idx]) : 1.0; EpM[idx] = i < nh ? exp(-Wp[idx]) : 1.0;
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    eb[j] = exp(ba[j]); eb[N + j] = exp(-ba[j]); eb[2 * N + j] = exp(bp[j]); eb[3 * N + j] = exp(-bp[j]);
+  }
+  if (threadIdx.x < 2) {  // thread 0: amplitude RBM, thread 1: phase RBM
+    const double* Wt = threadIdx.x == 0 ? Wa : Wp;
+    const double* cc = threadIdx.x == 0 ? ca : cp;
+    const double* bb = threadIdx.x == 0 ? ba : bp;
+    double sum_sp = 0.0, max_abs = 0.0, bpos = 0.0, bneg = 0.0;
+    bool bad = false;
+    for (int i = 0; i < nh; ++i) {
+      double hi = cc[i], lo = cc[i];
+      for (int j = 0; j < N; ++j) { hi += fmax(Wt[j * NHT + i], 0.0); lo += fmin(Wt[j * NHT + i], 0.0); }
+      if (!(fabs(hi) < 1e300) || !(fabs(lo) < 1e300)) bad = true;
+      sum_sp += fmax(hi, 0.0) + 0.6931471805599453;
+      max_abs = fmax(max_abs, fmax(fabs(hi), fabs(lo)));
+    }
+    for (int j = 0; j < N; ++j) { if (!(fabs(bb[j]) < 1e300)) bad = true; bpos += fmax(bb[j], 0.0); bneg += fmin(bb[j], 0.0); }
+    if (bad || !(sum_sp + bpos < 650.0) || !(bneg > -650.0) || !(max_abs < 650.0)) fast_ok = 0;
+  }
+  __syncthreads();
+  const bool fast = fast_ok != 0;
+  const double E20 = 485165195.40979028;  // e^20: torch's softplus threshold in the product form
 
   const int tps = 1 << tps_log2;            // threads per sample
   const int m = S - tps_log2;               // log2(states per thread)
@@ -112,13 +149,35 @@ __global__ void __launch_bounds__(CWF_THREADS) cwf_amp_kernel(StackedParams am, 
       }
     }
     const uint32_t steps = 1u << m;
+    double eba = 1.0, ebp = 1.0;
+    if (fast) {  // tha / thp now hold exp(theta) (padded units: factor 1)
+#pragma unroll
+      for (int i = 0; i < NHT; ++i) { tha[i] = i < nh ? exp(tha[i]) : 0.0; thp[i] = i < nh ? exp(thp[i]) : 0.0; }
+      eba = exp(bva);
+      ebp = exp(bvp);
+    }
     for (uint32_t k = 0; k < steps; ++k) {
       const uint32_t i_exp = ibase | (k ^ (k >> 1));
-      double xa = bva, xp = bvp;
+      double amp, phi;  // |psi| = sqrt(exp(-E_am)), phase = -E_ph / 2
+      if (fast) {
+        double pa0 = eba, pa1 = 1.0, pp0 = ebp, pp1 = 1.0;
 #pragma unroll
-      for (int i = 0; i < NHT; ++i)
-        if (i < nh) { xa += softplus20(tha[i]); xp += softplus20(thp[i]); }
-      const double amp = exp(0.5 * xa), phi = 0.5 * xp;  // |psi| = sqrt(exp(-E_am)), phase = -E_ph / 2
+        for (int i = 0; i < NHT; i += 2) {
+          pa0 *= tha[i] > E20 ? tha[i] : 1.0 + tha[i];
+          pa1 *= tha[i + 1] > E20 ? tha[i + 1] : 1.0 + tha[i + 1];
+          pp0 *= thp[i] > E20 ? thp[i] : 1.0 + thp[i];
+          pp1 *= thp[i + 1] > E20 ? thp[i + 1] : 1.0 + thp[i + 1];
+        }
+        amp = sqrt(pa0 * pa1);
+        phi = 0.5 * log(pp0 * pp1);
+      } else {
+        double xa = bva, xp = bvp;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i)
+          if (i < nh) { xa += softplus20(tha[i]); xp += softplus20(thp[i]); }
+        amp = exp(0.5 * xa);
+        phi = 0.5 * xp;
+      }
       double sn, cs;
       sincos(phi, &sn, &cs);
       double tr, ti;
@@ -130,12 +189,22 @@ __global__ void __launch_bounds__(CWF_THREADS) cwf_amp_kernel(StackedParams am, 
         const uint32_t k1 = k + 1;
         const int pbit = __ffs(k1) - 1;
         const uint32_t g1 = k1 ^ (k1 >> 1);
-        const double sgn = ((g1 >> pbit) & 1u) ? 1.0 : -1.0;
+        const bool up = (g1 >> pbit) & 1u;
+        const double sgn = up ? 1.0 : -1.0;
         const int j = si.site[S - 1 - pbit];
+        if (fast) {
+          const double* ea = (up ? EaP : EaM) + j * NHT;
+          const double* ep = (up ? EpP : EpM) + j * NHT;
 #pragma unroll
-        for (int i = 0; i < NHT; ++i) { tha[i] = fma(sgn, Wa[j * NHT + i], tha[i]); thp[i] = fma(sgn, Wp[j * NHT + i], thp[i]); }
-        bva = fma(sgn, ba[j], bva);
-        bvp = fma(sgn, bp[j], bvp);
+          for (int i = 0; i < NHT; ++i) { tha[i] *= ea[i]; thp[i] *= ep[i]; }
+          eba *= eb[(up ? 0 : N) + j];
+          ebp *= eb[(up ? 2 * N : 3 * N) + j];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NHT; ++i) { tha[i] = fma(sgn, Wa[j * NHT + i], tha[i]); thp[i] = fma(sgn, Wp[j * NHT + i], thp[i]); }
+          bva = fma(sgn, ba[j], bva);
+          bvp = fma(sgn, bp[j], bvp);
+        }
       }
     }
   }
@@ -189,10 +258,12 @@ static int launch_cwf_amp(const StackedParams& am, const StackedParams& ph, cons
                           const SiteInfo& si, const double* U, int K, double2* T, double2* D, double* Upsi, int64_t Btotal,
                           cudaStream_t st) {
   const int N = am.N;
-  const size_t smem = ((size_t)2 * N * NHT + 2 * NHT + 2 * round_up(N, 2) + (size_t)K * 8 + 2 * CWF_THREADS) * sizeof(double);
+  const size_t smem = ((size_t)6 * N * NHT + 2 * NHT + 2 * round_up(N, 2) + (size_t)K * 8 + 2 * CWF_THREADS + 4 * N) * sizeof(double);
   if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: parameters do not fit in shared memory");
   QCB_CUDA(cudaFuncSetAttribute(cwf_amp_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-  int tps_log2 = si.S < 7 ? si.S : 7;
+  // threads per sample: long Gray walks amortise the per-thread start-up when there are many samples
+  const int tps_cap = Bc >= 2048 ? 5 : 7;
+  int tps_log2 = si.S < tps_cap ? si.S : tps_cap;
   const int spc = CWF_THREADS >> tps_log2;
   const int64_t grid = (Bc + spc - 1) / spc;
   cwf_amp_kernel<NHT><<<(unsigned)grid, CWF_THREADS, smem, st>>>(am, ph, samples, b0, Bc, si, U, K, tps_log2, T, D, Upsi, Btotal);
