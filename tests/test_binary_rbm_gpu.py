@@ -232,3 +232,82 @@ def test_gradient_reduce_large_batch_tensor_core_path(lib, cuda, n, nh):
     vr = np.random.default_rng(93).standard_normal((2048, n))
     assert_close(rbm.effective_energy_gradient(torch.tensor(vr, device=cuda)), orc.effective_energy_gradient(vr),
                  what="reduced gradient (large batch, real rows)")
+
+
+def test_cd_step_matches_oracle_philox(lib, cuda):
+    """qcb_rbm_cd_step = pos_scale * sum grad E(pos) + neg_scale * sum grad E(v_k) with v_k from the
+    kernel's own Philox stream; the negative batch is left untouched."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, B, C, k = 12, 20, 300, 500, 4
+    W, b, c = make_binary_params(n, nh, 101)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    pos, neg = random_states(B, n, 102), random_states(C, n, 103)
+    vk = o.gibbs_steps_philox(k, neg, seed=555, chain_id0=9, sweep0=3)
+    want = o.effective_energy_gradient(pos) / B - o.effective_energy_gradient(vk) / C
+    args, keep = rbm._param_args()
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+    g = torch.empty(rbm.num_pars, dtype=torch.double, device=cuda)
+    ws = _lib.workspace(cuda, _lib.workspace_bytes(_lib.OP_CD_STEP, n, nh, 0, max(B, C)))
+    _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, k, 555, 9, 3, 1.0 / B, -1.0 / C, _lib.ptr(g), _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    assert_close(g, want, what="CD-k gradient")
+    assert np.array_equal(tn.cpu().numpy(), neg)
+
+
+def test_empty_and_degenerate_inputs(lib, cuda):
+    """Empty batches, zero sweeps and error reporting through the C ABI."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    rbm, orc = _pair(10, 7, 111, cuda)
+    empty = torch.zeros(0, 10, dtype=torch.double, device=cuda)
+    assert rbm.effective_energy(empty).shape == (0,)
+    assert rbm.gibbs_steps(3, empty).shape == (0, 10)
+    assert torch.equal(rbm.effective_energy_gradient(empty), torch.zeros(rbm.num_pars, dtype=torch.double, device=cuda))
+    v = torch.tensor(random_states(9, 10, 112), device=cuda)
+    assert torch.equal(rbm.gibbs_steps(0, v), v)
+    with pytest.raises(ValueError):
+        rbm.effective_energy(torch.zeros(3, 11, dtype=torch.double, device=cuda))
+    big = BinaryRBM(200, 200, gpu=True)
+    with pytest.raises(RuntimeError, match="exceeds the shared-memory resident limit"):
+        big.gibbs_steps(1, torch.zeros(4, 200, dtype=torch.double, device=cuda))
+    rc = lib.qcb_rbm_energy(None, None, None, None, None, 4, 4, 0, None, 1, None, None, 0, None)
+    assert rc == 1 and b"must not be NULL" in lib.qcb_last_error()
+
+
+def test_full_size_properties(lib, cuda):
+    """Size-independent properties at the BASELINE sizes the oracle cannot reach directly:
+    (1) 2^20 chains of N = nh = 64: halves sampled separately (by global chain id) == one call, and two
+        calls of k/2 sweeps == one call of k; (2) exact log Z over 2^30 states equals the closed form
+        obtained by tracing the *visible* units (2^nh terms) and is additive over index ranges."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh, C = 64, 64, 1 << 20
+    W, b, c = make_binary_params(n, nh, 121)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    v0 = (torch.rand(C, n, generator=g, device=cuda) < 0.5).double()
+    whole = rbm.gibbs_steps(4, v0, seed=31337)
+    half = C // 2 + 13
+    lo = rbm.gibbs_steps(4, v0[:half].clone(), seed=31337)
+    hi = rbm.gibbs_steps(4, v0[half:].clone(), seed=31337, chain_id0=half)
+    assert torch.equal(torch.cat([lo, hi]), whole)
+    two = rbm.gibbs_steps(2, rbm.gibbs_steps(2, v0, seed=31337), seed=31337, sweep0=2)
+    assert torch.equal(two, whole)
+    assert set(whole.unique().tolist()) == {0.0, 1.0}
+    frac = float(whole.mean())
+    assert 0.3 < frac < 0.7
+    # exact Z at N = 30
+    n2, nh2 = 30, 10
+    W2, b2, c2 = make_binary_params(n2, nh2, 122, bias_scale=0.3)
+    rbm2 = load_binary(BinaryRBM(n2, nh2, gpu=True), W2, b2, c2)
+    want = BinaryRBMOracle(W2, b2, c2).log_partition_hidden_side()
+    out2 = rbm2.log_partition().cpu().numpy()
+    got = out2[0] + np.log(out2[1])
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+    cut = (1 << n2) // 3 + 7
+    a, bb = rbm2.log_partition(0, cut).cpu().numpy(), rbm2.log_partition(cut, (1 << n2) - cut).cpu().numpy()
+    m = max(a[0], bb[0])
+    both = m + np.log(a[1] * np.exp(a[0] - m) + bb[1] * np.exp(bb[0] - m))
+    assert abs(both - want) <= 1e-10 * abs(want)
