@@ -136,6 +136,13 @@ int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const
 int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const double* c, const double* d,
                        int N, int nh, int na, const double* v, int64_t rows, double* g_rows, void* stream);
 
+/* out (rows, N): out[r][i] = E(v_r) - E(v_r with visible unit i flipped) = log p(v^(i)) - log p(v), for binary rows.
+ * The single-spin-flip ratios psi(v^(i)) / psi(v) of the local estimators (observables/pauli.py:50-83,
+ * examples/Tutorial4_DataGeneration_CalculateObservables/quantum_ising_chain.py:45-78) are
+ * exp(out / 2) for the amplitude RBM and exp(i out / 2) for the phase RBM. */
+int qcb_rbm_flip_logratio(const double* W, const double* U, const double* b, const double* c, const double* d,
+                          int N, int nh, int na, const double* v, int64_t rows, double* out, void* stream);
+
 /* Fused CD-k negative phase: k Gibbs sweeps on v (C, N) in place, then
  * g += scale * sum_chains grad E(v_k)  (nn_states/neural_state.py:443-445 with scale = -1/C). */
 int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const double* c, const double* d,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "qcb_rbm_grad_reduce": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_double, _P, c_int, _P,
                                     c_size_t, _P]),
     "qcb_rbm_grad_batch": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
+    "qcb_rbm_flip_logratio": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "qcb_rbm_cdk_neg": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64, c_uint64,
                                 _P, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_cd_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_uint64, c_uint64,

@@ -41,6 +41,7 @@ int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, doubl
 int run_exact_grad_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, double* g, void* ws,
                          size_t ws_bytes, cudaStream_t st);
 int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double* g_rows, cudaStream_t st);
+int run_flip_logratio(const StackedParams& p, const double* v, int64_t rows, double* out, cudaStream_t st);
 size_t enum_workspace_bytes();
 int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
                    cudaStream_t st);
@@ -160,6 +161,15 @@ int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const 
   if (rc != QCB_OK) return rc;
   if (rows < 0 || (rows > 0 && (v == nullptr || g_rows == nullptr))) return fail(QCB_ERR_BAD_ARG, "grad_batch: bad rows/v/out");
   return run_grad_batch(p, v, rows, g_rows, (cudaStream_t)stream);
+}
+
+int qcb_rbm_flip_logratio(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
+                          int nh, int na, const double* v, int64_t rows, double* out, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (rows < 0 || (rows > 0 && (v == nullptr || out == nullptr))) return fail(QCB_ERR_BAD_ARG, "flip_logratio: bad rows/v/out");
+  return run_flip_logratio(p, v, rows, out, (cudaStream_t)stream);
 }
 
 int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,

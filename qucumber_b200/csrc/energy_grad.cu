@@ -177,4 +177,61 @@ int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double
   return QCB_OK;
 }
 
+// ---- single-spin-flip log-ratios -----------------------------------------------------------------
+// out[r][i] = E(v_r) - E(v_r with visible unit i flipped) = log p(v^(i)) - log p(v): the quantity
+// every local estimator built from psi(v^(i)) / psi(v) needs (SigmaX / SigmaY, TFIM energy:
+// observables/pauli.py:50-83, examples/Tutorial4/quantum_ising_chain.py:45-78).  The reference
+// evaluates the full energy of N flipped copies of the batch; here theta = Wst v + hb is computed
+// once per row and each flip costs nh softplus evaluations of theta_h +- W_hi.
+__global__ void __launch_bounds__(ROWS_THREADS) rows_flip_kernel(AffineSpec s, const double* __restrict__ v,
+                                                                 const double* __restrict__ vb, int64_t rows,
+                                                                 double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ws = reinterpret_cast<double*>(smem_raw);
+  const int N = s.n_in1, H = s.n_out;
+  const int LD = N | 1;
+  double* bs = Ws + (size_t)H * LD;
+  double* vbs = bs + H;
+  double* wbuf = vbs + N + (threadIdx.x >> 5) * (N + 2 * H);  // per warp: v (N), theta (H), softplus(theta) (H)
+  double* vrow = wbuf;
+  double* th = wbuf + N;
+  double* sp = th + H;
+  stage_affine(s, Ws, LD, bs);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) vbs[i] = vb[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * ROWS_WARPS + warp; r < rows; r += (int64_t)gridDim.x * ROWS_WARPS) {
+    for (int i = lane; i < N; i += 32) vrow[i] = v[r * N + i];
+    __syncwarp();
+    for (int o = lane; o < H; o += 32) {
+      const double* wrow = Ws + (size_t)o * LD;
+      double t = bs[o];
+      for (int i = 0; i < N; ++i) t = fma(wrow[i], vrow[i], t);
+      th[o] = t;
+      sp[o] = softplus20(t);
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      const double sgn = 1.0 - 2.0 * vrow[i];  // flipping a binary unit changes it by +-1
+      double d = sgn * vbs[i];
+      for (int o = 0; o < H; ++o) d += softplus20(fma(sgn, Ws[(size_t)o * LD + i], th[o])) - sp[o];
+      out[r * N + i] = d;
+    }
+    __syncwarp();
+  }
+}
+
+int run_flip_logratio(const StackedParams& p, const double* v, int64_t rows, double* out, cudaStream_t st) {
+  if (rows == 0) return QCB_OK;
+  const int N = p.N, H = p.nhid();
+  const size_t smem = ((size_t)H * (N | 1) + H + N + (size_t)ROWS_WARPS * (N + 2 * H)) * sizeof(double);
+  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "flip_logratio: layer %d x %d does not fit in shared memory", H, N);
+  QCB_CUDA(cudaFuncSetAttribute(rows_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+  const int64_t need = (rows + ROWS_WARPS - 1) / ROWS_WARPS;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  rows_flip_kernel<<<(int)(need < cap ? need : cap), ROWS_THREADS, smem, st>>>(stacked_hidden_spec(p), v, p.b, rows, out);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
 }  // namespace qcb

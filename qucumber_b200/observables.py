@@ -1,0 +1,94 @@
+"""Local estimators on top of the CUDA RBMs (reference: qucumber/observables/pauli.py,
+observable.py:223-249). QuCumber's own observable classes keep working with the drop-in states (they
+call ``nn_state.sample`` / ``psi`` / ``importance_sampling_*``); the classes here compute the same
+estimators from ONE fused kernel call per RBM: qcb_rbm_flip_logratio gives
+log p(v^(i)) - log p(v) for all N single-spin flips of every sample, instead of N full energy
+evaluations of flipped copies of the batch."""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def flip_logratio(rbm, samples):
+    """(rows, N) tensor of E(v) - E(v with unit i flipped) for a BinaryRBM / PurificationRBM."""
+    lib = _lib.load()
+    args, keep = rbm._param_args()
+    like = keep[0]
+    rows = samples.to(like).reshape(-1, rbm.num_visible).contiguous()
+    out = torch.empty_like(rows)
+    _lib.check(lib.qcb_rbm_flip_logratio(*args, _lib.ptr(rows), rows.shape[0], _lib.ptr(out), _lib.stream_ptr(rows.device)),
+               "qcb_rbm_flip_logratio")
+    return out
+
+
+class _Estimator:
+    def statistics_from_samples(self, nn_state, samples):
+        """mean / variance / std_error / num_samples of the estimator over the given samples."""
+        obs = self.apply(nn_state, samples)
+        variance, mean = torch.var_mean(obs)
+        variance, mean = variance.item(), mean.item()
+        return {"mean": mean, "variance": variance, "std_error": float(np.sqrt(variance / len(obs))), "num_samples": len(obs)}
+
+    def statistics(self, nn_state, num_samples, num_chains=0, burn_in=1000, steps=1):
+        """Draw samples with block Gibbs (burn-in, then `steps` sweeps between recorded states, chains kept
+        on the device) and accumulate the statistics batch by batch like observable.py:135-221."""
+        num_chains = num_chains if num_chains > 0 else num_samples
+        chains = nn_state.sample(k=burn_in, num_samples=min(num_chains, num_samples))
+        total, s1, s2 = 0, 0.0, 0.0
+        while total < num_samples:
+            if total > 0:
+                chains = nn_state.sample(k=steps, initial_state=chains, overwrite=True)
+            take = min(chains.shape[0], num_samples - total)
+            obs = self.apply(nn_state, chains[:take])
+            s1 += float(obs.sum())
+            s2 += float((obs * obs).sum())
+            total += take
+        mean = s1 / total
+        variance = max(s2 - total * mean * mean, 0.0) / max(total - 1, 1)
+        return {"mean": mean, "variance": variance, "std_error": float(np.sqrt(variance / total)), "num_samples": total}
+
+
+class SigmaZ(_Estimator):
+    """Average magnetisation along Z (pauli.py:138-171): mean of the +-1 spins of each sample."""
+
+    def __init__(self, absolute=False):
+        self.name, self.symbol, self.absolute = "SigmaZ", "Z", absolute
+
+    def apply(self, nn_state, samples):
+        res = samples.to(device=nn_state.device, dtype=torch.double).mul(2.0).sub(1.0).mean(1)
+        return res.abs() if self.absolute else res
+
+
+class SigmaX(_Estimator):
+    """Average magnetisation along X (pauli.py:36-83): (1/N) sum_i Re[psi(v^(i)) / psi(v)]."""
+
+    def __init__(self, absolute=False):
+        self.name, self.symbol, self.absolute = "SigmaX", "X", absolute
+
+    def apply(self, nn_state, samples):
+        samples = samples.to(device=nn_state.device, dtype=torch.double)
+        ratio = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp()
+        rbm_ph = getattr(nn_state, "rbm_ph", None)
+        if rbm_ph is not None and hasattr(nn_state, "phase"):
+            ratio = ratio * (0.5 * flip_logratio(rbm_ph, samples)).cos()
+        res = ratio.mean(1)
+        return res.abs() if self.absolute else res
+
+
+class TFIMChainEnergy(_Estimator):
+    """Energy per site of the 1-D transverse-field Ising chain, -J sum s_i s_{i+1} - h sum sigma^x_i
+    (examples/Tutorial4_DataGeneration_CalculateObservables/quantum_ising_chain.py:24-78), open
+    boundaries unless ``periodic_bcs``; positive wavefunctions."""
+
+    def __init__(self, h, periodic_bcs=False):
+        self.name, self.symbol, self.h, self.periodic_bcs = "TFIMChainEnergy", "E", h, periodic_bcs
+
+    def apply(self, nn_state, samples):
+        samples = samples.to(device=nn_state.device, dtype=torch.double)
+        spins = samples.mul(2.0).sub(1.0)
+        interaction = (spins[:, :-1] * spins[:, 1:]).sum(1)
+        if self.periodic_bcs:
+            interaction = interaction + spins[:, 0] * spins[:, -1]
+        transverse = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp().sum(1)
+        return -(interaction + self.h * transverse) / samples.shape[-1]

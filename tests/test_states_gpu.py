@@ -371,3 +371,66 @@ def test_density_rotated_large_expansion(lib, cuda):
     ga, gp = orc.dm_rotated_gradient(am, ph, list(basis), samples)
     assert_close(rg[0], ga, what="rotated grad (amplitude)")
     assert_close(rg[1], gp, rtol=1e-9, what="rotated grad (phase)")
+
+
+# ------------------------------------------------------------------------------- local estimators
+def _flip_oracle(o, v):
+    out = np.zeros_like(v)
+    e0 = o.effective_energy(v)
+    for i in range(v.shape[1]):
+        vf = v.copy()
+        vf[:, i] = 1.0 - vf[:, i]
+        out[:, i] = e0 - o.effective_energy(vf)
+    return out
+
+
+@pytest.mark.parametrize("n,nh,na", [(10, 10, 0), (64, 64, 0), (7, 40, 0), (6, 5, 4)])
+def test_flip_logratio(lib, cuda, n, nh, na):
+    from qucumber_b200 import BinaryRBM, PurificationRBM
+    from qucumber_b200.observables import flip_logratio
+
+    v = random_states(333, n, 131)
+    if na:
+        pr = make_purification_params(n, nh, na, 132)
+        rbm, o = load_purification(PurificationRBM(n, nh, na, gpu=True), *pr), orc.PurificationRBMOracle(*pr)
+    else:
+        pr = make_binary_params(n, nh, 132)
+        rbm, o = load_binary(BinaryRBM(n, nh, gpu=True), *pr), orc.BinaryRBMOracle(*pr)
+    assert_close(flip_logratio(rbm, torch.tensor(v, device=cuda)), _flip_oracle(o, v), rtol=1e-9, what="flip log-ratios")
+
+
+def test_observables_tutorial4_style(lib, cuda):
+    """Config 3 in miniature: sample many chains (N = 10, k = 100), then SigmaZ / SigmaX / TFIM-energy
+    estimates; checked (a) sample by sample against the oracle's psi ratios, (b) statistically against
+    the exact expectation values over the 2^10 states (reference tests/test_observables.py:177-197 style)."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.observables import SigmaX, SigmaZ, TFIMChainEnergy
+
+    n = 10
+    g = gold("binary_rbm_tfim10.npz")
+    W, b, c = g["weights"] * 0.5, g["visible_bias"] * 0.5, g["hidden_bias"] * 0.5
+    nn = PositiveWaveFunction(n, n, gpu=True)
+    load_binary(nn.rbm_am, W, b, c)
+    o = orc.BinaryRBMOracle(W, b, c)
+    space = orc.hilbert_rows(n)
+    p = np.exp(-o.effective_energy(space))
+    p /= p.sum()
+    ratios = np.exp(0.5 * _flip_oracle(o, space))           # psi(v^(i)) / psi(v)
+    sx_exact = float((p * ratios.mean(1)).sum())
+    sz_exact = float((p * np.abs((2 * space - 1).mean(1))).sum())
+    spins = 2 * space - 1
+    e_local = -((spins[:, :-1] * spins[:, 1:]).sum(1) + 1.0 * ratios.sum(1)) / n
+    e_exact = float((p * e_local).sum())
+    # (a) per-sample parity
+    some = torch.tensor(space[::7], device=cuda)
+    assert_close(SigmaX().apply(nn, some), ratios[::7].mean(1), rtol=1e-9, what="SigmaX per sample")
+    assert_close(TFIMChainEnergy(1.0).apply(nn, some), e_local[::7], rtol=1e-9, what="TFIM local energy")
+    # (b) statistics from 10^6 chains after 100 sweeps
+    torch.manual_seed(11)
+    samples = nn.sample(k=100, num_samples=1_000_000)
+    for est, exact in ((SigmaX(), sx_exact), (SigmaZ(absolute=True), sz_exact), (TFIMChainEnergy(1.0), e_exact)):
+        st = est.statistics_from_samples(nn, samples)
+        assert st["num_samples"] == 1_000_000
+        assert abs(st["mean"] - exact) < 6 * st["std_error"] + 1e-12, (est.name, st, exact)
+    st = SigmaX().statistics(nn, num_samples=20000, num_chains=5000, burn_in=50, steps=2)
+    assert st["num_samples"] == 20000 and abs(st["mean"] - sx_exact) < 8 * st["std_error"]
