@@ -246,6 +246,30 @@ def extra_metrics(dev, lib_mod):
                            "chain_sweeps_per_s": (1 << 20) * 10 / (ms * 1e-3)}
     except Exception as exc:  # pragma: no cover
         out["cdk_step"] = {"error": str(exc)}
+    # ---- generation + observables (config 3): 2^20 chains, N = nh = 10, k = 100, then SigmaZ / SigmaX estimates
+    try:
+        from qucumber_b200.observables import SigmaX, SigmaZ
+
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "binary_rbm_tfim10.npz"))
+        t4 = PositiveWaveFunction(10, 10, gpu=True)
+        with torch.no_grad():
+            t4.rbm_am.weights.copy_(torch.tensor(gold["weights"])); t4.rbm_am.visible_bias.copy_(torch.tensor(gold["visible_bias"]))
+            t4.rbm_am.hidden_bias.copy_(torch.tensor(gold["hidden_bias"]))
+        C4 = 1 << 20
+        v4 = (torch.rand(C4, 10, device=dev) < 0.5).double()
+        ms_s, samples4 = timed(lambda: t4.rbm_am.gibbs_steps(100, v4, seed=5))
+        ms_o, _ = timed(lambda: (SigmaZ(absolute=True).statistics_from_samples(t4, samples4), SigmaX().statistics_from_samples(t4, samples4)))
+        Wc = torch.tensor(gold["weights"]); bc = torch.tensor(gold["visible_bias"]); cc = torch.tensor(gold["hidden_bias"])
+        vc = (torch.rand(1 << 17, 10) < 0.5).double()
+        t0 = _time.perf_counter()
+        cpu_path.gibbs_steps_cpu(Wc, bc, cc, 20, vc)
+        cpu_s = _time.perf_counter() - t0
+        out["generation_n10"] = {"chains": C4, "k": 100, "ms": ms_s, "chain_sweeps_per_s": C4 * 100 / (ms_s * 1e-3),
+                                 "observables_ms": ms_o, "cpu_reference_chain_sweeps_per_s": (1 << 17) * 20 / cpu_s,
+                                 "cores": torch.get_num_threads()}
+    except Exception as exc:  # pragma: no cover
+        out["generation_n10"] = {"error": str(exc)}
+
     # ---- rotated-basis gradient (config 5): ComplexWaveFunction N = nh = 20, S = 10 rotated sites
     try:
         from oracle import rbm_oracle as orc
