@@ -75,8 +75,14 @@ static int launch_rows_affine(const AffineSpec& s, const double* x, const double
   return QCB_OK;
 }
 
+int try_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int64_t rows, double* E, int* handled,
+                    cudaStream_t st);
+
 int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st) {
   if (rows == 0) return QCB_OK;
+  int handled = 0;  // large batches: theta on the FP64 tensor cores (grad_reduce_dmma.cu)
+  const int rc = try_energy_dmma(stacked_hidden_spec(p), v, p.b, rows, E, &handled, st);
+  if (rc != QCB_OK || handled) return rc;
   return launch_rows_affine<0>(stacked_hidden_spec(p), v, nullptr, p.b, rows, E, st);
 }
 

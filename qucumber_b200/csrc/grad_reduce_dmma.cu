@@ -216,4 +216,111 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
   return rc;
 }
 
+// ---- effective energy on the tensor cores (large batches) ---------------------------------------
+// E[r] = -(b . v_r + sum_i softplus(theta_i)), theta = Wst v_r + hb as DMMA tiles (phase 1 above).
+// The softplus sum is taken in product form per lane, exactly reproducing torch's threshold:
+//   sum_i softplus(theta_i) = sum_{theta_i > 20} theta_i + log prod_{theta_i <= 20} (1 + e^{theta_i});
+// a lane multiplies at most 32 factors <= 1 + e^20 before taking the log, so nothing can overflow.
+template <int NB8, int HB8>
+__global__ void __launch_bounds__(GD_THREADS) rows_energy_dmma_kernel(AffineSpec s, const double* __restrict__ v,
+                                                                      const double* __restrict__ vb, int64_t rows,
+                                                                      double* __restrict__ E) {
+  constexpr int Npad = 8 * NB8, Hpad = 8 * HB8;
+  constexpr int KN4 = 2 * NB8;
+  constexpr int LDV = Npad + 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Wf = reinterpret_cast<double*>(smem_raw);     // [KN4][HB8][32]
+  double* hb = Wf + (size_t)KN4 * HB8 * 32;             // [Hpad]
+  double* vbs = hb + Hpad;                              // [Npad]
+  double* Vt = vbs + Npad;                              // [GD_TR][LDV]
+  const int N = s.n_in1, H = s.n_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int idx = threadIdx.x; idx < KN4 * HB8 * 32; idx += GD_THREADS) {
+    const int l = idx & 31, nb = (idx >> 5) % HB8, kk = (idx >> 5) / HB8;
+    const int hid = 8 * nb + (l >> 2), vis = 4 * kk + (l & 3);
+    Wf[idx] = (hid < H && vis < N) ? s.mop(hid, vis) : 0.0;
+  }
+  // padded hidden units get a bias of -inf-like size so that they contribute log(1 + 0) = 0
+  for (int i = threadIdx.x; i < Hpad; i += GD_THREADS) hb[i] = i < H ? s.bias(i) : -1.0e300;
+  for (int i = threadIdx.x; i < Npad; i += GD_THREADS) vbs[i] = i < N ? vb[i] : 0.0;
+  for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
+  __syncthreads();
+  const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * GD_TR;
+    for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
+      const int rr = idx / N, j = idx - rr * N;
+      Vt[rr * LDV + j] = r0 + rr < rows ? v[(r0 + rr) * N + j] : 0.0;
+    }
+    __syncthreads();
+    double acc[HB8][2];
+#pragma unroll
+    for (int nb = 0; nb < HB8; ++nb) {
+      acc[nb][0] = hb[8 * nb + 2 * t];
+      acc[nb][1] = hb[8 * nb + 2 * t + 1];
+    }
+    const double* arow = Vt + (8 * warp + g) * LDV + t;
+    double bv = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < KN4; ++kk) {
+      const double a = arow[4 * kk];
+      bv = fma(vbs[4 * kk + t], a, bv);
+      const double* bf = Wf + (size_t)kk * HB8 * 32 + lane;
+#pragma unroll
+      for (int nb = 0; nb < HB8; ++nb) dmma884(acc[nb][0], acc[nb][1], a, bf[nb * 32]);
+    }
+    double lin = bv, prod = 1.0;
+#pragma unroll
+    for (int nb = 0; nb < HB8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double th = acc[nb][e];
+        if (th > 20.0) lin += th; else prod *= 1.0 + exp(th);
+      }
+    }
+    double val = lin + log(prod);
+    val += __shfl_xor_sync(0xffffffffu, val, 1);
+    val += __shfl_xor_sync(0xffffffffu, val, 2);
+    const int64_t r = r0 + 8 * warp + g;
+    if (t == 0 && r < rows) E[r] = -val;
+    __syncthreads();
+  }
+}
+
+template <int NB8, int HB8>
+static int launch_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int64_t rows, double* E, int grid,
+                              cudaStream_t st) {
+  const size_t smem = ((size_t)2 * NB8 * HB8 * 32 + 8 * HB8 + 8 * NB8 + (size_t)GD_TR * (8 * NB8 + 4)) * sizeof(double);
+  QCB_CUDA(cudaFuncSetAttribute(rows_energy_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rows_energy_dmma_kernel<NB8, HB8><<<grid, GD_THREADS, smem, st>>>(s, v, vb, rows, E);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+// *handled = 1 when the tensor-core path took the batch (rows >= 2048 and the layer fits)
+int try_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int64_t rows, double* E, int* handled,
+                    cudaStream_t st) {
+  *handled = 0;
+  if (rows < 2048) return QCB_OK;
+  const int NB8 = pick8(s.n_in1), HB8 = pick8(s.n_out);
+  if (NB8 == 0 || HB8 == 0 || HB8 > 8) return QCB_OK;  // a lane multiplies 2 HB8 <= 16 factors before its log
+  const size_t smem = ((size_t)2 * NB8 * HB8 * 32 + 8 * HB8 + 8 * NB8 + (size_t)GD_TR * (8 * NB8 + 4)) * sizeof(double);
+  if (smem > SMEM_LIMIT) return QCB_OK;
+  const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
+  const int64_t cap = (int64_t)sm_count() * 2;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  int rc = QCB_OK;
+#define QCB_EN_CASE(NB, HBx) \
+  if (NB8 == NB && HB8 == HBx) rc = launch_energy_dmma<NB, HBx>(s, v, vb, rows, E, grid, st); else
+  QCB_EN_CASE(2, 2) QCB_EN_CASE(2, 4) QCB_EN_CASE(2, 8)
+  QCB_EN_CASE(4, 2) QCB_EN_CASE(4, 4) QCB_EN_CASE(4, 8)
+  QCB_EN_CASE(8, 2) QCB_EN_CASE(8, 4) QCB_EN_CASE(8, 8)
+  QCB_EN_CASE(16, 2) QCB_EN_CASE(16, 4) QCB_EN_CASE(16, 8)
+  return QCB_OK;
+#undef QCB_EN_CASE
+  if (rc == QCB_OK) *handled = 1;
+  return rc;
+}
+
 }  // namespace qcb

@@ -311,3 +311,22 @@ def test_full_size_properties(lib, cuda):
     m = max(a[0], bb[0])
     both = m + np.log(a[1] * np.exp(a[0] - m) + bb[1] * np.exp(bb[0] - m))
     assert abs(both - want) <= 1e-10 * abs(want)
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (64, 64), (33, 60), (100, 40), (4, 9)])
+def test_effective_energy_large_batch_tensor_core_path(lib, cuda, n, nh):
+    """Batches >= 2048 rows: theta on the FP64 tensor cores, softplus sum in threshold-exact product form."""
+    from qucumber_b200 import BinaryRBM
+
+    rbm, orc = _pair(n, nh, 141, cuda)
+    v = random_states(4099, n, 142)
+    assert_close(rbm.effective_energy(torch.tensor(v, device=cuda)), orc.effective_energy(v), what="energy (large batch)")
+    vr = np.random.default_rng(143).standard_normal((2048, n)) * 3.0
+    assert_close(rbm.effective_energy(torch.tensor(vr, device=cuda)), orc.effective_energy(vr), what="energy (large batch, real rows)")
+    # pre-activations straddling torch's softplus threshold, and very negative ones
+    W, b, c = make_binary_params(n, nh, 144)
+    c = c + np.where(np.arange(nh) % 4 == 0, 20.00005, np.where(np.arange(nh) % 4 == 1, -45.0, 0.0))
+    W = W * 1e-4
+    r2 = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    assert_close(r2.effective_energy(torch.tensor(v, device=cuda)), BinaryRBMOracle(W, b, c).effective_energy(v), rtol=1e-13,
+                 what="energy near threshold (large batch)")
