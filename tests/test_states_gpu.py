@@ -434,3 +434,77 @@ def test_observables_tutorial4_style(lib, cuda):
         assert abs(st["mean"] - exact) < 6 * st["std_error"] + 1e-12, (est.name, st, exact)
     st = SigmaX().statistics(nn, num_samples=20000, num_chains=5000, burn_in=50, steps=2)
     assert st["num_samples"] == 20000 and abs(st["mean"] - sx_exact) < 8 * st["std_error"]
+
+
+# ------------------------------------------------------------------------------- finite differences
+def _numeric_grad(fn, param, eps=1e-6):
+    """Central finite differences of a scalar metric w.r.t. one flat parameter tensor (the reference's
+    own gradient check, tests/grads_utils.py:52-110, EPS = 1e-6, abs tolerance 2e-8)."""
+    flat = param.data.view(-1)
+    out = torch.zeros_like(flat)
+    for i in range(flat.numel()):
+        old = flat[i].item()
+        flat[i] = old + eps
+        fp = fn()
+        flat[i] = old - eps
+        fm = fn()
+        flat[i] = old
+        out[i] = (fp - fm) / (2 * eps)
+    return out
+
+
+def test_finite_difference_gradients_positive(lib, cuda):
+    """d NLL / d params (central differences through the CUDA metrics) == compute_exact_gradients,
+    mirroring reference tests/test_grads.py:247-279 for the PositiveWaveFunction."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.utils import training_statistics as ts
+
+    torch.manual_seed(1234)
+    n = 4
+    nn = PositiveWaveFunction(n, 5, gpu=True)
+    with torch.no_grad():
+        nn.rbm_am.visible_bias.copy_(0.1 * torch.randn(n, dtype=torch.double))
+        nn.rbm_am.hidden_bias.copy_(0.1 * torch.randn(5, dtype=torch.double))
+    data = torch.tensor(random_states(500, n, 151), device=cuda)
+    space = nn.generate_hilbert_space()
+    alg = nn.compute_exact_gradients(data, space)[0]
+    num = torch.cat([_numeric_grad(lambda: ts.NLL(nn, data, space), p) for p in nn.rbm_am.parameters()])
+    assert float((alg - num).abs().max()) < 2e-8
+    # KL against a random normalised target: gradient = sum_v (p_target - p_model) grad E
+    tgt = np.random.default_rng(152).random(1 << n)
+    tgt = np.sqrt(tgt / tgt.sum())
+    target = torch.tensor(np.stack([tgt, np.zeros_like(tgt)]), device=cuda)
+    numk = torch.cat([_numeric_grad(lambda: ts.KL(nn, target, space), p) for p in nn.rbm_am.parameters()])
+    Z = nn.normalization(space)
+    algk = torch.zeros_like(numk)
+    for i in range(len(space)):
+        g_i = nn.gradient(space[i])[0]
+        algk += (target[0, i] ** 2) * g_i - nn.probability(space[i], Z) * g_i
+    assert float((algk - numk).abs().max()) < 2e-8
+
+
+def test_finite_difference_gradients_complex_and_density(lib, cuda):
+    """Same check for the rotated-basis gradients: d NLL / d params of both RBMs vs compute_exact_gradients
+    on the reference's 2-qubit fixtures (tests/data/test_grad_data.pkl)."""
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("complex_2qubits.npz")
+    nn = _load_cwf(g, 2, 2)
+    space = nn.generate_hilbert_space()
+    samples = torch.tensor(g["train_samples"][:200], device=cuda)
+    tb = split_bases(g["train_bases"][:200])
+    alg = nn.compute_exact_gradients(samples, space, bases_batch=tb)
+    for net, a in zip(("rbm_am", "rbm_ph"), alg):
+        num = torch.cat([_numeric_grad(lambda: ts.NLL(nn, samples, space, sample_bases=tb), p) for p in getattr(nn, net).parameters()])
+        assert float((a - num).abs().max()) < 2e-8, net
+    gd = gold("density_2qubits.npz")
+    dm = _load_dm(gd, 2, 2, 2)
+    spaced = dm.generate_hilbert_space()
+    sd = torch.tensor(gd["train_samples"][:180], device=cuda)
+    tbd = split_bases(gd["train_bases"][:180])
+    algd = dm.compute_exact_gradients(sd, spaced, bases_batch=tbd)
+    for net, a in zip(("rbm_am", "rbm_ph"), algd):
+        num = torch.cat([_numeric_grad(lambda: ts.NLL(dm, sd, spaced, sample_bases=tbd), p) for p in getattr(dm, net).parameters()])
+        # the reference's +1e-8 regulariser in 1/(UrhoU + 1e-8) makes its analytic gradient differ from the
+        # true derivative at the 1e-8 level (density_matrix.py:296); its own test uses the same tolerance class
+        assert float((a - num).abs().max()) < 5e-7, (net, float((a - num).abs().max()))
