@@ -246,6 +246,38 @@ def extra_metrics(dev, lib_mod):
                            "chain_sweeps_per_s": (1 << 20) * 10 / (ms * 1e-3)}
     except Exception as exc:  # pragma: no cover
         out["cdk_step"] = {"error": str(exc)}
+    # ---- Tutorial 2 / 3 epochs (config 2): rotated-basis training of 2-qubit Complex / Density states
+    try:
+        from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+        def bases_of(arr):
+            return np.array([list(str(x)) for x in arr])
+
+        g2 = np.load(os.path.join(ROOT, "tests", "golden", "complex_2qubits.npz"))
+        cw2 = ComplexWaveFunction(2, 2, gpu=True)
+        d2, b2 = torch.tensor(g2["train_samples"]), bases_of(g2["train_bases"])
+        cw2.fit(d2, epochs=1, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=b2)
+        torch.cuda.synchronize(dev)
+        t0 = _time.perf_counter()
+        cw2.fit(d2, epochs=5, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=b2)
+        torch.cuda.synchronize(dev)
+        ms_c = (_time.perf_counter() - t0) / 5 * 1e3
+        g3 = np.load(os.path.join(ROOT, "tests", "golden", "density_2qubits.npz"))
+        dm2 = DensityMatrix(2, 2, 2, gpu=True)
+        d3, b3 = torch.tensor(g3["train_samples"]), bases_of(g3["train_bases"])
+        dm2.fit(d3, epochs=1, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=b3)
+        torch.cuda.synchronize(dev)
+        t0 = _time.perf_counter()
+        dm2.fit(d3, epochs=5, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=b3)
+        torch.cuda.synchronize(dev)
+        ms_d = (_time.perf_counter() - t0) / 5 * 1e3
+        out["two_qubit_epochs"] = {"complex_ms_per_epoch": ms_c, "complex_samples": int(d2.shape[0]),
+                                   "density_ms_per_epoch": ms_d, "density_samples": int(d3.shape[0]),
+                                   "note": "pos = neg = 100, CD-10, SGD; notebook timings of the reference (unknown CPU): "
+                                           "98 ms/epoch (1000 samples) and 350 ms/epoch (900 samples, Adadelta)"}
+    except Exception as exc:  # pragma: no cover
+        out["two_qubit_epochs"] = {"error": str(exc)}
+
     # ---- generation + observables (config 3): 2^20 chains, N = nh = 10, k = 100, then SigmaZ / SigmaX estimates
     try:
         from qucumber_b200.observables import SigmaX, SigmaZ
