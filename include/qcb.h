@@ -93,6 +93,19 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
                   uint64_t seed, uint64_t chain_id0, uint64_t sweep0, const double* uniforms,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* Kernel selection for qcb_rbm_gibbs when uniforms == NULL.  mode 0 (default): layers of up to 64 units use
+ * the integer-exact tensor-core filter (csrc/gibbs_imma.cu: W v in exact 24-bit fixed point on the int8
+ * tensor cores, FP64 re-evaluation of the units the rigorous error bound cannot decide); mode 1: always
+ * the FP64 tensor-core kernel (csrc/gibbs.cu).  Both draw the same numbers and make the same decisions. */
+int qcb_set_gibbs_mode(int mode);
+
+/* Test hook: runs the integer-filter kernel and reports in stats2 (device, two uint64, caller-zeroed)
+ * [0] = 2^20 * max over re-evaluated units of |x~ - x| / dx (must stay below 2^20: the bound holds),
+ * [1] = number of re-evaluated units. */
+int qcb_debug_gibbs_filter(const double* W, const double* U, const double* b, const double* c, const double* d,
+                           int N, int nh, int na, double* v, int64_t C, int k, uint64_t seed,
+                           unsigned long long* stats2, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Conditionals --------------------------------------------------------------------
  * out (rows, n_out) = clamp(sigmoid(x M^T + bias [+ x2 M2^T]), 0, 1).
  * prob_h_given_v: M = W (nh, N), transpose_m = 0;  prob_v_given_h: M = W used as (N, nh),

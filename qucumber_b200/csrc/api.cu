@@ -28,6 +28,9 @@ int fail(int code, const char* fmt, ...) {
 
 // implemented in the other translation units
 size_t gibbs_workspace_bytes(int N, int nhid);
+extern int g_gibbs_mode;
+int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                   uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
 int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st);
@@ -111,6 +114,26 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
   if (rc != QCB_OK) return rc;
   if (C < 0 || k < 0 || (C > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "gibbs: bad C/k/v");
   return run_gibbs(p, v, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_set_gibbs_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (auto) or 1 (FP64 tensor cores only)");
+  g_gibbs_mode = mode;
+  return QCB_OK;
+}
+
+int qcb_debug_gibbs_filter(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                           int na, double* v, int64_t C, int k, uint64_t seed, unsigned long long* stats2, void* ws,
+                           size_t ws_bytes, void* stream) {
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (stats2 == nullptr || v == nullptr) return fail(QCB_ERR_BAD_ARG, "debug_gibbs_filter: NULL argument");
+  int handled = 0;
+  rc = try_gibbs_imma(p, v, v, C, k, seed, 0, 0, ws, ws_bytes, stats2, &handled, (cudaStream_t)stream);
+  if (rc != QCB_OK) return rc;
+  if (!handled) return fail(QCB_ERR_UNSUPPORTED, "debug_gibbs_filter: shape not handled by the integer filter kernel");
+  return QCB_OK;
 }
 
 int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,

@@ -370,10 +370,13 @@ static int pick_blocks(int units) {
   return 0;
 }
 
+size_t gibbs_imma_workspace_bytes(int N, int nhid);
+
 size_t gibbs_workspace_bytes(int N, int nhid) {
   const int HB = pick_blocks(nhid), VB = pick_blocks(N);
   if (HB == 0 || VB == 0) return 0;
-  return align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256);
+  const size_t a = align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256), b = gibbs_imma_workspace_bytes(N, nhid);
+  return a > b ? a : b;
 }
 
 template <int HB, int VB>
@@ -395,6 +398,12 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
   return QCB_OK;
 }
 
+int g_gibbs_mode = 0;  // 0: integer-exact IMMA filter where it applies, 1: always the FP64 DMMA kernel
+
+size_t gibbs_imma_workspace_bytes(int N, int nhid);
+int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                   uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
+
 int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int nhid = p.nhid();
@@ -405,6 +414,11 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
   const size_t need = gibbs_workspace_bytes(p.N, nhid);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, need);
   if (C == 0 || k == 0) return QCB_OK;
+  if (uniforms == nullptr && g_gibbs_mode == 0) {
+    int handled = 0;
+    const int rc = try_gibbs_imma(p, v_in, v, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
+    if (rc != QCB_OK || handled) return rc;
+  }
 
   double* img = reinterpret_cast<double*>(ws);
   const int total = (int)gibbs_image_doubles(HB, VB);

@@ -1,0 +1,438 @@
+// Block Gibbs with an integer-exact tensor-core filter (layers up to 64 x 64, in-kernel Philox draws).
+//
+// A Bernoulli decision u < sigmoid(x) only needs x in full FP64 when u falls next to p.  This kernel
+// therefore evaluates x~ = W v + c with EXACT integer arithmetic on the int8 tensor cores and keeps the
+// FP64 evaluation for the rare undecided units, so the samples are those of the all-FP64 kernel
+// (gibbs.cu) — same Philox convention, same decisions — at a fraction of the FP64 work:
+//
+//  * W is quantised once per call to 24-bit fixed point, Wq = rint(W 2^s), and split into three signed
+//    int8 digits; a state bit is 0 or 1, so  t = sum_k v_k Wq_ik  is an exact int32 computed by
+//    3 x mma.sync.m16n8k32.s8 (IMMA) passes.  x~ = float(t) 2^-s + c.
+//  * |x~ - x| <= n_in 2^-(s+1) + 2^-22 (sum_k |W_ik| + |c_i|) =: dx  is a rigorous bound (quantisation +
+//    the two float roundings), hence |sigmoid(x~) - sigmoid(x)| <= dx / 4.  The filter decides from the
+//    16-bit cell of u unless p~ lies within margin = dx/4 + 2^-17 of it (2^-17 covers the float sigmoid);
+//    undecided units (~1e-4 of them) recompute x in FP64 from the original doubles and compare the full
+//    53-bit uniform with the exact sigmoid (fixup_slow_imma, out of line).
+//  * a warp owns 16 chains (two rows of the M = 16 tile per lane); states are bit masks in registers,
+//    the A operand is built from mask nibbles with one multiply-and-mask, the B image (36 KB for
+//    64 x 64, both directions) sits in shared memory, staged by one TMA bulk copy.
+//
+// Fed uniforms and larger layers use the FP64 DMMA kernel.
+#include "common.cuh"
+
+namespace qcb {
+
+constexpr int GI_THREADS = 256;
+constexpr int GI_WARPS = GI_THREADS / 32;
+constexpr int GI_CPW = 16;  // chains per warp
+
+struct GibbsImmaArgs {
+  const unsigned char* image;
+  uint32_t image_bytes;
+  StackedParams p;        // original FP64 parameters (cold path)
+  const double* v_in;
+  double* v;
+  int64_t C;
+  int k;
+  uint32_t key0, key1;
+  uint64_t chain_id0;
+  uint32_t sweep0;
+  unsigned long long* dbg;  // optional: [0] = max over cold-path units of |x~ - x| / dx scaled by 2^20, [1] = cold-path units
+};
+
+struct ImmaHeader {
+  float inv_scale;   // 2^-s
+  float margin_h, margin_v;
+  float dx_h, dx_v;
+  int s;
+  int pad[2];
+};
+
+__host__ __device__ inline int imma_kk(int units_pad) { return (units_pad + 31) / 32; }
+
+// bytes of the image for HB / VB 16-unit blocks
+static size_t imma_image_bytes(int HB, int VB) {
+  const int Hpad = 16 * HB, Npad = 16 * VB;
+  const size_t bh = (size_t)3 * imma_kk(Npad) * (Hpad / 8) * 32 * 8;  // h | v : K over visible, N over hidden
+  const size_t bv = (size_t)3 * imma_kk(Hpad) * (Npad / 8) * 32 * 8;
+  return align_up(sizeof(ImmaHeader) + bh + bv + (size_t)(Hpad + Npad) * 4, 16);
+}
+
+// unit owned by column c (0..7) of n-block nb: lane t ends up with the eight units of one Philox call
+__host__ __device__ inline int imma_unit(int nb, int c) { return 32 * (nb >> 2) + 16 * ((nb >> 1) & 1) + 4 * (c >> 1) + 2 * (nb & 1) + (c & 1); }
+
+// ---- pack: quantise, split into int8 digits, write fragment-ordered image ------------------------
+__global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, int HB, int VB, unsigned char* __restrict__ img) {
+  __shared__ double red[8];
+  __shared__ double s_maxw, s_rowmax, s_colmax;
+  const int H = p.nhid(), N = p.N;
+  const int Hpad = 16 * HB, Npad = 16 * VB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_max = [&](double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    double m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+    return m;
+  };
+  double mw = 0.0;
+  for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) mw = fmax(mw, fabs(p.w(idx / N, idx % N)));
+  mw = block_max(mw);
+  double rm = 0.0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    double r = fabs(p.hbias(i));
+    for (int j = 0; j < N; ++j) r += fabs(p.w(i, j));
+    rm = fmax(rm, r);
+  }
+  rm = block_max(rm);
+  double cm = 0.0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    double c = fabs(p.b[j]);
+    for (int i = 0; i < H; ++i) c += fabs(p.w(i, j));
+    cm = fmax(cm, c);
+  }
+  cm = block_max(cm);
+  if (threadIdx.x == 0) { s_maxw = mw; s_rowmax = rm; s_colmax = cm; }
+  __syncthreads();
+  int s = 0;
+  if (s_maxw > 0.0 && s_maxw < 1e300) s = 21 - ilogb(s_maxw);  // |Wq| <= 2^22
+  if (s > 60) s = 60;
+  if (s < -60) s = -60;
+  const double scale = ldexp(1.0, s);
+  ImmaHeader* hd = reinterpret_cast<ImmaHeader*>(img);
+  if (threadIdx.x == 0) {
+    hd->inv_scale = (float)ldexp(1.0, -s);
+    hd->s = s;
+    const double dxh = N * ldexp(1.0, -(s + 1)) + ldexp(1.0, -22) * s_rowmax;
+    const double dxv = H * ldexp(1.0, -(s + 1)) + ldexp(1.0, -22) * s_colmax;
+    hd->dx_h = (float)dxh;
+    hd->dx_v = (float)dxv;
+    // round the margins up a little: they are compared in float
+    hd->margin_h = (float)((dxh * 0.25 + ldexp(1.0, -17)) * 1.0001);
+    hd->margin_v = (float)((dxv * 0.25 + ldexp(1.0, -17)) * 1.0001);
+    hd->pad[0] = hd->pad[1] = 0;
+  }
+  const int KKv = imma_kk(Npad), NBh = Hpad / 8, KKh = imma_kk(Hpad), NBv = Npad / 8;
+  uint32_t* Bh = reinterpret_cast<uint32_t*>(img + sizeof(ImmaHeader));
+  const size_t nBh = (size_t)3 * KKv * NBh * 32 * 2;
+  uint32_t* Bv = Bh + nBh;
+  const size_t nBv = (size_t)3 * KKh * NBv * 32 * 2;
+  float* biasH = reinterpret_cast<float*>(Bv + nBv);
+  float* biasV = biasH + Hpad;
+  // one uint32 = 4 consecutive k of one slice; index = (((slice * KK + kk) * NB + nb) * 32 + lane) * 2 + half
+  for (size_t idx = threadIdx.x; idx < nBh + nBv; idx += blockDim.x) {
+    const bool hside = idx < nBh;
+    size_t r = hside ? idx : idx - nBh;
+    const int KK = hside ? KKv : KKh, NB = hside ? NBh : NBv;
+    const int half = r & 1; r >>= 1;
+    const int ln = r & 31; r >>= 5;
+    const int nb = r % NB; r /= NB;
+    const int kk = r % KK; const int slice = (int)(r / KK);
+    const int g = ln >> 2, t = ln & 3;
+    const int outu = imma_unit(nb, g);
+    uint32_t word = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int inu = 32 * kk + 16 * half + 4 * t + i;
+      const int hid = hside ? outu : inu, vis = hside ? inu : outu;
+      int q = 0;
+      if (hid < H && vis < N) {
+        long long wq = llrint(p.w(hid, vis) * scale);
+        const int q0 = (int)(((wq + 128) & 255) - 128);
+        wq = (wq - q0) >> 8;
+        const int q1 = (int)(((wq + 128) & 255) - 128);
+        const int q2 = (int)((wq - q1) >> 8);
+        q = slice == 0 ? q0 : (slice == 1 ? q1 : q2);
+      }
+      word |= (uint32_t)(q & 255) << (8 * i);
+    }
+    (hside ? Bh : Bv)[hside ? idx : idx - nBh] = word;
+  }
+  for (int i = threadIdx.x; i < Hpad; i += blockDim.x) biasH[i] = i < H ? (float)p.hbias(i) : 0.0f;
+  for (int j = threadIdx.x; j < Npad; j += blockDim.x) biasV[j] = j < N ? (float)p.b[j] : 0.0f;
+}
+
+__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// four mask bits -> four int8 (0/1) in one register
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ uint32_t stream_ctr_i(uint32_t stream, uint32_t q) { return (stream << 29) | q; }
+
+// Cold path: exact FP64 pre-activation of the flagged units from the original parameters, full 53-bit
+// uniform, exact sigmoid.  in_mask: the chain's input-layer bits; hidden_out: which conditional.
+__device__ __noinline__ uint32_t fixup_slow_imma(const GibbsImmaArgs* a, int hidden_out, const uint32_t* in_mask, uint32_t nibw,
+                                                 uint32_t slowmask, uint32_t c0, uint32_t c1, uint32_t sweep, uint32_t q0, int t,
+                                                 const float* xs, float dx) {
+  const StackedParams& p = a->p;
+  const int n_in = hidden_out ? p.N : p.nhid();
+  while (slowmask != 0u) {
+    const int gq = (__ffs(slowmask) - 1) >> 2;
+    const uint32_t sb = (slowmask >> (4 * gq)) & 0xFu;
+    slowmask &= ~(0xFu << (4 * gq));
+    const uint32_t half = (uint32_t)(gq & 1), q = q0 + 4u * (uint32_t)(gq >> 1) + (uint32_t)t;
+    uint32_t hi[4], la[4], lb[4];
+    philox4x32_10(c0, c1, sweep, stream_ctr_i(0u, q), a->key0, a->key1, hi);
+    philox4x32_10(c0, c1, sweep, stream_ctr_i(1u + 2u * half, q), a->key0, a->key1, la);
+    philox4x32_10(c0, c1, sweep, stream_ctr_i(2u + 2u * half, q), a->key0, a->key1, lb);
+#pragma unroll 1
+    for (int w = 0; w < 4; ++w) {
+      if (sb & (1u << w)) {
+        const int unit = 16 * gq + 4 * t + w;
+        double x = hidden_out ? p.hbias(unit) : p.b[unit];
+        for (int kin = 0; kin < n_in; ++kin)
+          if ((in_mask[kin >> 5] >> (kin & 31)) & 1u) x += hidden_out ? p.w(unit, kin) : p.w(kin, unit);
+        if (a->dbg != nullptr) {
+          const double ratio = fabs((double)xs[4 * gq + w] - x) / (double)dx;
+          atomicMax(a->dbg, (unsigned long long)(ratio * 1048576.0));
+          atomicAdd(a->dbg + 1, 1ull);
+        }
+        const uint64_t h16 = (hi[w] >> (16u * (1u - half))) & 0xFFFFu;
+        const uint64_t bits = (h16 << 37) | ((uint64_t)la[w] << 5) | (uint64_t)(lb[w] >> 27);
+        const double u = (double)bits * 0x1.0p-53;
+        const uint32_t m = 1u << (4 * gq + w);
+        if (u < sigmoid_exact(x)) nibw |= m; else nibw &= ~m;
+      }
+    }
+  }
+  return nibw;
+}
+
+// One conditional update of 16 chains.  KB_IN / OB: 16-unit blocks of the input / output layer.
+template <int KB_IN, int OB>
+__device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN + 1) / 2], uint32_t (&mout)[2][(OB + 1) / 2],
+                                                const uint2* __restrict__ Bimg, const float* __restrict__ bias, float inv_scale,
+                                                float margin, float dx, int n_out_real, const uint32_t (&cid)[2][2], uint32_t key0,
+                                                uint32_t key1, uint32_t sweep, uint32_t q0, const GibbsImmaArgs* args,
+                                                int hidden_out, int lane) {
+  constexpr int NB = 2 * OB;                 // n-blocks of 8 output units
+  constexpr int KK = (KB_IN + 1) / 2;        // k-steps of 32 input units (= mask words)
+  const int t = lane & 3;
+  int tot[NB][4];
+#pragma unroll
+  for (int slice = 2; slice >= 0; --slice) {
+    int acc[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = 0; acc[nb][1] = 0; acc[nb][2] = 0; acc[nb][3] = 0; }
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const uint32_t a0 = spread4((min[0][kk] >> (4 * t)) & 0xFu), a1 = spread4((min[1][kk] >> (4 * t)) & 0xFu);
+      const uint32_t a2 = spread4((min[0][kk] >> (16 + 4 * t)) & 0xFu), a3 = spread4((min[1][kk] >> (16 + 4 * t)) & 0xFu);
+      const uint2* row = Bimg + ((size_t)(slice * KK + kk) * NB) * 32 + lane;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const uint2 b = row[nb * 32];
+        imma16832(acc[nb], a0, a1, a2, a3, b.x, b.y);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tot[nb][e] = slice == 2 ? acc[nb][e] : tot[nb][e] * 256 + acc[nb][e];
+  }
+
+  // Bernoulli decisions; chain row r of this lane owns units 16 gq + 4 t + w, i.e. n-block 2 gq + w/2, column 2t + w%2
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t nibw = 0u, slowmask = 0u;
+    float xs[4 * OB];
+#pragma unroll
+    for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
+      uint32_t rnd[4];
+      philox4x32_10(cid[r][0], cid[r][1], sweep, stream_ctr_i(0u, q0 + 4 * pq + t), key0, key1, rnd);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int gq = 2 * pq + half;
+        if (gq < OB) {
+          int nvalid = n_out_real - (16 * gq + 4 * t);
+          nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+          const uint32_t valid = (1u << nvalid) - 1u;
+          uint32_t nib = 0u, slow = 0u;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int nb = 2 * gq + (w >> 1);
+            const float x = fmaf((float)tot[nb][2 * r + (w & 1)], inv_scale, bias[16 * gq + 4 * t + w]);
+            xs[4 * gq + w] = x;
+            const float p = __fdividef(1.0f, 1.0f + __expf(-x));
+            const uint32_t h16 = half ? (rnd[w] & 0xFFFFu) : (rnd[w] >> 16);
+            const float uf = __uint_as_float(0x3F800000u | (h16 << 7)) - 1.0f;  // u in [uf, uf + 2^-16)
+            const bool sure1 = uf + (0x1.0p-16f + margin) <= p;
+            const bool sure0 = uf >= p + margin;
+            nib |= (sure1 ? 1u : 0u) << w;
+            slow |= ((sure1 || sure0) ? 0u : 1u) << w;
+          }
+          nibw |= (nib & valid) << (4 * gq);
+          slowmask |= (slow & valid) << (4 * gq);
+        }
+      }
+    }
+    if (slowmask != 0u) {
+      uint32_t inm[(KB_IN + 1) / 2];
+#pragma unroll
+      for (int w = 0; w < (KB_IN + 1) / 2; ++w) inm[w] = min[r][w];
+      nibw = fixup_slow_imma(args, hidden_out, inm, nibw, slowmask, cid[r][0], cid[r][1], sweep, q0, t, xs, dx);
+    }
+#pragma unroll
+    for (int w = 0; w < (OB + 1) / 2; ++w) mout[r][w] = 0u;
+#pragma unroll
+    for (int gq = 0; gq < OB; ++gq) mout[r][gq / 2] |= ((nibw >> (4 * gq)) & 0xFu) << (16 * (gq % 2) + 4 * t);
+#pragma unroll
+    for (int w = 0; w < (OB + 1) / 2; ++w) {
+      mout[r][w] |= __shfl_xor_sync(0xffffffffu, mout[r][w], 1);
+      mout[r][w] |= __shfl_xor_sync(0xffffffffu, mout[r][w], 2);
+    }
+  }
+}
+
+template <int HB, int VB>
+__global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsImmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int Hpad = 16 * HB, Npad = 16 * VB;
+  constexpr int KKv = (VB + 1) / 2, NBh = 2 * HB, KKh = (HB + 1) / 2, NBv = 2 * VB;
+  constexpr size_t nBh = (size_t)3 * KKv * NBh * 32, nBv = (size_t)3 * KKh * NBv * 32;  // in uint2
+  const ImmaHeader* hd = reinterpret_cast<const ImmaHeader*>(smem_raw);
+  const uint2* Bh = reinterpret_cast<const uint2*>(smem_raw + sizeof(ImmaHeader));
+  const uint2* Bv = Bh + nBh;
+  const float* biasH = reinterpret_cast<const float*>(Bv + nBv);
+  const float* biasV = biasH + Hpad;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + align_up(sizeof(ImmaHeader) + (nBh + nBv) * 8 + (Hpad + Npad) * 4, 16));
+
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(mbar, a.image_bytes);
+    for (uint32_t off = 0; off < a.image_bytes; off += 32768u) {
+      const uint32_t n = a.image_bytes - off < 32768u ? a.image_bytes - off : 32768u;
+      tma_bulk_g2s(smem_raw + off, a.image + off, n, mbar);
+    }
+  }
+  mbar_wait(mbar, 0);
+  const float inv_scale = hd->inv_scale, margin_h = hd->margin_h, margin_v = hd->margin_v, dx_h = hd->dx_h, dx_v = hd->dx_v;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2;
+  constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
+  const int nhid = a.p.nhid(), N = a.p.N;
+  const uint32_t qv0 = (uint32_t)(4 * ((nhid + 31) / 32));
+  const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v_in);
+  const int64_t num_groups = (a.C + GI_CPW - 1) / GI_CPW;
+
+  for (int64_t gi = (int64_t)blockIdx.x * GI_WARPS + warp; gi < num_groups; gi += (int64_t)gridDim.x * GI_WARPS) {
+    const int64_t chain_base = gi * GI_CPW;
+    uint32_t mv[2][MV], mh[2][MH];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int w = 0; w < MV; ++w) mv[r][w] = 0u;
+#pragma unroll
+    for (int cc = 0; cc < GI_CPW; ++cc) {
+      const int64_t ch = chain_base + cc;
+#pragma unroll
+      for (int w = 0; w < MV; ++w) {
+        const int j = w * 32 + lane;
+        unsigned long long bits = 0ull;
+        if (ch < a.C && j < N) bits = vbits[ch * N + j];
+        const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
+        if (g == (cc & 7)) mv[cc >> 3][w] = bal;
+      }
+    }
+    uint32_t cid[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint64_t id = a.chain_id0 + (uint64_t)(chain_base + 8 * r + g);
+      cid[r][0] = (uint32_t)id;
+      cid[r][1] = (uint32_t)(id >> 32);
+    }
+    for (int s = 0; s < a.k; ++s) {
+      const uint32_t sweep = a.sweep0 + (uint32_t)s;
+      half_sweep_imma<VB, HB>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
+      half_sweep_imma<HB, VB>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
+    }
+#pragma unroll
+    for (int cc = 0; cc < GI_CPW; ++cc) {
+      const int64_t ch = chain_base + cc;
+#pragma unroll
+      for (int w = 0; w < MV; ++w) {
+        const uint32_t word = __shfl_sync(0xffffffffu, mv[cc >> 3][w], (cc & 7) * 4);
+        const int j = w * 32 + lane;
+        if (ch < a.C && j < N) a.v[ch * N + j] = ((word >> lane) & 1u) ? 1.0 : 0.0;
+      }
+    }
+  }
+}
+
+static int pick_blocks_imma(int units) {
+  if (units <= 16) return 1;
+  if (units <= 32) return 2;
+  if (units <= 64) return 4;
+  return 0;
+}
+
+template <int HB, int VB>
+static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
+  const size_t smem = imma_image_bytes(HB, VB) + 16;
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  if (!configured) {
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_imma_kernel<HB, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_imma_kernel<HB, VB>, GI_THREADS, smem));
+    if (blocks_per_sm < 1) return fail(QCB_ERR_CUDA, "gibbs (imma) kernel does not fit on an SM");
+    configured = true;
+  }
+  const int64_t groups = (a.C + GI_CPW - 1) / GI_CPW;
+  const int64_t need = (groups + GI_WARPS - 1) / GI_WARPS;
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  const int grid = (int)(need < cap ? need : cap);
+  gibbs_imma_kernel<HB, VB><<<grid, GI_THREADS, smem, st>>>(a);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+size_t gibbs_imma_workspace_bytes(int N, int nhid) {
+  const int HB = pick_blocks_imma(nhid), VB = pick_blocks_imma(N);
+  if (HB == 0 || VB == 0) return 0;
+  return align_up(imma_image_bytes(HB, VB), 256);
+}
+
+// *handled = 1 when this kernel took the call (layers <= 64 units, own Philox draws)
+int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                   uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st) {
+  *handled = 0;
+  const int HB = pick_blocks_imma(p.nhid()), VB = pick_blocks_imma(p.N);
+  if (HB == 0 || VB == 0) return QCB_OK;
+  const size_t need = gibbs_imma_workspace_bytes(p.N, p.nhid());
+  if (ws == nullptr || ws_bytes < need) return QCB_OK;
+  unsigned char* img = reinterpret_cast<unsigned char*>(ws);
+  gibbs_pack_imma_kernel<<<1, 256, 0, st>>>(p, HB, VB, img);
+  QCB_LAUNCH_CHECK();
+  GibbsImmaArgs a;
+  a.image = img;
+  a.image_bytes = (uint32_t)imma_image_bytes(HB, VB);
+  a.p = p;
+  a.v_in = v_in;
+  a.v = v;
+  a.C = C;
+  a.k = k;
+  a.key0 = (uint32_t)seed;
+  a.key1 = (uint32_t)(seed >> 32);
+  a.chain_id0 = chain_id0;
+  a.sweep0 = (uint32_t)sweep0;
+  a.dbg = dbg;
+  int rc = QCB_OK;
+#define QCB_GI_CASE(H, V) \
+  if (HB == H && VB == V) rc = launch_gibbs_imma<H, V>(a, st); else
+  QCB_GI_CASE(1, 1) QCB_GI_CASE(1, 2) QCB_GI_CASE(1, 4) QCB_GI_CASE(2, 1) QCB_GI_CASE(2, 2) QCB_GI_CASE(2, 4)
+  QCB_GI_CASE(4, 1) QCB_GI_CASE(4, 2) QCB_GI_CASE(4, 4)
+  return QCB_OK;
+#undef QCB_GI_CASE
+  if (rc == QCB_OK) *handled = 1;
+  return rc;
+}
+
+}  // namespace qcb

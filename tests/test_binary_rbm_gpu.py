@@ -330,3 +330,32 @@ def test_effective_energy_large_batch_tensor_core_path(lib, cuda, n, nh):
     r2 = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
     assert_close(r2.effective_energy(torch.tensor(v, device=cuda)), BinaryRBMOracle(W, b, c).effective_energy(v), rtol=1e-13,
                  what="energy near threshold (large batch)")
+
+
+def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
+    """The int8-tensor-core filter kernel (default for layers <= 64 units) and the FP64 DMMA kernel make
+    identical decisions on 2^20 chains; the rigorous error bound of the filter is never exceeded."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    for (n, nh, scale) in [(64, 64, None), (10, 10, None), (33, 60, 1.5), (64, 20, 0.01)]:
+        W, b, c = make_binary_params(n, nh, 161, bias_scale=0.5, weight_scale=scale)
+        rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+        C = 1 << 20 if n == 64 and nh == 64 else 1 << 16
+        g = torch.Generator(device="cuda").manual_seed(7)
+        v0 = (torch.rand(C, n, generator=g, device=cuda) < 0.5).double()
+        try:
+            _lib.check(lib.qcb_set_gibbs_mode(1), "mode")
+            ref = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
+        finally:
+            _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
+        got = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
+        assert torch.equal(got, ref), (n, nh)
+        stats = torch.zeros(2, dtype=torch.int64, device=cuda)
+        args, keep = rbm._param_args()
+        vv = v0.clone()
+        ws = _lib.workspace(cuda, _lib.workspace_bytes(_lib.OP_GIBBS, n, nh, 0, C))
+        _lib.check(lib.qcb_debug_gibbs_filter(*args, _lib.ptr(vv), C, 3, 2718, _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(cuda)), "debug filter")
+        ratio, count = stats[0].item() / 2 ** 20, stats[1].item()
+        assert count > 0 and ratio < 0.5, (n, nh, ratio, count)          # observed error well inside the bound
+        assert count < 2e-3 * C * 3 * (n + nh), (n, nh, count)            # and the cold path stays rare
