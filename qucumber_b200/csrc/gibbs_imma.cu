@@ -41,7 +41,7 @@ struct GibbsImmaArgs {
 };
 
 struct ImmaHeader {
-  float inv_scale;   // 2^-s
+  float inv_scale;   // -log2(e) * 2^-s: the kernel works with y = -log2(e) x so that e^{-x} = 2^y
   float margin_h, margin_v;
   float dx_h, dx_v;
   int s;
@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   const double scale = ldexp(1.0, s);
   ImmaHeader* hd = reinterpret_cast<ImmaHeader*>(img);
   if (threadIdx.x == 0) {
-    hd->inv_scale = (float)ldexp(1.0, -s);
+    hd->inv_scale = (float)(-1.4426950408889634 * ldexp(1.0, -s));
     hd->s = s;
-    const double dxh = N * ldexp(1.0, -(s + 1)) + ldexp(1.0, -22) * s_rowmax;
-    const double dxv = H * ldexp(1.0, -(s + 1)) + ldexp(1.0, -22) * s_colmax;
+    const double dxh = N * ldexp(1.0, -(s + 1)) + ldexp(1.0, -21) * s_rowmax;
+    const double dxv = H * ldexp(1.0, -(s + 1)) + ldexp(1.0, -21) * s_colmax;
     hd->dx_h = (float)dxh;
     hd->dx_v = (float)dxv;
     // round the margins up a little: they are compared in float
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
     }
     (hside ? Bh : Bv)[hside ? idx : idx - nBh] = word;
   }
-  for (int i = threadIdx.x; i < Hpad; i += blockDim.x) biasH[i] = i < H ? (float)p.hbias(i) : 0.0f;
-  for (int j = threadIdx.x; j < Npad; j += blockDim.x) biasV[j] = j < N ? (float)p.b[j] : 0.0f;
+  for (int i = threadIdx.x; i < Hpad; i += blockDim.x) biasH[i] = i < H ? (float)(-1.4426950408889634 * p.hbias(i)) : 0.0f;
+  for (int j = threadIdx.x; j < Npad; j += blockDim.x) biasV[j] = j < N ? (float)(-1.4426950408889634 * p.b[j]) : 0.0f;
 }
 
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -188,7 +188,7 @@ __device__ __noinline__ uint32_t fixup_slow_imma(const GibbsImmaArgs* a, int hid
         double x = hidden_out ? p.hbias(unit) : p.b[unit];
         for (int kin = 0; kin < n_in; ++kin)
           if ((in_mask[kin >> 5] >> (kin & 31)) & 1u) x += hidden_out ? p.w(unit, kin) : p.w(kin, unit);
-        if (a->dbg != nullptr) {
+        if (a->dbg != nullptr && xs != nullptr) {
           const double ratio = fabs((double)xs[4 * gq + w] - x) / (double)dx;
           atomicMax(a->dbg, (unsigned long long)(ratio * 1048576.0));
           atomicAdd(a->dbg + 1, 1ull);
@@ -204,44 +204,63 @@ __device__ __noinline__ uint32_t fixup_slow_imma(const GibbsImmaArgs* a, int hid
   return nibw;
 }
 
+__device__ __forceinline__ float ex2_approx(float y) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return r;
+}
+
 // One conditional update of 16 chains.  KB_IN / OB: 16-unit blocks of the input / output layer.
-template <int KB_IN, int OB>
+// DBG: keep the filter's pre-activations for the error-bound check of the cold path (test hook only).
+template <int KB_IN, int OB, bool DBG>
 __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN + 1) / 2], uint32_t (&mout)[2][(OB + 1) / 2],
-                                                const uint2* __restrict__ Bimg, const float* __restrict__ bias, float inv_scale,
+                                                const uint2* __restrict__ Bimg, const float* __restrict__ bias, float k1,
                                                 float margin, float dx, int n_out_real, const uint32_t (&cid)[2][2], uint32_t key0,
                                                 uint32_t key1, uint32_t sweep, uint32_t q0, const GibbsImmaArgs* args,
                                                 int hidden_out, int lane) {
   constexpr int NB = 2 * OB;                 // n-blocks of 8 output units
   constexpr int KK = (KB_IN + 1) / 2;        // k-steps of 32 input units (= mask words)
   const int t = lane & 3;
+  // A operand: the two chains' state bits as int8, built once per k-step
+  uint32_t afr[KK][4];
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+    afr[kk][0] = spread4((min[0][kk] >> (4 * t)) & 0xFu);
+    afr[kk][1] = spread4((min[1][kk] >> (4 * t)) & 0xFu);
+    afr[kk][2] = spread4((min[0][kk] >> (16 + 4 * t)) & 0xFu);
+    afr[kk][3] = spread4((min[1][kk] >> (16 + 4 * t)) & 0xFu);
+  }
+  // t = ((digit2 * 256 + digit1) * 256 + digit0) . v : the running total re-enters the next pass as C operand
   int tot[NB][4];
 #pragma unroll
-  for (int slice = 2; slice >= 0; --slice) {
-    int acc[NB][4];
+  for (int nb = 0; nb < NB; ++nb) { tot[nb][0] = 0; tot[nb][1] = 0; tot[nb][2] = 0; tot[nb][3] = 0; }
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = 0; acc[nb][1] = 0; acc[nb][2] = 0; acc[nb][3] = 0; }
+  for (int slice = 2; slice >= 0; --slice) {
+    if (slice != 2) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tot[nb][e] <<= 8;
+    }
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) {
-      const uint32_t a0 = spread4((min[0][kk] >> (4 * t)) & 0xFu), a1 = spread4((min[1][kk] >> (4 * t)) & 0xFu);
-      const uint32_t a2 = spread4((min[0][kk] >> (16 + 4 * t)) & 0xFu), a3 = spread4((min[1][kk] >> (16 + 4 * t)) & 0xFu);
       const uint2* row = Bimg + ((size_t)(slice * KK + kk) * NB) * 32 + lane;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
         const uint2 b = row[nb * 32];
-        imma16832(acc[nb], a0, a1, a2, a3, b.x, b.y);
+        imma16832(tot[nb], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.x, b.y);
       }
     }
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) tot[nb][e] = slice == 2 ? acc[nb][e] : tot[nb][e] * 256 + acc[nb][e];
   }
 
-  // Bernoulli decisions; chain row r of this lane owns units 16 gq + 4 t + w, i.e. n-block 2 gq + w/2, column 2t + w%2
+  // Bernoulli decisions; chain row r of this lane owns units 16 gq + 4 t + w, i.e. n-block 2 gq + w/2, column 2t + w%2.
+  // With q = 1 + e^{-x}:  u < 1/q  <=>  u q < 1.  u lies in the cell [uf, uf + 2^-16), uf = m - 1.
+  const float c1 = (0x1.0p-16f + margin) - 1.0f;   // (m + c1) q <= 1  =>  certainly u < p
+  const float c0 = -1.0f - margin;                 // (m + c0) q >= 1  =>  certainly u >= p
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     uint32_t nibw = 0u, slowmask = 0u;
-    float xs[4 * OB];
+    float xs[DBG ? 4 * OB : 1];
 #pragma unroll
     for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
       uint32_t rnd[4];
@@ -250,25 +269,25 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
       for (int half = 0; half < 2; ++half) {
         const int gq = 2 * pq + half;
         if (gq < OB) {
-          int nvalid = n_out_real - (16 * gq + 4 * t);
-          nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
-          const uint32_t valid = (1u << nvalid) - 1u;
-          uint32_t nib = 0u, slow = 0u;
+          uint32_t nib = 0u, und = 0u;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int nb = 2 * gq + (w >> 1);
-            const float x = fmaf((float)tot[nb][2 * r + (w & 1)], inv_scale, bias[16 * gq + 4 * t + w]);
-            xs[4 * gq + w] = x;
-            const float p = __fdividef(1.0f, 1.0f + __expf(-x));
+            const float y = fmaf((float)tot[nb][2 * r + (w & 1)], k1, bias[16 * gq + 4 * t + w]);  // -log2(e) x~
+            if (DBG) xs[4 * gq + w] = y * -0.6931471805599453f;
+            const float q = 1.0f + ex2_approx(y);
             const uint32_t h16 = half ? (rnd[w] & 0xFFFFu) : (rnd[w] >> 16);
-            const float uf = __uint_as_float(0x3F800000u | (h16 << 7)) - 1.0f;  // u in [uf, uf + 2^-16)
-            const bool sure1 = uf + (0x1.0p-16f + margin) <= p;
-            const bool sure0 = uf >= p + margin;
+            const float m = __uint_as_float(0x3F800000u | (h16 << 7));
+            const bool sure1 = (m + c1) * q <= 1.0f;
+            const bool sure0 = (m + c0) * q >= 1.0f;
             nib |= (sure1 ? 1u : 0u) << w;
-            slow |= ((sure1 || sure0) ? 0u : 1u) << w;
+            und |= ((sure1 || sure0) ? 0u : 1u) << w;
           }
+          int nvalid = n_out_real - (16 * gq + 4 * t);
+          nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
+          const uint32_t valid = (1u << nvalid) - 1u;
           nibw |= (nib & valid) << (4 * gq);
-          slowmask |= (slow & valid) << (4 * gq);
+          slowmask |= (und & valid) << (4 * gq);
         }
       }
     }
@@ -276,7 +295,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
       uint32_t inm[(KB_IN + 1) / 2];
 #pragma unroll
       for (int w = 0; w < (KB_IN + 1) / 2; ++w) inm[w] = min[r][w];
-      nibw = fixup_slow_imma(args, hidden_out, inm, nibw, slowmask, cid[r][0], cid[r][1], sweep, q0, t, xs, dx);
+      nibw = fixup_slow_imma(args, hidden_out, inm, nibw, slowmask, cid[r][0], cid[r][1], sweep, q0, t, DBG ? xs : nullptr, dx);
     }
 #pragma unroll
     for (int w = 0; w < (OB + 1) / 2; ++w) mout[r][w] = 0u;
@@ -290,7 +309,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
   }
 }
 
-template <int HB, int VB>
+template <int HB, int VB, bool DBG>
 __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsImmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Hpad = 16 * HB, Npad = 16 * VB;
@@ -351,8 +370,8 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
     }
     for (int s = 0; s < a.k; ++s) {
       const uint32_t sweep = a.sweep0 + (uint32_t)s;
-      half_sweep_imma<VB, HB>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
-      half_sweep_imma<HB, VB>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
+      half_sweep_imma<VB, HB, DBG>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
+      half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
     }
 #pragma unroll
     for (int cc = 0; cc < GI_CPW; ++cc) {
@@ -374,14 +393,14 @@ static int pick_blocks_imma(int units) {
   return 0;
 }
 
-template <int HB, int VB>
+template <int HB, int VB, bool DBG>
 static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
   const size_t smem = imma_image_bytes(HB, VB) + 16;
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
-    QCB_CUDA(cudaFuncSetAttribute(gibbs_imma_kernel<HB, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_imma_kernel<HB, VB>, GI_THREADS, smem));
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_imma_kernel<HB, VB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_imma_kernel<HB, VB, DBG>, GI_THREADS, smem));
     if (blocks_per_sm < 1) return fail(QCB_ERR_CUDA, "gibbs (imma) kernel does not fit on an SM");
     configured = true;
   }
@@ -389,7 +408,7 @@ static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
   const int64_t need = (groups + GI_WARPS - 1) / GI_WARPS;
   const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
   const int grid = (int)(need < cap ? need : cap);
-  gibbs_imma_kernel<HB, VB><<<grid, GI_THREADS, smem, st>>>(a);
+  gibbs_imma_kernel<HB, VB, DBG><<<grid, GI_THREADS, smem, st>>>(a);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
@@ -426,7 +445,7 @@ int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_
   a.dbg = dbg;
   int rc = QCB_OK;
 #define QCB_GI_CASE(H, V) \
-  if (HB == H && VB == V) rc = launch_gibbs_imma<H, V>(a, st); else
+  if (HB == H && VB == V) rc = (dbg != nullptr ? launch_gibbs_imma<H, V, true>(a, st) : launch_gibbs_imma<H, V, false>(a, st)); else
   QCB_GI_CASE(1, 1) QCB_GI_CASE(1, 2) QCB_GI_CASE(1, 4) QCB_GI_CASE(2, 1) QCB_GI_CASE(2, 2) QCB_GI_CASE(2, 4)
   QCB_GI_CASE(4, 1) QCB_GI_CASE(4, 2) QCB_GI_CASE(4, 4)
   return QCB_OK;
