@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
   constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
   const int nhid = a.p.nhid(), N = a.p.N;
   const uint32_t qv0 = (uint32_t)(4 * ((nhid + 31) / 32));
-  const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v_in);
+  const uint32_t* vhi = reinterpret_cast<const uint32_t*>(a.v_in) + 1;  // high words of the doubles
   const int64_t num_groups = (a.C + GI_CPW - 1) / GI_CPW;
 
   for (int64_t gi = (int64_t)blockIdx.x * GI_WARPS + warp; gi < num_groups; gi += (int64_t)gridDim.x * GI_WARPS) {
@@ -349,15 +349,22 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int w = 0; w < MV; ++w) mv[r][w] = 0u;
+    // all loads of the tile are issued before the first ballot (a state is 0.0 or 1.0: the high word decides)
+    uint32_t raw[GI_CPW][MV];
 #pragma unroll
     for (int cc = 0; cc < GI_CPW; ++cc) {
       const int64_t ch = chain_base + cc;
 #pragma unroll
       for (int w = 0; w < MV; ++w) {
         const int j = w * 32 + lane;
-        unsigned long long bits = 0ull;
-        if (ch < a.C && j < N) bits = vbits[ch * N + j];
-        const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
+        raw[cc][w] = (ch < a.C && j < N) ? __ldg(vhi + 2 * (ch * N + j)) : 0u;
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < GI_CPW; ++cc) {
+#pragma unroll
+      for (int w = 0; w < MV; ++w) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (raw[cc][w] << 1) != 0u);
         if (g == (cc & 7)) mv[cc >> 3][w] = bal;
       }
     }
@@ -368,10 +375,27 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
       cid[r][0] = (uint32_t)id;
       cid[r][1] = (uint32_t)(id >> 32);
     }
-    for (int s = 0; s < a.k; ++s) {
-      const uint32_t sweep = a.sweep0 + (uint32_t)s;
-      half_sweep_imma<VB, HB, DBG>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
-      half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
+    if constexpr (HB == VB) {
+      // Equal paddings: both conditional updates run through ONE copy of the half-sweep code (direction
+      // selected at run time), which keeps the loop body inside the 32 KB instruction cache.
+#pragma unroll 1
+      for (int hs = 0; hs < 2 * a.k; ++hs) {
+        const bool back = (hs & 1) != 0;  // false: h | v, true: v | h
+        half_sweep_imma<VB, HB, DBG>(mv, mh, back ? Bv : Bh, back ? biasV : biasH, inv_scale, back ? margin_v : margin_h,
+                                     back ? dx_v : dx_h, back ? N : nhid, cid, a.key0, a.key1, a.sweep0 + (uint32_t)(hs >> 1),
+                                     back ? qv0 : 0u, &a, back ? 0 : 1, lane);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int w = 0; w < MV; ++w) mv[r][w] = mh[r][w];
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < a.k; ++s) {
+        const uint32_t sweep = a.sweep0 + (uint32_t)s;
+        half_sweep_imma<VB, HB, DBG>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
+        half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
+      }
     }
 #pragma unroll
     for (int cc = 0; cc < GI_CPW; ++cc) {
