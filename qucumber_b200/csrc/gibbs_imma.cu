@@ -10,7 +10,7 @@
 //    3 x mma.sync.m16n8k32.s8 (IMMA) passes.  x~ = float(t) 2^-s + c.
 //  * |x~ - x| <= n_in 2^-(s+1) + 2^-22 (sum_k |W_ik| + |c_i|) =: dx  is a rigorous bound (quantisation +
 //    the two float roundings), hence |sigmoid(x~) - sigmoid(x)| <= dx / 4.  The filter decides from the
-//    16-bit cell of u unless p~ lies within margin = dx/4 + 2^-17 of it (2^-17 covers the float sigmoid);
+//    16-bit cell of u unless p~ lies within margin = dx/4 + 2^-19 of it (the float evaluation of the test is good to 2^-21.5);
 //    undecided units (~1e-4 of them) recompute x in FP64 from the original doubles and compare the full
 //    53-bit uniform with the exact sigmoid (fixup_slow_imma, out of line).
 //  * a warp owns 16 chains (two rows of the M = 16 tile per lane); states are bit masks in registers,
@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
     hd->dx_h = (float)dxh;
     hd->dx_v = (float)dxv;
     // round the margins up a little: they are compared in float
-    hd->margin_h = (float)((dxh * 0.25 + ldexp(1.0, -17)) * 1.0001);
-    hd->margin_v = (float)((dxv * 0.25 + ldexp(1.0, -17)) * 1.0001);
+    hd->margin_h = (float)((dxh * 0.25 + ldexp(1.0, -19)) * 1.0001);
+    hd->margin_v = (float)((dxv * 0.25 + ldexp(1.0, -19)) * 1.0001);
     hd->pad[0] = hd->pad[1] = 0;
   }
   const int KKv = imma_kk(Npad), NBh = Hpad / 8, KKh = imma_kk(Hpad), NBv = Npad / 8;
@@ -215,7 +215,7 @@ __device__ __forceinline__ float ex2_approx(float y) {
 template <int KB_IN, int OB, bool DBG>
 __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN + 1) / 2], uint32_t (&mout)[2][(OB + 1) / 2],
                                                 const uint2* __restrict__ Bimg, const float* __restrict__ bias, float k1,
-                                                float margin, float dx, int n_out_real, const uint32_t (&cid)[2][2], uint32_t key0,
+                                                float margin, float dx, uint32_t valid_mask, const uint32_t (&cid)[2][2], uint32_t key0,
                                                 uint32_t key1, uint32_t sweep, uint32_t q0, const GibbsImmaArgs* args,
                                                 int hidden_out, int lane) {
   constexpr int NB = 2 * OB;                 // n-blocks of 8 output units
@@ -255,42 +255,40 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
 
   // Bernoulli decisions; chain row r of this lane owns units 16 gq + 4 t + w, i.e. n-block 2 gq + w/2, column 2t + w%2.
   // With q = 1 + e^{-x}:  u < 1/q  <=>  u q < 1.  u lies in the cell [uf, uf + 2^-16), uf = m - 1.
-  const float c1 = (0x1.0p-16f + margin) - 1.0f;   // (m + c1) q <= 1  =>  certainly u < p
-  const float c0 = -1.0f - margin;                 // (m + c0) q >= 1  =>  certainly u >= p
+  // The two tests are sign tests of one FMA each (its sign is exact); the sign bits are shifted straight into
+  // the result masks, so units are visited from the highest index down.
+  const float c1 = (0x1.0p-16f + margin) - 1.0f;   // (m + c1) q - 1 <  0  =>  certainly u < p
+  const float c0 = -1.0f - margin;                 // (m + c0) q - 1 >= 0  =>  certainly u >= p
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    uint32_t nibw = 0u, slowmask = 0u;
+    uint32_t acc1 = 0u, acc0 = 0u;  // bit 4 gq + w: "certainly 1" / "not certainly 0"
     float xs[DBG ? 4 * OB : 1];
 #pragma unroll
-    for (int pq = 0; pq < (OB + 1) / 2; ++pq) {
+    for (int pq = (OB + 1) / 2 - 1; pq >= 0; --pq) {
       uint32_t rnd[4];
       philox4x32_10(cid[r][0], cid[r][1], sweep, stream_ctr_i(0u, q0 + 4 * pq + t), key0, key1, rnd);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 1; half >= 0; --half) {
         const int gq = 2 * pq + half;
         if (gq < OB) {
-          uint32_t nib = 0u, und = 0u;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
+          for (int w = 3; w >= 0; --w) {
             const int nb = 2 * gq + (w >> 1);
             const float y = fmaf((float)tot[nb][2 * r + (w & 1)], k1, bias[16 * gq + 4 * t + w]);  // -log2(e) x~
             if (DBG) xs[4 * gq + w] = y * -0.6931471805599453f;
             const float q = 1.0f + ex2_approx(y);
-            const uint32_t h16 = half ? (rnd[w] & 0xFFFFu) : (rnd[w] >> 16);
-            const float m = __uint_as_float(0x3F800000u | (h16 << 7));
-            const bool sure1 = (m + c1) * q <= 1.0f;
-            const bool sure0 = (m + c0) * q >= 1.0f;
-            nib |= (sure1 ? 1u : 0u) << w;
-            und |= ((sure1 || sure0) ? 0u : 1u) << w;
+            const uint32_t mant = half ? (rnd[w] << 7) : (rnd[w] >> 9);  // 16-bit cell of u in the top mantissa bits
+            const float m = __uint_as_float((mant & 0x007FFF80u) | 0x3F800000u);
+            const float s1 = fmaf(m + c1, q, -1.0f);
+            const float s0 = fmaf(m + c0, q, -1.0f);
+            acc1 = __funnelshift_l(__float_as_uint(s1), acc1, 1);
+            acc0 = __funnelshift_l(__float_as_uint(s0), acc0, 1);
           }
-          int nvalid = n_out_real - (16 * gq + 4 * t);
-          nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
-          const uint32_t valid = (1u << nvalid) - 1u;
-          nibw |= (nib & valid) << (4 * gq);
-          slowmask |= (und & valid) << (4 * gq);
         }
       }
     }
+    uint32_t nibw = acc1 & valid_mask;
+    const uint32_t slowmask = (acc0 ^ acc1) & valid_mask;  // certainly-1 implies not-certainly-0
     if (slowmask != 0u) {
       uint32_t inm[(KB_IN + 1) / 2];
 #pragma unroll
@@ -320,9 +318,11 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
   const uint2* Bv = Bh + nBh;
   const float* biasH = reinterpret_cast<const float*>(Bv + nBv);
   const float* biasV = biasH + Hpad;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + align_up(sizeof(ImmaHeader) + (nBh + nBv) * 8 + (Hpad + Npad) * 4, 16));
+  constexpr size_t image_end = align_up(sizeof(ImmaHeader) + (nBh + nBv) * 8 + (Hpad + Npad) * 4, 16);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + image_end);  // [0]: image, [1 + warp]: that warp's state tile
+  double* tiles = reinterpret_cast<double*>(smem_raw + align_up(image_end + 8 * (1 + GI_WARPS), 128));
 
-  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  if (threadIdx.x < 1 + GI_WARPS) mbar_init(mbar + threadIdx.x, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(mbar, a.image_bytes);
@@ -339,35 +339,66 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
   constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
   const int nhid = a.p.nhid(), N = a.p.N;
   const uint32_t qv0 = (uint32_t)(4 * ((nhid + 31) / 32));
-  const uint32_t* vhi = reinterpret_cast<const uint32_t*>(a.v_in) + 1;  // high words of the doubles
   const int64_t num_groups = (a.C + GI_CPW - 1) / GI_CPW;
+  uint32_t valid_h = 0u, valid_v = 0u;  // this lane's real (unpadded) units, bit 4 gq + w <-> unit 16 gq + 4 t + w
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int unit = 16 * (i >> 2) + 4 * (lane & 3) + (i & 3);
+    valid_h |= (unit < nhid ? 1u : 0u) << i;
+    valid_v |= (unit < N ? 1u : 0u) << i;
+  }
 
-  for (int64_t gi = (int64_t)blockIdx.x * GI_WARPS + warp; gi < num_groups; gi += (int64_t)gridDim.x * GI_WARPS) {
+  // A group's 16 chain rows are one contiguous span of v_in: the warp's tile is fetched by one TMA bulk copy,
+  // issued a whole group ahead (while the previous group is being swept), so its latency never shows.
+  double* tile = tiles + (size_t)warp * (GI_CPW * Npad);
+  uint64_t* tbar = mbar + 1 + warp;
+  uint32_t tphase = 0u;
+  const bool bulk_base_ok = (reinterpret_cast<uintptr_t>(a.v_in) & 15u) == 0u;
+  auto tile_doubles = [&](int64_t gi) -> uint32_t {
+    const int64_t left = a.C - gi * GI_CPW;
+    return (uint32_t)(left < GI_CPW ? left : GI_CPW) * (uint32_t)N;
+  };
+  auto bulk_fetch = [&](int64_t gi) {  // true when the copy was handed to the TMA unit
+    const uint32_t bytes = tile_doubles(gi) * 8u;
+    if (!bulk_base_ok || (bytes & 15u) != 0u) return false;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile vs. the async write
+      mbar_expect_tx(tbar, bytes);
+      tma_bulk_g2s(tile, a.v_in + gi * GI_CPW * (int64_t)N, bytes, tbar);
+    }
+    return true;
+  };
+  const int64_t gi0 = (int64_t)blockIdx.x * GI_WARPS + warp, gstride = (int64_t)gridDim.x * GI_WARPS;
+  bool fetched = gi0 < num_groups && bulk_fetch(gi0);
+
+  for (int64_t gi = gi0; gi < num_groups; gi += gstride) {
     const int64_t chain_base = gi * GI_CPW;
+    const int nch = (int)(tile_doubles(gi) / (uint32_t)N);
+    if (fetched) {
+      mbar_wait(tbar, tphase);
+      tphase ^= 1u;
+    } else {  // unaligned view or odd tile size: plain copy
+      for (uint32_t idx = lane; idx < tile_doubles(gi); idx += 32) tile[idx] = a.v_in[chain_base * N + idx];
+      __syncwarp();
+    }
     uint32_t mv[2][MV], mh[2][MH];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int w = 0; w < MV; ++w) mv[r][w] = 0u;
-    // all loads of the tile are issued before the first ballot (a state is 0.0 or 1.0: the high word decides)
-    uint32_t raw[GI_CPW][MV];
 #pragma unroll
     for (int cc = 0; cc < GI_CPW; ++cc) {
-      const int64_t ch = chain_base + cc;
 #pragma unroll
       for (int w = 0; w < MV; ++w) {
         const int j = w * 32 + lane;
-        raw[cc][w] = (ch < a.C && j < N) ? __ldg(vhi + 2 * (ch * N + j)) : 0u;
-      }
-    }
-#pragma unroll
-    for (int cc = 0; cc < GI_CPW; ++cc) {
-#pragma unroll
-      for (int w = 0; w < MV; ++w) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (raw[cc][w] << 1) != 0u);
+        unsigned long long bits = 0ull;
+        if (cc < nch && j < N) bits = reinterpret_cast<const unsigned long long*>(tile)[cc * N + j];
+        const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
         if (g == (cc & 7)) mv[cc >> 3][w] = bal;
       }
     }
+    __syncwarp();
+    fetched = gi + gstride < num_groups && bulk_fetch(gi + gstride);
     uint32_t cid[2][2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -382,7 +413,7 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
       for (int hs = 0; hs < 2 * a.k; ++hs) {
         const bool back = (hs & 1) != 0;  // false: h | v, true: v | h
         half_sweep_imma<VB, HB, DBG>(mv, mh, back ? Bv : Bh, back ? biasV : biasH, inv_scale, back ? margin_v : margin_h,
-                                     back ? dx_v : dx_h, back ? N : nhid, cid, a.key0, a.key1, a.sweep0 + (uint32_t)(hs >> 1),
+                                     back ? dx_v : dx_h, back ? valid_v : valid_h, cid, a.key0, a.key1, a.sweep0 + (uint32_t)(hs >> 1),
                                      back ? qv0 : 0u, &a, back ? 0 : 1, lane);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -393,8 +424,8 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
 #pragma unroll 1
       for (int s = 0; s < a.k; ++s) {
         const uint32_t sweep = a.sweep0 + (uint32_t)s;
-        half_sweep_imma<VB, HB, DBG>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, nhid, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
-        half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, N, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
+        half_sweep_imma<VB, HB, DBG>(mv, mh, Bh, biasH, inv_scale, margin_h, dx_h, valid_h, cid, a.key0, a.key1, sweep, 0u, &a, 1, lane);
+        half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, valid_v, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
       }
     }
 #pragma unroll
@@ -410,6 +441,11 @@ __global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsIm
   }
 }
 
+// image + mbarriers + one 16-chain state tile per warp
+static size_t imma_smem_bytes(int HB, int VB) {
+  return align_up(imma_image_bytes(HB, VB) + 8 * (1 + GI_WARPS), 128) + (size_t)GI_WARPS * GI_CPW * 16 * VB * sizeof(double);
+}
+
 static int pick_blocks_imma(int units) {
   if (units <= 16) return 1;
   if (units <= 32) return 2;
@@ -419,7 +455,7 @@ static int pick_blocks_imma(int units) {
 
 template <int HB, int VB, bool DBG>
 static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
-  const size_t smem = imma_image_bytes(HB, VB) + 16;
+  const size_t smem = imma_smem_bytes(HB, VB);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
