@@ -22,7 +22,11 @@
 
 namespace qcb {
 
-constexpr int GI_THREADS = 256;
+#ifndef QCB_GI_THREADS  // overridable for occupancy experiments (experiments/gibbs_imma_variants.sh)
+#define QCB_GI_THREADS 256
+#define QCB_GI_MIN_CTAS 2
+#endif
+constexpr int GI_THREADS = QCB_GI_THREADS;
 constexpr int GI_WARPS = GI_THREADS / 32;
 constexpr int GI_CPW = 16;  // chains per warp
 
@@ -165,39 +169,52 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
 
 __device__ __forceinline__ uint32_t stream_ctr_i(uint32_t stream, uint32_t q) { return (stream << 29) | q; }
 
-// Cold path: exact FP64 pre-activation of the flagged units from the original parameters, full 53-bit
-// uniform, exact sigmoid.  in_mask: the chain's input-layer bits; hidden_out: which conditional.
-__device__ __noinline__ uint32_t fixup_slow_imma(const GibbsImmaArgs* a, int hidden_out, const uint32_t* in_mask, uint32_t nibw,
-                                                 uint32_t slowmask, uint32_t c0, uint32_t c1, uint32_t sweep, uint32_t q0, int t,
+// Cold path, executed by the whole warp for every lane that has undecided units: exact FP64 pre-activation
+// from the original parameters (each lane adds the weights of its two input units, then a warp reduction),
+// full 53-bit uniform, exact sigmoid.  in0 / in1: the row's input-layer bits (identical on the four lanes
+// of a row); hidden_out: which conditional.  Must be called with all 32 lanes converged.
+__device__ __noinline__ uint32_t fixup_slow_imma(const GibbsImmaArgs* a, int hidden_out, uint32_t in0, uint32_t in1, uint32_t nibw,
+                                                 uint32_t slowmask, uint32_t c0, uint32_t c1, uint32_t sweep, uint32_t q0, int lane,
                                                  const float* xs, float dx) {
   const StackedParams& p = a->p;
   const int n_in = hidden_out ? p.N : p.nhid();
-  while (slowmask != 0u) {
-    const int gq = (__ffs(slowmask) - 1) >> 2;
-    const uint32_t sb = (slowmask >> (4 * gq)) & 0xFu;
-    slowmask &= ~(0xFu << (4 * gq));
-    const uint32_t half = (uint32_t)(gq & 1), q = q0 + 4u * (uint32_t)(gq >> 1) + (uint32_t)t;
-    uint32_t hi[4], la[4], lb[4];
-    philox4x32_10(c0, c1, sweep, stream_ctr_i(0u, q), a->key0, a->key1, hi);
-    philox4x32_10(c0, c1, sweep, stream_ctr_i(1u + 2u * half, q), a->key0, a->key1, la);
-    philox4x32_10(c0, c1, sweep, stream_ctr_i(2u + 2u * half, q), a->key0, a->key1, lb);
-#pragma unroll 1
-    for (int w = 0; w < 4; ++w) {
-      if (sb & (1u << w)) {
-        const int unit = 16 * gq + 4 * t + w;
-        double x = hidden_out ? p.hbias(unit) : p.b[unit];
-        for (int kin = 0; kin < n_in; ++kin)
-          if ((in_mask[kin >> 5] >> (kin & 31)) & 1u) x += hidden_out ? p.w(unit, kin) : p.w(kin, unit);
+  uint32_t pending = __ballot_sync(0xffffffffu, slowmask != 0u);
+  while (pending != 0u) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1u;
+    uint32_t sm = __shfl_sync(0xffffffffu, slowmask, src);
+    const uint32_t m0 = __shfl_sync(0xffffffffu, in0, src), m1 = __shfl_sync(0xffffffffu, in1, src);
+    const uint32_t sc0 = __shfl_sync(0xffffffffu, c0, src), sc1 = __shfl_sync(0xffffffffu, c1, src);
+    const int ts = src & 3;
+    while (sm != 0u) {
+      const int bit = __ffs(sm) - 1;
+      sm &= sm - 1u;
+      const int gq = bit >> 2, w = bit & 3;
+      const int unit = 16 * gq + 4 * ts + w;
+      double part = 0.0;
+      for (int kin = lane; kin < n_in; kin += 32)
+        if (((kin < 32 ? m0 : m1) >> (kin & 31)) & 1u) part += hidden_out ? p.w(unit, kin) : p.w(kin, unit);
+      part = warp_sum(part);
+      const double x = (hidden_out ? p.hbias(unit) : p.b[unit]) + part;
+      const uint32_t half = (uint32_t)(gq & 1), q = q0 + 4u * (uint32_t)(gq >> 1) + (uint32_t)ts;
+      uint32_t hi[4], la[4], lb[4];
+      philox4x32_10(sc0, sc1, sweep, stream_ctr_i(0u, q), a->key0, a->key1, hi);
+      philox4x32_10(sc0, sc1, sweep, stream_ctr_i(1u + 2u * half, q), a->key0, a->key1, la);
+      philox4x32_10(sc0, sc1, sweep, stream_ctr_i(2u + 2u * half, q), a->key0, a->key1, lb);
+      const uint32_t hw = w == 0 ? hi[0] : (w == 1 ? hi[1] : (w == 2 ? hi[2] : hi[3]));
+      const uint32_t aw = w == 0 ? la[0] : (w == 1 ? la[1] : (w == 2 ? la[2] : la[3]));
+      const uint32_t bw = w == 0 ? lb[0] : (w == 1 ? lb[1] : (w == 2 ? lb[2] : lb[3]));
+      const uint64_t h16 = (hw >> (16u * (1u - half))) & 0xFFFFu;
+      const uint64_t bits = (h16 << 37) | ((uint64_t)aw << 5) | (uint64_t)(bw >> 27);
+      const double u = (double)bits * 0x1.0p-53;
+      const bool one = u < sigmoid_exact(x);
+      if (lane == src) {
         if (a->dbg != nullptr && xs != nullptr) {
-          const double ratio = fabs((double)xs[4 * gq + w] - x) / (double)dx;
+          const double ratio = fabs((double)xs[bit] - x) / (double)dx;
           atomicMax(a->dbg, (unsigned long long)(ratio * 1048576.0));
           atomicAdd(a->dbg + 1, 1ull);
         }
-        const uint64_t h16 = (hi[w] >> (16u * (1u - half))) & 0xFFFFu;
-        const uint64_t bits = (h16 << 37) | ((uint64_t)la[w] << 5) | (uint64_t)(lb[w] >> 27);
-        const double u = (double)bits * 0x1.0p-53;
-        const uint32_t m = 1u << (4 * gq + w);
-        if (u < sigmoid_exact(x)) nibw |= m; else nibw &= ~m;
+        nibw = one ? (nibw | (1u << bit)) : (nibw & ~(1u << bit));
       }
     }
   }
@@ -289,12 +306,9 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
     }
     uint32_t nibw = acc1 & valid_mask;
     const uint32_t slowmask = (acc0 ^ acc1) & valid_mask;  // certainly-1 implies not-certainly-0
-    if (slowmask != 0u) {
-      uint32_t inm[(KB_IN + 1) / 2];
-#pragma unroll
-      for (int w = 0; w < (KB_IN + 1) / 2; ++w) inm[w] = min[r][w];
-      nibw = fixup_slow_imma(args, hidden_out, inm, nibw, slowmask, cid[r][0], cid[r][1], sweep, q0, t, DBG ? xs : nullptr, dx);
-    }
+    if (__any_sync(0xffffffffu, slowmask != 0u))
+      nibw = fixup_slow_imma(args, hidden_out, min[r][0], KK > 1 ? min[r][KK - 1] : 0u, nibw, slowmask, cid[r][0], cid[r][1], sweep,
+                             q0, lane, DBG ? xs : nullptr, dx);
 #pragma unroll
     for (int w = 0; w < (OB + 1) / 2; ++w) mout[r][w] = 0u;
 #pragma unroll
@@ -308,7 +322,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
 }
 
 template <int HB, int VB, bool DBG>
-__global__ void __launch_bounds__(GI_THREADS, 2) gibbs_imma_kernel(const GibbsImmaArgs a) {
+__global__ void __launch_bounds__(GI_THREADS, QCB_GI_MIN_CTAS) gibbs_imma_kernel(const GibbsImmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Hpad = 16 * HB, Npad = 16 * VB;
   constexpr int KKv = (VB + 1) / 2, NBh = 2 * HB, KKh = (HB + 1) / 2, NBv = 2 * VB;
