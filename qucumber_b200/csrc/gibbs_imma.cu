@@ -126,14 +126,15 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   const size_t nBv = (size_t)3 * KKh * NBv * 32 * 2;
   float* biasH = reinterpret_cast<float*>(Bv + nBv);
   float* biasV = biasH + Hpad;
-  // one uint32 = 4 consecutive k of one slice; index = (((slice * KK + kk) * NB + nb) * 32 + lane) * 2 + half
+  // one uint32 = 4 consecutive k of one slice; index = ((((slice * KK + kk) * NB/2 + nb/2) * 32 + lane) * 2 + nb%2) * 2 + half
   for (size_t idx = threadIdx.x; idx < nBh + nBv; idx += blockDim.x) {
     const bool hside = idx < nBh;
     size_t r = hside ? idx : idx - nBh;
     const int KK = hside ? KKv : KKh, NB = hside ? NBh : NBv;
     const int half = r & 1; r >>= 1;
+    const int nblo = r & 1; r >>= 1;  // two n-blocks share one 16-byte fragment load
     const int ln = r & 31; r >>= 5;
-    const int nb = r % NB; r /= NB;
+    const int nb = 2 * (int)(r % (NB / 2)) + nblo; r /= (NB / 2);
     const int kk = r % KK; const int slice = (int)(r / KK);
     const int g = ln >> 2, t = ln & 3;
     const int outu = imma_unit(nb, g);
@@ -261,11 +262,12 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
     }
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) {
-      const uint2* row = Bimg + ((size_t)(slice * KK + kk) * NB) * 32 + lane;
+      const uint4* row = reinterpret_cast<const uint4*>(Bimg) + ((size_t)(slice * KK + kk) * OB) * 32 + lane;
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const uint2 b = row[nb * 32];
-        imma16832(tot[nb], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.x, b.y);
+      for (int np = 0; np < OB; ++np) {  // one 16-byte load feeds two n-blocks
+        const uint4 b = row[np * 32];
+        imma16832(tot[2 * np], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.x, b.y);
+        imma16832(tot[2 * np + 1], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.z, b.w);
       }
     }
   }
@@ -275,7 +277,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
   // The two tests are sign tests of one FMA each (its sign is exact); the sign bits are shifted straight into
   // the result masks, so units are visited from the highest index down.
   const float c1 = (0x1.0p-16f + margin) - 1.0f;   // (m + c1) q - 1 <  0  =>  certainly u < p
-  const float c0 = -1.0f - margin;                 // (m + c0) q - 1 >= 0  =>  certainly u >= p
+  const float c01 = -(0x1.0p-16f + 2.0f * margin);  // (m + c1 + c01) q - 1 >= 0  =>  certainly u >= p  (m + c1 + c01 = u_f - margin)
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     uint32_t acc1 = 0u, acc0 = 0u;  // bit 4 gq + w: "certainly 1" / "not certainly 0"
@@ -294,10 +296,10 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
             const float y = fmaf((float)tot[nb][2 * r + (w & 1)], k1, bias[16 * gq + 4 * t + w]);  // -log2(e) x~
             if (DBG) xs[4 * gq + w] = y * -0.6931471805599453f;
             const float q = 1.0f + ex2_approx(y);
-            const uint32_t mant = half ? (rnd[w] << 7) : (rnd[w] >> 9);  // 16-bit cell of u in the top mantissa bits
-            const float m = __uint_as_float((mant & 0x007FFF80u) | 0x3F800000u);
+            // m = 1 + u_f: the 16-bit cell of u in the top mantissa bits, (0x7F0000 | h16) << 7
+            const float m = __uint_as_float(__byte_perm(rnd[w], 0x7Fu, half ? 0x5410u : 0x5432u) << 7);
             const float s1 = fmaf(m + c1, q, -1.0f);
-            const float s0 = fmaf(m + c0, q, -1.0f);
+            const float s0 = fmaf(c01, q, s1);  // re-rounding s1 costs 2^-23 in p, inside the 2^-19 allowance
             acc1 = __funnelshift_l(__float_as_uint(s1), acc1, 1);
             acc0 = __funnelshift_l(__float_as_uint(s0), acc0, 1);
           }
