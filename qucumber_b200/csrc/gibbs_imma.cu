@@ -66,41 +66,47 @@ static size_t imma_image_bytes(int HB, int VB) {
 __host__ __device__ inline int imma_unit(int nb, int c) { return 32 * (nb >> 2) + 16 * ((nb >> 1) & 1) + 4 * (c >> 1) + 2 * (nb & 1) + (c & 1); }
 
 // ---- pack: quantise, split into int8 digits, write fragment-ordered image ------------------------
+// One CTA (the global maximum fixes the scale); the parameters are staged in shared memory once so that
+// every later pass (maxima, abs-sums, the three digit images) reads them from there.
+constexpr int GI_PACK_LD = 65;  // row stride of the staged weights (odd: column walks are conflict-free)
 __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, int HB, int VB, unsigned char* __restrict__ img) {
-  __shared__ double red[8];
-  __shared__ double s_maxw, s_rowmax, s_colmax;
+  __shared__ double Ws[64 * GI_PACK_LD];
+  __shared__ double red[3][8];
   const int H = p.nhid(), N = p.N;
   const int Hpad = 16 * HB, Npad = 16 * VB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto block_max = [&](double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-    __syncthreads();
-    if (lane == 0) red[warp] = x;
-    __syncthreads();
-    double m = red[0];
-    for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
-    return m;
-  };
   double mw = 0.0;
-  for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) mw = fmax(mw, fabs(p.w(idx / N, idx % N)));
-  mw = block_max(mw);
-  double rm = 0.0;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    double r = fabs(p.hbias(i));
-    for (int j = 0; j < N; ++j) r += fabs(p.w(i, j));
-    rm = fmax(rm, r);
+  for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) {
+    const int i = idx / N, j = idx - i * N;
+    const double w = p.w(i, j);
+    Ws[i * GI_PACK_LD + j] = w;
+    mw = fmax(mw, fabs(w));
   }
-  rm = block_max(rm);
-  double cm = 0.0;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    double c = fabs(p.b[j]);
-    for (int i = 0; i < H; ++i) c += fabs(p.w(i, j));
-    cm = fmax(cm, c);
-  }
-  cm = block_max(cm);
-  if (threadIdx.x == 0) { s_maxw = mw; s_rowmax = rm; s_colmax = cm; }
   __syncthreads();
+  double rm = 0.0, cm = 0.0;
+  if (threadIdx.x < H) {  // |bias| + abs-sum of one row
+    const int i = threadIdx.x;
+    rm = fabs(p.hbias(i));
+    for (int j = 0; j < N; ++j) rm += fabs(Ws[i * GI_PACK_LD + j]);
+  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + N) {  // ... of one column (other warps)
+    const int j = threadIdx.x - 64;
+    cm = fabs(p.b[j]);
+    for (int i = 0; i < H; ++i) cm += fabs(Ws[i * GI_PACK_LD + j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+  }
+  if (lane == 0) { red[0][warp] = mw; red[1][warp] = rm; red[2][warp] = cm; }
+  __syncthreads();
+  double s_maxw = red[0][0], s_rowmax = red[1][0], s_colmax = red[2][0];
+  for (int w = 1; w < 8; ++w) {
+    s_maxw = fmax(s_maxw, red[0][w]);
+    s_rowmax = fmax(s_rowmax, red[1][w]);
+    s_colmax = fmax(s_colmax, red[2][w]);
+  }
   int s = 0;
   if (s_maxw > 0.0 && s_maxw < 1e300) s = 21 - ilogb(s_maxw);  // |Wq| <= 2^22
   if (s > 60) s = 60;
@@ -127,33 +133,37 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   float* biasH = reinterpret_cast<float*>(Bv + nBv);
   float* biasV = biasH + Hpad;
   // one uint32 = 4 consecutive k of one slice; index = ((((slice * KK + kk) * NB/2 + nb/2) * 32 + lane) * 2 + nb%2) * 2 + half
-  for (size_t idx = threadIdx.x; idx < nBh + nBv; idx += blockDim.x) {
-    const bool hside = idx < nBh;
-    size_t r = hside ? idx : idx - nBh;
-    const int KK = hside ? KKv : KKh, NB = hside ? NBh : NBv;
+  const size_t perH = nBh / 3, perV = nBv / 3;  // words of one digit slice
+  for (size_t idx = threadIdx.x; idx < perH + perV; idx += blockDim.x) {
+    const bool hside = idx < perH;
+    const size_t within = hside ? idx : idx - perH;
+    size_t r = within;
+    const int NB = hside ? NBh : NBv;
     const int half = r & 1; r >>= 1;
     const int nblo = r & 1; r >>= 1;  // two n-blocks share one 16-byte fragment load
     const int ln = r & 31; r >>= 5;
-    const int nb = 2 * (int)(r % (NB / 2)) + nblo; r /= (NB / 2);
-    const int kk = r % KK; const int slice = (int)(r / KK);
+    const int nb = 2 * (int)(r % (NB / 2)) + nblo;
+    const int kk = (int)(r / (NB / 2));
     const int g = ln >> 2, t = ln & 3;
     const int outu = imma_unit(nb, g);
-    uint32_t word = 0;
+    uint32_t word[3] = {0u, 0u, 0u};
     for (int i = 0; i < 4; ++i) {
       const int inu = 32 * kk + 16 * half + 4 * t + i;
       const int hid = hside ? outu : inu, vis = hside ? inu : outu;
-      int q = 0;
       if (hid < H && vis < N) {
-        long long wq = llrint(p.w(hid, vis) * scale);
+        long long wq = llrint(Ws[hid * GI_PACK_LD + vis] * scale);
         const int q0 = (int)(((wq + 128) & 255) - 128);
         wq = (wq - q0) >> 8;
         const int q1 = (int)(((wq + 128) & 255) - 128);
         const int q2 = (int)((wq - q1) >> 8);
-        q = slice == 0 ? q0 : (slice == 1 ? q1 : q2);
+        word[0] |= (uint32_t)(q0 & 255) << (8 * i);
+        word[1] |= (uint32_t)(q1 & 255) << (8 * i);
+        word[2] |= (uint32_t)(q2 & 255) << (8 * i);
       }
-      word |= (uint32_t)(q & 255) << (8 * i);
     }
-    (hside ? Bh : Bv)[hside ? idx : idx - nBh] = word;
+    uint32_t* dst = hside ? Bh : Bv;
+    const size_t per = hside ? perH : perV;
+    for (int slice = 0; slice < 3; ++slice) dst[slice * per + within] = word[slice];
   }
   for (int i = threadIdx.x; i < Hpad; i += blockDim.x) biasH[i] = i < H ? (float)(-1.4426950408889634 * p.hbias(i)) : 0.0f;
   for (int j = threadIdx.x; j < Npad; j += blockDim.x) biasV[j] = j < N ? (float)(-1.4426950408889634 * p.b[j]) : 0.0f;

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
-        "launch__block_size", "launch__occupancy_limit", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct", "sm__inst_executed_pipe_fp64.avg.pct",
+        "launch__block_size", "launch__occupancy_limit", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct", "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct", "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct", "sm__inst_executed_pipe_fp64.avg.pct",
         "sm__inst_executed_pipe_fma.avg.pct", "sm__inst_executed_pipe_alu.avg.pct", "sm__inst_executed_pipe_xu.avg.pct", "sm__inst_executed_pipe_lsu.avg.pct",
         "sm__warps_active.avg.pct", "smsp__issue_active.avg.pct", "smsp__average_warps_issue_stalled", "smsp__inst_executed.sum ",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct", "gpu__dram_throughput.avg.pct", "sm__cycles_active.avg "]
@@ -41,5 +41,10 @@ def full(rep, out):
 
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches_r01.csv", "profiles/launches_r01.txt")
-    full("gpurun_out/top_r01.ncu-rep", "profiles/top_kernels_r01_ncu.txt")
+    # usage: summarize_ncu.py launches <csv> <out.txt> | full <rep> <out.txt>
+    if len(sys.argv) == 4 and sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) == 4 and sys.argv[1] == "full":
+        full(sys.argv[2], sys.argv[3])
+    else:
+        raise SystemExit(__doc__)
