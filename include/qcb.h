@@ -171,6 +171,19 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
                     uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale,
                     double* g, void* ws, size_t ws_bytes, void* stream);
 
+/* A whole CD-k epoch with plain SGD in ONE launch, for a small BinaryRBM (1 <= N, nh <= 32): the batch loop of
+ * NeuralStateBase.fit (nn_states/neural_state.py:611-627).  For step i = 0 .. num_batches-1:
+ *   g = qcb_rbm_cd_step(pos[i*pos_batch : (i+1)*pos_batch], neg[i*neg_batch : (i+1)*neg_batch], k, seed,
+ *                       chain_id0 = 0, sweep0 + i*k, 1/B_i, -1/C_i);   W, b, c -= lr * g   (in place)
+ * pos (B_total, N) and neg (C_total, N) hold the epoch's batches back to back (the last one may be short).
+ * g_last (optional, nh*N + N + nh) receives the gradient of the last step (what param.grad would hold).
+ * Same Philox draws as the per-step call, hence the same chains; sums are associated differently
+ * (agreement to rounding).  Larger layers return QCB_ERR_UNSUPPORTED: use qcb_rbm_cd_step per batch. */
+int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh,
+                     const double* pos, int64_t B_total, int pos_batch,
+                     const double* neg, int64_t C_total, int neg_batch, int num_batches,
+                     int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last, void* stream);
+
 /* ---- Exact enumeration ---------------------------------------------------------------
  * Basis states are generated from their index r in [first_state, first_state + count):
  * visible unit j = (r >> (N-1-j)) & 1 — the row order of generate_hilbert_space

@@ -38,6 +38,9 @@ int run_linear(int mode, const double* M, int m_rows, int m_cols, int transpose_
                const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, cudaStream_t st);
 int run_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                   double* out, cudaStream_t st);
+int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch, const double* neg,
+                 int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last,
+                 cudaStream_t st);
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
 int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, double scale, double* g, int accumulate,
                     void* ws, size_t ws_bytes, cudaStream_t st);
@@ -231,6 +234,13 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
   rc = run_gibbs(p, neg, vk, C, k, seed, chain_id0, sweep0, nullptr, base, gb, st);
   if (rc != QCB_OK) return rc;
   return run_grad_reduce(p, vk, C, neg_scale, g, 1, base + gb, rb, st);
+}
+
+int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch,
+                     const double* neg, int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed,
+                     uint64_t sweep0, double* g_last, void* stream) {
+  return run_cd_epoch(W, b, c, N, nh, pos, B_total, pos_batch, neg, C_total, neg_batch, num_batches, k, lr, seed, sweep0, g_last,
+                      (cudaStream_t)stream);
 }
 
 int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const double* c, const double* d, int N,

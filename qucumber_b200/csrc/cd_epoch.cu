@@ -1,0 +1,269 @@
+// One launch for a whole contrastive-divergence epoch of a small BinaryRBM (N, nh <= 32, plain SGD).
+//
+// Replaces the batch loop of NeuralStateBase.fit (qucumber/nn_states/neural_state.py:611-627): for every
+// batch  g = <grad E>_data / B - <grad E>_{v_k} / C  (compute_batch_gradients, :417-447, with
+// effective_energy_gradient of rbm/binary_rbm.py:98-120 and gibbs_steps :200-228) followed by
+// p -= lr * g  (torch.optim.SGD without momentum).  At the tutorial size (N = nh = 10, 100 + 200 rows per
+// batch, k = 10) a step is a few microseconds of arithmetic, so the per-step path is bound by its seven
+// launches; here the batch loop runs inside one kernel:
+//
+//  * one thread-block cluster of 8 CTAs; every CTA keeps its own FP64 copy of W, b, c in shared memory;
+//  * rows and chains of a batch are dealt to (CTA, warp, slot); a slot is SW = 8/16/32 lanes, lane u of a
+//    slot is hidden unit u in the h | v update and visible unit u in the v | h update, states are bit
+//    masks exchanged by ballot;
+//  * the Gibbs draws follow the library's Philox convention (include/qcb.h) with chain id = row of the
+//    negative batch and sweep = sweep0 + step * k + s, i.e. the samples are those of qcb_rbm_cd_step;
+//    a decision compares the exact FP64 sigmoid with the 16-bit cell of u and evaluates the remaining 37
+//    bits only when p falls inside the cell, which is exactly  u < p;
+//  * per step each CTA reduces its gradient share in a fixed order, the shares are exchanged through
+//    distributed shared memory (one cluster barrier per step, double-buffered), and every CTA applies the
+//    identical update to its copy.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace qcb {
+
+constexpr int CE_CLUSTER = 8;
+
+struct CdEpochArgs {
+  double* W;
+  double* b;
+  double* c;
+  int N, nh;
+  const double* pos;
+  int64_t B_total;
+  int pos_batch;
+  const double* neg;
+  int64_t C_total;
+  int neg_batch;
+  int num_batches;
+  int k;
+  double lr;
+  uint32_t key0, key1;
+  uint32_t sweep0;
+  double* g_last;  // optional (nh*N + N + nh): gradient of the last batch
+};
+
+__host__ __device__ constexpr int ce_threads(int SW) { return SW == 32 ? 256 : 512; }
+
+struct CeSmem {
+  double* Wsm;      // nh x LD
+  double* bsm;      // N
+  double* csm;      // nh
+  double* partial;  // 2 x G, read by the other CTAs of the cluster
+  double* wpart;    // warps x G
+};
+
+__host__ __device__ inline size_t ce_smem_doubles(int N, int nh, int warps) {
+  const int LD = N | 1, G = nh * N + N + nh;
+  return (size_t)nh * LD + N + nh + 2 * (size_t)G + (size_t)warps * G;
+}
+
+// exact  u < sigmoid(x)  for the unit's uniform of (chain, sweep); q0 = first Philox call of the layer
+__device__ __forceinline__ bool ce_decide(double x, int u, uint32_t q0, uint32_t cid0, uint32_t cid1, uint32_t sweep, uint32_t key0,
+                                          uint32_t key1) {
+  const uint32_t q = q0 + 4u * (uint32_t)(u >> 5) + (uint32_t)((u & 15) >> 2);
+  const int word = u & 3;
+  const uint32_t half = (uint32_t)(u >> 4) & 1u;
+  uint32_t r[4];
+  philox4x32_10(cid0, cid1, sweep, q, key0, key1, r);
+  const uint32_t w32 = word == 0 ? r[0] : (word == 1 ? r[1] : (word == 2 ? r[2] : r[3]));
+  const uint32_t h16 = half ? (w32 & 0xFFFFu) : (w32 >> 16);
+  const double p = sigmoid_exact(x);
+  const double lo = (double)h16 * 0x1.0p-16;
+  if (p >= lo + 0x1.0p-16) return true;   // u < lo + 2^-16 <= p
+  if (p <= lo) return false;              // u >= lo >= p
+  uint32_t la[4], lb[4];
+  philox4x32_10(cid0, cid1, sweep, ((1u + 2u * half) << 29) | q, key0, key1, la);
+  philox4x32_10(cid0, cid1, sweep, ((2u + 2u * half) << 29) | q, key0, key1, lb);
+  const uint32_t aw = word == 0 ? la[0] : (word == 1 ? la[1] : (word == 2 ? la[2] : la[3]));
+  const uint32_t bw = word == 0 ? lb[0] : (word == 1 ? lb[1] : (word == 2 ? lb[2] : lb[3]));
+  const uint64_t bits = ((uint64_t)h16 << 37) | ((uint64_t)aw << 5) | (uint64_t)(bw >> 27);
+  return (double)bits * 0x1.0p-53 < p;
+}
+
+template <int SW>
+__global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpochArgs a) {
+  extern __shared__ __align__(16) double ce_smem[];
+  constexpr int NT = ce_threads(SW), NW = NT / 32, CPW = 32 / SW;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int N = a.N, nh = a.nh, LD = N | 1, G = nh * N + N + nh;
+  double* Wsm = ce_smem;
+  double* bsm = Wsm + (size_t)nh * LD;
+  double* csm = bsm + N;
+  double* partial = csm + nh;
+  double* wpart = partial + 2 * (size_t)G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int u = lane % SW, sub = lane / SW;
+  const uint32_t slot_mask = SW == 32 ? 0xffffffffu : ((1u << SW) - 1u);
+  const int slot = (rank * NW + warp) * CPW + sub, nslots = CE_CLUSTER * NW * CPW;
+
+  for (int idx = tid; idx < nh * N; idx += NT) Wsm[(idx / N) * LD + idx % N] = a.W[idx];
+  for (int idx = tid; idx < N; idx += NT) bsm[idx] = a.b[idx];
+  for (int idx = tid; idx < nh; idx += NT) csm[idx] = a.c[idx];
+  __syncthreads();
+
+  // theta_u = c_u + sum_j v_j W_uj  for hidden unit u of this lane
+  auto hidden_pre = [&](uint32_t vm) {
+    double x = u < nh ? csm[u] : 0.0;
+    if (u < nh) {
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        const double w = j < N ? Wsm[u * LD + j] : 0.0;
+        if ((vm >> j) & 1u) x += w;
+      }
+    }
+    return x;
+  };
+  auto visible_pre = [&](uint32_t hm) {
+    double x = u < N ? bsm[u] : 0.0;
+    if (u < N) {
+#pragma unroll
+      for (int i = 0; i < SW; ++i) {
+        const double w = i < nh ? Wsm[i * LD + u] : 0.0;
+        if ((hm >> i) & 1u) x += w;
+      }
+    }
+    return x;
+  };
+  auto slot_bits = [&](bool bit) { return (__ballot_sync(0xffffffffu, bit) >> (sub * SW)) & slot_mask; };
+
+  for (int step = 0; step < a.num_batches; ++step) {
+    const int64_t p0 = (int64_t)step * a.pos_batch, c0 = (int64_t)step * a.neg_batch;
+    const int Bs = (int)(a.B_total - p0 < a.pos_batch ? a.B_total - p0 : a.pos_batch);
+    const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
+    const double* pos_rows = a.pos + p0 * N;
+    const double* neg_rows = a.neg + c0 * N;
+    double accW[SW];
+#pragma unroll
+    for (int j = 0; j < SW; ++j) accW[j] = 0.0;
+    double accb = 0.0, accc = 0.0;
+    // g = (1/B) sum_data grad E - (1/C) sum_chains grad E,  grad E(v) = -[p v^T ; v ; p]
+    auto accumulate = [&](uint32_t vm, bool valid, double weight) {
+      const double pw = (valid && u < nh) ? weight * sigmoid_exact(hidden_pre(vm)) : 0.0;
+      accc += pw;
+#pragma unroll
+      for (int j = 0; j < SW; ++j)
+        if ((vm >> j) & 1u) accW[j] += pw;
+      if (valid && ((vm >> u) & 1u)) accb += weight;
+    };
+
+    // positive phase
+    for (int r0 = 0; r0 < Bs; r0 += nslots) {
+      const int r = r0 + slot;
+      const bool valid = r < Bs;
+      const double raw = (valid && u < N) ? pos_rows[(int64_t)r * N + u] : 0.0;
+      const uint32_t vm = slot_bits(raw != 0.0);
+      accumulate(vm, valid, -1.0 / (double)Bs);
+    }
+    // negative phase: k sweeps from the rows of the negative batch, then the gradient at v_k
+    for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {
+      const int ch = ch0 + slot;
+      const bool valid = ch < Cs;
+      const double raw = (valid && u < N) ? neg_rows[(int64_t)ch * N + u] : 0.0;
+      uint32_t vm = slot_bits(raw != 0.0);
+      const uint32_t cid0 = (uint32_t)ch, cid1 = 0u;
+      for (int s = 0; s < a.k; ++s) {
+        const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s);
+        const bool hb = u < nh && ce_decide(hidden_pre(vm), u, 0u, cid0, cid1, sweep, a.key0, a.key1);
+        const uint32_t hm = slot_bits(hb);
+        const bool vb = u < N && ce_decide(visible_pre(hm), u, 4u * (uint32_t)((nh + 31) / 32), cid0, cid1, sweep, a.key0, a.key1);
+        vm = slot_bits(vb);
+      }
+      accumulate(vm, valid, 1.0 / (double)Cs);
+    }
+
+    // the slots of a warp, then the warps of the CTA, in a fixed order
+#pragma unroll
+    for (int off = SW; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < SW; ++j) accW[j] += __shfl_xor_sync(0xffffffffu, accW[j], off);
+      accb += __shfl_xor_sync(0xffffffffu, accb, off);
+      accc += __shfl_xor_sync(0xffffffffu, accc, off);
+    }
+    double* mine = wpart + (size_t)warp * G;
+    if (sub == 0) {
+      if (u < nh) {
+#pragma unroll
+        for (int j = 0; j < SW; ++j)
+          if (j < N) mine[u * N + j] = accW[j];
+        mine[nh * N + N + u] = accc;
+      }
+      if (u < N) mine[nh * N + u] = accb;
+    }
+    __syncthreads();
+    double* my_partial = partial + (size_t)(step & 1) * G;
+    for (int idx = tid; idx < G; idx += NT) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += wpart[(size_t)w * G + idx];
+      my_partial[idx] = t;
+    }
+    cluster.sync();
+    for (int idx = tid; idx < G; idx += NT) {
+      double g = 0.0;
+      for (int rk = 0; rk < CE_CLUSTER; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
+      double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
+      *prm -= a.lr * g;
+      if (rank == 0 && a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
+    }
+    __syncthreads();
+  }
+  cluster.sync();  // nobody leaves while its shares may still be read
+  if (rank == 0) {
+    for (int idx = tid; idx < nh * N; idx += NT) a.W[idx] = Wsm[(idx / N) * LD + idx % N];
+    for (int idx = tid; idx < N; idx += NT) a.b[idx] = bsm[idx];
+    for (int idx = tid; idx < nh; idx += NT) a.c[idx] = csm[idx];
+  }
+}
+
+template <int SW>
+static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
+  constexpr int NT = ce_threads(SW);
+  const size_t smem = ce_smem_doubles(a.N, a.nh, NT / 32) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    QCB_CUDA(cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: layer too large for the fused epoch kernel");
+  cd_epoch_kernel<SW><<<CE_CLUSTER, NT, smem, st>>>(a);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch, const double* neg,
+                 int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last,
+                 cudaStream_t st) {
+  if (N < 1 || nh < 1 || N > 32 || nh > 32) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: needs 1 <= N, nh <= 32");
+  if (W == nullptr || b == nullptr || c == nullptr || pos == nullptr || neg == nullptr || pos_batch < 1 || neg_batch < 1 ||
+      num_batches < 0 || k < 0)
+    return fail(QCB_ERR_BAD_ARG, "cd_epoch: bad arguments");
+  if ((int64_t)(num_batches - 1) * pos_batch >= B_total && num_batches > 0)
+    return fail(QCB_ERR_BAD_ARG, "cd_epoch: fewer positive rows than batches");
+  if ((int64_t)(num_batches - 1) * neg_batch >= C_total && num_batches > 0)
+    return fail(QCB_ERR_BAD_ARG, "cd_epoch: fewer negative rows than batches");
+  if (sweep0 + (uint64_t)num_batches * (uint64_t)k >= (1ull << 32)) return fail(QCB_ERR_BAD_ARG, "cd_epoch: sweep counter overflow");
+  if (num_batches == 0) return QCB_OK;
+  CdEpochArgs a;
+  a.W = W; a.b = b; a.c = c;
+  a.N = N; a.nh = nh;
+  a.pos = pos; a.B_total = B_total; a.pos_batch = pos_batch;
+  a.neg = neg; a.C_total = C_total; a.neg_batch = neg_batch;
+  a.num_batches = num_batches;
+  a.k = k;
+  a.lr = lr;
+  a.key0 = (uint32_t)seed;
+  a.key1 = (uint32_t)(seed >> 32);
+  a.sweep0 = (uint32_t)sweep0;
+  a.g_last = g_last;
+  const int m = N > nh ? N : nh;
+  if (m <= 8) return launch_cd_epoch<8>(a, st);
+  if (m <= 16) return launch_cd_epoch<16>(a, st);
+  return launch_cd_epoch<32>(a, st);
+}
+
+}  // namespace qcb

@@ -279,6 +279,18 @@ class NeuralStateBase(abc.ABC):
         """Per-epoch batching (neural_state.py:449-498): positive batches are a permutation of the
         data; negative batches reuse it when the sizes match, otherwise they are drawn with
         replacement (from the all-Z samples when bases are given)."""
+        pos, neg, pos_perm = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
+        pos_batches = [pos[s:s + pos_batch_size] for s in range(0, len(pos), pos_batch_size)]
+        neg_batches = [neg[s:s + neg_batch_size] for s in range(0, len(neg), neg_batch_size)]
+        if input_bases is not None:
+            pos_bases = input_bases[pos_perm]
+            bases_batches = [pos_bases[s:s + pos_batch_size] for s in range(0, len(train_samples), pos_batch_size)]
+            return zip(pos_batches, neg_batches, bases_batches)
+        return zip(pos_batches, neg_batches)
+
+    @staticmethod
+    def _shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples):
+        """The epoch's positive rows, negative rows (batches back to back) and the permutation used."""
         pos_perm = torch.randperm(train_samples.shape[0])
         pos = train_samples[pos_perm]
         if input_bases is None:
@@ -290,13 +302,49 @@ class NeuralStateBase(abc.ABC):
         else:
             neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long)
             neg = z_samples[neg_perm]
-        pos_batches = [pos[s:s + pos_batch_size] for s in range(0, len(pos), pos_batch_size)]
-        neg_batches = [neg[s:s + neg_batch_size] for s in range(0, len(neg), neg_batch_size)]
-        if input_bases is not None:
-            pos_bases = input_bases[pos_perm]
-            bases_batches = [pos_bases[s:s + pos_batch_size] for s in range(0, len(train_samples), pos_batch_size)]
-            return zip(pos_batches, neg_batches, bases_batches)
-        return zip(pos_batches, neg_batches)
+        return pos, neg, pos_perm
+
+    #: set to False to force one C call per batch even where a whole epoch fits one launch
+    fuse_epochs = True
+
+    def _epoch_fusable(self, optimizer, cbs, input_bases):
+        """True when the batch loop of an epoch can run as ONE kernel (qcb_rbm_cd_epoch): a single small
+        BinaryRBM, no bases, vanilla SGD, and no callback that acts per batch."""
+        from ..rbm import BinaryRBM
+
+        pg = optimizer.param_groups
+        rbm = getattr(self, "rbm_am", None)
+        if not (self.fuse_epochs and input_bases is None and list(self.networks) == ["rbm_am"] and type(rbm) is BinaryRBM
+                and rbm.num_visible <= 32 and rbm.num_hidden <= 32):
+            return False
+        if not (type(optimizer) is torch.optim.SGD and len(pg) == 1 and pg[0].get("momentum", 0) == 0
+                and pg[0].get("weight_decay", 0) == 0 and pg[0].get("dampening", 0) == 0 and not pg[0].get("nesterov", False)
+                and not pg[0].get("maximize", False)):
+            return False
+
+        def trivial(fn):  # a hook that is absent or only `pass`
+            code = getattr(fn, "__code__", None)
+            return fn is None or (code is not None and len(code.co_code) <= 8 and not code.co_names)
+
+        return all(trivial(getattr(type(cb), hook, None)) for cb in cbs.callbacks for hook in ("on_batch_start", "on_batch_end"))
+
+    def _fit_epoch_fused(self, pos, neg, num_batches, pos_batch_size, neg_batch_size, k, lr, want_grads):
+        """All batches of one epoch in one launch; parameters are updated in place."""
+        rbm = self.rbm_am
+        lib = _lib.load()
+        if self._cd_sweep + num_batches * int(k) >= (1 << 31):
+            self._cd_seed, self._cd_sweep = next_seed(), 0
+        pos = pos.contiguous()
+        neg = neg.contiguous()
+        g_last = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device) if want_grads else None
+        _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(rbm.weights.data), _lib.ptr(rbm.visible_bias.data), _lib.ptr(rbm.hidden_bias.data),
+                                        rbm.num_visible, rbm.num_hidden, _lib.ptr(pos), pos.shape[0], int(pos_batch_size),
+                                        _lib.ptr(neg), neg.shape[0], int(neg_batch_size), int(num_batches), int(k), float(lr),
+                                        self._cd_seed, self._cd_sweep, _lib.ptr(g_last), _lib.stream_ptr(self.device)),
+                   "qcb_rbm_cd_epoch")
+        self._cd_sweep += num_batches * int(k)
+        if want_grads:
+            vector_to_grads(g_last, rbm.parameters())
 
     def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1e-3, input_bases=None, progbar=False,
             starting_epoch=1, time=False, callbacks=None, optimizer=torch.optim.SGD, optimizer_args=None, scheduler=None,
@@ -338,9 +386,18 @@ class NeuralStateBase(abc.ABC):
             from tqdm import tqdm, tqdm_notebook
 
             epoch_iter = (tqdm_notebook if progbar == "notebook" else tqdm)(epoch_iter, desc="Epochs ")
+        fused_epoch = self._epoch_fusable(optimizer, cbs, input_bases)
         for ep in epoch_iter:
-            batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
-            cbs.fire("on_epoch_start", self, ep)
+            if fused_epoch:
+                pos, neg, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None)
+                cbs.fire("on_epoch_start", self, ep)
+                nb = min(num_batches, ceil(neg.shape[0] / neg_batch_size))
+                self._fit_epoch_fused(pos, neg, nb, pos_batch_size, neg_batch_size, k, optimizer.param_groups[0]["lr"],
+                                      want_grads=bool(cbs.callbacks))
+                batches = ()
+            else:
+                batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
+                cbs.fire("on_epoch_start", self, ep)
             for b, batch in enumerate(batches):
                 cbs.fire("on_batch_start", self, ep, b)
                 all_grads = self.compute_batch_gradients(k, *batch)

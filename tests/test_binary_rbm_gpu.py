@@ -256,6 +256,49 @@ def test_cd_step_matches_oracle_philox(lib, cuda):
     assert np.array_equal(tn.cpu().numpy(), neg)
 
 
+@pytest.mark.parametrize("n,nh,B,C,pb,nb_,k", [(7, 5, 53, 90, 10, 17, 2), (10, 10, 230, 460, 100, 200, 3), (20, 30, 64, 64, 16, 16, 2),
+                                                (32, 32, 40, 40, 40, 40, 1)])
+def test_cd_epoch_matches_oracle(lib, cuda, n, nh, B, C, pb, nb_, k):
+    """qcb_rbm_cd_epoch (a whole epoch of CD-k + SGD in one launch) == the oracle's batch loop:
+    g_i = <grad E>_pos_i / B_i - <grad E>_{v_k} / C_i with v_k from the Philox stream (chain id = row of
+    the negative batch, sweep = sweep0 + i k + s), W, b, c -= lr g_i; short last batches included."""
+    from qucumber_b200 import _lib
+
+    W, b, c = make_binary_params(n, nh, 400 + n)
+    pos, neg = random_states(B, n, 401), random_states(C, n, 402)
+    lr, seed, sweep0 = 0.05, 777, 11
+    num_batches = min(-(-B // pb), -(-C // nb_))
+    Wo, bo, co = W.copy(), b.copy(), c.copy()
+    g_want = None
+    for i in range(num_batches):
+        o = BinaryRBMOracle(Wo, bo, co)
+        p_i, n_i = pos[i * pb:(i + 1) * pb], neg[i * nb_:(i + 1) * nb_]
+        vk = o.gibbs_steps_philox(k, n_i, seed=seed, chain_id0=0, sweep0=sweep0 + i * k)
+        g_want = o.effective_energy_gradient(p_i) / len(p_i) - o.effective_energy_gradient(vk) / len(n_i)
+        Wo = Wo - lr * g_want[:nh * n].reshape(nh, n)
+        bo = bo - lr * g_want[nh * n:nh * n + n]
+        co = co - lr * g_want[nh * n + n:]
+    tW, tb, tc = (torch.tensor(x, device=cuda) for x in (W, b, c))
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+    g_last = torch.empty(nh * n + n + nh, dtype=torch.double, device=cuda)
+    _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), n, nh, _lib.ptr(tp), B, pb, _lib.ptr(tn), C, nb_,
+                                    num_batches, k, lr, seed, sweep0, _lib.ptr(g_last), _lib.stream_ptr(cuda)), "qcb_rbm_cd_epoch")
+    assert_close(tW, Wo, what="weights after the fused epoch")
+    assert_close(tb, bo, what="visible bias after the fused epoch")
+    assert_close(tc, co, what="hidden bias after the fused epoch")
+    assert_close(g_last, g_want, what="gradient of the last batch")
+    assert np.array_equal(tn.cpu().numpy(), neg) and np.array_equal(tp.cpu().numpy(), pos)
+
+
+def test_cd_epoch_rejects_large_layers(lib, cuda):
+    from qucumber_b200 import _lib
+
+    z = torch.zeros(64 * 64, dtype=torch.double, device=cuda)
+    rc = lib.qcb_rbm_cd_epoch(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 64, 64, _lib.ptr(z), 4, 2, _lib.ptr(z), 4, 2, 2, 1, 0.1, 1, 0, None,
+                              _lib.stream_ptr(cuda))
+    assert rc != 0 and b"cd_epoch" in lib.qcb_last_error()
+
+
 def test_empty_and_degenerate_inputs(lib, cuda):
     """Empty batches, zero sweeps and error reporting through the C ABI."""
     from qucumber_b200 import BinaryRBM, _lib

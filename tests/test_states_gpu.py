@@ -302,6 +302,43 @@ def test_fit_trains_tutorial1_like(lib, cuda):
     assert abs(np.mean(kls) - 0.29) < 0.03, kls
 
 
+def test_fit_fused_epoch_equals_per_batch_path(lib, cuda):
+    """fit() runs an epoch of a small PositiveWaveFunction as one launch (qcb_rbm_cd_epoch); with the same
+    torch seed it must land on the parameters of the per-batch path (one qcb_rbm_cd_step + SGD update per
+    batch), and a callback with batch hooks must switch the fusion off."""
+    from qucumber_b200 import PositiveWaveFunction
+
+    g = gold("binary_rbm_tfim10.npz")
+    train = torch.tensor(np.unpackbits(g["train_packed"], axis=1)[:1030, :10].astype(np.float64))
+    out = []
+    for fuse in (True, False):
+        torch.manual_seed(4242)
+        nn = PositiveWaveFunction(10, 10, gpu=True)
+        nn.fuse_epochs = fuse
+        load_binary(nn.rbm_am, g["weights"], g["visible_bias"], g["hidden_bias"])
+        launches0 = lib.qcb_launch_count()
+        nn.fit(train, epochs=3, pos_batch_size=100, neg_batch_size=200, k=5, lr=0.05)
+        out.append(([p.detach().cpu().numpy().copy() for p in nn.rbm_am.parameters()], lib.qcb_launch_count() - launches0))
+    (pf, lf), (pu, lu) = out
+    assert lf == 3 and lu > 3 * 11
+    for a, b, name in zip(pf, pu, ("weights", "visible_bias", "hidden_bias")):
+        assert_close(a, b, what=f"{name}: fused epoch vs per-batch path")
+
+    class BatchHook:
+        def __init__(self):
+            self.n = 0
+
+        def on_batch_end(self, s, ep, b):
+            self.n += 1
+
+    torch.manual_seed(4242)
+    nn = PositiveWaveFunction(10, 10, gpu=True)
+    load_binary(nn.rbm_am, g["weights"], g["visible_bias"], g["hidden_bias"])
+    hook = BatchHook()
+    nn.fit(train, epochs=1, pos_batch_size=100, neg_batch_size=200, k=5, lr=0.05, callbacks=[hook])
+    assert hook.n == 11
+
+
 def test_fit_complex_and_density_smoke(lib, cuda):
     """Parameters move after one epoch with mixed bases (reference tests/test_training.py:40-70)."""
     from qucumber_b200 import ComplexWaveFunction, DensityMatrix
