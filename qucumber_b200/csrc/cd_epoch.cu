@@ -7,7 +7,7 @@
 // batch, k = 10) a step is a few microseconds of arithmetic, so the per-step path is bound by its seven
 // launches; here the batch loop runs inside one kernel:
 //
-//  * one thread-block cluster of 8 CTAs; every CTA keeps its own FP64 copy of W, b, c in shared memory;
+//  * one thread-block cluster of 16 CTAs (8 where 16 cannot be co-scheduled); every CTA keeps its own FP64 copy of W, b, c in shared memory;
 //  * rows and chains of a batch are dealt to (CTA, warp, slot); a slot is SW = 8/16/32 lanes, lane u of a
 //    slot is hidden unit u in the h | v update and visible unit u in the v | h update, states are bit
 //    masks exchanged by ballot;
@@ -26,7 +26,7 @@ namespace cg = cooperative_groups;
 
 namespace qcb {
 
-constexpr int CE_CLUSTER = 8;
+constexpr int CE_CLUSTER_PORTABLE = 8, CE_CLUSTER_MAX = 16;
 
 struct CdEpochArgs {
   double* W;
@@ -47,31 +47,44 @@ struct CdEpochArgs {
   double* g_last;  // optional (nh*N + N + nh): gradient of the last batch
 };
 
-__host__ __device__ constexpr int ce_threads(int SW) { return SW == 32 ? 256 : 512; }
+__host__ __device__ constexpr int ce_threads(int) { return 256; }
 
-struct CeSmem {
-  double* Wsm;      // nh x LD
-  double* bsm;      // N
-  double* csm;      // nh
-  double* partial;  // 2 x G, read by the other CTAs of the cluster
-  double* wpart;    // warps x G
-};
-
-__host__ __device__ inline size_t ce_smem_doubles(int N, int nh, int warps) {
+// shared memory: W (nh x LD), b, c, the CTA's gradient share (2 x G, read by the other CTAs), per-warp shares (warps x G)
+__host__ __device__ inline size_t ce_smem_doubles(int N, int nh, int SW, int warps) {
   const int LD = N | 1, G = nh * N + N + nh;
-  return (size_t)nh * LD + N + nh + 2 * (size_t)G + (size_t)warps * G;
+  return (size_t)SW * LD + N + nh + 2 * (size_t)G + (size_t)warps * G;
 }
 
-// exact  u < sigmoid(x)  for the unit's uniform of (chain, sweep); q0 = first Philox call of the layer
-__device__ __forceinline__ bool ce_decide(double x, int u, uint32_t q0, uint32_t cid0, uint32_t cid1, uint32_t sweep, uint32_t key0,
-                                          uint32_t key1) {
+// The 16-bit cell of the unit's uniform for (chain, sweep); q0 = first Philox call of the layer.
+__device__ __forceinline__ uint32_t ce_cell(int u, uint32_t q0, uint32_t cid0, uint32_t cid1, uint32_t sweep, uint32_t key0, uint32_t key1) {
   const uint32_t q = q0 + 4u * (uint32_t)(u >> 5) + (uint32_t)((u & 15) >> 2);
   const int word = u & 3;
-  const uint32_t half = (uint32_t)(u >> 4) & 1u;
   uint32_t r[4];
   philox4x32_10(cid0, cid1, sweep, q, key0, key1, r);
   const uint32_t w32 = word == 0 ? r[0] : (word == 1 ? r[1] : (word == 2 ? r[2] : r[3]));
-  const uint32_t h16 = half ? (w32 & 0xFFFFu) : (w32 >> 16);
+  return ((u >> 4) & 1) ? (w32 & 0xFFFFu) : (w32 >> 16);
+}
+
+// Branch-free float filter: 1 / 0 when  u < sigmoid(x)  is certainly true / false, 2 when undecided.
+// |p~ - sigmoid(x)| <= 0.25 (3 |x| 2^-24 + 2^-22) + 2^-22 < 2^-18 for |x| <= 64 (conversion of x, the two roundings of
+// the exponent argument, ex2.approx, 1 + e, rcp.approx); tested with margin 2^-17.
+__device__ __forceinline__ int ce_filter(double x, uint32_t h16) {
+  const float xf = (float)x;
+  float e, pf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xf * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pf) : "f"(1.0f + e));
+  const float lof = (float)h16 * 0x1.0p-16f;
+  const bool sure1 = pf - 0x1.0p-17f >= lof + 0x1.0p-16f, sure0 = pf + 0x1.0p-17f <= lof;
+  const int verdict = sure1 ? 1 : (sure0 ? 0 : 2);
+  return fabsf(xf) <= 64.0f ? verdict : 2;
+}
+
+// Cold path: the exact FP64 comparison  u < sigmoid(x)  with the full 53-bit uniform.
+__device__ __noinline__ bool ce_decide_exact(double x, uint32_t h16, int u, uint32_t q0, uint32_t cid0, uint32_t cid1, uint32_t sweep,
+                                             uint32_t key0, uint32_t key1) {
+  const uint32_t q = q0 + 4u * (uint32_t)(u >> 5) + (uint32_t)((u & 15) >> 2);
+  const int word = u & 3;
+  const uint32_t half = (uint32_t)(u >> 4) & 1u;
   const double p = sigmoid_exact(x);
   const double lo = (double)h16 * 0x1.0p-16;
   if (p >= lo + 0x1.0p-16) return true;   // u < lo + 2^-16 <= p
@@ -86,51 +99,57 @@ __device__ __forceinline__ bool ce_decide(double x, int u, uint32_t q0, uint32_t
 }
 
 template <int SW>
-__global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpochArgs a) {
+__global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpochArgs a) {
   extern __shared__ __align__(16) double ce_smem[];
   constexpr int NT = ce_threads(SW), NW = NT / 32, CPW = 32 / SW;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int N = a.N, nh = a.nh, LD = N | 1, G = nh * N + N + nh;
   double* Wsm = ce_smem;
-  double* bsm = Wsm + (size_t)nh * LD;
+  double* bsm = Wsm + (size_t)SW * LD;  // W region padded to SW rows
   double* csm = bsm + N;
   double* partial = csm + nh;
   double* wpart = partial + 2 * (size_t)G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u = lane % SW, sub = lane / SW;
   const uint32_t slot_mask = SW == 32 ? 0xffffffffu : ((1u << SW) - 1u);
-  const int slot = (rank * NW + warp) * CPW + sub, nslots = CE_CLUSTER * NW * CPW;
+  const int nranks = (int)cluster.num_blocks();
+  const int slot = (rank * NW + warp) * CPW + sub, nslots = nranks * NW * CPW;
 
   for (int idx = tid; idx < nh * N; idx += NT) Wsm[(idx / N) * LD + idx % N] = a.W[idx];
   for (int idx = tid; idx < N; idx += NT) bsm[idx] = a.b[idx];
   for (int idx = tid; idx < nh; idx += NT) csm[idx] = a.c[idx];
   __syncthreads();
 
-  // theta_u = c_u + sum_j v_j W_uj  for hidden unit u of this lane
+  // theta_u = c_u + sum_j v_j W_uj  for hidden unit u of this lane.  Branch-free: lanes past the layer compute on a
+  // clamped row, and columns j >= N are loaded (the W region is padded to SW rows, so this stays in bounds) but never
+  // selected because mask bits >= N are zero.
+  const int uh = u < nh ? u : nh - 1, uv = u < N ? u : N - 1;
   auto hidden_pre = [&](uint32_t vm) {
-    double x = u < nh ? csm[u] : 0.0;
-    if (u < nh) {
+    const double* row = Wsm + uh * LD;
+    double x[4] = {csm[uh], 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int j = 0; j < SW; ++j) {
-        const double w = j < N ? Wsm[u * LD + j] : 0.0;
-        if ((vm >> j) & 1u) x += w;
-      }
-    }
-    return x;
+    for (int j = 0; j < SW; ++j)
+      if ((vm >> j) & 1u) x[j & 3] += row[j];
+    return (x[0] + x[1]) + (x[2] + x[3]);
   };
   auto visible_pre = [&](uint32_t hm) {
-    double x = u < N ? bsm[u] : 0.0;
-    if (u < N) {
+    const double* col = Wsm + uv;
+    double x[4] = {bsm[uv], 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int i = 0; i < SW; ++i) {
-        const double w = i < nh ? Wsm[i * LD + u] : 0.0;
-        if ((hm >> i) & 1u) x += w;
-      }
-    }
-    return x;
+    for (int i = 0; i < SW; ++i)
+      if ((hm >> i) & 1u) x[i & 3] += col[i * LD];
+    return (x[0] + x[1]) + (x[2] + x[3]);
   };
   auto slot_bits = [&](bool bit) { return (__ballot_sync(0xffffffffu, bit) >> (sub * SW)) & slot_mask; };
+
+  // the slot's first row of each phase is fetched one step ahead (the batches are known in advance)
+  auto first_row = [&](const double* rows_all, int64_t total, int batch, int step) {
+    const int64_t start = (int64_t)step * batch;
+    const int64_t rows = total - start < batch ? total - start : batch;
+    return (step < a.num_batches && slot < rows && u < N) ? rows_all[(start + slot) * N + u] : 0.0;
+  };
+  double next_pos = first_row(a.pos, a.B_total, a.pos_batch, 0), next_neg = first_row(a.neg, a.C_total, a.neg_batch, 0);
 
   for (int step = 0; step < a.num_batches; ++step) {
     const int64_t p0 = (int64_t)step * a.pos_batch, c0 = (int64_t)step * a.neg_batch;
@@ -138,13 +157,17 @@ __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(
     const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
     const double* pos_rows = a.pos + p0 * N;
     const double* neg_rows = a.neg + c0 * N;
+    const double first_pos = next_pos, first_neg = next_neg;
+    next_pos = first_row(a.pos, a.B_total, a.pos_batch, step + 1);
+    next_neg = first_row(a.neg, a.C_total, a.neg_batch, step + 1);
     double accW[SW];
 #pragma unroll
     for (int j = 0; j < SW; ++j) accW[j] = 0.0;
     double accb = 0.0, accc = 0.0;
     // g = (1/B) sum_data grad E - (1/C) sum_chains grad E,  grad E(v) = -[p v^T ; v ; p]
     auto accumulate = [&](uint32_t vm, bool valid, double weight) {
-      const double pw = (valid && u < nh) ? weight * sigmoid_exact(hidden_pre(vm)) : 0.0;
+      const double sg = sigmoid_exact(hidden_pre(vm));
+      const double pw = (valid && u < nh) ? weight * sg : 0.0;
       accc += pw;
 #pragma unroll
       for (int j = 0; j < SW; ++j)
@@ -156,7 +179,7 @@ __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(
     for (int r0 = 0; r0 < Bs; r0 += nslots) {
       const int r = r0 + slot;
       const bool valid = r < Bs;
-      const double raw = (valid && u < N) ? pos_rows[(int64_t)r * N + u] : 0.0;
+      const double raw = r0 == 0 ? first_pos : ((valid && u < N) ? pos_rows[(int64_t)r * N + u] : 0.0);
       const uint32_t vm = slot_bits(raw != 0.0);
       accumulate(vm, valid, -1.0 / (double)Bs);
     }
@@ -164,15 +187,30 @@ __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(
     for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {
       const int ch = ch0 + slot;
       const bool valid = ch < Cs;
-      const double raw = (valid && u < N) ? neg_rows[(int64_t)ch * N + u] : 0.0;
+      const double raw = ch0 == 0 ? first_neg : ((valid && u < N) ? neg_rows[(int64_t)ch * N + u] : 0.0);
       uint32_t vm = slot_bits(raw != 0.0);
       const uint32_t cid0 = (uint32_t)ch, cid1 = 0u;
       for (int s = 0; s < a.k; ++s) {
         const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s);
-        const bool hb = u < nh && ce_decide(hidden_pre(vm), u, 0u, cid0, cid1, sweep, a.key0, a.key1);
-        const uint32_t hm = slot_bits(hb);
-        const bool vb = u < N && ce_decide(visible_pre(hm), u, 4u * (uint32_t)((nh + 31) / 32), cid0, cid1, sweep, a.key0, a.key1);
-        vm = slot_bits(vb);
+        const uint32_t qv0 = 4u * (uint32_t)((nh + 31) / 32);
+        const uint32_t cell_h = ce_cell(u, 0u, cid0, cid1, sweep, a.key0, a.key1);
+        const uint32_t cell_v = ce_cell(u, qv0, cid0, cid1, sweep, a.key0, a.key1);  // independent of the state: overlaps the h | v update
+        const double xh = hidden_pre(vm);
+        int verdict = ce_filter(xh, cell_h);
+        verdict = u < nh ? verdict : 0;
+        if (__any_sync(0xffffffffu, verdict == 2)) {
+          if (verdict == 2) verdict = ce_decide_exact(xh, cell_h, u, 0u, cid0, cid1, sweep, a.key0, a.key1) ? 1 : 0;
+          __syncwarp();
+        }
+        const uint32_t hm = slot_bits(verdict == 1);
+        const double xv = visible_pre(hm);
+        verdict = ce_filter(xv, cell_v);
+        verdict = u < N ? verdict : 0;
+        if (__any_sync(0xffffffffu, verdict == 2)) {
+          if (verdict == 2) verdict = ce_decide_exact(xv, cell_v, u, qv0, cid0, cid1, sweep, a.key0, a.key1) ? 1 : 0;
+          __syncwarp();
+        }
+        vm = slot_bits(verdict == 1);
       }
       accumulate(vm, valid, 1.0 / (double)Cs);
     }
@@ -205,7 +243,7 @@ __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(
     cluster.sync();
     for (int idx = tid; idx < G; idx += NT) {
       double g = 0.0;
-      for (int rk = 0; rk < CE_CLUSTER; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
+      for (int rk = 0; rk < nranks; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
       double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
       *prm -= a.lr * g;
       if (rank == 0 && a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
@@ -223,14 +261,36 @@ __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(ce_threads(
 template <int SW>
 static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
   constexpr int NT = ce_threads(SW);
-  const size_t smem = ce_smem_doubles(a.N, a.nh, NT / 32) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    QCB_CUDA(cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  const size_t smem = ce_smem_doubles(a.N, a.nh, SW, NT / 32) * sizeof(double);
   if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: layer too large for the fused epoch kernel");
-  cd_epoch_kernel<SW><<<CE_CLUSTER, NT, smem, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // one cluster; 16 CTAs (non-portable size) when the device can co-schedule them, else the portable 8
+  static int cluster_size = 0;
+  if (cluster_size == 0) {
+    QCB_CUDA(cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cluster_size = CE_CLUSTER_PORTABLE;
+    if (cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      int nclusters = 0;
+      cfg.gridDim = dim3(CE_CLUSTER_MAX, 1, 1);
+      attr[0].val.clusterDim.x = CE_CLUSTER_MAX;
+      cfg.dynamicSmemBytes = 200 * 1024;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, cd_epoch_kernel<SW>, &cfg) == cudaSuccess && nclusters >= 1) cluster_size = CE_CLUSTER_MAX;
+      cfg.dynamicSmemBytes = smem;
+    }
+    (void)cudaGetLastError();
+  }
+  cfg.gridDim = dim3(cluster_size, 1, 1);
+  attr[0].val.clusterDim.x = cluster_size;
+  QCB_CUDA(cudaLaunchKernelEx(&cfg, cd_epoch_kernel<SW>, a));
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
