@@ -150,7 +150,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extra_metrics(dev, lib_mod):
@@ -409,10 +409,10 @@ def run_ours(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_step, "site_updates_per_s": value * N_VIS,
+            emit({"quick": True, "value": value, "ms_per_step": ms_step, "site_updates_per_s": value * N_VIS,
                               "fp64_equiv_frac": C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 37.117e12,
                               "fp64_mode_value": world * C * k / (fp64_ms_step * 1e-3),
-                              "fp64_mode_frac": C * k * FLOP_PER_SWEEP / (fp64_ms_step * 1e-3) / 37.117e12, "clocks": clocks}), flush=True)
+                              "fp64_mode_frac": C * k * FLOP_PER_SWEEP / (fp64_ms_step * 1e-3) / 37.117e12, "clocks": clocks})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -487,12 +487,26 @@ def run_ours(args):
                                     "sample": f"{args.ref_chains} chains x k={k} sweeps, best of 3 ({min(cpu_times):.2f} s), "
                                               "reference torch-CPU operator sequence (oracle/cpu_path.py)"}
             line["extra"] = extra_metrics(dev, _lib)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL's version banner,
+    library chatter) was redirected to stderr in main()."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
