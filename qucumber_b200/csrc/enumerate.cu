@@ -326,6 +326,119 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_fast_kernel(const EnumArgs 
   }
 }
 
+// ---- product-form fast path for the fidelity / KL sums ---------------------------------------------
+// Same walk as enum_fast_kernel, but a WARP owns an aligned block of 2^(m+5) indices: lane l holds the five
+// lowest index bits (its own visible bits for the last five units) and all lanes flip the same higher bit at
+// every step, so the per-state reads of the target amplitudes are 256 contiguous bytes per warp.
+// Per state: p = e^{-E} / Z from the running product, then the five sums of MODE 1 above.
+template <int NHT>
+__global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const EnumArgs a, double* __restrict__ partials,
+                                                                       const int* __restrict__ flags) {
+  if (flags[0] == 0) return;
+  const bool no_thresh = flags[1] != 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = a.p.N, H = a.p.nhid();
+  double* Wt = reinterpret_cast<double*>(smem_raw);
+  double* Ep = Wt + (size_t)N * NHT;
+  double* Em = Ep + (size_t)N * NHT;
+  double* hb = Em + (size_t)N * NHT;
+  double* vb = hb + NHT;
+  double* ebp = vb + round_up(N, 2);
+  double* ebm = ebp + round_up(N, 2);
+  double* red = ebm + round_up(N, 2);  // 8 doubles per warp
+  stage_enum<NHT>(a.p, Wt, hb, vb);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
+    const int i = idx % NHT;
+    Ep[idx] = i < H ? exp(Wt[idx]) : 1.0;
+    Em[idx] = i < H ? exp(-Wt[idx]) : 1.0;
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) { ebp[j] = exp(vb[j]); ebm[j] = exp(-vb[j]); }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = a.m < N - 5 ? a.m : N - 5;  // per-lane walk length (log2); the caller guarantees N >= 7
+  const int wshift = m + 5;
+  const uint64_t last = a.first + a.count;
+  const uint64_t wb0 = a.first >> wshift, nwb = ((last - 1) >> wshift) - wb0 + 1;
+  const uint32_t steps = 1u << m;
+  const double E20 = 485165195.40979028;  // e^20
+  const double Zinv = exp(-a.logZ);
+  const double eps = 0x1.0p-52;
+  double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (uint64_t wb = (uint64_t)blockIdx.x * (ENUM_THREADS / 32) + warp; wb < nwb; wb += (uint64_t)gridDim.x * (ENUM_THREADS / 32)) {
+    const uint64_t base = ((wb0 + wb) << wshift) | (uint64_t)lane;
+    double t[NHT];
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) t[i] = hb[i];
+    double bv = 0.0;
+    for (int j = 0; j < N; ++j) {
+      if ((base >> (N - 1 - j)) & 1ull) {
+        const double* col = Wt + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) t[i] += col[i];
+        bv += vb[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NHT; ++i) t[i] = i < H ? exp(t[i]) : 0.0;
+    double eb = exp(bv);
+    for (uint32_t k = 0; k < steps; ++k) {
+      const uint64_t idx = base | ((uint64_t)(k ^ (k >> 1)) << 5);
+      double p0 = eb, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+      if (no_thresh) {
+#pragma unroll
+        for (int i = 0; i < NHT; i += 4) {
+          p0 *= 1.0 + t[i]; p1 *= 1.0 + t[i + 1]; p2 *= 1.0 + t[i + 2]; p3 *= 1.0 + t[i + 3];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NHT; i += 4) {
+          p0 *= t[i] > E20 ? t[i] : 1.0 + t[i];
+          p1 *= t[i + 1] > E20 ? t[i + 1] : 1.0 + t[i + 1];
+          p2 *= t[i + 2] > E20 ? t[i + 2] : 1.0 + t[i + 2];
+          p3 *= t[i + 3] > E20 ? t[i + 3] : 1.0 + t[i + 3];
+        }
+      }
+      const double p = ((p0 * p1) * (p2 * p3)) * Zinv;
+      if (idx >= a.first && idx < last) {
+        sums[4] += p;
+        if (a.t_re != nullptr) {
+          const double tr = a.t_re[idx - a.first];
+          const double ti = a.t_im != nullptr ? a.t_im[idx - a.first] : 0.0;
+          const double psi = sqrt(p);
+          sums[0] = fma(tr, psi, sums[0]);
+          sums[1] = fma(ti, psi, sums[1]);
+          const double pt = tr * tr + ti * ti;
+          sums[2] = fma(pt, log(fmin(fmax(pt, eps), 1.0 - eps)), sums[2]);
+          sums[3] = fma(pt, log(fmin(fmax(p, eps), 1.0 - eps)), sums[3]);
+        }
+      }
+      if (k + 1 < steps) {
+        const uint32_t k1 = k + 1;
+        const int pbit = __ffs(k1) - 1;
+        const uint32_t g1 = k1 ^ (k1 >> 1);
+        const bool up = (g1 >> pbit) & 1u;
+        const int j = N - 1 - (pbit + 5);
+        const double* col = (up ? Ep : Em) + (size_t)j * NHT;
+#pragma unroll
+        for (int i = 0; i < NHT; ++i) t[i] *= col[i];
+        eb *= up ? ebp[j] : ebm[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) sums[q] = warp_sum(sums[q]);
+  if (lane == 0)
+    for (int q = 0; q < 5; ++q) red[8 * warp + q] = sums[q];
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double tot = 0.0;
+    for (int w = 0; w < ENUM_THREADS / 32; ++w) tot += red[8 * w + threadIdx.x];
+    partials[8 * blockIdx.x + threadIdx.x] = tot;
+  }
+}
+
 __global__ void lse_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   LSE t{-INFINITY, 0.0};
@@ -502,9 +615,38 @@ int run_exact_stats_range(const StackedParams& p, uint64_t first, uint64_t count
   a.t_re = t_re;
   a.t_im = t_im;
   double* partials = reinterpret_cast<double*>(ws);
+  int* flags = reinterpret_cast<int*>(static_cast<char*>(ws) + enum_partials_bytes());
   int grid = 0;
   if (count > 0) {
-    QCB_ENUM_DISPATCH(1, a, partials, &grid, st)
+    const int nht = pick_nht(p.nhid());
+    const size_t fast_smem = ((size_t)3 * p.N * nht + nht + 3 * round_up(p.N, 2) + 8 * (ENUM_THREADS / 32)) * sizeof(double);
+    const bool fast = p.N >= 7 && fast_smem <= 200 * 1024 && logZ > -600.0 && logZ < 700.0;
+    // both kernels are launched on the same grid; the device-side pre-pass picks the one that works
+    const uint64_t need = (a.nblocks + ENUM_THREADS - 1) / ENUM_THREADS;
+    const uint64_t cap = (uint64_t)enum_max_grid();
+    const int fgrid = (int)(need < cap ? need : cap);
+    if (fast) {
+      enum_bounds_kernel<<<1, 128, 0, st>>>(p, flags);
+      QCB_LAUNCH_CHECK();
+#define QCB_STATS_FAST(NHT)                                                                                              \
+  QCB_CUDA(cudaFuncSetAttribute(enum_stats_fast_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+  enum_stats_fast_kernel<NHT><<<fgrid, ENUM_THREADS, fast_smem, st>>>(a, partials, flags);
+      switch (nht) {
+        case 8: { QCB_STATS_FAST(8) } break;
+        case 16: { QCB_STATS_FAST(16) } break;
+        case 32: { QCB_STATS_FAST(32) } break;
+        default: { QCB_STATS_FAST(64) } break;
+      }
+#undef QCB_STATS_FAST
+      QCB_LAUNCH_CHECK();
+    }
+    const int* gflags = fast ? flags : nullptr;
+    switch (nht) {
+      case 8: rc = launch_enum<8, 1>(a, partials, &grid, st, gflags); break;
+      case 16: rc = launch_enum<16, 1>(a, partials, &grid, st, gflags); break;
+      case 32: rc = launch_enum<32, 1>(a, partials, &grid, st, gflags); break;
+      default: rc = launch_enum<64, 1>(a, partials, &grid, st, gflags); break;
+    }
     if (rc != QCB_OK) return rc;
   }
   sums_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out8);
