@@ -247,6 +247,38 @@ def extra_metrics(dev, lib_mod):
                            "chain_sweeps_per_s": (1 << 20) * 10 / (ms * 1e-3)}
     except Exception as exc:  # pragma: no cover
         out["cdk_step"] = {"error": str(exc)}
+
+    # ---- batched gradient (north_star item 2): effective_energy_gradient(v) over 2^20 rows, both named shapes.
+    # Algorithmic cost per row: N*8 B read, 4*N*nh flop -> HBM GB/s against the measured peak and
+    # FP64 TFLOP/s against the measured DMMA peak, whichever binds.
+    try:
+        hbm_peak = 6550.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                mp = json.load(fh)
+            hbm_peak = float(mp.get("hbm_gbs", hbm_peak))
+        except Exception:
+            pass
+        rows = 1 << 20
+        res = {}
+        for name, (nv, nhd) in {"S64": (64, 64), "T4": (10, 10)}.items():
+            rb = BinaryRBM(nv, nhd, gpu=True)
+            gen = torch.Generator().manual_seed(99)
+            with torch.no_grad():
+                rb.weights.copy_(torch.randn(nhd, nv, dtype=torch.double, generator=gen) / np.sqrt(nv))
+            vv = (torch.rand(rows, nv, generator=gen) < 0.5).to(torch.double).to(dev)
+            ms_g, _ = timed(lambda: rb.effective_energy_gradient(vv))
+            gbs = rows * nv * 8 / (ms_g * 1e-3) / 1e9
+            tf = rows * 4 * nv * nhd / (ms_g * 1e-3) / 1e12
+            res[name] = {"N": nv, "nh": nhd, "rows": rows, "ms": ms_g, "hbm_gbps": gbs, "hbm_frac": gbs / hbm_peak,
+                         "fp64_tflops": tf, "fp64_frac_of_dmma_peak": tf / 37.117,
+                         # floors: HBM = N*8 B per row; FP64 pipe = the contraction (4*N*nh flop) plus nh exact sigmoids (~50 DFMA each)
+                         "hbm_floor_ms": rows * nv * 8 / (hbm_peak * 1e9) * 1e3,
+                         "fp64_floor_ms": rows * (2 * nv * nhd + 50 * nhd) / 18.4e12 * 1e3}
+        res["hbm_peak_gbps"] = hbm_peak
+        out["batched_gradient"] = res
+    except Exception as exc:  # pragma: no cover
+        out["batched_gradient"] = {"error": str(exc)}
     # ---- Tutorial 2 / 3 epochs (config 2): rotated-basis training of 2-qubit Complex / Density states
     try:
         from qucumber_b200 import ComplexWaveFunction, DensityMatrix

@@ -74,7 +74,8 @@ enum {
   QCB_OP_CWF_ROTATED = 6,
   QCB_OP_DM_ROTATED = 7,
   QCB_OP_CDK_NEG = 8,
-  QCB_OP_CD_STEP = 9
+  QCB_OP_CD_STEP = 9,
+  QCB_OP_KL_TERMS = 10
 };
 
 int qcb_version(void);
@@ -242,6 +243,22 @@ int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, c
                    int N, int nh, int na, const double* samples, int64_t B, const uint8_t* basis,
                    const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Full-space rotated metrics --------------------------------------------------------
+ * qcb_kron_rotate: x <- (U_0 (x) U_1 (x) ... (x) U_{n-1}) x on the leading index of a planar complex array
+ * x[i * batch + t], i in [0, 2^n), in place (re and im planes).  basis is a HOST array of n codes into
+ * unitaries (K, 2, 2, 2) = [code][re/im][row][col]; code 0 is the identity.  Site s acts on bit n-1-s of i
+ * (row order of generate_hilbert_space).  Replaces _kron_mult / rotate_psi / rotate_rho
+ * (utils/unitaries.py:64-150): rho -> U rho U^dagger is two calls (rotate, conjugate-transpose, rotate). */
+int qcb_kron_rotate(double* re, double* im, int n, int64_t batch, const uint8_t* basis,
+                    const double* unitaries, int K, void* stream);
+
+/* qcb_kl_terms: out2[0] = sum_i p_t log clamp(p_t), out2[1] = sum_i p_t log clamp(p), clamp to
+ * [2^-52, 1 - 2^-52] (_single_basis_KL, utils/training_statistics.py:131-135; KL = out2[0] - out2[1]).
+ * p_t = t_re^2 + t_im^2, or t_re itself when t_im is NULL; p = (p_re^2 + p_im^2) exp(-logZ), or
+ * p_re exp(-logZ) when p_im is NULL.  Workspace: qcb_workspace_bytes(QCB_OP_KL_TERMS, ...). */
+int qcb_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n,
+                 double logZ, double* out2, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Host-buffer convenience (the end-to-end path bench.py times) ---------------------
  * Same as qcb_rbm_gibbs but v_host / params are HOST pointers (pinned for full speed); the

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QCB_LIB_PATH") or os.path.join(_HERE, "libqucumber_b200.so")  # override: kernel experiments only
 
 QCB_OK = 0
-OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP = range(1, 10)
+OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP, OP_KL_TERMS = range(1, 11)
 
 # name -> (restype, argtypes); must list every symbol declared in include/qcb.h
 _P = c_void_p
@@ -42,6 +42,8 @@ SIGNATURES = {
                                  c_uint64, _P, _P]),
     "qcb_rbm_logz_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, _P, _P, c_size_t, _P]),
     "qcb_neg_logsumexp": (c_int, [_P, c_int64, _P, _P, c_size_t, _P]),
+    "qcb_kron_rotate": (c_int, [_P, _P, c_int, c_int64, _P, _P, c_int, _P]),
+    "qcb_kl_terms": (c_int, [_P, _P, _P, _P, c_int64, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_exact_stats_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, c_double, _P, _P,
                                           _P, _P, _P, c_size_t, _P]),
     "qcb_cwf_rotated": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, c_int, _P, _P, _P, _P,

@@ -42,6 +42,11 @@ int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* p
                  int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last,
                  cudaStream_t st);
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
+size_t kl_workspace_bytes();
+int run_kron_rotate(double* re, double* im, int n, int64_t batch, const unsigned char* basis_codes, const double* unitaries, int K,
+                    cudaStream_t st);
+int run_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n, double logZ, double* out2,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
 int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, double scale, double* g, int accumulate,
                     void* ws, size_t ws_bytes, cudaStream_t st);
 int run_exact_grad_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, double* g, void* ws,
@@ -101,6 +106,7 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
       const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b + align_up((size_t)(rows > 0 ? rows : 0) * N * sizeof(double), 256);
     }
+    case QCB_OP_KL_TERMS: return kl_workspace_bytes();
     case QCB_OP_CDK_NEG: {
       const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b;
@@ -251,6 +257,15 @@ int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const 
   if (rc != QCB_OK) return rc;
   if (out2 == nullptr) return fail(QCB_ERR_BAD_ARG, "logz_range: out2 is NULL");
   return run_logz_range(p, first_state, count, out2, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_kron_rotate(double* re, double* im, int n, int64_t batch, const uint8_t* basis, const double* unitaries, int K, void* stream) {
+  return run_kron_rotate(re, im, n, batch, basis, unitaries, K, (cudaStream_t)stream);
+}
+
+int qcb_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n, double logZ,
+                 double* out2, void* ws, size_t ws_bytes, void* stream) {
+  return run_kl_terms(t_re, t_im, p_re, p_im, n, logZ, out2, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, void* stream) {

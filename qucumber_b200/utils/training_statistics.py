@@ -98,7 +98,25 @@ def NLL(nn_state, samples, space=None, sample_bases=None, **kwargs):
 
 
 def _single_basis_KL(target_probs, nn_probs):
+    if target_probs.is_cuda and nn_probs.is_cuda:
+        return _kl_terms(target_probs, None, nn_probs, None, 0.0)
     return torch.sum(target_probs * probs_to_logits(target_probs)) - torch.sum(target_probs * probs_to_logits(nn_probs))
+
+
+def _kl_terms(t_re, t_im, p_re, p_im, logZ):
+    """sum p_t log clamp(p_t) - sum p_t log clamp(p) in one reduction kernel (qcb_kl_terms); p_t and p are
+    given as amplitudes (re, im) or, with im = None, as probabilities; p is scaled by exp(-logZ)."""
+    lib = _lib.load()
+    dev = t_re.device
+    planes = [None if x is None else x.to(device=dev, dtype=torch.double).contiguous() for x in (t_re, t_im, p_re, p_im)]
+    n = planes[0].numel()
+    if planes[2].numel() != n:
+        raise ValueError("target and model distributions differ in size")
+    out2 = torch.empty(2, dtype=torch.double, device=dev)
+    ws = _lib.workspace(dev, lib.qcb_workspace_bytes(_lib.OP_KL_TERMS, 0, 0, 0, n))
+    _lib.check(lib.qcb_kl_terms(*[_lib.ptr(x) for x in planes], n, float(logZ), _lib.ptr(out2), _lib.ptr(ws), ws.numel(),
+                                _lib.stream_ptr(dev)), "qcb_kl_terms")
+    return out2[0] - out2[1]
 
 
 def KL(nn_state, target, space=None, bases=None, **kwargs):
@@ -135,7 +153,7 @@ def KL(nn_state, target, space=None, bases=None, **kwargs):
                 target_psi_r = rotate_psi(nn_state, basis, space, psi=target)
             assert target_psi_r.dim() == 2, "target must be a complex vector!"
             psi_r = rotate_psi(nn_state, basis, space)
-            kl += _single_basis_KL(cplx.absolute_value(target_psi_r) ** 2, (cplx.absolute_value(psi_r) ** 2) / Z)
+            kl += _kl_terms(target_psi_r[0], target_psi_r[1], psi_r[0], psi_r[1], float(torch.log(torch.as_tensor(Z))))
         kl /= float(len(bases))
     else:
         for basis in bases:

@@ -50,14 +50,19 @@ def _kron_apply(us, x):
     """Apply U_0 (x) U_1 (x) ... to the state index of x (2, 2^n, ...) — one contraction per site
     (what the reference's _kron_mult butterfly computes, unitaries.py:64-83)."""
     n = len(us)
-    z = torch.complex(x[0], x[1])
-    tail = z.shape[1:]
-    z = z.reshape((2,) * n + tuple(tail))
-    for site, u in enumerate(us):
-        uc = torch.complex(u[0], u[1]).to(z.device)
-        z = torch.movedim(torch.tensordot(uc, z, dims=([1], [site])), 0, site)
-    z = z.reshape(-1, *tail)
-    return torch.stack([z.real, z.imag])
+    if x.shape[1] != (1 << n):
+        raise ValueError(f"state has {x.shape[1]} rows, expected 2^{n}")
+    _lib.require_cuda(x, "rotate")
+    lib = _lib.load()
+    out = x.to(dtype=torch.double).contiguous().clone()  # (2, 2^n, *tail): re and im planes, rotated in place
+    eye = torch.tensor([[[1.0, 0.0], [0.0, 1.0]], [[0.0, 0.0], [0.0, 0.0]]], dtype=torch.double)
+    mats = [u.detach().to(device="cpu", dtype=torch.double) for u in us]
+    codes = np.array([0 if torch.equal(m, eye) else s + 1 for s, m in enumerate(mats)], dtype=np.uint8)
+    table = torch.stack([eye] + mats).to(out.device).contiguous()
+    batch = out[0].numel() >> n
+    _lib.check(lib.qcb_kron_rotate(_lib.ptr(out[0]), _lib.ptr(out[1]), n, batch, codes.ctypes.data, _lib.ptr(table), n + 1,
+                                   _lib.stream_ptr(out.device)), "qcb_kron_rotate")
+    return out
 
 
 def rotate_psi(nn_state, basis, space, unitaries=None, psi=None):

@@ -545,3 +545,49 @@ def test_finite_difference_gradients_complex_and_density(lib, cuda):
         # the reference's +1e-8 regulariser in 1/(UrhoU + 1e-8) makes its analytic gradient differ from the
         # true derivative at the 1e-8 level (density_matrix.py:296); its own test uses the same tolerance class
         assert float((a - num).abs().max()) < 5e-7, (net, float((a - num).abs().max()))
+
+
+def test_kron_rotate_and_kl_terms_match_numpy(lib, cuda):
+    """qcb_kron_rotate == the dense Kronecker product of the one-site unitaries (utils/unitaries.py:64-115) on a
+    batched planar complex array, identities skipped; qcb_kl_terms == _single_basis_KL with the probs_to_logits
+    clamp, for amplitude and probability inputs."""
+    from qucumber_b200 import _lib
+    from qucumber_b200.utils import training_statistics as ts
+    from qucumber_b200.utils.unitaries import _kron_apply
+
+    rng = np.random.default_rng(77)
+    n, batch = 6, 3
+    us = []
+    for s in range(n):
+        if s in (1, 4):
+            u = np.eye(2, dtype=complex)
+        else:
+            q, _ = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))
+            u = q
+        us.append(u)
+    full = np.array([[1.0 + 0j]])
+    for u in us:
+        full = np.kron(full, u)
+    x = rng.standard_normal((1 << n, batch)) + 1j * rng.standard_normal((1 << n, batch))
+    want = full @ x
+    ut = [torch.tensor(np.stack([u.real, u.imag])) for u in us]
+    xt = torch.tensor(np.stack([x.real, x.imag]), device=cuda)
+    got = _kron_apply(ut, xt)
+    assert_close(got[0], want.real, what="kron rotate (re)")
+    assert_close(got[1], want.imag, what="kron rotate (im)")
+    assert torch.equal(xt, torch.tensor(np.stack([x.real, x.imag]), device=cuda))  # input untouched
+
+    m = 1 << 12
+    t = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    t /= np.linalg.norm(t)
+    t[:5] = 0.0  # zero target probability: clamp path
+    psi = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    logZ = np.log(np.sum(np.abs(psi) ** 2))
+    eps = 2.0 ** -52
+    pt, p = np.abs(t) ** 2, np.abs(psi) ** 2 / np.exp(logZ)
+    want_kl = np.sum(pt * np.log(np.clip(pt, eps, 1 - eps))) - np.sum(pt * np.log(np.clip(p, eps, 1 - eps)))
+    tt = [torch.tensor(a, device=cuda) for a in (t.real, t.imag, psi.real, psi.imag)]
+    assert_close(ts._kl_terms(tt[0], tt[1], tt[2], tt[3], logZ), want_kl, what="KL from amplitudes")
+    assert_close(ts._single_basis_KL(torch.tensor(pt, device=cuda), torch.tensor(p, device=cuda)), want_kl, what="KL from probabilities")
+    rc = lib.qcb_kl_terms(None, None, None, None, 4, 0.0, None, None, 0, None)
+    assert rc != 0 and b"kl_terms" in lib.qcb_last_error()
