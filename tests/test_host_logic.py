@@ -85,17 +85,16 @@ def test_host_helpers(tmp_path):
     assert np.allclose(cplx.numpy(cplx.inner_prod(a, b)), np.vdot(cplx.numpy(a), cplx.numpy(b)))
     assert np.allclose(cplx.numpy(cplx.inverse(a)), 1 / cplx.numpy(a))
     assert np.allclose(cplx.numpy(cplx.einsum("i,i->", a, b)), np.sum(cplx.numpy(a) * cplx.numpy(b)))
-    # full-space rotation == explicit Kronecker product
+    # the full-space rotation is a CUDA kernel (qcb_kron_rotate; parity in tests/test_states_gpu.py): no CPU path
     rng = np.random.default_rng(0)
     psi = rng.standard_normal(8) + 1j * rng.standard_normal(8)
-    U = np.kron(np.kron(default_unitaries()["X"], default_unitaries()["Z"]), default_unitaries()["Y"])
 
     class S:
         unitary_dict = d
         device = torch.device("cpu")
 
-    got = cplx.numpy(unitaries.rotate_psi(S(), "XZY", None, psi=cplx.make_complex(psi)))
-    assert np.allclose(got, U @ psi, atol=1e-14)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        unitaries.rotate_psi(S(), "XZY", None, psi=cplx.make_complex(psi))
     samples = tmp_path / "s.txt"
     samples.write_text("1 0\n0 1\n1 1\n")
     bases = tmp_path / "b.txt"
