@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   int s = 0;
   if (s_maxw > 0.0 && s_maxw < 1e300) s = 21 - ilogb(s_maxw);  // |Wq| <= 2^22
   if (s > 60) s = 60;
+  // weights beyond 2^81 (or non-finite) do not fit the fixed-point image: the digits are zeroed and the margins
+  // set to 4, which makes every unit undecided, i.e. the kernel degenerates to its exact FP64 path
+  const bool degenerate = !(s_maxw < 1e300) || s < -60;
   if (s < -60) s = -60;
-  const double scale = ldexp(1.0, s);
+  const double scale = degenerate ? 0.0 : ldexp(1.0, s);
   ImmaHeader* hd = reinterpret_cast<ImmaHeader*>(img);
   if (threadIdx.x == 0) {
     hd->inv_scale = (float)(-1.4426950408889634 * ldexp(1.0, -s));
@@ -121,8 +124,9 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
     hd->dx_h = (float)dxh;
     hd->dx_v = (float)dxv;
     // round the margins up a little: they are compared in float
-    hd->margin_h = (float)((dxh * 0.25 + ldexp(1.0, -19)) * 1.0001);
-    hd->margin_v = (float)((dxv * 0.25 + ldexp(1.0, -19)) * 1.0001);
+    const double mh = (dxh * 0.25 + ldexp(1.0, -19)) * 1.0001, mv = (dxv * 0.25 + ldexp(1.0, -19)) * 1.0001;
+    hd->margin_h = (degenerate || !(mh < 4.0)) ? 4.0f : (float)mh;  // a margin >= 1 leaves every unit undecided
+    hd->margin_v = (degenerate || !(mv < 4.0)) ? 4.0f : (float)mv;
     hd->pad[0] = hd->pad[1] = 0;
   }
   const int KKv = imma_kk(Npad), NBh = Hpad / 8, KKh = imma_kk(Hpad), NBv = Npad / 8;
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
     for (int i = 0; i < 4; ++i) {
       const int inu = 32 * kk + 16 * half + 4 * t + i;
       const int hid = hside ? outu : inu, vis = hside ? inu : outu;
-      if (hid < H && vis < N) {
+      if (!degenerate && hid < H && vis < N) {
         long long wq = llrint(Ws[hid * GI_PACK_LD + vis] * scale);
         const int q0 = (int)(((wq + 128) & 255) - 128);
         wq = (wq - q0) >> 8;
@@ -286,11 +290,12 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
   // With q = 1 + e^{-x}:  u < 1/q  <=>  u q < 1.  u lies in the cell [uf, uf + 2^-16), uf = m - 1.
   // The two tests are sign tests of one FMA each (its sign is exact); the sign bits are shifted straight into
   // the result masks, so units are visited from the highest index down.
-  const float c1 = (0x1.0p-16f + margin) - 1.0f;   // (m + c1) q - 1 <  0  =>  certainly u < p
-  const float c01 = -(0x1.0p-16f + 2.0f * margin);  // (m + c1 + c01) q - 1 >= 0  =>  certainly u >= p  (m + c1 + c01 = u_f - margin)
+  // A verdict is a SET sign bit, so a NaN (q = inf when x~ < -88: inf - inf) or a margin >= 1 reads as "undecided".
+  const float c1 = (0x1.0p-16f + margin) - 1.0f;  // s1 = (m + c1) q - 1 < 0            =>  certainly u < p
+  const float d01 = 0x1.0p-16f + 2.0f * margin;   // s0 = d01 q - s1 = 1 - (u_f - margin) q < 0  =>  certainly u >= p
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    uint32_t acc1 = 0u, acc0 = 0u;  // bit 4 gq + w: "certainly 1" / "not certainly 0"
+    uint32_t acc1 = 0u, acc0 = 0u;  // bit 4 gq + w: "certainly 1" / "certainly 0"
     float xs[DBG ? 4 * OB : 1];
 #pragma unroll
     for (int pq = (OB + 1) / 2 - 1; pq >= 0; --pq) {
@@ -309,7 +314,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
             // m = 1 + u_f: the 16-bit cell of u in the top mantissa bits, (0x7F0000 | h16) << 7
             const float m = __uint_as_float(__byte_perm(rnd[w], 0x7Fu, half ? 0x5410u : 0x5432u) << 7);
             const float s1 = fmaf(m + c1, q, -1.0f);
-            const float s0 = fmaf(c01, q, s1);  // re-rounding s1 costs 2^-23 in p, inside the 2^-19 allowance
+            const float s0 = fmaf(d01, q, -s1);  // re-rounding s1 costs 2^-23 in p, inside the 2^-19 allowance
             acc1 = __funnelshift_l(__float_as_uint(s1), acc1, 1);
             acc0 = __funnelshift_l(__float_as_uint(s0), acc0, 1);
           }
@@ -317,7 +322,7 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
       }
     }
     uint32_t nibw = acc1 & valid_mask;
-    const uint32_t slowmask = (acc0 ^ acc1) & valid_mask;  // certainly-1 implies not-certainly-0
+    const uint32_t slowmask = ~(acc0 | acc1) & valid_mask;  // the two verdicts exclude each other
     if (__any_sync(0xffffffffu, slowmask != 0u))
       nibw = fixup_slow_imma(args, hidden_out, min[r][0], KK > 1 ? min[r][KK - 1] : 0u, nibw, slowmask, cid[r][0], cid[r][1], sweep,
                              q0, lane, DBG ? xs : nullptr, dx);

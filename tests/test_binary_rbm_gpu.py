@@ -402,3 +402,35 @@ def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
         ratio, count = stats[0].item() / 2 ** 20, stats[1].item()
         assert count > 0 and ratio < 0.5, (n, nh, ratio, count)          # observed error well inside the bound
         assert count < 2e-3 * C * 3 * (n + nh), (n, nh, count)            # and the cold path stays rare
+
+
+@pytest.mark.parametrize("case", ["saturated", "huge", "tiny", "mixed_scales", "zero"])
+def test_integer_filter_kernel_extreme_parameters(lib, cuda, case):
+    """Regimes where the fixed-point filter cannot decide (pre-activations beyond +-88, weights beyond the
+    24-bit window, margins >= 1) must fall through to the exact path: same samples as the FP64 kernel."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, C = 24, 40, 4096
+    W, b, c = make_binary_params(n, nh, 171, bias_scale=0.5)
+    if case == "saturated":
+        W *= 40.0            # |x| up to several hundred: e^{-x} overflows float
+        c[::3] -= 150.0
+        b[::4] += 120.0
+    elif case == "huge":
+        W *= 1e30            # does not fit the fixed-point image at all
+    elif case == "tiny":
+        W *= 1e-30
+    elif case == "mixed_scales":
+        W[0, :] *= 1e6       # one row dominates the scale: the others quantise to (almost) nothing
+    elif case == "zero":
+        W[:] = 0.0
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    v0 = (torch.rand(C, n, generator=g, device=cuda) < 0.5).double()
+    try:
+        _lib.check(lib.qcb_set_gibbs_mode(1), "mode")
+        ref = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
+    finally:
+        _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
+    got = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
+    assert torch.equal(got, ref), case
