@@ -26,6 +26,10 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
   constexpr int KN4 = 2 * NB8;            // k-steps of phase 1
   constexpr int LDV = Npad + 4, LDP = Hpad + 4;
   constexpr int MB = (HB8 + GD_WARPS - 1) / GD_WARPS;  // G row blocks per warp
+  // Narrow hidden layers (HB8 < 8) would leave warps idle in phase 2: KG groups of HB8 warps then split the 64 rows
+  // of a tile between them and their partial sums are combined in shared memory at the end.
+  constexpr int KG = HB8 < GD_WARPS ? ((GD_WARPS / HB8) >= 4 ? 4 : (GD_WARPS / HB8 >= 2 ? 2 : 1)) : 1;
+  constexpr int VPW = KG > 1 ? (NB8 + HB8 - 1) / HB8 : (NB8 + GD_WARPS - 1) / GD_WARPS;  // bias-sum columns per warp
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Wf = reinterpret_cast<double*>(smem_raw);     // [KN4][HB8][32] B fragments of phase 1
   double* hb = Wf + (size_t)KN4 * HB8 * 32;             // [Hpad]
@@ -46,12 +50,17 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
     Wf[idx] = (hid < Hc && vis < N) ? s.mop(hid, vis) : 0.0;
   }
   for (int i = threadIdx.x; i < Hpad; i += GD_THREADS) hb[i] = i < Hc ? s.bias(i) : 0.0;
+  __shared__ int8_t spos[128];
+  if (threadIdx.x < 128) spos[threadIdx.x] = mode == ROWS_EXPANDED ? src.ex.sitepos[threadIdx.x] : (int8_t)-1;
   for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
   for (int i = threadIdx.x; i < GD_TR * LDP; i += GD_THREADS) Pt[i] = 0.0;
   __syncthreads();
 
   double G[MB][NB8][2];
-  double hsum[MB], vsum[(NB8 + GD_WARPS - 1) / GD_WARPS];
+  double hsum[MB], vsum[VPW];
+  const int kgroup = KG > 1 ? warp / HB8 : 0, wing = KG > 1 ? warp % HB8 : warp;  // k-group and position inside it
+  const bool p2_active = KG > 1 ? kgroup < KG : true;
+  const int vstride = KG > 1 ? HB8 : GD_WARPS;
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     hsum[m] = 0.0;
@@ -59,18 +68,34 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
     for (int nb = 0; nb < NB8; ++nb) { G[m][nb][0] = 0.0; G[m][nb][1] = 0.0; }
   }
 #pragma unroll
-  for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) vsum[i] = 0.0;
+  for (int i = 0; i < VPW; ++i) vsum[i] = 0.0;
 
+  const int fill_r0 = threadIdx.x / N, fill_j0 = threadIdx.x - fill_r0 * N;
+  const int fill_dr = GD_THREADS / N, fill_dj = GD_THREADS - fill_dr * N;
   const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * GD_TR;
     // ---- fill the V tile, the row weights and the aux columns of the P tile
-    for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
-      const int rr = idx / N, j = idx - rr * N;
-      const int64_t r = r0 + rr;
-      double val = 0.0;
-      if (r < rows) val = mode == ROWS_EXPANDED ? src.ex.value(r, j) : src.v[r * N + j];
-      Vt[rr * LDV + j] = val;
+    // element idx = rr * N + j of the tile, stepped without divisions; the rotated-site table comes from shared memory
+    {
+      int rr = fill_r0, j = fill_j0;
+      for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
+        const int64_t r = r0 + rr;
+        double val = 0.0;
+        if (r < rows) {
+          if (mode == ROWS_EXPANDED) {
+            const int tpos = (int)spos[j];
+            val = tpos < 0 ? src.ex.samples[(r >> src.ex.S) * N + j]
+                           : ((((uint32_t)r & ((1u << src.ex.S) - 1u)) >> (src.ex.S - 1 - tpos)) & 1u ? 1.0 : 0.0);
+          } else {
+            val = src.v[r * N + j];
+          }
+        }
+        Vt[rr * LDV + j] = val;
+        rr += fill_dr;
+        j += fill_dj;
+        if (j >= N) { j -= N; ++rr; }
+      }
     }
     for (int rr = threadIdx.x; rr < GD_TR; rr += GD_THREADS) {
       const int64_t r = r0 + rr;
@@ -113,8 +138,11 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
     __syncthreads();
 
     // ---- phase 2: G += P^T V for this warp's row blocks of G; column sums for the bias gradients
+    constexpr int KPG = (GD_TR / 4) / KG;  // k-steps per group
 #pragma unroll 2
-    for (int kk = 0; kk < GD_TR / 4; ++kk) {
+    for (int kq = 0; kq < KPG; ++kq) {
+      if (!p2_active) break;
+      const int kk = kgroup * KPG + kq;
       const double* vrow = Vt + (4 * kk + t) * LDV + g;
       const double* prow = Pt + (4 * kk + t) * LDP + g;
       double b[NB8];
@@ -122,13 +150,13 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
       for (int nb = 0; nb < NB8; ++nb) b[nb] = vrow[8 * nb];
       const double wk = wts[4 * kk + t];
 #pragma unroll
-      for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) {
-        const int nb = warp + GD_WARPS * i;
+      for (int i = 0; i < VPW; ++i) {
+        const int nb = wing + vstride * i;
         if (nb < NB8) vsum[i] = fma(wk, vrow[8 * nb], vsum[i]);
       }
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
-        const int mb = warp + GD_WARPS * m;
+        const int mb = wing + GD_WARPS * m;
         if (mb < HB8) {
           const double a = prow[8 * mb];
           hsum[m] += a;
@@ -141,11 +169,17 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
   }
 
   // ---- write this CTA's partial in flat order [Wst (H x N) | vb (N) | hb (H)]
-  double* out = partials + (size_t)blockIdx.x * ((size_t)H * N + N + H);
+  const size_t Gflat = (size_t)H * N + N + H;
+  double* cta_out = partials + (size_t)blockIdx.x * Gflat;
+  double* out = cta_out;
+  if (KG > 1) {  // each k-group first writes its sums to shared memory (the tiles are no longer needed)
+    __syncthreads();
+    out = Vt + (size_t)kgroup * Gflat;
+  }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
-    const int mb = warp + GD_WARPS * m;
-    if (mb < HB8) {
+    const int mb = wing + GD_WARPS * m;
+    if (p2_active && mb < HB8) {
       const int hid = 8 * mb + g;
 #pragma unroll
       for (int nb = 0; nb < NB8; ++nb)
@@ -161,18 +195,27 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
     }
   }
 #pragma unroll
-  for (int i = 0; i < (NB8 + GD_WARPS - 1) / GD_WARPS; ++i) {
-    const int nb = warp + GD_WARPS * i;
+  for (int i = 0; i < VPW; ++i) {
+    const int nb = wing + vstride * i;
     double vs = vsum[i];
     vs += __shfl_xor_sync(0xffffffffu, vs, 1);
     vs += __shfl_xor_sync(0xffffffffu, vs, 2);
     const int vis = 8 * nb + g;
-    if (nb < NB8 && t == 0 && vis < N) out[(size_t)H * N + vis] = vs;
+    if (p2_active && nb < NB8 && t == 0 && vis < N) out[(size_t)H * N + vis] = vs;
+  }
+  if (KG > 1) {  // groups summed in a fixed order
+    __syncthreads();
+    for (size_t idx = threadIdx.x; idx < Gflat; idx += GD_THREADS) {
+      double tsum = Vt[idx];
+      for (int kg = 1; kg < KG; ++kg) tsum += Vt[(size_t)kg * Gflat + idx];
+      cta_out[idx] = tsum;
+    }
   }
 }
 
 static int pick8(int units) {
   if (units <= 16) return 2;
+  if (units <= 24) return 3;
   if (units <= 32) return 4;
   if (units <= 64) return 8;
   if (units <= 128) return 16;
@@ -206,10 +249,11 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
   int rc = QCB_OK;
 #define QCB_GD_CASE(NB, HBx) \
   if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx>(s, src, mode, rows, partials, grid, st); else
-  QCB_GD_CASE(2, 2) QCB_GD_CASE(2, 4) QCB_GD_CASE(2, 8) QCB_GD_CASE(2, 16)
-  QCB_GD_CASE(4, 2) QCB_GD_CASE(4, 4) QCB_GD_CASE(4, 8) QCB_GD_CASE(4, 16)
-  QCB_GD_CASE(8, 2) QCB_GD_CASE(8, 4) QCB_GD_CASE(8, 8) QCB_GD_CASE(8, 16)
-  QCB_GD_CASE(16, 2) QCB_GD_CASE(16, 4) QCB_GD_CASE(16, 8)
+  QCB_GD_CASE(2, 2) QCB_GD_CASE(2, 3) QCB_GD_CASE(2, 4) QCB_GD_CASE(2, 8) QCB_GD_CASE(2, 16)
+  QCB_GD_CASE(3, 2) QCB_GD_CASE(3, 3) QCB_GD_CASE(3, 4) QCB_GD_CASE(3, 8) QCB_GD_CASE(3, 16)
+  QCB_GD_CASE(4, 2) QCB_GD_CASE(4, 3) QCB_GD_CASE(4, 4) QCB_GD_CASE(4, 8) QCB_GD_CASE(4, 16)
+  QCB_GD_CASE(8, 2) QCB_GD_CASE(8, 3) QCB_GD_CASE(8, 4) QCB_GD_CASE(8, 8) QCB_GD_CASE(8, 16)
+  QCB_GD_CASE(16, 2) QCB_GD_CASE(16, 3) QCB_GD_CASE(16, 4) QCB_GD_CASE(16, 8)
   return QCB_OK;  // (16, 16) does not fit: FMA kernel
 #undef QCB_GD_CASE
   if (rc == QCB_OK) *grid_out = grid;
