@@ -373,7 +373,6 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
     const int64_t per = ((C + nslices - 1) / nslices + 15) / 16 * 16;
     QCB_CUDA(cudaEventRecord(ev_params, st));
     QCB_CUDA(cudaStreamWaitEvent(s_in, ev_params, 0));
-    int used = 0;
     for (int i = 0; i < nslices; ++i) {
       const int64_t c0 = (int64_t)i * per;
       if (c0 >= C) break;
@@ -387,9 +386,7 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
       QCB_CUDA(cudaEventRecord(ev_k[i], st));
       QCB_CUDA(cudaStreamWaitEvent(s_out, ev_k[i], 0));
       QCB_CUDA(cudaMemcpyAsync(v_host + off, dv + off, nb, cudaMemcpyDeviceToHost, s_out));
-      used = i + 1;
     }
-    (void)used;
     QCB_CUDA(cudaEventRecord(ev_done, s_out));
     QCB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
   }

@@ -542,14 +542,6 @@ static int setup_enum(const StackedParams& p, uint64_t first, uint64_t count, En
   return QCB_OK;
 }
 
-#define QCB_ENUM_DISPATCH(MODE, a, partials, gridp, st)                        \
-  switch (pick_nht((a).p.nhid())) {                                            \
-    case 8: rc = launch_enum<8, MODE>(a, partials, gridp, st); break;          \
-    case 16: rc = launch_enum<16, MODE>(a, partials, gridp, st); break;        \
-    case 32: rc = launch_enum<32, MODE>(a, partials, gridp, st); break;        \
-    default: rc = launch_enum<64, MODE>(a, partials, gridp, st); break;        \
-  }
-
 int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
                    cudaStream_t st) {
   EnumArgs a;
