@@ -449,6 +449,44 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- the two sharded paths that DO have a collective (N > 1 only): exact log Z over index ranges (all-gather of
+    # (max, sum) pairs) and the CD-10 gradient with chains and data sharded (one all-reduce of 4 224 doubles)
+    sharded = None
+    if world > 1:
+        from qucumber_b200 import PositiveWaveFunction
+        from qucumber_b200 import distributed as qdist
+
+        def timed_collective(fn, reps=3):
+            fn()
+            best = 1e30
+            for _ in range(reps):
+                barrier()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                out_ = fn()
+                s1.record()
+                torch.cuda.synchronize(dev)
+                best = min(best, max_over_ranks(s0.elapsed_time(s1)))
+            return best, out_
+
+        nz = 32
+        gz = torch.Generator().manual_seed(1234)
+        rz = BinaryRBM(nz, nz, gpu=True)
+        with torch.no_grad():
+            rz.weights.copy_(torch.randn(nz, nz, dtype=torch.double, generator=gz) / np.sqrt(nz))
+        ms_z, logz = timed_collective(lambda: qdist.sharded_log_partition(rz))
+        st = PositiveWaveFunction(N_VIS, N_HID, gpu=True)
+        with torch.no_grad():
+            st.rbm_am.weights.copy_(W)
+            st.rbm_am.visible_bias.copy_(b)
+            st.rbm_am.hidden_bias.copy_(c)
+        ms_cd, _ = timed_collective(lambda: qdist.sharded_cd_gradients(st, 10, v, v, world * C, world * C, args.seed, chain0))
+        sharded = {"exact_z": {"N": nz, "ms": ms_z, "states_per_s": (1 << nz) / (ms_z * 1e-3), "logZ": float(logz),
+                               "collective": "all_gather of one (max, sum) pair per rank"},
+                   "cd10_step": {"ms": ms_cd, "global_pos": world * C, "global_chains": world * C,
+                                 "chain_sweeps_per_s": world * C * 10 / (ms_cd * 1e-3),
+                                 "collective": "all_reduce(sum) of 4224 float64"}}
+
     # ---- end to end through the C ABI with host buffers ("e2e") ----
     scratch_bytes = lib.qcb_gibbs_host_scratch_bytes(N_VIS, N_HID, 0, C)
     scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
@@ -519,6 +557,8 @@ def run_ours(args):
                                     "sample": f"{args.ref_chains} chains x k={k} sweeps, best of 3 ({min(cpu_times):.2f} s), "
                                               "reference torch-CPU operator sequence (oracle/cpu_path.py)"}
             line["extra"] = extra_metrics(dev, _lib)
+        if sharded is not None:
+            line["sharded"] = sharded
         emit(line)
     if world > 1:
         dist.destroy_process_group()
