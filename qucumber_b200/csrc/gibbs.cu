@@ -277,10 +277,11 @@ __global__ void __launch_bounds__(GIBBS_THREADS) gibbs_kernel(const GibbsArgs a)
   const double2* Iv = reinterpret_cast<const double2*>(smem + nI);
   const double* biasH = smem + 2 * nI;
   const double* biasV = biasH + Hpad;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * nI + Hpad + Npad);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * nI + Hpad + Npad);  // [0]: image, [1 + warp]: that warp's state tile
+  double* tiles = reinterpret_cast<double*>(smem_raw + align_up((size_t)(2 * nI + Hpad + Npad) * 8 + 8 * (1 + GIBBS_WARPS), 128));
 
   // Stage the packed parameters with one TMA bulk copy per <=32 KB chunk.
-  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  if (threadIdx.x < 1 + GIBBS_WARPS) mbar_init(mbar + threadIdx.x, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(mbar, a.image_bytes);
@@ -298,35 +299,66 @@ __global__ void __launch_bounds__(GIBBS_THREADS) gibbs_kernel(const GibbsArgs a)
   constexpr int MV = (VB + 1) / 2, MH = (HB + 1) / 2;
   const int nunits = a.nhid + a.N;
   const uint32_t qv0 = (uint32_t)(4 * ((a.nhid + 31) / 32));  // first Philox call of the visible layer
-  const unsigned long long* vbits = reinterpret_cast<const unsigned long long*>(a.v_in);
+
+  // A group's 8 chain rows are one contiguous span of v_in: the warp's tile is fetched by one TMA bulk copy issued
+  // a whole group ahead (while the previous group is being swept), so its latency never shows.
+  double* tile = tiles + (size_t)warp * (CHAINS_PER_WARP * Npad);
+  uint64_t* tbar = mbar + 1 + warp;
+  uint32_t tphase = 0u;
+  const bool bulk_base_ok = (reinterpret_cast<uintptr_t>(a.v_in) & 15u) == 0u;
+  auto tile_doubles = [&](int64_t gi) -> uint32_t {
+    const int64_t left = a.C - gi * CHAINS_PER_WARP;
+    return left <= 0 ? 0u : (uint32_t)(left < CHAINS_PER_WARP ? left : CHAINS_PER_WARP) * (uint32_t)a.N;
+  };
+  auto bulk_fetch = [&](int64_t gi) {  // true when the copy was handed to the TMA unit
+    const uint32_t bytes = tile_doubles(gi) * 8u;
+    if (bytes == 0u || !bulk_base_ok || (bytes & 15u) != 0u) return false;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile vs. the async write
+      mbar_expect_tx(tbar, bytes);
+      tma_bulk_g2s(tile, a.v_in + gi * CHAINS_PER_WARP * (int64_t)a.N, bytes, tbar);
+    }
+    return true;
+  };
 
   // every warp runs the same number of iterations (groups past the end are dummies) so that the
   // ping-pong partners stay in lock step; role-1 warps let their partners start first
   if (warp >> 2) pipe_release(warp);
   const int64_t stride = (int64_t)gridDim.x * GIBBS_WARPS;
   const int64_t iters = (a.num_groups + stride - 1) / stride;
+  bool fetched = iters > 0 && bulk_fetch((int64_t)blockIdx.x * GIBBS_WARPS + warp);
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t gi = it * stride + (int64_t)blockIdx.x * GIBBS_WARPS + warp;
     const int64_t chain_base = gi * CHAINS_PER_WARP;
     const int64_t my_chain = chain_base + g;
     const bool my_valid = my_chain < a.C;
 
-    // v0 -> bit masks (coalesced row reads + ballot)
+    // v0 tile (shared memory) -> bit masks
+    const uint32_t ndbl = tile_doubles(gi);
+    const int nch = (int)(ndbl / (uint32_t)a.N);
+    if (fetched) {
+      mbar_wait(tbar, tphase);
+      tphase ^= 1u;
+    } else if (ndbl != 0u) {  // unaligned view or odd tile size: plain copy
+      for (uint32_t idx = lane; idx < ndbl; idx += 32) tile[idx] = a.v_in[chain_base * a.N + idx];
+      __syncwarp();
+    }
     uint32_t mv[MV], mh[MH];
 #pragma unroll
     for (int w = 0; w < MV; ++w) mv[w] = 0u;
 #pragma unroll
     for (int cc = 0; cc < CHAINS_PER_WARP; ++cc) {
-      const int64_t ch = chain_base + cc;
 #pragma unroll
       for (int w = 0; w < MV; ++w) {
         const int j = w * 32 + lane;
         unsigned long long bits = 0ull;  // integer image of the double: the != 0 test stays off the FP64 pipe
-        if (ch < a.C && j < a.N) bits = vbits[ch * a.N + j];
+        if (cc < nch && j < a.N) bits = reinterpret_cast<const unsigned long long*>(tile)[cc * a.N + j];
         const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
         if (g == cc) mv[w] = bal;
       }
     }
+    __syncwarp();
+    fetched = it + 1 < iters && bulk_fetch(gi + stride);
 
     RngCtx rc;
     const uint64_t cid = a.chain_id0 + (uint64_t)my_chain;
@@ -381,7 +413,9 @@ size_t gibbs_workspace_bytes(int N, int nhid) {
 
 template <int HB, int VB>
 static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
-  const size_t smem = gibbs_image_doubles(HB, VB) * sizeof(double) + 16;
+  // image + mbarriers + one 8-chain state tile per warp
+  const size_t smem = align_up(gibbs_image_doubles(HB, VB) * sizeof(double) + 8 * (1 + GIBBS_WARPS), 128) +
+                      (size_t)GIBBS_WARPS * CHAINS_PER_WARP * 16 * VB * sizeof(double);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
