@@ -202,6 +202,30 @@ def extra_metrics(dev, lib_mod):
     except Exception as exc:  # pragma: no cover - reported, not hidden
         out["exact_z"] = {"error": str(exc)}
 
+    # ---- exact fidelity + KL against an explicit target over the full space (config 5), N = nh = 28: 2^28 states,
+    # 4.3 GB of target amplitudes read once
+    try:
+        from qucumber_b200.utils import training_statistics as ts
+
+        n = 28
+        torch.manual_seed(1234)
+        nn28 = PositiveWaveFunction(n, n, gpu=True)
+        gt = torch.Generator(device="cuda").manual_seed(5)
+        target = torch.zeros(2, 1 << n, dtype=torch.double, device=dev)
+        target[0].copy_(torch.rand(1 << n, dtype=torch.double, device=dev, generator=gt))
+        target /= target[0].norm()
+        ms_z, _ = timed(lambda: nn28.rbm_am.log_partition())
+        ms_all, res = timed(lambda: ts._positive_stats(nn28, target))
+        o8 = res[1].cpu()
+        out["exact_fidelity_kl"] = {"N": n, "nh": n, "ms_logz_plus_stats": ms_all, "ms_logz": ms_z,
+                                    "states_per_s_stats_pass": (1 << n) / ((ms_all - ms_z) * 1e-3),
+                                    "target_bytes": 16 * (1 << n), "target_gbps": 16 * (1 << n) / ((ms_all - ms_z) * 1e-3) / 1e9,
+                                    "fidelity": float(o8[0] ** 2 + o8[1] ** 2), "KL": float(o8[2] - o8[3]), "sum_p": float(o8[4])}
+        del target, nn28
+        torch.cuda.empty_cache()
+    except Exception as exc:  # pragma: no cover
+        out["exact_fidelity_kl"] = {"error": str(exc)}
+
     # ---- epoch time TFIM N=10 (metric 3): Tutorial-1 data, pos 100 / neg 200, CD-10, SGD lr 0.01, no callbacks
     try:
         gpath = os.path.join(ROOT, "tests", "golden", "binary_rbm_tfim10.npz")
