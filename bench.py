@@ -383,6 +383,43 @@ def extra_metrics(dev, lib_mod):
                                        "cpu_note": f"numpy oracle restatement on {Bc} samples (the reference itself measured 0.9-2.9e5/s, SURVEY.md)"}
     except Exception as exc:  # pragma: no cover
         out["cwf_rotated_gradient"] = {"error": str(exc)}
+
+    # ---- the sweeps SURVEY 8(d) names: exact Z over N, rotated gradients over S, one DensityMatrix shape
+    try:
+        sweep = {}
+        for n in (20, 24, 26, 28, 30):
+            gz = torch.Generator().manual_seed(1234)
+            rz = BinaryRBM(n, n, gpu=True)
+            with torch.no_grad():
+                rz.weights.copy_(torch.randn(n, n, dtype=torch.double, generator=gz) / np.sqrt(n))
+            ms_n, o2 = timed(lambda: rz.log_partition())
+            sweep[str(n)] = {"ms": ms_n, "states_per_s": (1 << n) / (ms_n * 1e-3), "logZ": float(o2[0] + o2[1].log())}
+        out["exact_z_sweep"] = sweep
+    except Exception as exc:  # pragma: no cover
+        out["exact_z_sweep"] = {"error": str(exc)}
+    try:
+        from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+        n, B = 20, 4096
+        rng = np.random.default_rng(7)
+        cw = ComplexWaveFunction(n, n, gpu=True)
+        samples = torch.tensor((rng.random((B, n)) < 0.5).astype(np.float64), device=dev)
+        sw = {}
+        for S in (1, 2, 4, 8, 10):
+            sites = np.sort(rng.choice(n, S, replace=False))
+            basis = np.array(["Z"] * n)
+            basis[sites] = rng.choice(["X", "Y"], S)
+            ms_s, _ = timed(lambda: cw.rotated_gradient(basis, samples))
+            sw[str(S)] = {"ms": ms_s, "expanded_states_per_s": B * (1 << S) / (ms_s * 1e-3)}
+        out["cwf_rotated_gradient_sweep"] = {"N": n, "nh": n, "B": B, "by_S": sw}
+        dm = DensityMatrix(6, 6, 6, gpu=True)
+        s6 = torch.tensor((rng.random((B, 6)) < 0.5).astype(np.float64), device=dev)
+        basis6 = np.array(list("XYZXZZ"))
+        ms_d, _ = timed(lambda: dm.rotated_gradient(basis6, s6))
+        out["dm_rotated_gradient"] = {"N": 6, "nh": 6, "na": 6, "S": 3, "B": B, "ms": ms_d,
+                                      "expanded_pairs_per_s": B * (1 << 6) / (ms_d * 1e-3)}
+    except Exception as exc:  # pragma: no cover
+        out["cwf_rotated_gradient_sweep"] = {"error": str(exc)}
     return out
 
 

@@ -439,12 +439,27 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const Enu
   }
 }
 
-__global__ void lse_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  LSE t{-INFINITY, 0.0};
-  for (int i = 0; i < n; ++i) t = lse_merge(t, LSE{partials[2 * i], partials[2 * i + 1]});
-  out2[0] = t.m;
-  out2[1] = t.s;
+// One block of 256 threads; strided partials per thread, then warps, then the block — a fixed order.
+__global__ void __launch_bounds__(256) lse_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
+  __shared__ double red[16];
+  LSE acc{-INFINITY, 0.0};
+  for (int i = threadIdx.x; i < n; i += 256) acc = lse_merge(acc, LSE{partials[2 * i], partials[2 * i + 1]});
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    LSE other;
+    other.m = __shfl_xor_sync(0xffffffffu, acc.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+    acc = lse_merge(acc, other);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[2 * warp] = acc.m; red[2 * warp + 1] = acc.s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LSE t{red[0], red[1]};
+    for (int w = 1; w < 8; ++w) t = lse_merge(t, LSE{red[2 * w], red[2 * w + 1]});
+    out2[0] = t.m;
+    out2[1] = t.s;
+  }
 }
 
 __global__ void sums_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out8) {
@@ -577,7 +592,7 @@ int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, doubl
     }
     if (rc != QCB_OK) return rc;
   }
-  lse_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out2);
+  lse_combine_kernel<<<1, 256, 0, st>>>(partials, grid, out2);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
@@ -592,7 +607,7 @@ int run_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t
     neg_lse_kernel<<<grid, 256, 0, st>>>(E, n, partials);
     QCB_LAUNCH_CHECK();
   }
-  lse_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out2);
+  lse_combine_kernel<<<1, 256, 0, st>>>(partials, grid, out2);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
