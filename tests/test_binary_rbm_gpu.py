@@ -434,3 +434,33 @@ def test_integer_filter_kernel_extreme_parameters(lib, cuda, case):
         _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
     got = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
     assert torch.equal(got, ref), case
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,nh,C", [(7, 5, 37), (33, 20, 50), (64, 64, 19), (10, 10, 1)])
+def test_gibbs_ragged_and_unaligned_state_tiles(lib, cuda, mode, n, nh, C):
+    """State tiles reach the kernels by TMA bulk copies when the span is 16-byte aligned and a multiple of 16 bytes;
+    odd N, a ragged last group and an 8-byte-misaligned view must take the plain-copy path and give the same
+    samples as the oracle, in place and out of place, for both Gibbs kernels."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    W, b, c = make_binary_params(n, nh, 181 + n)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    v0 = random_states(C, n, 182)
+    want = o.gibbs_steps_philox(3, v0, seed=4321, chain_id0=5, sweep0=2)
+    backing = torch.zeros(C * n + 1, dtype=torch.double, device=cuda)
+    view = backing[1:].view(C, n)          # contiguous, data pointer 8 bytes off a 16-byte boundary
+    view.copy_(torch.tensor(v0, device=cuda))
+    assert view.data_ptr() % 16 == 8
+    try:
+        _lib.check(lib.qcb_set_gibbs_mode(mode), "mode")
+        out = rbm.gibbs_steps(3, view, seed=4321, chain_id0=5, sweep0=2)
+        assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(view.cpu().numpy(), v0)
+        rbm.gibbs_steps(3, view, overwrite=True, seed=4321, chain_id0=5, sweep0=2)
+        assert np.array_equal(view.cpu().numpy(), want)
+        aligned = torch.tensor(v0, device=cuda)
+        assert np.array_equal(rbm.gibbs_steps(3, aligned, seed=4321, chain_id0=5, sweep0=2).cpu().numpy(), want)
+    finally:
+        _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
+    assert backing[0].item() == 0.0
