@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
   const int nranks = (int)cluster.num_blocks();
   const int slot = (rank * NW + warp) * CPW + sub, nslots = nranks * NW * CPW;
 
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
   for (int idx = tid; idx < nh * N; idx += NT) Wsm[(idx / N) * LD + idx % N] = a.W[idx];
   for (int idx = tid; idx < N; idx += NT) bsm[idx] = a.b[idx];
   for (int idx = tid; idx < nh; idx += NT) csm[idx] = a.c[idx];
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
     double accb = 0.0, accc = 0.0;
     // g = (1/B) sum_data grad E - (1/C) sum_chains grad E,  grad E(v) = -[p v^T ; v ; p]
     auto accumulate = [&](uint32_t vm, bool valid, double weight) {
-      const double sg = sigmoid_exact(hidden_pre(vm));
+      const double sg = sigmoid_tab(hidden_pre(vm), e2tab);
       const double pw = (valid && u < nh) ? weight * sg : 0.0;
       accc += pw;
 #pragma unroll

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
   }
   for (int i = threadIdx.x; i < Hpad; i += GD_THREADS) hb[i] = i < Hc ? s.bias(i) : 0.0;
   __shared__ int8_t spos[128];
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
   if (threadIdx.x < 128) spos[threadIdx.x] = mode == ROWS_EXPANDED ? src.ex.sitepos[threadIdx.x] : (int8_t)-1;
   for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
   for (int i = threadIdx.x; i < GD_TR * LDP; i += GD_THREADS) Pt[i] = 0.0;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int unit = 8 * nb + 2 * t + e;
-          if (unit < Hc) prow[unit] = wr * fmin(fmax(sigmoid_exact(acc[nb][e]), 0.0), 1.0);
+          if (unit < Hc) prow[unit] = wr * fmin(fmax(sigmoid_tab(acc[nb][e], e2tab), 0.0), 1.0);
         }
       }
     }

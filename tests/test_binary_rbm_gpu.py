@@ -464,3 +464,22 @@ def test_gibbs_ragged_and_unaligned_state_tiles(lib, cuda, mode, n, nh, C):
     finally:
         _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
     assert backing[0].item() == 0.0
+
+
+def test_reduced_gradient_saturated_units_large_batch(lib, cuda):
+    """The tensor-core gradient path evaluates the logistic function with a table + Newton scheme
+    (common.cuh: sigmoid_tab); saturated and far-out pre-activations (|theta| up to ~1000) must still match
+    the oracle's 1 / (1 + exp(-x)) to 1e-10 in every gradient entry."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh, B = 24, 40, 4096
+    W, b, c = make_binary_params(n, nh, 191, bias_scale=0.5)
+    W[::2] *= 60.0
+    c[1::4] -= 400.0
+    c[2::4] += 300.0
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    v = random_states(B, n, 192)
+    with np.errstate(over="ignore"):
+        want = o.effective_energy_gradient(v)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), want, what="reduced gradient, saturated units")
