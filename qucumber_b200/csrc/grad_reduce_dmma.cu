@@ -20,7 +20,7 @@ constexpr int GD_TR = 64;  // rows per tile
 
 // NB8: 8-column blocks of the visible layer, HB8: 8-unit blocks of all hidden-like features (computed + aux)
 template <int NB8, int HB8>
-__global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec s, RowSrc src, int mode, int64_t rows,
+__global__ void __launch_bounds__(GD_THREADS, 2) grad_reduce_dmma_kernel(AffineSpec s, RowSrc src, int mode, int64_t rows,
                                                                       double* __restrict__ partials) {
   constexpr int Npad = 8 * NB8, Hpad = 8 * HB8;
   constexpr int KN4 = 2 * NB8;            // k-steps of phase 1
@@ -78,25 +78,46 @@ __global__ void __launch_bounds__(GD_THREADS) grad_reduce_dmma_kernel(AffineSpec
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * GD_TR;
     // ---- fill the V tile, the row weights and the aux columns of the P tile
+    if (mode == ROWS_EXPLICIT) {  // pull the CTA's next tile (one contiguous span) into L2 while this one is processed
+      const int64_t rn = r0 + (int64_t)gridDim.x * GD_TR;
+      const int64_t nbytes = ((rows - rn < GD_TR ? rows - rn : (int64_t)GD_TR)) * N * (int64_t)sizeof(double);
+      const char* nbase = reinterpret_cast<const char*>(src.v + rn * N);
+      for (int64_t off = (int64_t)threadIdx.x * 128; off < nbytes; off += (int64_t)GD_THREADS * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + off));
+    }
     // element idx = rr * N + j of the tile, stepped without divisions; the rotated-site table comes from shared memory
     {
+      // batches of 8 elements per thread: the 8 loads of a batch are issued before its first store
+      constexpr int FILL = (GD_TR * Npad + GD_THREADS - 1) / GD_THREADS, FB = FILL < 8 ? FILL : 8;
       int rr = fill_r0, j = fill_j0;
-      for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
-        const int64_t r = r0 + rr;
-        double val = 0.0;
-        if (r < rows) {
-          if (mode == ROWS_EXPANDED) {
-            const int tpos = (int)spos[j];
-            val = tpos < 0 ? src.ex.samples[(r >> src.ex.S) * N + j]
-                           : ((((uint32_t)r & ((1u << src.ex.S) - 1u)) >> (src.ex.S - 1 - tpos)) & 1u ? 1.0 : 0.0);
-          } else {
-            val = src.v[r * N + j];
+      for (int i0 = 0; i0 < FILL; i0 += FB) {
+        double vals[FB];
+        int rr2 = rr, j2 = j;
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+          const int64_t r = r0 + rr2;
+          double val = 0.0;
+          if (threadIdx.x + (i0 + i) * GD_THREADS < GD_TR * N && r < rows) {
+            if (mode == ROWS_EXPANDED) {
+              const int tpos = (int)spos[j2];
+              val = tpos < 0 ? src.ex.samples[(r >> src.ex.S) * N + j2]
+                             : ((((uint32_t)r & ((1u << src.ex.S) - 1u)) >> (src.ex.S - 1 - tpos)) & 1u ? 1.0 : 0.0);
+            } else {
+              val = src.v[r * N + j2];
+            }
           }
+          vals[i] = val;
+          rr2 += fill_dr;
+          j2 += fill_dj;
+          if (j2 >= N) { j2 -= N; ++rr2; }
         }
-        Vt[rr * LDV + j] = val;
-        rr += fill_dr;
-        j += fill_dj;
-        if (j >= N) { j -= N; ++rr; }
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+          if (threadIdx.x + (i0 + i) * GD_THREADS < GD_TR * N) Vt[rr * LDV + j] = vals[i];
+          rr += fill_dr;
+          j += fill_dj;
+          if (j >= N) { j -= N; ++rr; }
+        }
       }
     }
     for (int rr = threadIdx.x; rr < GD_TR; rr += GD_THREADS) {
