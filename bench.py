@@ -54,8 +54,53 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.thread = None
+        self.nvml = None          # (handle, stop event, samples) when NVML is used
+        self.visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+
+    def _start_nvml(self):
+        """Preferred: poll NVML every 2 ms from a thread (a 35 ms timed region still yields ~15 samples)."""
+        import pynvml
+
+        pynvml.nvmlInit()
+        idx = self.index
+        if self.visible:  # map the CUDA ordinal to the physical index / UUID
+            ent = self.visible.split(",")[idx].strip()
+            handle = pynvml.nvmlDeviceGetHandleByUUID(ent) if ent.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(ent))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        stop, samples = threading.Event(), []
+        smax = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+
+        def poll():
+            while not stop.is_set():
+                try:
+                    samples.append((pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM),
+                                    pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)))
+                except Exception:
+                    pass
+                stop.wait(0.002)
+
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
+        self.nvml = (pynvml, stop, samples, smax)
+
+    def _stop_nvml(self):
+        pynvml, stop, samples, smax = self.nvml
+        stop.set()
+        self.thread.join(timeout=1)
+        flags = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(name for name, bit in flags.items() if any(r & bit for _, r in samples))
+        sm = [c for c, _ in samples]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(smax), "samples": len(sm), "reasons": reasons,
+                "source": "nvml"}
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -71,6 +116,8 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
