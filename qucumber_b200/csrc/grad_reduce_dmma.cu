@@ -14,13 +14,17 @@
 
 namespace qcb {
 
-constexpr int GD_THREADS = 256;
-constexpr int GD_WARPS = 8;
-constexpr int GD_TR = 64;  // rows per tile
+#ifndef QCB_GD_WARPS  // overridable for occupancy experiments
+#define QCB_GD_WARPS 8
+#define QCB_GD_MIN_CTAS 2
+#endif
+constexpr int GD_WARPS = QCB_GD_WARPS;
+constexpr int GD_THREADS = 32 * GD_WARPS;
+constexpr int GD_TR = 8 * GD_WARPS;  // rows per tile: warp w owns rows 8w .. 8w+7 in phase 1
 
 // NB8: 8-column blocks of the visible layer, HB8: 8-unit blocks of all hidden-like features (computed + aux)
 template <int NB8, int HB8>
-__global__ void __launch_bounds__(GD_THREADS, 2) grad_reduce_dmma_kernel(AffineSpec s, RowSrc src, int mode, int64_t rows,
+__global__ void __launch_bounds__(GD_THREADS, QCB_GD_MIN_CTAS) grad_reduce_dmma_kernel(AffineSpec s, RowSrc src, int mode, int64_t rows,
                                                                       double* __restrict__ partials) {
   constexpr int Npad = 8 * NB8, Hpad = 8 * HB8;
   constexpr int KN4 = 2 * NB8;            // k-steps of phase 1
