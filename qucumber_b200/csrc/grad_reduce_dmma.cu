@@ -255,9 +255,17 @@ static size_t gd_smem(int NB8, int HB8) {
 }
 
 template <int NB8, int HB8>
-static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int grid, cudaStream_t st) {
+static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int* grid_io, cudaStream_t st) {
   const size_t smem = gd_smem(NB8, HB8);
-  QCB_CUDA(cudaFuncSetAttribute(grad_reduce_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int ctas_per_sm = 0;  // persistent grid = exactly the resident CTAs
+  if (ctas_per_sm == 0) {
+    QCB_CUDA(cudaFuncSetAttribute(grad_reduce_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, grad_reduce_dmma_kernel<NB8, HB8>, GD_THREADS, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int64_t resident = (int64_t)sm_count() * ctas_per_sm;
+  if (*grid_io > resident) *grid_io = (int)resident;
+  const int grid = *grid_io;
   grad_reduce_dmma_kernel<NB8, HB8><<<grid, GD_THREADS, smem, st>>>(s, src, mode, rows, partials);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
@@ -272,10 +280,10 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
   const int NB8 = pick8(s.n_in1), HB8 = pick8(H);
   if (NB8 == 0 || HB8 == 0 || gd_smem(NB8, HB8) > SMEM_LIMIT) return QCB_OK;
   const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
-  const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
+  int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
   int rc = QCB_OK;
 #define QCB_GD_CASE(NB, HBx) \
-  if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx>(s, src, mode, rows, partials, grid, st); else
+  if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx>(s, src, mode, rows, partials, &grid, st); else
   QCB_GD_CASE(2, 2) QCB_GD_CASE(2, 3) QCB_GD_CASE(2, 4) QCB_GD_CASE(2, 8) QCB_GD_CASE(2, 16)
   QCB_GD_CASE(3, 2) QCB_GD_CASE(3, 3) QCB_GD_CASE(3, 4) QCB_GD_CASE(3, 8) QCB_GD_CASE(3, 16)
   QCB_GD_CASE(4, 2) QCB_GD_CASE(4, 3) QCB_GD_CASE(4, 4) QCB_GD_CASE(4, 8) QCB_GD_CASE(4, 16)
@@ -363,7 +371,14 @@ template <int NB8, int HB8>
 static int launch_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int64_t rows, double* E, int grid,
                               cudaStream_t st) {
   const size_t smem = ((size_t)2 * NB8 * HB8 * 32 + 8 * HB8 + 8 * NB8 + (size_t)GD_TR * (8 * NB8 + 4)) * sizeof(double);
-  QCB_CUDA(cudaFuncSetAttribute(rows_energy_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int ctas_per_sm = 0;  // persistent grid = exactly the resident CTAs (a partial second wave costs more than it gives)
+  if (ctas_per_sm == 0) {
+    QCB_CUDA(cudaFuncSetAttribute(rows_energy_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rows_energy_dmma_kernel<NB8, HB8>, GD_THREADS, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int64_t resident = (int64_t)sm_count() * ctas_per_sm;
+  if (grid > resident) grid = (int)resident;
   rows_energy_dmma_kernel<NB8, HB8><<<grid, GD_THREADS, smem, st>>>(s, v, vb, rows, E);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
@@ -379,15 +394,16 @@ int try_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int6
   const size_t smem = ((size_t)2 * NB8 * HB8 * 32 + 8 * HB8 + 8 * NB8 + (size_t)GD_TR * (8 * NB8 + 4)) * sizeof(double);
   if (smem > SMEM_LIMIT) return QCB_OK;
   const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
-  const int64_t cap = (int64_t)sm_count() * 2;
+  const int64_t cap = (int64_t)sm_count() * 8;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
   int rc = QCB_OK;
 #define QCB_EN_CASE(NB, HBx) \
   if (NB8 == NB && HB8 == HBx) rc = launch_energy_dmma<NB, HBx>(s, v, vb, rows, E, grid, st); else
-  QCB_EN_CASE(2, 2) QCB_EN_CASE(2, 4) QCB_EN_CASE(2, 8)
-  QCB_EN_CASE(4, 2) QCB_EN_CASE(4, 4) QCB_EN_CASE(4, 8)
-  QCB_EN_CASE(8, 2) QCB_EN_CASE(8, 4) QCB_EN_CASE(8, 8)
-  QCB_EN_CASE(16, 2) QCB_EN_CASE(16, 4) QCB_EN_CASE(16, 8)
+  QCB_EN_CASE(2, 2) QCB_EN_CASE(2, 3) QCB_EN_CASE(2, 4) QCB_EN_CASE(2, 8)
+  QCB_EN_CASE(3, 2) QCB_EN_CASE(3, 3) QCB_EN_CASE(3, 4) QCB_EN_CASE(3, 8)
+  QCB_EN_CASE(4, 2) QCB_EN_CASE(4, 3) QCB_EN_CASE(4, 4) QCB_EN_CASE(4, 8)
+  QCB_EN_CASE(8, 2) QCB_EN_CASE(8, 3) QCB_EN_CASE(8, 4) QCB_EN_CASE(8, 8)
+  QCB_EN_CASE(16, 2) QCB_EN_CASE(16, 3) QCB_EN_CASE(16, 4) QCB_EN_CASE(16, 8)
   return QCB_OK;
 #undef QCB_EN_CASE
   if (rc == QCB_OK) *handled = 1;
