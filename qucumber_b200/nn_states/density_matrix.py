@@ -152,11 +152,15 @@ class DensityMatrix(NeuralStateBase):
         """density_matrix.py:319-330."""
         return cplx.scalar_mult(self.rbm_ph.gamma_grad(v, v, eta=-1, expand=True), cplx.I) + self.pi_grad(v, v, phase=True, expand=True)
 
-    def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1, input_bases=None, **kwargs):
+    def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1, input_bases=None, progbar=False,
+            starting_epoch=1, time=False, callbacks=None, optimizer=torch.optim.SGD, optimizer_args=None, scheduler=None,
+            scheduler_args=None, **kwargs):
         if input_bases is None:
             raise ValueError("input_bases must be provided to train a DensityMatrix!")
         return super().fit(data=data, epochs=epochs, pos_batch_size=pos_batch_size, neg_batch_size=neg_batch_size, k=k, lr=lr,
-                           input_bases=input_bases, **kwargs)
+                           input_bases=input_bases, progbar=progbar, starting_epoch=starting_epoch, time=time, callbacks=callbacks,
+                           optimizer=optimizer, optimizer_args=optimizer_args, scheduler=scheduler, scheduler_args=scheduler_args,
+                           **kwargs)
 
     @staticmethod
     def autoload(location, gpu=True):

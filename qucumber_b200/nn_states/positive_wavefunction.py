@@ -52,16 +52,28 @@ class PositiveWaveFunction(WaveFunctionBase):
         """Gradient of the amplitude RBM only; bases are ignored (positive_wavefunction.py:126-146)."""
         return super().gradient(v, bases=None)
 
+    def positive_phase_gradients(self, samples_batch, *args, **kwargs):
+        """Positive phase of the gradients; extra arguments are ignored (positive_wavefunction.py:142-154)."""
+        return super().positive_phase_gradients(samples_batch, bases_batch=None)
+
     def compute_batch_gradients(self, k, samples_batch, neg_batch, *args, **kwargs):
         return super().compute_batch_gradients(k, samples_batch, neg_batch, bases_batch=None)
 
     def compute_exact_gradients(self, samples_batch, space=None, *args, **kwargs):
         return super().compute_exact_gradients(samples_batch, space, bases_batch=None)
 
-    def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1e-3, input_bases=None, **kwargs):
+    def compute_exact_grads(self, samples_batch, space=None, *args, **kwargs):
+        """Name used by the reference's subclass (positive_wavefunction.py:156-171); same as compute_exact_gradients."""
+        return self.compute_exact_gradients(samples_batch, space)
+
+    def fit(self, data, epochs=100, pos_batch_size=100, neg_batch_size=None, k=1, lr=1e-3, progbar=False, starting_epoch=1,
+            time=False, callbacks=None, optimizer=torch.optim.SGD, optimizer_args=None, scheduler=None, scheduler_args=None,
+            **kwargs):
         """Bases are not used for a positive wavefunction (positive_wavefunction.py:194-229)."""
+        kwargs["input_bases"] = None
         return super().fit(data=data, epochs=epochs, pos_batch_size=pos_batch_size, neg_batch_size=neg_batch_size, k=k, lr=lr,
-                           input_bases=None, **kwargs)
+                           progbar=progbar, starting_epoch=starting_epoch, time=time, callbacks=callbacks, optimizer=optimizer,
+                           optimizer_args=optimizer_args, scheduler=scheduler, scheduler_args=scheduler_args, **kwargs)
 
     @staticmethod
     def autoload(location, gpu=True):
