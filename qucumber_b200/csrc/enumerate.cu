@@ -462,13 +462,25 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const double* __restri
   }
 }
 
-__global__ void sums_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out8) {
-  const int q = threadIdx.x;
-  if (q >= 8) return;
-  double t = 0.0;
-  if (q < 5)
-    for (int i = 0; i < n; ++i) t += partials[8 * i + q];
-  out8[q] = t;
+// One block of 256 threads: strided partials per thread, then warps, then the block — a fixed order.
+__global__ void __launch_bounds__(256) sums_combine_kernel(const double* __restrict__ partials, int n, double* __restrict__ out8) {
+  __shared__ double red[8][8];
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += 256)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) s[q] += partials[8 * i + q];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) s[q] = warp_sum(s[q]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int q = 0; q < 5; ++q) red[warp][q] = s[q];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    if (threadIdx.x < 5)
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    out8[threadIdx.x] = t;
+  }
 }
 
 __global__ void __launch_bounds__(256) neg_lse_kernel(const double* __restrict__ E, int64_t n, double* __restrict__ partials) {
@@ -656,7 +668,7 @@ int run_exact_stats_range(const StackedParams& p, uint64_t first, uint64_t count
     }
     if (rc != QCB_OK) return rc;
   }
-  sums_combine_kernel<<<1, 32, 0, st>>>(partials, grid, out8);
+  sums_combine_kernel<<<1, 256, 0, st>>>(partials, grid, out8);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
