@@ -54,6 +54,9 @@ struct ImmaHeader {
 
 __host__ __device__ inline int imma_kk(int units_pad) { return (units_pad + 31) / 32; }
 
+// Fixed-point weights are split as Wq = d2 2^15 + d1 2^8 + d0 with signed digits d0 (8 bits), d1 (7 bits), d2 (8 bits)
+constexpr long long IMMA_WQ_MAX = 127ll * 32768 + 63 * 256 + 127;
+
 // bytes of the image for HB / VB 16-unit blocks
 static size_t imma_image_bytes(int HB, int VB) {
   const int Hpad = 16 * HB, Npad = 16 * VB;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   int s = 0;
   if (s_maxw > 0.0 && s_maxw < 1e300) s = 21 - ilogb(s_maxw);  // |Wq| <= 2^22
   if (s > 60) s = 60;
+  if (s_maxw > 0.0 && s_maxw < 1e300 && llrint(s_maxw * ldexp(1.0, s)) > IMMA_WQ_MAX) s -= 1;  // keep the top digit inside int8
   // weights beyond 2^81 (or non-finite) do not fit the fixed-point image: the digits are zeroed and the margins
   // set to 4, which makes every unit undecided, i.e. the kernel degenerates to its exact FP64 path
   const bool degenerate = !(s_maxw < 1e300) || s < -60;
@@ -158,10 +162,10 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
         long long wq = llrint(Ws[hid * GI_PACK_LD + vis] * scale);
         const int q0 = (int)(((wq + 128) & 255) - 128);
         wq = (wq - q0) >> 8;
-        const int q1 = (int)(((wq + 128) & 255) - 128);
-        const int q2 = (int)((wq - q1) >> 8);
+        const int q1 = (int)(((wq + 64) & 127) - 64);   // 7 bits: stored doubled, multiplied by the 0 / 128 state operand
+        const int q2 = (int)((wq - q1) >> 7);           // |q2| <= 127 because |Wq| <= IMMA_WQ_MAX
         word[0] |= (uint32_t)(q0 & 255) << (8 * i);
-        word[1] |= (uint32_t)(q1 & 255) << (8 * i);
+        word[1] |= (uint32_t)((2 * q1) & 255) << (8 * i);
         word[2] |= (uint32_t)(q2 & 255) << (8 * i);
       }
     }
@@ -174,7 +178,8 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
 }
 
 __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  // A (state bits, 0 / 1 / 128) unsigned, B (weight digits) signed
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -266,22 +271,26 @@ __device__ __forceinline__ void half_sweep_imma(const uint32_t (&min)[2][(KB_IN 
   int tot[NB][4];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) { tot[nb][0] = 0; tot[nb][1] = 0; tot[nb][2] = 0; tot[nb][3] = 0; }
+  // Wq = d2 2^15 + d1 2^8 + d0 (d0, d2: 8 bits, d1: 7 bits).  The top digit goes first and is shifted once; the middle
+  // digit needs no shift of the accumulators: it is stored as 2 d1 and multiplied by a state operand scaled to 128.
 #pragma unroll
   for (int slice = 2; slice >= 0; --slice) {
-    if (slice != 2) {
+    if (slice == 1) {
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tot[nb][e] <<= 8;
+        for (int e = 0; e < 4; ++e) tot[nb][e] <<= 15;
     }
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) {
       const uint4* row = reinterpret_cast<const uint4*>(Bimg) + ((size_t)(slice * KK + kk) * OB) * 32 + lane;
+      const int sh = slice == 1 ? 7 : 0;  // state bits as 0 / 128 (u8) for the middle digit, 0 / 1 otherwise
+      const uint32_t a0 = afr[kk][0] << sh, a1 = afr[kk][1] << sh, a2 = afr[kk][2] << sh, a3 = afr[kk][3] << sh;
 #pragma unroll
       for (int np = 0; np < OB; ++np) {  // one 16-byte load feeds two n-blocks
         const uint4 b = row[np * 32];
-        imma16832(tot[2 * np], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.x, b.y);
-        imma16832(tot[2 * np + 1], afr[kk][0], afr[kk][1], afr[kk][2], afr[kk][3], b.z, b.w);
+        imma16832(tot[2 * np], a0, a1, a2, a3, b.x, b.y);
+        imma16832(tot[2 * np + 1], a0, a1, a2, a3, b.z, b.w);
       }
     }
   }
