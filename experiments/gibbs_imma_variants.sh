@@ -2,7 +2,7 @@
 # Builds occupancy variants of the IMMA Gibbs kernel on the GPU box and times each (kernel experiments only).
 cd "$(dirname "$0")/.."
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC"
-OTHERS="api gibbs energy_grad grad_reduce grad_reduce_dmma enumerate rotated"
+OTHERS="api gibbs cd_epoch energy_grad grad_reduce grad_reduce_dmma enumerate rotated fullspace"
 for f in $OTHERS; do nvcc $FLAGS -c qucumber_b200/csrc/$f.cu -o /tmp/$f.o & done
 VARIANTS="${VARIANTS:-256:2 576:1 640:1}"
 for v in $VARIANTS; do

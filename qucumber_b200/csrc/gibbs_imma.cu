@@ -5,9 +5,10 @@
 // FP64 evaluation for the rare undecided units, so the samples are those of the all-FP64 kernel
 // (gibbs.cu) — same Philox convention, same decisions — at a fraction of the FP64 work:
 //
-//  * W is quantised once per call to 24-bit fixed point, Wq = rint(W 2^s), and split into three signed
-//    int8 digits; a state bit is 0 or 1, so  t = sum_k v_k Wq_ik  is an exact int32 computed by
-//    3 x mma.sync.m16n8k32.s8 (IMMA) passes.  x~ = float(t) 2^-s + c.
+//  * W is quantised once per call to 24-bit fixed point, Wq = rint(W 2^s) = d2 2^15 + d1 2^8 + d0 with signed
+//    digits of 8, 7 and 8 bits; a state bit is 0 or 1, so  t = sum_k v_k Wq_ik  is an exact int32 computed by
+//    3 x mma.sync.m16n8k32 (u8 x s8, IMMA) passes: d2 first, one shift by 15, then 2 d1 against the state
+//    bits scaled to 128 and d0 against the plain bits.  x~ = float(t) 2^-s + c.
 //  * |x~ - x| <= n_in 2^-(s+1) + 2^-22 (sum_k |W_ik| + |c_i|) =: dx  is a rigorous bound (quantisation +
 //    the two float roundings), hence |sigmoid(x~) - sigmoid(x)| <= dx / 4.  The filter decides from the
 //    16-bit cell of u unless p~ lies within margin = dx/4 + 2^-19 of it (the float evaluation of the test is good to 2^-21.5);
