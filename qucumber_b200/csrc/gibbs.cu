@@ -448,6 +448,8 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
   const size_t need = gibbs_workspace_bytes(p.N, nhid);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, need);
   if (C == 0 || k == 0) return QCB_OK;
+  if (sweep0 + (uint64_t)k > (1ull << 32))
+    return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
   if (uniforms == nullptr && g_gibbs_mode == 0) {
     int handled = 0;
     const int rc = try_gibbs_imma(p, v_in, v, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
