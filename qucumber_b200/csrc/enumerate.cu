@@ -383,8 +383,22 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const Enu
 #pragma unroll
     for (int i = 0; i < NHT; ++i) t[i] = i < H ? exp(t[i]) : 0.0;
     double eb = exp(bv);
+    // the target amplitudes of a state are fetched two steps ahead (few warps are resident: 64 registers hold t_i)
+    auto fetch = [&](uint32_t k, double& re, double& im) {
+      const uint64_t idx = base | ((uint64_t)(k ^ (k >> 1)) << 5);
+      const bool live = k < steps && a.t_re != nullptr && idx >= a.first && idx < last;
+      re = live ? a.t_re[idx - a.first] : 0.0;
+      im = (live && a.t_im != nullptr) ? a.t_im[idx - a.first] : 0.0;
+    };
+    double tr0, ti0, tr1, ti1;
+    fetch(0u, tr0, ti0);
+    fetch(1u, tr1, ti1);
     for (uint32_t k = 0; k < steps; ++k) {
       const uint64_t idx = base | ((uint64_t)(k ^ (k >> 1)) << 5);
+      const double tr = tr0, ti = ti0;
+      tr0 = tr1;
+      ti0 = ti1;
+      fetch(k + 2u, tr1, ti1);
       double p0 = eb, p1 = 1.0, p2 = 1.0, p3 = 1.0;
       if (no_thresh) {
 #pragma unroll
@@ -404,8 +418,6 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const Enu
       if (idx >= a.first && idx < last) {
         sums[4] += p;
         if (a.t_re != nullptr) {
-          const double tr = a.t_re[idx - a.first];
-          const double ti = a.t_im != nullptr ? a.t_im[idx - a.first] : 0.0;
           const double psi = sqrt(p);
           sums[0] = fma(tr, psi, sums[0]);
           sums[1] = fma(ti, psi, sums[1]);
