@@ -325,12 +325,34 @@ __global__ void __launch_bounds__(GD_THREADS) rows_energy_dmma_kernel(AffineSpec
   for (int i = threadIdx.x; i < Npad; i += GD_THREADS) vbs[i] = i < N ? vb[i] : 0.0;
   for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
   __syncthreads();
+  const int fill_r0 = threadIdx.x / N, fill_j0 = threadIdx.x - fill_r0 * N;
+  const int fill_dr = GD_THREADS / N, fill_dj = GD_THREADS - fill_dr * N;
   const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * GD_TR;
-    for (int idx = threadIdx.x; idx < GD_TR * N; idx += GD_THREADS) {
-      const int rr = idx / N, j = idx - rr * N;
-      Vt[rr * LDV + j] = r0 + rr < rows ? v[(r0 + rr) * N + j] : 0.0;
+    {
+      // batches of 8 elements per thread, stepped without divisions: the loads of a batch are issued before its stores
+      constexpr int FILL = (GD_TR * Npad + GD_THREADS - 1) / GD_THREADS, FB = FILL < 8 ? FILL : 8;
+      int rr = fill_r0, j = fill_j0;
+      for (int i0 = 0; i0 < FILL; i0 += FB) {
+        double vals[FB];
+        int rr2 = rr, j2 = j;
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+          const bool live = threadIdx.x + (i0 + i) * GD_THREADS < GD_TR * N && r0 + rr2 < rows;
+          vals[i] = live ? v[(r0 + rr2) * N + j2] : 0.0;
+          rr2 += fill_dr;
+          j2 += fill_dj;
+          if (j2 >= N) { j2 -= N; ++rr2; }
+        }
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+          if (threadIdx.x + (i0 + i) * GD_THREADS < GD_TR * N) Vt[rr * LDV + j] = vals[i];
+          rr += fill_dr;
+          j += fill_dj;
+          if (j >= N) { j -= N; ++rr; }
+        }
+      }
     }
     __syncthreads();
     double acc[HB8][2];
