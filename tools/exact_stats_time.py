@@ -10,12 +10,12 @@ from qucumber_b200 import PositiveWaveFunction  # noqa: E402
 from qucumber_b200.utils import training_statistics as ts  # noqa: E402
 
 dev = torch.device("cuda")
-for n in (20, 24, 26, 28):
+for n in [int(x) for x in sys.argv[1:]] or (20, 24, 26, 28):
     torch.manual_seed(1234)
     nn = PositiveWaveFunction(n, n, gpu=True)
     g = torch.Generator(device="cuda").manual_seed(5)
-    t = torch.rand(2, 1 << n, dtype=torch.double, device=dev, generator=g)
-    t[1] = 0
+    t = torch.zeros(2, 1 << n, dtype=torch.double, device=dev)
+    t[0].uniform_(generator=g)
     t /= t[0].norm()
 
     def timed(fn):
