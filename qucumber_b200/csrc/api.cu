@@ -78,6 +78,33 @@ static int make_params(StackedParams& p, const double* W, const double* U, const
   return QCB_OK;
 }
 
+// A process may drive several GPUs: run each call on the device that owns the caller's stream and restore the
+// caller's current device afterwards (the legacy NULL stream carries no device: the current one is used).
+struct StreamDeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  // stream: the caller's stream; hint: any device pointer of the call (consulted for the legacy NULL stream,
+  // which carries no device — PyTorch's default stream is that stream)
+  StreamDeviceGuard(void* stream, const void* hint) {
+    int dev = -1;
+    if (stream != nullptr) {
+      // a capturing stream must not be queried (it would invalidate the capture); graph capture runs on the current device
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); return; }
+      if (cap != cudaStreamCaptureStatusNone) return;
+      if (cudaStreamGetDevice((cudaStream_t)stream, &dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
+    } else if (hint != nullptr) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, hint) == cudaSuccess && attr.type == cudaMemoryTypeDevice) dev = attr.device;
+      else (void)cudaGetLastError();
+    }
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev && cudaSetDevice(dev) == cudaSuccess) changed = true;
+  }
+  ~StreamDeviceGuard() {
+    if (changed) (void)cudaSetDevice(prev);
+  }
+};
+
 }  // namespace qcb
 
 using namespace qcb;
@@ -118,6 +145,7 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
 int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
                   int na, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                   const double* uniforms, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -134,6 +162,7 @@ int qcb_set_gibbs_mode(int mode) {
 int qcb_debug_gibbs_filter(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
                            int na, double* v, int64_t C, int k, uint64_t seed, unsigned long long* stats2, void* ws,
                            size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -147,6 +176,7 @@ int qcb_debug_gibbs_filter(const double* W, const double* U, const double* b, co
 
 int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x,
                        const double* M2, int m2_rows, const double* x2, int64_t rows, double* out, void* stream) {
+  StreamDeviceGuard device_guard(stream, M);
   if (M == nullptr || x == nullptr || out == nullptr || m_rows < 1 || m_cols < 1 || rows < 0)
     return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: bad arguments");
   if ((M2 == nullptr) != (x2 == nullptr)) return fail(QCB_ERR_BAD_ARG, "linear_sigmoid: M2 and x2 go together");
@@ -155,6 +185,7 @@ int qcb_linear_sigmoid(const double* M, int m_rows, int m_cols, int transpose_m,
 
 int qcb_linear(const double* M, int m_rows, int m_cols, int transpose_m, const double* bias, const double* x, int64_t rows,
                double* out, void* stream) {
+  StreamDeviceGuard device_guard(stream, M);
   if (M == nullptr || x == nullptr || out == nullptr || m_rows < 1 || m_cols < 1 || rows < 0)
     return fail(QCB_ERR_BAD_ARG, "linear: bad arguments");
   return run_linear(2, M, m_rows, m_cols, transpose_m, bias, x, nullptr, 0, nullptr, rows, out, (cudaStream_t)stream);
@@ -162,12 +193,14 @@ int qcb_linear(const double* M, int m_rows, int m_cols, int transpose_m, const d
 
 int qcb_bernoulli(const double* p, int64_t n, const double* uniforms, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                   double* out, void* stream) {
+  StreamDeviceGuard device_guard(stream, p);
   if (n < 0 || (n > 0 && (p == nullptr || out == nullptr))) return fail(QCB_ERR_BAD_ARG, "bernoulli: bad arguments");
   return run_bernoulli(p, n, uniforms, seed, chain_id0, sweep0, out, (cudaStream_t)stream);
 }
 
 int qcb_rbm_energy(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
                    int na, const double* v, int64_t rows, double* E_out, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   (void)ws; (void)ws_bytes;
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
@@ -179,6 +212,7 @@ int qcb_rbm_energy(const double* W, const double* U, const double* b, const doub
 int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
                         int nh, int na, const double* v, int64_t rows, double scale, double* g, int accumulate, void* ws,
                         size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -188,6 +222,7 @@ int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const
 
 int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
                        int nh, int na, const double* v, int64_t rows, double* g_rows, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -197,6 +232,7 @@ int qcb_rbm_grad_batch(const double* W, const double* U, const double* b, const 
 
 int qcb_rbm_flip_logratio(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
                           int nh, int na, const double* v, int64_t rows, double* out, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -207,6 +243,7 @@ int qcb_rbm_flip_logratio(const double* W, const double* U, const double* b, con
 int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
                     int na, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                     const double* uniforms, double scale, double* g, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -223,6 +260,7 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
                     int na, const double* pos, int64_t B, const double* neg, int64_t C, int k, uint64_t seed,
                     uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale, double* g, void* ws,
                     size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -245,6 +283,7 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
 int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch,
                      const double* neg, int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed,
                      uint64_t sweep0, double* g_last, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   return run_cd_epoch(W, b, c, N, nh, pos, B_total, pos_batch, neg, C_total, neg_batch, num_batches, k, lr, seed, sweep0, g_last,
                       (cudaStream_t)stream);
 }
@@ -252,6 +291,7 @@ int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh, const doubl
 int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const double* c, const double* d, int N,
                        int nh, int na, uint64_t first_state, uint64_t count, double* out2, void* ws, size_t ws_bytes,
                        void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -260,15 +300,18 @@ int qcb_rbm_logz_range(const double* W, const double* U, const double* b, const 
 }
 
 int qcb_kron_rotate(double* re, double* im, int n, int64_t batch, const uint8_t* basis, const double* unitaries, int K, void* stream) {
+  StreamDeviceGuard device_guard(stream, re);
   return run_kron_rotate(re, im, n, batch, basis, unitaries, K, (cudaStream_t)stream);
 }
 
 int qcb_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n, double logZ,
                  double* out2, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, t_re);
   return run_kl_terms(t_re, t_im, p_re, p_im, n, logZ, out2, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int qcb_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, E);
   if (n < 0 || out2 == nullptr || (n > 0 && E == nullptr)) return fail(QCB_ERR_BAD_ARG, "neg_logsumexp: bad arguments");
   return run_neg_logsumexp(E, n, out2, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -277,6 +320,7 @@ int qcb_rbm_exact_stats_range(const double* W, const double* U, const double* b,
                               int nh, int na, uint64_t first_state, uint64_t count, double logZ, const double* target_re,
                               const double* target_im, double* out8, double* g_exact, void* ws, size_t ws_bytes,
                               void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
   StackedParams p;
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
@@ -290,6 +334,7 @@ int qcb_cwf_rotated(const double* W_am, const double* b_am, const double* c_am, 
                     const double* c_ph, int N, int nh, const double* samples, int64_t B, const uint8_t* basis,
                     const double* unitaries, int K, double* Upsi, double* g_am, double* g_ph, void* ws, size_t ws_bytes,
                     void* stream) {
+  StreamDeviceGuard device_guard(stream, W_am);
   StackedParams am, ph;
   int rc = make_params(am, W_am, nullptr, b_am, c_am, nullptr, N, nh, 0);
   if (rc != QCB_OK) return rc;
@@ -305,6 +350,7 @@ int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, c
                    const double* W_ph, const double* U_ph, const double* b_ph, const double* c_ph, const double* d_ph,
                    int N, int nh, int na, const double* samples, int64_t B, const uint8_t* basis, const double* unitaries,
                    int K, double* UrhoU, double* g_am, double* g_ph, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W_am);
   StackedParams am, ph;
   if (na < 1) return fail(QCB_ERR_BAD_ARG, "dm_rotated: na must be >= 1");
   int rc = make_params(am, W_am, U_am, b_am, c_am, d_am, N, nh, na);
@@ -325,6 +371,7 @@ size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C) {
 int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
                        const double* d_host, int N, int nh, int na, double* v_host, int64_t C, int k, uint64_t seed,
                        uint64_t chain_id0, uint64_t sweep0, void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, dev_scratch);
   if (N < 1 || nh < 1 || na < 0 || C < 0 || k < 0) return fail(QCB_ERR_BAD_ARG, "gibbs_host: bad sizes");
   if (W_host == nullptr || b_host == nullptr || c_host == nullptr || (na > 0 && (U_host == nullptr || d_host == nullptr)) ||
       (C > 0 && v_host == nullptr))

@@ -276,7 +276,8 @@ static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // one cluster; 16 CTAs (non-portable size) when the device can co-schedule them, else the portable 8
-  static int cluster_size = 0;
+  static int cluster_on[QCB_MAX_DEVICES] = {0};  // cached per device
+  int& cluster_size = cluster_on[device_slot()];
   if (cluster_size == 0) {
     QCB_CUDA(cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cluster_size = CE_CLUSTER_PORTABLE;

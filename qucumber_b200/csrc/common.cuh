@@ -43,6 +43,15 @@ inline int sm_count() {
   return n;
 }
 
+// Function attributes (dynamic shared memory limit, cluster size) and occupancy figures are cached per device: a
+// process may drive several GPUs, and cudaFuncSetAttribute applies to the current device only.
+constexpr int QCB_MAX_DEVICES = 64;
+inline int device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < QCB_MAX_DEVICES) ? dev : 0;
+}
+
 __host__ __device__ constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ constexpr int round_up(int x, int a) { return (x + a - 1) / a * a; }
 

@@ -416,13 +416,14 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
   // image + mbarriers + one 8-chain state tile per warp
   const size_t smem = align_up(gibbs_image_doubles(HB, VB) * sizeof(double) + 8 * (1 + GIBBS_WARPS), 128) +
                       (size_t)GIBBS_WARPS * CHAINS_PER_WARP * 16 * VB * sizeof(double);
-  static bool configured = false;
-  static int blocks_per_sm = 1;
-  if (!configured) {
+  static int blocks_on[QCB_MAX_DEVICES] = {0};  // 0: this device is not configured yet
+  int& blocks_per_sm = blocks_on[device_slot()];
+  if (blocks_per_sm == 0) {
+    int occ = 0;
     QCB_CUDA(cudaFuncSetAttribute(gibbs_kernel<HB, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_kernel<HB, VB>, GIBBS_THREADS, smem));
-    if (blocks_per_sm < 1) return fail(QCB_ERR_CUDA, "gibbs kernel does not fit on an SM (smem %zu B)", smem);
-    configured = true;
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_kernel<HB, VB>, GIBBS_THREADS, smem));
+    if (occ < 1) return fail(QCB_ERR_CUDA, "gibbs kernel does not fit on an SM (smem %zu B)", smem);
+    blocks_per_sm = occ;
   }
   const int64_t need = (a.num_groups + GIBBS_WARPS - 1) / GIBBS_WARPS;
   const int64_t cap = (int64_t)sm_count() * blocks_per_sm;

@@ -497,13 +497,14 @@ static int pick_blocks_imma(int units) {
 template <int HB, int VB, bool DBG>
 static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
   const size_t smem = imma_smem_bytes(HB, VB);
-  static bool configured = false;
-  static int blocks_per_sm = 1;
-  if (!configured) {
+  static int blocks_on[QCB_MAX_DEVICES] = {0};  // 0: this device is not configured yet
+  int& blocks_per_sm = blocks_on[device_slot()];
+  if (blocks_per_sm == 0) {
+    int occ = 0;
     QCB_CUDA(cudaFuncSetAttribute(gibbs_imma_kernel<HB, VB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gibbs_imma_kernel<HB, VB, DBG>, GI_THREADS, smem));
-    if (blocks_per_sm < 1) return fail(QCB_ERR_CUDA, "gibbs (imma) kernel does not fit on an SM");
-    configured = true;
+    QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_imma_kernel<HB, VB, DBG>, GI_THREADS, smem));
+    if (occ < 1) return fail(QCB_ERR_CUDA, "gibbs (imma) kernel does not fit on an SM");
+    blocks_per_sm = occ;
   }
   const int64_t groups = (a.C + GI_CPW - 1) / GI_CPW;
   const int64_t need = (groups + GI_WARPS - 1) / GI_WARPS;

@@ -257,7 +257,8 @@ static size_t gd_smem(int NB8, int HB8) {
 template <int NB8, int HB8>
 static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int* grid_io, cudaStream_t st) {
   const size_t smem = gd_smem(NB8, HB8);
-  static int ctas_per_sm = 0;  // persistent grid = exactly the resident CTAs
+  static int ctas_on[QCB_MAX_DEVICES] = {0};  // persistent grid = exactly the resident CTAs (cached per device)
+  int& ctas_per_sm = ctas_on[device_slot()];
   if (ctas_per_sm == 0) {
     QCB_CUDA(cudaFuncSetAttribute(grad_reduce_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, grad_reduce_dmma_kernel<NB8, HB8>, GD_THREADS, smem));
@@ -393,7 +394,8 @@ template <int NB8, int HB8>
 static int launch_energy_dmma(const AffineSpec& s, const double* v, const double* vb, int64_t rows, double* E, int grid,
                               cudaStream_t st) {
   const size_t smem = ((size_t)2 * NB8 * HB8 * 32 + 8 * HB8 + 8 * NB8 + (size_t)GD_TR * (8 * NB8 + 4)) * sizeof(double);
-  static int ctas_per_sm = 0;  // persistent grid = exactly the resident CTAs (a partial second wave costs more than it gives)
+  static int ctas_on[QCB_MAX_DEVICES] = {0};  // persistent grid = exactly the resident CTAs (a partial second wave costs more than it gives)
+  int& ctas_per_sm = ctas_on[device_slot()];
   if (ctas_per_sm == 0) {
     QCB_CUDA(cudaFuncSetAttribute(rows_energy_dmma_kernel<NB8, HB8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rows_energy_dmma_kernel<NB8, HB8>, GD_THREADS, smem));

@@ -483,3 +483,53 @@ def test_reduced_gradient_saturated_units_large_batch(lib, cuda):
     with np.errstate(over="ignore"):
         want = o.effective_energy_gradient(v)
     assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), want, what="reduced gradient, saturated units")
+
+
+def test_calls_are_capturable_in_a_cuda_graph(lib, cuda):
+    """The C ABI only enqueues work on the caller's stream (no allocation, no synchronisation, no stream query that
+    would invalidate a capture): a Gibbs call and a gradient call captured in a CUDA graph replay to the eager result."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh, C = 16, 12, 300
+    W, b, c = make_binary_params(n, nh, 201)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    v0 = torch.tensor(random_states(C, n, 202), device=cuda)
+    want_v = rbm.gibbs_steps(4, v0, seed=77)
+    want_g = rbm.effective_energy_gradient(want_v)
+    static_v = v0.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        rbm.gibbs_steps(4, static_v.clone(), overwrite=True, seed=77)  # warm-up: workspaces, function attributes
+        rbm.effective_energy_gradient(static_v)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            rbm.gibbs_steps(4, static_v, overwrite=True, seed=77)
+            g_out = rbm.effective_energy_gradient(static_v)
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(2):
+        static_v.copy_(v0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_v, want_v)
+        assert_close(g_out, want_g.cpu().numpy(), what="gradient from a replayed graph")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices(lib, cuda):
+    """A model living on cuda:1 while the current device stays cuda:0 runs on cuda:1 (the library switches to the
+    device of the caller's stream or, for the legacy default stream, of the data) and gives cuda:0's results."""
+    from qucumber_b200 import BinaryRBM
+
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        W, b, c = make_binary_params(24, 24, 211)
+        rbm = load_binary(BinaryRBM(24, 24, gpu=True), W, b, c).to(dev)
+        rbm.device = torch.device(dev)
+        v = torch.tensor(random_states(500, 24, 212), device=dev)
+        outs.append([rbm.gibbs_steps(3, v, seed=5).cpu(), rbm.effective_energy(v).cpu(), rbm.effective_energy_gradient(v).cpu(),
+                     rbm.log_partition().cpu()])
+        assert torch.cuda.current_device() == 0
+    for a, b_ in zip(*outs):
+        assert torch.equal(a, b_)
