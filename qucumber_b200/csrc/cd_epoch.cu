@@ -13,8 +13,9 @@
 //    masks exchanged by ballot;
 //  * the Gibbs draws follow the library's Philox convention (include/qcb.h) with chain id = row of the
 //    negative batch and sweep = sweep0 + step * k + s, i.e. the samples are those of qcb_rbm_cd_step;
-//    a decision compares the exact FP64 sigmoid with the 16-bit cell of u and evaluates the remaining 37
-//    bits only when p falls inside the cell, which is exactly  u < p;
+//    a decision is taken by a float filter against the 16-bit cell of u (margin 2^-17, |x| <= 64); what the
+//    filter leaves open goes to the exact path: FP64 sigmoid against the cell, and the remaining 37 bits of u
+//    only when p falls inside the cell — together exactly  u < p;
 //  * per step each CTA reduces its gradient share in a fixed order, the shares are exchanged through
 //    distributed shared memory (one cluster barrier per step, double-buffered), and every CTA applies the
 //    identical update to its copy.
