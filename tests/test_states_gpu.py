@@ -591,3 +591,80 @@ def test_kron_rotate_and_kl_terms_match_numpy(lib, cuda):
     assert_close(ts._single_basis_KL(torch.tensor(pt, device=cuda), torch.tensor(p, device=cuda)), want_kl, what="KL from probabilities")
     rc = lib.qcb_kl_terms(None, None, None, None, 4, 0.0, None, None, 0, None)
     assert rc != 0 and b"kl_terms" in lib.qcb_last_error()
+
+
+def test_exact_stats_ranges_and_fallback_agree(lib, cuda):
+    """qcb_rbm_exact_stats_range: (1) against a direct numpy evaluation, (2) additive over arbitrary, unaligned index
+    ranges (the fast kernel deals aligned 2^(m+5) blocks to warps and masks the ends), (3) the product-form kernel and
+    the log-domain fallback (forced by a bias that breaks the overflow pre-check) give the same five sums."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh = 13, 9
+    W, b, c = make_binary_params(n, nh, 301, bias_scale=0.3)
+    rng = np.random.default_rng(302)
+    t = rng.standard_normal((2, 1 << n))
+    t /= np.sqrt((t ** 2).sum())
+    tt = torch.tensor(t, device=cuda)
+
+    def stats(Wm, bm, cm, first, count):
+        rbm = load_binary(BinaryRBM(n, nh, gpu=True), Wm, bm, cm)
+        o2 = rbm.log_partition()
+        logZ = float(o2[0] + o2[1].log())
+        args, keep = rbm._param_args()
+        out8 = torch.empty(8, dtype=torch.double, device=cuda)
+        ws = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_EXACT_STATS, n, nh, 0, count))
+        _lib.check(lib.qcb_rbm_exact_stats_range(*args, first, count, logZ, _lib.ptr(tt[0, first:first + count].contiguous()),
+                                                 _lib.ptr(tt[1, first:first + count].contiguous()), _lib.ptr(out8), None, _lib.ptr(ws),
+                                                 ws.numel(), _lib.stream_ptr(cuda)), "exact_stats")
+        return out8.cpu().numpy()[:5], logZ
+
+    full, logZ = stats(W, b, c, 0, 1 << n)
+    o = orc.BinaryRBMOracle(W, b, c)
+    space = ((np.arange(1 << n)[:, None] >> np.arange(n - 1, -1, -1)) & 1).astype(np.float64)
+    p = np.exp(-o.effective_energy(space) - logZ)
+    eps = 2.0 ** -52
+    pt = t[0] ** 2 + t[1] ** 2
+    want = np.array([np.sum(t[0] * np.sqrt(p)), np.sum(t[1] * np.sqrt(p)), np.sum(pt * np.log(np.clip(pt, eps, 1 - eps))),
+                     np.sum(pt * np.log(np.clip(p, eps, 1 - eps))), np.sum(p)])
+    assert_close(full, want, what="five sums vs numpy")
+    cuts = [0, 1, 37, 1000, 4097, 8190, 1 << n]
+    parts = sum(stats(W, b, c, lo, hi - lo)[0] for lo, hi in zip(cuts[:-1], cuts[1:]))
+    assert_close(parts, full, what="range additivity of the five sums")
+    # a huge visible bias makes e^{b.v} overflow the pre-check -> log-domain kernel; the distribution collapses but stays finite
+    b_big = b.copy()
+    b_big[0] = 700.0
+    slow, logZ_big = stats(W, b_big, c, 0, 1 << n)
+    o_big = orc.BinaryRBMOracle(W, b_big, c)
+    p_big = np.exp(-o_big.effective_energy(space) - logZ_big)
+    want_big = np.array([np.sum(t[0] * np.sqrt(p_big)), np.sum(t[1] * np.sqrt(p_big)), want[2],
+                         np.sum(pt * np.log(np.clip(p_big, eps, 1 - eps))), np.sum(p_big)])
+    assert_close(slow, want_big, what="five sums, log-domain fallback")
+
+
+def test_small_and_trivial_shapes(lib, cuda):
+    """Degenerate sizes: a fused epoch of one batch of one row with k = 0, rotations of a single qubit and of an
+    all-identity basis, KL terms of a single element."""
+    from qucumber_b200 import _lib
+    from qucumber_b200.utils import training_statistics as ts
+    from qucumber_b200.utils.unitaries import _kron_apply, create_dict
+
+    W, b, c = make_binary_params(3, 2, 311)
+    o = orc.BinaryRBMOracle(W, b, c)
+    pos, neg = random_states(1, 3, 312), random_states(1, 3, 313)
+    g = o.effective_energy_gradient(pos) - o.effective_energy_gradient(neg)   # k = 0: v_k is the negative row itself
+    tW, tb, tc = (torch.tensor(x, device=cuda) for x in (W, b, c))
+    _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), 3, 2, _lib.ptr(torch.tensor(pos, device=cuda)), 1, 1,
+                                    _lib.ptr(torch.tensor(neg, device=cuda)), 1, 1, 1, 0, 0.5, 1, 0, None, _lib.stream_ptr(cuda)),
+               "cd_epoch")
+    assert_close(tW, W - 0.5 * g[:6].reshape(2, 3), what="one-row epoch, weights")
+    assert_close(tc, c - 0.5 * g[9:], what="one-row epoch, hidden bias")
+
+    d = create_dict()
+    x = torch.tensor([[0.6, -0.8], [0.1, 0.2]], device=cuda)  # (2, 2): one qubit, re / im planes
+    ux = np.array([[1, 1], [1, -1]]) / np.sqrt(2.0)
+    got = _kron_apply([d["X"]], x).cpu().numpy()
+    assert np.allclose(got[0] + 1j * got[1], ux @ (np.array([0.6, -0.8]) + 1j * np.array([0.1, 0.2])), atol=1e-15)
+    y = torch.randn(2, 8, 3, dtype=torch.double, device=cuda)
+    assert torch.equal(_kron_apply([d["Z"]] * 3, y), y)
+    one = torch.tensor([1.0], device=cuda)
+    assert abs(float(ts._kl_terms(one, None, one * 0.25, None, 0.0)) - (np.log(1 - 2.0 ** -52) - np.log(0.25))) < 1e-15
