@@ -178,6 +178,8 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
  *                       chain_id0 = 0, sweep0 + i*k, 1/B_i, -1/C_i);   W, b, c -= lr * g   (in place)
  * pos (B_total, N) and neg (C_total, N) hold the epoch's batches back to back (the last one may be short).
  * g_last (optional, nh*N + N + nh) receives the gradient of the last step (what param.grad would hold).
+ * lr = 0 leaves W, b, c untouched (never written): with num_batches = 1 the call is the CD-k gradient of one
+ * batch in a single launch, for optimizers and callbacks that act per batch.
  * Same Philox draws as the per-step call, hence the same chains; sums are associated differently
  * (agreement to rounding).  Larger layers return QCB_ERR_UNSUPPORTED: use qcb_rbm_cd_step per batch. */
 int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh,

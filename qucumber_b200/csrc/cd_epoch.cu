@@ -248,13 +248,13 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
       double g = 0.0;
       for (int rk = 0; rk < nranks; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
       double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
-      *prm -= a.lr * g;
+      if (a.lr != 0.0) *prm -= a.lr * g;  // lr = 0: gradient only (qcb_rbm_cd_step semantics in one launch)
       if (rank == 0 && a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
     }
     __syncthreads();
   }
   cluster.sync();  // nobody leaves while its shares may still be read
-  if (rank == 0) {
+  if (rank == 0 && a.lr != 0.0) {
     for (int idx = tid; idx < nh * N; idx += NT) a.W[idx] = Wsm[(idx / N) * LD + idx % N];
     for (int idx = tid; idx < N; idx += NT) a.b[idx] = bsm[idx];
     for (int idx = tid; idx < nh; idx += NT) a.c[idx] = csm[idx];

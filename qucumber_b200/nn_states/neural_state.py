@@ -256,8 +256,20 @@ class NeuralStateBase(abc.ABC):
         if bases_batch is None:
             pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
             B = pos.shape[0]
-            args, keep = rbm._param_args()
             g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
+            if (self.fuse_epochs and na == 0 and rbm.num_visible <= 32 and rbm.num_hidden <= 32 and 0 < B <= 4096
+                    and 0 < C <= 4096 and hasattr(rbm, "weights")):
+                # small RBM, small batch: positive phase, k sweeps and negative phase in ONE cluster launch
+                # (qcb_rbm_cd_epoch with a single batch and lr = 0: parameters untouched, gradient out)
+                _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(rbm.weights.data), _lib.ptr(rbm.visible_bias.data),
+                                                _lib.ptr(rbm.hidden_bias.data), rbm.num_visible, rbm.num_hidden, _lib.ptr(pos), B, B,
+                                                _lib.ptr(neg), C, C, 1, int(k), 0.0, seed, sweep0, _lib.ptr(g),
+                                                _lib.stream_ptr(self.device)), "qcb_rbm_cd_epoch")
+                grad = [g]
+                for net in self.networks[1:]:
+                    grad.append(torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device))
+                return grad
+            args, keep = rbm._param_args()
             ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CD_STEP, rbm.num_visible, rbm.num_hidden, na, max(B, C)))
             _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), B, _lib.ptr(neg), C, int(k), seed, 0, sweep0, 1.0 / float(B),
                                            -1.0 / float(C), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)),
@@ -367,9 +379,9 @@ class NeuralStateBase(abc.ABC):
         optimizer = optimizer(all_params, lr=lr, **(optimizer_args or {}))
         if scheduler is not None:
             scheduler = scheduler(optimizer, **(scheduler_args or {}))
-        # plain SGD without callbacks (nobody can observe .grad or optimizer hooks): fused update path
+        # plain SGD (no momentum / weight decay / hooks): fused multi-tensor update, .grad set only when callbacks can look
         pg = optimizer.param_groups
-        plain_sgd = (type(optimizer) is torch.optim.SGD and len(pg) == 1 and not cbs.callbacks and scheduler is None
+        plain_sgd = (type(optimizer) is torch.optim.SGD and len(pg) == 1 and scheduler is None
                      and pg[0].get("momentum", 0) == 0 and pg[0].get("weight_decay", 0) == 0
                      and pg[0].get("dampening", 0) == 0 and not pg[0].get("nesterov", False)
                      and not pg[0].get("maximize", False))
@@ -386,7 +398,7 @@ class NeuralStateBase(abc.ABC):
             from tqdm import tqdm, tqdm_notebook
 
             epoch_iter = (tqdm_notebook if progbar == "notebook" else tqdm)(epoch_iter, desc="Epochs ")
-        fused_epoch = self._epoch_fusable(optimizer, cbs, input_bases)
+        fused_epoch = scheduler is None and self._epoch_fusable(optimizer, cbs, input_bases)  # schedulers count optimizer.step() calls
         for ep in epoch_iter:
             if fused_epoch:
                 pos, neg, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None)
@@ -410,6 +422,9 @@ class NeuralStateBase(abc.ABC):
                         for prm in net_params[i]:
                             views.append(all_grads[i][offset:offset + prm.numel()].view(prm.size()))
                             offset += prm.numel()
+                    if cbs.callbacks:  # observers find this batch's gradient in .grad, as after optimizer.step()
+                        for prm, view in zip(all_params, views):
+                            prm.grad = view
                     torch._foreach_add_(all_params, views, alpha=-optimizer.param_groups[0]["lr"])
                 else:
                     optimizer.zero_grad()
