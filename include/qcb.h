@@ -172,7 +172,7 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
                     uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale,
                     double* g, void* ws, size_t ws_bytes, void* stream);
 
-/* A whole CD-k epoch with plain SGD in ONE launch, for a small BinaryRBM (1 <= N, nh <= 32): the batch loop of
+/* A whole CD-k epoch with plain SGD in ONE launch, for a small BinaryRBM (1 <= N, nh <= 64): the batch loop of
  * NeuralStateBase.fit (nn_states/neural_state.py:611-627).  For step i = 0 .. num_batches-1:
  *   g = qcb_rbm_cd_step(pos[i*pos_batch : (i+1)*pos_batch], neg[i*neg_batch : (i+1)*neg_batch], k, seed,
  *                       chain_id0 = 0, sweep0 + i*k, 1/B_i, -1/C_i);   W, b, c -= lr * g   (in place)

@@ -1,4 +1,4 @@
-// One launch for a whole contrastive-divergence epoch of a small BinaryRBM (N, nh <= 32, plain SGD).
+// One launch for a whole contrastive-divergence epoch of a small BinaryRBM (N, nh <= 64, plain SGD).
 //
 // Replaces the batch loop of NeuralStateBase.fit (qucumber/nn_states/neural_state.py:611-627): for every
 // batch  g = <grad E>_data / B - <grad E>_{v_k} / C  (compute_batch_gradients, :417-447, with
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
       const double raw = ch0 == 0 ? first_neg : ((valid && u < N) ? neg_rows[(int64_t)ch * N + u] : 0.0);
       uint32_t vm = slot_bits(raw != 0.0);
       const uint32_t cid0 = (uint32_t)ch, cid1 = 0u;
-      for (int s = 0; s < a.k; ++s) {
+      const bool warp_has_chain = __any_sync(0xffffffffu, valid);
+      for (int s = 0; s < (warp_has_chain ? a.k : 0); ++s) {
         const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s);
         const uint32_t qv0 = 4u * (uint32_t)((nh + 31) / 32);
         const uint32_t cell_h = ce_cell(u, 0u, cid0, cid1, sweep, a.key0, a.key1);
@@ -261,13 +262,217 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
   }
 }
 
-template <int SW>
-static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
-  constexpr int NT = ce_threads(SW);
-  const size_t smem = ce_smem_doubles(a.N, a.nh, SW, NT / 32) * sizeof(double);
+// ---- layers of 33 .. 64 units ------------------------------------------------------------------------
+// Same scheme with one chain per warp and two units per lane (u and u + 32).  A lane cannot keep a row of the
+// gradient in registers any more, so after every round the warps park (w p, v, w) of their row in shared memory
+// and all threads add the round's outer products to the gradient entries they own (17 per thread).  The step's
+// gradient is reduce-scattered and all-gathered across the cluster through distributed shared memory
+// (two cluster barriers per step), and every CTA applies the identical update to its copy of W, b, c.
+constexpr int CEW_THREADS = 512, CEW_WARPS = CEW_THREADS / 32, CEW_LD = 65, CEW_GMAX = 64 * 64 + 128;
+constexpr int CEW_EPT = (CEW_GMAX + CEW_THREADS - 1) / CEW_THREADS;  // gradient entries owned by a thread
+static_assert(CEW_EPT * CEW_THREADS >= CEW_GMAX, "every gradient entry needs an owner");
+
+__host__ __device__ inline size_t cew_smem_doubles() {
+  // W (64 x 65) | b (64) | c (64) | parked rows (warps x 64) | row weights | row masks | own share (G) | reduced slice (<= G / 8)
+  return (size_t)64 * CEW_LD + 64 + 64 + CEW_WARPS * 64 + CEW_WARPS + CEW_WARPS + CEW_GMAX + (CEW_GMAX + 7) / 8 + 8;
+}
+
+__global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdEpochArgs a) {
+  extern __shared__ __align__(16) double ce_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
+  const int N = a.N, nh = a.nh, G = nh * N + N + nh;
+  double* Wsm = ce_smem;
+  double* bsm = Wsm + 64 * CEW_LD;
+  double* csm = bsm + 64;
+  double* Prow = csm + 64;
+  double* wts = Prow + CEW_WARPS * 64;
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(wts + CEW_WARPS);
+  double* Gpart = reinterpret_cast<double*>(masks + CEW_WARPS);
+  double* Gred = Gpart + CEW_GMAX;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = rank * CEW_WARPS + warp, nslots = nranks * CEW_WARPS;
+  const int u0 = lane, u1 = lane + 32;
+  const int slice = (G + nranks - 1) / nranks;  // gradient entries reduced by one CTA
+
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
+  for (int idx = tid; idx < 64 * CEW_LD; idx += CEW_THREADS) Wsm[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < nh * N; idx += CEW_THREADS) Wsm[(idx / N) * CEW_LD + idx % N] = a.W[idx];
+  for (int idx = tid; idx < 64; idx += CEW_THREADS) {
+    bsm[idx] = idx < N ? a.b[idx] : 0.0;
+    csm[idx] = idx < nh ? a.c[idx] : 0.0;
+  }
+  __syncthreads();
+
+  // pre-activations of this lane's two hidden (visible) units; padded rows / columns of W are zero
+  auto hidden_pre2 = [&](unsigned long long vm, double& x0, double& x1) {
+    const double* r0 = Wsm + u0 * CEW_LD;
+    const double* r1 = Wsm + u1 * CEW_LD;
+    const uint32_t lo = (uint32_t)vm, hi = (uint32_t)(vm >> 32);
+    double s0[4] = {csm[u0], 0.0, 0.0, 0.0}, s1[4] = {csm[u1], 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {  // fully unrolled: predicated adds, no branches
+      if ((lo >> j) & 1u) { s0[j & 3] += r0[j]; s1[j & 3] += r1[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((hi >> j) & 1u) { s0[j & 3] += r0[32 + j]; s1[j & 3] += r1[32 + j]; }
+    }
+    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
+    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+  };
+  auto visible_pre2 = [&](unsigned long long hm, double& x0, double& x1) {
+    const double* c0 = Wsm + u0;
+    const double* c1 = Wsm + u1;
+    const uint32_t lo = (uint32_t)hm, hi = (uint32_t)(hm >> 32);
+    double s0[4] = {bsm[u0], 0.0, 0.0, 0.0}, s1[4] = {bsm[u1], 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((lo >> i) & 1u) { s0[i & 3] += c0[i * CEW_LD]; s1[i & 3] += c1[i * CEW_LD]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((hi >> i) & 1u) { s0[i & 3] += c0[(32 + i) * CEW_LD]; s1[i & 3] += c1[(32 + i) * CEW_LD]; }
+    }
+    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
+    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+  };
+  auto mask64 = [&](bool b0, bool b1) {
+    return (unsigned long long)__ballot_sync(0xffffffffu, b0) | ((unsigned long long)__ballot_sync(0xffffffffu, b1) << 32);
+  };
+  auto load_row = [&](const double* rows, int64_t r, bool valid) {
+    const double a0 = (valid && u0 < N) ? rows[r * N + u0] : 0.0;
+    const double a1 = (valid && u1 < N) ? rows[r * N + u1] : 0.0;
+    return mask64(a0 != 0.0, a1 != 0.0);
+  };
+  // a Bernoulli draw for units u0, u1 of one layer: float filter, exact cold path
+  auto draw2 = [&](double x0, double x1, int n_units, uint32_t q0, uint32_t cid0, uint32_t sweep) {
+    const uint32_t cell0 = ce_cell(u0, q0, cid0, 0u, sweep, a.key0, a.key1);
+    const uint32_t cell1 = ce_cell(u1, q0, cid0, 0u, sweep, a.key0, a.key1);
+    int v0 = ce_filter(x0, cell0), v1 = ce_filter(x1, cell1);
+    v0 = u0 < n_units ? v0 : 0;
+    v1 = u1 < n_units ? v1 : 0;
+    if (__any_sync(0xffffffffu, v0 == 2 || v1 == 2)) {
+      if (v0 == 2) v0 = ce_decide_exact(x0, cell0, u0, q0, cid0, 0u, sweep, a.key0, a.key1) ? 1 : 0;
+      if (v1 == 2) v1 = ce_decide_exact(x1, cell1, u1, q0, cid0, 0u, sweep, a.key0, a.key1) ? 1 : 0;
+      __syncwarp();
+    }
+    return mask64(v0 == 1, v1 == 1);
+  };
+
+  for (int step = 0; step < a.num_batches; ++step) {
+    const int64_t p0 = (int64_t)step * a.pos_batch, c0 = (int64_t)step * a.neg_batch;
+    const int Bs = (int)(a.B_total - p0 < a.pos_batch ? a.B_total - p0 : a.pos_batch);
+    const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
+    const double* pos_rows = a.pos + p0 * N;
+    const double* neg_rows = a.neg + c0 * N;
+    double gacc[CEW_EPT];
+#pragma unroll
+    for (int e = 0; e < CEW_EPT; ++e) gacc[e] = 0.0;
+
+    // the warp's row: (w p, v, w) to shared memory; then every thread adds the round to its entries
+    auto park = [&](unsigned long long vm, bool valid, double weight) {
+      double x0, x1;
+      hidden_pre2(vm, x0, x1);
+      Prow[warp * 64 + u0] = (valid && u0 < nh) ? weight * sigmoid_tab(x0, e2tab) : 0.0;
+      Prow[warp * 64 + u1] = (valid && u1 < nh) ? weight * sigmoid_tab(x1, e2tab) : 0.0;
+      if (lane == 0) {
+        wts[warp] = valid ? weight : 0.0;
+        masks[warp] = valid ? vm : 0ull;
+      }
+    };
+    auto accumulate_round = [&]() {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < CEW_EPT; ++e) {
+        const int idx = tid + CEW_THREADS * e;
+        if (idx < G) {
+          double g = 0.0;
+          if (idx < nh * N) {
+            const int i = idx / N, j = idx - i * N;
+#pragma unroll
+            for (int r = 0; r < CEW_WARPS; ++r)
+              if ((masks[r] >> j) & 1ull) g += Prow[r * 64 + i];
+          } else if (idx < nh * N + N) {
+            const int j = idx - nh * N;
+#pragma unroll
+            for (int r = 0; r < CEW_WARPS; ++r)
+              if ((masks[r] >> j) & 1ull) g += wts[r];
+          } else {
+            const int i = idx - nh * N - N;
+#pragma unroll
+            for (int r = 0; r < CEW_WARPS; ++r) g += Prow[r * 64 + i];
+          }
+          gacc[e] += g;
+        }
+      }
+      __syncthreads();
+    };
+
+    for (int r0 = 0; r0 < Bs; r0 += nslots) {  // positive phase: grad E(v) = -[p v^T ; v ; p], weight -1/B
+      const int r = r0 + slot;
+      const bool valid = r < Bs;
+      park(load_row(pos_rows, r, valid), valid, -1.0 / (double)Bs);
+      accumulate_round();
+    }
+    for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {  // negative phase: k sweeps, then weight +1/C
+      const int ch = ch0 + slot;
+      const bool valid = ch < Cs;
+      unsigned long long vm = load_row(neg_rows, ch, valid);
+      const uint32_t qv0 = 4u * (uint32_t)((nh + 31) / 32);
+      for (int s = 0; s < (valid ? a.k : 0); ++s) {  // a warp without a chain in this round sits the sweeps out
+        const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s);
+        double x0, x1;
+        hidden_pre2(vm, x0, x1);
+        const unsigned long long hm = draw2(x0, x1, nh, 0u, (uint32_t)ch, sweep);
+        visible_pre2(hm, x0, x1);
+        vm = draw2(x0, x1, N, qv0, (uint32_t)ch, sweep);
+      }
+      park(vm, valid, 1.0 / (double)Cs);
+      accumulate_round();
+    }
+
+    // own share -> shared memory; slice `rank` of the cluster sum; everybody pulls all slices
+#pragma unroll
+    for (int e = 0; e < CEW_EPT; ++e) {
+      const int idx = tid + CEW_THREADS * e;
+      if (idx < G) Gpart[idx] = gacc[e];
+    }
+    cluster.sync();
+    const int lo = rank * slice, hi = lo + slice < G ? lo + slice : G;
+    for (int idx = lo + tid; idx < hi; idx += CEW_THREADS) {
+      double g = 0.0;
+      for (int rk = 0; rk < nranks; ++rk) g += cluster.map_shared_rank(Gpart, rk)[idx];
+      Gred[idx - lo] = g;
+      if (a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
+    }
+    cluster.sync();
+    if (a.lr != 0.0) {
+      for (int idx = tid; idx < G; idx += CEW_THREADS) {
+        const int owner = idx / slice;
+        const double g = cluster.map_shared_rank(Gred, owner)[idx - owner * slice];
+        double* prm = idx < nh * N ? &Wsm[(idx / N) * CEW_LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
+        *prm -= a.lr * g;
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync();  // nobody leaves while its shares may still be read
+  if (rank == 0 && a.lr != 0.0) {
+    for (int idx = tid; idx < nh * N; idx += CEW_THREADS) a.W[idx] = Wsm[(idx / N) * CEW_LD + idx % N];
+    for (int idx = tid; idx < N; idx += CEW_THREADS) a.b[idx] = bsm[idx];
+    for (int idx = tid; idx < nh; idx += CEW_THREADS) a.c[idx] = csm[idx];
+  }
+}
+
+// One cluster per launch: 16 CTAs (non-portable size) when the device can co-schedule them, else the portable 8.
+template <typename Kernel>
+static int launch_one_cluster(Kernel kernel, int threads, size_t smem, const CdEpochArgs& a, cudaStream_t st, int* cluster_cache) {
   if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: layer too large for the fused epoch kernel");
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -276,33 +481,43 @@ static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // one cluster; 16 CTAs (non-portable size) when the device can co-schedule them, else the portable 8
-  static int cluster_on[QCB_MAX_DEVICES] = {0};  // cached per device
-  int& cluster_size = cluster_on[device_slot()];
+  int& cluster_size = cluster_cache[device_slot()];  // cached per device
   if (cluster_size == 0) {
-    QCB_CUDA(cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cluster_size = CE_CLUSTER_PORTABLE;
-    if (cudaFuncSetAttribute(cd_epoch_kernel<SW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       int nclusters = 0;
       cfg.gridDim = dim3(CE_CLUSTER_MAX, 1, 1);
       attr[0].val.clusterDim.x = CE_CLUSTER_MAX;
       cfg.dynamicSmemBytes = 200 * 1024;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, cd_epoch_kernel<SW>, &cfg) == cudaSuccess && nclusters >= 1) cluster_size = CE_CLUSTER_MAX;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) == cudaSuccess && nclusters >= 1) cluster_size = CE_CLUSTER_MAX;
       cfg.dynamicSmemBytes = smem;
     }
     (void)cudaGetLastError();
   }
   cfg.gridDim = dim3(cluster_size, 1, 1);
   attr[0].val.clusterDim.x = cluster_size;
-  QCB_CUDA(cudaLaunchKernelEx(&cfg, cd_epoch_kernel<SW>, a));
+  QCB_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   QCB_LAUNCH_CHECK();
   return QCB_OK;
+}
+
+template <int SW>
+static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
+  constexpr int NT = ce_threads(SW);
+  static int cluster_on[QCB_MAX_DEVICES] = {0};
+  return launch_one_cluster(cd_epoch_kernel<SW>, NT, ce_smem_doubles(a.N, a.nh, SW, NT / 32) * sizeof(double), a, st, cluster_on);
+}
+
+static int launch_cd_epoch_wide(const CdEpochArgs& a, cudaStream_t st) {
+  static int cluster_on[QCB_MAX_DEVICES] = {0};
+  return launch_one_cluster(cd_epoch_wide_kernel, CEW_THREADS, cew_smem_doubles() * sizeof(double), a, st, cluster_on);
 }
 
 int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch, const double* neg,
                  int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last,
                  cudaStream_t st) {
-  if (N < 1 || nh < 1 || N > 32 || nh > 32) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: needs 1 <= N, nh <= 32");
+  if (N < 1 || nh < 1 || N > 64 || nh > 64) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: needs 1 <= N, nh <= 64");
   if (W == nullptr || b == nullptr || c == nullptr || pos == nullptr || neg == nullptr || pos_batch < 1 || neg_batch < 1 ||
       num_batches < 0 || k < 0)
     return fail(QCB_ERR_BAD_ARG, "cd_epoch: bad arguments");
@@ -327,7 +542,8 @@ int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* p
   const int m = N > nh ? N : nh;
   if (m <= 8) return launch_cd_epoch<8>(a, st);
   if (m <= 16) return launch_cd_epoch<16>(a, st);
-  return launch_cd_epoch<32>(a, st);
+  if (m <= 32) return launch_cd_epoch<32>(a, st);
+  return launch_cd_epoch_wide(a, st);
 }
 
 }  // namespace qcb

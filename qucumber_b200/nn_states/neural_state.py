@@ -257,7 +257,7 @@ class NeuralStateBase(abc.ABC):
             pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
             B = pos.shape[0]
             g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
-            if (self.fuse_epochs and na == 0 and rbm.num_visible <= 32 and rbm.num_hidden <= 32 and 0 < B <= 4096
+            if (self.fuse_epochs and na == 0 and rbm.num_visible <= 64 and rbm.num_hidden <= 64 and 0 < B <= 4096
                     and 0 < C <= 4096 and hasattr(rbm, "weights")):
                 # small RBM, small batch: positive phase, k sweeps and negative phase in ONE cluster launch
                 # (qcb_rbm_cd_epoch with a single batch and lr = 0: parameters untouched, gradient out)
@@ -327,7 +327,7 @@ class NeuralStateBase(abc.ABC):
         pg = optimizer.param_groups
         rbm = getattr(self, "rbm_am", None)
         if not (self.fuse_epochs and input_bases is None and list(self.networks) == ["rbm_am"] and type(rbm) is BinaryRBM
-                and rbm.num_visible <= 32 and rbm.num_hidden <= 32):
+                and rbm.num_visible <= 64 and rbm.num_hidden <= 64):
             return False
         if not (type(optimizer) is torch.optim.SGD and len(pg) == 1 and pg[0].get("momentum", 0) == 0
                 and pg[0].get("weight_decay", 0) == 0 and pg[0].get("dampening", 0) == 0 and not pg[0].get("nesterov", False)

@@ -257,7 +257,8 @@ def test_cd_step_matches_oracle_philox(lib, cuda):
 
 
 @pytest.mark.parametrize("n,nh,B,C,pb,nb_,k", [(7, 5, 53, 90, 10, 17, 2), (10, 10, 230, 460, 100, 200, 3), (20, 30, 64, 64, 16, 16, 2),
-                                                (32, 32, 40, 40, 40, 40, 1)])
+                                                (32, 32, 40, 40, 40, 40, 1), (48, 40, 300, 520, 100, 200, 2),
+                                                (64, 64, 260, 260, 130, 130, 2), (33, 64, 50, 70, 25, 35, 1), (64, 33, 9, 9, 4, 4, 3)])
 def test_cd_epoch_matches_oracle(lib, cuda, n, nh, B, C, pb, nb_, k):
     """qcb_rbm_cd_epoch (a whole epoch of CD-k + SGD in one launch) == the oracle's batch loop:
     g_i = <grad E>_pos_i / B_i - <grad E>_{v_k} / C_i with v_k from the Philox stream (chain id = row of
@@ -293,8 +294,8 @@ def test_cd_epoch_matches_oracle(lib, cuda, n, nh, B, C, pb, nb_, k):
 def test_cd_epoch_rejects_large_layers(lib, cuda):
     from qucumber_b200 import _lib
 
-    z = torch.zeros(64 * 64, dtype=torch.double, device=cuda)
-    rc = lib.qcb_rbm_cd_epoch(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 64, 64, _lib.ptr(z), 4, 2, _lib.ptr(z), 4, 2, 2, 1, 0.1, 1, 0, None,
+    z = torch.zeros(65 * 65, dtype=torch.double, device=cuda)
+    rc = lib.qcb_rbm_cd_epoch(_lib.ptr(z), _lib.ptr(z), _lib.ptr(z), 65, 65, _lib.ptr(z), 4, 2, _lib.ptr(z), 4, 2, 2, 1, 0.1, 1, 0, None,
                               _lib.stream_ptr(cuda))
     assert rc != 0 and b"cd_epoch" in lib.qcb_last_error()
 
