@@ -48,7 +48,7 @@ struct CdEpochArgs {
   double* g_last;  // optional (nh*N + N + nh): gradient of the last batch
 };
 
-__host__ __device__ constexpr int ce_threads(int) { return 256; }
+__host__ __device__ constexpr int ce_threads(int SW) { return SW == 32 ? 512 : 256; }
 
 // shared memory: W (nh x LD), b, c, the CTA's gradient share (2 x G, read by the other CTAs), per-warp shares (warps x G)
 __host__ __device__ inline size_t ce_smem_doubles(int N, int nh, int SW, int warps) {
