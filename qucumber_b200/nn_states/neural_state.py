@@ -187,11 +187,18 @@ class NeuralStateBase(abc.ABC):
         if samples.dim() < 2:
             samples = samples.unsqueeze(0)
             bases = np.array(list(bases)).reshape(1, -1)
+        # group the rows by basis on the host, gather them ONCE on the device (a boolean-mask index per basis would
+        # synchronise the stream every time): after the gather each basis owns a contiguous slice
         unique_bases, indices = np.unique(bases, axis=0, return_inverse=True)
-        indices = torch.as_tensor(np.asarray(indices).reshape(-1), device=samples.device)
+        indices = np.asarray(indices).reshape(-1)
+        order = np.argsort(indices, kind="stable")
+        counts = np.bincount(indices, minlength=unique_bases.shape[0])
+        grouped = samples.index_select(0, torch.as_tensor(order, device=samples.device))
+        start = 0
         for i in range(unique_bases.shape[0]):
             basis = unique_bases[i, :]
-            sub = samples[indices == i, :]
+            sub = grouped[start:start + int(counts[i]), :]
+            start += int(counts[i])
             if np.any(basis != "Z"):
                 self._accumulate_rotated_gradient(basis, sub, grad[0], grad[1])
             else:

@@ -42,8 +42,22 @@ def encode_basis(basis, unitary_dict):
     return codes, names
 
 
+_table_cache = {}
+
+
 def unitary_table(unitary_dict, names, device):
-    return torch.stack([unitary_dict[n].to(device=device, dtype=torch.double) for n in names]).contiguous()
+    """(K, 2, 2, 2) device table of the dictionary's unitaries in ``names`` order. The training loop asks for the
+    same table for every basis of every batch, so it is cached per (dictionary contents, device): the key holds
+    each tensor's identity and version counter, i.e. an in-place edit or a replaced entry builds a new table."""
+    key = (str(device), tuple((n, id(unitary_dict[n]), unitary_dict[n]._version) for n in names))
+    hit = _table_cache.get(key)
+    if hit is None:
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        hit = torch.stack([unitary_dict[n].to(dtype=torch.double) for n in names]).to(device).contiguous()
+        _table_cache[key] = (hit, [unitary_dict[n] for n in names])  # keep the sources alive: ids stay unique
+        return hit
+    return hit[0]
 
 
 def _kron_apply(us, x):
