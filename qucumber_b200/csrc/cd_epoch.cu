@@ -80,6 +80,18 @@ __device__ __forceinline__ int ce_filter(double x, uint32_t h16) {
   return fabsf(xf) <= 64.0f ? verdict : 2;
 }
 
+// The same filter for a pre-activation that was itself accumulated in float: `margin` = a quarter of the bound on
+// |x~ - x| plus the 2^-17 of the float sigmoid.
+__device__ __forceinline__ int ce_filter_f(float xf, uint32_t h16, float margin) {
+  float e, pf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xf * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pf) : "f"(1.0f + e));
+  const float lof = (float)h16 * 0x1.0p-16f;
+  const bool sure1 = pf - margin >= lof + 0x1.0p-16f, sure0 = pf + margin <= lof;
+  const int verdict = sure1 ? 1 : (sure0 ? 0 : 2);
+  return fabsf(xf) <= 64.0f ? verdict : 2;
+}
+
 // Cold path: the exact FP64 comparison  u < sigmoid(x)  with the full 53-bit uniform.
 __device__ __noinline__ bool ce_decide_exact(double x, uint32_t h16, int u, uint32_t q0, uint32_t cid0, uint32_t cid1, uint32_t sweep,
                                              uint32_t key0, uint32_t key1) {
@@ -274,7 +286,8 @@ static_assert(CEW_EPT * CEW_THREADS >= CEW_GMAX, "every gradient entry needs an 
 
 __host__ __device__ inline size_t cew_smem_doubles() {
   // W (64 x 65) | b (64) | c (64) | parked rows (warps x 64) | row weights | row masks | own share (G) | reduced slice (<= G / 8)
-  return (size_t)64 * CEW_LD + 64 + 64 + CEW_WARPS * 64 + CEW_WARPS + CEW_WARPS + CEW_GMAX + (CEW_GMAX + 7) / 8 + 8;
+  // ... | float copies of W, b, c and the per-unit filter margins (64 x 65 + 4 x 64 floats)
+  return (size_t)64 * CEW_LD + 64 + 64 + CEW_WARPS * 64 + CEW_WARPS + CEW_WARPS + CEW_GMAX + (CEW_GMAX + 7) / 8 + 8 + (64 * CEW_LD + 4 * 64 + 1) / 2;
 }
 
 __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdEpochArgs a) {
@@ -290,6 +303,11 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
   unsigned long long* masks = reinterpret_cast<unsigned long long*>(wts + CEW_WARPS);
   double* Gpart = reinterpret_cast<double*>(masks + CEW_WARPS);
   double* Gred = Gpart + CEW_GMAX;
+  float* Wf = reinterpret_cast<float*>(Gred + (CEW_GMAX + 7) / 8 + 8);  // float image of W for the filter
+  float* bf = Wf + 64 * CEW_LD;
+  float* cf = bf + 64;
+  float* mrg_h = cf + 64;  // filter margins per hidden / visible unit
+  float* mrg_v = mrg_h + 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = rank * CEW_WARPS + warp, nslots = nranks * CEW_WARPS;
   const int u0 = lane, u1 = lane + 32;
@@ -339,6 +357,56 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
     x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
     x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
   };
+  // Float image and margins, rebuilt whenever the parameters change.  x~ (float sum of float-rounded weights) obeys
+  // |x~ - x| <= (n_in + 3) 2^-24 (|bias| + sum |w|) =: dx, so |sigmoid(x~) - sigmoid(x)| <= dx / 4; 2^-17 covers the
+  // float evaluation of the sigmoid itself (ce_filter).  Units the filter leaves open are redone in FP64.
+  auto refresh_float = [&]() {
+    for (int idx = tid; idx < 64 * CEW_LD; idx += CEW_THREADS) Wf[idx] = (float)Wsm[idx];
+    for (int idx = tid; idx < 64; idx += CEW_THREADS) { bf[idx] = (float)bsm[idx]; cf[idx] = (float)csm[idx]; }
+    if (tid < 64) {
+      double S = fabs(csm[tid]);
+      for (int j = 0; j < 64; ++j) S += fabs(Wsm[tid * CEW_LD + j]);
+      mrg_h[tid] = (float)(((N + 3) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
+    } else if (tid < 128) {
+      const int j = tid - 64;
+      double S = fabs(bsm[j]);
+      for (int i = 0; i < 64; ++i) S += fabs(Wsm[i * CEW_LD + j]);
+      mrg_v[j] = (float)(((nh + 3) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
+    }
+    __syncthreads();
+  };
+  auto hidden_pre2_f = [&](unsigned long long vm, float& x0, float& x1) {
+    const float* r0 = Wf + u0 * CEW_LD;
+    const float* r1 = Wf + u1 * CEW_LD;
+    const uint32_t lo = (uint32_t)vm, hi = (uint32_t)(vm >> 32);
+    float s0[4] = {cf[u0], 0.0f, 0.0f, 0.0f}, s1[4] = {cf[u1], 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((lo >> j) & 1u) { s0[j & 3] += r0[j]; s1[j & 3] += r1[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((hi >> j) & 1u) { s0[j & 3] += r0[32 + j]; s1[j & 3] += r1[32 + j]; }
+    }
+    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
+    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+  };
+  auto visible_pre2_f = [&](unsigned long long hm, float& x0, float& x1) {
+    const float* c0 = Wf + u0;
+    const float* c1 = Wf + u1;
+    const uint32_t lo = (uint32_t)hm, hi = (uint32_t)(hm >> 32);
+    float s0[4] = {bf[u0], 0.0f, 0.0f, 0.0f}, s1[4] = {bf[u1], 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((lo >> i) & 1u) { s0[i & 3] += c0[i * CEW_LD]; s1[i & 3] += c1[i * CEW_LD]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((hi >> i) & 1u) { s0[i & 3] += c0[(32 + i) * CEW_LD]; s1[i & 3] += c1[(32 + i) * CEW_LD]; }
+    }
+    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
+    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+  };
   auto mask64 = [&](bool b0, bool b1) {
     return (unsigned long long)__ballot_sync(0xffffffffu, b0) | ((unsigned long long)__ballot_sync(0xffffffffu, b1) << 32);
   };
@@ -347,20 +415,28 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
     const double a1 = (valid && u1 < N) ? rows[r * N + u1] : 0.0;
     return mask64(a0 != 0.0, a1 != 0.0);
   };
-  // a Bernoulli draw for units u0, u1 of one layer: float filter, exact cold path
-  auto draw2 = [&](double x0, double x1, int n_units, uint32_t q0, uint32_t cid0, uint32_t sweep) {
+  // a Bernoulli draw for units u0, u1 of one layer from the state `in`: float pre-activations and filter; if any lane
+  // of the warp is left undecided the warp recomputes the FP64 pre-activations and those lanes take the exact path
+  auto draw2 = [&](unsigned long long in, bool hidden_layer, uint32_t q0, uint32_t cid0, uint32_t sweep) {
+    const int n_units = hidden_layer ? nh : N;
+    const float* mrg = hidden_layer ? mrg_h : mrg_v;
+    float xf0, xf1;
+    if (hidden_layer) hidden_pre2_f(in, xf0, xf1); else visible_pre2_f(in, xf0, xf1);
     const uint32_t cell0 = ce_cell(u0, q0, cid0, 0u, sweep, a.key0, a.key1);
     const uint32_t cell1 = ce_cell(u1, q0, cid0, 0u, sweep, a.key0, a.key1);
-    int v0 = ce_filter(x0, cell0), v1 = ce_filter(x1, cell1);
+    int v0 = ce_filter_f(xf0, cell0, mrg[u0]), v1 = ce_filter_f(xf1, cell1, mrg[u1]);
     v0 = u0 < n_units ? v0 : 0;
     v1 = u1 < n_units ? v1 : 0;
     if (__any_sync(0xffffffffu, v0 == 2 || v1 == 2)) {
+      double x0, x1;
+      if (hidden_layer) hidden_pre2(in, x0, x1); else visible_pre2(in, x0, x1);
       if (v0 == 2) v0 = ce_decide_exact(x0, cell0, u0, q0, cid0, 0u, sweep, a.key0, a.key1) ? 1 : 0;
       if (v1 == 2) v1 = ce_decide_exact(x1, cell1, u1, q0, cid0, 0u, sweep, a.key0, a.key1) ? 1 : 0;
       __syncwarp();
     }
     return mask64(v0 == 1, v1 == 1);
   };
+  refresh_float();
 
   for (int step = 0; step < a.num_batches; ++step) {
     const int64_t p0 = (int64_t)step * a.pos_batch, c0 = (int64_t)step * a.neg_batch;
@@ -424,11 +500,8 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
       const uint32_t qv0 = 4u * (uint32_t)((nh + 31) / 32);
       for (int s = 0; s < (valid ? a.k : 0); ++s) {  // a warp without a chain in this round sits the sweeps out
         const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s);
-        double x0, x1;
-        hidden_pre2(vm, x0, x1);
-        const unsigned long long hm = draw2(x0, x1, nh, 0u, (uint32_t)ch, sweep);
-        visible_pre2(hm, x0, x1);
-        vm = draw2(x0, x1, N, qv0, (uint32_t)ch, sweep);
+        const unsigned long long hm = draw2(vm, true, 0u, (uint32_t)ch, sweep);
+        vm = draw2(hm, false, qv0, (uint32_t)ch, sweep);
       }
       park(vm, valid, 1.0 / (double)Cs);
       accumulate_round();
@@ -458,6 +531,7 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
       }
     }
     __syncthreads();
+    if (a.lr != 0.0 && step + 1 < a.num_batches) refresh_float();
   }
   cluster.sync();  // nobody leaves while its shares may still be read
   if (rank == 0 && a.lr != 0.0) {
