@@ -448,7 +448,11 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
                 p.N, nhid);
   const size_t need = gibbs_workspace_bytes(p.N, nhid);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, need);
-  if (C == 0 || k == 0) return QCB_OK;
+  if (C == 0) return QCB_OK;
+  if (k == 0) {  // no sweep: v_k is the initial state (out-of-place callers still expect it in v)
+    if (v != v_in) QCB_CUDA(cudaMemcpyAsync(v, v_in, (size_t)C * p.N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return QCB_OK;
+  }
   if (sweep0 + (uint64_t)k > (1ull << 32))
     return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
   if (uniforms == nullptr && g_gibbs_mode == 0) {

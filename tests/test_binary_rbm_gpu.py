@@ -534,3 +534,46 @@ def test_one_process_two_devices(lib, cuda):
         assert torch.cuda.current_device() == 0
     for a, b_ in zip(*outs):
         assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("n,nh,scale", [(12, 9, 3.0), (40, 36, 1.5), (64, 64, 0.6), (30, 30, 40.0)])
+def test_cd_epoch_large_weights(lib, cuda, n, nh, scale):
+    """Strong couplings (pre-activations of tens to thousands): the epoch kernels' float filters must hand the
+    undecided and the out-of-range units to the exact path, i.e. the chains stay those of the oracle."""
+    from qucumber_b200 import _lib
+
+    W, b, c = make_binary_params(n, nh, 500 + n, bias_scale=1.0, weight_scale=scale)
+    pos, neg = random_states(120, n, 501), random_states(150, n, 502)
+    k, seed = 3, 31
+    o = BinaryRBMOracle(W, b, c)
+    vk = o.gibbs_steps_philox(k, neg, seed=seed, chain_id0=0, sweep0=4)
+    with np.errstate(over="ignore"):
+        want = o.effective_energy_gradient(pos) / len(pos) - o.effective_energy_gradient(vk) / len(neg)
+    tW, tb, tc = (torch.tensor(x, device=cuda) for x in (W, b, c))
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)  # named: they must outlive the asynchronous call
+    g = torch.empty(nh * n + n + nh, dtype=torch.double, device=cuda)
+    _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), n, nh, _lib.ptr(tp), 120, 120, _lib.ptr(tn), 150, 150, 1, k,
+                                    0.0, seed, 4, _lib.ptr(g), _lib.stream_ptr(cuda)), "qcb_rbm_cd_epoch")
+    assert_close(g, want, what="CD-k gradient from the fused kernel (lr = 0)")
+    assert np.array_equal(tW.cpu().numpy(), W) and np.array_equal(tb.cpu().numpy(), b) and np.array_equal(tc.cpu().numpy(), c)
+
+
+def test_cd_step_with_zero_sweeps(lib, cuda):
+    """k = 0: the negative phase is evaluated at the negative batch itself (v_k = v_0), also through the out-of-place
+    path of qcb_rbm_cd_step / qcb_rbm_cdk_neg."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, B, C = 11, 6, 40, 70
+    W, b, c = make_binary_params(n, nh, 601)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    pos, neg = random_states(B, n, 602), random_states(C, n, 603)
+    want = o.effective_energy_gradient(pos) / B - o.effective_energy_gradient(neg) / C
+    args, keep = rbm._param_args()
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+    g = torch.empty(rbm.num_pars, dtype=torch.double, device=cuda)
+    ws = _lib.workspace(cuda, _lib.workspace_bytes(_lib.OP_CD_STEP, n, nh, 0, max(B, C)))
+    ws.fill_(255)  # stale workspace contents must not leak into the result
+    _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, 0, 1, 0, 0, 1.0 / B, -1.0 / C, _lib.ptr(g), _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    assert_close(g, want, what="CD-0 gradient")

@@ -653,9 +653,9 @@ def test_small_and_trivial_shapes(lib, cuda):
     pos, neg = random_states(1, 3, 312), random_states(1, 3, 313)
     g = o.effective_energy_gradient(pos) - o.effective_energy_gradient(neg)   # k = 0: v_k is the negative row itself
     tW, tb, tc = (torch.tensor(x, device=cuda) for x in (W, b, c))
-    _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), 3, 2, _lib.ptr(torch.tensor(pos, device=cuda)), 1, 1,
-                                    _lib.ptr(torch.tensor(neg, device=cuda)), 1, 1, 1, 0, 0.5, 1, 0, None, _lib.stream_ptr(cuda)),
-               "cd_epoch")
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)  # named: they must outlive the asynchronous call
+    _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), 3, 2, _lib.ptr(tp), 1, 1, _lib.ptr(tn), 1, 1, 1, 0, 0.5, 1, 0,
+                                    None, _lib.stream_ptr(cuda)), "cd_epoch")
     assert_close(tW, W - 0.5 * g[:6].reshape(2, 3), what="one-row epoch, weights")
     assert_close(tc, c - 0.5 * g[9:], what="one-row epoch, hidden bias")
 
