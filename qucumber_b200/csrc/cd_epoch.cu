@@ -53,7 +53,7 @@ __host__ __device__ constexpr int ce_threads(int SW) { return SW == 32 ? 512 : 2
 // shared memory: W (nh x LD), b, c, the CTA's gradient share (2 x G, read by the other CTAs), per-warp shares (warps x G)
 __host__ __device__ inline size_t ce_smem_doubles(int N, int nh, int SW, int warps) {
   const int LD = N | 1, G = nh * N + N + nh;
-  return (size_t)SW * LD + N + nh + 2 * (size_t)G + (size_t)warps * G;
+  return (size_t)SW * LD + N + nh + 2 * (size_t)G + (size_t)warps * (G + nh);  // per-warp shares are padded (GP = G + nh at most)
 }
 
 // The 16-bit cell of the unit's uniform for (chain, sweep); q0 = first Philox call of the layer.
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
   constexpr int NT = ce_threads(SW), NW = NT / 32, CPW = 32 / SW;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int N = a.N, nh = a.nh, LD = N | 1, G = nh * N + N + nh;
+  const int N = a.N, nh = a.nh, LD = N | 1, G = nh * N + N + nh, GP = nh * LD + N + nh;
   double* Wsm = ce_smem;
   double* bsm = Wsm + (size_t)SW * LD;  // W region padded to SW rows
   double* csm = bsm + N;
@@ -239,30 +239,44 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
       accb += __shfl_xor_sync(0xffffffffu, accb, off);
       accc += __shfl_xor_sync(0xffffffffu, accc, off);
     }
-    double* mine = wpart + (size_t)warp * G;
+    // per-warp shares: rows of the W part padded to LD (odd) so that the 32 lanes of a warp hit 32 banks
+    double* mine = wpart + (size_t)warp * GP;
     if (sub == 0) {
       if (u < nh) {
 #pragma unroll
         for (int j = 0; j < SW; ++j)
-          if (j < N) mine[u * N + j] = accW[j];
-        mine[nh * N + N + u] = accc;
+          if (j < N) mine[u * LD + j] = accW[j];
+        mine[nh * LD + N + u] = accc;
       }
-      if (u < N) mine[nh * N + u] = accb;
+      if (u < N) mine[nh * LD + u] = accb;
     }
     __syncthreads();
-    double* my_partial = partial + (size_t)(step & 1) * G;
+    double* my_partial = partial;       // this CTA's share of the step's gradient (read by the slice owners)
+    double* my_red = partial + G;       // the slice of the cluster sum this CTA owns (read by everybody)
     for (int idx = tid; idx < G; idx += NT) {
+      const int off = idx < nh * N ? (idx / N) * LD + idx % N : idx - nh * N + nh * LD;
       double t = 0.0;
-      for (int w = 0; w < NW; ++w) t += wpart[(size_t)w * G + idx];
+      for (int w = 0; w < NW; ++w) t += wpart[(size_t)w * GP + off];
       my_partial[idx] = t;
     }
     cluster.sync();
-    for (int idx = tid; idx < G; idx += NT) {
+    // reduce-scatter: CTA `rank` sums slice `rank` over the cluster; all-gather: everybody pulls all slices
+    const int slice = (G + nranks - 1) / nranks;
+    const int lo = rank * slice, hi = lo + slice < G ? lo + slice : G;
+    for (int idx = lo + tid; idx < hi; idx += NT) {
       double g = 0.0;
       for (int rk = 0; rk < nranks; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
-      double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
-      if (a.lr != 0.0) *prm -= a.lr * g;  // lr = 0: gradient only (qcb_rbm_cd_step semantics in one launch)
-      if (rank == 0 && a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
+      my_red[idx - lo] = g;
+      if (a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
+    }
+    cluster.sync();
+    if (a.lr != 0.0) {  // lr = 0: gradient only (qcb_rbm_cd_step semantics in one launch)
+      for (int idx = tid; idx < G; idx += NT) {
+        const int owner = idx / slice;
+        const double g = cluster.map_shared_rank(my_red, owner)[idx - owner * slice];
+        double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
+        *prm -= a.lr * g;
+      }
     }
     __syncthreads();
   }

@@ -9,8 +9,8 @@ from qucumber_b200 import _lib  # noqa: E402
 
 dev = torch.device("cuda")
 lib = _lib.load()
-n = nh = 10
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+n = nh = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 torch.manual_seed(0)
 W = (torch.randn(nh, n, dtype=torch.double) / n ** 0.5).to(dev)
 b = torch.zeros(n, dtype=torch.double, device=dev)
@@ -33,4 +33,4 @@ for _ in range(10):
     run()
 e1.record()
 torch.cuda.synchronize()
-print(f"fused epoch kernel: {e0.elapsed_time(e1) / 10:.3f} ms per epoch of 100 steps (k = {k})")
+print(f"fused epoch kernel N = nh = {n}: {e0.elapsed_time(e1) / 10:.3f} ms per epoch of 100 steps (k = {k})")
