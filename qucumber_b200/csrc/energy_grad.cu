@@ -188,54 +188,220 @@ int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double
 // every local estimator built from psi(v^(i)) / psi(v) needs (SigmaX / SigmaY, TFIM energy:
 // observables/pauli.py:50-83, examples/Tutorial4/quantum_ising_chain.py:45-78).  The reference
 // evaluates the full energy of N flipped copies of the batch; here theta = Wst v + hb is computed
-// once per row and each flip costs nh softplus evaluations of theta_h +- W_hi.
-__global__ void __launch_bounds__(ROWS_THREADS) rows_flip_kernel(AffineSpec s, const double* __restrict__ v,
+// once per row and a flip of unit i changes hidden unit o's softplus by
+//   log(1 + e^(theta_o +- W_oi)) - log(1 + e^theta_o) = log(tau_o + sigma_o e^(+-W_oi)),  sigma = sigmoid(theta), tau = 1 - sigma,
+// so one flip is a product of nh FMAs against tables of e^(+-W) and ONE log (TAB = true).  Both terms of each FMA
+// are positive, i.e. no cancellation.  The identity needs the reference's softplus to be in its log1p(exp) branch
+// (F.softplus threshold 20) on both sides and binary inputs: a row with theta_o + max_i |W_oi| > 20 for some o, or a
+// non-binary entry, or a layer whose products could leave the double range (sum_o max_i |W_oi| > 700, non-finite
+// weights), takes the term-by-term path with the thresholded softplus instead (always when TAB = false: tables do
+// not fit in shared memory).  A warp handles RW = 32 / N rows at a time so that small layers use all lanes; for
+// binary rows of up to 64 units theta is accumulated over the SET bits only (adding W_oi in ascending i: bit-identical
+// to the dense FMA loop for finite weights), and layers wider than 32 give each lane two columns that share the
+// (sigma, tau) loads — the kernel is bound by shared-memory wavefronts, not by the FP64 pipe.
+struct FlipGeom { int RW, PW; };  // rows per warp pass, doubles of per-warp scratch (even)
+inline FlipGeom flip_geom(int N, int H) {
+  int rw = 32 / N;
+  if (rw < 1) rw = 1;
+  const int cap = 256 / H > 1 ? 256 / H : 1;
+  if (rw > cap) rw = cap;
+  int pw = 3 * rw * H + rw * N;
+  pw += pw & 1;
+  return {rw, pw};
+}
+
+template <bool TAB>
+__global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const double* __restrict__ v,
                                                                  const double* __restrict__ vb, int64_t rows,
-                                                                 double* __restrict__ out) {
+                                                                 double* __restrict__ out, int RW, int PW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ws = reinterpret_cast<double*>(smem_raw);
   const int N = s.n_in1, H = s.n_out;
   const int LD = N | 1;
   double* bs = Ws + (size_t)H * LD;
   double* vbs = bs + H;
-  double* wbuf = vbs + N + (threadIdx.x >> 5) * (N + 2 * H);  // per warp: v (N), theta (H), softplus(theta) (H)
-  double* vrow = wbuf;
-  double* th = wbuf + N;
-  double* sp = th + H;
+  double* Ep = vbs + N;                                   // e^{+W}, e^{-W}, max_i |W_oi| (TAB only)
+  double* Em = Ep + (TAB ? (size_t)H * LD : 0);
+  double* wmax = Em + (TAB ? (size_t)H * LD : 0);
+  const int WARPS = blockDim.x >> 5;
+  size_t off = (size_t)H * LD * (TAB ? 3 : 1) + 2 * H * (TAB ? 1 : 0) + (TAB ? 0 : H) + N;  // doubles before the scratch
+  off += off & 1;                                         // (sigma, tau) pairs are read as 16-byte words
+  double* scratch = Ws + off;
+  double* wbuf = scratch + (size_t)(threadIdx.x >> 5) * PW;
+  double2* st = reinterpret_cast<double2*>(wbuf);         // (RW, H): (sigma, tau) on product rows, (softplus(theta), -) otherwise
+  double* th = wbuf + 2 * RW * H;                         // (RW, H) theta
+  double* vrow = th + RW * H;                             // (RW, N)
+  unsigned* words = reinterpret_cast<unsigned*>(scratch + (size_t)WARPS * PW);
+  unsigned* cta_slow = words;                             // all ones: every row term by term
+  unsigned* flag = words + 1 + (threadIdx.x >> 5);        // per warp: mask of term-by-term rows
+  unsigned* bits = words + 1 + WARPS + (threadIdx.x >> 5) * 2;  // per warp: set bits of the pass, flattened (row, unit)
   stage_affine(s, Ws, LD, bs);
   for (int i = threadIdx.x; i < N; i += blockDim.x) vbs[i] = vb[i];
+  if (threadIdx.x == 0) *cta_slow = TAB ? 0u : 0xffffffffu;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t r = (int64_t)blockIdx.x * ROWS_WARPS + warp; r < rows; r += (int64_t)gridDim.x * ROWS_WARPS) {
-    for (int i = lane; i < N; i += 32) vrow[i] = v[r * N + i];
+  if (TAB) {
+    for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) {
+      const int o = idx / N, i = idx - o * N;
+      const double w = Ws[o * LD + i];
+      Ep[o * LD + i] = exp(w);
+      Em[o * LD + i] = exp(-w);
+    }
+    for (int o = threadIdx.x; o < H; o += blockDim.x) {
+      double m = 0.0;
+      for (int i = 0; i < N; ++i) {
+        const double a = fabs(Ws[o * LD + i]);
+        if (!(a <= m) && m == m) m = a;  // a NaN sticks
+      }
+      wmax[o] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int o = 0; o < H; ++o) tot += wmax[o];
+      if (!(tot <= 700.0)) *cta_slow = 0xffffffffu;  // also inf / NaN weights
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const bool sparse_ok = TAB && N <= 64 && *cta_slow == 0u;
+  for (int64_t g = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); g * RW < rows; g += (int64_t)gridDim.x * WARPS) {
+    const int64_t r0 = g * RW;
+    const int nr = (int)(rows - r0 < RW ? rows - r0 : RW);
+    if (lane == 0) *flag = *cta_slow;
     __syncwarp();
-    for (int o = lane; o < H; o += 32) {
-      const double* wrow = Ws + (size_t)o * LD;
-      double t = bs[o];
-      for (int i = 0; i < N; ++i) t = fma(wrow[i], vrow[i], t);
-      th[o] = t;
-      sp[o] = softplus20(t);
+    for (int e0 = 0; e0 < nr * N; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < nr * N;
+      const double x = valid ? v[r0 * N + e] : 0.0;
+      if (valid) vrow[e] = x;
+      if (TAB) {
+        if (x != 0.0 && x != 1.0) atomicOr(flag, 1u << (e / N));
+        const unsigned ones = __ballot_sync(0xffffffffu, x == 1.0);  // bit = flattened (row, unit) index of the pass
+        if (sparse_ok && lane == 0 && e0 < 64) bits[e0 >> 5] = ones;
+      }
     }
     __syncwarp();
-    for (int i = lane; i < N; i += 32) {
-      const double sgn = 1.0 - 2.0 * vrow[i];  // flipping a binary unit changes it by +-1
-      double d = sgn * vbs[i];
-      for (int o = 0; o < H; ++o) d += softplus20(fma(sgn, Ws[(size_t)o * LD + i], th[o])) - sp[o];
-      out[r * N + i] = d;
+    const unsigned f0 = *flag;  // non-binary rows so far
+    for (int e = lane; e < nr * H; e += 32) {
+      const int rr = e / H, o = e - rr * H;
+      const double* wrow = Ws + (size_t)o * LD;
+      double t = bs[o];
+      if (sparse_ok && !((f0 >> rr) & 1u)) {
+        unsigned m = N > 32 ? bits[0] : (bits[0] >> (rr * N)) & (0xffffffffu >> (32 - N));
+        while (m) {
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          t += wrow[i];
+        }
+        m = N > 32 ? bits[1] : 0u;
+        while (m) {
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          t += wrow[32 + i];
+        }
+      } else {
+        const double* x = vrow + rr * N;
+        for (int i = 0; i < N; ++i) t = fma(wrow[i], x[i], t);
+      }
+      th[e] = t;
+      if (TAB) {
+        if (!(t + wmax[o] <= 20.0)) atomicOr(flag, 1u << rr);
+        const double ex = exp(t);
+        const double tau = 1.0 / (1.0 + ex);
+        st[e] = make_double2(ex * tau, tau);
+      }
+    }
+    __syncwarp();
+    const unsigned f = *flag;
+    if (f != 0u) {
+      for (int e = lane; e < nr * H; e += 32)
+        if ((f >> (e / H)) & 1u) st[e].x = softplus20(th[e]);
+      __syncwarp();
+    }
+    if (TAB && RW == 1 && N > 32 && f == 0u) {
+      // one product row per pass: columns i and i + 32 of a lane share the (sigma, tau) loads
+      for (int i = lane; i < N; i += 64) {
+        const bool two = i + 32 < N;
+        const int i2 = two ? i + 32 : i;
+        const double x1 = vrow[i], x2 = vrow[i2];
+        const double* T1 = (x1 == 0.0 ? Ep : Em) + i;
+        const double* T2 = (x2 == 0.0 ? Ep : Em) + i2;
+        double p = 1.0, q = 1.0;
+#pragma unroll 4
+        for (int o = 0; o < H; ++o) {
+          const double2 a = st[o];
+          p *= fma(a.x, T1[(size_t)o * LD], a.y);
+          q *= fma(a.x, T2[(size_t)o * LD], a.y);
+        }
+        out[r0 * N + i] = fma(1.0 - 2.0 * x1, vbs[i], log(p));
+        if (two) out[r0 * N + i2] = fma(1.0 - 2.0 * x2, vbs[i2], log(q));
+      }
+    } else {
+      for (int e = lane; e < nr * N; e += 32) {
+        const int rr = e / N, i = e - rr * N;
+        const double x = vrow[e];
+        const double sgn = 1.0 - 2.0 * x;  // flipping a binary unit changes it by +-1
+        double d = sgn * vbs[i];
+        if (!TAB || ((f >> rr) & 1u)) {
+          const double* t = th + rr * H;
+          const double2* sp = st + rr * H;
+          for (int o = 0; o < H; ++o) d += softplus20(fma(sgn, Ws[(size_t)o * LD + i], t[o])) - sp[o].x;
+        } else {
+          const double* T = (x == 0.0 ? Ep : Em) + i;
+          const double2* a = st + rr * H;
+          double p0 = 1.0, p1 = 1.0;
+          int o = 0;
+          for (; o + 1 < H; o += 2) {
+            p0 *= fma(a[o].x, T[(size_t)o * LD], a[o].y);
+            p1 *= fma(a[o + 1].x, T[(size_t)(o + 1) * LD], a[o + 1].y);
+          }
+          if (o < H) p0 *= fma(a[o].x, T[(size_t)o * LD], a[o].y);
+          d += log(p0 * p1);
+        }
+        out[r0 * N + e] = d;
+      }
     }
     __syncwarp();
   }
 }
 
+static size_t flip_smem(int N, int H, bool tab, const FlipGeom& g, int warps) {
+  const size_t LD = (size_t)(N | 1);
+  return ((size_t)H * LD * (tab ? 3 : 1) + H + N + (tab ? H : 0) + 1 + (size_t)warps * g.PW) * sizeof(double) +
+         (1 + 3 * (size_t)warps) * sizeof(unsigned);
+}
+
 int run_flip_logratio(const StackedParams& p, const double* v, int64_t rows, double* out, cudaStream_t st) {
   if (rows == 0) return QCB_OK;
   const int N = p.N, H = p.nhid();
-  const size_t smem = ((size_t)H * (N | 1) + H + N + (size_t)ROWS_WARPS * (N + 2 * H)) * sizeof(double);
+  const FlipGeom g = flip_geom(N, H);
+  // CTA size: 8 warps while eight such CTAs fit on an SM; layers whose tables take most of the shared memory get
+  // up to 32 warps around ONE copy of the tables instead (the row loop is latency-bound: it wants the warps)
+  const size_t sm_bytes = 227 * 1024;
+  bool tab = true;
+  int warps = 8;
+  if (flip_smem(N, H, true, g, 8) * 8 > sm_bytes) {
+    warps = 32;
+    while (warps > 8 && flip_smem(N, H, true, g, warps) > SMEM_LIMIT) warps >>= 1;
+    if (flip_smem(N, H, true, g, warps) > SMEM_LIMIT) {
+      tab = false;
+      warps = 32;
+      while (warps > 8 && flip_smem(N, H, false, g, warps) > SMEM_LIMIT) warps >>= 1;
+    }
+  }
+  const size_t smem = flip_smem(N, H, tab, g, warps);
   if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "flip_logratio: layer %d x %d does not fit in shared memory", H, N);
-  QCB_CUDA(cudaFuncSetAttribute(rows_flip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-  const int64_t need = (rows + ROWS_WARPS - 1) / ROWS_WARPS;
-  const int64_t cap = (int64_t)sm_count() * 4;
-  rows_flip_kernel<<<(int)(need < cap ? need : cap), ROWS_THREADS, smem, st>>>(stacked_hidden_spec(p), v, p.b, rows, out);
+  const int64_t groups = (rows + g.RW - 1) / g.RW;
+  const int64_t need = (groups + warps - 1) / warps;
+  const int64_t cap = (int64_t)sm_count() * (64 / warps);
+  const int grid = (int)(need < cap ? need : cap);
+  if (tab) {
+    QCB_CUDA(cudaFuncSetAttribute(rows_flip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    rows_flip_kernel<true><<<grid, warps * 32, smem, st>>>(stacked_hidden_spec(p), v, p.b, rows, out, g.RW, g.PW);
+  } else {
+    QCB_CUDA(cudaFuncSetAttribute(rows_flip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    rows_flip_kernel<false><<<grid, warps * 32, smem, st>>>(stacked_hidden_spec(p), v, p.b, rows, out, g.RW, g.PW);
+  }
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }

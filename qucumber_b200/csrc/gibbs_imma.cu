@@ -1,4 +1,7 @@
 // Block Gibbs with an integer-exact tensor-core filter (layers up to 64 x 64, in-kernel Philox draws).
+// Like gibbs.cu it replaces the k-sweep loops of BinaryRBM.gibbs_steps (rbm/binary_rbm.py:200-228: h | v then
+// v | h through prob_*/sample_*, :129-198) and PurificationRBM.gibbs_steps (rbm/purification_rbm.py:309-337) with
+// one launch; the PurificationRBM runs as the stacked hidden layer [W; U], [c; d].
 //
 // A Bernoulli decision u < sigmoid(x) only needs x in full FP64 when u falls next to p.  This kernel
 // therefore evaluates x~ = W v + c with EXACT integer arithmetic on the int8 tensor cores and keeps the

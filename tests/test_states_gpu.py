@@ -421,12 +421,12 @@ def _flip_oracle(o, v):
     return out
 
 
-@pytest.mark.parametrize("n,nh,na", [(10, 10, 0), (64, 64, 0), (7, 40, 0), (6, 5, 4)])
+@pytest.mark.parametrize("n,nh,na", [(10, 10, 0), (64, 64, 0), (7, 40, 0), (6, 5, 4), (1, 3, 0), (3, 150, 0), (33, 2, 0), (100, 120, 0)])
 def test_flip_logratio(lib, cuda, n, nh, na):
     from qucumber_b200 import BinaryRBM, PurificationRBM
     from qucumber_b200.observables import flip_logratio
 
-    v = random_states(333, n, 131)
+    v = random_states(335, n, 131)
     if na:
         pr = make_purification_params(n, nh, na, 132)
         rbm, o = load_purification(PurificationRBM(n, nh, na, gpu=True), *pr), orc.PurificationRBMOracle(*pr)
@@ -434,6 +434,35 @@ def test_flip_logratio(lib, cuda, n, nh, na):
         pr = make_binary_params(n, nh, 132)
         rbm, o = load_binary(BinaryRBM(n, nh, gpu=True), *pr), orc.BinaryRBMOracle(*pr)
     assert_close(flip_logratio(rbm, torch.tensor(v, device=cuda)), _flip_oracle(o, v), rtol=1e-9, what="flip log-ratios")
+
+
+@pytest.mark.parametrize("case", ["threshold", "nonbinary", "huge"])
+def test_flip_logratio_term_by_term_rows(lib, cuda, case):
+    """Rows the product form must not take: theta beyond the reference's softplus threshold (20) on some rows only,
+    non-binary entries, layers whose products would overflow. All are evaluated term by term
+    with the thresholded softplus like binary_rbm.py:92-96 and have to agree with the oracle."""
+    from qucumber_b200 import BinaryRBM
+    from qucumber_b200.observables import flip_logratio
+
+    n, nh = 10, 12
+    W, b, c = make_binary_params(n, nh, 140, weight_scale=1.5)
+    v = random_states(200, n, 141)
+    if case == "threshold":
+        c = c + 14.0  # theta crosses 20 on part of the rows
+    elif case == "nonbinary":
+        v[::3, 2] = 0.25
+        v[5, :] = np.linspace(-1.0, 2.0, n)
+    else:
+        W = W * 80.0  # sum of max |W| far beyond 700
+    rbm, o = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c), orc.BinaryRBMOracle(W, b, c)
+    got = flip_logratio(rbm, torch.tensor(v, device=cuda)).cpu().numpy()
+    with np.errstate(all="ignore"):
+        want = _flip_oracle(o, v)
+    if case == "threshold":
+        th = v @ W.T + c
+        assert (th.max(1) > 20).any() and (th.max(1) + np.abs(W).max() < 20).any()  # both kinds of row present
+    assert np.isfinite(got).all()
+    assert_close(got, want, rtol=1e-9, what=f"flip log-ratios ({case})")
 
 
 def test_observables_tutorial4_style(lib, cuda):
