@@ -709,3 +709,48 @@ def exact_gradient_with_bases(kind, rbm_am, rbm_ph, samples, bases, unitaries=No
     probs = probs / probs.sum()
     g[0] = g[0] - rbm_am.effective_energy_gradient(space, reduce=False).T @ probs
     return g
+
+
+# ------------------------------------------------------------------------------- local estimators
+def pauli_magnetisation(axis, weight_fn, v, absolute=False):
+    """SigmaX / SigmaY / SigmaZ .apply (observables/pauli.py:50-83, 100-135, 151-171): per-sample magnetisation
+    (1/N) sum_i Re[c_i w(v with unit i flipped, v)], c_i = 1 (X) or i (2 v_i - 1) (Y); Z is the mean of the +-1
+    spins. ``weight_fn(vp, v)`` is the importance-sampling weight (neural_state.py:283-300): psi(vp) / psi(v) for
+    wavefunctions (wavefunction.py:84-92), rho(vp, v) / rho(v, v) for density matrices (density_matrix.py:275-279)."""
+    v = np.asarray(v, dtype=np.float64)
+    if axis == "Z":
+        res = (2.0 * v - 1.0).mean(1)
+        return np.abs(res) if absolute else res
+    total = np.zeros(v.shape[0], dtype=np.complex128)
+    for i in range(v.shape[1]):
+        vf = v.copy()
+        vf[:, i] = np.abs(vf[:, i] - 1.0)  # flip_spin, pauli.py:23-33
+        coeff = 1.0 if axis == "X" else 1j * (2.0 * v[:, i] - 1.0)
+        total = total + coeff * weight_fn(vf, v)
+    res = total.real / v.shape[1]
+    return np.abs(res) if absolute else res
+
+
+def wavefunction_weight(psi_fn):
+    return lambda vp, v: psi_fn(vp) / psi_fn(v)
+
+
+def dm_weight(rbm_am, rbm_ph):
+    return lambda vp, v: dm_rho(rbm_am, rbm_ph, vp, v, expand=False) / dm_rho(rbm_am, rbm_ph, v, v, expand=False).real
+
+
+def tfim_chain_energy(rbm_am, v, h):
+    """TFIMChainEnergy.apply (examples/Tutorial4_DataGeneration_CalculateObservables/quantum_ising_chain.py:45-78):
+    -(sum_i s_i s_{i+1} + h sum_i psi(v^(i)) / psi(v)) / N with open boundaries, positive wavefunction."""
+    v = np.asarray(v, dtype=np.float64)
+    s = 2.0 * v - 1.0
+    log_psi = -0.5 * rbm_am.effective_energy(v)
+    flipped = np.empty(v.shape)
+    for i in range(v.shape[1]):
+        vf = v.copy()
+        vf[:, i] = 1.0 - vf[:, i]
+        flipped[:, i] = -0.5 * rbm_am.effective_energy(vf)
+    m = flipped.max(1, keepdims=True)
+    lse = (m + np.log(np.exp(flipped - m).sum(1, keepdims=True)))[:, 0]
+    transverse = np.exp(lse - log_psi)
+    return -(h * transverse + (s[:, :-1] * s[:, 1:]).sum(1)) / v.shape[1]

@@ -22,6 +22,28 @@ def flip_logratio(rbm, samples):
     return out
 
 
+def _is_wavefunction(nn_state):
+    return hasattr(nn_state, "phase")
+
+
+def _importance_sampled_pauli(nn_state, samples, axis):
+    """The reference's loop over flipped copies (pauli.py:62-83, 113-135) for states without a psi(v) factorisation
+    (DensityMatrix: weights rho(v^(i), v) / rho(v, v)); every call inside is one of the drop-in's CUDA paths."""
+    from .utils import cplx
+
+    denom = nn_state.importance_sampling_denominator(samples)
+    numer_sum = torch.zeros_like(denom)
+    for i in range(samples.shape[-1]):
+        flipped = samples.clone()
+        flipped[..., i].sub_(1).abs_()
+        numer = nn_state.importance_sampling_numerator(flipped, samples)
+        if axis == "Y":
+            coeff = samples[..., i].mul(2.0).sub(1.0)
+            numer = cplx.elementwise_mult(numer, cplx.make_complex(torch.zeros_like(coeff), coeff))
+        numer_sum.add_(numer)
+    return cplx.real(cplx.elementwise_division(numer_sum, denom)).div_(samples.shape[-1])
+
+
 class _Estimator:
     def statistics_from_samples(self, nn_state, samples):
         """mean / variance / std_error / num_samples of the estimator over the given samples."""
@@ -68,11 +90,32 @@ class SigmaX(_Estimator):
 
     def apply(self, nn_state, samples):
         samples = samples.to(device=nn_state.device, dtype=torch.double)
-        ratio = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp()
-        rbm_ph = getattr(nn_state, "rbm_ph", None)
-        if rbm_ph is not None and hasattr(nn_state, "phase"):
-            ratio = ratio * (0.5 * flip_logratio(rbm_ph, samples)).cos()
-        res = ratio.mean(1)
+        if _is_wavefunction(nn_state):
+            ratio = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp()
+            if getattr(nn_state, "rbm_ph", None) is not None:
+                ratio = ratio * (0.5 * flip_logratio(nn_state.rbm_ph, samples)).cos()
+            res = ratio.mean(1)
+        else:
+            res = _importance_sampled_pauli(nn_state, samples, "X")
+        return res.abs() if self.absolute else res
+
+
+class SigmaY(_Estimator):
+    """Average magnetisation along Y (pauli.py:86-135): (1/N) sum_i Re[i s_i psi(v^(i)) / psi(v)], s_i = 2 v_i - 1;
+    identically zero for a positive wavefunction."""
+
+    def __init__(self, absolute=False):
+        self.name, self.symbol, self.absolute = "SigmaY", "Y", absolute
+
+    def apply(self, nn_state, samples):
+        samples = samples.to(device=nn_state.device, dtype=torch.double)
+        if not _is_wavefunction(nn_state):
+            res = _importance_sampled_pauli(nn_state, samples, "Y")
+        elif getattr(nn_state, "rbm_ph", None) is None:
+            return torch.zeros(samples.shape[:-1], dtype=torch.double, device=samples.device)
+        else:
+            ratio = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp()
+            res = -(samples.mul(2.0).sub(1.0) * ratio * (0.5 * flip_logratio(nn_state.rbm_ph, samples)).sin()).mean(1)
         return res.abs() if self.absolute else res
 
 

@@ -199,3 +199,36 @@ def test_density_2qubits_reference_fixture():
     ge = orc.exact_gradient_with_bases("dm", am, ph, g["train_samples"], tb)
     close(ge[0], g["exact_grad_am"], 1e-10)
     close(ge[1], g["exact_grad_ph"], 1e-10)
+
+
+def test_observables_reference_fixture():
+    """SigmaX / SigmaY / SigmaZ of the reference (observables/pauli.py) and the Tutorial-4 TFIM energy on positive,
+    complex and density-matrix states (tests/golden/make_golden_observables.py)."""
+    g = load("observables.npz")
+    t = load("binary_rbm_tfim10.npz")
+    am = orc.BinaryRBMOracle(t["weights"], t["visible_bias"], t["hidden_bias"])
+    w = orc.wavefunction_weight(lambda v: orc.psi_positive(am, v))
+    v = g["pos_states"]
+    close(orc.pauli_magnetisation("X", w, v), g["pos_sigma_x"])
+    close(orc.pauli_magnetisation("X", w, v, absolute=True), g["pos_abs_sigma_x"])
+    assert np.all(g["pos_sigma_y"] == 0) and np.all(orc.pauli_magnetisation("Y", w, v) == 0)
+    close(orc.pauli_magnetisation("Z", w, v), g["pos_sigma_z"])
+    close(orc.pauli_magnetisation("Z", w, v, absolute=True), g["pos_abs_sigma_z"])
+    close(orc.tfim_chain_energy(am, v, 1.0), g["pos_tfim_energy_h1"])
+    close(orc.tfim_chain_energy(am, v, 0.5), g["pos_tfim_energy_h05"])
+
+    c = load("complex_wavefunction.npz")
+    cam, cph = _complex_pair(c)
+    w = orc.wavefunction_weight(lambda v: orc.psi_complex(cam, cph, v))
+    v = g["cwf_states"]
+    close(orc.pauli_magnetisation("X", w, v), g["cwf_sigma_x"])
+    close(orc.pauli_magnetisation("Y", w, v), g["cwf_sigma_y"])
+    close(orc.pauli_magnetisation("Y", w, v, absolute=True), g["cwf_abs_sigma_y"])
+    close(orc.pauli_magnetisation("Z", w, v), g["cwf_sigma_z"])
+
+    d = load("density_matrix.npz")
+    w = orc.dm_weight(*_dm_pair(d))
+    v = g["dm_states"]
+    close(orc.pauli_magnetisation("X", w, v), g["dm_sigma_x"])
+    close(orc.pauli_magnetisation("Y", w, v), g["dm_sigma_y"], 1e-11)
+    close(orc.pauli_magnetisation("Z", w, v), g["dm_sigma_z"])

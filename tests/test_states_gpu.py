@@ -465,6 +465,39 @@ def test_flip_logratio_term_by_term_rows(lib, cuda, case):
     assert_close(got, want, rtol=1e-9, what=f"flip log-ratios ({case})")
 
 
+def test_observables_reference_fixture(lib, cuda):
+    """The estimator classes against values computed by the reference's own observables (pauli.py SigmaX/Y/Z, the
+    Tutorial-4 TFIMChainEnergy) on positive, complex and density-matrix states (tests/golden/observables.npz)."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.observables import SigmaX, SigmaY, SigmaZ, TFIMChainEnergy
+
+    g, t = gold("observables.npz"), gold("binary_rbm_tfim10.npz")
+    nn = PositiveWaveFunction(10, 10, gpu=True)
+    load_binary(nn.rbm_am, t["weights"], t["visible_bias"], t["hidden_bias"])
+    v = torch.tensor(g["pos_states"], device=cuda)
+    assert_close(SigmaX().apply(nn, v), g["pos_sigma_x"], what="SigmaX (positive)")
+    assert_close(SigmaX(absolute=True).apply(nn, v), g["pos_abs_sigma_x"], what="|SigmaX| (positive)")
+    assert np.all(SigmaY().apply(nn, v).cpu().numpy() == 0) and np.all(g["pos_sigma_y"] == 0)
+    assert_close(SigmaZ().apply(nn, v), g["pos_sigma_z"], what="SigmaZ (positive)")
+    assert_close(SigmaZ(absolute=True).apply(nn, v), g["pos_abs_sigma_z"], what="|SigmaZ| (positive)")
+    assert_close(TFIMChainEnergy(1.0).apply(nn, v), g["pos_tfim_energy_h1"], what="TFIM energy h=1")
+    assert_close(TFIMChainEnergy(0.5).apply(nn, v), g["pos_tfim_energy_h05"], what="TFIM energy h=0.5")
+
+    cwf = _load_cwf(gold("complex_wavefunction.npz"), 5, 4)
+    v = torch.tensor(g["cwf_states"], device=cuda)
+    assert_close(SigmaX().apply(cwf, v), g["cwf_sigma_x"], what="SigmaX (complex)")
+    assert_close(SigmaY().apply(cwf, v), g["cwf_sigma_y"], what="SigmaY (complex)")
+    assert_close(SigmaY(absolute=True).apply(cwf, v), g["cwf_abs_sigma_y"], what="|SigmaY| (complex)")
+    assert_close(SigmaZ().apply(cwf, v), g["cwf_sigma_z"], what="SigmaZ (complex)")
+
+    dm = _load_dm(gold("density_matrix.npz"), 4, 3, 5)
+    v = torch.tensor(g["dm_states"], device=cuda)
+    assert_close(SigmaX().apply(dm, v), g["dm_sigma_x"], what="SigmaX (density matrix)")
+    assert_close(SigmaY().apply(dm, v), g["dm_sigma_y"], what="SigmaY (density matrix)")
+    assert_close(SigmaZ().apply(dm, v), g["dm_sigma_z"], what="SigmaZ (density matrix)")
+    assert v.cpu().numpy().tolist() == g["dm_states"].tolist()  # inputs are not modified
+
+
 def test_observables_tutorial4_style(lib, cuda):
     """Config 3 in miniature: sample many chains (N = 10, k = 100), then SigmaZ / SigmaX / TFIM-energy
     estimates; checked (a) sample by sample against the oracle's psi ratios, (b) statistically against
