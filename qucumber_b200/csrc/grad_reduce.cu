@@ -21,7 +21,7 @@ constexpr int GR = 32;  // rows per tile
 constexpr int GR_MAX_CTAS_PER_SM = 4;  // partial-sum slots per SM in the workspace (tensor-core kernel: up to 4 CTAs/SM)
 
 int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
-                         int* grid_out, cudaStream_t st);
+                         int* grid_out, int* flag, cudaStream_t st);
 
 template <int TPT, int SRC>  // TPT = 4x4 tiles per thread
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s, RowSrc src, int64_t rows,
@@ -179,7 +179,7 @@ static int grad_reduce_grid(int64_t rows) {
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows) {
   (void)rows;
   const size_t G = (size_t)nhid * N + N + nhid;
-  return align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256);
+  return align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256) + 256;  // partials + one flag word
 }
 
 template <int SRC>
@@ -198,7 +198,8 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
   int grid_dmma = 0;
   if (rows > 0) {
     // large batches of explicit / expanded rows run on the FP64 tensor cores (grad_reduce_dmma.cu)
-    const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, st);
+    int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + need - 256);
+    const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, flag, st);
     if (rc != QCB_OK) return rc;
   }
   if (grid_dmma > 0) {

@@ -486,6 +486,64 @@ def test_reduced_gradient_saturated_units_large_batch(lib, cuda):
     assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), want, what="reduced gradient, saturated units")
 
 
+@pytest.mark.parametrize("n,nh,case", [(64, 64, "plain"), (32, 64, "plain"), (64, 25, "plain"), (40, 33, "plain"), (64, 64, "mixed_scale"),
+                                       (64, 64, "large"), (64, 64, "tiny"), (64, 64, "zero"), (48, 64, "nonbinary_tail"),
+                                       (64, 64, "nonbinary"), (64, 64, "nonfinite"), (64, 64, "subnormal_scale"), (49, 64, "plain"),
+                                       (64, 64, "unaligned"), (56, 48, "unaligned_real")])
+def test_reduced_gradient_integer_theta_large_batch(lib, cuda, n, nh, case):
+    """Batches of >= 16384 binary rows on 25..64-unit layers compute theta from 3 x 23-bit fixed-point images of W on the
+    int8 tensor cores (grad_reduce_dmma.cu); non-binary rows anywhere in the batch, non-finite weights or weights outside
+    the image's range hand the whole batch to the FP64 kernel. Rows of >= 48 units with 16-byte aligned starts enter the
+    tile through TMA row copies, odd widths and misaligned views element by element. Same 1e-10 gate in every case."""
+    from qucumber_b200 import BinaryRBM
+
+    rows = 16384 + 37
+    W, b, c = make_binary_params(n, nh, 301, bias_scale=0.3)
+    v = random_states(rows, n, 302)
+    rng = np.random.default_rng(303)
+    if case == "mixed_scale":
+        W = W * 10.0 ** rng.uniform(-9, 0.5, size=W.shape)
+    elif case == "large":
+        W = W * 37.0
+    elif case == "tiny":
+        W = W * 1e-12
+    elif case == "zero":
+        W = np.zeros_like(W)
+    elif case == "nonbinary_tail":
+        v[-1, 3] = 0.5
+    elif case == "nonbinary":
+        v = rng.standard_normal((rows, n))
+    elif case == "nonfinite":
+        W[5, 7] = np.inf
+    elif case == "subnormal_scale":
+        W = W * 1e-300
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    with np.errstate(all="ignore"):
+        want = o.effective_energy_gradient(v)
+    if case == "unaligned_real":
+        v = rng.standard_normal((rows, n))
+        with np.errstate(all="ignore"):
+            want = o.effective_energy_gradient(v)
+    if case.startswith("unaligned"):  # rows that start 8 bytes off a 16-byte boundary: no TMA row copies
+        backing = torch.empty(rows * n + 1, dtype=torch.double, device=cuda)
+        vt = backing[1:].view(rows, n)
+        vt.copy_(torch.tensor(v))
+        assert vt.data_ptr() % 16 == 8
+    else:
+        vt = torch.tensor(v, device=cuda)
+    got = rbm.effective_energy_gradient(vt).cpu().numpy()
+    if case == "nonfinite":
+        ok = np.isfinite(want)  # everything outside hidden unit 5
+        assert_close(got[ok], want[ok], what="finite entries next to a non-finite weight")
+    else:
+        assert_close(got, want, what=f"reduced gradient, integer theta ({case})")
+    # per-entry check on the weight block as well (the bias sums dominate the global scale)
+    if case in ("plain", "mixed_scale", "tiny"):
+        gw, ww = got[: nh * n], want[: nh * n]
+        assert float(np.max(np.abs(gw - ww) / (np.abs(ww) + 1e-6 * np.abs(ww).max()))) < 1e-9
+
+
 def test_calls_are_capturable_in_a_cuda_graph(lib, cuda):
     """The C ABI only enqueues work on the caller's stream (no allocation, no synchronisation, no stream query that
     would invalidate a capture): a Gibbs call and a gradient call captured in a CUDA graph replay to the eager result."""

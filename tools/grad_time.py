@@ -10,7 +10,7 @@ from qucumber_b200 import BinaryRBM  # noqa: E402
 
 dev = torch.device("cuda")
 rows = 1 << 20
-for nv, nh in ((64, 64), (20, 20), (10, 10)):
+for nv, nh in ((64, 64), (32, 32), (20, 20), (10, 10)):
     rb = BinaryRBM(nv, nh, gpu=True)
     g = torch.Generator().manual_seed(99)
     with torch.no_grad():
