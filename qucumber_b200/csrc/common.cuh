@@ -104,8 +104,8 @@ constexpr int EXP2_TABLE = 64;
 __device__ __forceinline__ void fill_exp2_table(double* tab) {  // call with all threads of the CTA, then sync
   for (int j = threadIdx.x; j < EXP2_TABLE; j += blockDim.x) tab[j] = exp2((double)j / EXP2_TABLE);
 }
-__device__ __forceinline__ double sigmoid_tab(double x, const double* __restrict__ tab) {
-  const double t = fmin(fmax(-x, -700.0), 700.0);
+// e^t for |t| <= 700 (callers clamp), ~1.5 ulp
+__device__ __forceinline__ double exp_tab(double t, const double* __restrict__ tab) {
   const double shifted = fma(t, 92.332482616893656, 0x1.8p52);           // 64 / ln 2
   const int n = __double2loint(shifted);
   const double nf = shifted - 0x1.8p52;
@@ -117,7 +117,10 @@ __device__ __forceinline__ double sigmoid_tab(double x, const double* __restrict
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double m = tab[n & (EXP2_TABLE - 1)] * p;                        // in [1, 2 e^{ln2/128})
-  const double e = __hiloint2double(__double2hiint(m) + ((n >> 6) << 20), __double2loint(m));
+  return __hiloint2double(__double2hiint(m) + ((n >> 6) << 20), __double2loint(m));
+}
+__device__ __forceinline__ double sigmoid_tab(double x, const double* __restrict__ tab) {
+  const double e = exp_tab(fmin(fmax(-x, -700.0), 700.0), tab);
   const double d = 1.0 + e;
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));

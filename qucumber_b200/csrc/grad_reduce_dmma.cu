@@ -566,13 +566,32 @@ __global__ void __launch_bounds__(GD_THREADS) rows_energy_dmma_kernel(AffineSpec
   for (int i = threadIdx.x; i < Hpad; i += GD_THREADS) hb[i] = i < H ? s.bias(i) : -1.0e300;
   for (int i = threadIdx.x; i < Npad; i += GD_THREADS) vbs[i] = i < N ? vb[i] : 0.0;
   for (int i = threadIdx.x; i < GD_TR * LDV; i += GD_THREADS) Vt[i] = 0.0;
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
+  __shared__ __align__(8) uint64_t fill_bar;  // wide, aligned rows come in through TMA row copies as in the gradient kernel
+  const bool bulk_fill = N >= 48 && (N & 1) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+  uint32_t fill_parity = 0;
+  if (threadIdx.x == 0) mbar_init(&fill_bar, 1);
   __syncthreads();
   const int fill_r0 = threadIdx.x / N, fill_j0 = threadIdx.x - fill_r0 * N;
   const int fill_dr = GD_THREADS / N, fill_dj = GD_THREADS - fill_dr * N;
   const int64_t ntiles = (rows + GD_TR - 1) / GD_TR;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * GD_TR;
-    {
+    if (bulk_fill) {
+      const int nrows = (int)(rows - r0 < GD_TR ? rows - r0 : (int64_t)GD_TR);
+      if (threadIdx.x < GD_TR) {
+        if (threadIdx.x < nrows) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tma_bulk_g2s(Vt + threadIdx.x * LDV, v + (r0 + threadIdx.x) * N, (uint32_t)(N * sizeof(double)), &fill_bar);
+        } else {
+          for (int jj = 0; jj < N; ++jj) Vt[threadIdx.x * LDV + jj] = 0.0;  // ragged last tile
+        }
+      }
+      if (threadIdx.x == 0) mbar_expect_tx(&fill_bar, (uint32_t)(nrows * N * sizeof(double)));
+      mbar_wait(&fill_bar, fill_parity);
+      fill_parity ^= 1u;
+    } else {
       // batches of 8 elements per thread, stepped without divisions: the loads of a batch are issued before its stores
       constexpr int FILL = (GD_TR * Npad + GD_THREADS - 1) / GD_THREADS, FB = FILL < 8 ? FILL : 8;
       int rr = fill_r0, j = fill_j0;
@@ -619,7 +638,7 @@ __global__ void __launch_bounds__(GD_THREADS) rows_energy_dmma_kernel(AffineSpec
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const double th = acc[nb][e];
-        if (th > 20.0) lin += th; else prod *= 1.0 + exp(th);
+        if (!(th <= 20.0)) lin += th; else prod *= 1.0 + exp_tab(fmax(th, -700.0), e2tab);  // a NaN stays a NaN
       }
     }
     double val = lin + log(prod);

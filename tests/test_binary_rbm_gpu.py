@@ -374,6 +374,15 @@ def test_effective_energy_large_batch_tensor_core_path(lib, cuda, n, nh):
     r2 = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
     assert_close(r2.effective_energy(torch.tensor(v, device=cuda)), BinaryRBMOracle(W, b, c).effective_energy(v), rtol=1e-13,
                  what="energy near threshold (large batch)")
+    # rows starting 8 bytes off a 16-byte boundary (no TMA row copies) and a NaN entry (stays a NaN, only in its row)
+    backing = torch.empty(v.size + 1, dtype=torch.double, device=cuda)
+    vt = backing[1:].view(*v.shape)
+    vt.copy_(torch.tensor(v))
+    assert_close(rbm.effective_energy(vt), orc.effective_energy(v), what="energy (large batch, misaligned rows)")
+    vn = torch.tensor(v, device=cuda)
+    vn[7, 0] = float("nan")
+    en = rbm.effective_energy(vn).cpu().numpy()
+    assert np.isnan(en[7]) and np.isfinite(np.delete(en, 7)).all()
 
 
 def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
