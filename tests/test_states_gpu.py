@@ -161,6 +161,30 @@ def test_complex_rotated_vs_oracle(lib, cuda, n, nh, basis):
     assert_close(rg[1], gp, what="rotated grad (phase)")
 
 
+def test_complex_rotated_gradient_large_expansion_integer_theta(lib, cuda):
+    """>= 16384 expanded rows on a 26-visible / 28-hidden layer: the weighted reductions over the expansion take the
+    tensor-core kernel with the integer phase 1 (rows generated from sample bits and expansion index, signed weights).
+    Compared with the oracle's expansion on a subset of the samples via linearity over samples."""
+    from qucumber_b200 import ComplexWaveFunction
+
+    n, nh, basis = 26, 28, list("ZXZZYZZZXZZZZZZZYZZZZZZZZZ")  # S = 4
+    nn = ComplexWaveFunction(n, nh, gpu=True)
+    pa = make_binary_params(n, nh, 31, bias_scale=0.3)
+    pp = make_binary_params(n, nh, 32, bias_scale=0.3)
+    load_binary(nn.rbm_am, *pa)
+    load_binary(nn.rbm_ph, *pp)
+    am, ph = orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp)
+    small = random_states(64, n, 33)
+    ga, gp = orc.complex_rotated_gradient(am, ph, basis, small)
+    reps = 20  # 1280 samples x 16 expanded states = 20480 rows; the gradient is a sum over samples
+    big = torch.tensor(np.tile(small, (reps, 1)), device=cuda)
+    rg = nn.rotated_gradient(np.array(basis), big)
+    assert_close(rg[0], reps * ga, what="rotated grad (amplitude), large expansion")
+    assert_close(rg[1], reps * gp, what="rotated grad (phase), large expansion")
+    rs = nn.rotated_gradient(np.array(basis), torch.tensor(small, device=cuda))  # small batch: FMA kernel
+    assert_close(rg[0], reps * rs[0].cpu().numpy(), rtol=1e-12, what="large == small x reps (amplitude)")
+
+
 def test_complex_2qubits_reference_fixture(lib, cuda):
     from qucumber_b200.utils import training_statistics as ts
 
