@@ -754,3 +754,14 @@ def tfim_chain_energy(rbm_am, v, h):
     lse = (m + np.log(np.exp(flipped - m).sum(1, keepdims=True)))[:, 0]
     transverse = np.exp(lse - log_psi)
     return -(h * transverse + (s[:, :-1] * s[:, 1:]).sum(1)) / v.shape[1]
+
+
+def swap_estimator(weight_fn, v, A):
+    """SWAP.apply (observables/entanglement.py:58-80): replica 2 = the batch rolled by one row (torch.roll(s, 1, 0)),
+    region A exchanged between the replicas, Re[w(s1', s1) w(s2', s2)]."""
+    s1 = np.asarray(v, dtype=np.float64)
+    s2 = np.roll(s1, 1, axis=0)
+    s1_, s2_ = s1.copy(), s2.copy()
+    s1_[:, A] = s2[:, A]
+    s2_[:, A] = s1[:, A]
+    return (weight_fn(s1_, s1) * weight_fn(s2_, s2)).real

@@ -135,3 +135,24 @@ class TFIMChainEnergy(_Estimator):
             interaction = interaction + spins[:, 0] * spins[:, -1]
         transverse = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp().sum(1)
         return -(interaction + self.h * transverse) / samples.shape[-1]
+
+
+class SWAP(_Estimator):
+    """Swap_A between two replicas (observables/entanglement.py:40-80): S_2 = -ln <SWAP_A>. The second replica is the
+    batch rolled by one row, like the reference; the importance weights psi(s') / psi(s) (or rho(s', s) / rho(s, s))
+    come from the drop-in state's CUDA energy / density-matrix paths."""
+
+    def __init__(self, A):
+        self.name, self.symbol, self.A = "SWAP", "S", A
+
+    def apply(self, nn_state, samples):
+        from .utils import cplx
+
+        s1 = samples.to(device=nn_state.device, dtype=torch.double)
+        s2 = torch.roll(s1, 1, 0)
+        s1_, s2_ = s1.clone(), s2.clone()
+        s1_[:, self.A] = s2[:, self.A]
+        s2_[:, self.A] = s1[:, self.A]
+        w1 = nn_state.importance_sampling_weight(s1_, s1)
+        w2 = nn_state.importance_sampling_weight(s2_, s2)
+        return cplx.real(cplx.elementwise_mult(w1, w2))

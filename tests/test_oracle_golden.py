@@ -202,7 +202,7 @@ def test_density_2qubits_reference_fixture():
 
 
 def test_observables_reference_fixture():
-    """SigmaX / SigmaY / SigmaZ of the reference (observables/pauli.py) and the Tutorial-4 TFIM energy on positive,
+    """SigmaX / SigmaY / SigmaZ / SWAP of the reference (observables/pauli.py, entanglement.py) and the Tutorial-4 TFIM energy on positive,
     complex and density-matrix states (tests/golden/make_golden_observables.py)."""
     g = load("observables.npz")
     t = load("binary_rbm_tfim10.npz")
@@ -216,6 +216,7 @@ def test_observables_reference_fixture():
     close(orc.pauli_magnetisation("Z", w, v, absolute=True), g["pos_abs_sigma_z"])
     close(orc.tfim_chain_energy(am, v, 1.0), g["pos_tfim_energy_h1"])
     close(orc.tfim_chain_energy(am, v, 0.5), g["pos_tfim_energy_h05"])
+    close(orc.swap_estimator(w, v, g["pos_swap_A"]), g["pos_swap"])
 
     c = load("complex_wavefunction.npz")
     cam, cph = _complex_pair(c)
@@ -225,6 +226,7 @@ def test_observables_reference_fixture():
     close(orc.pauli_magnetisation("Y", w, v), g["cwf_sigma_y"])
     close(orc.pauli_magnetisation("Y", w, v, absolute=True), g["cwf_abs_sigma_y"])
     close(orc.pauli_magnetisation("Z", w, v), g["cwf_sigma_z"])
+    close(orc.swap_estimator(w, v, g["cwf_swap_A"]), g["cwf_swap"])
 
     d = load("density_matrix.npz")
     w = orc.dm_weight(*_dm_pair(d))
@@ -232,3 +234,4 @@ def test_observables_reference_fixture():
     close(orc.pauli_magnetisation("X", w, v), g["dm_sigma_x"])
     close(orc.pauli_magnetisation("Y", w, v), g["dm_sigma_y"], 1e-11)
     close(orc.pauli_magnetisation("Z", w, v), g["dm_sigma_z"])
+    close(orc.swap_estimator(w, v, g["dm_swap_A"]), g["dm_swap"], 1e-11)

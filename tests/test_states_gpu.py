@@ -493,7 +493,7 @@ def test_observables_reference_fixture(lib, cuda):
     """The estimator classes against values computed by the reference's own observables (pauli.py SigmaX/Y/Z, the
     Tutorial-4 TFIMChainEnergy) on positive, complex and density-matrix states (tests/golden/observables.npz)."""
     from qucumber_b200 import PositiveWaveFunction
-    from qucumber_b200.observables import SigmaX, SigmaY, SigmaZ, TFIMChainEnergy
+    from qucumber_b200.observables import SWAP, SigmaX, SigmaY, SigmaZ, TFIMChainEnergy
 
     g, t = gold("observables.npz"), gold("binary_rbm_tfim10.npz")
     nn = PositiveWaveFunction(10, 10, gpu=True)
@@ -506,6 +506,7 @@ def test_observables_reference_fixture(lib, cuda):
     assert_close(SigmaZ(absolute=True).apply(nn, v), g["pos_abs_sigma_z"], what="|SigmaZ| (positive)")
     assert_close(TFIMChainEnergy(1.0).apply(nn, v), g["pos_tfim_energy_h1"], what="TFIM energy h=1")
     assert_close(TFIMChainEnergy(0.5).apply(nn, v), g["pos_tfim_energy_h05"], what="TFIM energy h=0.5")
+    assert_close(SWAP(g["pos_swap_A"].tolist()).apply(nn, v), g["pos_swap"], what="SWAP (positive)")
 
     cwf = _load_cwf(gold("complex_wavefunction.npz"), 5, 4)
     v = torch.tensor(g["cwf_states"], device=cuda)
@@ -513,12 +514,14 @@ def test_observables_reference_fixture(lib, cuda):
     assert_close(SigmaY().apply(cwf, v), g["cwf_sigma_y"], what="SigmaY (complex)")
     assert_close(SigmaY(absolute=True).apply(cwf, v), g["cwf_abs_sigma_y"], what="|SigmaY| (complex)")
     assert_close(SigmaZ().apply(cwf, v), g["cwf_sigma_z"], what="SigmaZ (complex)")
+    assert_close(SWAP(g["cwf_swap_A"].tolist()).apply(cwf, v), g["cwf_swap"], what="SWAP (complex)")
 
     dm = _load_dm(gold("density_matrix.npz"), 4, 3, 5)
     v = torch.tensor(g["dm_states"], device=cuda)
     assert_close(SigmaX().apply(dm, v), g["dm_sigma_x"], what="SigmaX (density matrix)")
     assert_close(SigmaY().apply(dm, v), g["dm_sigma_y"], what="SigmaY (density matrix)")
     assert_close(SigmaZ().apply(dm, v), g["dm_sigma_z"], what="SigmaZ (density matrix)")
+    assert_close(SWAP(g["dm_swap_A"].tolist()).apply(dm, v), g["dm_swap"], what="SWAP (density matrix)")
     assert v.cpu().numpy().tolist() == g["dm_states"].tolist()  # inputs are not modified
 
 
