@@ -405,6 +405,40 @@ def test_save_load_sample_determinism(lib, cuda, tmp_path):
                         {"weights_W", "weights_U", "visible_bias", "hidden_bias", "aux_bias"})
 
 
+@pytest.mark.parametrize("tag", ["positive", "complex", "density"])
+def test_reference_checkpoint_interchange(lib, cuda, tmp_path, tag):
+    """A checkpoint written by stock QuCumber's NeuralState.save (tests/golden/make_golden_checkpoints.py) autoloads into
+    the drop-in class, reproduces the reference's energies, and the drop-in's own save writes the same layout (keys,
+    tensor names, shapes, dtypes) so files interchange in both directions (neural_state.py:199-246)."""
+    import qucumber_b200 as qb
+
+    cls = {"positive": qb.PositiveWaveFunction, "complex": qb.ComplexWaveFunction, "density": qb.DensityMatrix}[tag]
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_checkpoint_{tag}.pt")
+    ref = torch.load(path, map_location="cpu", weights_only=False)
+    nn = cls.autoload(path, gpu=True)
+    rows = ref["rows"].to(cuda)
+    assert_close(nn.rbm_am.effective_energy(rows), ref["energy_am"].numpy(), what="energy (amplitude RBM) from a reference checkpoint")
+    if "energy_ph" in ref:
+        assert_close(nn.rbm_ph.effective_energy(rows), ref["energy_ph"].numpy(), what="energy (phase RBM) from a reference checkpoint")
+    for net in nn.networks:
+        for k, t in ref[net].items():
+            assert torch.equal(getattr(nn, net).state_dict()[k].cpu(), t), (net, k)
+    out = str(tmp_path / "mine.pt")
+    nn.save(out, metadata={"rows": ref["rows"], "epochs_done": 7})
+    mine = torch.load(out, map_location="cpu", weights_only=False)
+    assert set(mine.keys()) == set(ref.keys()) - {"energy_am", "energy_ph"}
+    for net in nn.networks:
+        assert list(mine[net].keys()) == list(ref[net].keys())
+        for k in ref[net]:
+            assert mine[net][k].dtype == ref[net][k].dtype and mine[net][k].shape == ref[net][k].shape
+    if "unitary_dict" in ref:
+        assert set(mine["unitary_dict"].keys()) == set(ref["unitary_dict"].keys())
+        for k in ref["unitary_dict"]:
+            assert torch.allclose(mine["unitary_dict"][k].cpu(), ref["unitary_dict"][k].cpu())
+    with pytest.raises(ValueError):
+        nn.save(out, metadata={"rbm_am": 1})
+
+
 def test_purification_gradient_large_batch(lib, cuda):
     from qucumber_b200 import PurificationRBM
 
