@@ -196,9 +196,10 @@ int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double
 // non-binary entry, or a layer whose products could leave the double range (sum_o max_i |W_oi| > 700, non-finite
 // weights), takes the term-by-term path with the thresholded softplus instead (always when TAB = false: tables do
 // not fit in shared memory).  A warp handles RW = 32 / N rows at a time so that small layers use all lanes; for
-// binary rows of up to 64 units theta is accumulated over the SET bits only (adding W_oi in ascending i: bit-identical
-// to the dense FMA loop for finite weights), and layers wider than 32 give each lane two columns that share the
-// (sigma, tau) loads — the kernel is bound by shared-memory wavefronts, not by the FP64 pipe.
+// binary rows of 33..64 units (one row per warp pass) theta is accumulated over the SET bits only (adding W_oi in
+// ascending i: bit-identical to the dense FMA loop for finite weights) and each lane takes two columns that share the
+// (sigma, tau) loads.  The kernel is bound by instruction issue (N = 10: 72 % of the issue slots) and shared-memory
+// wavefronts, not by the FP64 pipe; sigma / tau use the table exponential and a Newton reciprocal.
 struct FlipGeom { int RW, PW; };  // rows per warp pass, doubles of per-warp scratch (even)
 inline FlipGeom flip_geom(int N, int H) {
   int rw = 32 / N;
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
   stage_affine(s, Ws, LD, bs);
   for (int i = threadIdx.x; i < N; i += blockDim.x) vbs[i] = vb[i];
   if (threadIdx.x == 0) *cta_slow = TAB ? 0u : 0xffffffffu;
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
   __syncthreads();
   if (TAB) {
     for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) {
@@ -263,7 +266,11 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
-  const bool sparse_ok = TAB && N <= 64 && *cta_slow == 0u;
+  // set-bit accumulation of theta pays when a warp walks ONE row (33..64 units: uniform trip count, half the loads);
+  // with several short rows per warp the lanes' trip counts diverge and the dense loop is cheaper
+  const bool sparse_ok = TAB && N > 32 && N <= 64 && *cta_slow == 0u;
+  const int rrH0 = lane / H, oH0 = lane - rrH0 * H;  // (row, unit) of a lane in the first pass of each loop, hoisted
+  const int rrN0 = lane / N, iN0 = lane - rrN0 * N;
   for (int64_t g = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); g * RW < rows; g += (int64_t)gridDim.x * WARPS) {
     const int64_t r0 = g * RW;
     const int nr = (int)(rows - r0 < RW ? rows - r0 : RW);
@@ -283,17 +290,17 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
     __syncwarp();
     const unsigned f0 = *flag;  // non-binary rows so far
     for (int e = lane; e < nr * H; e += 32) {
-      const int rr = e / H, o = e - rr * H;
+      const int rr = e < 32 ? rrH0 : e / H, o = e < 32 ? oH0 : e - rr * H;
       const double* wrow = Ws + (size_t)o * LD;
       double t = bs[o];
       if (sparse_ok && !((f0 >> rr) & 1u)) {
-        unsigned m = N > 32 ? bits[0] : (bits[0] >> (rr * N)) & (0xffffffffu >> (32 - N));
+        unsigned m = bits[0];  // one row per pass here (N > 32)
         while (m) {
           const int i = __ffs(m) - 1;
           m &= m - 1;
           t += wrow[i];
         }
-        m = N > 32 ? bits[1] : 0u;
+        m = bits[1];
         while (m) {
           const int i = __ffs(m) - 1;
           m &= m - 1;
@@ -306,8 +313,13 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
       th[e] = t;
       if (TAB) {
         if (!(t + wmax[o] <= 20.0)) atomicOr(flag, 1u << rr);
-        const double ex = exp(t);
-        const double tau = 1.0 / (1.0 + ex);
+        // sigma, tau with the table exponential and a Newton reciprocal (only used when t <= 20, see above)
+        const double ex = exp_tab(fmin(fmax(t, -700.0), 700.0), e2tab);
+        const double dn = 1.0 + ex;
+        double tau;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(tau) : "d"(dn));
+        tau = fma(tau, fma(-dn, tau, 1.0), tau);
+        tau = fma(tau, fma(-dn, tau, 1.0), tau);
         st[e] = make_double2(ex * tau, tau);
       }
     }
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
       }
     } else {
       for (int e = lane; e < nr * N; e += 32) {
-        const int rr = e / N, i = e - rr * N;
+        const int rr = e < 32 ? rrN0 : e / N, i = e < 32 ? iN0 : e - rr * N;
         const double x = vrow[e];
         const double sgn = 1.0 - 2.0 * x;  // flipping a binary unit changes it by +-1
         double d = sgn * vbs[i];

@@ -48,8 +48,7 @@ class _Estimator:
     def statistics_from_samples(self, nn_state, samples):
         """mean / variance / std_error / num_samples of the estimator over the given samples."""
         obs = self.apply(nn_state, samples)
-        variance, mean = torch.var_mean(obs)
-        variance, mean = variance.item(), mean.item()
+        variance, mean = torch.stack(torch.var_mean(obs)).tolist()  # one device-to-host read
         return {"mean": mean, "variance": variance, "std_error": float(np.sqrt(variance / len(obs))), "num_samples": len(obs)}
 
     def statistics(self, nn_state, num_samples, num_chains=0, burn_in=1000, steps=1):
@@ -78,8 +77,8 @@ class SigmaZ(_Estimator):
         self.name, self.symbol, self.absolute = "SigmaZ", "Z", absolute
 
     def apply(self, nn_state, samples):
-        res = samples.to(device=nn_state.device, dtype=torch.double).mul(2.0).sub(1.0).mean(1)
-        return res.abs() if self.absolute else res
+        res = samples.to(device=nn_state.device, dtype=torch.double).mean(1).mul_(2.0).sub_(1.0)  # mean of the +-1 spins
+        return res.abs_() if self.absolute else res
 
 
 class SigmaX(_Estimator):
@@ -91,9 +90,9 @@ class SigmaX(_Estimator):
     def apply(self, nn_state, samples):
         samples = samples.to(device=nn_state.device, dtype=torch.double)
         if _is_wavefunction(nn_state):
-            ratio = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp()
+            ratio = flip_logratio(nn_state.rbm_am, samples).mul_(0.5).exp_()  # fresh tensor: in place
             if getattr(nn_state, "rbm_ph", None) is not None:
-                ratio = ratio * (0.5 * flip_logratio(nn_state.rbm_ph, samples)).cos()
+                ratio.mul_(flip_logratio(nn_state.rbm_ph, samples).mul_(0.5).cos_())
             res = ratio.mean(1)
         else:
             res = _importance_sampled_pauli(nn_state, samples, "X")
@@ -133,7 +132,7 @@ class TFIMChainEnergy(_Estimator):
         interaction = (spins[:, :-1] * spins[:, 1:]).sum(1)
         if self.periodic_bcs:
             interaction = interaction + spins[:, 0] * spins[:, -1]
-        transverse = (0.5 * flip_logratio(nn_state.rbm_am, samples)).exp().sum(1)
+        transverse = flip_logratio(nn_state.rbm_am, samples).mul_(0.5).exp_().sum(1)
         return -(interaction + self.h * transverse) / samples.shape[-1]
 
 
