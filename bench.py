@@ -343,7 +343,9 @@ def extra_metrics(dev, lib_mod):
             tf = rows * 4 * nv * nhd / (ms_g * 1e-3) / 1e12
             res[name] = {"N": nv, "nh": nhd, "rows": rows, "ms": ms_g, "hbm_gbps": gbs, "hbm_frac": gbs / hbm_peak,
                          "fp64_tflops": tf, "fp64_frac_of_dmma_peak": tf / 37.117,
-                         # floors: HBM = N*8 B per row; FP64 pipe = the contraction (4*N*nh flop) plus nh exact sigmoids (~50 DFMA each)
+                         # floors: HBM = N*8 B per row; FP64 pipe with both contractions in FP64 (4*N*nh flop) plus nh sigmoids
+                         # (~50 DFMA each).  Binary rows of 25..64-unit layers take theta from exact int8 tensor-core sums
+                         # (DESIGN.md 3.3), which halves the FP64 contraction work: the frac above counts ALGORITHMIC flop.
                          "hbm_floor_ms": rows * nv * 8 / (hbm_peak * 1e9) * 1e3,
                          "fp64_floor_ms": rows * (2 * nv * nhd + 50 * nhd) / 18.4e12 * 1e3}
         res["hbm_peak_gbps"] = hbm_peak
