@@ -347,6 +347,8 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const Enu
   double* ebm = ebp + round_up(N, 2);
   double* red = ebm + round_up(N, 2);  // 8 doubles per warp
   stage_enum<NHT>(a.p, Wt, hb, vb);
+  __shared__ double2 ltab[LOG_TABLE];
+  fill_log_table(ltab);
   __syncthreads();
   for (int idx = threadIdx.x; idx < N * NHT; idx += blockDim.x) {
     const int i = idx % NHT;
@@ -422,8 +424,8 @@ __global__ void __launch_bounds__(ENUM_THREADS) enum_stats_fast_kernel(const Enu
           sums[0] = fma(tr, psi, sums[0]);
           sums[1] = fma(ti, psi, sums[1]);
           const double pt = tr * tr + ti * ti;
-          sums[2] = fma(pt, log(fmin(fmax(pt, eps), 1.0 - eps)), sums[2]);
-          sums[3] = fma(pt, log(fmin(fmax(p, eps), 1.0 - eps)), sums[3]);
+          sums[2] = fma(pt, log_tab(fmin(fmax(pt, eps), 1.0 - eps), ltab), sums[2]);  // arguments in [2^-52, 1): normal
+          sums[3] = fma(pt, log_tab(fmin(fmax(p, eps), 1.0 - eps), ltab), sums[3]);
         }
       }
       if (k + 1 < steps) {
