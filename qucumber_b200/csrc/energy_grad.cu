@@ -240,7 +240,9 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
   for (int i = threadIdx.x; i < N; i += blockDim.x) vbs[i] = vb[i];
   if (threadIdx.x == 0) *cta_slow = TAB ? 0u : 0xffffffffu;
   __shared__ double e2tab[EXP2_TABLE];
+  __shared__ double2 ltab[LOG_TABLE];
   fill_exp2_table(e2tab);
+  fill_log_table(ltab);
   __syncthreads();
   if (TAB) {
     for (int idx = threadIdx.x; idx < H * N; idx += blockDim.x) {
@@ -345,8 +347,8 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
           p *= fma(a.x, T1[(size_t)o * LD], a.y);
           q *= fma(a.x, T2[(size_t)o * LD], a.y);
         }
-        out[r0 * N + i] = fma(1.0 - 2.0 * x1, vbs[i], log(p));
-        if (two) out[r0 * N + i2] = fma(1.0 - 2.0 * x2, vbs[i2], log(q));
+        out[r0 * N + i] = fma(1.0 - 2.0 * x1, vbs[i], log_tab(p, ltab));
+        if (two) out[r0 * N + i2] = fma(1.0 - 2.0 * x2, vbs[i2], log_tab(q, ltab));
       }
     } else {
       for (int e = lane; e < nr * N; e += 32) {
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(1024) rows_flip_kernel(AffineSpec s, const dou
             p1 *= fma(a[o + 1].x, T[(size_t)(o + 1) * LD], a[o + 1].y);
           }
           if (o < H) p0 *= fma(a[o].x, T[(size_t)o * LD], a[o].y);
-          d += log(p0 * p1);
+          d += log_tab(p0 * p1, ltab);  // the product is a normal positive double (sum of max |W| <= 700)
         }
         out[r0 * N + e] = d;
       }
