@@ -583,6 +583,36 @@ def test_calls_are_capturable_in_a_cuda_graph(lib, cuda):
         assert_close(g_out, want_g.cpu().numpy(), what="gradient from a replayed graph")
 
 
+@pytest.mark.parametrize("binary", [True, False])
+def test_large_batch_gradient_is_capturable(lib, cuda, binary):
+    """The large-batch gradient is a memset of the flag word, the integer-theta kernel and the FP64 kernel behind it,
+    selected on the device: the sequence captures into a CUDA graph and replays correctly for 0/1 rows (integer path)
+    and for real rows (flag raised, FP64 kernel does the batch) with the SAME captured graph shape."""
+    from qucumber_b200 import BinaryRBM
+
+    n, nh, rows = 48, 40, 16384 + 5
+    W, b, c = make_binary_params(n, nh, 211)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    rng = np.random.default_rng(212)
+    first = random_states(rows, n, 213) if binary else rng.standard_normal((rows, n))
+    second = rng.standard_normal((rows, n)) if binary else random_states(rows, n, 214)  # replay with the other kind of rows
+    static_v = torch.tensor(first, device=cuda)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        rbm.effective_energy_gradient(static_v)  # warm-up
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            g_out = rbm.effective_energy_gradient(static_v)
+    torch.cuda.current_stream().wait_stream(s)
+    for rows_np in (first, second, first):
+        static_v.copy_(torch.tensor(rows_np))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert_close(g_out, o.effective_energy_gradient(rows_np), what="large-batch gradient from a replayed graph")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_one_process_two_devices(lib, cuda):
     """A model living on cuda:1 while the current device stays cuda:0 runs on cuda:1 (the library switches to the
