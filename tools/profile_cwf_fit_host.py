@@ -1,6 +1,13 @@
-import cProfile, pstats, sys, os
-import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+"""Host-side cProfile of the two-qubit trainings (Tutorial-2 / Tutorial-3 style): where the per-batch Python time goes."""
+import cProfile
+import os
+import pstats
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qucumber_b200 import ComplexWaveFunction, DensityMatrix
 rng = np.random.default_rng(3)
 bases_all = ["XX", "XY", "XZ", "YX", "YY", "YZ", "ZX", "ZY", "ZZ"]

@@ -1,5 +1,10 @@
-import os, sys, torch
-sys.path.insert(0, "/root/repo")
+"""Two fused epochs of a 64 x 64 PositiveWaveFunction fit (target of an ncu capture of cd_epoch_wide_kernel)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qucumber_b200 import PositiveWaveFunction
 torch.manual_seed(0)
 n = 64
