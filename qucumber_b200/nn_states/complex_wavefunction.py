@@ -3,6 +3,7 @@ import torch
 
 from ..rbm import BinaryRBM
 from ..utils import unitaries
+from .neural_state import stored_attribute
 from .wavefunction import WaveFunctionBase
 
 
@@ -14,6 +15,9 @@ class ComplexWaveFunction(WaveFunctionBase):
     _rbm_am = None
     _rbm_ph = None
     _device = None
+    rbm_am = stored_attribute("_rbm_am")
+    rbm_ph = stored_attribute("_rbm_ph")
+    device = stored_attribute("_device")
 
     def __init__(self, num_visible, num_hidden=None, unitary_dict=None, gpu=True, module=None):
         if module is not None:
@@ -29,30 +33,6 @@ class ComplexWaveFunction(WaveFunctionBase):
     @property
     def networks(self):
         return ["rbm_am", "rbm_ph"]
-
-    @property
-    def rbm_am(self):
-        return self._rbm_am
-
-    @rbm_am.setter
-    def rbm_am(self, new_val):
-        self._rbm_am = new_val
-
-    @property
-    def rbm_ph(self):
-        return self._rbm_ph
-
-    @rbm_ph.setter
-    def rbm_ph(self, new_val):
-        self._rbm_ph = new_val
-
-    @property
-    def device(self):
-        return self._device
-
-    @device.setter
-    def device(self, new_val):
-        self._device = new_val
 
     def phase(self, v):
         """-E_ph(v) / 2 (complex_wavefunction.py:129-142)."""

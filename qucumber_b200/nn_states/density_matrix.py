@@ -4,13 +4,16 @@ import torch
 
 from ..rbm import PurificationRBM
 from ..utils import cplx, unitaries
-from .neural_state import NeuralStateBase
+from .neural_state import NeuralStateBase, stored_attribute
 
 
 class DensityMatrix(NeuralStateBase):
     _rbm_am = None
     _rbm_ph = None
     _device = None
+    rbm_am = stored_attribute("_rbm_am")
+    rbm_ph = stored_attribute("_rbm_ph")
+    device = stored_attribute("_device")
 
     def __init__(self, num_visible, num_hidden=None, num_aux=None, unitary_dict=None, gpu=True, module=None):
         if module is not None:
@@ -27,30 +30,6 @@ class DensityMatrix(NeuralStateBase):
     @property
     def networks(self):
         return ["rbm_am", "rbm_ph"]
-
-    @property
-    def rbm_am(self):
-        return self._rbm_am
-
-    @rbm_am.setter
-    def rbm_am(self, new_val):
-        self._rbm_am = new_val
-
-    @property
-    def rbm_ph(self):
-        return self._rbm_ph
-
-    @rbm_ph.setter
-    def rbm_ph(self, new_val):
-        self._rbm_ph = new_val
-
-    @property
-    def device(self):
-        return self._device
-
-    @device.setter
-    def device(self, new_val):
-        self._device = new_val
 
     def _mix_terms(self, v, vp, expand):
         """Arguments of the Pi matrix: (1/2)[U_am(v + v') + 2 d_am] and (1/2) U_ph (v - v')

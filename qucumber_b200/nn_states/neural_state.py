@@ -42,6 +42,13 @@ class _Callbacks:
                 fn(*args)
 
 
+def stored_attribute(slot):
+    """A settable property over a plain instance slot. The reference exposes ``rbm_am`` / ``rbm_ph`` / ``device`` as
+    settable properties (e.g. complex_wavefunction.py:74-103) so that a module can be swapped in from outside —
+    INTEGRATION.md section 1 relies on exactly that; the subclasses here declare them with this helper."""
+    return property(lambda self: getattr(self, slot), lambda self, value: setattr(self, slot, value))
+
+
 class NeuralStateBase(abc.ABC):
     """Abstract base class for neural-network quantum states backed by CUDA RBMs."""
 

@@ -2,6 +2,7 @@
 import torch
 
 from ..rbm import BinaryRBM
+from .neural_state import stored_attribute
 from .wavefunction import WaveFunctionBase
 
 
@@ -10,6 +11,8 @@ class PositiveWaveFunction(WaveFunctionBase):
 
     _rbm_am = None
     _device = None
+    rbm_am = stored_attribute("_rbm_am")
+    device = stored_attribute("_device")
 
     def __init__(self, num_visible, num_hidden=None, gpu=True, module=None):
         if module is None:
@@ -24,22 +27,6 @@ class PositiveWaveFunction(WaveFunctionBase):
     @property
     def networks(self):
         return ["rbm_am"]
-
-    @property
-    def rbm_am(self):
-        return self._rbm_am
-
-    @rbm_am.setter
-    def rbm_am(self, new_val):
-        self._rbm_am = new_val
-
-    @property
-    def device(self):
-        return self._device
-
-    @device.setter
-    def device(self, new_val):
-        self._device = new_val
 
     def phase(self, v):
         """Identically zero (positive_wavefunction.py:95-106)."""
