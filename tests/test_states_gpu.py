@@ -363,6 +363,41 @@ def test_fit_fused_epoch_equals_per_batch_path(lib, cuda):
     assert hook.n == 11
 
 
+@pytest.mark.parametrize("kind", ["complex", "density"])
+def test_fit_reaches_reference_training_targets(lib, cuda, kind):
+    """The reference's own training regression for states with rotated bases (tests/test_training.py:143-279, `slow`):
+    5 epochs of CD-10 at lr = 0.1 on the Tutorial-2 / Tutorial-3 data, fidelity and KL averaged over repeated runs must
+    land on the reference's targets (0.38 / 0.33 from its fixed initial parameters; 0.45 / 0.42 from random initial
+    parameters). The reference asserts +-0.02 on ten runs; the kernels draw from a different RNG, so: 8 / 12 runs, +-0.03."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+    from qucumber_b200.utils import training_statistics as ts
+
+    g = gold("training_2qubits.npz")
+    tag = "cwf" if kind == "complex" else "dm"
+    samples = torch.tensor(g[f"{tag}_samples"].astype(np.float64))
+    train_bases = split_bases(g[f"{tag}_train_bases"])
+    bases = [str(b) for b in g[f"{tag}_bases"]]
+    target = torch.tensor(g["cwf_target_psi" if kind == "complex" else "dm_target_rho"], device=cuda)
+    fids, kls = [], []
+    for run in range(8 if kind == "complex" else 12):  # random initial parameters spread more: more runs
+        torch.manual_seed(4000 + run)
+        if kind == "complex":
+            nn = ComplexWaveFunction(2, 2, gpu=True)
+            load_binary(nn.rbm_am, g["cwf_init_am_weights"], g["cwf_init_am_visible_bias"], g["cwf_init_am_hidden_bias"])
+            load_binary(nn.rbm_ph, g["cwf_init_ph_weights"], g["cwf_init_ph_visible_bias"], g["cwf_init_ph_hidden_bias"])
+        else:
+            nn = DensityMatrix(2, gpu=True)
+            nn.reinitialize_parameters()
+        nn.fit(samples, epochs=5, pos_batch_size=int(g[f"{tag}_pos_batch"]), neg_batch_size=int(g[f"{tag}_neg_batch"]), k=10, lr=0.1,
+               input_bases=train_bases)
+        space = nn.generate_hilbert_space()
+        fids.append(ts.fidelity(nn, target, space))
+        kls.append(ts.KL(nn, target, space, bases=bases))
+    assert abs(np.mean(fids) - float(g[f"{tag}_fid_target"])) < 0.03, fids
+    assert abs(np.mean(kls) - float(g[f"{tag}_kl_target"])) < 0.03, kls
+    assert np.std(fids) / np.sqrt(len(fids)) < 0.02 and np.std(kls) / np.sqrt(len(kls)) < 0.02
+
+
 def test_fit_complex_and_density_smoke(lib, cuda):
     """Parameters move after one epoch with mixed bases (reference tests/test_training.py:40-70)."""
     from qucumber_b200 import ComplexWaveFunction, DensityMatrix
