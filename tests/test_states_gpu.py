@@ -398,6 +398,114 @@ def test_fit_reaches_reference_training_targets(lib, cuda, kind):
     assert np.std(fids) / np.sqrt(len(fids)) < 0.02 and np.std(kls) / np.sqrt(len(kls)) < 0.02
 
 
+def test_stop_training_semantics(lib, cuda):
+    """stop_training set before fit() leaves the parameters untouched; set from a batch hook it ends the loop after that
+    batch, from an epoch hook after that epoch (reference tests/test_training.py:86-141); non-boolean values are refused."""
+    from torch.nn.utils import parameters_to_vector
+
+    from qucumber_b200 import PositiveWaveFunction
+
+    data = torch.ones(100, 10)
+    nn = PositiveWaveFunction(10, gpu=True)
+    before = parameters_to_vector(nn.rbm_am.parameters()).clone()
+    nn.stop_training = True
+    nn.fit(data)
+    assert torch.equal(before, parameters_to_vector(nn.rbm_am.parameters()))
+    with pytest.raises(ValueError):
+        nn.stop_training = "yes"
+
+    class StopInBatch:
+        seen = []
+
+        def on_batch_end(self, state, ep, b):
+            self.seen.append((ep, b))
+            state.stop_training = True
+
+    hook = StopInBatch()
+    nn = PositiveWaveFunction(10, gpu=True)
+    nn.fit(data, epochs=3, pos_batch_size=10, callbacks=[hook])
+    assert nn.stop_training and hook.seen == [(1, 0)]
+
+    class StopInEpoch:
+        seen = []
+
+        def on_epoch_end(self, state, ep):
+            self.seen.append(ep)
+            state.stop_training = True
+
+    hook = StopInEpoch()
+    nn = PositiveWaveFunction(10, gpu=True)
+    before = parameters_to_vector(nn.rbm_am.parameters()).clone()
+    nn.fit(data, epochs=3, pos_batch_size=10, callbacks=[hook])
+    assert nn.stop_training and hook.seen == [1]
+    assert not torch.equal(before, parameters_to_vector(nn.rbm_am.parameters()))  # the first epoch did train
+
+
+@pytest.mark.parametrize("what", ["rho", "pi", "gamma+", "gamma-", "pi_grad_phase", "pi_grad", "gamma_grad+", "gamma_grad-"])
+def test_density_matrix_expansion_invariants(lib, cuda, what):
+    """Algebraic invariants of the density-matrix layouts (reference tests/test_models_misc.py:148-234): rho / Z is
+    Hermitian with unit trace, rho(v, vp) has shape (2, |v|, |vp|), and the diagonal of every expand=True matrix equals
+    its expand=False evaluation."""
+    from qucumber_b200 import DensityMatrix
+    from qucumber_b200.utils import cplx
+
+    torch.manual_seed(17)
+    nn = DensityMatrix(5, gpu=True)
+    v = nn.generate_hilbert_space(5)
+    vp = v[torch.randperm(v.shape[0], device=v.device), :]
+    if what == "rho":
+        rho = nn.rho(v, v) / nn.normalization(v)
+        herm = cplx.conjugate(rho)
+        assert float((rho - herm).abs().max()) <= 1e-15 * float(rho.abs().max())
+        assert abs(float(torch.trace(rho[0])) - 1.0) <= 2e-8
+        assert nn.rho(v, v[:4]).shape == (2, 32, 4)
+        assert_close(torch.einsum("cii->ci", nn.rho(v, expand=True)), nn.rho(v, expand=False).cpu().numpy(), what="diagonal of rho")
+    fn, args, is_complex = {
+        "rho": (nn.rho, (), True), "pi": (nn.pi, (), True),
+        "gamma+": (nn.rbm_am.gamma, (+1,), False), "gamma-": (nn.rbm_am.gamma, (-1,), False),
+        "pi_grad_phase": (nn.pi_grad, (True,), True), "pi_grad": (nn.pi_grad, (False,), True),
+        "gamma_grad+": (nn.rbm_am.gamma_grad, (+1,), True), "gamma_grad-": (nn.rbm_am.gamma_grad, (-1,), True),
+    }[what]
+    full = fn(v, vp, *args, expand=True)
+    diag = fn(v, vp, *args, expand=False)
+    got = torch.einsum("cii...->ci..." if is_complex else "ii->i", full)
+    scale = max(float(diag.abs().max()), 1.0)
+    assert got.shape == diag.shape
+    assert float((got - diag).abs().max()) <= 2e-8 * scale, what
+
+
+def test_hilbert_space_guard_and_rotations_cross_check(lib, cuda):
+    """generate_hilbert_space refuses sizes above max_size (reference tests/test_models_misc.py:285-297); the fast full
+    space rotation equals the explicit Kronecker product and the per-sample inner products over the full space, for
+    wavefunctions and density matrices, N in {1, 2, 7}, all sites in X (:300-384)."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+    from qucumber_b200.utils import cplx
+    from qucumber_b200.utils import unitaries as un
+
+    nn = ComplexWaveFunction(3, gpu=True)
+    with pytest.raises(ValueError):
+        nn.generate_hilbert_space(nn.max_size + 1)
+    r = 1.0 / np.sqrt(2.0)
+    X = np.array([[r, r], [r, -r]], dtype=np.complex128)
+    for n in (1, 2, 7):
+        torch.manual_seed(30 + n)
+        basis = np.array(["X"] * n)
+        U = np.array([[1.0]], dtype=np.complex128)
+        for _ in range(n):
+            U = np.kron(U, X)
+        cwf = ComplexWaveFunction(n, gpu=True)
+        space = cwf.generate_hilbert_space()
+        psi = cpx(cwf.psi(space))
+        assert_close(cpx(un.rotate_psi(cwf, basis, space)), U @ psi, rtol=1e-12, what=f"rotate_psi vs Kronecker product, N={n}")
+        assert_close(cpx(un.rotate_psi_inner_prod(cwf, basis, space)), U @ psi, rtol=1e-12, what=f"rotate_psi_inner_prod, N={n}")
+        if n <= 2:
+            dm = DensityMatrix(n, gpu=True)
+            rho = cpx(dm.rho(space, space))
+            want = U @ rho @ U.conj().T
+            assert_close(cpx(un.rotate_rho(dm, basis, space)), want, rtol=1e-12, what=f"rotate_rho vs Kronecker product, N={n}")
+            assert_close(un.rotate_rho_probs(dm, basis, space), np.diag(want).real, rtol=1e-12, what=f"rotate_rho_probs, N={n}")
+
+
 def test_fit_complex_and_density_smoke(lib, cuda):
     """Parameters move after one epoch with mixed bases (reference tests/test_training.py:40-70)."""
     from qucumber_b200 import ComplexWaveFunction, DensityMatrix
