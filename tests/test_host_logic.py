@@ -167,3 +167,55 @@ def test_two_rank_combine_logic_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_complex_helper_algebra():
+    """utils/cplx.py against numpy complex arithmetic on random inputs (what the reference's tests/test_cplx.py pins with
+    literal tensors): construction, products, conjugation, division, norms, Kronecker products, the complex sigmoid,
+    and the error cases for mismatched shapes."""
+    from qucumber_b200.utils import cplx
+
+    rng = np.random.default_rng(5)
+
+    def rand(*shape):
+        z = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        return z, cplx.make_complex(torch.tensor(z.real), torch.tensor(z.imag))
+
+    def same(t, z, tol=1e-13):
+        got = cplx.numpy(t) if t.shape[0] == 2 and t.dim() == np.ndim(z) + 1 else t.numpy()
+        assert got.shape == np.shape(z), (got.shape, np.shape(z))
+        assert np.allclose(got, z, rtol=tol, atol=tol)
+
+    s, S = rand()            # scalar
+    v, V = rand(5)           # vector
+    w, W = rand(5)
+    m, M = rand(4, 5)        # matrices
+    k, K = rand(5, 3)
+    q, Q = rand(4, 5)
+    assert torch.equal(cplx.make_complex(torch.tensor([1.0, 2.0])), torch.tensor([[1.0, 2.0], [0.0, 0.0]]))
+    assert torch.equal(cplx.real(V), torch.tensor(v.real)) and torch.equal(cplx.imag(V), torch.tensor(v.imag))
+    same(cplx.scalar_mult(S, V), s * v)
+    same(cplx.scalar_mult(V, W), v * w)
+    same(cplx.elementwise_mult(M, Q), m * q)
+    same(cplx.elementwise_division(M, Q), m / q)
+    same(cplx.scalar_divide(V, S), v / s)
+    same(cplx.matmul(M, K), m @ k)
+    same(cplx.matmul(M, V), m @ v)
+    same(cplx.inner_prod(V, W), np.vdot(v, w))
+    same(cplx.inner_prod(S, cplx.make_complex(torch.tensor(2.0), torch.tensor(-1.0))), np.conj(s) * (2 - 1j))
+    same(cplx.outer_prod(V, W), np.outer(v, w))
+    same(cplx.einsum("ij,jk->ik", M, K), m @ k)
+    assert np.allclose(cplx.einsum("ij,jk->ik", M, K, imag_part=False).numpy(), (m @ k).real)
+    assert np.allclose(cplx.einsum("ij,jk->ik", M, K, real_part=False).numpy(), (m @ k).imag)
+    same(cplx.conjugate(M), m.conj().T)
+    same(cplx.conjugate(V), v.conj())
+    same(cplx.conj(M), m.conj())
+    assert np.allclose(cplx.absolute_value(M).numpy(), np.abs(m))
+    same(cplx.kronecker_prod(M, K), np.kron(m, k))
+    same(cplx.sigmoid(torch.tensor(m.real), torch.tensor(m.imag)), 1.0 / (1.0 + np.exp(-m)))
+    same(cplx.inverse(M), 1.0 / m)
+    assert np.isclose(float(cplx.norm_sqr(V)), np.vdot(v, v).real) and np.isclose(float(cplx.norm(V)), np.linalg.norm(v))
+    for bad in (lambda: cplx.elementwise_division(M, K), lambda: cplx.outer_prod(M, V), lambda: cplx.kronecker_prod(M, V),
+                lambda: cplx.inner_prod(M, V), lambda: cplx.einsum("i,i->", V, W, real_part=False, imag_part=False)):
+        with pytest.raises(ValueError):
+            bad()
