@@ -702,6 +702,29 @@ def test_observables_reference_fixture(lib, cuda):
     assert v.cpu().numpy().tolist() == g["dm_states"].tolist()  # inputs are not modified
 
 
+@pytest.mark.parametrize("n", [2, 7])
+@pytest.mark.parametrize("kind", ["positive", "complex", "density"])
+def test_observables_smoke_every_estimator_every_state(lib, cuda, kind, n):
+    """Every estimator on every state type: apply returns one value per sample, statistics_from_samples / statistics
+    return the reference's four keys with the requested sample count (reference tests/test_observables.py:200-268)."""
+    import qucumber_b200 as qb
+    from qucumber_b200.observables import SWAP, SigmaX, SigmaY, SigmaZ
+
+    torch.manual_seed(50 + n)
+    nn = {"positive": lambda: qb.PositiveWaveFunction(n, gpu=True), "complex": lambda: qb.ComplexWaveFunction(n, gpu=True),
+          "density": lambda: qb.DensityMatrix(n, gpu=True)}[kind]()
+    samples = nn.sample(k=10, num_samples=100)
+    for obs in (SigmaX(), SigmaX(absolute=True), SigmaY(), SigmaZ(), SigmaZ(absolute=True), SWAP([0])):
+        vals = obs.apply(nn, samples)
+        assert vals.shape == (100,) and bool(torch.isfinite(vals).all()), (obs.name, kind)
+        st = obs.statistics_from_samples(nn, samples)
+        assert set(st) == {"mean", "variance", "std_error", "num_samples"} and st["num_samples"] == 100
+        st = obs.statistics(nn, num_samples=250, num_chains=100, burn_in=5, steps=2)
+        assert st["num_samples"] == 250 and np.isfinite(st["mean"]) and st["variance"] >= 0.0
+    if kind == "positive":
+        assert float(SigmaY().apply(nn, samples).abs().max()) == 0.0
+
+
 def test_observables_tutorial4_style(lib, cuda):
     """Config 3 in miniature: sample many chains (N = 10, k = 100), then SigmaZ / SigmaX / TFIM-energy
     estimates; checked (a) sample by sample against the oracle's psi ratios, (b) statistically against
