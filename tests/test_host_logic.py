@@ -219,3 +219,19 @@ def test_complex_helper_algebra():
                 lambda: cplx.inner_prod(M, V), lambda: cplx.einsum("i,i->", V, W, real_part=False, imag_part=False)):
         with pytest.raises(ValueError):
             bad()
+
+
+def test_every_golden_fixture_has_a_committed_generator():
+    """Each file under tests/golden/ is written by one of the committed make_golden*.py scripts (which import the
+    reference read-only in the build container) — no fixture of unknown origin."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    scripts = sorted(f for f in os.listdir(gold) if f.startswith("make_golden") and f.endswith(".py"))
+    assert scripts, "generator scripts missing"
+    source = "".join(open(os.path.join(gold, f)).read() for f in scripts)
+    for name in sorted(os.listdir(gold)):
+        if name in scripts or name.startswith("__"):
+            continue
+        stem, ext = os.path.splitext(name)
+        assert ext in (".npz", ".pt"), name
+        prefix = stem.rsplit("_", 1)[0] + "_"  # e.g. binary_rbm_{tag}.npz, ref_checkpoint_{tag}.pt
+        assert name in source or (prefix in source and ext in source), f"{name}: no generator writes it"
