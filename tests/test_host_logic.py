@@ -235,3 +235,30 @@ def test_every_golden_fixture_has_a_committed_generator():
         assert ext in (".npz", ".pt"), name
         prefix = stem.rsplit("_", 1)[0] + "_"  # e.g. binary_rbm_{tag}.npz, ref_checkpoint_{tag}.pt
         assert name in source or (prefix in source and ext in source), f"{name}: no generator writes it"
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` runs without a GPU (it times the CPU restatement of the reference's operator sequence)
+    and prints ONE JSON line with the contract's keys; ranks other than 0 exit 0 without output."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    run = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [ln for ln in run.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+    assert "workload" in d["config"] and d["vs_baseline"] is None and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    env.update(RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29871")
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=120, env=env, cwd=root)
+    assert other.returncode == 0 and other.stdout.strip() == ""
