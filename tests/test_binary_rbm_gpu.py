@@ -3,6 +3,8 @@
 Mirrors the reference's tests/test_models_misc.py (aliasing, 1-D inputs, seed replay) and the
 property style of tests/test_grads.py, with the tolerance the north star states: 1e-10 relative
 for energies/gradients/normalisations, bit-exact samples under fed uniforms."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -674,3 +676,32 @@ def test_cd_step_with_zero_sweeps(lib, cuda):
     _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, 0, 1, 0, 0, 1.0 / B, -1.0 / C, _lib.ptr(g), _lib.ptr(ws),
                                    ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
     assert_close(g, want, what="CD-0 gradient")
+
+
+def test_bench_json_contract(lib, cuda):
+    """`python bench.py` prints ONE JSON line on stdout (everything else goes to stderr) with the driver's keys: the metric
+    and its config, device-timed value, roofline, CPU baseline, end-to-end figure with its copy sizes, launch count, clocks."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    run = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--chains", "131072",
+                          "--ref-chains", "16384"], capture_output=True, text=True, timeout=900, env=env, cwd=root)
+    assert run.returncode == 0, run.stderr[-3000:]
+    lines = [ln for ln in run.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines[:3]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 1e8 and d["gpu_launches"] > 0
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"] and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 131072 * 64 * 8 and e["d2h_bytes_per_step"] >= 131072 * 64 * 8
+    assert e["value"] < d["value"]  # host buffers and copies inside the timed region
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
