@@ -140,7 +140,9 @@ int qcb_rbm_energy(const double* W, const double* U, const double* b, const doub
  * g (G) = [accumulate ? g : 0] + scale * sum_r grad E(v_r), grad E(v) = -[p_h (x) v, (p_a (x) v,) v, p_h (, p_a)].
  * Replaces effective_energy_gradient(v, reduce=True) (rbm/binary_rbm.py:98-120;
  * rbm/purification_rbm.py:160-185) and the 1/batch scalings of
- * nn_states/neural_state.py:383,445. */
+ * nn_states/neural_state.py:383,445.  v may hold arbitrary reals like the reference's; batches of 0/1 rows take a
+ * faster exact-integer evaluation of the pre-activations that is selected on the device (a flag word in ws), so the
+ * call never synchronises and can be captured in a CUDA graph either way. */
 int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const double* c, const double* d,
                         int N, int nh, int na, const double* v, int64_t rows, double scale,
                         double* g, int accumulate, void* ws, size_t ws_bytes, void* stream);
