@@ -28,7 +28,7 @@ constexpr int GD_TR = 8 * GD_WARPS;  // rows per tile: warp w owns rows 8w .. 8w
 // weight within 2^-13 of the largest is represented exactly, the rest to 2^-66 of it), each group as signed
 // digits of 8 / 7 / 8 bits like gibbs_imma.cu.  T_g = sum_k v_k q_g,ik is then an exact int32 from three chained
 // mma.sync.m16n8k32 (u8 x s8) passes, and theta = hb + 2^-s (T2 + 2^-22 (T1 + 2^-22 T0)) costs three FP64 FMAs
-// per unit (two of them exact) instead of N: closer to the exact sum than the FP64 FMA chain, and the FP64 pipe
+// per unit (the innermost exact) instead of N: closer to the exact sum than the FP64 FMA chain, and the FP64 pipe
 // keeps only the sigmoid and the outer products.  A tile with a non-binary entry (or weights that do not fit the
 // image) raises *flag and the CTA stops; the FP64 kernel queued behind then redoes the whole batch.
 constexpr long long GD_WQ_MAX = 127LL * 32768 + 63 * 256 + 127;
