@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define QCB_VERSION 100 /* 0.1.0 */
+#define QCB_VERSION 110 /* 0.1.1 */
 
 enum {
   QCB_OK = 0,
@@ -75,7 +75,8 @@ enum {
   QCB_OP_DM_ROTATED = 7,
   QCB_OP_CDK_NEG = 8,
   QCB_OP_CD_STEP = 9,
-  QCB_OP_KL_TERMS = 10
+  QCB_OP_KL_TERMS = 10,
+  QCB_OP_SAMPLE = 11 /* qcb_rbm_sample / qcb_rbm_gibbs_packed; rows = C */
 };
 
 int qcb_version(void);
@@ -264,15 +265,49 @@ int qcb_kron_rotate(double* re, double* im, int n, int64_t batch, const uint8_t*
 int qcb_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n,
                  double logZ, double* out2, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Compact states -------------------------------------------------------------------
+ * A chain state is one bit per unit; the reference carries it as a float64 (rbm/binary_rbm.py:220: `.to(self.weights)`).
+ * "Packed rows" are ceil(N / 8) bytes per chain, unit j = bit 7 - j % 8 of byte j / 8 — exactly
+ * numpy.packbits(v.astype(uint8), axis=1) — so a host program packs / unpacks with numpy and the PCIe payload of a
+ * sampling call is N / 8 bytes per chain instead of 8 N. */
+int qcb_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, void* stream);   /* any non-zero entry packs as 1 */
+int qcb_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, void* stream); /* writes 0.0 / 1.0 */
+
+/* NeuralStateBase.sample(k, num_samples) without an initial_state (nn_states/neural_state.py:107-131): the initial
+ * state v0 ~ Bernoulli(1/2) is drawn IN the kernel (no host RNG, no host-to-device copy) — unit j of chain c is bit
+ * j % 32 of word j / 32 of the Philox call with counter (chain id, sweep0, stream 5 << 29 | 0) — then k block-Gibbs
+ * sweeps exactly as qcb_rbm_gibbs would run them from that v0 (same draws for the same seed / chain ids / sweep0).
+ * v_out (C, N) float64 and / or bits_out (C, ceil(N / 8)) packed rows receive v_k; either may be NULL, not both.
+ * Workspace: qcb_workspace_bytes(QCB_OP_SAMPLE, N, nh, na, C).  N <= 128. */
+int qcb_rbm_sample(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh, int na,
+                   int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double* v_out, uint8_t* bits_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* qcb_rbm_gibbs on packed rows, in place (device memory).  Workspace as for qcb_rbm_sample. */
+int qcb_rbm_gibbs_packed(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                         int na, uint8_t* bits, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, void* ws,
+                         size_t ws_bytes, void* stream);
+
 /* ---- Host-buffer convenience (the end-to-end path bench.py times) ---------------------
  * Same as qcb_rbm_gibbs but v_host / params are HOST pointers (pinned for full speed); the
  * call copies in, runs, copies out on `stream` using the caller's device scratch
- * dev_scratch (>= qcb_gibbs_host_scratch_bytes) and synchronises the stream before returning. */
+ * dev_scratch (>= qcb_gibbs_host_scratch_bytes) and synchronises the stream before returning.  Float64 rows: the
+ * reference's own representation, 8 N bytes per chain each way — PCIe-bound; prefer the packed variant below. */
 size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C);
 int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
                        const double* d_host, int N, int nh, int na, double* v_host, int64_t C, int k,
                        uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                        void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* The same with packed rows in HOST memory (in place): bits_host (C, ceil(N / 8)).  draw_initial = 0: bits_host holds
+ * the initial states; draw_initial = 1: v0 ~ Bernoulli(1/2) is drawn in-kernel as in qcb_rbm_sample and bits_host is
+ * output only.  Slices of whole grid waves are copied in, sampled and copied out concurrently.  Calls on one device
+ * serialise on an internal lock (they share that device's copy streams); different devices run concurrently. */
+size_t qcb_gibbs_host_packed_scratch_bytes(int N, int nh, int na, int64_t C);
+int qcb_rbm_gibbs_host_packed(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
+                              const double* d_host, int N, int nh, int na, uint8_t* bits_host, int64_t C, int k, uint64_t seed,
+                              uint64_t chain_id0, uint64_t sweep0, int draw_initial, void* dev_scratch, size_t dev_scratch_bytes,
+                              void* stream);
 
 /* Kernel-launch counter (incremented by every kernel this library launches); bench.py reads it
  * to report gpu_launches. */

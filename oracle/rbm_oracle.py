@@ -124,6 +124,27 @@ def layer_uniforms(seed, chain_ids, sweep, q0, count):
     return bits.astype(np.float64) * (2.0 ** -53)
 
 
+def philox_initial_states(seed, chain_ids, sweep0, n):
+    """v0 ~ Bernoulli(1/2) of qcb_rbm_sample (the in-kernel stand-in for the host draw of NeuralStateBase.sample,
+    nn_states/neural_state.py:124-129): unit j of a chain = bit j % 32 of word j // 32 of the Philox call with
+    counter (chain id low, chain id high, sweep0, 5 << 29), key = seed. n <= 128."""
+    chain_ids = np.asarray(chain_ids, dtype=np.uint64)
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    words = np.stack(philox4x32_10(chain_ids & _MASK32, chain_ids >> np.uint64(32), np.uint64(sweep0), np.uint64(5 << 29), k0, k1),
+                     axis=-1).astype(np.uint64)                                   # (C, 4)
+    j = np.arange(int(n))
+    return ((words[:, j // 32] >> (j % 32).astype(np.uint64)[None, :]) & np.uint64(1)).astype(np.float64)
+
+
+def pack_states(v):
+    """Packed rows of include/qcb.h: numpy.packbits order, ceil(N / 8) bytes per row."""
+    return np.packbits(np.asarray(v) != 0, axis=-1)
+
+
+def unpack_states(bits, n):
+    return np.unpackbits(np.asarray(bits, dtype=np.uint8), axis=-1)[..., : int(n)].astype(np.float64)
+
+
 def visible_q0(nhid):
     """First Philox call of the visible layer: the hidden-like layer occupies 4 calls per 32 units."""
     return 4 * ((int(nhid) + 31) // 32)
@@ -210,6 +231,11 @@ class BinaryRBMOracle:
             uv = layer_uniforms(seed, ids, sweep0 + s, qv, self.n)
             v = (uv < self.prob_v_given_h(h)).astype(np.float64)
         return v.reshape(np.shape(initial_state))
+
+    def sample_chains_philox(self, k, num_chains, seed, chain_id0=0, sweep0=0):
+        """qcb_rbm_sample: in-kernel Bernoulli(1/2) start, then the sweeps of gibbs_steps_philox."""
+        ids = np.arange(chain_id0, chain_id0 + num_chains, dtype=np.uint64)
+        return self.gibbs_steps_philox(k, philox_initial_states(seed, ids, sweep0, self.n), seed, chain_id0, sweep0)
 
     # rbm/binary_rbm.py:230-241 evaluated range-wise: returns (m, s) with
     # logsumexp_{r in range}(-E(row r)) = m + log(s)
@@ -322,6 +348,10 @@ class PurificationRBMOracle:
             a = (uha[:, self.nh:] < self.prob_a_given_v(v)).astype(np.float64)
             v = (layer_uniforms(seed, ids, sweep0 + s, qv, self.n) < self.prob_v_given_ha(h, a)).astype(np.float64)
         return v.reshape(np.shape(initial_state))
+
+    def sample_chains_philox(self, k, num_chains, seed, chain_id0=0, sweep0=0):
+        ids = np.arange(chain_id0, chain_id0 + num_chains, dtype=np.uint64)
+        return self.gibbs_steps_philox(k, philox_initial_states(seed, ids, sweep0, self.n), seed, chain_id0, sweep0)
 
     def logz_range(self, first=0, count=None, chunk=1 << 16):  # :453-463
         total = 1 << self.n

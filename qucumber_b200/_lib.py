@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QCB_LIB_PATH") or os.path.join(_HERE, "libqucumber_b200.so")  # override: kernel experiments only
 
 QCB_OK = 0
-OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP, OP_KL_TERMS = range(1, 11)
+OP_GIBBS, OP_ENERGY, OP_GRAD_REDUCE, OP_LOGZ, OP_EXACT_STATS, OP_CWF_ROTATED, OP_DM_ROTATED, OP_CDK_NEG, OP_CD_STEP, OP_KL_TERMS, OP_SAMPLE = range(1, 12)
 
 # name -> (restype, argtypes); must list every symbol declared in include/qcb.h
 _P = c_void_p
@@ -50,6 +50,15 @@ SIGNATURES = {
                                 c_size_t, _P]),
     "qcb_dm_rotated": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P, c_int,
                                _P, _P, _P, _P, c_size_t, _P]),
+    "qcb_pack_states": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "qcb_unpack_states": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "qcb_rbm_sample": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, c_uint64, c_uint64, c_uint64, _P, _P, _P,
+                               c_size_t, _P]),
+    "qcb_rbm_gibbs_packed": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64, c_uint64, _P,
+                                     c_size_t, _P]),
+    "qcb_gibbs_host_packed_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
+    "qcb_rbm_gibbs_host_packed": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64,
+                                          c_uint64, c_int, _P, c_size_t, _P]),
     "qcb_gibbs_host_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
     "qcb_rbm_gibbs_host": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, c_uint64,
                                    c_uint64, _P, c_size_t, _P]),

@@ -1,6 +1,7 @@
 // extern "C" surface of libqucumber_b200.so (declared in include/qcb.h).
 #include "common.cuh"
 #include <cstring>
+#include <mutex>
 #include <string>
 
 namespace qcb {
@@ -29,8 +30,14 @@ int fail(int code, const char* fmt, ...) {
 // implemented in the other translation units
 size_t gibbs_workspace_bytes(int N, int nhid);
 extern int g_gibbs_mode;
-int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
+int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C);
+int64_t gibbs_wave_chains(int N, int nhid);
+int run_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, cudaStream_t st);
+int run_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st);
 int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_energy(const StackedParams& p, const double* v, int64_t rows, double* E, cudaStream_t st);
@@ -134,6 +141,7 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
       return a + b + align_up((size_t)(rows > 0 ? rows : 0) * N * sizeof(double), 256);
     }
     case QCB_OP_KL_TERMS: return kl_workspace_bytes();
+    case QCB_OP_SAMPLE: return gibbs_io_workspace_bytes(N, nh + na, rows);
     case QCB_OP_CDK_NEG: {
       const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b;
@@ -168,7 +176,10 @@ int qcb_debug_gibbs_filter(const double* W, const double* U, const double* b, co
   if (rc != QCB_OK) return rc;
   if (stats2 == nullptr || v == nullptr) return fail(QCB_ERR_BAD_ARG, "debug_gibbs_filter: NULL argument");
   int handled = 0;
-  rc = try_gibbs_imma(p, v, v, C, k, seed, 0, 0, ws, ws_bytes, stats2, &handled, (cudaStream_t)stream);
+  ChainIO io;
+  io.v_in = v;
+  io.v_out = v;
+  rc = try_gibbs_imma(p, io, C, k, seed, 0, 0, ws, ws_bytes, stats2, &handled, (cudaStream_t)stream);
   if (rc != QCB_OK) return rc;
   if (!handled) return fail(QCB_ERR_UNSUPPORTED, "debug_gibbs_filter: shape not handled by the integer filter kernel");
   return QCB_OK;
@@ -363,9 +374,129 @@ int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, c
   return run_dm_rotated(am, ph, samples, B, basis, unitaries, K, UrhoU, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// ---- compact states -------------------------------------------------------------------------------
+int qcb_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, void* stream) {
+  StreamDeviceGuard device_guard(stream, v);
+  if (N < 1 || rows < 0 || (rows > 0 && (v == nullptr || bits == nullptr))) return fail(QCB_ERR_BAD_ARG, "pack_states: bad arguments");
+  return run_pack_states(v, rows, N, bits, (cudaStream_t)stream);
+}
+
+int qcb_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, void* stream) {
+  StreamDeviceGuard device_guard(stream, v);
+  if (N < 1 || rows < 0 || (rows > 0 && (v == nullptr || bits == nullptr))) return fail(QCB_ERR_BAD_ARG, "unpack_states: bad arguments");
+  return run_unpack_states(bits, rows, N, v, (cudaStream_t)stream);
+}
+
+int qcb_rbm_sample(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh, int na,
+                   int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double* v_out, uint8_t* bits_out,
+                   void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (C < 0 || k < 0 || (C > 0 && v_out == nullptr && bits_out == nullptr)) return fail(QCB_ERR_BAD_ARG, "sample: bad C/k or no output buffer");
+  ChainIO io;
+  io.philox_init = 1;
+  io.v_out = v_out;
+  io.bits_out = bits_out;
+  return run_gibbs_io(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcb_rbm_gibbs_packed(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                         int na, uint8_t* bits, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, void* ws,
+                         size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (C < 0 || k < 0 || (C > 0 && bits == nullptr)) return fail(QCB_ERR_BAD_ARG, "gibbs_packed: bad C/k/bits");
+  ChainIO io;
+  io.bits_in = bits;
+  io.bits_out = bits;
+  return run_gibbs_io(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---- host-buffer calls ----------------------------------------------------------------------------
+namespace {
+
+constexpr int MAX_SLICES = 64;
+struct HostPipe {  // copy streams and events of one device (created on first use there); one call at a time per device
+  std::mutex lock;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[MAX_SLICES], ev_k[MAX_SLICES], ev_params, ev_done;
+};
+HostPipe g_pipes[QCB_MAX_DEVICES];
+
+int pipe_ready(HostPipe& hp) {
+  if (hp.s_in != nullptr) return QCB_OK;
+  QCB_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+  QCB_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < MAX_SLICES; ++i) {
+    QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+    QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_k[i], cudaEventDisableTiming));
+  }
+  QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_params, cudaEventDisableTiming));
+  QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_done, cudaEventDisableTiming));
+  return QCB_OK;
+}
+
+size_t param_bytes(int N, int nh, int na) { return align_up(((size_t)(nh + na) * N + N + nh + na) * sizeof(double), 256); }
+
+// copies the host parameters into dev_scratch on st and fills p with the device views
+int stage_params(StackedParams& p, const double* W_host, const double* U_host, const double* b_host, const double* c_host,
+                 const double* d_host, int N, int nh, int na, void* dev_scratch, cudaStream_t st) {
+  double* dW = static_cast<double*>(dev_scratch);
+  double* dU = dW + (size_t)nh * N;
+  double* db = dU + (size_t)na * N;
+  double* dc = db + N;
+  double* dd = dc + nh;
+  QCB_CUDA(cudaMemcpyAsync(dW, W_host, (size_t)nh * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (na > 0) {
+    QCB_CUDA(cudaMemcpyAsync(dU, U_host, (size_t)na * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    QCB_CUDA(cudaMemcpyAsync(dd, d_host, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  QCB_CUDA(cudaMemcpyAsync(db, b_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+  QCB_CUDA(cudaMemcpyAsync(dc, c_host, (size_t)nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  return make_params(p, dW, na > 0 ? dU : nullptr, db, dc, na > 0 ? dd : nullptr, N, nh, na);
+}
+
+// The chains are independent, so a host call is pipelined in slices: slice i+1 travels host->device and slice i-1
+// device->host (PCIe is full duplex, two copy engines) while slice i is sampled.  Philox draws are keyed by global chain
+// id, so slicing does not change any sample.  row_bytes: bytes of one chain in the host / device buffers; copy_in: whether
+// the host buffer holds the initial states; run(c0, cn): enqueue the sampling of chains [c0, c0 + cn) on st.
+template <class Run>
+int host_pipeline(HostPipe& hp, char* host, char* dev, size_t row_bytes, int64_t C, int64_t per, bool copy_in, cudaStream_t st, Run run) {
+  if (C <= 0) return QCB_OK;
+  QCB_CUDA(cudaEventRecord(hp.ev_params, st));
+  QCB_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_params, 0));
+  int i = 0;
+  for (int64_t c0 = 0; c0 < C; c0 += per, ++i) {
+    const int64_t cn = C - c0 < per ? C - c0 : per;
+    const size_t off = (size_t)c0 * row_bytes, nb = (size_t)cn * row_bytes;
+    if (copy_in) {
+      QCB_CUDA(cudaMemcpyAsync(dev + off, host + off, nb, cudaMemcpyHostToDevice, hp.s_in));
+      QCB_CUDA(cudaEventRecord(hp.ev_in[i], hp.s_in));
+      QCB_CUDA(cudaStreamWaitEvent(st, hp.ev_in[i], 0));
+    }
+    const int rc = run(c0, cn);
+    if (rc != QCB_OK) return rc;
+    QCB_CUDA(cudaEventRecord(hp.ev_k[i], st));
+    QCB_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_k[i], 0));
+    QCB_CUDA(cudaMemcpyAsync(host + off, dev + off, nb, cudaMemcpyDeviceToHost, hp.s_out));
+  }
+  QCB_CUDA(cudaEventRecord(hp.ev_done, hp.s_out));
+  QCB_CUDA(cudaStreamWaitEvent(st, hp.ev_done, 0));
+  return QCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C) {
-  const size_t params = align_up(((size_t)(nh + na) * N + N + nh + na) * sizeof(double), 256);
-  return params + align_up((size_t)C * N * sizeof(double), 256) + gibbs_workspace_bytes(N, nh + na);
+  return param_bytes(N, nh, na) + align_up((size_t)C * N * sizeof(double), 256) + gibbs_workspace_bytes(N, nh + na);
 }
 
 int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
@@ -379,72 +510,74 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
   if (dev_scratch == nullptr || dev_scratch_bytes < qcb_gibbs_host_scratch_bytes(N, nh, na, C))
     return fail(QCB_ERR_BAD_ARG, "gibbs_host: device scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
-  double* dW = static_cast<double*>(dev_scratch);
-  double* dU = dW + (size_t)nh * N;
-  double* db = dU + (size_t)na * N;
-  double* dc = db + N;
-  double* dd = dc + nh;
-  const size_t params = align_up(((size_t)(nh + na) * N + N + nh + na) * sizeof(double), 256);
+  HostPipe& hp = g_pipes[device_slot()];
+  std::lock_guard<std::mutex> hold(hp.lock);
+  int rc = pipe_ready(hp);
+  if (rc != QCB_OK) return rc;
+  StackedParams p;
+  rc = stage_params(p, W_host, U_host, b_host, c_host, d_host, N, nh, na, dev_scratch, st);
+  if (rc != QCB_OK) return rc;
+  const size_t params = param_bytes(N, nh, na);
   double* dv = reinterpret_cast<double*>(static_cast<char*>(dev_scratch) + params);
   const size_t vbytes = (size_t)C * N * sizeof(double);
   void* ws = static_cast<char*>(dev_scratch) + params + align_up(vbytes, 256);
-  QCB_CUDA(cudaMemcpyAsync(dW, W_host, (size_t)nh * N * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (na > 0) {
-    QCB_CUDA(cudaMemcpyAsync(dU, U_host, (size_t)na * N * sizeof(double), cudaMemcpyHostToDevice, st));
-    QCB_CUDA(cudaMemcpyAsync(dd, d_host, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, st));
-  }
-  QCB_CUDA(cudaMemcpyAsync(db, b_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
-  QCB_CUDA(cudaMemcpyAsync(dc, c_host, (size_t)nh * sizeof(double), cudaMemcpyHostToDevice, st));
-  StackedParams p;
-  int rc = make_params(p, dW, na > 0 ? dU : nullptr, db, dc, na > 0 ? dd : nullptr, N, nh, na);
-  if (rc != QCB_OK) return rc;
-  // The chains are independent, so the call is pipelined in slices: slice i+1 travels host->device
-  // and slice i-1 device->host (PCIe is full duplex, two copy engines) while slice i is sampled.
-  // Philox draws are keyed by global chain id, so slicing does not change any sample.
   // Slices of ~32 MiB: 8 MiB slices were measured slower (14.0 vs 12.2 ms for 2 x 512 MiB: per-slice copy set-up,
   // event hand-offs and two small launches outweigh the shorter fill and drain).
-  constexpr int MAX_SLICES = 64;
-  struct HostPipe {  // copy streams and events of one device (created on first use there)
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[MAX_SLICES], ev_k[MAX_SLICES], ev_params, ev_done;
-  };
-  static HostPipe pipes[QCB_MAX_DEVICES];
-  HostPipe& hp = pipes[device_slot()];
-  if (hp.s_in == nullptr) {
-    QCB_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
-    QCB_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < MAX_SLICES; ++i) {
-      QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
-      QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_k[i], cudaEventDisableTiming));
-    }
-    QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_params, cudaEventDisableTiming));
-    QCB_CUDA(cudaEventCreateWithFlags(&hp.ev_done, cudaEventDisableTiming));
-  }
-  cudaStream_t s_in = hp.s_in, s_out = hp.s_out;
-  cudaEvent_t *ev_in = hp.ev_in, *ev_k = hp.ev_k, &ev_params = hp.ev_params, &ev_done = hp.ev_done;
-  if (C > 0) {
-    int nslices = (int)(vbytes / ((size_t)32 << 20));
-    nslices = nslices < 1 ? 1 : (nslices > MAX_SLICES ? MAX_SLICES : nslices);
-    const int64_t per = ((C + nslices - 1) / nslices + 15) / 16 * 16;
-    QCB_CUDA(cudaEventRecord(ev_params, st));
-    QCB_CUDA(cudaStreamWaitEvent(s_in, ev_params, 0));
-    for (int i = 0; i < nslices; ++i) {
-      const int64_t c0 = (int64_t)i * per;
-      if (c0 >= C) break;
-      const int64_t cn = C - c0 < per ? C - c0 : per;
-      const size_t off = (size_t)c0 * N, nb = (size_t)cn * N * sizeof(double);
-      QCB_CUDA(cudaMemcpyAsync(dv + off, v_host + off, nb, cudaMemcpyHostToDevice, s_in));
-      QCB_CUDA(cudaEventRecord(ev_in[i], s_in));
-      QCB_CUDA(cudaStreamWaitEvent(st, ev_in[i], 0));
-      rc = run_gibbs(p, dv + off, dv + off, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gibbs_workspace_bytes(N, nh + na), st);
-      if (rc != QCB_OK) return rc;
-      QCB_CUDA(cudaEventRecord(ev_k[i], st));
-      QCB_CUDA(cudaStreamWaitEvent(s_out, ev_k[i], 0));
-      QCB_CUDA(cudaMemcpyAsync(v_host + off, dv + off, nb, cudaMemcpyDeviceToHost, s_out));
-    }
-    QCB_CUDA(cudaEventRecord(ev_done, s_out));
-    QCB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
-  }
+  int nslices = (int)(vbytes / ((size_t)32 << 20));
+  nslices = nslices < 1 ? 1 : (nslices > MAX_SLICES ? MAX_SLICES : nslices);
+  const int64_t per = ((C + nslices - 1) / nslices + 15) / 16 * 16;
+  const size_t gws = gibbs_workspace_bytes(N, nh + na);
+  rc = host_pipeline(hp, reinterpret_cast<char*>(v_host), reinterpret_cast<char*>(dv), (size_t)N * sizeof(double), C, per, true, st,
+                     [&](int64_t c0, int64_t cn) {
+                       return run_gibbs(p, dv + c0 * N, dv + c0 * N, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gws, st);
+                     });
+  if (rc != QCB_OK) return rc;
+  QCB_CUDA(cudaStreamSynchronize(st));
+  return QCB_OK;
+}
+
+size_t qcb_gibbs_host_packed_scratch_bytes(int N, int nh, int na, int64_t C) {
+  const int64_t wave = gibbs_wave_chains(N, nh + na);
+  const int64_t slice = C < 8 * wave ? C : 8 * wave;  // the float64 staging rows (shapes outside the integer kernel) cover one slice
+  return param_bytes(N, nh, na) + align_up((size_t)(C > 0 ? C : 0) * packed_row_bytes(N), 256) + gibbs_io_workspace_bytes(N, nh + na, slice);
+}
+
+int qcb_rbm_gibbs_host_packed(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
+                              const double* d_host, int N, int nh, int na, uint8_t* bits_host, int64_t C, int k, uint64_t seed,
+                              uint64_t chain_id0, uint64_t sweep0, int draw_initial, void* dev_scratch, size_t dev_scratch_bytes,
+                              void* stream) {
+  StreamDeviceGuard device_guard(stream, dev_scratch);
+  if (N < 1 || nh < 1 || na < 0 || C < 0 || k < 0) return fail(QCB_ERR_BAD_ARG, "gibbs_host_packed: bad sizes");
+  if (W_host == nullptr || b_host == nullptr || c_host == nullptr || (na > 0 && (U_host == nullptr || d_host == nullptr)) ||
+      (C > 0 && bits_host == nullptr))
+    return fail(QCB_ERR_BAD_ARG, "gibbs_host_packed: NULL argument");
+  if (dev_scratch == nullptr || dev_scratch_bytes < qcb_gibbs_host_packed_scratch_bytes(N, nh, na, C))
+    return fail(QCB_ERR_BAD_ARG, "gibbs_host_packed: device scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  HostPipe& hp = g_pipes[device_slot()];
+  std::lock_guard<std::mutex> hold(hp.lock);
+  int rc = pipe_ready(hp);
+  if (rc != QCB_OK) return rc;
+  StackedParams p;
+  rc = stage_params(p, W_host, U_host, b_host, c_host, d_host, N, nh, na, dev_scratch, st);
+  if (rc != QCB_OK) return rc;
+  const size_t params = param_bytes(N, nh, na), rowb = (size_t)packed_row_bytes(N);
+  uint8_t* dbits = reinterpret_cast<uint8_t*>(static_cast<char*>(dev_scratch) + params);
+  void* ws = static_cast<char*>(dev_scratch) + params + align_up((size_t)C * rowb, 256);
+  const size_t ws_bytes = dev_scratch_bytes - params - align_up((size_t)C * rowb, 256);
+  // slices are whole waves of the persistent grid (no ragged tail per slice): 8 waves each, so that the first copy in
+  // and the last copy out (a few tens of microseconds for ~2 MiB) are all that is not hidden behind sampling
+  const int64_t wave = gibbs_wave_chains(N, nh + na);
+  int64_t per = 8 * wave;
+  if ((C + per - 1) / per > MAX_SLICES) per = ((C + MAX_SLICES - 1) / MAX_SLICES + wave - 1) / wave * wave;
+  rc = host_pipeline(hp, reinterpret_cast<char*>(bits_host), reinterpret_cast<char*>(dbits), rowb, C, per, draw_initial == 0, st,
+                     [&](int64_t c0, int64_t cn) {
+                       ChainIO io;
+                       io.bits_out = dbits + c0 * rowb;
+                       if (draw_initial) io.philox_init = 1; else io.bits_in = io.bits_out;
+                       return run_gibbs_io(p, io, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, ws, ws_bytes, st);
+                     });
+  if (rc != QCB_OK) return rc;
   QCB_CUDA(cudaStreamSynchronize(st));
   return QCB_OK;
 }

@@ -70,6 +70,20 @@ struct StackedParams {
   __device__ __forceinline__ double hbias(int hid) const { return hid < nh ? c[hid] : d[hid - nh]; }
 };
 
+// Where the chain states of a Gibbs call come from and where they go.  Exactly one source: v_in (float64 rows),
+// bits_in (packed rows, see qcb.h "Compact states") or philox_init (v0 ~ Bernoulli(1/2) drawn in-kernel, Philox
+// stream 5); v_out and / or bits_out receive v_k.
+struct ChainIO {
+  const double* v_in = nullptr;
+  double* v_out = nullptr;
+  const uint8_t* bits_in = nullptr;
+  uint8_t* bits_out = nullptr;
+  int philox_init = 0;
+  __host__ __device__ bool plain() const { return bits_in == nullptr && bits_out == nullptr && !philox_init; }
+};
+__host__ __device__ inline int packed_row_bytes(int N) { return (N + 7) / 8; }
+constexpr uint32_t PHILOX_STREAM_V0 = 5u;  // counter word 3 = (5 << 29) | call: the initial-state draws
+
 #ifdef __CUDACC__
 // ---- Philox4x32-10 ---------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -436,16 +436,89 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
 int g_gibbs_mode = 0;  // 0: integer-exact IMMA filter where it applies, 1: always the FP64 DMMA kernel
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
-int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
+int run_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, cudaStream_t st);
+int run_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st);
+int run_philox_init_states(double* v, int64_t C, int N, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, cudaStream_t st);
+int64_t gibbs_imma_wave_chains(int N, int nhid);
+
+static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
+  const int HB = pick_blocks(p.nhid()), VB = pick_blocks(p.N);
+  if (HB == 0 || VB == 0 || (HB == 8 && VB == 8))
+    return fail(QCB_ERR_UNSUPPORTED, "gibbs: N=%d, nh+na=%d exceeds the shared-memory resident limit (<=128 each, not both >64)",
+                p.N, p.nhid());
+  *HBo = HB;
+  *VBo = VB;
+  return QCB_OK;
+}
+
+// Workspace of a call with compact or in-kernel-initialised states: the fragment image plus, for shapes or modes the
+// integer-filter kernel does not take, one float64 copy of the chain state.
+size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
+  const size_t img = gibbs_workspace_bytes(N, nhid);
+  const bool imma = gibbs_imma_workspace_bytes(N, nhid) != 0;
+  return img + (imma && g_gibbs_mode == 0 ? 0 : align_up((size_t)(C > 0 ? C : 0) * N * sizeof(double), 256));
+}
+
+// Chains one full wave of the persistent grid processes (slicing a host pipeline at multiples of it avoids ragged tails)
+int64_t gibbs_wave_chains(int N, int nhid) {
+  const int64_t w = gibbs_imma_wave_chains(N, nhid);
+  return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
+}
+
+static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                          uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, int allow_imma, cudaStream_t st);
+
+// General entry: any source (float64 rows, packed rows, in-kernel Bernoulli(1/2)) and any sink (float64 rows, packed rows).
+int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  int HB, VB;
+  int rc = gibbs_shape_check(p, &HB, &VB);
+  if (rc != QCB_OK) return rc;
+  const size_t img_bytes = gibbs_workspace_bytes(p.N, p.nhid());
+  if (ws == nullptr || ws_bytes < img_bytes) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, img_bytes);
+  if (C == 0) return QCB_OK;
+  if (sweep0 + (uint64_t)k > (1ull << 32))
+    return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
+  if (g_gibbs_mode == 0) {
+    int handled = 0;
+    rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
+    if (rc != QCB_OK || handled) return rc;
+  }
+  // FP64 kernel: float64 rows in and out; compact / generated states are converted around it
+  double* rows = io.v_out;
+  if (rows == nullptr) {
+    const size_t need = img_bytes + align_up((size_t)C * p.N * sizeof(double), 256);
+    if (ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small for the float64 staging rows (%zu < %zu)", ws_bytes, need);
+    rows = reinterpret_cast<double*>(static_cast<char*>(ws) + img_bytes);
+  }
+  const double* src = io.v_in;
+  if (io.philox_init) {
+    rc = run_philox_init_states(rows, C, p.N, seed, chain_id0, sweep0, st);
+    src = rows;
+  } else if (io.bits_in != nullptr) {
+    rc = run_unpack_states(io.bits_in, C, p.N, rows, st);
+    src = rows;
+  }
+  if (rc != QCB_OK) return rc;
+  rc = run_gibbs_rows(p, src, rows, C, k, seed, chain_id0, sweep0, nullptr, ws, img_bytes, 0, st);
+  if (rc != QCB_OK) return rc;
+  if (io.bits_out != nullptr) rc = run_pack_states(rows, C, p.N, io.bits_out, st);
+  return rc;
+}
 
 int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
               const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return run_gibbs_rows(p, v_in, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, 1, st);
+}
+
+static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                          uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, int allow_imma, cudaStream_t st) {
   const int nhid = p.nhid();
-  const int HB = pick_blocks(nhid), VB = pick_blocks(p.N);
-  if (HB == 0 || VB == 0 || (HB == 8 && VB == 8))
-    return fail(QCB_ERR_UNSUPPORTED, "gibbs: N=%d, nh+na=%d exceeds the shared-memory resident limit (<=128 each, not both >64)",
-                p.N, nhid);
+  int HB, VB;
+  int rc0 = gibbs_shape_check(p, &HB, &VB);
+  if (rc0 != QCB_OK) return rc0;
   const size_t need = gibbs_workspace_bytes(p.N, nhid);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, need);
   if (C == 0) return QCB_OK;
@@ -455,9 +528,12 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
   }
   if (sweep0 + (uint64_t)k > (1ull << 32))
     return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
-  if (uniforms == nullptr && g_gibbs_mode == 0) {
+  if (uniforms == nullptr && g_gibbs_mode == 0 && allow_imma) {
     int handled = 0;
-    const int rc = try_gibbs_imma(p, v_in, v, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
+    ChainIO io;
+    io.v_in = v_in;
+    io.v_out = v;
+    const int rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
     if (rc != QCB_OK || handled) return rc;
   }
 

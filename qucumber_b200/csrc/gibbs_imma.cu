@@ -40,6 +40,9 @@ struct GibbsImmaArgs {
   StackedParams p;        // original FP64 parameters (cold path)
   const double* v_in;
   double* v;
+  const uint8_t* bits_in;  // packed rows in (in_mode 1)
+  uint8_t* bits_out;       // packed rows out (optional, next to / instead of v)
+  int in_mode;             // 0: v_in (float64 rows), 1: bits_in, 2: v0 ~ Bernoulli(1/2) from Philox stream 5
   int64_t C;
   int k;
   uint32_t key0, key1;
@@ -413,42 +416,75 @@ __global__ void __launch_bounds__(GI_THREADS, QCB_GI_MIN_CTAS) gibbs_imma_kernel
     return true;
   };
   const int64_t gi0 = (int64_t)blockIdx.x * GI_WARPS + warp, gstride = (int64_t)gridDim.x * GI_WARPS;
-  bool fetched = gi0 < num_groups && bulk_fetch(gi0);
+  const int rowbytes = packed_row_bytes(N);
+  uint32_t vword[MV];  // real (unpadded) visible units per mask word
+#pragma unroll
+  for (int w = 0; w < MV; ++w) vword[w] = N >= 32 * (w + 1) ? 0xffffffffu : (N > 32 * w ? (1u << (N - 32 * w)) - 1u : 0u);
+  const bool from_rows = a.in_mode == 0;
+  bool fetched = from_rows && gi0 < num_groups && bulk_fetch(gi0);
 
   for (int64_t gi = gi0; gi < num_groups; gi += gstride) {
     const int64_t chain_base = gi * GI_CPW;
     const int nch = (int)(tile_doubles(gi) / (uint32_t)N);
-    if (fetched) {
-      mbar_wait(tbar, tphase);
-      tphase ^= 1u;
-    } else {  // unaligned view or odd tile size: plain copy
-      for (uint32_t idx = lane; idx < tile_doubles(gi); idx += 32) tile[idx] = a.v_in[chain_base * N + idx];
-      __syncwarp();
-    }
-    uint32_t mv[2][MV], mh[2][MH];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int w = 0; w < MV; ++w) mv[r][w] = 0u;
-#pragma unroll
-    for (int cc = 0; cc < GI_CPW; ++cc) {
-#pragma unroll
-      for (int w = 0; w < MV; ++w) {
-        const int j = w * 32 + lane;
-        unsigned long long bits = 0ull;
-        if (cc < nch && j < N) bits = reinterpret_cast<const unsigned long long*>(tile)[cc * N + j];
-        const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
-        if (g == (cc & 7)) mv[cc >> 3][w] = bal;
-      }
-    }
-    __syncwarp();
-    fetched = gi + gstride < num_groups && bulk_fetch(gi + gstride);
     uint32_t cid[2][2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const uint64_t id = a.chain_id0 + (uint64_t)(chain_base + 8 * r + g);
       cid[r][0] = (uint32_t)id;
       cid[r][1] = (uint32_t)(id >> 32);
+    }
+    uint32_t mv[2][MV], mh[2][MH];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int w = 0; w < MV; ++w) mv[r][w] = 0u;
+    if (from_rows) {
+      if (fetched) {
+        mbar_wait(tbar, tphase);
+        tphase ^= 1u;
+      } else {  // unaligned view or odd tile size: plain copy
+        for (uint32_t idx = lane; idx < tile_doubles(gi); idx += 32) tile[idx] = a.v_in[chain_base * N + idx];
+        __syncwarp();
+      }
+#pragma unroll
+      for (int cc = 0; cc < GI_CPW; ++cc) {
+#pragma unroll
+        for (int w = 0; w < MV; ++w) {
+          const int j = w * 32 + lane;
+          unsigned long long bits = 0ull;
+          if (cc < nch && j < N) bits = reinterpret_cast<const unsigned long long*>(tile)[cc * N + j];
+          const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
+          if (g == (cc & 7)) mv[cc >> 3][w] = bal;
+        }
+      }
+      __syncwarp();
+      fetched = gi + gstride < num_groups && bulk_fetch(gi + gstride);
+    } else if (a.in_mode == 1) {
+      // packed rows: unit j = bit 7 - j % 8 of byte j / 8 (numpy.packbits order); the four lanes of a row read the same bytes
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t ch = chain_base + 8 * r + g;
+        if (ch < a.C) {
+          const uint8_t* row = a.bits_in + ch * rowbytes;
+#pragma unroll
+          for (int w = 0; w < MV; ++w) {
+            uint32_t x = 0u;
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (4 * w + bb < rowbytes) x |= (uint32_t)row[4 * w + bb] << (8 * bb);
+            mv[r][w] = __brev(__byte_perm(x, 0u, 0x0123u)) & vword[w];
+          }
+        }
+      }
+    } else {
+      // v0 ~ Bernoulli(1/2): unit j = bit j % 32 of word j / 32 of ONE Philox call (stream 5, call 0) at sweep index sweep0
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        uint32_t rnd[4];
+        philox4x32_10(cid[r][0], cid[r][1], a.sweep0, stream_ctr_i(PHILOX_STREAM_V0, 0u), a.key0, a.key1, rnd);
+#pragma unroll
+        for (int w = 0; w < MV; ++w) mv[r][w] = rnd[w] & vword[w];
+      }
     }
     if constexpr (HB == VB) {
       // Equal paddings: both conditional updates run through ONE copy of the half-sweep code (direction
@@ -472,14 +508,32 @@ __global__ void __launch_bounds__(GI_THREADS, QCB_GI_MIN_CTAS) gibbs_imma_kernel
         half_sweep_imma<HB, VB, DBG>(mh, mv, Bv, biasV, inv_scale, margin_v, dx_v, valid_v, cid, a.key0, a.key1, sweep, qv0, &a, 0, lane);
       }
     }
+    if (a.v != nullptr) {
 #pragma unroll
-    for (int cc = 0; cc < GI_CPW; ++cc) {
-      const int64_t ch = chain_base + cc;
+      for (int cc = 0; cc < GI_CPW; ++cc) {
+        const int64_t ch = chain_base + cc;
 #pragma unroll
-      for (int w = 0; w < MV; ++w) {
-        const uint32_t word = __shfl_sync(0xffffffffu, mv[cc >> 3][w], (cc & 7) * 4);
-        const int j = w * 32 + lane;
-        if (ch < a.C && j < N) a.v[ch * N + j] = ((word >> lane) & 1u) ? 1.0 : 0.0;
+        for (int w = 0; w < MV; ++w) {
+          const uint32_t word = __shfl_sync(0xffffffffu, mv[cc >> 3][w], (cc & 7) * 4);
+          const int j = w * 32 + lane;
+          if (ch < a.C && j < N) a.v[ch * N + j] = ((word >> lane) & 1u) ? 1.0 : 0.0;
+        }
+      }
+    }
+    if (a.bits_out != nullptr && (lane & 3) == 0) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t ch = chain_base + 8 * r + g;
+        if (ch < a.C) {
+          uint8_t* row = a.bits_out + ch * rowbytes;
+#pragma unroll
+          for (int w = 0; w < MV; ++w) {
+            const uint32_t x = __byte_perm(__brev(mv[r][w] & vword[w]), 0u, 0x0123u);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (4 * w + bb < rowbytes) row[4 * w + bb] = (uint8_t)(x >> (8 * bb));
+          }
+        }
       }
     }
   }
@@ -518,6 +572,13 @@ static int launch_gibbs_imma(const GibbsImmaArgs& a, cudaStream_t st) {
   return QCB_OK;
 }
 
+// chains in one full wave of the persistent grid (2 CTAs per SM at 64 x 64); 0 when the shape is not handled here
+int64_t gibbs_imma_wave_chains(int N, int nhid) {
+  const int HB = pick_blocks_imma(nhid), VB = pick_blocks_imma(N);
+  if (HB == 0 || VB == 0) return 0;
+  return (int64_t)sm_count() * QCB_GI_MIN_CTAS * GI_WARPS * GI_CPW;
+}
+
 size_t gibbs_imma_workspace_bytes(int N, int nhid) {
   const int HB = pick_blocks_imma(nhid), VB = pick_blocks_imma(N);
   if (HB == 0 || VB == 0) return 0;
@@ -525,7 +586,7 @@ size_t gibbs_imma_workspace_bytes(int N, int nhid) {
 }
 
 // *handled = 1 when this kernel took the call (layers <= 64 units, own Philox draws)
-int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st) {
   *handled = 0;
   const int HB = pick_blocks_imma(p.nhid()), VB = pick_blocks_imma(p.N);
@@ -539,8 +600,11 @@ int try_gibbs_imma(const StackedParams& p, const double* v_in, double* v, int64_
   a.image = img;
   a.image_bytes = (uint32_t)imma_image_bytes(HB, VB);
   a.p = p;
-  a.v_in = v_in;
-  a.v = v;
+  a.v_in = io.v_in;
+  a.v = io.v_out;
+  a.bits_in = io.bits_in;
+  a.bits_out = io.bits_out;
+  a.in_mode = io.philox_init ? 2 : (io.bits_in != nullptr ? 1 : 0);
   a.C = C;
   a.k = k;
   a.key0 = (uint32_t)seed;

@@ -42,6 +42,28 @@ class _Callbacks:
                 fn(*args)
 
 
+def _noop_plain(*args, **kwargs):
+    pass
+
+
+def _noop_documented(*args, **kwargs):
+    """A hook that only carries a docstring."""
+
+
+_NOOP_BYTECODE = {_noop_plain.__code__.co_code, _noop_documented.__code__.co_code, (lambda *a, **k: None).__code__.co_code}
+
+
+def _is_noop_hook(fn):
+    """True for a hook that is absent or a plain Python function whose body is `pass` / a docstring / `return None`
+    (compared with the bytecode this interpreter emits for such bodies). Anything else — including any callable that is
+    not a Python function — counts as doing work."""
+    if fn is None:
+        return True
+    fn = getattr(fn, "__func__", fn)
+    code = getattr(fn, "__code__", None)
+    return code is not None and code.co_code in _NOOP_BYTECODE and not code.co_names
+
+
 def stored_attribute(slot):
     """A settable property over a plain instance slot. The reference exposes ``rbm_am`` / ``rbm_ph`` / ``device`` as
     settable properties (e.g. complex_wavefunction.py:74-103) so that a module can be swapped in from outside —
@@ -99,12 +121,25 @@ class NeuralStateBase(abc.ABC):
         v = v.to(device=self.device, dtype=torch.double)
         return (-self.rbm_am.effective_energy(v)).exp() / Z
 
-    def sample(self, k, num_samples=1, initial_state=None, overwrite=False):
-        """k block-Gibbs sweeps from a random (or given) state (neural_state.py:107-131)."""
+    def sample(self, k, num_samples=1, initial_state=None, overwrite=False, packed=False):
+        """k block-Gibbs sweeps from a random (or given) state (neural_state.py:107-131).
+
+        Without ``initial_state`` the reference draws ``Bernoulli(0.5)`` on the host and copies it over
+        (neural_state.py:124-129); here the chains start from Bernoulli(1/2) bits drawn INSIDE the sampling kernel
+        (Philox keyed from torch's generator, so ``torch.manual_seed`` still reproduces a run): one launch, nothing
+        crosses PCIe. ``packed=True`` (not in the reference) returns ``(num_samples, ceil(N / 8))`` uint8 rows in
+        numpy.packbits order instead of float64 rows — 64 x fewer bytes to bring to the host."""
         if initial_state is None:
-            dist = torch.distributions.Bernoulli(probs=0.5)
+            if hasattr(self.rbm_am, "sample_chains"):
+                return self.rbm_am.sample_chains(k, num_samples, packed=packed)
+            dist = torch.distributions.Bernoulli(probs=0.5)  # a foreign RBM module behind rbm_am: the reference's own route
             initial_state = dist.sample(torch.Size((num_samples, self.num_visible))).to(device=self.device, dtype=torch.double)
-        return self.rbm_am.gibbs_steps(k, initial_state, overwrite=overwrite)
+        out = self.rbm_am.gibbs_steps(k, initial_state, overwrite=overwrite)
+        if packed:
+            from ..rbm._sampling import pack_states
+
+            return pack_states(out)
+        return out
 
     def subspace_vector(self, num, size=None, device=None):
         """Basis state number ``num`` (MSB first) as a vector (neural_state.py:133-154)."""
@@ -348,11 +383,9 @@ class NeuralStateBase(abc.ABC):
                 and not pg[0].get("maximize", False)):
             return False
 
-        def trivial(fn):  # a hook that is absent or only `pass`
-            code = getattr(fn, "__code__", None)
-            return fn is None or (code is not None and len(code.co_code) <= 8 and not code.co_names)
-
-        return all(trivial(getattr(type(cb), hook, None)) for cb in cbs.callbacks for hook in ("on_batch_start", "on_batch_end"))
+        # hooks are resolved exactly as fire() resolves them (instance attributes included: the reference's
+        # LambdaCallback installs its hooks on the instance, callbacks/lambda_callback.py:84-97)
+        return all(_is_noop_hook(getattr(cb, hook, None)) for cb in cbs.callbacks for hook in ("on_batch_start", "on_batch_end"))
 
     def _fit_epoch_fused(self, pos, neg, num_batches, pos_batch_size, neg_batch_size, k, lr, want_grads):
         """All batches of one epoch in one launch; parameters are updated in place."""

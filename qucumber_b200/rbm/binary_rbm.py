@@ -14,6 +14,7 @@ from torch import nn
 from .. import _lib
 from ..rng import next_seed
 from ..utils import auto_unsqueeze_args
+from ._sampling import ChainSamplingMixin
 
 
 def _as_rows(x, like, width, what):
@@ -24,7 +25,7 @@ def _as_rows(x, like, width, what):
     return x.reshape(-1, width).contiguous()
 
 
-class BinaryRBM(nn.Module):
+class BinaryRBM(ChainSamplingMixin, nn.Module):
     def __init__(self, num_visible, num_hidden=None, zero_weights=False, gpu=True):
         super().__init__()
         self.num_visible = int(num_visible)

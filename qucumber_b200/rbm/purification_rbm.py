@@ -14,10 +14,11 @@ from .. import _lib
 from ..rng import next_seed
 from ..utils import auto_unsqueeze_args
 from ..utils import cplx
+from ._sampling import ChainSamplingMixin
 from .binary_rbm import _as_rows
 
 
-class PurificationRBM(nn.Module):
+class PurificationRBM(ChainSamplingMixin, nn.Module):
     def __init__(self, num_visible, num_hidden=None, num_aux=None, zero_weights=False, gpu=False):
         super().__init__()
         self.num_visible = int(num_visible)

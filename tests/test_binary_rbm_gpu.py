@@ -705,3 +705,49 @@ def test_bench_json_contract(lib, cuda):
     assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 131072 * 64 * 8 and e["d2h_bytes_per_step"] >= 131072 * 64 * 8
     assert e["value"] < d["value"]  # host buffers and copies inside the timed region
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+# ---- round 2: parity gaps named by the review ---------------------------------------------------------------------
+@pytest.mark.parametrize("n,nh,k", [(64, 64, 2), (10, 10, 10)])
+def test_gibbs_fed_uniforms_bit_exact_131072_chains(lib, cuda, n, nh, k):
+    """fed-uniform Gibbs at C = 2^17 (every chain group of a full persistent grid and more)."""
+    rbm, orc = _pair(n, nh, 221, cuda)
+    chains = 1 << 17
+    v0 = random_states(chains, n, 222)
+    u = np.random.default_rng(223).random((k, chains, nh + n))
+    got = rbm.gibbs_steps(k, torch.tensor(v0, device=cuda), uniforms=torch.tensor(u, device=cuda))
+    assert np.array_equal(got.cpu().numpy(), orc.gibbs_steps_fed(k, v0, u))
+
+
+def test_log_partition_n24_vs_chunked_oracle(lib, cuda):
+    """N = nh = 24 (beyond the reference's max_size = 20, nn_states/neural_state.py:52-55): the oracle evaluates the
+    reference's effective_energy chunk-wise with a streaming log-sum-exp (rbm/binary_rbm.py:92-96, 240-241)."""
+    n = nh = 24
+    rbm, orc = _pair(n, nh, 231, cuda)
+    m, s = orc.logz_range(chunk=1 << 18)
+    want = m + np.log(s)
+    out2 = rbm.log_partition().cpu().numpy()
+    got = out2[0] + np.log(out2[1])
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+    # a sub-range against the same oracle, and additivity of two ranges
+    first, count = 123_457, 3_000_001
+    ms, ss = orc.logz_range(first, count, chunk=1 << 18)
+    o = rbm.log_partition(first, count).cpu().numpy()
+    assert abs((o[0] + np.log(o[1])) - (ms + np.log(ss))) <= 1e-10 * abs(ms + np.log(ss))
+
+
+@pytest.mark.parametrize("nh", [12, 20])
+def test_log_partition_n32_vs_hidden_side_trace(lib, cuda, nh):
+    """N = 32 (2^32 states, the benchmark's size) against the closed form that traces the VISIBLE units analytically and
+    sums over the 2^nh hidden states — independent of the enumeration kernel. Weights small enough that no
+    pre-activation reaches the softplus threshold (the closed form has none)."""
+    n = 32
+    W, b, c = make_binary_params(n, nh, 241, bias_scale=0.2)
+    from qucumber_b200 import BinaryRBM
+
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    assert np.abs(W).sum(1).max() + np.abs(c).max() < 20.0
+    want = BinaryRBMOracle(W, b, c).log_partition_hidden_side()
+    out2 = rbm.log_partition().cpu().numpy()
+    got = out2[0] + np.log(out2[1])
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)

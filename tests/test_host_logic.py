@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in qcb.h but not exported"
-    assert lib.qcb_version() == 100
+    assert lib.qcb_version() == 110
     assert lib.qcb_workspace_bytes(_lib.OP_GIBBS, 64, 64, 0, 1) > 2 * 64 * 64 * 8
     assert lib.qcb_workspace_bytes(_lib.OP_GIBBS, 200, 200, 0, 1) == 0  # unsupported shape
 
@@ -41,6 +41,56 @@ def test_no_cpu_fallback():
     assert p.num_pars == 4 * 3 + 4 * 2 + 4 + 3 + 2
     with pytest.raises(RuntimeError, match="no CPU path"):
         PositiveWaveFunction(4, gpu=False).sample(k=1, num_samples=2)
+
+
+def test_epoch_fusion_sees_instance_level_batch_hooks():
+    """a callback whose per-batch hooks are INSTANCE attributes (the reference's LambdaCallback,
+    callbacks/lambda_callback.py:84-97) must keep the per-batch path, exactly like class-level hooks; hooks that do
+    nothing (pass / docstring only / absent) must not."""
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200.callbacks import CallbackBase, Timer
+    from qucumber_b200.nn_states.neural_state import _Callbacks, _is_noop_hook
+
+    nn = PositiveWaveFunction(4, 4, gpu=False)
+    opt = torch.optim.SGD(list(nn.rbm_am.parameters()), lr=0.1)
+
+    class LambdaLike(CallbackBase):  # hooks installed on the instance, class-level ones are the base no-ops
+        def __init__(self, **hooks):
+            for name, fn in hooks.items():
+                setattr(self, name, fn)
+
+    class Documented:
+        def on_batch_end(self, nn_state, epoch, batch):
+            """only a docstring"""
+
+    class ClassLevel(CallbackBase):
+        def on_batch_start(self, nn_state, epoch, batch):
+            nn_state.seen = batch
+
+    class CallableObject:
+        def __call__(self, *a):
+            return None
+
+    calls = []
+    fusable = lambda *cbs: nn._epoch_fusable(opt, _Callbacks(list(cbs)), None)  # noqa: E731
+    assert fusable() and fusable(CallbackBase()) and fusable(Timer(verbose=False)) and fusable(Documented())
+    assert fusable(LambdaLike(on_epoch_end=lambda s, e: calls.append(e)))
+    assert not fusable(LambdaLike(on_batch_end=lambda s, e, b: calls.append(b)))
+    assert not fusable(LambdaLike(on_batch_start=lambda s, e, b: setattr(s, "stop_training", True)))
+    assert not fusable(ClassLevel())
+    assert not fusable(LambdaLike(on_batch_end=CallableObject()))
+    assert not fusable(LambdaLike(on_batch_end=print))
+    assert _is_noop_hook(None) and _is_noop_hook(lambda *a: None) and not _is_noop_hook(lambda *a: calls.append(1))
+    # the reference's own LambdaCallback, when the vendored copy is present
+    sys.path.insert(0, ROOT)
+    from oracle import make_ref
+
+    if make_ref.available():
+        make_ref.import_reference()
+        from qucumber.callbacks import LambdaCallback
+
+        assert not fusable(LambdaCallback(on_batch_end=lambda s, e, b: calls.append(b)))
+        assert fusable(LambdaCallback(on_epoch_end=lambda s, e: calls.append(e)))
 
 
 def test_product_does_not_import_oracle():
