@@ -151,53 +151,201 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline_sample(k, chains, reps):
-    """The reference's torch-CPU Gibbs path on a bounded sample of the workload."""
+def load_reference():
+    """The UNMODIFIED reference (oracle/_ref, made by oracle/make_ref.py; pure Python, travels to the GPU box), or None."""
+    try:
+        from oracle import make_ref
+
+        if not make_ref.available():
+            make_ref.make()
+        if not make_ref.available():
+            return None
+        import warnings
+
+        warnings.filterwarnings("ignore", category=ResourceWarning)
+        return make_ref.import_reference()
+    except Exception as exc:  # pragma: no cover - reported in the JSON line
+        print(f"bench.py: reference unavailable ({exc}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+def reference_rbm(gpu):
+    """qucumber.rbm.BinaryRBM (the reference's own class) with the benchmark's parameters, or None."""
+    if load_reference() is None:
+        return None
+    from qucumber.rbm import BinaryRBM as RefBinaryRBM
+
+    W, b, c = synthetic_rbm()
+    rbm = RefBinaryRBM(N_VIS, N_HID, gpu=gpu)
+    with torch.no_grad():
+        rbm.weights.copy_(W)
+        rbm.visible_bias.copy_(b)
+        rbm.hidden_bias.copy_(c)
+    return rbm
+
+
+def reference_gibbs_cpu():
+    """(callable(k, v) -> v_k, kind): the reference's BinaryRBM.gibbs_steps (rbm/binary_rbm.py:200-228) on the host
+    cores, or the oracle's restatement of its operator sequence when oracle/_ref is absent."""
+    rbm = reference_rbm(gpu=False)
+    if rbm is not None:
+        return (lambda k, v: rbm.gibbs_steps(k, v)), "reference"
     from oracle.cpu_path import gibbs_steps_cpu
 
     W, b, c = synthetic_rbm()
+    return (lambda k, v: gibbs_steps_cpu(W, b, c, k, v)), "port"
+
+
+def cpu_baseline_sample(k, chains, reps):
+    """The reference's torch-CPU Gibbs path on a bounded sample of the workload."""
+    run, kind = reference_gibbs_cpu()
     v = initial_state(chains, 0)
     torch.manual_seed(7)
-    gibbs_steps_cpu(W, b, c, 1, v)  # warm-up
+    run(1, v)  # warm-up
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        gibbs_steps_cpu(W, b, c, k, v)
+        run(k, v)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return chains * k / best, times
+    return chains * k / best, times, kind
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from oracle.cpu_path import gibbs_steps_cpu
-
+    run, kind = reference_gibbs_cpu()
     chains = args.ref_chains
-    W, b, c = synthetic_rbm()
     v = initial_state(chains, 0)
     torch.manual_seed(7)
     for _ in range(args.warmup):
-        gibbs_steps_cpu(W, b, c, args.k, v)
+        run(args.k, v)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        gibbs_steps_cpu(W, b, c, args.k, v)
+        run(args.k, v)
     dt = time.perf_counter() - t0
     value = chains * args.k * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{chains} chains x k={args.k} sweeps per step (same RBM, N=nh=64, float64)"
+    what = ("qucumber.rbm.BinaryRBM.gibbs_steps of the unmodified reference (oracle/_ref), gpu=False" if kind == "reference"
+            else "oracle restatement of the reference's torch-CPU operator sequence (oracle/_ref absent)")
+    sample = f"{chains} chains x k={args.k} sweeps per step (same RBM, N=nh=64, float64); {what}"
     line = {
         "impl": "reference", "metric": "gibbs_chain_sweeps_per_s", "value": value, "unit": "chain-sweeps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BinaryRBM N=64 nh=64 block Gibbs, k={args.k} sweeps/step", "chains_per_step": chains,
-                   "k": args.k, "note": "reference torch-CPU operator sequence (oracle port); bounded sample of the GPU workload"},
-        "cpu_baseline": {"value": value, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+                   "k": args.k, "note": "the reference's own CPU implementation on the host cores; bounded sample of the GPU workload "
+                                        "(a rate: size-independent above 1e5 chains, SURVEY.md 8(d))"},
+        "cpu_baseline": {"value": value, "unit": "chain-sweeps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def torch_cuda_baseline(dev, k):
+    """SURVEY 8(d) "second baseline": the UNMODIFIED reference with gpu=True — its torch-CUDA op chain, ten launches per
+    Gibbs sweep (rbm/binary_rbm.py:129-228) — timed on this same B200 with CUDA events, best of 3 after a warm-up.
+    Kernel-for-kernel bar for the device-resident `value` (same inputs resident in HBM)."""
+    out = {"kind": "reference", "how": "qucumber (oracle/_ref) with gpu=True on the same GPU; CUDA events, best of 3 after 1 warm-up"}
+    if load_reference() is None:
+        return {"unavailable": "oracle/_ref is missing (python oracle/make_ref.py)"}
+    import warnings
+
+    from qucumber.nn_states import PositiveWaveFunction as RefPositive
+    from qucumber.rbm import BinaryRBM as RefBinaryRBM
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    def wall(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        return best
+
+    try:  # S64: the headline workload
+        C = 1 << 20
+        rbm = reference_rbm(gpu=True)
+        v = initial_state(C, 0).to(dev)
+        ms = timed(lambda: rbm.gibbs_steps(k, v))
+        out["gibbs_s64"] = {"chains": C, "k": k, "ms": ms, "chain_sweeps_per_s": C * k / (ms * 1e-3)}
+        ms_g = timed(lambda: rbm.effective_energy_gradient(v))
+        out["grad_reduce_s64"] = {"rows": C, "ms": ms_g}
+        del rbm, v
+    except Exception as exc:  # pragma: no cover
+        out["gibbs_s64"] = {"error": str(exc)}
+    try:  # T4: generation at N = nh = 10, k = 100
+        C = 1 << 20
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "binary_rbm_tfim10.npz"))
+        r10 = RefBinaryRBM(10, 10, gpu=True)
+        with torch.no_grad():
+            r10.weights.copy_(torch.tensor(gold["weights"])); r10.visible_bias.copy_(torch.tensor(gold["visible_bias"]))
+            r10.hidden_bias.copy_(torch.tensor(gold["hidden_bias"]))
+        v10 = (torch.rand(C, 10, device=dev) < 0.5).double()
+        ms = timed(lambda: r10.gibbs_steps(100, v10), reps=2)
+        out["generation_n10"] = {"chains": C, "k": 100, "ms": ms, "chain_sweeps_per_s": C * 100 / (ms * 1e-3)}
+        del v10
+    except Exception as exc:  # pragma: no cover
+        out["generation_n10"] = {"error": str(exc)}
+    try:  # exact Z at the reference's largest size, N = 20: Hilbert space built on the host (NumPy), energies + LSE on the GPU
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = RefPositive(20, 20, gpu=True)
+        space = st.generate_hilbert_space()
+        ms_z = timed(lambda: st.normalization(space))
+        ms_all = wall(lambda: st.normalization(st.generate_hilbert_space()), reps=2)
+        out["exact_z_n20"] = {"N": 20, "ms_partition_only": ms_z, "states_per_s_partition_only": (1 << 20) / (ms_z * 1e-3),
+                              "ms_with_space_generation": ms_all, "states_per_s_with_space_generation": (1 << 20) / (ms_all * 1e-3),
+                              "note": "N = 20 is the reference's max_size; larger spaces raise ValueError (neural_state.py:52-55,169-171)"}
+        del space, st
+    except Exception as exc:  # pragma: no cover
+        out["exact_z_n20"] = {"error": str(exc)}
+    try:  # Tutorial-1 epoch: fit() on TFIM N = 10, pos 100 / neg 200, CD-10, SGD
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "binary_rbm_tfim10.npz"))
+        train = torch.tensor(np.unpackbits(gold["train_packed"], axis=1)[:, :10].astype(np.float64))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = RefPositive(10, 10, gpu=True)
+        st.fit(train, epochs=1, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        st.fit(train, epochs=3, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+        torch.cuda.synchronize(dev)
+        out["tfim_epoch"] = {"ms_per_epoch": (time.perf_counter() - t0) / 3 * 1e3, "steps_per_epoch": 100}
+    except Exception as exc:  # pragma: no cover
+        out["tfim_epoch"] = {"error": str(exc)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_fit_epoch_cpu(train):
+    """ms per epoch of the UNMODIFIED reference's fit() on the host cores (Tutorial-1 configuration), or None."""
+    if load_reference() is None:
+        return None
+    from qucumber.nn_states import PositiveWaveFunction as RefPositive
+
+    st = RefPositive(10, 10, gpu=False)
+    st.fit(train, epochs=1, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+    t0 = time.perf_counter()
+    st.fit(train, epochs=3, pos_batch_size=100, neg_batch_size=200, k=10, lr=0.01)
+    return (time.perf_counter() - t0) / 3 * 1e3
 
 
 def extra_metrics(dev, lib_mod):
@@ -300,8 +448,11 @@ def extra_metrics(dev, lib_mod):
             gr = gpos - cpu_path.grad_reduce_cpu(Wc, bc, cc, vk) / 200.0
             Wc = Wc - 0.01 * gr[:100].view(10, 10); bc = bc - 0.01 * gr[100:110]; cc = cc - 0.01 * gr[110:]
         cpu_ms_epoch = (_time.perf_counter() - t0) / steps * 100 * 1e3
+        ref_fit_ms = reference_fit_epoch_cpu(train)
         out["tfim_epoch"] = {"ms_per_epoch": ms_epoch, "steps_per_epoch": 100, "config": "N=nh=10, 10k samples, pos 100 / neg 200, CD-10, SGD",
-                             "cpu_reference_ms_per_epoch": cpu_ms_epoch, "cores": torch.get_num_threads(),
+                             "cpu_reference_ms_per_epoch": ref_fit_ms if ref_fit_ms is not None else cpu_ms_epoch,
+                             "cpu_reference_kind": "reference (qucumber fit(), oracle/_ref)" if ref_fit_ms is not None else "port",
+                             "cpu_port_ms_per_epoch": cpu_ms_epoch, "cores": torch.get_num_threads(),
                              "note": "wall clock through PositiveWaveFunction.fit (launch-latency bound)"}
     except Exception as exc:  # pragma: no cover
         out["tfim_epoch"] = {"error": str(exc)}
@@ -597,27 +748,94 @@ def run_ours(args):
                                  "chain_sweeps_per_s": world * C * 10 / (ms_cd * 1e-3),
                                  "collective": "all_reduce(sum) of 4224 float64"}}
 
-    # ---- end to end through the C ABI with host buffers ("e2e") ----
-    scratch_bytes = lib.qcb_gibbs_host_scratch_bytes(N_VIS, N_HID, 0, C)
-    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+    # ---- sustained: the same device-resident loop for >= args.sustain_s seconds with its own clock record ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / ms_step) + 1)
+        barrier()
+        sus_sampler = ClockSampler(local)
+        if rank == 0:
+            sus_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            rbm.gibbs_steps(k, v, overwrite=True, seed=args.seed, chain_id0=chain0, sweep0=sweep % (1 << 30))
+            sweep += k
+        s1.record()
+        barrier()
+        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        sustained = {"value": world * C * k * n_sus / (sus_ms * 1e-3), "unit": "chain-sweeps/s", "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus, "clocks": sus_clocks}
+
+    # ---- end to end ("e2e"): HOST buffers in, HOST buffers out, copies inside the timed region ----
+    # (1) headline: the packed host call of the C ABI — chain states travel as ceil(N/8) = 8 bytes per chain each way
+    # (include/qcb.h "Compact states"), sliced so that copy-in, sampling and copy-out overlap.
+    rowb = (N_VIS + 7) // 8
+    bits_host = torch.from_numpy(np.packbits(v_host.numpy() != 0, axis=1)).pin_memory()
+    assert bits_host.shape == (C, rowb)
+    pscratch_bytes = lib.qcb_gibbs_host_packed_scratch_bytes(N_VIS, N_HID, 0, C)
+    pscratch = torch.empty(pscratch_bytes, dtype=torch.uint8, device=dev)
     Wh, bh, ch = W.contiguous().pin_memory(), b.pin_memory(), c.pin_memory()
     stream = _lib.stream_ptr(dev)
+    param_bytes = (N_HID * N_VIS + N_VIS + N_HID) * 8
 
-    def e2e_step(sw):
+    def e2e_packed_step(sw):
+        _lib.check(lib.qcb_rbm_gibbs_host_packed(_lib.ptr(Wh), None, _lib.ptr(bh), _lib.ptr(ch), None, N_VIS, N_HID, 0,
+                                                 _lib.ptr(bits_host), C, k, args.seed, chain0, sw, 0, _lib.ptr(pscratch),
+                                                 pscratch_bytes, stream), "qcb_rbm_gibbs_host_packed")
+
+    def time_host_loop(step_fn, steps):
+        for i in range(max(1, min(args.warmup, 3))):
+            step_fn(i * k)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step_fn((i + 10) * k)
+        torch.cuda.synchronize(dev)
+        return max_over_ranks(time.perf_counter() - t0)
+
+    launches1 = lib.qcb_launch_count()
+    e2e_s = time_host_loop(e2e_packed_step, args.steps)
+    e2e_launches = lib.qcb_launch_count() - launches1
+    e2e_value = world * C * k * args.steps / e2e_s
+
+    # (2) the public Python API a QuCumber user calls: nn_state.sample(k, num_samples) — chains START in the kernel (no host
+    # RNG, no H2D) — followed by the device-to-host read of the result, as packed rows and as the reference's float64 rows
+    from qucumber_b200 import PositiveWaveFunction
+
+    api_state = PositiveWaveFunction(N_VIS, N_HID, gpu=True)
+    with torch.no_grad():
+        api_state.rbm_am.weights.copy_(W)
+        api_state.rbm_am.visible_bias.copy_(b)
+        api_state.rbm_am.hidden_bias.copy_(c)
+    out_bits = torch.empty(C, rowb, dtype=torch.uint8).pin_memory()
+
+    def api_packed_step(sw):
+        out_bits.copy_(api_state.sample(k, C, packed=True), non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    api_packed_s = time_host_loop(api_packed_step, args.steps)
+    api_rows_steps = max(2, min(args.steps, 5))
+
+    def api_rows_step(sw):
+        v_host.copy_(api_state.sample(k, C), non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    api_rows_s = time_host_loop(api_rows_step, api_rows_steps)
+
+    # (3) round 1's call for continuity: float64 rows both ways through qcb_rbm_gibbs_host (2 x 512 MiB per step over PCIe)
+    scratch_bytes = lib.qcb_gibbs_host_scratch_bytes(N_VIS, N_HID, 0, C)
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+
+    def e2e_rows_step(sw):
         _lib.check(lib.qcb_rbm_gibbs_host(_lib.ptr(Wh), None, _lib.ptr(bh), _lib.ptr(ch), None, N_VIS, N_HID, 0,
                                           _lib.ptr(v_host), C, k, args.seed, chain0, sw, _lib.ptr(scratch), scratch_bytes,
                                           stream), "qcb_rbm_gibbs_host")
 
-    for i in range(max(1, min(args.warmup, 3))):
-        e2e_step(i * k)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step((i + 10) * k)
-    torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * C * k * args.steps / e2e_s
-    param_bytes = (N_HID * N_VIS + N_VIS + N_HID) * 8
+    rows_steps = max(2, min(args.steps, 5))
+    e2e_rows_s = time_host_loop(e2e_rows_step, rows_steps)
+    del scratch, pscratch
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
@@ -626,7 +844,7 @@ def run_ours(args):
             with open(peaks_path) as fh:
                 peak_tflops = json.load(fh)["dmma_m8n8k4_tflops"]
             peak_src = "measured: FP64 DMMA m8n8k4 peak, tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure"
-        achieved = C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 1e12  # per GPU: one launch processes C*k chain-sweeps
+        fp64_equiv = C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 1e12  # per GPU: one launch processes C*k chain-sweeps
         traffic, imma_peak_tops = None, 1137.0
         tpath = os.path.join(ROOT, "profiles", "gibbs_traffic_r01.json")
         if os.path.exists(tpath):
@@ -636,6 +854,12 @@ def run_ours(args):
             imma_peak_tops = tj.get("imma_s8_m16n8k32_peak_tops", imma_peak_tops)
         imma_tops = C * k * IMMA_OPS_PER_SWEEP / (ms_step * 1e-3) / 1e12
         fp64_achieved = C * k * FLOP_PER_SWEEP / (fp64_ms_step * 1e-3) / 1e12
+        # issue slots: warp instructions of the hot loop (static SASS count per warp half-sweep of 16 chains,
+        # profiles/sass_r02.txt) against 4 schedulers x SMs x clock; ncu's measured issue-active is quoted beside it
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        instr_per_half_sweep = 849.0
+        issue_rate = (C / 16.0) * k * 2 * instr_per_half_sweep / (ms_step * 1e-3)
+        issue_peak = 148 * 4 * sm_mhz * 1e6
         line = {
             "metric": "gibbs_chain_sweeps_per_s", "value": value, "unit": "chain-sweeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -643,29 +867,52 @@ def run_ours(args):
             "config": {"workload": f"BinaryRBM N=64 nh=64 block Gibbs, k={k} sweeps/step, {C} chains per GPU",
                        "chains_per_gpu": C, "k": k, "l2": "inputs larger than L2 (512 MiB chain state per GPU per step)",
                        "visible_site_updates_per_s": value * N_VIS, "rng": "in-kernel Philox4x32-10"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": "gibbs_imma_kernel<4,4,false>",
-                         "peak_source": peak_src, "flop_per_chain_sweep": FLOP_PER_SWEEP,
-                         "note": "achieved = the path's ALGORITHMIC FP64 flop (SURVEY 8(d): 4*N*nh per chain-sweep) over the measured "
-                                 "launch time; the default kernel evaluates that contraction exactly in int8 tensor-core arithmetic "
-                                 "and keeps FP64 for the ~2e-5 undecided units, so frac > 1 against the FP64 pipe is expected. Its own "
-                                 "limiter is the issue slot (Philox + Bernoulli epilogue), see imma / DESIGN.md 3.1.",
-                         "imma": {"achieved_tops": imma_tops, "peak_tops": imma_peak_tops, "frac": imma_tops / imma_peak_tops,
-                                  "int8_ops_per_chain_sweep": IMMA_OPS_PER_SWEEP,
-                                  "peak_source": "mma.sync.m16n8k32.s8 rate measured with tools/imma_rate.cu on this pool"},
+            "roofline": {"bound": "tensor", "achieved": imma_tops, "peak": imma_peak_tops, "unit": "TOP/s",
+                         "frac": imma_tops / imma_peak_tops, "traffic": traffic, "kernel": "gibbs_imma_kernel<4,4,false>",
+                         "peak_source": "int8 mma.sync.m16n8k32 (IMMA) rate measured with tools/imma_rate.cu on this pool's B200; "
+                                        "MEASURED_PEAKS.json holds no integer figure",
+                         "int8_ops_per_chain_sweep": IMMA_OPS_PER_SWEEP,
+                         "note": "achieved = the int8 tensor-core work the kernel EXECUTES (3 digit passes x 4*N*nh per chain-sweep) over "
+                                 "the measured launch time. The tensor pipe is not what limits it: the issue slots are "
+                                 "(Philox + Bernoulli epilogue), see issue_slots; fp64_equivalent restates the rate in the unit of "
+                                 "SURVEY 8(d) and is NOT a hardware fraction.",
+                         "issue_slots": {"achieved_ginstr_per_s": issue_rate / 1e9, "peak_ginstr_per_s": issue_peak / 1e9,
+                                         "frac": issue_rate / issue_peak, "instr_per_warp_half_sweep": instr_per_half_sweep,
+                                         "ncu_issue_active": 0.635, "ncu_source": "profiles/gibbs_imma_r01_ncu.txt"},
+                         "fp64_equivalent": {"tflops": fp64_equiv, "dmma_peak_tflops": peak_tflops, "ratio": fp64_equiv / peak_tflops,
+                                             "flop_per_chain_sweep": FLOP_PER_SWEEP, "peak_source": peak_src},
                          "fp64_path": {"kernel": "gibbs_kernel<4,4>", "value": world * C * k / (fp64_ms_step * 1e-3),
-                                       "ms_per_step": fp64_ms_step, "achieved": fp64_achieved, "frac": fp64_achieved / peak_tflops,
+                                       "ms_per_step": fp64_ms_step, "achieved": fp64_achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                                       "frac": fp64_achieved / peak_tflops,
                                        "how": "qcb_set_gibbs_mode(1): all-FP64 DMMA kernel, same samples bit for bit"}},
-            "e2e": {"value": e2e_value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": C * N_VIS * 8 + param_bytes,
-                    "d2h_bytes_per_step": C * N_VIS * 8, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "call": "qcb_rbm_gibbs_host (pinned host buffers, copies inside the timed region)"},
+            "e2e": {"value": e2e_value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": C * rowb + param_bytes,
+                    "d2h_bytes_per_step": C * rowb, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "call": "qcb_rbm_gibbs_host_packed (pinned host buffers; packed rows, ceil(N/8) bytes per chain each way; copies and "
+                            "sampling inside the timed region, pipelined in slices of whole grid waves)",
+                    "gpu_launches": int(e2e_launches),
+                    "sample_api": {"value": world * C * k * args.steps / api_packed_s, "ms_per_step": api_packed_s / args.steps * 1e3,
+                                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": C * rowb,
+                                   "call": "PositiveWaveFunction.sample(k, num_samples, packed=True) + device-to-host copy of the packed rows "
+                                           "(chains start in-kernel: no host RNG, no H2D)"},
+                    "sample_api_float64_rows": {"value": world * C * k * api_rows_steps / api_rows_s,
+                                                "ms_per_step": api_rows_s / api_rows_steps * 1e3, "h2d_bytes_per_step": 0,
+                                                "d2h_bytes_per_step": C * N_VIS * 8,
+                                                "call": "PositiveWaveFunction.sample(k, num_samples) (the reference's signature and float64 "
+                                                        "rows) + device-to-host copy of the rows"},
+                    "float64_rows_host_call": {"value": world * C * k * rows_steps / e2e_rows_s, "ms_per_step": e2e_rows_s / rows_steps * 1e3,
+                                               "h2d_bytes_per_step": C * N_VIS * 8 + param_bytes, "d2h_bytes_per_step": C * N_VIS * 8,
+                                               "call": "qcb_rbm_gibbs_host (round 1's e2e: float64 rows both ways, PCIe-bound)"}},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if sustained is not None:
+            line["sustained"] = sustained
         if world == 1:
-            cpu_v, cpu_times = cpu_baseline_sample(k, args.ref_chains, 3)
-            line["cpu_baseline"] = {"value": cpu_v, "unit": "chain-sweeps/s", "cores": torch.get_num_threads(), "kind": "port",
+            cpu_v, cpu_times, cpu_kind = cpu_baseline_sample(k, args.ref_chains, 3)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "chain-sweeps/s", "cores": torch.get_num_threads(), "kind": cpu_kind,
                                     "sample": f"{args.ref_chains} chains x k={k} sweeps, best of 3 ({min(cpu_times):.2f} s), "
-                                              "reference torch-CPU operator sequence (oracle/cpu_path.py)"}
+                                              + ("qucumber.rbm.BinaryRBM.gibbs_steps of the unmodified reference (oracle/_ref), gpu=False"
+                                                 if cpu_kind == "reference" else "reference torch-CPU operator sequence (oracle/cpu_path.py)")}
+            line["torch_cuda_baseline"] = torch_cuda_baseline(dev, k)
             line["extra"] = extra_metrics(dev, _lib)
         if sharded is not None:
             line["sharded"] = sharded
@@ -698,6 +945,7 @@ def main():
     ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
     ap.add_argument("--ref-chains", type=int, default=1 << 17, help="chains per step of the CPU reference sample")
     ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of the extra sustained run (0: skip)")
     ap.add_argument("--quick", action="store_true", help="kernel throughput only (skip e2e, CPU baseline and extras)")
     args = ap.parse_args()
     if args.impl == "reference":
