@@ -162,8 +162,30 @@ class NeuralStateBase(abc.ABC):
         """Lazy handle on the full visible space: accepted wherever a ``space`` tensor is."""
         return HilbertSpace(self.rbm_am.num_visible, self.device)
 
+    #: "auto" splits a full-space enumeration over the ranks from this many visible units on (smaller spaces are launch-bound)
+    shard_min_visible = 24
+
+    def _shards_space(self):
+        """(rank, world_size) to split a full-space enumeration over, or (0, 1)."""
+        from .. import distributed as qd
+
+        rank, world_size = qd.world()
+        if world_size == 1 or self.distributed is False:
+            return 0, 1
+        if self.distributed is True or self.rbm_am.num_visible >= self.shard_min_visible:
+            return rank, world_size
+        return 0, 1
+
     def normalization(self, space=None):
-        """Partition function / trace of the unnormalised state (neural_state.py:178-197)."""
+        """Partition function / trace of the unnormalised state (neural_state.py:178-197). Over the full space
+        (``space=None`` or a HilbertSpace handle) and under torch.distributed, each rank enumerates its index range and
+        the (max, sum) pairs are merged after one all-gather."""
+        rank, world_size = self._shards_space()
+        if world_size > 1 and (space is None or isinstance(space, HilbertSpace)):
+            from .. import distributed as qd
+
+            first, count = qd.shard_range(1 << self.rbm_am.num_visible, rank, world_size)
+            return qd.combine_logz(self.rbm_am.log_partition(first, count)).exp()
         return self.rbm_am.partition(space)
 
     def compute_normalization(self, space=None):
@@ -263,17 +285,24 @@ class NeuralStateBase(abc.ABC):
             all_grads = rbm.effective_energy_gradient(space, reduce=False)
             grad[0] -= torch.mv(all_grads.t(), probs)
             return grad
+        from .. import distributed as qd
+
         lib = _lib.load()
         args, keep = rbm._param_args()
-        out2 = rbm.log_partition()
-        logZ = float(out2[0] + out2[1].log())
+        # the index range splits over the ranks like the partition function; with log Z known the partial
+        # sums of p(r) grad E(r) are plain sums (one all-reduce of num_pars doubles)
+        rank, world_size = self._shards_space()
+        first, count = qd.shard_range(1 << rbm.num_visible, rank, world_size)
+        out2 = rbm.log_partition(first, count)
+        logZ = float(qd.combine_logz(out2) if world_size > 1 else out2[0] + out2[1].log())
         na = getattr(rbm, "num_aux", 0)
-        count = 1 << rbm.num_visible
         neg = torch.zeros(rbm.num_pars, dtype=torch.double, device=self.device)
         out8 = torch.empty(8, dtype=torch.double, device=self.device)
         ws = _lib.workspace(self.device, lib.qcb_workspace_bytes(_lib.OP_EXACT_STATS, rbm.num_visible, rbm.num_hidden, na, count))
-        _lib.check(lib.qcb_rbm_exact_stats_range(*args, 0, count, logZ, None, None, _lib.ptr(out8), _lib.ptr(neg), _lib.ptr(ws),
+        _lib.check(lib.qcb_rbm_exact_stats_range(*args, first, count, logZ, None, None, _lib.ptr(out8), _lib.ptr(neg), _lib.ptr(ws),
                                                  ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_exact_stats_range")
+        if world_size > 1:
+            qd.allreduce_sum_(neg)
         grad[0] -= neg
         return grad
 
@@ -291,56 +320,102 @@ class NeuralStateBase(abc.ABC):
             self._cd_seed, self._cd_sweep = next_seed(), 0
         return self._cd_seed, sweep0
 
+    #: "auto": under torch.distributed (world_size > 1) large batches are sharded over the ranks and the partial gradient
+    #: sums all-reduced; small ones run as replicas. True / False force one or the other.
+    distributed = "auto"
+    #: "auto" shards a batch of at least this many rows per rank (rotated-basis batches: 1/64 of it, a row there costs 2^S rows)
+    shard_min_rows_per_rank = 4096
+
+    def _shards_batches(self, pos_rows, neg_rows, with_bases):
+        """(rank, world_size) to shard this batch over, or (0, 1) to run it on every rank as a replica."""
+        from .. import distributed as qd
+
+        rank, world_size = qd.world()
+        if world_size == 1 or self.distributed is False:
+            return 0, 1
+        if self.distributed is True:
+            return rank, world_size
+        floor = self.shard_min_rows_per_rank // (64 if with_bases else 1)
+        return (rank, world_size) if max(pos_rows, neg_rows) >= floor * world_size else (0, 1)
+
+    def _cd_gradients_local(self, k, pos, neg, bases, pos_scale, neg_scale, chain_id0, seed, sweep0):
+        """pos_scale * sum_rows grad E(pos rows [in their bases]) + neg_scale * sum_chains grad E(v_k) for THESE rows and
+        chains — a partial sum when the batch is sharded. Chains are numbered chain_id0, chain_id0 + 1, ... (the Philox
+        key of a chain is its global number, so shards draw what the unsharded batch would). Without bases the whole
+        thing is ONE call (qcb_rbm_cd_step: gradient reduction, k fused sweeps, gradient reduction); v_k never leaves
+        the device workspace and ``neg`` is not modified."""
+        rbm = self.rbm_am
+        lib = _lib.load()
+        na = getattr(rbm, "num_aux", 0)
+        C = neg.shape[0]
+        args, keep = rbm._param_args()
+        if bases is None:
+            B = pos.shape[0]
+            g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
+            ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CD_STEP, rbm.num_visible, rbm.num_hidden, na, max(B, C, 1)))
+            _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), B, _lib.ptr(neg), C, int(k), seed, int(chain_id0), sweep0,
+                                           float(pos_scale), float(neg_scale), _lib.ptr(g), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(self.device)), "qcb_rbm_cd_step")
+            grad = [g]
+            for net in self.networks[1:]:
+                grad.append(torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device))
+            return grad
+        grad = self.gradient(pos, bases=bases) if pos.shape[0] else [
+            torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device) for net in self.networks]
+        for gr in grad:
+            gr.mul_(float(pos_scale))
+        if C:
+            vk = neg.clone()
+            ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CDK_NEG, rbm.num_visible, rbm.num_hidden, na, C))
+            _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, int(k), seed, int(chain_id0), sweep0, None, float(neg_scale),
+                                           _lib.ptr(grad[0]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_cdk_neg")
+        return grad
+
     def compute_batch_gradients(self, k, samples_batch, neg_batch, bases_batch=None):
-        """CD-k gradient of one batch (neural_state.py:417-447): positive phase from the data, negative
-        phase from k Gibbs sweeps started at ``neg_batch``. Without bases the whole thing is ONE call
-        (qcb_rbm_cd_step: gradient reduction, k fused sweeps, gradient reduction); v_k never leaves
-        the device workspace."""
+        """CD-k gradient of one batch (neural_state.py:417-447): positive phase from the data, negative phase from k
+        Gibbs sweeps started at ``neg_batch``. Under torch.distributed a large batch is sharded: each rank reduces its
+        rows and chains (scaled by the GLOBAL batch sizes), one sum all-reduce of the gradient vectors follows, issued
+        asynchronously and waited on right before the vectors are handed back for the update; every rank returns the
+        same gradients (the same as a single process up to summation order)."""
+        from .. import distributed as qd
+
         rbm = self.rbm_am
         lib = _lib.load()
         na = getattr(rbm, "num_aux", 0)
         seed, sweep0 = self._next_cd_stream(k)
         neg = neg_batch.to(device=self.device, dtype=torch.double).contiguous()
-        C = neg.shape[0]
-        if bases_batch is None:
-            pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
-            B = pos.shape[0]
+        pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
+        B, C = pos.shape[0], neg.shape[0]
+        rank, world_size = self._shards_batches(B, C, bases_batch is not None)
+        if world_size > 1:
+            pf, pc = qd.shard_range(B, rank, world_size)
+            nf, nc = qd.shard_range(C, rank, world_size)
+            bases = None if bases_batch is None else np.asarray(bases_batch)[pf:pf + pc]
+            grad = self._cd_gradients_local(k, pos[pf:pf + pc], neg[nf:nf + nc], bases, 1.0 / float(B), -1.0 / float(C), nf, seed, sweep0)
+            qd.allreduce_sum_(grad)
+            return grad
+        if (bases_batch is None and self.fuse_epochs and na == 0 and rbm.num_visible <= 64 and rbm.num_hidden <= 64 and 0 < B <= 4096
+                and 0 < C <= 4096 and hasattr(rbm, "weights")):
+            # small RBM, small batch: positive phase, k sweeps and negative phase in ONE cluster launch
+            # (qcb_rbm_cd_epoch with a single batch and lr = 0: parameters untouched, gradient out)
             g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
-            if (self.fuse_epochs and na == 0 and rbm.num_visible <= 64 and rbm.num_hidden <= 64 and 0 < B <= 4096
-                    and 0 < C <= 4096 and hasattr(rbm, "weights")):
-                # small RBM, small batch: positive phase, k sweeps and negative phase in ONE cluster launch
-                # (qcb_rbm_cd_epoch with a single batch and lr = 0: parameters untouched, gradient out)
-                _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(rbm.weights.data), _lib.ptr(rbm.visible_bias.data),
-                                                _lib.ptr(rbm.hidden_bias.data), rbm.num_visible, rbm.num_hidden, _lib.ptr(pos), B, B,
-                                                _lib.ptr(neg), C, C, 1, int(k), 0.0, seed, sweep0, _lib.ptr(g),
-                                                _lib.stream_ptr(self.device)), "qcb_rbm_cd_epoch")
-                grad = [g]
-                for net in self.networks[1:]:
-                    grad.append(torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device))
-                return grad
-            args, keep = rbm._param_args()
-            ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CD_STEP, rbm.num_visible, rbm.num_hidden, na, max(B, C)))
-            _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), B, _lib.ptr(neg), C, int(k), seed, 0, sweep0, 1.0 / float(B),
-                                           -1.0 / float(C), _lib.ptr(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)),
-                       "qcb_rbm_cd_step")
+            _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(rbm.weights.data), _lib.ptr(rbm.visible_bias.data),
+                                            _lib.ptr(rbm.hidden_bias.data), rbm.num_visible, rbm.num_hidden, _lib.ptr(pos), B, B,
+                                            _lib.ptr(neg), C, C, 1, int(k), 0.0, seed, sweep0, _lib.ptr(g),
+                                            _lib.stream_ptr(self.device)), "qcb_rbm_cd_epoch")
             grad = [g]
             for net in self.networks[1:]:
                 grad.append(torch.zeros(getattr(self, net).num_pars, dtype=torch.double, device=self.device))
             return grad
-        grad = self.positive_phase_gradients(samples_batch, bases_batch=bases_batch)
-        args, keep = rbm._param_args()
-        vk = neg.clone()
-        ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CDK_NEG, rbm.num_visible, rbm.num_hidden, na, C))
-        _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(vk), C, int(k), seed, 0, sweep0, None, -1.0 / float(C), _lib.ptr(grad[0]),
-                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_cdk_neg")
-        return grad
+        return self._cd_gradients_local(k, pos, neg, bases_batch, 1.0 / float(B), -1.0 / float(C), 0, seed, sweep0)
 
     # ---- training loop --------------------------------------------------------------------------
     def _shuffle_data(self, pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples):
         """Per-epoch batching (neural_state.py:449-498): positive batches are a permutation of the
         data; negative batches reuse it when the sizes match, otherwise they are drawn with
         replacement (from the all-Z samples when bases are given)."""
-        pos, neg, pos_perm = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
+        pos, neg, pos_perm = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples,
+                                                   generator=self._shuffle_generator)
         pos_batches = [pos[s:s + pos_batch_size] for s in range(0, len(pos), pos_batch_size)]
         neg_batches = [neg[s:s + neg_batch_size] for s in range(0, len(neg), neg_batch_size)]
         if input_bases is not None:
@@ -350,20 +425,24 @@ class NeuralStateBase(abc.ABC):
         return zip(pos_batches, neg_batches)
 
     @staticmethod
-    def _shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples):
-        """The epoch's positive rows, negative rows (batches back to back) and the permutation used."""
-        pos_perm = torch.randperm(train_samples.shape[0])
+    def _shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples, generator=None):
+        """The epoch's positive rows, negative rows (batches back to back) and the permutation used. ``generator``: the
+        host generator to draw from (None: torch's default; under torch.distributed one seeded identically on all ranks)."""
+        pos_perm = torch.randperm(train_samples.shape[0], generator=generator)
         pos = train_samples[pos_perm]
         if input_bases is None:
             if neg_batch_size == pos_batch_size:
                 neg_perm = pos_perm
             else:
-                neg_perm = torch.randint(train_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long)
+                neg_perm = torch.randint(train_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long,
+                                         generator=generator)
             neg = train_samples[neg_perm]
         else:
-            neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long)
+            neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long, generator=generator)
             neg = z_samples[neg_perm]
         return pos, neg, pos_perm
+
+    _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
 
     #: set to False to force one C call per batch even where a whole epoch fits one launch
     fuse_epochs = True
@@ -437,7 +516,12 @@ class NeuralStateBase(abc.ABC):
         if input_bases is not None:
             z_samples = extract_refbasis_samples(train_samples, input_bases).to(device=self.device)
 
-        self._cd_seed, self._cd_sweep = next_seed(), 0
+        from .. import distributed as qd
+
+        # one Philox key per fit() call; under torch.distributed rank 0's key is broadcast and also seeds the host generator of
+        # the shuffles, so that every rank walks through the same batches whatever its own seeding was
+        self._cd_seed, self._cd_sweep = qd.broadcast_seed(next_seed(), self.device), 0
+        self._shuffle_generator = torch.Generator().manual_seed(self._cd_seed) if qd.world()[1] > 1 else None
         cbs.fire("on_train_start", self)
         num_batches = ceil(train_samples.shape[0] / pos_batch_size)
         epoch_iter = range(starting_epoch, epochs + 1)
@@ -445,10 +529,15 @@ class NeuralStateBase(abc.ABC):
             from tqdm import tqdm, tqdm_notebook
 
             epoch_iter = (tqdm_notebook if progbar == "notebook" else tqdm)(epoch_iter, desc="Epochs ")
-        fused_epoch = scheduler is None and self._epoch_fusable(optimizer, cbs, input_bases)  # schedulers count optimizer.step() calls
+        # one launch per epoch: small RBM, small batches (a single thread-block cluster walks the whole epoch); schedulers count
+        # optimizer.step() calls, so they keep the per-batch loop
+        fused_epoch = (scheduler is None and max(pos_batch_size, neg_batch_size) <= 4096
+                       and self._shards_batches(pos_batch_size, neg_batch_size, input_bases is not None)[1] == 1
+                       and self._epoch_fusable(optimizer, cbs, input_bases))
         for ep in epoch_iter:
             if fused_epoch:
-                pos, neg, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None)
+                pos, neg, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None,
+                                                    generator=self._shuffle_generator)
                 cbs.fire("on_epoch_start", self, ep)
                 nb = min(num_batches, ceil(neg.shape[0] / neg_batch_size))
                 self._fit_epoch_fused(pos, neg, nb, pos_batch_size, neg_batch_size, k, optimizer.param_groups[0]["lr"],
@@ -487,4 +576,5 @@ class NeuralStateBase(abc.ABC):
             if self.stop_training:
                 break
         self._cd_seed = None
+        self._shuffle_generator = None
         cbs.fire("on_train_end", self)

@@ -24,22 +24,29 @@ def _positive_stats(nn_state, target):
     """(logZ, out8) for a PositiveWaveFunction over the full space; target is (2, 2^N) or None."""
     from ..nn_states import PositiveWaveFunction
 
+    from .. import distributed as qd
+
     assert isinstance(nn_state, PositiveWaveFunction)
     rbm = nn_state.rbm_am
     lib = _lib.load()
-    out2 = rbm.log_partition()
-    logZ = float(out2[0] + out2[1].log())
+    # Under torch.distributed the index range is split over the ranks (SURVEY 8(e)): per-rank (max, sum) pairs are
+    # all-gathered and merged into log Z, the five partial sums of the second pass are plain sums -> one all-reduce.
+    rank, world_size = nn_state._shards_space()
+    first, count = qd.shard_range(1 << rbm.num_visible, rank, world_size)
+    out2 = rbm.log_partition(first, count)
+    logZ = float(qd.combine_logz(out2) if world_size > 1 else out2[0] + out2[1].log())
     args, keep = rbm._param_args()
-    count = 1 << rbm.num_visible
     t_re = t_im = None
     if target is not None:
         target = target.to(device=nn_state.device, dtype=torch.double)
-        t_re, t_im = target[0].contiguous(), target[1].contiguous()
+        t_re, t_im = target[0][first:first + count].contiguous(), target[1][first:first + count].contiguous()
     out8 = torch.empty(8, dtype=torch.double, device=nn_state.device)
     ws = _lib.workspace(nn_state.device, lib.qcb_workspace_bytes(_lib.OP_EXACT_STATS, rbm.num_visible, rbm.num_hidden, 0, count))
-    _lib.check(lib.qcb_rbm_exact_stats_range(*args, 0, count, logZ, _lib.ptr(t_re), _lib.ptr(t_im), _lib.ptr(out8), None,
+    _lib.check(lib.qcb_rbm_exact_stats_range(*args, first, count, logZ, _lib.ptr(t_re), _lib.ptr(t_im), _lib.ptr(out8), None,
                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(nn_state.device)),
                "qcb_rbm_exact_stats_range")
+    if world_size > 1:
+        qd.allreduce_sum_(out8)
     return logZ, out8
 
 

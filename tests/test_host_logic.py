@@ -211,6 +211,76 @@ def _worker(rank, world_size, port, out_dir):
     dist.destroy_process_group()
 
 
+def _fit_worker(rank, world_size, port, out_dir):
+    """fit() with the batch sharded over two gloo ranks. The per-rank numbers come from the oracle (no GPU here): the
+    state class below overrides the ONE numeric hook of the sharded path, so what is exercised is the host logic that
+    ships — row / chain shards, global scales, global chain ids, seed broadcast, identical shuffles, all-reduce, update."""
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_binary_params, random_states
+    from oracle.rbm_oracle import BinaryRBMOracle
+    from qucumber_b200 import PositiveWaveFunction
+    from qucumber_b200 import distributed as qd
+
+    calls = []
+
+    class OracleBacked(PositiveWaveFunction):
+        def _cd_gradients_local(self, k, pos, neg, bases, pos_scale, neg_scale, chain_id0, seed, sweep0):
+            rbm = self.rbm_am
+            orc = BinaryRBMOracle(rbm.weights.numpy(), rbm.visible_bias.numpy(), rbm.hidden_bias.numpy())
+            g = np.zeros(rbm.num_pars)
+            if pos.shape[0]:
+                g += pos_scale * orc.effective_energy_gradient(pos.numpy())
+            if neg.shape[0]:
+                vk = orc.gibbs_steps_philox(k, neg.numpy(), seed=seed, chain_id0=chain_id0, sweep0=sweep0)
+                g += neg_scale * orc.effective_energy_gradient(vk)
+            calls.append((pos.shape[0], neg.shape[0], chain_id0))
+            return [torch.tensor(g)]
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world_size)
+    n, nh = 6, 5
+    W, b, c = make_binary_params(n, nh, 3)
+    data = torch.tensor(random_states(53, n, 4))
+
+    def run(sharded):
+        torch.manual_seed(100 + rank)  # ranks seeded DIFFERENTLY on purpose: fit() must broadcast rank 0's key
+        st = OracleBacked(n, nh, gpu=False)
+        with torch.no_grad():
+            st.rbm_am.weights.copy_(torch.tensor(W)); st.rbm_am.visible_bias.copy_(torch.tensor(b)); st.rbm_am.hidden_bias.copy_(torch.tensor(c))
+        st.distributed = sharded
+        st.fuse_epochs = False  # the one-launch-per-epoch kernel needs the GPU; the replica run goes batch by batch too
+        del calls[:]
+        torch.manual_seed(7 if rank == 0 else 8)
+        st.fit(data, epochs=2, pos_batch_size=10, neg_batch_size=15, k=2, lr=0.1)
+        return torch.cat([p.detach().reshape(-1) for p in st.rbm_am.parameters()]), list(calls)
+
+    sharded, calls_s = run(True)
+    # every rank took its shard of each batch (last batch: 3 positive rows -> 2 + 1), chains numbered globally
+    assert [c[0] for c in calls_s[:6]] == ([5] * 5 + [2 if rank == 0 else 1])
+    assert all(c[1] in (7, 8) for c in calls_s) and all(c[2] == (0 if rank == 0 else 8) for c in calls_s)
+    gathered = [torch.empty_like(sharded) for _ in range(world_size)]
+    dist.all_gather(gathered, sharded)
+    assert torch.equal(gathered[0], gathered[1]), "ranks ended with different parameters"
+    # the unsharded run: same key (run() reseeds torch's generator, rank 0's key is broadcast either way) and therefore the
+    # same shuffles and draws, full batches on every rank -> the same parameters up to the order of the sums
+    replica, calls_r = run(False)
+    assert [c[0] for c in calls_r[:6]] == [10] * 5 + [3] and all(c[2] == 0 for c in calls_r)
+    assert torch.allclose(sharded, replica, rtol=1e-12, atol=1e-14), float((sharded - replica).abs().max())
+    assert not torch.equal(sharded, torch.cat([torch.tensor(x).reshape(-1) for x in (W, b, c)])), "fit() did not move the parameters"
+    open(os.path.join(out_dir, f"fit_ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_fit_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_fit_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "fit_ok0").exists() and (tmp_path / "fit_ok1").exists()
+
+
 def test_two_rank_combine_logic_gloo(tmp_path):
     import torch.multiprocessing as mp
 

@@ -48,6 +48,59 @@ _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), 2048, _lib.ptr(v0), C, 3, 7
                                ws.numel(), _lib.stream_ptr(dev)), "cd_step")
 err = float((gs - gref).abs().max() / gref.abs().max())
 assert err <= 1e-12, err
+# ---- the same things through the public API (round 2): fit(), normalization(), fidelity / KL, exact gradients ----
+from qucumber_b200 import ComplexWaveFunction  # noqa: E402
+from qucumber_b200.utils import training_statistics as ts  # noqa: E402
+
+
+def flat(state):
+    return torch.cat([p.detach().reshape(-1) for net in state.networks for p in getattr(state, net).parameters()])
+
+
+def fitted(cls, distributed, data, bases=None, **kw):
+    torch.manual_seed(11)
+    st = cls(data.shape[1], gpu=True)
+    st.distributed = distributed
+    torch.manual_seed(12)
+    st.fit(data, input_bases=bases, **kw)
+    return flat(st)
+
+
+gd = torch.Generator().manual_seed(5)
+data = (torch.rand(40000, 20, generator=gd) < 0.3).double()
+a = fitted(PositiveWaveFunction, True, data, epochs=2, pos_batch_size=10000, neg_batch_size=12000, k=3, lr=0.05)
+b = fitted(PositiveWaveFunction, False, data, epochs=2, pos_batch_size=10000, neg_batch_size=12000, k=3, lr=0.05)
+fit_err = float((a - b).abs().max() / b.abs().max())
+assert fit_err <= 1e-10, fit_err
+gathered = [torch.empty_like(a) for _ in range(world)]
+dist.all_gather(gathered, a)
+assert all(torch.equal(gathered[0], x) for x in gathered), "ranks ended fit() with different parameters"
+# rotated-basis training: the batch rows (with their bases) are sharded, both gradient vectors all-reduced
+nq = 6
+dq = (torch.rand(512, nq, generator=gd) < 0.5).double()
+bq = np.array([list("XZYZZZ") if i % 3 == 0 else (list("ZZZZXY") if i % 3 == 1 else list("ZZZZZZ")) for i in range(512)])
+ac = fitted(ComplexWaveFunction, True, dq, bq, epochs=2, pos_batch_size=128, neg_batch_size=128, k=2, lr=0.05)
+bc = fitted(ComplexWaveFunction, False, dq, bq, epochs=2, pos_batch_size=128, neg_batch_size=128, k=2, lr=0.05)
+cfit_err = float((ac - bc).abs().max() / bc.abs().max())
+assert cfit_err <= 1e-10, cfit_err
+# normalization / fidelity / KL / exact gradients with the index range split over the ranks
+st = PositiveWaveFunction(n, n, gpu=True)
+st.rbm_am.load_state_dict(rbm.state_dict())
+tg = torch.Generator(device="cuda").manual_seed(9)
+target = torch.zeros(2, 1 << n, dtype=torch.double, device=dev)
+target[0].copy_(torch.rand(1 << n, dtype=torch.double, device=dev, generator=tg))
+target /= target[0].norm()
+vals = {}
+for mode in (True, False):
+    st.distributed = mode
+    vals[mode] = (float(st.normalization()), ts.fidelity(st, target), ts.KL(st, target),
+                  st.compute_exact_gradients(pos[:64])[0])
+for i in range(3):
+    assert abs(vals[True][i] - vals[False][i]) <= 1e-11 * abs(vals[False][i]), (i, vals[True][i], vals[False][i])
+eg_err = float((vals[True][3] - vals[False][3]).abs().max() / vals[False][3].abs().max())
+assert eg_err <= 1e-10, eg_err
 if rank == 0:
-    print(f"dist_check ok on {world} GPUs: sharded logZ {sharded:.12f}, gibbs shards identical, CD gradient rel err {err:.2e}")
+    print(f"dist_check ok on {world} GPUs: sharded logZ {sharded:.12f}, gibbs shards identical, CD gradient rel err {err:.2e}, "
+          f"fit() sharded vs replica {fit_err:.1e} (positive) {cfit_err:.1e} (complex, bases), Z / fidelity / KL equal, "
+          f"exact gradient {eg_err:.1e}")
 dist.destroy_process_group()
