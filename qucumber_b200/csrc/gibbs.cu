@@ -403,12 +403,14 @@ static int pick_blocks(int units) {
 }
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
+size_t gibbs_umma_workspace_bytes(int N, int nhid);
 
 size_t gibbs_workspace_bytes(int N, int nhid) {
   const int HB = pick_blocks(nhid), VB = pick_blocks(N);
   if (HB == 0 || VB == 0) return 0;
   const size_t a = align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256), b = gibbs_imma_workspace_bytes(N, nhid);
-  return a > b ? a : b;
+  const size_t c = gibbs_umma_workspace_bytes(N, nhid);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 template <int HB, int VB>
@@ -442,6 +444,10 @@ int run_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, cudaStr
 int run_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st);
 int run_philox_init_states(double* v, int64_t C, int N, uint64_t seed, uint64_t chain_id0, uint64_t sweep0, cudaStream_t st);
 int64_t gibbs_imma_wave_chains(int N, int nhid);
+size_t gibbs_umma_workspace_bytes(int N, int nhid);
+int64_t gibbs_umma_wave_chains();
+int try_gibbs_umma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                   void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
 
 static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
   const int HB = pick_blocks(p.nhid()), VB = pick_blocks(p.N);
@@ -458,11 +464,12 @@ static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
 size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
   const size_t img = gibbs_workspace_bytes(N, nhid);
   const bool imma = gibbs_imma_workspace_bytes(N, nhid) != 0;
-  return img + (imma && g_gibbs_mode == 0 ? 0 : align_up((size_t)(C > 0 ? C : 0) * N * sizeof(double), 256));
+  return img + (imma && g_gibbs_mode != 1 ? 0 : align_up((size_t)(C > 0 ? C : 0) * N * sizeof(double), 256));
 }
 
 // Chains one full wave of the persistent grid processes (slicing a host pipeline at multiples of it avoids ragged tails)
 int64_t gibbs_wave_chains(int N, int nhid) {
+  if (g_gibbs_mode == 2 && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
   const int64_t w = gibbs_imma_wave_chains(N, nhid);
   return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
 }
@@ -481,7 +488,12 @@ int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, ui
   if (C == 0) return QCB_OK;
   if (sweep0 + (uint64_t)k > (1ull << 32))
     return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
-  if (g_gibbs_mode == 0) {
+  if (g_gibbs_mode == 2) {
+    int handled = 0;
+    rc = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+    if (rc != QCB_OK || handled) return rc;
+  }
+  if (g_gibbs_mode == 0 || g_gibbs_mode == 2) {
     int handled = 0;
     rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
     if (rc != QCB_OK || handled) return rc;
@@ -528,11 +540,15 @@ static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v,
   }
   if (sweep0 + (uint64_t)k > (1ull << 32))
     return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
-  if (uniforms == nullptr && g_gibbs_mode == 0 && allow_imma) {
+  if (uniforms == nullptr && g_gibbs_mode != 1 && allow_imma) {
     int handled = 0;
     ChainIO io;
     io.v_in = v_in;
     io.v_out = v;
+    if (g_gibbs_mode == 2) {
+      const int rcu = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+      if (rcu != QCB_OK || handled) return rcu;
+    }
     const int rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
     if (rc != QCB_OK || handled) return rc;
   }
