@@ -95,10 +95,14 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
                   uint64_t seed, uint64_t chain_id0, uint64_t sweep0, const double* uniforms,
                   void* ws, size_t ws_bytes, void* stream);
 
-/* Kernel selection for qcb_rbm_gibbs when uniforms == NULL.  mode 0 (default): layers of up to 64 units use
- * the integer-exact tensor-core filter (csrc/gibbs_imma.cu: W v in exact 24-bit fixed point on the int8
- * tensor cores, FP64 re-evaluation of the units the rigorous error bound cannot decide); mode 1: always
- * the FP64 tensor-core kernel (csrc/gibbs.cu).  Both draw the same numbers and make the same decisions. */
+/* Kernel selection for qcb_rbm_gibbs / qcb_rbm_sample / the packed and host variants when uniforms == NULL.
+ * Layers of up to 64 units use an integer-exact tensor-core filter: W v in exact 24-bit fixed point on the int8 tensor
+ * cores, FP64 re-evaluation of the units the rigorous error bound cannot decide.  Two implementations:
+ *   csrc/gibbs_umma.cu — tcgen05.mma.kind::i8, accumulators in tensor memory (both layers 33..64 units);
+ *   csrc/gibbs_imma.cu — mma.sync.m16n8k32 (any layers up to 64 units).
+ * mode 0 (default): automatic — the tcgen05 kernel where its shape fits and k >= 3, else the mma.sync kernel, else the
+ * FP64 kernel; mode 1: always the FP64 tensor-core kernel (csrc/gibbs.cu); mode 2: the tcgen05 kernel wherever its shape
+ * fits (any k); mode 3: never the tcgen05 kernel.  All kernels draw the same numbers and make the same decisions. */
 int qcb_set_gibbs_mode(int mode);
 
 /* Test hook: runs the integer-filter kernel and reports in stats2 (device, two uint64, caller-zeroed)

@@ -162,8 +162,9 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
 }
 
 int qcb_set_gibbs_mode(int mode) {
-  if (mode < 0 || mode > 2)
-    return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (default), 1 (FP64 tensor cores only) or 2 (tcgen05 / TMEM integer filter where it applies)");
+  if (mode < 0 || mode > 3)
+    return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits) "
+                                 "or 3 (mma.sync integer filter, never tcgen05)");
   g_gibbs_mode = mode;
   return QCB_OK;
 }

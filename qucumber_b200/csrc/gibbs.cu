@@ -435,7 +435,12 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
   return QCB_OK;
 }
 
-int g_gibbs_mode = 0;  // 0: integer-exact IMMA filter where it applies, 1: always the FP64 DMMA kernel
+// 0: automatic (integer-exact filter where it applies: tcgen05 / TMEM kernel for two layers of 33..64 units and at least
+// GIBBS_UMMA_MIN_K sweeps, mma.sync kernel otherwise), 1: always the FP64 DMMA kernel, 2: tcgen05 kernel wherever its shape
+// fits, 3: never the tcgen05 kernel.  All of them draw the same numbers and make the same decisions.
+int g_gibbs_mode = 0;
+constexpr int GIBBS_UMMA_MIN_K = 3;  // below that the mma.sync kernel's TMA-prefetched state tiles win (k = 1: 0.29 vs 0.35 ms)
+static bool use_umma(int k) { return g_gibbs_mode == 2 || (g_gibbs_mode == 0 && k >= GIBBS_UMMA_MIN_K); }
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
@@ -469,7 +474,7 @@ size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
 
 // Chains one full wave of the persistent grid processes (slicing a host pipeline at multiples of it avoids ragged tails)
 int64_t gibbs_wave_chains(int N, int nhid) {
-  if (g_gibbs_mode == 2 && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
+  if ((g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
   const int64_t w = gibbs_imma_wave_chains(N, nhid);
   return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
 }
@@ -488,12 +493,12 @@ int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, ui
   if (C == 0) return QCB_OK;
   if (sweep0 + (uint64_t)k > (1ull << 32))
     return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
-  if (g_gibbs_mode == 2) {
+  if (use_umma(k)) {
     int handled = 0;
     rc = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
     if (rc != QCB_OK || handled) return rc;
   }
-  if (g_gibbs_mode == 0 || g_gibbs_mode == 2) {
+  if (g_gibbs_mode != 1) {
     int handled = 0;
     rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
     if (rc != QCB_OK || handled) return rc;
@@ -545,7 +550,7 @@ static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v,
     ChainIO io;
     io.v_in = v_in;
     io.v_out = v;
-    if (g_gibbs_mode == 2) {
+    if (use_umma(k)) {
       const int rcu = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
       if (rcu != QCB_OK || handled) return rcu;
     }

@@ -17,6 +17,7 @@
 // Units are kept in "p-order" inside the kernel so that the 8 units served by one Philox call are 8 consecutive TMEM
 // columns: unit u = 32 hh + 16 h + 4 c + w  <->  p = 32 hh + 8 c + 4 h + w  (hh: 32-unit half, c: call, h: 16-bit half).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace qcb {
 
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
   uint32_t* words = reinterpret_cast<uint32_t*>(smem + GU_IMAGE_BYTES + GU_OPERAND_BYTES);  // [2 buffers][2 halves][128 rows]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(words + 2 * 2 * GU_TILE);            // [0]: image copy, [1]: MMA completion
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  uint32_t* arrive_cnt = tmem_slot + 1;  // threads that have published their bits for the next conditional update
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hh = warp >> 2;                  // which 32-unit half of the output layer this thread decides
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
   if (tid == 0) {
     mbar_init(mbar, 1);
     mbar_init(mbar + 1, 1);
+    *arrive_cnt = 0u;
   }
   __syncthreads();
   if (tid == 0) {
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
   const int rowbytes = packed_row_bytes(N);
   // instruction descriptor: D s32, A u8, B s8, both K-major, N = 128, M = 128
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint32_t sA_addr = smem_u32(sA), sBh_addr = smem_u32(smem + GU_BH_OFF), sBv_addr = smem_u32(smem + GU_BV_OFF);
+  const uint64_t adesc = gu_desc(smem_u32(sA)), bdesc_h = gu_desc(smem_u32(smem + GU_BH_OFF)), bdesc_v = gu_desc(smem_u32(smem + GU_BV_OFF));
   uint32_t mma_phase = 0u;
 
   const int64_t num_tiles = (a.C + GU_TILE - 1) / GU_TILE;
@@ -302,16 +305,27 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
     // ---- initial state of this thread's (chain, visible half), natural bit order -> p-order ----
     uint32_t cur = 0u;
     if (a.in_mode == 0) {
-      // float64 rows: a warp walks its 32 chains row by row (256 contiguous bytes per load), ballots the bits
-      const int64_t wbase = chain_base + 32 * (warp & 3);
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const int j = 32 * hh + lane;
-        unsigned long long bits = 0ull;
-        if (wbase + rr < a.C && j < N) bits = reinterpret_cast<const unsigned long long*>(a.v_in)[(wbase + rr) * N + j];
-        const uint32_t bal = __ballot_sync(0xffffffffu, (bits << 1) != 0ull);
-        if (lane == rr) cur = bal;
+      // float64 rows: warp w fetches rows 16 w .. 16 w + 15 of the tile, 256 contiguous bytes per load (two per row), ballots
+      // the bits and leaves the two 32-bit words of each row in shared memory (buffer 0 of `words`, which nobody reads at
+      // this point); after the barrier every thread picks up the word of its own (chain, half)
+#pragma unroll 8
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * warp + rr;
+        const int64_t c = chain_base + r;
+        unsigned long long d0 = 0ull, d1 = 0ull;
+        if (c < a.C) {
+          const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(a.v_in) + c * N;
+          if (lane < N) d0 = rp[lane];
+          if (lane + 32 < N) d1 = rp[lane + 32];
+        }
+        const uint32_t b0 = __ballot_sync(0xffffffffu, (d0 << 1) != 0ull), b1 = __ballot_sync(0xffffffffu, (d1 << 1) != 0ull);
+        if (lane == 0) {
+          words[r] = b0;
+          words[GU_TILE + r] = b1;
+        }
       }
+      __syncthreads();
+      cur = words[hh * GU_TILE + row];
     } else if (a.in_mode == 1) {
       if (ch < a.C) {
         const uint8_t* rowp = a.bits_in + ch * rowbytes;
@@ -347,14 +361,19 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
         *reinterpret_cast<uint4*>(base + (4 + 2 * hh + 1) * GU_LBO) = hi4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
-      asm volatile("tcgen05.fence::before_thread_sync;\n");
-      __syncthreads();
-      if (tid == 0) {
+      asm volatile("tcgen05.fence::before_thread_sync;\n");       // ... and this thread's TMEM reads of the previous accumulators are done
+      // No CTA barrier: every thread checks in on a shared counter (release) and carries on with its Philox draws; the LAST one
+      // to arrive (acquire: it sees all 256 publications) resets the counter and issues the MMAs.  A barrier here made 24 % of all
+      // warp samples wait for the slowest warp of the CTA (ncu, profiles/gibbs_umma_r02b_ncu.txt).
+      uint32_t arrived;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(arrived) : "r"(smem_u32(arrive_cnt)) : "memory");
+      if (arrived == GU_THREADS - 1) {
+        *reinterpret_cast<volatile uint32_t*>(arrive_cnt) = 0u;  // nobody checks in again before this MMA has completed
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const uint32_t sB_addr = back ? sBv_addr : sBh_addr;
+        const uint64_t bdesc = back ? bdesc_v : bdesc_h;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          gu_mma(tmem, gu_desc(sA_addr + ks * 2 * GU_LBO), gu_desc(sB_addr + ks * 2 * GU_LBO), idesc, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks)  // consecutive K = 32 slices are 2 LBO apart: only the start-address field moves
+          gu_mma(tmem, adesc + (uint64_t)(ks * ((2 * GU_LBO) >> 4)), bdesc + (uint64_t)(ks * ((2 * GU_LBO) >> 4)), idesc, ks > 0 ? 1u : 0u);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 1)) : "memory");
       }
       const float* bias = (back ? biasV : biasH) + 32 * hh;
@@ -404,12 +423,21 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
     // ---- final state: p-order -> natural, float64 rows and / or packed rows ----
     const uint32_t nat = gu_p_to_natural(cur & valid_v);
     if (a.v != nullptr) {
-      const int64_t wbase = chain_base + 32 * (warp & 3);
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const uint32_t word = __shfl_sync(0xffffffffu, nat, rr);
-        const int j = 32 * hh + lane;
-        if (wbase + rr < a.C && j < N) a.v[(wbase + rr) * N + j] = ((word >> lane) & 1u) ? 1.0 : 0.0;
+      // float64 rows out: the words go through buffer 1 of `words` (free once every thread has left the last update's cold
+      // path), then warp w writes rows 16 w .. 16 w + 15, 256 contiguous bytes per store
+      __syncthreads();
+      words[2 * GU_TILE + hh * GU_TILE + row] = nat;
+      __syncthreads();
+#pragma unroll 8
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * warp + rr;
+        const int64_t c = chain_base + r;
+        if (c < a.C) {
+          const uint32_t w0 = words[2 * GU_TILE + r], w1 = words[3 * GU_TILE + r];
+          double* rp = a.v + c * N;
+          if (lane < N) rp[lane] = (w0 >> lane) & 1u ? 1.0 : 0.0;
+          if (lane + 32 < N) rp[lane + 32] = (w1 >> lane) & 1u ? 1.0 : 0.0;
+        }
       }
     }
     if (a.bits_out != nullptr && ch < a.C) {
@@ -465,7 +493,11 @@ int try_gibbs_umma(const StackedParams& p, const ChainIO& io, int64_t C, int k, 
     QCB_CUDA(cudaFuncSetAttribute(gibbs_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_umma_kernel, GU_THREADS, smem));
     if (occ < 1) return fail(QCB_ERR_CUDA, "gibbs (umma) kernel does not fit on an SM");
-    blocks_per_sm = occ > GU_MIN_CTAS ? GU_MIN_CTAS : occ;  // never more CTAs than 512 / 128 TMEM columns: tcgen05.alloc would spin
+    if (getenv("QCB_DEBUG_OCCUPANCY") != nullptr) fprintf(stderr, "qcb: gibbs_umma occupancy query = %d CTAs / SM (smem %zu B)\n", occ, smem);
+    // 4 CTAs per SM by construction: 64 registers x 256 threads, 52 KB of shared memory and 128 of the 512 TMEM columns each
+    // (shared memory keeps a fifth CTA out, so tcgen05.alloc never has to wait).  The occupancy query of this toolkit
+    // answers 1 for a kernel that allocates tensor memory; CTAs beyond what is resident simply wait their turn.
+    blocks_per_sm = GU_MIN_CTAS;
   }
   const int64_t tiles = (C + GU_TILE - 1) / GU_TILE;
   const int64_t cap = (int64_t)sm_count() * blocks_per_sm;

@@ -392,7 +392,7 @@ def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
     identical decisions on 2^20 chains; the rigorous error bound of the filter is never exceeded."""
     from qucumber_b200 import BinaryRBM, _lib
 
-    for (n, nh, scale) in [(64, 64, None), (10, 10, None), (33, 60, 1.5), (64, 20, 0.01)]:
+    for (n, nh, scale) in [(64, 64, None), (10, 10, None), (33, 60, 1.5), (64, 20, 0.01), (48, 64, 0.3), (64, 33, None)]:
         W, b, c = make_binary_params(n, nh, 161, bias_scale=0.5, weight_scale=scale)
         rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
         C = 1 << 20 if n == 64 and nh == 64 else 1 << 16
@@ -403,8 +403,13 @@ def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
             ref = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
         finally:
             _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
-        got = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
-        assert torch.equal(got, ref), (n, nh)
+        for mode in (0, 2, 3):  # automatic, tcgen05 / TMEM kernel (where the shape fits), mma.sync kernel
+            try:
+                _lib.check(lib.qcb_set_gibbs_mode(mode), "mode")
+                got = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
+            finally:
+                _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
+            assert torch.equal(got, ref), (n, nh, mode)
         stats = torch.zeros(2, dtype=torch.int64, device=cuda)
         args, keep = rbm._param_args()
         vv = v0.clone()
@@ -422,7 +427,14 @@ def test_integer_filter_kernel_extreme_parameters(lib, cuda, case):
     24-bit window, margins >= 1) must fall through to the exact path: same samples as the FP64 kernel."""
     from qucumber_b200 import BinaryRBM, _lib
 
-    n, nh, C = 24, 40, 4096
+    _run_extreme_case(lib, cuda, case, 24, 40)
+    _run_extreme_case(lib, cuda, case, 40, 64)   # both layers in 33..64: the tcgen05 kernel's shapes
+
+
+def _run_extreme_case(lib, cuda, case, n, nh):
+    from qucumber_b200 import BinaryRBM, _lib
+
+    C = 4096
     W, b, c = make_binary_params(n, nh, 171, bias_scale=0.5)
     if case == "saturated":
         W *= 40.0            # |x| up to several hundred: e^{-x} overflows float
@@ -444,12 +456,17 @@ def test_integer_filter_kernel_extreme_parameters(lib, cuda, case):
         ref = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
     finally:
         _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
-    got = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
-    assert torch.equal(got, ref), case
+    for mode in (0, 2, 3):
+        try:
+            _lib.check(lib.qcb_set_gibbs_mode(mode), "mode")
+            got = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
+        finally:
+            _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
+        assert torch.equal(got, ref), (case, n, nh, mode)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("n,nh,C", [(7, 5, 37), (33, 20, 50), (64, 64, 19), (10, 10, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,nh,C", [(7, 5, 37), (33, 20, 50), (64, 64, 19), (10, 10, 1), (63, 41, 300)])
 def test_gibbs_ragged_and_unaligned_state_tiles(lib, cuda, mode, n, nh, C):
     """State tiles reach the kernels by TMA bulk copies when the span is 16-byte aligned and a multiple of 16 bytes;
     odd N, a ragged last group and an 8-byte-misaligned view must take the plain-copy path and give the same

@@ -41,10 +41,11 @@ def test_pack_unpack_equals_numpy_packbits(lib, cuda, n):
 
 
 @pytest.mark.parametrize("n,nh", SHAPES)
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_sample_chains_bit_exact_vs_oracle(lib, cuda, n, nh, mode):
-    """v0 drawn in the kernel (Philox stream 5) + k sweeps == the oracle's restatement, for both kernels
-    (mode 1 forces the FP64 kernel, which goes through the separate init / pack kernels)."""
+    """v0 drawn in the kernel (Philox stream 5) + k sweeps == the oracle's restatement, for every kernel (mode 0 automatic,
+    1 forces the FP64 kernel, which goes through the separate init / pack kernels, 2 the tcgen05 / TMEM kernel where the
+    shape fits, 3 the mma.sync kernel)."""
     rbm, orc = _pair(n, nh, 61)
     lib.qcb_set_gibbs_mode(mode)
     try:
@@ -63,7 +64,7 @@ def test_sample_chains_bit_exact_vs_oracle(lib, cuda, n, nh, mode):
 def test_sample_chains_purification(lib, cuda):
     from qucumber_b200 import PurificationRBM
 
-    for (n, nh, na) in [(2, 2, 2), (6, 5, 7), (10, 10, 10), (20, 40, 30)]:
+    for (n, nh, na) in [(2, 2, 2), (6, 5, 7), (10, 10, 10), (20, 40, 30), (40, 20, 30), (64, 32, 32)]:  # the last two: tcgen05 shapes
         W, U, b, c, d = make_purification_params(n, nh, na, 5)
         rbm = load_purification(PurificationRBM(n, nh, na, gpu=True), W, U, b, c, d)
         orc = PurificationRBMOracle(W, U, b, c, d)

@@ -1,4 +1,5 @@
-"""One launch of the default Gibbs kernel at benchmark shape (target of an ncu --set full capture)."""
+"""Launches of a Gibbs kernel at benchmark shape (target of an ncu --set full capture): gibbs_profile.py [k] [mode]
+(mode 0: mma.sync integer filter, 1: FP64 DMMA, 2: tcgen05 / TMEM integer filter)."""
 import os
 import sys
 
@@ -6,10 +7,12 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from qucumber_b200 import BinaryRBM  # noqa: E402
+from qucumber_b200 import BinaryRBM, _lib  # noqa: E402
 
 dev = torch.device("cuda")
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+_lib.load().qcb_set_gibbs_mode(mode)
 n = 64
 g = torch.Generator().manual_seed(7)
 rbm = BinaryRBM(n, n, gpu=True)

@@ -132,6 +132,44 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128u));
 }
 
+// Throughput of the same MMA shape: `reps` batches of 4 x tcgen05.mma (M = N = 128, K = 32 each) issued back to back by one thread
+// per CTA, one commit + wait at the end; one CTA per SM (the tensor pipe is per SM).  Operand contents do not matter.
+__global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (M * K + N * K) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(128u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t lbo = (M / 8) * 128;
+  if (tid == 0) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int ks = 0; ks < K / 32; ++ks)
+        mma_i8(tmem, make_desc(smem_u32(smem) + ks * 2 * lbo, lbo, 128), make_desc(smem_u32(smem + M * K) + ks * 2 * lbo, lbo, 128), idesc, 1u);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    mbar_wait(&mbar, 0);
+    if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128u));
+}
+
 int main() {
   std::vector<uint8_t> hA((size_t)M * K);
   std::vector<int8_t> hB((size_t)N * K), hBl((size_t)N * K);
@@ -164,6 +202,26 @@ int main() {
         ++bad;
       }
     }
-  printf("{\"probe\": \"tcgen05.mma.kind::i8 M=%d N=%d K=%d\", \"mismatches\": %lld, \"round_trip_cycles\": %lld}\n", M, N, K, bad, cyc);
+  // rate: all SMs, timed with events
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int reps = 20000;
+  rate_kernel<<<sms, 128, smem>>>(100, dC);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  rate_kernel<<<sms, 128, smem>>>(reps, dC);
+  cudaEventRecord(e1);
+  e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  long long rcyc = 0;
+  cudaMemcpy(&rcyc, dC, 8, cudaMemcpyDeviceToHost);
+  const double ops = 2.0 * M * N * K * (double)reps * sms;
+  printf("{\"probe\": \"tcgen05.mma.kind::i8 M=%d N=%d K=%d\", \"mismatches\": %lld, \"round_trip_cycles\": %lld, "
+         "\"rate\": {\"sms\": %d, \"ms\": %.4f, \"tops\": %.1f, \"cycles_per_4_mma\": %.1f, \"error\": \"%s\"}}\n",
+         M, N, K, bad, cyc, sms, ms, ops / (ms * 1e-3) / 1e12, (double)rcyc / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
   return bad == 0 ? 0 : 2;
 }
