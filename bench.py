@@ -27,7 +27,10 @@ import torch  # noqa: E402
 
 N_VIS, N_HID = 64, 64
 FLOP_PER_SWEEP = 4 * N_VIS * N_HID  # dense contraction, both half-sweeps
-IMMA_OPS_PER_SWEEP = 3 * FLOP_PER_SWEEP  # the integer filter runs the contraction once per int8 digit of the 24-bit weights
+# int8 tensor-core work the default kernel EXECUTES per chain-sweep: two conditional updates, each a 128 x 128 x 128 tile
+# product per 128 chains ([v ; 128 v] against [d0 ; 2 d1 | d2 ; 0], structural zeros included) = 2 * 2 * 128 * 128 ops per chain
+UMMA_OPS_PER_SWEEP = 2 * 2 * 128 * 128
+IMMA_OPS_PER_SWEEP = 3 * FLOP_PER_SWEEP  # the mma.sync variant runs the contraction once per int8 digit of the 24-bit weights
 
 
 def synthetic_rbm():
@@ -699,6 +702,19 @@ def run_ours(args):
     barrier()
     lib.qcb_set_gibbs_mode(0)
     fp64_ms_step = max_over_ranks(f0.elapsed_time(f1)) / fp64_steps
+    # ... and the mma.sync (pre-Blackwell tensor path) variant of the integer filter: round 1's headline kernel
+    lib.qcb_set_gibbs_mode(3)
+    for _ in range(2):
+        rbm.gibbs_steps(k, v, overwrite=True, seed=args.seed, chain_id0=chain0, sweep0=sweep)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(fp64_steps):
+        rbm.gibbs_steps(k, v, overwrite=True, seed=args.seed, chain_id0=chain0, sweep0=sweep)
+    g1.record()
+    barrier()
+    lib.qcb_set_gibbs_mode(0)
+    imma_ms_step = max_over_ranks(g0.elapsed_time(g1)) / fp64_steps
 
     if args.quick:
         if rank == 0:
@@ -877,20 +893,28 @@ def run_ours(args):
                 peak_tflops = json.load(fh)["dmma_m8n8k4_tflops"]
             peak_src = "measured: FP64 DMMA m8n8k4 peak, tools/fp64_peaks.cu on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure"
         fp64_equiv = C * k * FLOP_PER_SWEEP / (ms_step * 1e-3) / 1e12  # per GPU: one launch processes C*k chain-sweeps
-        traffic, imma_peak_tops = None, 1137.0
-        tpath = os.path.join(ROOT, "profiles", "gibbs_traffic_r01.json")
+        traffic, imma_peak_tops, umma_peak_tops = None, 1137.0, 4500.0
+        tpath = os.path.join(ROOT, "profiles", "gibbs_traffic_r02.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
             traffic = tj.get("dram_bytes_per_launch")
             imma_peak_tops = tj.get("imma_s8_m16n8k32_peak_tops", imma_peak_tops)
-        imma_tops = C * k * IMMA_OPS_PER_SWEEP / (ms_step * 1e-3) / 1e12
+        ppath = os.path.join(ROOT, "profiles", "umma_i8_probe_r02.json")
+        umma_src = "fallback: nominal dense int8 peak (profiles/umma_i8_probe_r02.json missing)"
+        if os.path.exists(ppath):
+            with open(ppath) as fh:
+                umma_peak_tops = json.load(fh)["rate"]["tops"]
+            umma_src = ("measured: tcgen05.mma.kind::i8 M=N=128 issue rate on all 148 SMs of this pool's B200, tools/umma_i8_probe.cu "
+                        "(profiles/umma_i8_probe_r02.json); MEASURED_PEAKS.json holds no integer figure")
+        umma_tops = C * k * UMMA_OPS_PER_SWEEP / (ms_step * 1e-3) / 1e12
+        imma_tops = C * k * IMMA_OPS_PER_SWEEP / (imma_ms_step * 1e-3) / 1e12
         fp64_achieved = C * k * FLOP_PER_SWEEP / (fp64_ms_step * 1e-3) / 1e12
-        # issue slots: warp instructions of the hot loop (static SASS count per warp half-sweep of 16 chains,
-        # profiles/sass_r02.txt) against 4 schedulers x SMs x clock; ncu's measured issue-active is quoted beside it
+        # issue slots: warp instructions executed per chain-sweep (ncu smsp__inst_executed.sum of one k = 10 launch over C * k,
+        # profiles/gibbs_umma_r02_ncu.txt) against 4 schedulers x SMs x clock; ncu's measured issue-active is quoted beside it
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        instr_per_half_sweep = 849.0
-        issue_rate = (C / 16.0) * k * 2 * instr_per_half_sweep / (ms_step * 1e-3)
+        instr_per_chain_sweep = 107.2
+        issue_rate = C * k * instr_per_chain_sweep / (ms_step * 1e-3)
         issue_peak = 148 * 4 * sm_mhz * 1e6
         line = {
             "metric": "gibbs_chain_sweeps_per_s", "value": value, "unit": "chain-sweeps/s", "n_gpus": world,
@@ -899,18 +923,20 @@ def run_ours(args):
             "config": {"workload": f"BinaryRBM N=64 nh=64 block Gibbs, k={k} sweeps/step, {C} chains per GPU",
                        "chains_per_gpu": C, "k": k, "l2": "inputs larger than L2 (512 MiB chain state per GPU per step)",
                        "visible_site_updates_per_s": value * N_VIS, "rng": "in-kernel Philox4x32-10"},
-            "roofline": {"bound": "tensor", "achieved": imma_tops, "peak": imma_peak_tops, "unit": "TOP/s",
-                         "frac": imma_tops / imma_peak_tops, "traffic": traffic, "kernel": "gibbs_imma_kernel<4,4,false>",
-                         "peak_source": "int8 mma.sync.m16n8k32 (IMMA) rate measured with tools/imma_rate.cu on this pool's B200; "
-                                        "MEASURED_PEAKS.json holds no integer figure",
-                         "int8_ops_per_chain_sweep": IMMA_OPS_PER_SWEEP,
-                         "note": "achieved = the int8 tensor-core work the kernel EXECUTES (3 digit passes x 4*N*nh per chain-sweep) over "
-                                 "the measured launch time. The tensor pipe is not what limits it: the issue slots are "
-                                 "(Philox + Bernoulli epilogue), see issue_slots; fp64_equivalent restates the rate in the unit of "
-                                 "SURVEY 8(d) and is NOT a hardware fraction.",
+            "roofline": {"bound": "tensor", "achieved": umma_tops, "peak": umma_peak_tops, "unit": "TOP/s",
+                         "frac": umma_tops / umma_peak_tops, "traffic": traffic, "kernel": "gibbs_umma_kernel (tcgen05.mma.kind::i8, TMEM accumulators)",
+                         "peak_source": umma_src, "int8_ops_per_chain_sweep": UMMA_OPS_PER_SWEEP,
+                         "note": "achieved = the int8 tensor-core work the kernel EXECUTES (two 128x128x128 tile products per 128 chains and "
+                                 "sweep) over the measured launch time. The tensor pipe is not what limits it: the issue slots are "
+                                 "(Philox + Bernoulli epilogue, 69.6 % issue-active in ncu), see issue_slots; fp64_equivalent restates the "
+                                 "rate in the unit of SURVEY 8(d) and is NOT a hardware fraction.",
                          "issue_slots": {"achieved_ginstr_per_s": issue_rate / 1e9, "peak_ginstr_per_s": issue_peak / 1e9,
-                                         "frac": issue_rate / issue_peak, "instr_per_warp_half_sweep": instr_per_half_sweep,
-                                         "ncu_issue_active": 0.635, "ncu_source": "profiles/gibbs_imma_r01_ncu.txt"},
+                                         "frac": issue_rate / issue_peak, "warp_instr_per_chain_sweep": instr_per_chain_sweep,
+                                         "ncu_issue_active": 0.696, "ncu_source": "profiles/gibbs_umma_r02_ncu.txt"},
+                         "mma_sync_path": {"kernel": "gibbs_imma_kernel<4,4,false> (mma.sync.m16n8k32, round 1's default)",
+                                           "value": world * C * k / (imma_ms_step * 1e-3), "ms_per_step": imma_ms_step,
+                                           "achieved": imma_tops, "peak": imma_peak_tops, "unit": "TOP/s", "frac": imma_tops / imma_peak_tops,
+                                           "how": "qcb_set_gibbs_mode(3); same samples bit for bit"},
                          "fp64_equivalent": {"tflops": fp64_equiv, "dmma_peak_tflops": peak_tflops, "ratio": fp64_equiv / peak_tflops,
                                              "flop_per_chain_sweep": FLOP_PER_SWEEP, "peak_source": peak_src},
                          "fp64_path": {"kernel": "gibbs_kernel<4,4>", "value": world * C * k / (fp64_ms_step * 1e-3),

@@ -56,6 +56,7 @@ struct GibbsUmmaArgs {
   uint32_t key0, key1;
   uint64_t chain_id0;
   uint32_t sweep0;
+  uint32_t rk[20];        // Philox round keys (key0 + r W0, key1 + r W1): launch constants, read straight from the constant bank
 };
 
 __host__ __device__ inline int gu_unit_of_p(int p) { return (p & 32) | (((p >> 2) & 1) << 4) | (((p >> 3) & 3) << 2) | (p & 3); }
@@ -151,6 +152,20 @@ __global__ void __launch_bounds__(256) gibbs_pack_umma_kernel(StackedParams p, u
     }
     img[(hside ? GU_BH_OFF : GU_BV_OFF) + gu_operand_offset(n, k)] = (unsigned char)(val & 255);
   }
+}
+
+// Philox4x32-10 with the key schedule precomputed on the host (same function as philox4x32_10 of common.cuh)
+__device__ __forceinline__ void gu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20], uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk[2 * r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
 // ---- tcgen05 helpers ----------------------------------------------------------------------------------------------
@@ -326,6 +341,13 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
       }
       __syncthreads();
       cur = words[hh * GU_TILE + row];
+      // pull this CTA's NEXT tile (one contiguous span of v_in) into L2 while this one is swept
+      const int64_t nbase = (ti + gridDim.x) * GU_TILE;
+      if (nbase < a.C) {
+        const int64_t nbytes = (a.C - nbase < GU_TILE ? a.C - nbase : (int64_t)GU_TILE) * N * (int64_t)sizeof(double);
+        const char* np = reinterpret_cast<const char*>(a.v_in + nbase * N);
+        for (int64_t off = (int64_t)tid * 128; off < nbytes; off += (int64_t)GU_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
+      }
     } else if (a.in_mode == 1) {
       if (ch < a.C) {
         const uint8_t* rowp = a.bits_in + ch * rowbytes;
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
         gu_ld8(taddr + 8u * (uint32_t)c, a01);
         gu_ld8(taddr + 64u + 8u * (uint32_t)c, a2);
         uint32_t rnd[4];
-        philox4x32_10(cid0, cid1, sweep, q0 + (uint32_t)c, a.key0, a.key1, rnd);  // stream 0; overlaps the TMEM loads
+        gu_philox(cid0, cid1, sweep, q0 + (uint32_t)c, a.rk, rnd);  // stream 0; overlaps the TMEM loads
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const float4 b_lo = *reinterpret_cast<const float4*>(bias + 8 * c);
         const float4 b_hi = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
@@ -485,6 +507,10 @@ int try_gibbs_umma(const StackedParams& p, const ChainIO& io, int64_t C, int k, 
   a.key1 = (uint32_t)(seed >> 32);
   a.chain_id0 = chain_id0;
   a.sweep0 = (uint32_t)sweep0;
+  for (int r = 0; r < 10; ++r) {
+    a.rk[2 * r] = a.key0 + (uint32_t)r * 0x9E3779B9u;
+    a.rk[2 * r + 1] = a.key1 + (uint32_t)r * 0xBB67AE85u;
+  }
   const size_t smem = umma_smem_bytes();
   static int blocks_on[QCB_MAX_DEVICES] = {0};
   int& blocks_per_sm = blocks_on[device_slot()];
