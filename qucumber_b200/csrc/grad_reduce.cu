@@ -20,6 +20,8 @@ namespace qcb {
 constexpr int GR = 32;  // rows per tile
 constexpr int GR_MAX_CTAS_PER_SM = 4;  // partial-sum slots per SM in the workspace (tensor-core kernel: up to 4 CTAs/SM)
 
+int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
+                          int* grid_out, cudaStream_t st);
 int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
                          int* grid_out, int* flag, cudaStream_t st);
 
@@ -196,7 +198,11 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
   int grid = grad_reduce_grid(rows);
   double* partials = reinterpret_cast<double*>(ws);
   int grid_dmma = 0;
-  if (rows > 0) {
+  if (rows > 0) {  // small layers, large batches of explicit rows: the streaming kernel of grad_reduce_small.cu
+    const int rc = try_grad_reduce_small(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, st);
+    if (rc != QCB_OK) return rc;
+  }
+  if (rows > 0 && grid_dmma == 0) {
     // large batches of explicit / expanded rows run on the FP64 tensor cores (grad_reduce_dmma.cu)
     int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + need - 256);
     const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, flag, st);

@@ -777,3 +777,41 @@ def test_log_partition_n32_vs_hidden_side_trace(lib, cuda, nh):
     out2 = rbm.log_partition().cpu().numpy()
     got = out2[0] + np.log(out2[1])
     assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (4, 9), (16, 16), (1, 1), (13, 3), (3, 16), (16, 15)])
+def test_gradient_reduce_small_layers_large_batch(lib, cuda, n, nh):
+    """Layers of at most 16 x 16 units with >= 4096 explicit rows take the streaming kernel of grad_reduce_small.cu (the T4
+    shape of SURVEY 8(d)): 1e-10 against the oracle for binary rows, real-valued rows, ragged last tiles (rows not a
+    multiple of 512), an 8-byte-misaligned view, saturated units, and scale / accumulate through the C ABI."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    rbm, orc = _pair(n, nh, 301, cuda)
+    for rows in (4096, 5003, 70_001):
+        v = random_states(rows, n, 302 + rows)
+        assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), orc.effective_energy_gradient(v),
+                     what=f"small-layer gradient, {rows} binary rows")
+    vr = np.random.default_rng(303).standard_normal((4999, n)) * 2.0
+    assert_close(rbm.effective_energy_gradient(torch.tensor(vr, device=cuda)), orc.effective_energy_gradient(vr),
+                 what="small-layer gradient, real rows")
+    backing = torch.zeros(6001 * n + 1, dtype=torch.double, device=cuda)
+    view = backing[1:].view(6001, n)
+    v = random_states(6001, n, 304)
+    view.copy_(torch.tensor(v, device=cuda))
+    assert view.data_ptr() % 16 == 8
+    assert_close(rbm.effective_energy_gradient(view), orc.effective_energy_gradient(v), what="small-layer gradient, misaligned rows")
+    # saturated hidden units (|theta| in the hundreds) and the C ABI's scale / accumulate
+    W, b, c = make_binary_params(n, nh, 305, bias_scale=0.5)
+    W *= 60.0
+    c[::2] += 300.0
+    sat = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    v = random_states(8192, n, 306)
+    want = BinaryRBMOracle(W, b, c).effective_energy_gradient(v)
+    assert_close(sat.effective_energy_gradient(torch.tensor(v, device=cuda)), want, what="small-layer gradient, saturated units")
+    args, keep = sat._param_args()
+    g = torch.full((sat.num_pars,), 2.0, dtype=torch.double, device=cuda)
+    tv = torch.tensor(v, device=cuda)
+    ws = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_GRAD_REDUCE, n, nh, 0, 8192))
+    _lib.check(lib.qcb_rbm_grad_reduce(*args, _lib.ptr(tv), 8192, -0.25, _lib.ptr(g), 1, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(cuda)),
+               "qcb_rbm_grad_reduce")
+    assert_close(g, 2.0 - 0.25 * want, what="small-layer gradient, scale and accumulate")
