@@ -5,8 +5,9 @@
 // Here a CTA streams tiles of 512 rows through shared memory (one contiguous, coalesced copy per tile):
 //   phase A  one thread = two rows: theta from the weights in shared memory (every load a warp-wide broadcast, each feeding
 //            both rows), the table logistic of common.cuh, p into shared memory;
-//   phase B  one thread = one entry of the flat gradient x one half of the tile's rows: the outer products and the two
-//            bias sums are plain dot products over the rows, accumulated in a register for the whole kernel.
+//   phase B  the outer products P^T V on the FP64 tensor cores (mma.sync m8n8k4): warp w owns rows 64 w .. 64 w + 63 of the
+//            tile and keeps its share of the (at most 2 x 2) output blocks in registers for the whole kernel; the two bias
+//            gradients are column sums taken by 8 (N + H) threads (one per column and 64-row slice).
 // Rows may hold arbitrary reals (the reference's contract).  Per-CTA partials go to the workspace in the flat order
 // [Wst (H x N) | vb (N) | hb (H)] and are summed by grad_finalize_kernel in a fixed order, like the other two kernels.
 #include "rows.cuh"
@@ -33,27 +34,21 @@ __global__ void __launch_bounds__(GS_THREADS, 2) grad_reduce_small_kernel(Affine
   for (int i = threadIdx.x; i < HT; i += GS_THREADS) hbs[i] = i < H ? s.bias(i) : 0.0;
   fill_exp2_table(e2tab);
 
-  // phase B ownership: entry e of [Wst | vb | hb] and a half of the rows
+  // phase B: G (H x N) += P^T (H x rows) . V (rows x N) as FP64 tensor-core tiles (mma.sync m8n8k4); warp w takes rows
+  // 64 w .. 64 w + 63 of every tile and keeps its share of all (HT / 8) x (NT / 8) output blocks in registers.  The bias
+  // gradients are column sums: thread c < N + H adds column c of [V | P] over the tile's rows.
+  constexpr int MB = (HT + 7) / 8, NB = (NT + 7) / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double G[MB][NB][2];
+#pragma unroll
+  for (int m = 0; m < MB; ++m)
+#pragma unroll
+    for (int n = 0; n < NB; ++n) G[m][n][0] = G[m][n][1] = 0.0;
+  double colsum = 0.0;
+  const int cs_col = threadIdx.x % (N + H), cs_slice = threadIdx.x / (N + H);  // column of [V | P] and 64-row slice of the tile
+  const int cs_ld = cs_col < N ? N : H;
   const int E = H * N + N + H;
-  const int slices = GS_THREADS / E >= 2 ? 2 : 1;   // E <= 288; two row halves when the entries fit twice
-  const int e = threadIdx.x % E, slice = threadIdx.x / E;
-  const bool owner = slice < slices && (slices == 2 || threadIdx.x < E);
-  // the two operands of this entry: a column of Pt (or the constant 1) and a column of Vt (or the constant 1)
-  int pi = -1, vj = -1;
-  if (e < H * N) { pi = e / N; vj = e - pi * N; }
-  else if (e < H * N + N) vj = e - H * N;
-  else pi = e - H * N - N;
-  double acc = 0.0;
-  // entries that do not fit one pass over the threads (E > 256) take a second one
-  const int e2 = threadIdx.x + GS_THREADS;
-  int pi2 = -1, vj2 = -1;
-  const bool owner2 = slices == 1 && e2 < E;
-  if (owner2) {
-    if (e2 < H * N) { pi2 = e2 / N; vj2 = e2 - pi2 * N; }
-    else if (e2 < H * N + N) vj2 = e2 - H * N;
-    else pi2 = e2 - H * N - N;
-  }
-  double acc2 = 0.0;
   __syncthreads();
 
   const bool vec_ok = (reinterpret_cast<uintptr_t>(v) & 15) == 0 && ((GS_TILE * N) & 1) == 0;
@@ -87,69 +82,88 @@ __global__ void __launch_bounds__(GS_THREADS, 2) grad_reduce_small_kernel(Affine
       double* pa = Pt + (size_t)threadIdx.x * H;
       double* pb = Pt + (size_t)(threadIdx.x + GS_THREADS) * H;
       const bool live_a = threadIdx.x < nrows, live_b = threadIdx.x + GS_THREADS < nrows;
+      // two hidden units x two rows at a time: four independent FMA chains and four independent logistic evaluations keep
+      // the FP64 pipe fed with 16 warps per SM (one chain per thread left 2.5 warps per issue waiting on a dependency)
 #pragma unroll
-      for (int i = 0; i < HT; ++i) {
+      for (int i = 0; i < HT; i += 2) {
         if (i < H) {
-          double ta = hbs[i], tb = ta;
+          double ta0 = hbs[i], tb0 = ta0, ta1 = hbs[i + 1], tb1 = ta1;   // hbs and Ws are zero-padded to HT
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
-            const double w = Ws[i * NT + j];
-            ta = fma(w, va[j], ta);
-            tb = fma(w, vb2[j], tb);
+            const double w0 = Ws[i * NT + j], w1 = Ws[(i + 1) * NT + j];
+            ta0 = fma(w0, va[j], ta0);
+            tb0 = fma(w0, vb2[j], tb0);
+            ta1 = fma(w1, va[j], ta1);
+            tb1 = fma(w1, vb2[j], tb1);
           }
-          pa[i] = live_a ? sigmoid_tab(ta, e2tab) : 0.0;   // rows beyond the batch contribute nothing
-          pb[i] = live_b ? sigmoid_tab(tb, e2tab) : 0.0;
+          const double sa0 = sigmoid_tab(ta0, e2tab), sb0 = sigmoid_tab(tb0, e2tab);
+          const double sa1 = sigmoid_tab(ta1, e2tab), sb1 = sigmoid_tab(tb1, e2tab);
+          pa[i] = live_a ? sa0 : 0.0;   // rows beyond the batch contribute nothing
+          pb[i] = live_b ? sb0 : 0.0;
+          if (i + 1 < H) {
+            pa[i + 1] = live_a ? sa1 : 0.0;
+            pb[i + 1] = live_b ? sb1 : 0.0;
+          }
         }
       }
     }
     __syncthreads();
 
-    // ---- phase B: this thread's entry over its rows
-    if (owner) {
-      const int rbeg = slices == 2 ? slice * (GS_TILE / 2) : 0, rend = slices == 2 ? rbeg + GS_TILE / 2 : GS_TILE;
-      const int rlim = rend < nrows ? rend : nrows;
-      const double* pp = pi >= 0 ? Pt + pi : nullptr;
-      const double* vp = vj >= 0 ? Vt + vj : nullptr;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int r = rbeg;
-      if (pp != nullptr && vp != nullptr) {
-        for (; r + 4 <= rlim; r += 4) {
-          a0 = fma(pp[(size_t)r * H], vp[(size_t)r * N], a0);
-          a1 = fma(pp[(size_t)(r + 1) * H], vp[(size_t)(r + 1) * N], a1);
-          a2 = fma(pp[(size_t)(r + 2) * H], vp[(size_t)(r + 2) * N], a2);
-          a3 = fma(pp[(size_t)(r + 3) * H], vp[(size_t)(r + 3) * N], a3);
-        }
-        for (; r < rlim; ++r) a0 = fma(pp[(size_t)r * H], vp[(size_t)r * N], a0);
-      } else if (vp != nullptr) {
-        for (; r + 4 <= rlim; r += 4) {
-          a0 += vp[(size_t)r * N]; a1 += vp[(size_t)(r + 1) * N]; a2 += vp[(size_t)(r + 2) * N]; a3 += vp[(size_t)(r + 3) * N];
-        }
-        for (; r < rlim; ++r) a0 += vp[(size_t)r * N];
-      } else {
-        for (; r + 4 <= rlim; r += 4) {
-          a0 += pp[(size_t)r * H]; a1 += pp[(size_t)(r + 1) * H]; a2 += pp[(size_t)(r + 2) * H]; a3 += pp[(size_t)(r + 3) * H];
-        }
-        for (; r < rlim; ++r) a0 += pp[(size_t)r * H];
+    // ---- phase B: tensor-core outer products over this warp's 64 rows, column sums for the biases
+    {
+      const int rw = 64 * warp;
+#pragma unroll 4
+      for (int kk = 0; kk < 16; ++kk) {
+        const int r = rw + 4 * kk + t;
+        double afr[MB], bfr[NB];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) afr[m] = 8 * m + g < H ? Pt[(size_t)r * H + 8 * m + g] : 0.0;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) bfr[n] = 8 * n + g < N ? Vt[(size_t)r * N + 8 * n + g] : 0.0;
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+#pragma unroll
+          for (int n = 0; n < NB; ++n) dmma884(G[m][n][0], G[m][n][1], afr[m], bfr[n]);
       }
-      acc += (a0 + a1) + (a2 + a3);
-    }
-    if (owner2) {
-      const double* pp = pi2 >= 0 ? Pt + pi2 : nullptr;
-      const double* vp = vj2 >= 0 ? Vt + vj2 : nullptr;
-      double a0 = 0.0;
-      for (int r = 0; r < nrows; ++r) a0 = fma(pp != nullptr ? pp[(size_t)r * H] : 1.0, vp != nullptr ? vp[(size_t)r * N] : 1.0, a0);
-      acc2 += a0;
+      if (cs_slice < 8) {  // rows beyond the batch are zero in both tiles
+        const double* col = (cs_col < N ? Vt + cs_col : Pt + (cs_col - N)) + (size_t)(64 * cs_slice) * cs_ld;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < 64; r += 4) {
+          a0 += col[(size_t)r * cs_ld]; a1 += col[(size_t)(r + 1) * cs_ld]; a2 += col[(size_t)(r + 2) * cs_ld]; a3 += col[(size_t)(r + 3) * cs_ld];
+        }
+        colsum += (a0 + a1) + (a2 + a3);
+      }
     }
     __syncthreads();
   }
 
-  // ---- this CTA's partial: the two row halves are added in a fixed order through shared memory
+  // ---- this CTA's partial: the eight warps' shares of G are added in a fixed order through shared memory
   double* out = partials + (size_t)blockIdx.x * E;
-  double* red = Vt;
-  if (owner && slices == 2 && slice == 1) red[e] = acc;
+  double* red = Vt;  // [8 warps][8 MB][8 NB]: the register blocks are whole 8 x 8 tiles (HT, NT are multiples of 4 only)
+#pragma unroll
+  for (int m = 0; m < MB; ++m)
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) red[((size_t)warp * (8 * MB) + 8 * m + g) * (8 * NB) + 8 * n + 2 * t + e2] = G[m][n][e2];
   __syncthreads();
-  if (owner && slice == 0) out[e] = slices == 2 ? acc + red[e] : acc;
-  if (owner2) out[e2] = acc2;
+  for (int idx = threadIdx.x; idx < H * N; idx += GS_THREADS) {
+    const int i = idx / N, j = idx - i * N;
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < GS_THREADS / 32; ++w) sum += red[((size_t)w * (8 * MB) + i) * (8 * NB) + j];
+    out[idx] = sum;
+  }
+  __syncthreads();
+  if (cs_slice < 8) red[cs_slice * (N + H) + cs_col] = colsum;
+  __syncthreads();
+  if (threadIdx.x < N + H) {  // [vb (N) | hb (H)] follow the weights
+    double sum = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) sum += red[sl * (N + H) + threadIdx.x];
+    out[H * N + threadIdx.x] = sum;
+  }
 }
 
 static size_t gs_smem(int N, int H) { return (size_t)GS_TILE * (N + H) * sizeof(double); }
