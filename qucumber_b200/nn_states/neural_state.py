@@ -428,21 +428,24 @@ class NeuralStateBase(abc.ABC):
     def _shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples, generator=None):
         """The epoch's positive rows, negative rows (batches back to back) and the permutation used. ``generator``: the
         host generator to draw from (None: torch's default; under torch.distributed one seeded identically on all ranks)."""
-        pos_perm = torch.randperm(train_samples.shape[0], generator=generator)
+        where = generator.device if generator is not None else torch.device("cpu")  # a device generator shuffles on the device
+        pos_perm = torch.randperm(train_samples.shape[0], generator=generator, device=where)
         pos = train_samples[pos_perm]
         if input_bases is None:
             if neg_batch_size == pos_batch_size:
                 neg_perm = pos_perm
             else:
                 neg_perm = torch.randint(train_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long,
-                                         generator=generator)
+                                         generator=generator, device=where)
             neg = train_samples[neg_perm]
         else:
-            neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long, generator=generator)
+            neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long, generator=generator,
+                                     device=where)
             neg = z_samples[neg_perm]
         return pos, neg, pos_perm
 
     _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
+    device_shuffle_min_rows = 1 << 16  # from this many samples on, fit() shuffles on the device
 
     #: set to False to force one C call per batch even where a whole epoch fits one launch
     fuse_epochs = True
@@ -521,7 +524,12 @@ class NeuralStateBase(abc.ABC):
         # one Philox key per fit() call; under torch.distributed rank 0's key is broadcast and also seeds the host generator of
         # the shuffles, so that every rank walks through the same batches whatever its own seeding was
         self._cd_seed, self._cd_sweep = qd.broadcast_seed(next_seed(), self.device), 0
-        self._shuffle_generator = torch.Generator().manual_seed(self._cd_seed) if qd.world()[1] > 1 else None
+        # large data sets without bases are shuffled on the device (a host randperm of 8 M rows takes longer than the epoch's
+        # kernels); the generator is seeded from the fit key, so torch.manual_seed still reproduces the run
+        if input_bases is None and train_samples.is_cuda and train_samples.shape[0] >= self.device_shuffle_min_rows:
+            self._shuffle_generator = torch.Generator(device=train_samples.device).manual_seed(self._cd_seed)
+        else:
+            self._shuffle_generator = torch.Generator().manual_seed(self._cd_seed) if qd.world()[1] > 1 else None
         cbs.fire("on_train_start", self)
         num_batches = ceil(train_samples.shape[0] / pos_batch_size)
         epoch_iter = range(starting_epoch, epochs + 1)
