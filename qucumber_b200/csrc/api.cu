@@ -30,6 +30,7 @@ int fail(int code, const char* fmt, ...) {
 // implemented in the other translation units
 size_t gibbs_workspace_bytes(int N, int nhid);
 extern int g_gibbs_mode;
+extern int g_grad_mode;
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
 int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
@@ -166,6 +167,13 @@ int qcb_set_gibbs_mode(int mode) {
     return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits) "
                                  "or 3 (mma.sync integer filter, never tcgen05)");
   g_gibbs_mode = mode;
+  return QCB_OK;
+}
+
+int qcb_set_grad_reduce_mode(int mode) {
+  if (mode != 0 && mode != 1 && mode != 3)
+    return fail(QCB_ERR_BAD_ARG, "grad_reduce mode must be 0 (automatic), 1 (FP64 tensor cores only) or 3 (integer theta + FP64 outer products, never tcgen05)");
+  g_grad_mode = mode;
   return QCB_OK;
 }
 

@@ -23,7 +23,8 @@ constexpr int GR_MAX_CTAS_PER_SM = 4;  // partial-sum slots per SM in the worksp
 int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
                           int* grid_out, cudaStream_t st);
 int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
-                         int* grid_out, int* flag, cudaStream_t st);
+                         int* grid_out, int* flag, unsigned char* umma_img, cudaStream_t st);
+size_t grad_umma_workspace_bytes();
 
 template <int TPT, int SRC>  // TPT = 4x4 tiles per thread
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s, RowSrc src, int64_t rows,
@@ -181,7 +182,8 @@ static int grad_reduce_grid(int64_t rows) {
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows) {
   (void)rows;
   const size_t G = (size_t)nhid * N + N + nhid;
-  return align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256) + 256;  // partials + one flag word
+  // partials + the weight image of the tcgen05 kernel + one flag word
+  return align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256) + grad_umma_workspace_bytes() + 256;
 }
 
 template <int SRC>
@@ -205,7 +207,8 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
   if (rows > 0 && grid_dmma == 0) {
     // large batches of explicit / expanded rows run on the FP64 tensor cores (grad_reduce_dmma.cu)
     int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + need - 256);
-    const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, flag, st);
+    unsigned char* umma_img = reinterpret_cast<unsigned char*>(ws) + need - 256 - grad_umma_workspace_bytes();
+    const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, flag, umma_img, st);
     if (rc != QCB_OK) return rc;
   }
   if (grid_dmma > 0) {

@@ -486,9 +486,13 @@ static int gd_residency(int* out) {
 
 // persistent grid = exactly the resident CTAs.  With a flag the integer-phase-1 kernel goes first and the FP64 kernel
 // behind it only works when the first one gave up (non-binary rows, weights outside the image); both use one grid.
+int try_grad_reduce_umma(const AffineSpec& s, const double* v, int H, int64_t rows, double* partials, int nslots, int* flag,
+                         unsigned char* img, int* launched, cudaStream_t st);
+int g_grad_mode = 0;  // qcb_set_grad_reduce_mode: 0 automatic, 1 FP64 tensor cores only, 3 never the tcgen05 kernel
+
 template <int NB8, int HB8, bool WITH_IMMA>
 static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int* grid_io, int* flag,
-                     cudaStream_t st) {
+                     unsigned char* umma_img, cudaStream_t st) {
   int per_sm = 0;
   if (int rc = gd_residency<NB8, HB8, false>(&per_sm)) return rc;
   if (WITH_IMMA && flag != nullptr) {
@@ -501,8 +505,17 @@ static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t r
   const int grid = *grid_io;
   if (WITH_IMMA && flag != nullptr) {
     QCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-    grad_reduce_dmma_kernel<NB8, HB8, WITH_IMMA><<<grid, GD_THREADS, gd_smem(NB8, HB8, true), st>>>(s, src, mode, rows, partials, flag);
-    QCB_LAUNCH_CHECK();
+    // binary rows: both contractions on tcgen05 / TMEM (grad_reduce_umma.cu) where the shape fits, else integer theta + DMMA
+    int on_umma = 0;
+    if (mode == ROWS_EXPLICIT && g_grad_mode != 3) {
+      if (int rc = try_grad_reduce_umma(s, src.v, s.n_out, rows, partials, grid, flag, umma_img, &on_umma, st)) return rc;
+    }
+    if (!on_umma && g_grad_mode != 1) {
+      grad_reduce_dmma_kernel<NB8, HB8, WITH_IMMA><<<grid, GD_THREADS, gd_smem(NB8, HB8, true), st>>>(s, src, mode, rows, partials, flag);
+      QCB_LAUNCH_CHECK();
+    } else if (!on_umma) {
+      flag = nullptr;  // FP64 only
+    }
   } else {
     flag = nullptr;
   }
@@ -515,7 +528,7 @@ static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t r
 // "not applicable, use the FMA kernel".  H = computed + aux hidden-like units.
 // flag: one int of device scratch (or NULL): enables the integer phase 1 for 25..64 x 25..64 layers and >= 16384 rows.
 int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
-                         int* grid_out, int* flag, cudaStream_t st) {
+                         int* grid_out, int* flag, unsigned char* umma_img, cudaStream_t st) {
   *grid_out = 0;
   if (mode == ROWS_ENUM || rows < 2048) return QCB_OK;
   const int NB8 = pick8(s.n_in1), HB8 = pick8(H);
@@ -525,7 +538,7 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
   if (rows < 16384 || H != s.n_out) flag = nullptr;  // small batches: not worth a second launch; aux features: FP64 only
   int rc = QCB_OK;
 #define QCB_GD_CASE(NB, HBx) \
-  if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx, (NB >= 4 && NB <= 8 && HBx >= 4 && HBx <= 8 && GD_WARPS == 8)>(s, src, mode, rows, partials, &grid, flag, st); else
+  if (NB8 == NB && HB8 == HBx) rc = launch_gd<NB, HBx, (NB >= 4 && NB <= 8 && HBx >= 4 && HBx <= 8 && GD_WARPS == 8)>(s, src, mode, rows, partials, &grid, flag, umma_img, st); else
   QCB_GD_CASE(2, 2) QCB_GD_CASE(2, 3) QCB_GD_CASE(2, 4) QCB_GD_CASE(2, 8) QCB_GD_CASE(2, 16)
   QCB_GD_CASE(3, 2) QCB_GD_CASE(3, 3) QCB_GD_CASE(3, 4) QCB_GD_CASE(3, 8) QCB_GD_CASE(3, 16)
   QCB_GD_CASE(4, 2) QCB_GD_CASE(4, 3) QCB_GD_CASE(4, 4) QCB_GD_CASE(4, 8) QCB_GD_CASE(4, 16)
