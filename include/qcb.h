@@ -152,7 +152,7 @@ int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const
                         int N, int nh, int na, const double* v, int64_t rows, double scale,
                         double* g, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
-/* Kernel selection for large batches (>= 16384 rows) of 0/1 rows on 17..64-unit layers.  mode 0 (default): automatic —
+/* Kernel selection for large batches (>= 16384 rows) of 0/1 rows on 33..64-unit layers.  mode 0 (default): automatic —
  * both contractions on tcgen05.mma.kind::i8 with TMEM accumulators (csrc/grad_reduce_umma.cu: theta from two 23-bit
  * fixed-point groups of W, p digitised to 48 bits for the outer products), falling back on the device to the kernels
  * below when a row is not binary or the weights do not fit; mode 3: never tcgen05 (integer theta on mma.sync + FP64

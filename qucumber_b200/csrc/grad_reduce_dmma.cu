@@ -507,7 +507,7 @@ static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t r
     QCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     // binary rows: both contractions on tcgen05 / TMEM (grad_reduce_umma.cu) where the shape fits, else integer theta + DMMA
     int on_umma = 0;
-    if (mode == ROWS_EXPLICIT && g_grad_mode != 3) {
+    if (mode == ROWS_EXPLICIT && g_grad_mode == 0) {
       if (int rc = try_grad_reduce_umma(s, src.v, s.n_out, rows, partials, grid, flag, umma_img, &on_umma, st)) return rc;
     }
     if (!on_umma && g_grad_mode != 1) {

@@ -1,17 +1,17 @@
 // Reduced energy gradient of large batches of BINARY rows with BOTH contractions on the 5th-generation tensor cores
-// (tcgen05.mma.kind::i8, accumulators in tensor memory), for layers of 17..64 units on both sides:
+// (tcgen05.mma.kind::i8, accumulators in tensor memory), for layers of 33..64 units on both sides:
 //   g_partial = sum_rows [ p_r (x) v_r ; v_r ; p_r ],  p_r = sigmoid(W v_r + c)               (rbm/binary_rbm.py:113-120)
 // The FP64 tensor-core kernel (grad_reduce_dmma.cu) spends 0.75 ms on 2^20 rows at N = nh = 64 against a DMMA floor of
 // 0.23 ms.  For 0/1 rows neither contraction needs FP64 products:
 //   phase 1  theta = c + W v  exactly as in gibbs_umma.cu, but with TWO 23-bit fixed-point groups of W (46 bits: the
 //            quantisation error of theta stays below 2e-12 max|W|), each group as [d0 ; 2 d1 | d2 ; 0] against the chains'
 //            byte rows [v ; 128 v]: 8 x tcgen05.mma per tile of 128 rows, four 64-column accumulators in TMEM;
-//   FP64     p = sigmoid(theta) (table logistic of common.cuh) — the only FP64 work left — and P = rint(p 2^48);
+//   FP64     p = sigmoid(theta) (table logistic of common.cuh) — the only FP64 work left — and P = rint(p (2^48 - 1));
 //   phase 2  G = P^T V with P split into six unsigned bytes: the byte tiles are written M-major by the thread that owns the
 //            row (M = 2 digits x 64 hidden units, K = 128 rows), V is the SAME shared-memory tile that served as A operand
 //            of phase 1, now read N-major (N = 64 visible columns + one all-ones column for the hidden-bias sums); three
 //            int32 accumulators (one per digit pair) stay in TMEM for the whole kernel and are read out once:
-//            G_ij = sum_d 2^(8 d - 48) G_d,ij.  Every partial sum is an exact integer, so the result is the exact sum of
+//            G_ij = sum_d 2^(8 d) G_d,ij / (2^48 - 1).  Every partial sum is an exact integer, so the result is the exact sum of
 //            the rounded p: absolute error <= rows 2^-49, i.e. far below 1e-10 of any entry that is not itself negligible.
 // The visible-bias gradient is a column count of bits.  A row that is not 0/1, or weights the two groups cannot hold
 // (non-finite, max|W| > 8 or < 1e-290), raise *flag and the FP64 kernel queued behind redoes the batch (same protocol as the
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) grad_pack_umma_kernel(AffineSpec s, unsig
     hd->pad = 0;
   }
   double* hb = reinterpret_cast<double*>(img + GM_IMG_HB);
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) hb[i] = i < H ? s.bias(i) : 0.0;
+  // padded hidden units get a bias far below the logistic function's clamp: p = e^-700, which rounds to zero digits
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) hb[i] = i < H ? s.bias(i) : -1.0e4;
   // B operands: group g (0 = high 23 bits, 1 = the next 23), row n, column k:
   //   n < 64: hidden unit n, k < 64: digit 0 of visible k, k >= 64: twice digit 1 of visible k - 64;  n >= 64: digit 2 / zero
   for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
@@ -134,9 +135,11 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
   unsigned char* sD = sA + GM_A_BYTES;                             // three digit-pair tiles
   uint32_t* words = reinterpret_cast<uint32_t*>(sD + 3 * GM_DIG_BYTES);  // [2 halves][128 rows]
   double* e2tab = reinterpret_cast<double*>(words + 2 * GM_TILE);  // [EXP2_TABLE]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(e2tab + EXP2_TABLE);  // [0]: image, [1]: theta MMAs, [2]: outer-product MMAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(e2tab + EXP2_TABLE);  // [0]: image, [1]: theta MMAs, [2]: outer-product MMAs, [3]: row tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
   int* colcnt = reinterpret_cast<int*>(tmem_slot + 2);             // [64] column counts of the state bits (visible-bias gradient)
+  // [128][N]: the NEXT tile's rows, fetched by TMA while this one is processed (bulk copies need a 16-byte aligned destination)
+  double* stage = reinterpret_cast<double*>(smem + align_up((size_t)(reinterpret_cast<unsigned char*>(colcnt + 64) - smem), 128));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hh = warp >> 2;
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
     mbar_init(mbar, 1);
     mbar_init(mbar + 1, 1);
     mbar_init(mbar + 2, 1);
+    mbar_init(mbar + 3, 1);
   }
   if (tid < 64) colcnt[tid] = 0;
   fill_exp2_table(e2tab);
@@ -184,18 +188,43 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
   int cnt0 = 0, cnt1 = 0;  // this lane's column counts (columns lane and lane + 32) over the rows its warp loads
 
   const int64_t ntiles = (rows + GM_TILE - 1) / GM_TILE;
+  uint32_t ph3 = 0u;
+  const bool base_aligned = (reinterpret_cast<uintptr_t>(v) & 15u) == 0u;
+  auto tile_bytes = [&](int64_t t) -> uint32_t {
+    const int64_t left = rows - t * GM_TILE;
+    return (uint32_t)((left < GM_TILE ? left : (int64_t)GM_TILE) * N * (int64_t)sizeof(double));
+  };
+  auto tile_staged = [&](int64_t t) { return base_aligned && ((tile_bytes(t) & 15u) == 0u) && (((int64_t)GM_TILE * N) & 1) == 0; };
+  auto stage_fetch = [&](int64_t t) {  // one thread: bulk copies of at most 16 KB each, all completing on mbar[3]
+    if (t >= ntiles || !tile_staged(t)) return;
+    const uint32_t bytes = tile_bytes(t);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the staging rows vs. the async writes
+    mbar_expect_tx(mbar + 3, bytes);
+    const char* src = reinterpret_cast<const char*>(v) + t * (int64_t)GM_TILE * N * (int64_t)sizeof(double);
+    for (uint32_t off = 0; off < bytes; off += 16384u)
+      tma_bulk_g2s(reinterpret_cast<char*>(stage) + off, src + off, bytes - off < 16384u ? bytes - off : 16384u, mbar + 3);
+  };
+  if (tid == 0 && weights_ok) stage_fetch(blockIdx.x);
   bool give_up = !weights_ok;
+  int why = 2;  // what ends up in *flag when this CTA gives up: 2 = weights outside the two groups, 3 = a row that is not 0/1
   for (int64_t tile = blockIdx.x; tile < ntiles && !give_up; tile += gridDim.x) {
     const int64_t r0 = tile * GM_TILE;
-    // ---- rows -> bits: warp w fetches rows 16 w .. 16 w + 15, 256 contiguous bytes per load
+    // ---- rows -> bits.  A tile's rows are one contiguous span: it was handed to the TMA engine a whole tile ago (16-byte
+    // aligned spans; anything else is read directly).  Warp w turns rows 16 w .. 16 w + 15 into two ballot words each.
     bool nonbinary = false;
+    const bool staged = tile_staged(tile);
+    if (staged) {
+      mbar_wait(mbar + 3, ph3);
+      ph3 ^= 1u;
+    }
 #pragma unroll 8
     for (int rr = 0; rr < 16; ++rr) {
       const int r = 16 * warp + rr;
       const int64_t gr = r0 + r;
       unsigned long long d0 = 0ull, d1 = 0ull;
       if (gr < rows) {
-        const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(v) + gr * N;
+        const unsigned long long* rp = staged ? reinterpret_cast<const unsigned long long*>(stage) + r * N
+                                              : reinterpret_cast<const unsigned long long*>(v) + gr * N;
         if (lane < N) d0 = rp[lane];
         if (lane + 32 < N) d1 = rp[lane + 32];
       }
@@ -211,8 +240,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
     if (tid == 0) nonbinary |= *reinterpret_cast<volatile int*>(flag) != 0;  // another CTA gave up already
     if (__syncthreads_or(nonbinary)) {
       give_up = true;
+      why = 3;
       break;
     }
+    if (tid == 0) stage_fetch(tile + gridDim.x);  // the staging rows have been consumed (barrier above): fetch the next tile
     if (g_started) {  // the previous tile's outer-product MMAs still read the state bytes and the digit tiles
       mbar_wait(mbar + 2, ph2);
       ph2 ^= 1u;
@@ -250,7 +281,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
     asm volatile("tcgen05.fence::after_thread_sync;\n");
 
     // ---- theta -> p -> six bytes of rint(p 2^48), written M-major into the digit tiles
-    const bool live = r0 + row < rows;
+    // P = rint(p (2^48 - 1)) fits six bytes for every p in [0, 1] (no clamp); rows beyond the batch get a zero scale
+    const double pscale = r0 + row < rows ? 281474976710655.0 : 0.0;
     const uint32_t tcol = tmem + lane_base + 32u * (uint32_t)hh;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -266,24 +298,24 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
         const int unit = 32 * hh + 8 * c + i;
         const double thi = gm_i2d(h2[i] * 32768 + h01[i]), tlo = gm_i2d(l2[i] * 32768 + l01[i]);
         const double theta = fma(fma(tlo, 2.384185791015625e-07, thi), inv_scale, hb[unit]);  // 2^-22
-        const double p = sigmoid_tab(theta, e2tab);
-        unsigned long long q = __double2ull_rn(p * 281474976710656.0);  // 2^48
-        q = q > 281474976710655ull ? 281474976710655ull : q;             // p = 1: six bytes of ones
-        P[i] = (live && unit < H) ? q : 0ull;
+        P[i] = __double2ull_rn(sigmoid_tab(theta, e2tab) * pscale);
       }
       // byte d of the eight values -> eight consecutive bytes of digit d's M-major tile
       const int u0 = 32 * hh + 8 * c;  // first unit of the chunk: m = (d & 1) * 64 + u0 + i
 #pragma unroll
       for (int d = 0; d < 6; ++d) {
-        uint32_t w0 = 0u, w1 = 0u;
+        // byte d of P[0..3] and of P[4..7] -> two words: three byte permutes each (bytes 0..3 live in the low word, 4..5 in the high one)
+        uint32_t w[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          w0 |= (uint32_t)((P[i] >> (8 * d)) & 0xFFull) << (8 * i);
-          w1 |= (uint32_t)((P[4 + i] >> (8 * d)) & 0xFFull) << (8 * i);
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const uint32_t x0 = d < 4 ? (uint32_t)P[4 * q4] : (uint32_t)(P[4 * q4] >> 32), x1 = d < 4 ? (uint32_t)P[4 * q4 + 1] : (uint32_t)(P[4 * q4 + 1] >> 32);
+          const uint32_t x2 = d < 4 ? (uint32_t)P[4 * q4 + 2] : (uint32_t)(P[4 * q4 + 2] >> 32), x3 = d < 4 ? (uint32_t)P[4 * q4 + 3] : (uint32_t)(P[4 * q4 + 3] >> 32);
+          const uint32_t sel = (uint32_t)(d & 3) | ((uint32_t)(4 + (d & 3)) << 4);  // byte (d & 3) of the first, then of the second operand
+          w[q4] = __byte_perm(__byte_perm(x0, x1, sel), __byte_perm(x2, x3, sel), 0x5410u);
         }
         const int m = (d & 1) * 64 + u0;
         unsigned char* dst = sD + (d >> 1) * GM_DIG_BYTES + (m >> 4) * GM_LBO + row * 16 + (m & 15);
-        *reinterpret_cast<uint2*>(dst) = make_uint2(w0, w1);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -305,7 +337,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
   // ---- outcome
   double* out = partials + (size_t)blockIdx.x * E;
   if (give_up) {
-    if (tid == 0) *flag = 1;
+    if (tid == 0) *flag = why;
     if (g_started) mbar_wait(mbar + 2, ph2);  // no MMA may be in flight when the tensor memory is released
   } else {
     if (g_started) {
@@ -329,7 +361,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
             int gi[8];
             gm_ld8(tmem + lane_base + GM_COL_G + 80u * (uint32_t)pr + (uint32_t)c0, gi);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const double w = scalbn(1.0, 8 * (2 * pr + (m >> 6)) - 48);
+            const double w = scalbn(1.0, 8 * (2 * pr + (m >> 6))) / 281474976710655.0;  // digit weight 2^(8 d) over the scale 2^48 - 1
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fma(gm_i2d(gi[i]), w, acc[i]);
           }
@@ -359,7 +391,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
 }
 
 static size_t gm_smem_bytes() {
-  return GM_IMAGE_BYTES + GM_A_BYTES + 3 * GM_DIG_BYTES + 2 * GM_TILE * sizeof(uint32_t) + EXP2_TABLE * sizeof(double) + 3 * 8 + 8 + 64 * sizeof(int);
+  return GM_IMAGE_BYTES + GM_A_BYTES + 3 * GM_DIG_BYTES + 2 * GM_TILE * sizeof(uint32_t) + EXP2_TABLE * sizeof(double) + 4 * 8 + 8 + 64 * sizeof(int) +
+         128 + (size_t)GM_TILE * 64 * sizeof(double);
 }
 
 size_t grad_umma_workspace_bytes() { return align_up(GM_IMAGE_BYTES, 256); }
@@ -370,7 +403,8 @@ int try_grad_reduce_umma(const AffineSpec& s, const double* v, int H, int64_t ro
                          unsigned char* img, int* launched, cudaStream_t st) {
   *launched = 0;
   const int N = s.n_in1;
-  if (flag == nullptr || img == nullptr || H != s.n_out || N < 17 || N > 64 || H < 17 || H > 64 || rows < 16384) return QCB_OK;
+  // both layers 33..64 units: below that the FP64 tensor-core kernel, whose tiles shrink with the layer, is faster (measured)
+  if (flag == nullptr || img == nullptr || H != s.n_out || N < 33 || N > 64 || H < 33 || H > 64 || rows < 16384) return QCB_OK;
   const int grid = sm_count() < nslots ? sm_count() : nslots;
   if (rows / grid > (int64_t)8000000) return QCB_OK;  // int32 accumulators: 255 * rows per CTA must stay below 2^31
   const size_t smem = gm_smem_bytes();

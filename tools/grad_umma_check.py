@@ -16,7 +16,7 @@ from qucumber_b200 import BinaryRBM, _lib  # noqa: E402
 lib = _lib.load()
 dev = torch.device("cuda")
 ok = True
-for (n, nh, rows) in [(64, 64, 16384), (64, 64, 16421), (40, 33, 20000), (17, 64, 16500), (64, 17, 16500), (50, 50, 100_003)]:
+for (n, nh, rows) in [(64, 64, 16384), (64, 64, 16421), (40, 33, 20000), (33, 64, 16500), (64, 35, 16500), (50, 50, 100_003)]:
     W, b, c = make_binary_params(n, nh, 5, bias_scale=0.3)
     rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
     v = random_states(rows, n, 6)
