@@ -498,10 +498,15 @@ def extra_metrics(dev, lib_mod):
 
             ms_10, _ = timed(ten_calls)
             ms_g = ms_10 / 10.0
+            lib_mod.load().qcb_set_grad_reduce_mode(3)  # round 1's kernels (integer theta on mma.sync + DMMA outer products)
+            ms_10_r1, _ = timed(ten_calls)
+            lib_mod.load().qcb_set_grad_reduce_mode(0)
             gbs = rows * nv * 8 / (ms_g * 1e-3) / 1e9
             tf = rows * 4 * nv * nhd / (ms_g * 1e-3) / 1e12
             res[name] = {"N": nv, "nh": nhd, "rows": rows, "ms": ms_g, "hbm_gbps": gbs, "hbm_frac": gbs / hbm_peak,
-                         "fp64_tflops": tf, "fp64_frac_of_dmma_peak": tf / 37.117,
+                         "fp64_tflops": tf, "fp64_frac_of_dmma_peak": tf / 37.117, "ms_round1_kernels": ms_10_r1 / 10.0,
+                         "kernel": ("grad_reduce_umma_kernel (both contractions on tcgen05.mma.kind::i8, TMEM accumulators)" if nv > 32
+                                    else "grad_reduce_small_kernel (streaming, DMMA outer products)"),
                          # floors: HBM = N*8 B per row; FP64 pipe with both contractions in FP64 (4*N*nh flop) plus nh sigmoids
                          # (~50 DFMA each).  Binary rows of 25..64-unit layers take theta from exact int8 tensor-core sums
                          # (DESIGN.md 3.3), which halves the FP64 contraction work: the frac above counts ALGORITHMIC flop.

@@ -517,18 +517,35 @@ def test_reduced_gradient_saturated_units_large_batch(lib, cuda):
 @pytest.mark.parametrize("n,nh,case", [(64, 64, "plain"), (32, 64, "plain"), (64, 25, "plain"), (40, 33, "plain"), (64, 64, "mixed_scale"),
                                        (64, 64, "large"), (64, 64, "tiny"), (64, 64, "zero"), (48, 64, "nonbinary_tail"),
                                        (64, 64, "nonbinary"), (64, 64, "nonfinite"), (64, 64, "subnormal_scale"), (49, 64, "plain"),
-                                       (64, 64, "unaligned"), (56, 48, "unaligned_real")])
-def test_reduced_gradient_integer_theta_large_batch(lib, cuda, n, nh, case):
-    """Batches of >= 16384 binary rows on 25..64-unit layers compute theta from 3 x 23-bit fixed-point images of W on the
-    int8 tensor cores (grad_reduce_dmma.cu); non-binary rows anywhere in the batch, non-finite weights or weights outside
-    the image's range hand the whole batch to the FP64 kernel. Rows of >= 48 units with 16-byte aligned starts enter the
-    tile through TMA row copies, odd widths and misaligned views element by element. Same 1e-10 gate in every case."""
+                                       (64, 64, "unaligned"), (56, 48, "unaligned_real"), (64, 64, "saturated"), (33, 33, "plain"),
+                                       (63, 41, "plain"), (64, 64, "ragged_tail")])
+@pytest.mark.parametrize("mode", [0, 3])
+def test_reduced_gradient_integer_theta_large_batch(lib, cuda, n, nh, case, mode):
+    """Batches of >= 16384 binary rows. mode 0 (automatic): on 33..64-unit layers BOTH contractions run on tcgen05 /
+    TMEM (grad_reduce_umma.cu: theta from two 23-bit fixed-point groups, p digitised to 48 bits); mode 3: theta from 3 x 23-bit
+    fixed-point images on mma.sync + FP64 tensor-core outer products (grad_reduce_dmma.cu, also mode 0's choice for 25..32-unit
+    layers). Non-binary rows anywhere in the batch, non-finite weights or weights outside the images' range hand the whole
+    batch to the FP64 kernel on the device. Aligned row tiles arrive by TMA, odd widths and misaligned views element by
+    element. Same 1e-10 gates (max-norm and elementwise) in every case."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    _lib.check(lib.qcb_set_grad_reduce_mode(mode), "mode")
+    try:
+        _integer_theta_case(lib, cuda, n, nh, case)
+    finally:
+        _lib.check(lib.qcb_set_grad_reduce_mode(0), "mode")
+
+
+def _integer_theta_case(lib, cuda, n, nh, case):
     from qucumber_b200 import BinaryRBM
 
-    rows = 16384 + 37
+    rows = 16384 + (1 if case == "ragged_tail" else 37)
     W, b, c = make_binary_params(n, nh, 301, bias_scale=0.3)
     v = random_states(rows, n, 302)
     rng = np.random.default_rng(303)
+    if case == "saturated":   # hidden units pinned on and off: p = 1 and p ~ 1e-40 must digitise to all-ones / all-zero bytes
+        c[::3] += 90.0
+        c[1::3] -= 90.0
     if case == "mixed_scale":
         W = W * 10.0 ** rng.uniform(-9, 0.5, size=W.shape)
     elif case == "large":
