@@ -156,7 +156,9 @@ int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const
  * both contractions on tcgen05.mma.kind::i8 with TMEM accumulators (csrc/grad_reduce_umma.cu: theta from two 23-bit
  * fixed-point groups of W, p digitised to 48 bits for the outer products), falling back on the device to the kernels
  * below when a row is not binary or the weights do not fit; mode 3: never tcgen05 (integer theta on mma.sync + FP64
- * tensor-core outer products, csrc/grad_reduce_dmma.cu); mode 1: FP64 tensor cores only. */
+ * tensor-core outer products, csrc/grad_reduce_dmma.cu); mode 1: FP64 tensor cores only.  Modes 1 and 3 also make
+ * qcb_cwf_rotated reduce the expanded rows through those kernels instead of the Gray-walk subset sums of
+ * csrc/rotated_gray.cu (same results to rounding; for tests and measurements). */
 int qcb_set_grad_reduce_mode(int mode);
 
 /* g_rows (rows, G): per-row gradients, effective_energy_gradient(v, reduce=False)

@@ -31,6 +31,7 @@ int fail(int code, const char* fmt, ...) {
 size_t gibbs_workspace_bytes(int N, int nhid);
 extern int g_gibbs_mode;
 extern int g_grad_mode;
+extern int g_cwf_mode;
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
 int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
@@ -174,6 +175,7 @@ int qcb_set_grad_reduce_mode(int mode) {
   if (mode != 0 && mode != 1 && mode != 3)
     return fail(QCB_ERR_BAD_ARG, "grad_reduce mode must be 0 (automatic), 1 (FP64 tensor cores only) or 3 (integer theta + FP64 outer products, never tcgen05)");
   g_grad_mode = mode;
+  g_cwf_mode = mode != 0 ? 1 : 0;  // modes 1 and 3 also send the rotated-basis gradients through the expanded-row reduction
   return QCB_OK;
 }
 

@@ -26,16 +26,15 @@ int run_grad_reduce_expanded(const StackedParams& p, const Expansion& ex, int64_
                              const double* aux, int n_aux, int zero_tail, double scale, double* g, void* ws, size_t ws_bytes,
                              cudaStream_t st);
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
+size_t cwf_gray_workspace_bytes(int N);
+int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t Bc, const SiteInfo& si,
+                      const double* wa, const double* wp, double* g_am, double* g_ph, void* ws, size_t ws_bytes, int* handled,
+                      cudaStream_t st);
+int g_cwf_mode = 0;  // 0: automatic (Gray-walk gradient where it applies), 1: always the expanded-row reduction (test / measurement hook)
 
 constexpr int64_t ROT_MAX_ROWS = (int64_t)1 << 21;  // expanded rows processed per chunk
 constexpr int ROT_MAX_S = 21;
 constexpr int CWF_THREADS = 128;
-
-struct SiteInfo {
-  int S;
-  int8_t site[32];    // rotated site t -> visible unit
-  uint8_t ucode[32];  // rotated site t -> unitary code
-};
 
 __device__ __forceinline__ void cmul(double& ar, double& ai, double br, double bi) {
   const double r = ar * br - ai * bi;
@@ -250,7 +249,8 @@ static int make_sites(const uint8_t* basis_host, int N, int K, SiteInfo& si, Exp
 }
 
 size_t cwf_workspace_bytes(int N, int nh, int64_t B) {
-  return align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)(B > 0 ? B : 1) * 16, 256) + grad_reduce_workspace_bytes(N, nh, 0);
+  const size_t red = grad_reduce_workspace_bytes(N, nh, 0), gray = cwf_gray_workspace_bytes(N);
+  return align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)(B > 0 ? B : 1) * 16, 256) + (red > gray ? red : gray);
 }
 
 template <int NHT>
@@ -289,7 +289,7 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
   double* wp = wa + ROT_MAX_ROWS;
   double2* D = reinterpret_cast<double2*>(base + align_up((size_t)ROT_MAX_ROWS * 32, 256));
   void* gws = base + align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)B * 16, 256);
-  const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh, 0);
+  const size_t gws_bytes = ws_bytes - (size_t)(static_cast<char*>(gws) - base);
   const int S = si.S;
   const int64_t chunkB = ROT_MAX_ROWS >> S;
   for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
@@ -303,6 +303,12 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
     cwf_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(T, D, S, rows, wa, wp);
     QCB_LAUNCH_CHECK();
     ex.samples = samples + b0 * N;
+    if (g_cwf_mode == 0) {  // the rows of a sample differ only in the rotated sites: subset sums instead of outer products
+      int handled = 0;
+      rc = run_cwf_grad_gray(am, ph, samples + b0 * N, Bc, si, wa, wp, g_am, g_ph, gws, gws_bytes, &handled, st);
+      if (rc != QCB_OK) return rc;
+      if (handled) continue;
+    }
     rc = run_grad_reduce_expanded(am, ex, rows, wa, nullptr, 0, 0, 1.0, g_am, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
     rc = run_grad_reduce_expanded(ph, ex, rows, wp, nullptr, 0, 0, 1.0, g_ph, gws, gws_bytes, st);

@@ -83,6 +83,13 @@ struct Expansion {
   }
 };
 
+// The rotated sites of a measurement basis (utils/unitaries.py:154-181)
+struct SiteInfo {
+  int S;
+  int8_t site[32];    // rotated site t -> visible unit
+  uint8_t ucode[32];  // rotated site t -> unitary code
+};
+
 // Where the rows of a reduced-gradient pass come from, and how they are weighted.
 enum { ROWS_EXPLICIT = 0, ROWS_ENUM = 1, ROWS_EXPANDED = 2 };
 struct RowSrc {

@@ -961,3 +961,40 @@ def test_small_and_trivial_shapes(lib, cuda):
     assert torch.equal(_kron_apply([d["Z"]] * 3, y), y)
     one = torch.tensor([1.0], device=cuda)
     assert abs(float(ts._kl_terms(one, None, one * 0.25, None, 0.0)) - (np.log(1 - 2.0 ** -52) - np.log(0.25))) < 1e-15
+
+
+@pytest.mark.parametrize("n,nh,S,B,scale", [(20, 20, 10, 19, 1.0), (20, 20, 10, 4096, 1.0), (12, 9, 5, 300, 1.0), (16, 31, 8, 7, 1.0),
+                                            (24, 17, 12, 3, 1.0), (10, 6, 6, 50, 200.0), (14, 14, 7, 9000, 1.0)])
+def test_complex_rotated_gradient_gray_walk(lib, cuda, n, nh, S, B, scale):
+    """Rotated-basis gradients with >= 5 rotated sites come from the Gray-walk subset sums of rotated_gray.cu (the rows of one
+    sample differ only in the rotated sites: no expanded outer products). Checked against the expanded-row reduction
+    (qcb_set_grad_reduce_mode(3): round 1's path) for few samples split into sub-ranges and many samples walked whole,
+    and against the oracle where its (2^S, B, G) tensors are affordable; scale = 200 makes e^theta overflow, which sends the
+    kernel through its additive-theta / table-logistic branch."""
+    from qucumber_b200 import ComplexWaveFunction, _lib
+
+    rng = np.random.default_rng(1000 + S)
+    nn = ComplexWaveFunction(n, nh, gpu=True)
+    pa = make_binary_params(n, nh, 41, bias_scale=0.3)
+    pp = make_binary_params(n, nh, 42, bias_scale=0.3)
+    pa = (pa[0] * scale, pa[1], pa[2])
+    load_binary(nn.rbm_am, *pa)
+    load_binary(nn.rbm_ph, *pp)
+    sites = np.sort(rng.choice(n, S, replace=False))
+    basis = np.array(["Z"] * n)
+    basis[sites] = rng.choice(["X", "Y"], S)
+    samples = random_states(B, n, 43)
+    ts = torch.tensor(samples, device=cuda)
+    new = [g.cpu().numpy() for g in nn.rotated_gradient(basis, ts)]
+    _lib.check(lib.qcb_set_grad_reduce_mode(3), "mode")
+    try:
+        old = [g.cpu().numpy() for g in nn.rotated_gradient(basis, ts)]
+    finally:
+        _lib.check(lib.qcb_set_grad_reduce_mode(0), "mode")
+    assert_close(new[0], old[0], what="Gray-walk vs expanded rows (amplitude)")
+    assert_close(new[1], old[1], what="Gray-walk vs expanded rows (phase)")
+    if B * (1 << S) <= 40000 and scale == 1.0:
+        am, ph = orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp)
+        ga, gp = orc.complex_rotated_gradient(am, ph, list(basis), samples)
+        assert_close(new[0], ga, what="Gray-walk vs oracle (amplitude)")
+        assert_close(new[1], gp, what="Gray-walk vs oracle (phase)")
