@@ -29,6 +29,7 @@ int fail(int code, const char* fmt, ...) {
 
 // implemented in the other translation units
 size_t gibbs_workspace_bytes(int N, int nhid);
+size_t gibbs_workspace_bytes_rows(int N, int nhid, int64_t rows);
 extern int g_gibbs_mode;
 extern int g_grad_mode;
 extern int g_cwf_mode;
@@ -128,7 +129,7 @@ uint64_t qcb_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
   switch (op) {
-    case QCB_OP_GIBBS: return gibbs_workspace_bytes(N, nh + na);
+    case QCB_OP_GIBBS: return gibbs_workspace_bytes_rows(N, nh + na, rows);
     case QCB_OP_ENERGY: return 0;
     case QCB_OP_GRAD_REDUCE: return grad_reduce_workspace_bytes(N, nh + na, rows);
     case QCB_OP_LOGZ: return enum_workspace_bytes();
@@ -139,13 +140,13 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
     case QCB_OP_CWF_ROTATED: return cwf_workspace_bytes(N, nh, rows);
     case QCB_OP_DM_ROTATED: return dm_workspace_bytes(N, nh, na, rows);
     case QCB_OP_CD_STEP: {
-      const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      const size_t a = gibbs_workspace_bytes_rows(N, nh + na, rows), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b + align_up((size_t)(rows > 0 ? rows : 0) * N * sizeof(double), 256);
     }
     case QCB_OP_KL_TERMS: return kl_workspace_bytes();
     case QCB_OP_SAMPLE: return gibbs_io_workspace_bytes(N, nh + na, rows);
     case QCB_OP_CDK_NEG: {
-      const size_t a = gibbs_workspace_bytes(N, nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      const size_t a = gibbs_workspace_bytes_rows(N, nh + na, rows), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a + b;
     }
     default: return 0;
@@ -271,7 +272,7 @@ int qcb_rbm_cdk_neg(const double* W, const double* U, const double* b, const dou
   int rc = make_params(p, W, U, b, c, d, N, nh, na);
   if (rc != QCB_OK) return rc;
   if (C < 0 || k < 0 || g == nullptr || (C > 0 && v == nullptr)) return fail(QCB_ERR_BAD_ARG, "cdk_neg: bad arguments");
-  const size_t gb = gibbs_workspace_bytes(N, nh + na);
+  const size_t gb = gibbs_workspace_bytes_rows(N, nh + na, C);
   if (ws == nullptr || ws_bytes < gb + grad_reduce_workspace_bytes(N, nh + na, C))
     return fail(QCB_ERR_BAD_ARG, "cdk_neg: workspace too small");
   rc = run_gibbs(p, v, v, C, k, seed, chain_id0, sweep0, uniforms, ws, gb, (cudaStream_t)stream);
@@ -289,7 +290,7 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
   if (rc != QCB_OK) return rc;
   if (B < 0 || C < 0 || k < 0 || g == nullptr || (B > 0 && pos == nullptr) || (C > 0 && neg == nullptr))
     return fail(QCB_ERR_BAD_ARG, "cd_step: bad arguments");
-  const size_t gb = gibbs_workspace_bytes(N, nh + na);
+  const size_t gb = gibbs_workspace_bytes_rows(N, nh + na, B > C ? B : C);  // sized like qcb_workspace_bytes(QCB_OP_CD_STEP, ..., max(B, C))
   const size_t rb = grad_reduce_workspace_bytes(N, nh + na, B > C ? B : C);
   const size_t vb = align_up((size_t)C * N * sizeof(double), 256);
   if (ws == nullptr || ws_bytes < gb + rb + vb) return fail(QCB_ERR_BAD_ARG, "cd_step: workspace too small");
@@ -508,7 +509,7 @@ int host_pipeline(HostPipe& hp, char* host, char* dev, size_t row_bytes, int64_t
 extern "C" {
 
 size_t qcb_gibbs_host_scratch_bytes(int N, int nh, int na, int64_t C) {
-  return param_bytes(N, nh, na) + align_up((size_t)C * N * sizeof(double), 256) + gibbs_workspace_bytes(N, nh + na);
+  return param_bytes(N, nh, na) + align_up((size_t)C * N * sizeof(double), 256) + gibbs_workspace_bytes_rows(N, nh + na, C);
 }
 
 int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double* b_host, const double* c_host,
@@ -538,7 +539,7 @@ int qcb_rbm_gibbs_host(const double* W_host, const double* U_host, const double*
   int nslices = (int)(vbytes / ((size_t)32 << 20));
   nslices = nslices < 1 ? 1 : (nslices > MAX_SLICES ? MAX_SLICES : nslices);
   const int64_t per = ((C + nslices - 1) / nslices + 15) / 16 * 16;
-  const size_t gws = gibbs_workspace_bytes(N, nh + na);
+  const size_t gws = gibbs_workspace_bytes_rows(N, nh + na, C);
   rc = host_pipeline(hp, reinterpret_cast<char*>(v_host), reinterpret_cast<char*>(dv), (size_t)N * sizeof(double), C, per, true, st,
                      [&](int64_t c0, int64_t cn) {
                        return run_gibbs(p, dv + c0 * N, dv + c0 * N, cn, k, seed, chain_id0 + (uint64_t)c0, sweep0, nullptr, ws, gws, st);

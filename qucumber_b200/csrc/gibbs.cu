@@ -405,6 +405,18 @@ static int pick_blocks(int units) {
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 size_t gibbs_umma_workspace_bytes(int N, int nhid);
 
+size_t gibbs_large_workspace_bytes(int N, int nhid, int64_t C);
+int run_gibbs_large(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
+                    uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
+static bool gibbs_fused_shape(int N, int nhid);
+size_t gibbs_workspace_bytes(int N, int nhid);
+
+// rows: the number of chains (only the composed path for large layers needs scratch that grows with it)
+size_t gibbs_workspace_bytes_rows(int N, int nhid, int64_t rows) {
+  if (!gibbs_fused_shape(N, nhid)) return gibbs_large_workspace_bytes(N, nhid, rows);
+  return gibbs_workspace_bytes(N, nhid);
+}
+
 size_t gibbs_workspace_bytes(int N, int nhid) {
   const int HB = pick_blocks(nhid), VB = pick_blocks(N);
   if (HB == 0 || VB == 0) return 0;
@@ -454,6 +466,11 @@ int64_t gibbs_umma_wave_chains();
 int try_gibbs_umma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                    void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
 
+static bool gibbs_fused_shape(int N, int nhid) {
+  const int HB = pick_blocks(nhid), VB = pick_blocks(N);
+  return HB != 0 && VB != 0 && !(HB == 8 && VB == 8);
+}
+
 static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
   const int HB = pick_blocks(p.nhid()), VB = pick_blocks(p.N);
   if (HB == 0 || VB == 0 || (HB == 8 && VB == 8))
@@ -467,7 +484,7 @@ static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
 // Workspace of a call with compact or in-kernel-initialised states: the fragment image plus, for shapes or modes the
 // integer-filter kernel does not take, one float64 copy of the chain state.
 size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
-  const size_t img = gibbs_workspace_bytes(N, nhid);
+  const size_t img = gibbs_workspace_bytes_rows(N, nhid, C);
   const bool imma = gibbs_imma_workspace_bytes(N, nhid) != 0;
   return img + (imma && g_gibbs_mode != 1 ? 0 : align_up((size_t)(C > 0 ? C : 0) * N * sizeof(double), 256));
 }
@@ -485,10 +502,8 @@ static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v,
 // General entry: any source (float64 rows, packed rows, in-kernel Bernoulli(1/2)) and any sink (float64 rows, packed rows).
 int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                  void* ws, size_t ws_bytes, cudaStream_t st) {
-  int HB, VB;
-  int rc = gibbs_shape_check(p, &HB, &VB);
-  if (rc != QCB_OK) return rc;
-  const size_t img_bytes = gibbs_workspace_bytes(p.N, p.nhid());
+  int rc = QCB_OK;
+  const size_t img_bytes = gibbs_workspace_bytes_rows(p.N, p.nhid(), C);
   if (ws == nullptr || ws_bytes < img_bytes) return fail(QCB_ERR_BAD_ARG, "gibbs: workspace too small (%zu < %zu)", ws_bytes, img_bytes);
   if (C == 0) return QCB_OK;
   if (sweep0 + (uint64_t)k > (1ull << 32))
@@ -533,6 +548,11 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
 static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                           uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, int allow_imma, cudaStream_t st) {
   const int nhid = p.nhid();
+  if (!gibbs_fused_shape(p.N, nhid)) {  // layers beyond the fused kernels: one affine + Bernoulli pass per conditional update
+    if (sweep0 + (uint64_t)k > (1ull << 32))
+      return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");
+    return run_gibbs_large(p, v_in, v, C, k, seed, chain_id0, sweep0, uniforms, ws, ws_bytes, st);
+  }
   int HB, VB;
   int rc0 = gibbs_shape_check(p, &HB, &VB);
   if (rc0 != QCB_OK) return rc0;

@@ -28,7 +28,7 @@ int run_grad_reduce_expanded(const StackedParams& p, const Expansion& ex, int64_
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
 size_t cwf_gray_workspace_bytes(int N);
 int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t Bc, const SiteInfo& si,
-                      const double* wa, const double* wp, double* g_am, double* g_ph, void* ws, size_t ws_bytes, int* handled,
+                      const double2* T, const double2* D, double* g_am, double* g_ph, void* ws, size_t ws_bytes, int* handled,
                       cudaStream_t st);
 int g_cwf_mode = 0;  // 0: automatic (Gray-walk gradient where it applies), 1: always the expanded-row reduction (test / measurement hook)
 
@@ -300,15 +300,15 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
     else rc = launch_cwf_amp<32>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
     if (rc != QCB_OK) return rc;
     if (g_am == nullptr) continue;
-    cwf_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(T, D, S, rows, wa, wp);
-    QCB_LAUNCH_CHECK();
-    ex.samples = samples + b0 * N;
     if (g_cwf_mode == 0) {  // the rows of a sample differ only in the rotated sites: subset sums instead of outer products
       int handled = 0;
-      rc = run_cwf_grad_gray(am, ph, samples + b0 * N, Bc, si, wa, wp, g_am, g_ph, gws, gws_bytes, &handled, st);
+      rc = run_cwf_grad_gray(am, ph, samples + b0 * N, Bc, si, T, D, g_am, g_ph, gws, gws_bytes, &handled, st);
       if (rc != QCB_OK) return rc;
       if (handled) continue;
     }
+    cwf_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(T, D, S, rows, wa, wp);
+    QCB_LAUNCH_CHECK();
+    ex.samples = samples + b0 * N;
     rc = run_grad_reduce_expanded(am, ex, rows, wa, nullptr, 0, 0, 1.0, g_am, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
     rc = run_grad_reduce_expanded(ph, ex, rows, wp, nullptr, 0, 0, 1.0, g_ph, gws, gws_bytes, st);

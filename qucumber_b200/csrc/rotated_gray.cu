@@ -30,8 +30,8 @@ struct GrayArgs {
   const double* samples;   // (Bc, N) rows of this chunk
   int64_t Bc;
   SiteInfo si;
-  const double* wa;        // per expanded row of the chunk: Re(T / D)
-  const double* wp;        // -Im(T / D)
+  const double2* T;        // per expanded row of the chunk: T_i = Ut_i psi(v_i)
+  const double2* D;        // per sample: sum_i T_i; the row weights are Re(T / D) and -Im(T / D)
   int sub_log2;            // sub-ranges per sample
   double* Qtot;            // [Bc << sub_log2][2][32]
   double* partQ;           // [grid][2][S][32]
@@ -100,16 +100,24 @@ __global__ void __launch_bounds__(GRAY_THREADS) cwf_gray_kernel(const GrayArgs a
       }
       if (fast) { tha = exp(tha); thp = exp(thp); }
     }
-    const double* wa = a.wa + (b << S);
-    const double* wp = a.wp + (b << S);
+    const double2* Trow = a.T + (b << S);
+    const double2 d = a.D[b];
+    const double dinv = 1.0 / (d.x * d.x + d.y * d.y);
     double Ra = 0.0, Rp = 0.0;
     const uint32_t steps = 1u << m;
-    double wa_n = wa[ibase], wp_n = wp[ibase];
+    double wa_l = 0.0, wp_l = 0.0;  // this lane's share of the next 32 states' weights
     for (uint32_t k = 0; k < steps; ++k) {
-      const double wak = wa_n, wpk = wp_n;
+      if ((k & 31u) == 0u) {  // 32 states' weights at once: lane l fetches state k + l (scattered, all in flight together)
+        const uint32_t kl = k + (uint32_t)lane;
+        if (kl < steps) {
+          const double2 t = Trow[ibase | (kl ^ (kl >> 1))];
+          wa_l = (t.x * d.x + t.y * d.y) * dinv;
+          wp_l = -((t.y * d.x - t.x * d.y) * dinv);
+        }
+      }
+      const double wak = __shfl_sync(0xffffffffu, wa_l, (int)(k & 31u)), wpk = __shfl_sync(0xffffffffu, wp_l, (int)(k & 31u));
       const uint32_t k1 = k + 1;
       const uint32_t g1 = k1 ^ (k1 >> 1);
-      if (k1 < steps) { wa_n = wa[ibase | g1]; wp_n = wp[ibase | g1]; }  // next state's weights, ahead of their use
       double pa, pp;
       if (fast) {
         pa = unit ? tha * rcp_newton(1.0 + tha) : (ones ? 1.0 : 0.0);
@@ -212,7 +220,7 @@ size_t cwf_gray_workspace_bytes(int N) {
 
 // *handled = 1 when this path took the chunk (5 <= S, nh <= 31, chunk small enough for the scratch)
 int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t Bc, const SiteInfo& si,
-                      const double* wa, const double* wp, double* g_am, double* g_ph, void* ws, size_t ws_bytes, int* handled,
+                      const double2* T, const double2* D, double* g_am, double* g_ph, void* ws, size_t ws_bytes, int* handled,
                       cudaStream_t st) {
   *handled = 0;
   const int N = am.N, nh = am.nh, S = si.S;
@@ -229,7 +237,7 @@ int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const do
   }
   char* base = static_cast<char*>(ws);
   GrayArgs a;
-  a.am = am; a.ph = ph; a.samples = samples; a.Bc = Bc; a.si = si; a.wa = wa; a.wp = wp; a.sub_log2 = sub;
+  a.am = am; a.ph = ph; a.samples = samples; a.Bc = Bc; a.si = si; a.T = T; a.D = D; a.sub_log2 = sub;
   a.Qtot = reinterpret_cast<double*>(base);
   a.partQ = reinterpret_cast<double*>(base + align_up((size_t)GRAY_MAX_SLOTS * 64 * sizeof(double), 256));
   double* Gfix = reinterpret_cast<double*>(reinterpret_cast<char*>(a.partQ) + align_up((size_t)sm_count() * 4 * 2 * 21 * 32 * sizeof(double), 256));

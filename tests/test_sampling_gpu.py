@@ -209,3 +209,61 @@ def test_single_step_samplers_follow_the_conditional(lib, cuda):
     sigma = (p * (1 - p) / rows).sqrt()
     assert torch.all((h.mean(0) - p).abs() < 5 * sigma)
     assert set(h.unique().tolist()) <= {0.0, 1.0}
+
+
+# ---- layers beyond the fused kernels (round-1 review: "Gibbs returns QCB_ERR_UNSUPPORTED above 128 units or with both layers > 64")
+@pytest.mark.parametrize("n,nh", [(100, 100), (130, 20), (20, 140), (150, 150), (65, 65)])
+def test_gibbs_large_layers_composed_path(lib, cuda, n, nh):
+    """Layers the fused kernels cannot hold take one affine + Bernoulli pass per conditional update (gibbs_large.cu): same
+    Philox convention, exact FP64 decisions — bit-exact against the oracle under its own draws and under fed uniforms, shard- and
+    split-invariant like the fused kernels; packed rows and in-kernel starts (N <= 128) work through the conversions."""
+    import qucumber_b200 as qb
+
+    rbm, orc = _pair(n, nh, 401)
+    v0 = random_states(257, n, 402)
+    got = rbm.gibbs_steps(3, torch.tensor(v0, device=cuda), seed=0xFEEDBEEF, chain_id0=7, sweep0=2)
+    assert np.array_equal(got.cpu().numpy(), orc.gibbs_steps_philox(3, v0, seed=0xFEEDBEEF, chain_id0=7, sweep0=2))
+    u = np.random.default_rng(403).random((2, 257, nh + n))
+    fed = rbm.gibbs_steps(2, torch.tensor(v0, device=cuda), uniforms=torch.tensor(u, device=cuda))
+    assert np.array_equal(fed.cpu().numpy(), orc.gibbs_steps_fed(2, v0, u))
+    lo = rbm.gibbs_steps(3, torch.tensor(v0[:100], device=cuda), seed=5)
+    hi = rbm.gibbs_steps(3, torch.tensor(v0[100:], device=cuda), seed=5, chain_id0=100)
+    assert torch.equal(torch.cat([lo, hi]), rbm.gibbs_steps(3, torch.tensor(v0, device=cuda), seed=5))
+    bits = rbm.gibbs_steps_packed(3, qb.pack_states(torch.tensor(v0, device=cuda)), seed=5)
+    assert torch.equal(qb.unpack_states(bits, n), torch.cat([lo, hi]))
+    if n <= 128:
+        s = rbm.sample_chains(2, 300, seed=11, chain_id0=4)
+        assert np.array_equal(s.cpu().numpy(), orc.sample_chains_philox(2, 300, seed=11, chain_id0=4))
+
+
+def test_gibbs_large_purification_and_cd_step(lib, cuda):
+    """PurificationRBM with nh + na = 150 hidden-like units (the stacked layer continues the unit numbering across h and a),
+    and the CD-k gradient call on a 100 x 100 BinaryRBM (Gibbs through the composed path, gradients through the FP64 kernels)."""
+    from qucumber_b200 import BinaryRBM, PurificationRBM, _lib
+
+    n, nh, na = 30, 90, 60
+    W, U, b, c, d = make_purification_params(n, nh, na, 411)
+    rbm = load_purification(PurificationRBM(n, nh, na, gpu=True), W, U, b, c, d)
+    orc = PurificationRBMOracle(W, U, b, c, d)
+    v0 = random_states(99, n, 412)
+    got = rbm.gibbs_steps(3, torch.tensor(v0, device=cuda), seed=77, chain_id0=3, sweep0=1)
+    assert np.array_equal(got.cpu().numpy(), orc.gibbs_steps_philox(3, v0, seed=77, chain_id0=3, sweep0=1))
+    u = np.random.default_rng(413).random((2, 99, nh + na + n))
+    fed = rbm.gibbs_steps(2, torch.tensor(v0, device=cuda), uniforms=torch.tensor(u, device=cuda))
+    assert np.array_equal(fed.cpu().numpy(), orc.gibbs_steps_fed(2, v0, u))
+    n, nh, B, C, k = 100, 100, 300, 200, 2
+    Wb, bb, cb = make_binary_params(n, nh, 414)
+    big = load_binary(BinaryRBM(n, nh, gpu=True), Wb, bb, cb)
+    o = BinaryRBMOracle(Wb, bb, cb)
+    pos, neg = random_states(B, n, 415), random_states(C, n, 416)
+    vk = o.gibbs_steps_philox(k, neg, seed=555, chain_id0=9, sweep0=3)
+    want = o.effective_energy_gradient(pos) / B - o.effective_energy_gradient(vk) / C
+    args, keep = big._param_args()
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+    g = torch.empty(big.num_pars, dtype=torch.double, device=cuda)
+    ws = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_CD_STEP, n, nh, 0, max(B, C)))
+    _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, k, 555, 9, 3, 1.0 / B, -1.0 / C, _lib.ptr(g), _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    from helpers import assert_close
+
+    assert_close(g, want, what="CD-k gradient, 100 x 100 layer")
