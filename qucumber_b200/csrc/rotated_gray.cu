@@ -16,7 +16,8 @@
 //    memory; Q per (sample, sub-range) goes to global memory.  When the products could leave the double range
 //    (the same device-side test as cwf_amp_kernel) theta is carried additively and p is the table logistic.
 //  * cwf_fixed_kernel: the fixed-site columns and the hidden-bias gradient, sum_b sigma_bj Q_b: one CTA per visible unit.
-//  * cwf_assemble_kernel: g += -(rotated-site columns from the per-CTA Q^t partials | fixed columns), fixed summation order.
+//  * cwf_partq_reduce_kernel / cwf_assemble_kernel: the per-CTA Q^t partials and the sample chunks of the fixed columns are
+//    added in a fixed order, g += -(rotated-site columns | fixed columns).
 #include "rows.cuh"
 
 namespace qcb {
@@ -159,14 +160,19 @@ __global__ void __launch_bounds__(GRAY_THREADS) cwf_gray_kernel(const GrayArgs a
   }
 }
 
-// Gfix[rbm][j][h] = sum_b sigma_bj sum_sub Q[b][sub][rbm][h] for j < N (used for the fixed sites), j = N: sigma = 1 (hidden bias)
+constexpr int GRAY_FIX_CHUNKS = 16;
+
+// Gfix[chunk][rbm][j][h] = sum over the chunk's samples b of sigma_bj sum_sub Q[b][sub][rbm][h] for j < N (used for the fixed sites);
+// j = N: sigma = 1 (hidden-bias gradient).  grid (N + 1, GRAY_FIX_CHUNKS): the chunks are added in a fixed order by cwf_assemble_kernel.
 __global__ void __launch_bounds__(256) cwf_fixed_kernel(const double* __restrict__ samples, int64_t Bc, int N, int sub_log2,
                                                         const double* __restrict__ Qtot, double* __restrict__ Gfix) {
   __shared__ double red[8][64];
   const int j = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nsub = 1 << sub_log2;
+  const int64_t per = (Bc + GRAY_FIX_CHUNKS - 1) / GRAY_FIX_CHUNKS;
+  const int64_t b_lo = blockIdx.y * per, b_hi = b_lo + per < Bc ? b_lo + per : Bc;
   double sa = 0.0, sp = 0.0;
-  for (int64_t b = warp; b < Bc; b += 8) {
+  for (int64_t b = b_lo + warp; b < b_hi; b += 8) {
     if (j < N && samples[b * N + j] == 0.0) continue;
     for (int s = 0; s < nsub; ++s) {
       const double* q = Qtot + ((b * nsub + s) * 2) * 32;
@@ -181,18 +187,34 @@ __global__ void __launch_bounds__(256) cwf_fixed_kernel(const double* __restrict
     double sum = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
-    Gfix[((size_t)(threadIdx.x >> 5) * (N + 1) + j) * 32 + (threadIdx.x & 31)] = sum;
+    Gfix[(((size_t)blockIdx.y * 2 + (threadIdx.x >> 5)) * (N + 1) + j) * 32 + (threadIdx.x & 31)] = sum;
+  }
+}
+
+// Qsum[rbm][t][h] = sum over the CTAs of cwf_gray_kernel of their subset-sum partials, fixed order.  grid 2 S, 256 threads.
+__global__ void __launch_bounds__(256) cwf_partq_reduce_kernel(const double* __restrict__ partQ, int nparts, int S, double* __restrict__ Qsum) {
+  __shared__ double red[8][32];
+  const int rt = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // rt = rbm * S + t
+  double sum = 0.0;
+  for (int p = warp; p < nparts; p += 8) sum += partQ[((size_t)p * 2 * S + rt) * 32 + lane];
+  red[warp][lane] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
+    Qsum[(size_t)rt * 32 + threadIdx.x] = tot;
   }
 }
 
 // g_am / g_ph += -(flat gradient [W (nh x N) | b (N) | c (nh)])
-__global__ void cwf_assemble_kernel(const double* __restrict__ partQ, int nparts, const double* __restrict__ Gfix, SiteInfo si, int N, int nh,
+__global__ void cwf_assemble_kernel(const double* __restrict__ Qsum, const double* __restrict__ Gfix, SiteInfo si, int N, int nh,
                                     double* __restrict__ g_am, double* __restrict__ g_ph) {
   const int G = nh * N + N + nh;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * G) return;
   const int rbm = e / G, f = e - rbm * G;
-  int h, j;  // h = 32..: none;  j = N: hidden-bias entry
+  int h, j;  // j = N: hidden-bias entry
   if (f < nh * N) { h = f / N; j = f - h * N; }
   else if (f < nh * N + N) { h = nh; j = f - nh * N; }  // visible bias: the pseudo unit
   else { h = f - nh * N - N; j = N; }
@@ -200,12 +222,12 @@ __global__ void cwf_assemble_kernel(const double* __restrict__ partQ, int nparts
   if (j < N)
     for (int q = 0; q < si.S; ++q)
       if (si.site[q] == j) t = q;
-  double val;
+  double val = 0.0;
   if (t >= 0) {
-    val = 0.0;
-    for (int p = 0; p < nparts; ++p) val += partQ[((size_t)p * 2 + rbm) * si.S * 32 + t * 32 + h];
+    val = Qsum[((size_t)rbm * si.S + t) * 32 + h];
   } else {
-    val = Gfix[((size_t)rbm * (N + 1) + j) * 32 + h];
+#pragma unroll
+    for (int c = 0; c < GRAY_FIX_CHUNKS; ++c) val += Gfix[(((size_t)c * 2 + rbm) * (N + 1) + j) * 32 + h];
   }
   double* g = rbm == 0 ? g_am : g_ph;
   g[f] -= val;
@@ -215,7 +237,7 @@ static size_t gray_smem(int S) { return ((size_t)2 * S * 64 + (size_t)2 * GRAY_W
 
 size_t cwf_gray_workspace_bytes(int N) {
   return align_up((size_t)GRAY_MAX_SLOTS * 64 * sizeof(double), 256) + align_up((size_t)sm_count() * 4 * 2 * 21 * 32 * sizeof(double), 256) +
-         align_up((size_t)2 * (N + 1) * 32 * sizeof(double), 256);
+         align_up((size_t)GRAY_FIX_CHUNKS * 2 * (N + 1) * 32 * sizeof(double), 256) + align_up((size_t)2 * 21 * 32 * sizeof(double), 256);
 }
 
 // *handled = 1 when this path took the chunk (5 <= S, nh <= 31, chunk small enough for the scratch)
@@ -246,10 +268,13 @@ int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const do
   const int grid = (int)(need < cap ? need : cap);
   cwf_gray_kernel<<<grid, GRAY_THREADS, smem, st>>>(a);
   QCB_LAUNCH_CHECK();
-  cwf_fixed_kernel<<<N + 1, 256, 0, st>>>(samples, Bc, N, sub, a.Qtot, Gfix);
+  double* Qsum = reinterpret_cast<double*>(reinterpret_cast<char*>(Gfix) + align_up((size_t)GRAY_FIX_CHUNKS * 2 * (N + 1) * 32 * sizeof(double), 256));
+  cwf_fixed_kernel<<<dim3(N + 1, GRAY_FIX_CHUNKS), 256, 0, st>>>(samples, Bc, N, sub, a.Qtot, Gfix);
+  QCB_LAUNCH_CHECK();
+  cwf_partq_reduce_kernel<<<2 * S, 256, 0, st>>>(a.partQ, grid, S, Qsum);
   QCB_LAUNCH_CHECK();
   const int G2 = 2 * (nh * N + N + nh);
-  cwf_assemble_kernel<<<(G2 + 127) / 128, 128, 0, st>>>(a.partQ, grid, Gfix, si, N, nh, g_am, g_ph);
+  cwf_assemble_kernel<<<(G2 + 127) / 128, 128, 0, st>>>(Qsum, Gfix, si, N, nh, g_am, g_ph);
   QCB_LAUNCH_CHECK();
   *handled = 1;
   return QCB_OK;
