@@ -3,7 +3,7 @@ import torch
 
 from ..rbm import BinaryRBM
 from ..utils import unitaries
-from .neural_state import stored_attribute
+from .neural_state import load_checkpoint, stored_attribute
 from .wavefunction import WaveFunctionBase
 
 
@@ -18,6 +18,8 @@ class ComplexWaveFunction(WaveFunctionBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
+    _rotated_limits = (("num_hidden", 32, "num_hidden"), ("num_visible", 128, "num_visible"))
+    _max_rotated_sites = 21
 
     def __init__(self, num_visible, num_hidden=None, unitary_dict=None, gpu=True, module=None):
         if module is not None:
@@ -80,7 +82,7 @@ class ComplexWaveFunction(WaveFunctionBase):
 
     @staticmethod
     def autoload(location, gpu=True):
-        state_dict = torch.load(location, map_location="cpu", weights_only=False)
+        state_dict = load_checkpoint(location)
         wvfn = ComplexWaveFunction(unitary_dict=state_dict["unitary_dict"],
                                    num_visible=len(state_dict["rbm_am"]["visible_bias"]),
                                    num_hidden=len(state_dict["rbm_am"]["hidden_bias"]), gpu=gpu)

@@ -4,7 +4,7 @@ import torch
 
 from ..rbm import PurificationRBM
 from ..utils import cplx, unitaries
-from .neural_state import NeuralStateBase, stored_attribute
+from .neural_state import NeuralStateBase, load_checkpoint, stored_attribute
 
 
 class DensityMatrix(NeuralStateBase):
@@ -14,6 +14,8 @@ class DensityMatrix(NeuralStateBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
+    _rotated_limits = (("num_aux", 16, "num_aux"), ("num_visible", 128, "num_visible"))
+    _max_rotated_sites = 8  # 4^S pairs per sample
 
     def __init__(self, num_visible, num_hidden=None, num_aux=None, unitary_dict=None, gpu=True, module=None):
         if module is not None:
@@ -143,7 +145,7 @@ class DensityMatrix(NeuralStateBase):
 
     @staticmethod
     def autoload(location, gpu=True):
-        state_dict = torch.load(location, map_location="cpu", weights_only=False)
+        state_dict = load_checkpoint(location)
         nn_state = DensityMatrix(unitary_dict=state_dict["unitary_dict"],
                                  num_visible=len(state_dict["rbm_am"]["visible_bias"]),
                                  num_hidden=len(state_dict["rbm_am"]["hidden_bias"]),

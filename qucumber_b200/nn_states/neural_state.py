@@ -25,6 +25,21 @@ from ..utils.data import extract_refbasis_samples
 from ..utils.gradients_utils import vector_to_grads
 
 
+def load_checkpoint(location, map_location="cpu"):
+    """torch.load of a QuCumber checkpoint. Tensors-only unpickling is tried first; a file whose metadata holds other Python
+    objects (the reference's save() accepts any picklable metadata, neural_state.py:199-226) needs the full unpickler, which can
+    run code from the file: that fallback warns, so only load such checkpoints from sources you trust."""
+    import pickle
+    import warnings
+
+    try:
+        return torch.load(location, map_location=map_location, weights_only=True)
+    except pickle.UnpicklingError:
+        warnings.warn(f"{location}: metadata is not tensors-only; unpickling arbitrary objects (trusted files only)",
+                      RuntimeWarning, stacklevel=3)
+        return torch.load(location, map_location=map_location, weights_only=False)
+
+
 class _Callbacks:
     """Minimal dispatcher for the reference's callback protocol (on_train_start, on_epoch_start,
     on_batch_start, on_batch_end, on_epoch_end, on_train_end); any object implementing a subset of
@@ -208,7 +223,7 @@ class NeuralStateBase(abc.ABC):
 
     def load(self, location):
         """Load parameters saved by this class or by stock QuCumber (neural_state.py:228-246)."""
-        state_dict = torch.load(location, map_location=self.device, weights_only=False)
+        state_dict = load_checkpoint(location, map_location=self.device)
         for net in self.networks:
             getattr(self, net).load_state_dict(state_dict[net])
         if hasattr(self, "unitary_dict") and "unitary_dict" in state_dict:
@@ -239,6 +254,24 @@ class NeuralStateBase(abc.ABC):
     def _accumulate_rotated_gradient(self, basis, samples, g_am, g_ph):
         """Subclasses with measurement bases accumulate the rotated-basis gradient of ``samples``."""
         raise NotImplementedError
+
+    #: shape limits of the fused rotated-basis kernels: (attribute of the state, largest supported value, what it is)
+    _rotated_limits = ()
+    _max_rotated_sites = 21
+
+    def _validate_rotated_shapes(self, bases):
+        """Raises ValueError when rotated-basis data cannot be handled by the fused kernels of this state type (the reference
+        has no such limits; they are listed in README.md)."""
+        rotated = int(np.max(np.sum(np.asarray(bases) != "Z", axis=-1))) if len(bases) else 0
+        if rotated == 0:
+            return
+        for attr, limit, what in self._rotated_limits:
+            if getattr(self, attr) > limit:
+                raise ValueError(f"{type(self).__name__}: rotated-basis data needs {what} <= {limit} in qucumber_b200 "
+                                 f"(this state has {getattr(self, attr)})")
+        if rotated > self._max_rotated_sites:
+            raise ValueError(f"{type(self).__name__}: at most {self._max_rotated_sites} non-Z sites per basis are supported "
+                             f"(the data has a basis with {rotated})")
 
     def gradient(self, samples, bases=None):
         """Summed gradients of a batch measured in the given bases (neural_state.py:326-369)."""
@@ -517,6 +550,7 @@ class NeuralStateBase(abc.ABC):
         net_params = [list(getattr(self, net).parameters()) for net in self.networks]
         z_samples = None
         if input_bases is not None:
+            self._validate_rotated_shapes(input_bases)  # a clear error now instead of QCB_ERR_UNSUPPORTED on the first rotated batch
             z_samples = extract_refbasis_samples(train_samples, input_bases).to(device=self.device)
 
         from .. import distributed as qd

@@ -2,7 +2,7 @@
 import torch
 
 from ..rbm import BinaryRBM
-from .neural_state import stored_attribute
+from .neural_state import load_checkpoint, stored_attribute
 from .wavefunction import WaveFunctionBase
 
 
@@ -18,7 +18,7 @@ class PositiveWaveFunction(WaveFunctionBase):
         if module is None:
             self.rbm_am = BinaryRBM(num_visible, num_hidden, gpu=gpu)
         else:
-            self.rbm_am = module.to(torch.device("cuda") if (gpu and torch.cuda.is_available()) else torch.device("cpu"))
+            self.rbm_am = module.to(torch.device("cuda", torch.cuda.current_device()) if (gpu and torch.cuda.is_available()) else torch.device("cpu"))
             self.rbm_am.device = next(self.rbm_am.parameters()).device
         self.num_visible = self.rbm_am.num_visible
         self.num_hidden = self.rbm_am.num_hidden
@@ -64,7 +64,7 @@ class PositiveWaveFunction(WaveFunctionBase):
 
     @staticmethod
     def autoload(location, gpu=True):
-        state_dict = torch.load(location, map_location="cpu", weights_only=False)
+        state_dict = load_checkpoint(location)
         wvfn = PositiveWaveFunction(num_visible=len(state_dict["rbm_am"]["visible_bias"]),
                                     num_hidden=len(state_dict["rbm_am"]["hidden_bias"]), gpu=gpu)
         wvfn.load(location)

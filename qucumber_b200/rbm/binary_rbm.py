@@ -32,7 +32,9 @@ class BinaryRBM(ChainSamplingMixin, nn.Module):
         self.num_hidden = int(num_hidden) if num_hidden else self.num_visible
         self.num_pars = (self.num_visible * self.num_hidden) + self.num_visible + self.num_hidden
         self.gpu = gpu and torch.cuda.is_available()
-        self.device = torch.device("cuda") if self.gpu else torch.device("cpu")
+        # an INDEXED device: streams and workspaces are looked up per device, and "cuda" alone would follow whatever device is
+        # current at call time rather than the one that owns the parameters
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.gpu else torch.device("cpu")
         self.initialize_parameters(zero_weights=zero_weights)
 
     def __repr__(self):

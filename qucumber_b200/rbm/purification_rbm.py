@@ -30,7 +30,9 @@ class PurificationRBM(ChainSamplingMixin, nn.Module):
             + self.num_visible + self.num_hidden + self.num_aux
         )
         self.gpu = gpu and torch.cuda.is_available()
-        self.device = torch.device("cuda") if self.gpu else torch.device("cpu")
+        # an INDEXED device: streams and workspaces are looked up per device, and "cuda" alone would follow whatever device is
+        # current at call time rather than the one that owns the parameters
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.gpu else torch.device("cpu")
         self.initialize_parameters(zero_weights=zero_weights)
 
     def __repr__(self):

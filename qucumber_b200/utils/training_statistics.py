@@ -17,7 +17,16 @@ from .unitaries import rotate_psi, rotate_psi_inner_prod, rotate_rho_probs
 
 
 def _is_full_space(nn_state, space):
-    return space is None or isinstance(space, HilbertSpace) or space.shape[0] == (1 << nn_state.num_visible)
+    """True when ``space`` is the canonical enumeration (row r = binary digits of r, MSB first): None, a HilbertSpace handle,
+    or an explicit tensor that EQUALS it — a caller-supplied space in another row order (or with repeated rows) must be
+    evaluated row by row like the reference does, because the target is indexed in space order."""
+    if space is None or isinstance(space, HilbertSpace):
+        return True
+    n = nn_state.num_visible
+    if space.dim() != 2 or space.shape[0] != (1 << n) or space.shape[1] != n or n > 24:
+        return False
+    canonical = HilbertSpace(n, space.device).tensor()
+    return bool(torch.equal(space.to(torch.double), canonical))
 
 
 def _positive_stats(nn_state, target):

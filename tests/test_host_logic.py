@@ -386,3 +386,65 @@ def test_reference_arm_json_contract():
     other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                            capture_output=True, text=True, timeout=120, env=env, cwd=root)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_rotated_shape_limits_raise_before_training():
+    """shapes the fused rotated-basis kernels cannot take are refused with a clear ValueError at the start of fit(),
+    not with QCB_ERR_UNSUPPORTED on the first rotated batch."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+    big = ComplexWaveFunction(40, gpu=False)  # default num_hidden = num_visible = 40 > 32
+    z_only = np.array([["Z"] * 40] * 3)
+    big._validate_rotated_shapes(z_only)  # reference-basis data needs no rotated kernel
+    rotated = z_only.copy()
+    rotated[1, 5] = "X"
+    with pytest.raises(ValueError, match="num_hidden <= 32"):
+        big._validate_rotated_shapes(rotated)
+    ok = ComplexWaveFunction(40, 32, gpu=False)
+    ok._validate_rotated_shapes(rotated)
+    many = np.array([["X"] * 22 + ["Z"] * 18])
+    with pytest.raises(ValueError, match="at most 21 non-Z sites"):
+        ok._validate_rotated_shapes(many)
+    dm = DensityMatrix(20, gpu=False)  # default num_aux = 20 > 16
+    with pytest.raises(ValueError, match="num_aux <= 16"):
+        dm._validate_rotated_shapes(np.array([["X"] + ["Z"] * 19]))
+    dm = DensityMatrix(12, 12, 12, gpu=False)
+    with pytest.raises(ValueError, match="at most 8 non-Z sites"):
+        dm._validate_rotated_shapes(np.array([["Y"] * 9 + ["Z"] * 3]))
+
+
+def test_full_space_fast_path_only_for_the_canonical_enumeration():
+    """an explicit space tensor takes the index-generated path only when it IS the canonical enumeration."""
+    from types import SimpleNamespace
+
+    from qucumber_b200.hilbert import HilbertSpace
+    from qucumber_b200.utils.training_statistics import _is_full_space
+
+    st = SimpleNamespace(num_visible=4)
+    canonical = HilbertSpace(4, "cpu").tensor()
+    assert _is_full_space(st, None) and _is_full_space(st, HilbertSpace(4, "cpu")) and _is_full_space(st, canonical)
+    assert not _is_full_space(st, canonical.flip(0))  # another row order
+    dup = canonical.clone()
+    dup[3] = dup[2]
+    assert not _is_full_space(st, dup)  # repeated rows
+    assert not _is_full_space(st, canonical[:8])
+
+
+def test_checkpoint_loader_prefers_tensors_only(tmp_path):
+    """checkpoints are read with the tensors-only unpickler; arbitrary-object metadata falls back with a warning."""
+    import warnings
+
+    from qucumber_b200.nn_states.neural_state import load_checkpoint
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        for kind in ("positive", "complex", "density"):
+            assert "rbm_am" in load_checkpoint(os.path.join(os.path.dirname(__file__), "golden", f"ref_checkpoint_{kind}.pt"))
+    path = tmp_path / "odd.pt"
+    torch.save({"rbm_am": {"weights": torch.zeros(2, 2)}, "note": SimpleNamespaceForPickle()}, path)
+    with pytest.warns(RuntimeWarning, match="trusted files only"):
+        assert "note" in load_checkpoint(path)
+
+
+class SimpleNamespaceForPickle:
+    """A module-level class: picklable, and not on torch's tensors-only allowlist."""
