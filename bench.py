@@ -498,6 +498,22 @@ def extra_metrics(dev, lib_mod):
 
             ms_10, _ = timed(ten_calls)
             ms_g = ms_10 / 10.0
+            # the same ten calls replayed from a CUDA graph: device time without the host's per-call work (the calls never
+            # synchronise, so they capture as they are)
+            ms_graph = None
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    ten_calls()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ten_calls()
+                ms_graph = timed(graph.replay)[0] / 10.0
+                del graph
+            except Exception as exc:  # pragma: no cover
+                ms_graph = f"unavailable: {exc}"
             lib_mod.load().qcb_set_grad_reduce_mode(3)  # round 1's kernels (integer theta on mma.sync + DMMA outer products)
             ms_10_r1, _ = timed(ten_calls)
             lib_mod.load().qcb_set_grad_reduce_mode(0)
@@ -505,8 +521,9 @@ def extra_metrics(dev, lib_mod):
             tf = rows * 4 * nv * nhd / (ms_g * 1e-3) / 1e12
             res[name] = {"N": nv, "nh": nhd, "rows": rows, "ms": ms_g, "hbm_gbps": gbs, "hbm_frac": gbs / hbm_peak,
                          "fp64_tflops": tf, "fp64_frac_of_dmma_peak": tf / 37.117, "ms_round1_kernels": ms_10_r1 / 10.0,
+                         "ms_cuda_graph_replay": ms_graph,
                          "kernel": ("grad_reduce_umma_kernel (both contractions on tcgen05.mma.kind::i8, TMEM accumulators)" if nv > 32
-                                    else "grad_reduce_small_kernel (streaming, DMMA outer products)"),
+                                    else "state_hist_kernel + grad_hist_kernel (binary rows counted: 2^N distinct states; mode 3 = the streaming kernel)"),
                          # floors: HBM = N*8 B per row; FP64 pipe with both contractions in FP64 (4*N*nh flop) plus nh sigmoids
                          # (~50 DFMA each).  Binary rows of 25..64-unit layers take theta from exact int8 tensor-core sums
                          # (DESIGN.md 3.3), which halves the FP64 contraction work: the frac above counts ALGORITHMIC flop.

@@ -32,6 +32,7 @@ size_t gibbs_workspace_bytes(int N, int nhid);
 size_t gibbs_workspace_bytes_rows(int N, int nhid, int64_t rows);
 extern int g_gibbs_mode;
 extern int g_grad_mode;
+extern int g_grad_small_hist;
 extern int g_cwf_mode;
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
@@ -57,6 +58,10 @@ int run_kron_rotate(double* re, double* im, int n, int64_t batch, const unsigned
                     cudaStream_t st);
 int run_kl_terms(const double* t_re, const double* t_im, const double* p_re, const double* p_im, int64_t n, double logZ, double* out2,
                  void* ws, size_t ws_bytes, cudaStream_t st);
+bool grad_reduce_bits_supported(int N, int H, int64_t rows);
+size_t gibbs_imma_workspace_bytes(int N, int nhid);
+int run_grad_reduce_bits(const StackedParams& p, const uint8_t* bits, double* scratch_rows, int64_t rows, double scale, double* g,
+                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, double scale, double* g, int accumulate,
                     void* ws, size_t ws_bytes, cudaStream_t st);
 int run_exact_grad_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, double* g, void* ws,
@@ -141,7 +146,8 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
     case QCB_OP_DM_ROTATED: return dm_workspace_bytes(N, nh, na, rows);
     case QCB_OP_CD_STEP: {
       const size_t a = gibbs_workspace_bytes_rows(N, nh + na, rows), b = grad_reduce_workspace_bytes(N, nh + na, rows);
-      return a + b + align_up((size_t)(rows > 0 ? rows : 0) * N * sizeof(double), 256);
+      const size_t r = (size_t)(rows > 0 ? rows : 0);
+      return a + b + align_up(r * N * sizeof(double), 256) + align_up(r * packed_row_bytes(N), 256);  // v_k as rows, and packed
     }
     case QCB_OP_KL_TERMS: return kl_workspace_bytes();
     case QCB_OP_SAMPLE: return gibbs_io_workspace_bytes(N, nh + na, rows);
@@ -176,6 +182,7 @@ int qcb_set_grad_reduce_mode(int mode) {
   if (mode != 0 && mode != 1 && mode != 3)
     return fail(QCB_ERR_BAD_ARG, "grad_reduce mode must be 0 (automatic), 1 (FP64 tensor cores only) or 3 (integer theta + FP64 outer products, never tcgen05)");
   g_grad_mode = mode;
+  g_grad_small_hist = mode == 0 ? 1 : 0;  // the histogram path of small binary layers is part of the automatic selection
   g_cwf_mode = mode != 0 ? 1 : 0;  // modes 1 and 3 also send the rotated-basis gradients through the expanded-row reduction
   return QCB_OK;
 }
@@ -293,12 +300,25 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
   const size_t gb = gibbs_workspace_bytes_rows(N, nh + na, B > C ? B : C);  // sized like qcb_workspace_bytes(QCB_OP_CD_STEP, ..., max(B, C))
   const size_t rb = grad_reduce_workspace_bytes(N, nh + na, B > C ? B : C);
   const size_t vb = align_up((size_t)C * N * sizeof(double), 256);
-  if (ws == nullptr || ws_bytes < gb + rb + vb) return fail(QCB_ERR_BAD_ARG, "cd_step: workspace too small");
+  const size_t pb = align_up((size_t)C * packed_row_bytes(N), 256);
+  if (ws == nullptr || ws_bytes < gb + rb + vb + pb) return fail(QCB_ERR_BAD_ARG, "cd_step: workspace too small");
   char* base = static_cast<char*>(ws);
   double* vk = reinterpret_cast<double*>(base + gb + rb);
   cudaStream_t st = (cudaStream_t)stream;
   rc = run_grad_reduce(p, pos, B, pos_scale, g, 0, base + gb, rb, st);
   if (rc != QCB_OK) return rc;
+  // v_k is internal to the step.  Where the integer-filter Gibbs kernels and the tcgen05 gradient kernel both take the shape it
+  // travels between them PACKED (8 bytes per chain at N = 64 instead of 512: the Gibbs kernel writes bits, the gradient kernel
+  // reads them as the operand bytes it needs anyway); the float64 rows are only materialised if that kernel gives the batch up.
+  if (k >= 1 && g_gibbs_mode != 1 && gibbs_imma_workspace_bytes(N, nh + na) != 0 && grad_reduce_bits_supported(N, nh + na, C)) {
+    uint8_t* vk_bits = reinterpret_cast<uint8_t*>(base + gb + rb + vb);
+    ChainIO io;
+    io.v_in = neg;
+    io.bits_out = vk_bits;
+    rc = run_gibbs_io(p, io, C, k, seed, chain_id0, sweep0, base, gb, st);
+    if (rc != QCB_OK) return rc;
+    return run_grad_reduce_bits(p, vk_bits, vk, C, neg_scale, g, 1, base + gb, rb, st);
+  }
   rc = run_gibbs(p, neg, vk, C, k, seed, chain_id0, sweep0, nullptr, base, gb, st);
   if (rc != QCB_OK) return rc;
   return run_grad_reduce(p, vk, C, neg_scale, g, 1, base + gb, rb, st);

@@ -21,7 +21,8 @@ constexpr int GR = 32;  // rows per tile
 constexpr int GR_MAX_CTAS_PER_SM = 4;  // partial-sum slots per SM in the workspace (tensor-core kernel: up to 4 CTAs/SM)
 
 int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
-                          int* grid_out, cudaStream_t st);
+                          int* grid_out, void* hist_scratch, cudaStream_t st);
+size_t grad_hist_scratch_bytes();
 int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
                          int* grid_out, int* flag, unsigned char* umma_img, cudaStream_t st);
 size_t grad_umma_workspace_bytes();
@@ -201,7 +202,9 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
   double* partials = reinterpret_cast<double*>(ws);
   int grid_dmma = 0;
   if (rows > 0) {  // small layers, large batches of explicit rows: the streaming kernel of grad_reduce_small.cu
-    const int rc = try_grad_reduce_small(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, st);
+    // its histogram path borrows the scratch of the tcgen05 weight image (that kernel only takes layers of 33..64 units)
+    void* hist_scratch = grad_umma_workspace_bytes() >= grad_hist_scratch_bytes() ? reinterpret_cast<char*>(ws) + need - 256 - grad_umma_workspace_bytes() : nullptr;
+    const int rc = try_grad_reduce_small(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, hist_scratch, st);
     if (rc != QCB_OK) return rc;
   }
   if (rows > 0 && grid_dmma == 0) {
@@ -236,6 +239,20 @@ int run_grad_reduce(const StackedParams& p, const double* v, int64_t rows, doubl
   RowSrc src{};
   src.v = v;
   const int H = p.nhid();
+  return launch_grad_reduce<ROWS_EXPLICIT>(stacked_hidden_spec(p), src, H, rows, scale, g, accumulate, H * p.N + p.N + H, ws,
+                                           ws_bytes, st);
+}
+
+// The same reduction over PACKED binary rows (v_k of a CD step straight from the Gibbs kernel); scratch_rows: rows x N doubles
+// that the FP64 stand-in reads if the tcgen05 kernel gives the batch up.  Only for shapes grad_reduce_bits_supported() accepts.
+bool grad_reduce_bits_supported(int N, int H, int64_t rows);
+int run_grad_reduce_bits(const StackedParams& p, const uint8_t* bits, double* scratch_rows, int64_t rows, double scale, double* g,
+                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int H = p.nhid();
+  if (!grad_reduce_bits_supported(p.N, H, rows)) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: packed rows not supported for this shape");
+  RowSrc src{};
+  src.v = scratch_rows;
+  src.bits = bits;
   return launch_grad_reduce<ROWS_EXPLICIT>(stacked_hidden_spec(p), src, H, rows, scale, g, accumulate, H * p.N + p.N + H, ws,
                                            ws_bytes, st);
 }

@@ -486,9 +486,17 @@ static int gd_residency(int* out) {
 
 // persistent grid = exactly the resident CTAs.  With a flag the integer-phase-1 kernel goes first and the FP64 kernel
 // behind it only works when the first one gave up (non-binary rows, weights outside the image); both use one grid.
-int try_grad_reduce_umma(const AffineSpec& s, const double* v, int H, int64_t rows, double* partials, int nslots, int* flag,
-                         unsigned char* img, int* launched, cudaStream_t st);
-int g_grad_mode = 0;  // qcb_set_grad_reduce_mode: 0 automatic, 1 FP64 tensor cores only, 3 never the tcgen05 kernel
+int try_grad_reduce_umma(const AffineSpec& s, const double* v, const unsigned char* bits, int H, int64_t rows, double* partials, int nslots,
+                         int* flag, unsigned char* img, int* launched, cudaStream_t st);
+bool grad_umma_shape(int N, int H, int64_t rows);
+int run_unpack_states_if(const int* flag, const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st);
+int g_grad_mode = 0;
+
+// Packed rows are only taken by the tcgen05 kernel (the FP64 kernel behind it reads the float64 scratch rows, which are
+// unpacked on the device only when that kernel is needed): true when launch_gd below will route such a batch there.
+bool grad_reduce_bits_supported(int N, int H, int64_t rows) {
+  return g_grad_mode == 0 && grad_umma_shape(N, H, rows) && rows <= ((int64_t)1 << 29) && gd_smem(pick8(N), pick8(H)) <= SMEM_LIMIT;
+}  // qcb_set_grad_reduce_mode: 0 automatic, 1 FP64 tensor cores only, 3 never the tcgen05 kernel
 
 template <int NB8, int HB8, bool WITH_IMMA>
 static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t rows, double* partials, int* grid_io, int* flag,
@@ -508,8 +516,12 @@ static int launch_gd(const AffineSpec& s, const RowSrc& src, int mode, int64_t r
     // binary rows: both contractions on tcgen05 / TMEM (grad_reduce_umma.cu) where the shape fits, else integer theta + DMMA
     int on_umma = 0;
     if (mode == ROWS_EXPLICIT && g_grad_mode == 0) {
-      if (int rc = try_grad_reduce_umma(s, src.v, s.n_out, rows, partials, grid, flag, umma_img, &on_umma, st)) return rc;
+      if (int rc = try_grad_reduce_umma(s, src.v, src.bits, s.n_out, rows, partials, grid, flag, umma_img, &on_umma, st)) return rc;
+      // packed source: the FP64 kernel queued below reads float64 rows, written from the bits only if *flag was raised
+      if (on_umma && src.bits != nullptr)
+        if (int rc = run_unpack_states_if(flag, src.bits, rows, s.n_in1, const_cast<double*>(src.v), st)) return rc;
     }
+    if (src.bits != nullptr && !on_umma) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: packed rows need the tcgen05 kernel");
     if (!on_umma && g_grad_mode != 1) {
       grad_reduce_dmma_kernel<NB8, HB8, WITH_IMMA><<<grid, GD_THREADS, gd_smem(NB8, HB8, true), st>>>(s, src, mode, rows, partials, flag);
       QCB_LAUNCH_CHECK();

@@ -14,14 +14,19 @@
 
 namespace qcb {
 
+int g_grad_small_hist = 1;  // qcb_set_grad_reduce_mode(1 or 3) turns the histogram path off (the streaming kernel alone)
 constexpr int GS_THREADS = 256;
 constexpr int GS_TILE = 2 * GS_THREADS;  // rows per tile
 
 template <int NT, int HT>
 __global__ void __launch_bounds__(GS_THREADS, 2) grad_reduce_small_kernel(AffineSpec s, const double* __restrict__ v, int64_t rows,
-                                                                          double* __restrict__ partials) {
+                                                                          double* __restrict__ partials, const int* __restrict__ gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = s.n_in1, H = s.n_out;
+  if (gate != nullptr && *gate == 0) {  // queued behind the histogram path (below), which took the batch: this slot counts as zero
+    for (int idx = threadIdx.x; idx < H * N + N + H; idx += GS_THREADS) partials[(size_t)blockIdx.x * (H * N + N + H) + idx] = 0.0;
+    return;
+  }
   double* Vt = reinterpret_cast<double*>(smem_raw);   // [GS_TILE][N]  the tile as it lies in global memory
   double* Pt = Vt + (size_t)GS_TILE * N;              // [GS_TILE][H]
   __shared__ double Ws[HT * NT];                      // zero-padded weights
@@ -168,12 +173,132 @@ __global__ void __launch_bounds__(GS_THREADS, 2) grad_reduce_small_kernel(Affine
 
 static size_t gs_smem(int N, int H) { return (size_t)GS_TILE * (N + H) * sizeof(double); }
 
+// ---- binary rows of a very small visible layer: histogram, then one weighted pass over the 2^N states ----------------------
+// At N = 10 a batch of 2^20 rows holds at most 1 024 DISTINCT rows.  sum_rows grad E(v_r) = sum_states count(s) grad E(s), so
+// the batch is only COUNTED (one coalesced read of the rows: the HBM floor of this reduction, 80 B per row) and the logistic
+// function is evaluated once per distinct state.  The counts are integers, so the result is the row sum in another order.
+// A row that is not 0/1 raises *flag; the streaming kernel queued behind (gate = flag) then redoes the batch.
+constexpr int GH_THREADS = 256;
+constexpr int GH_MAX_N = 12;
+
+__global__ void __launch_bounds__(GH_THREADS) state_hist_kernel(const double* __restrict__ v, int64_t rows, int N, unsigned int* __restrict__ hist,
+                                                                int* __restrict__ flag) {
+  extern __shared__ unsigned int sh[];                 // [2^N] counters, then [8 warps][GH_MAX_N] ballot words
+  const int nstates = 1 << N;
+  unsigned int* words = sh + nstates + (threadIdx.x >> 5) * (GH_MAX_N + 1);
+  for (int i = threadIdx.x; i < nstates; i += GH_THREADS) sh[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t nchunks = (rows + 31) >> 5;             // a warp takes 32 rows = 32 N consecutive doubles at a time
+  const int64_t total = rows * N;
+  bool nonbinary = false;
+  for (int64_t chunk = (int64_t)blockIdx.x * (GH_THREADS / 32) + (threadIdx.x >> 5); chunk < nchunks;
+       chunk += (int64_t)gridDim.x * (GH_THREADS / 32)) {
+    const int64_t base = chunk * 32 * N;
+    unsigned long long d[GH_MAX_N];
+#pragma unroll
+    for (int i = 0; i < GH_MAX_N; ++i) {                // all loads first: N x 256 contiguous bytes in flight per warp
+      const int64_t at = base + 32 * i + lane;
+      d[i] = (i < N && at < total) ? __ldg(reinterpret_cast<const unsigned long long*>(v) + at) : 0ull;
+    }
+#pragma unroll
+    for (int i = 0; i < GH_MAX_N; ++i) {
+      if (i < N) {
+        nonbinary |= (d[i] << 1) != 0ull && d[i] != 0x3FF0000000000000ull;
+        const unsigned int w = __ballot_sync(0xffffffffu, (d[i] << 1) != 0ull);  // bit l = double 32 i + l of the chunk
+        if (lane == 0) words[i] = w;
+      }
+    }
+    if (lane == 0) words[N] = 0u;
+    __syncwarp();
+    // lane l owns row 32 chunk + l: bits [l N, l N + N) of the chunk's bit string, unit j at bit j; the state index of the
+    // enumeration has unit 0 as its MOST significant bit (nn_states/neural_state.py:173-176)
+    const int at = lane * N;
+    const unsigned int raw = __funnelshift_r(words[at >> 5], words[(at >> 5) + 1], at & 31) & (unsigned int)(nstates - 1);
+    const unsigned int key = chunk * 32 + lane < rows ? (__brev(raw) >> (32 - N)) : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, key);  // equal rows of the warp are counted by one atomic
+    if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(sh + key, (unsigned int)__popc(peers));
+    __syncwarp();
+  }
+  if (nonbinary) *flag = 3;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nstates; i += GH_THREADS)
+    if (sh[i] != 0u) atomicAdd(hist + i, sh[i]);
+}
+
+// partial sums of count(s) [p(s) (x) s ; s ; p(s)] over GH_THREADS states per CTA, in the flat order of the other kernels
+__global__ void __launch_bounds__(GH_THREADS) grad_hist_kernel(AffineSpec s, const unsigned int* __restrict__ hist, const int* __restrict__ flag,
+                                                               double* __restrict__ partials) {
+  const int N = s.n_in1, H = s.n_out;
+  const int E = H * N + N + H;
+  double* out = partials + (size_t)blockIdx.x * E;
+  __shared__ double Ws[16 * GH_MAX_N], hbs[16];
+  __shared__ double Pt[GH_THREADS][17];               // count * p, column 16 = the count itself
+  if (*flag != 0) {                                   // the batch was not binary: the gated kernel behind this one redoes it
+    for (int idx = threadIdx.x; idx < E; idx += GH_THREADS) out[idx] = 0.0;
+    return;
+  }
+  for (int idx = threadIdx.x; idx < H * N; idx += GH_THREADS) Ws[idx] = s.mop(idx / N, idx % N);
+  if (threadIdx.x < H) hbs[threadIdx.x] = s.bias(threadIdx.x);
+  __syncthreads();
+  const unsigned int state = blockIdx.x * GH_THREADS + threadIdx.x;   // unit j = bit N - 1 - j
+  const unsigned int count = state < (1u << N) ? hist[state] : 0u;
+  const double w = (double)count;
+  for (int i = 0; i < H; ++i) {
+    double pw = 0.0;
+    if (count != 0u) {
+      double th = hbs[i];
+      for (int j = 0; j < N; ++j) th += ((state >> (N - 1 - j)) & 1u) ? Ws[i * N + j] : 0.0;
+      pw = w * fmin(fmax(sigmoid_exact(th), 0.0), 1.0);
+    }
+    Pt[threadIdx.x][i] = pw;
+  }
+  Pt[threadIdx.x][16] = w;
+  __syncthreads();
+  // entry e of the flat gradient: a sum over the CTA's states in a fixed order
+  for (int e = threadIdx.x; e < E; e += GH_THREADS) {
+    int col, bit;  // column of Pt, and the unit whose bit selects the states (-1: all)
+    if (e < H * N) { col = e / N; bit = e - col * N; }
+    else if (e < H * N + N) { col = 16; bit = e - H * N; }
+    else { col = e - H * N - N; bit = -1; }
+    const unsigned int sel = bit < 0 ? 0u : 1u << (N - 1 - bit);
+    const unsigned int s0 = blockIdx.x * GH_THREADS;
+    double a0 = 0.0, a1 = 0.0;
+    for (int r = 0; r < GH_THREADS; r += 2) {
+      a0 += (bit < 0 || ((s0 + r) & sel)) ? Pt[r][col] : 0.0;
+      a1 += (bit < 0 || ((s0 + r + 1) & sel)) ? Pt[r + 1][col] : 0.0;
+    }
+    out[e] = a0 + a1;
+  }
+}
+
+size_t grad_hist_scratch_bytes() { return ((size_t)1 << GH_MAX_N) * sizeof(unsigned int) + 256; }
+
 // *grid_out > 0 when this kernel took the batch (explicit rows, no aux features, N and H <= 16, >= 4096 rows)
+// hist_scratch: grad_hist_scratch_bytes() of device memory (or NULL): enables the histogram path for N <= 12 and rows >= 16 * 2^N
 int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
-                          int* grid_out, cudaStream_t st) {
+                          int* grid_out, void* hist_scratch, cudaStream_t st) {
   *grid_out = 0;
   const int N = s.n_in1;
   if (mode != ROWS_EXPLICIT || H != s.n_out || rows < 4096 || N > 16 || H > 16 || N < 1 || H < 1) return QCB_OK;
+  const int* gate = nullptr;
+  int first_slot = 0;
+  if (hist_scratch != nullptr && g_grad_small_hist && N <= GH_MAX_N && rows >= ((int64_t)16 << N) && rows < ((int64_t)1 << 31)) {
+    const int nstates = 1 << N;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(hist_scratch);
+    int* flag = reinterpret_cast<int*>(hist + nstates);
+    QCB_CUDA(cudaMemsetAsync(hist, 0, (size_t)(nstates + 1) * sizeof(unsigned int), st));
+    const size_t hsmem = ((size_t)nstates + (GH_THREADS / 32) * (GH_MAX_N + 1)) * sizeof(unsigned int);
+    const int64_t nchunks = (rows + 31) / 32, want = (nchunks + GH_THREADS / 32 - 1) / (GH_THREADS / 32), hcap = (int64_t)sm_count() * 4;
+    state_hist_kernel<<<(int)(want < hcap ? want : hcap), GH_THREADS, hsmem, st>>>(src.v, rows, N, hist, flag);
+    QCB_LAUNCH_CHECK();
+    first_slot = (nstates + GH_THREADS - 1) / GH_THREADS;
+    grad_hist_kernel<<<first_slot, GH_THREADS, 0, st>>>(s, hist, flag, partials);
+    QCB_LAUNCH_CHECK();
+    gate = flag;
+    partials += (size_t)first_slot * ((size_t)H * N + N + H);
+    max_grid -= first_slot;
+  }
   const int NT = (N + 3) / 4 * 4, HT = (H + 3) / 4 * 4;
   const size_t smem = gs_smem(N, H);
   const int64_t ntiles = (rows + GS_TILE - 1) / GS_TILE;
@@ -183,9 +308,9 @@ int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int 
 #define QCB_GS_CASE(NTx, HTx)                                                                                                  \
   if (NT == NTx && HT == HTx) {                                                                                                \
     QCB_CUDA(cudaFuncSetAttribute(grad_reduce_small_kernel<NTx, HTx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    grad_reduce_small_kernel<NTx, HTx><<<grid, GS_THREADS, smem, st>>>(s, src.v, rows, partials);                              \
+    grad_reduce_small_kernel<NTx, HTx><<<grid, GS_THREADS, smem, st>>>(s, src.v, rows, partials, gate);                        \
     QCB_LAUNCH_CHECK();                                                                                                        \
-    *grid_out = grid;                                                                                                          \
+    *grid_out = first_slot + grid;                                                                                             \
     return QCB_OK;                                                                                                             \
   }
   QCB_GS_CASE(4, 4) QCB_GS_CASE(4, 8) QCB_GS_CASE(4, 12) QCB_GS_CASE(4, 16)

@@ -125,9 +125,11 @@ __device__ __forceinline__ uint32_t gm_spread4(uint32_t nib) { return (nib * 0x0
 // exact int32 -> double through the 2^52 bit pattern
 __device__ __forceinline__ double gm_i2d(int t) { return __hiloint2double(0x43300000, (int)((uint32_t)t ^ 0x80000000u)) - 4503601774854144.0; }
 
+// bits != NULL: the rows come packed (ceil(N / 8) bytes per row, numpy.packbits order) and v is not read — the negative phase
+// of a CD step takes v_k from the Gibbs kernel this way, 8 bytes per chain instead of 512 (N = 64).
 __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const unsigned char* __restrict__ image, const double* __restrict__ v,
-                                                                         int N, int H, int64_t rows, double* __restrict__ partials,
-                                                                         int nslots, int* __restrict__ flag) {
+                                                                         const unsigned char* __restrict__ bits, int N, int H, int64_t rows,
+                                                                         double* __restrict__ partials, int nslots, int* __restrict__ flag) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GradUmmaHeader* hd = reinterpret_cast<const GradUmmaHeader*>(smem);
   const double* hb = reinterpret_cast<const double*>(smem + GM_IMG_HB);
@@ -194,7 +196,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
     const int64_t left = rows - t * GM_TILE;
     return (uint32_t)((left < GM_TILE ? left : (int64_t)GM_TILE) * N * (int64_t)sizeof(double));
   };
-  auto tile_staged = [&](int64_t t) { return base_aligned && ((tile_bytes(t) & 15u) == 0u) && (((int64_t)GM_TILE * N) & 1) == 0; };
+  auto tile_staged = [&](int64_t t) { return bits == nullptr && base_aligned && ((tile_bytes(t) & 15u) == 0u) && (((int64_t)GM_TILE * N) & 1) == 0; };
+  const int rowbytes = packed_row_bytes(N);
+  const bool bits_wide = rowbytes == 8 && (reinterpret_cast<uintptr_t>(bits) & 7u) == 0u;
+  const uint32_t hi_mask = N >= 64 ? 0xffffffffu : ((1u << (N - 32)) - 1u);
   auto stage_fetch = [&](int64_t t) {  // one thread: bulk copies of at most 16 KB each, all completing on mbar[3]
     if (t >= ntiles || !tile_staged(t)) return;
     const uint32_t bytes = tile_bytes(t);
@@ -217,6 +222,37 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
       mbar_wait(mbar + 3, ph3);
       ph3 ^= 1u;
     }
+    if (bits != nullptr) {
+      // packed rows: lanes 0..15 fetch one row each (one 8-byte load at N > 56), undo the MSB-first bit order of the bytes and
+      // publish the two words; the column counts come from 16 broadcasts
+      uint32_t w0 = 0u, w1 = 0u;
+      const int64_t gr = r0 + 16 * warp + lane;
+      if (lane < 16 && gr < rows) {
+        const unsigned char* rp = bits + gr * rowbytes;
+        if (bits_wide) {
+          const uint2 x = *reinterpret_cast<const uint2*>(rp);
+          w0 = x.x;
+          w1 = x.y;
+        } else {
+          for (int b = 0; b < rowbytes; ++b) {
+            const uint32_t byte = rp[b];
+            if (b < 4) w0 |= byte << (8 * b);
+            else w1 |= byte << (8 * (b - 4));
+          }
+        }
+        w0 = __byte_perm(__brev(w0), 0u, 0x0123u);  // unit 8 b + i = bit 7 - i of byte b  ->  bit 8 b + i
+        w1 = __byte_perm(__brev(w1), 0u, 0x0123u) & hi_mask;
+      }
+      if (lane < 16) {
+        words[16 * warp + lane] = w0;
+        words[GM_TILE + 16 * warp + lane] = w1;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        cnt0 += (int)((__shfl_sync(0xffffffffu, w0, rr) >> lane) & 1u);
+        cnt1 += (int)((__shfl_sync(0xffffffffu, w1, rr) >> lane) & 1u);
+      }
+    } else {
 #pragma unroll 8
     for (int rr = 0; rr < 16; ++rr) {
       const int r = 16 * warp + rr;
@@ -236,6 +272,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
         words[r] = b0;
         words[GM_TILE + r] = b1;
       }
+    }
     }
     if (tid == 0) nonbinary |= *reinterpret_cast<volatile int*>(flag) != 0;  // another CTA gave up already
     if (__syncthreads_or(nonbinary)) {
@@ -399,12 +436,14 @@ size_t grad_umma_workspace_bytes() { return align_up(GM_IMAGE_BYTES, 256); }
 
 // Launches pack + kernel when the shape fits; *launched = 1 then (the caller queues the FP64 kernel behind it with the same flag).
 // img: device scratch of grad_umma_workspace_bytes(); nslots: partial slots the finalize pass will sum.
-int try_grad_reduce_umma(const AffineSpec& s, const double* v, int H, int64_t rows, double* partials, int nslots, int* flag,
-                         unsigned char* img, int* launched, cudaStream_t st) {
+bool grad_umma_shape(int N, int H, int64_t rows) { return N >= 33 && N <= 64 && H >= 33 && H <= 64 && rows >= 16384; }
+
+int try_grad_reduce_umma(const AffineSpec& s, const double* v, const unsigned char* bits, int H, int64_t rows, double* partials, int nslots,
+                         int* flag, unsigned char* img, int* launched, cudaStream_t st) {
   *launched = 0;
   const int N = s.n_in1;
   // both layers 33..64 units: below that the FP64 tensor-core kernel, whose tiles shrink with the layer, is faster (measured)
-  if (flag == nullptr || img == nullptr || H != s.n_out || N < 33 || N > 64 || H < 33 || H > 64 || rows < 16384) return QCB_OK;
+  if (flag == nullptr || img == nullptr || H != s.n_out || !grad_umma_shape(N, H, rows)) return QCB_OK;
   const int grid = sm_count() < nslots ? sm_count() : nslots;
   if (rows / grid > (int64_t)8000000) return QCB_OK;  // int32 accumulators: 255 * rows per CTA must stay below 2^31
   const size_t smem = gm_smem_bytes();
@@ -415,7 +454,7 @@ int try_grad_reduce_umma(const AffineSpec& s, const double* v, int H, int64_t ro
   }
   grad_pack_umma_kernel<<<1, 256, 0, st>>>(s, img);
   QCB_LAUNCH_CHECK();
-  grad_reduce_umma_kernel<<<grid, GM_THREADS, smem, st>>>(img, v, N, H, rows, partials, nslots, flag);
+  grad_reduce_umma_kernel<<<grid, GM_THREADS, smem, st>>>(img, v, bits, N, H, rows, partials, nslots, flag);
   QCB_LAUNCH_CHECK();
   *launched = 1;
   return QCB_OK;

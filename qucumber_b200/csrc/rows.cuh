@@ -94,6 +94,8 @@ struct SiteInfo {
 enum { ROWS_EXPLICIT = 0, ROWS_ENUM = 1, ROWS_EXPANDED = 2 };
 struct RowSrc {
   const double* v;       // ROWS_EXPLICIT: (rows, N)
+  const uint8_t* bits;   // ROWS_EXPLICIT, optional: the same rows packed (qcb.h "Compact states"); v is then SCRATCH of rows x N
+                         // doubles that is only filled (from the bits) when the tcgen05 kernel hands the batch to the FP64 kernel
   uint64_t first;        // ROWS_ENUM: index of row 0; weight = exp(-E - logZ)
   double logZ;
   const double* vb;      // ROWS_ENUM: visible bias

@@ -36,6 +36,20 @@ __global__ void __launch_bounds__(256) unpack_states_kernel(const uint8_t* __res
   }
 }
 
+// the same, but only when *flag != 0: queued between the tcgen05 gradient kernel (packed rows) and its FP64 stand-in, which
+// needs float64 rows in the rare case that it has to redo the batch (no host synchronisation, capturable)
+__global__ void __launch_bounds__(256) unpack_states_if_kernel(const int* __restrict__ flag, const uint8_t* __restrict__ bits, int64_t rows,
+                                                               int N, double* __restrict__ v) {
+  if (*flag == 0) return;
+  const int rowbytes = packed_row_bytes(N);
+  const int64_t total = rows * N;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / N;
+    const int j = (int)(idx - r * N);
+    v[idx] = ((bits[r * rowbytes + (j >> 3)] >> (7 - (j & 7))) & 1u) ? 1.0 : 0.0;
+  }
+}
+
 // v0 ~ Bernoulli(1/2): unit j of chain c = bit j % 32 of word j / 32 of Philox call (chain id, sweep0, stream 5, call 0)
 __global__ void __launch_bounds__(256) philox_init_states_kernel(double* __restrict__ v, int64_t C, int N, uint32_t key0, uint32_t key1,
                                                                  uint64_t chain_id0, uint32_t sweep0) {
@@ -68,6 +82,13 @@ int run_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, cudaStr
 int run_unpack_states(const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st) {
   if (rows == 0) return QCB_OK;
   unpack_states_kernel<<<grid_for(rows * N), 256, 0, st>>>(bits, rows, N, v);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+int run_unpack_states_if(const int* flag, const uint8_t* bits, int64_t rows, int N, double* v, cudaStream_t st) {
+  if (rows == 0) return QCB_OK;
+  unpack_states_if_kernel<<<grid_for(rows * N), 256, 0, st>>>(flag, bits, rows, N, v);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
 }

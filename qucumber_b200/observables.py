@@ -26,22 +26,29 @@ def _is_wavefunction(nn_state):
     return hasattr(nn_state, "phase")
 
 
-def _importance_sampled_pauli(nn_state, samples, axis):
-    """The reference's loop over flipped copies (pauli.py:62-83, 113-135) for states without a psi(v) factorisation
-    (DensityMatrix: weights rho(v^(i), v) / rho(v, v)); every call inside is one of the drop-in's CUDA paths."""
+def _importance_sampled_pauli(nn_state, samples, axis, max_rows=1 << 22):
+    """(1/N) sum_i Re[c_i rho(v^(i), v) / rho(v, v)] (pauli.py:62-83, 113-135) for states without a psi(v) factorisation
+    (DensityMatrix). The reference loops over the sites; here all N single-flip copies of a block of samples form ONE batch
+    (N, rows, N), so each of the drop-in's CUDA paths inside rho() runs once per block instead of once per site."""
     from .utils import cplx
 
-    denom = nn_state.importance_sampling_denominator(samples)
-    numer_sum = torch.zeros_like(denom)
-    for i in range(samples.shape[-1]):
-        flipped = samples.clone()
-        flipped[..., i].sub_(1).abs_()
-        numer = nn_state.importance_sampling_numerator(flipped, samples)
-        if axis == "Y":
-            coeff = samples[..., i].mul(2.0).sub(1.0)
-            numer = cplx.elementwise_mult(numer, cplx.make_complex(torch.zeros_like(coeff), coeff))
-        numer_sum.add_(numer)
-    return cplx.real(cplx.elementwise_division(numer_sum, denom)).div_(samples.shape[-1])
+    n = samples.shape[-1]
+    flat = samples.reshape(-1, n)
+    out = torch.empty(flat.shape[0], dtype=torch.double, device=flat.device)
+    flips = torch.eye(n, dtype=torch.double, device=flat.device).unsqueeze(1)  # (N, 1, N): copy i flips unit i
+    block = max(1, max_rows // n)
+    for first in range(0, flat.shape[0], block):  # bounded scratch: n * block rows at a time
+        v = flat[first:first + block]
+        denom = nn_state.importance_sampling_denominator(v)
+        tiled = v.unsqueeze(0).expand(n, -1, -1)
+        flipped = (tiled - flips).abs_()  # |v - e_i|: unit i flipped, the others unchanged
+        numer = nn_state.importance_sampling_numerator(flipped.reshape(-1, n), tiled.reshape(-1, n))
+        numer = numer.reshape(2, n, v.shape[0])
+        if axis == "Y":  # coefficient i (2 v_i - 1) per site
+            coeff = v.t().mul(2.0).sub(1.0)
+            numer = cplx.make_complex(-cplx.imag(numer) * coeff, cplx.real(numer) * coeff)
+        out[first:first + block] = cplx.real(cplx.elementwise_division(numer.sum(1), denom)).div_(n)
+    return out.reshape(samples.shape[:-1])
 
 
 class _Estimator:

@@ -83,9 +83,30 @@ def fidelity(nn_state, target, space=None, **kwargs):
         return cplx.absolute_value(F).pow_(2).item()
     assert target.dim() == 3, "target must be a complex matrix!"
     rho = nn_state.rho(space, space) / Z
-    prod = np.matmul(cplx.numpy(target), cplx.numpy(rho))
-    eigvals = np.abs(np.linalg.eigvals(prod).real)  # the tiny negative ones are round-off
-    return float(np.sum(np.sqrt(eigvals)) ** 2)
+    return _mixed_state_fidelity(target.to(torch.double), rho)
+
+
+def _mixed_state_fidelity(target, rho):
+    """(tr sqrt(sqrt(sigma) rho sqrt(sigma)))^2 of two density matrices given as (2, D, D) re/im planes, on the device that
+    holds them. The reference takes the eigenvalues of the NON-Hermitian product sigma rho on the host
+    (training_statistics.py:63-76); the same spectrum belongs to the Hermitian matrix sqrt(sigma) rho sqrt(sigma), which two
+    symmetric eigensolves (cuSOLVER through torch.linalg.eigh) give without leaving the GPU and without complex round-off in
+    the eigenvalues. Negative eigenvalues are round-off and enter by absolute value, as in the reference; eigenvalues of
+    round-off size are dropped before the square root (the reference keeps them, which costs it ~1e-8 absolute on
+    rank-deficient targets: sqrt(1e-17) per null direction)."""
+    sigma = torch.complex(target[0], target[1])
+    r = torch.complex(rho[0], rho[1])
+    dim = sigma.shape[-1]
+
+    def spectrum(w):  # |w|, with round-off-sized entries (below dim * eps * largest) set to zero before the square root
+        w = w.abs()
+        return torch.where(w < w.max() * (dim * torch.finfo(torch.double).eps), torch.zeros_like(w), w)
+
+    w, vec = torch.linalg.eigh(0.5 * (sigma + sigma.mH))
+    root = (vec * spectrum(w).sqrt().to(vec.dtype)) @ vec.mH
+    m = root @ r @ root
+    ev = spectrum(torch.linalg.eigvalsh(0.5 * (m + m.mH)))
+    return float(ev.sqrt().sum() ** 2)
 
 
 def NLL(nn_state, samples, space=None, sample_bases=None, **kwargs):

@@ -258,6 +258,43 @@ def test_cd_step_matches_oracle_philox(lib, cuda):
     assert np.array_equal(tn.cpu().numpy(), neg)
 
 
+@pytest.mark.parametrize("n,nh,k,wscale", [(64, 64, 3, None), (40, 50, 2, None), (57, 33, 1, None), (64, 64, 2, 12.0)])
+def test_cd_step_packed_vk_matches_oracle(lib, cuda, n, nh, k, wscale):
+    """Round 2: where the integer-filter Gibbs kernels and the tcgen05 gradient kernel both take the shape (33..64 units,
+    >= 16384 chains), v_k travels between them PACKED inside qcb_rbm_cd_step (ceil(N / 8) bytes per chain). Same gate as the
+    float64-row path: the oracle's Philox chains and its gradients at 1e-10, elementwise. Row widths that are not whole words
+    (N = 40, 57) exercise the byte-wise loader; the last case has weights the two fixed-point groups cannot hold (max|W| > 8):
+    the tcgen05 kernel raises its flag, the rows are unpacked on the device and the FP64 kernel redoes the batch."""
+    from qucumber_b200 import BinaryRBM, _lib
+
+    B, C = 1000, 16384 + 37  # ragged last tile
+    W, b, c = make_binary_params(n, nh, 1300 + n + nh, weight_scale=wscale)
+    if wscale is not None:
+        assert np.abs(W).max() > 8.0
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    o = BinaryRBMOracle(W, b, c)
+    pos, neg = random_states(B, n, 1302), random_states(C, n, 1303)
+    vk = o.gibbs_steps_philox(k, neg, seed=4242, chain_id0=5, sweep0=2)
+    want = o.effective_energy_gradient(pos) / B - o.effective_energy_gradient(vk) / C
+    args, keep = rbm._param_args()
+    tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+    g = torch.empty(rbm.num_pars, dtype=torch.double, device=cuda)
+    ws = _lib.workspace(cuda, _lib.workspace_bytes(_lib.OP_CD_STEP, n, nh, 0, max(B, C)))
+    _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, k, 4242, 5, 2, 1.0 / B, -1.0 / C, _lib.ptr(g), _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    assert_close(g, want, what=f"CD-{k} gradient with packed v_k ({n} x {nh})")
+    assert np.array_equal(tn.cpu().numpy(), neg)
+    # the same call with the float64-row route forced (FP64 gradient kernels only) gives the same vector
+    g2 = torch.empty_like(g)
+    lib.qcb_set_grad_reduce_mode(1)
+    try:
+        _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(tp), B, _lib.ptr(tn), C, k, 4242, 5, 2, 1.0 / B, -1.0 / C, _lib.ptr(g2),
+                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    finally:
+        lib.qcb_set_grad_reduce_mode(0)
+    assert_close(g, g2.cpu().numpy(), what="packed v_k route == float64-row route")
+
+
 @pytest.mark.parametrize("n,nh,B,C,pb,nb_,k", [(7, 5, 53, 90, 10, 17, 2), (10, 10, 230, 460, 100, 200, 3), (20, 30, 64, 64, 16, 16, 2),
                                                 (32, 32, 40, 40, 40, 40, 1), (48, 40, 300, 520, 100, 200, 2),
                                                 (64, 64, 260, 260, 130, 130, 2), (33, 64, 50, 70, 25, 35, 1), (64, 33, 9, 9, 4, 4, 3)])
@@ -833,3 +870,46 @@ def test_gradient_reduce_small_layers_large_batch(lib, cuda, n, nh):
     _lib.check(lib.qcb_rbm_grad_reduce(*args, _lib.ptr(tv), 8192, -0.25, _lib.ptr(g), 1, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(cuda)),
                "qcb_rbm_grad_reduce")
     assert_close(g, 2.0 - 0.25 * want, what="small-layer gradient, scale and accumulate")
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (12, 16), (5, 3), (8, 13)])
+def test_gradient_reduce_histogram_path(lib, cuda, n, nh):
+    """Round 2: small visible layers (N <= 12) with >= 16 * 2^N binary rows are counted (state histogram + one weighted pass
+    over the 2^N states, grad_reduce_small.cu) instead of streamed. Same 1e-10 gate against the oracle on uniform rows, on
+    concentrated distributions (every row equal; 90 % one state — the warp-aggregated counters), on a ragged row count, with
+    one non-binary entry in the last row (device-side hand-over to the streaming kernel), and equal to the streaming kernel."""
+    rbm, orc = _pair(n, nh, 1401, cuda)
+    rows = (16 << n) + 4099
+    rng = np.random.default_rng(1402)
+    v = random_states(rows, n, 1403)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), orc.effective_energy_gradient(v), what="histogram path, uniform rows")
+    same = np.repeat(random_states(1, n, 1404), rows, axis=0)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(same, device=cuda)), orc.effective_energy_gradient(same), what="histogram path, one state")
+    skew = np.where(rng.random((rows, 1)) < 0.9, same, v)
+    want = orc.effective_energy_gradient(skew)
+    got = rbm.effective_energy_gradient(torch.tensor(skew, device=cuda))
+    assert_close(got, want, what="histogram path, 90 % one state")
+    lib.qcb_set_grad_reduce_mode(3)
+    try:
+        streamed = rbm.effective_energy_gradient(torch.tensor(skew, device=cuda))
+    finally:
+        lib.qcb_set_grad_reduce_mode(0)
+    assert_close(got, streamed.cpu().numpy(), what="histogram path == streaming kernel")
+    odd = skew.copy()
+    odd[-1, n - 1] = 0.5
+    assert_close(rbm.effective_energy_gradient(torch.tensor(odd, device=cuda)), orc.effective_energy_gradient(odd),
+                 what="histogram path, non-binary row handed to the streaming kernel")
+
+
+def test_gradient_reduce_histogram_path_purification(lib, cuda):
+    """The same for a PurificationRBM (stacked [W; U], gradient order [W, U, b, c, d])."""
+    from helpers import load_purification, make_purification_params
+    from oracle.rbm_oracle import PurificationRBMOracle
+    from qucumber_b200 import PurificationRBM
+
+    n, nh, na = 6, 5, 4
+    W, U, b, c, d = make_purification_params(n, nh, na, 1410)
+    rbm = load_purification(PurificationRBM(n, nh, na, gpu=True), W, U, b, c, d)
+    v = random_states(5000, n, 1411)
+    assert_close(rbm.effective_energy_gradient(torch.tensor(v, device=cuda)), PurificationRBMOracle(W, U, b, c, d).effective_energy_gradient(v),
+                 what="histogram path, purification RBM")

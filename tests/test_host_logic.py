@@ -448,3 +448,31 @@ def test_checkpoint_loader_prefers_tensors_only(tmp_path):
 
 class SimpleNamespaceForPickle:
     """A module-level class: picklable, and not on torch's tensors-only allowlist."""
+
+
+def test_mixed_state_fidelity_formula():
+    """The Hermitian two-eigensolve form of the mixed-state fidelity against the reference's eigvals(sigma rho) recipe
+    (training_statistics.py:63-76) on full-rank matrices (1e-12), and against <psi|rho|psi> for a pure target, where the
+    reference's own round-off is ~1e-8."""
+    from qucumber_b200.utils.training_statistics import _mixed_state_fidelity
+
+    rng = np.random.default_rng(11)
+
+    def density(dim, rank):
+        a = rng.normal(size=(dim, rank)) + 1j * rng.normal(size=(dim, rank))
+        m = a @ a.conj().T
+        return m / np.trace(m).real
+
+    def planes(m):
+        return torch.tensor(np.stack([m.real, m.imag]))
+
+    for dim in (2, 4, 16, 32):
+        sigma, rho = density(dim, dim), density(dim, dim)
+        ref = np.sum(np.sqrt(np.abs(np.linalg.eigvals(sigma @ rho).real))) ** 2
+        assert abs(_mixed_state_fidelity(planes(sigma), planes(rho)) - ref) <= 1e-12 * ref
+    psi = rng.normal(size=(16, 1)) + 1j * rng.normal(size=(16, 1))
+    psi /= np.linalg.norm(psi)
+    rho = density(16, 16)
+    truth = (psi.conj().T @ rho @ psi).real.item()
+    assert abs(_mixed_state_fidelity(planes(psi @ psi.conj().T), planes(rho)) - truth) <= 1e-13 * truth
+    assert abs(_mixed_state_fidelity(planes(rho), planes(rho)) - 1.0) <= 1e-12
