@@ -61,11 +61,17 @@ static size_t rows_affine_smem(const AffineSpec& s) {
   return ((size_t)s.n_out * (nin | 1) + s.n_out + nin + (size_t)ROWS_WARPS * nin) * sizeof(double);
 }
 
+// layers beyond the shared-memory-resident kernels: row-tiled kernels with the weights in global memory (large.cu)
+int run_rows_affine_tiled(int mode, const AffineSpec& s, const double* x, const double* x2, const double* vb, int64_t rows, double* out,
+                          cudaStream_t st);
+int run_grad_batch_tiled(const StackedParams& p, const double* v, int64_t rows, double* g_rows, cudaStream_t st);
+int run_flip_logratio_tiled(const StackedParams& p, const double* v, int64_t rows, double* out, cudaStream_t st);
+
 template <int MODE>
 static int launch_rows_affine(const AffineSpec& s, const double* x, const double* x2, const double* vb, int64_t rows,
                               double* out, cudaStream_t st) {
   const size_t smem = rows_affine_smem(s);
-  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "layer %d x %d does not fit in shared memory", s.n_out, s.n_in());
+  if (smem > SMEM_LIMIT) return run_rows_affine_tiled(MODE, s, x, x2, vb, rows, out, st);
   QCB_CUDA(cudaFuncSetAttribute(rows_affine_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
   const int64_t need = (rows + ROWS_WARPS - 1) / ROWS_WARPS;
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -174,7 +180,7 @@ int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double
   if (rows == 0) return QCB_OK;
   const int N = p.N, H = p.nhid();
   const size_t smem = ((size_t)H * (N | 1) + H + (size_t)ROWS_WARPS * (N + H)) * sizeof(double);
-  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "grad_batch: layer %d x %d does not fit in shared memory", H, N);
+  if (smem > SMEM_LIMIT) return run_grad_batch_tiled(p, v, rows, g_rows, st);
   QCB_CUDA(cudaFuncSetAttribute(grad_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
   const int64_t need = (rows + ROWS_WARPS - 1) / ROWS_WARPS;
   const int64_t cap = (int64_t)sm_count() * 4;
@@ -404,7 +410,7 @@ int run_flip_logratio(const StackedParams& p, const double* v, int64_t rows, dou
     }
   }
   const size_t smem = flip_smem(N, H, tab, g, warps);
-  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "flip_logratio: layer %d x %d does not fit in shared memory", H, N);
+  if (smem > SMEM_LIMIT) return run_flip_logratio_tiled(p, v, rows, out, st);
   const int64_t groups = (rows + g.RW - 1) / g.RW;
   const int64_t need = (groups + warps - 1) / warps;
   const int64_t cap = (int64_t)sm_count() * (64 / warps);

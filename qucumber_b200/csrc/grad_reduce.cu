@@ -169,6 +169,19 @@ __global__ void grad_finalize_kernel(const double* __restrict__ partials, int np
   g[e] = accumulate ? g[e] + val : val;
 }
 
+int run_grad_finalize(const double* partials, int nparts, int G, double scale, int accumulate, int zero_from, double* g, cudaStream_t st) {
+  grad_finalize_kernel<<<(G + 255) / 256, 256, 0, st>>>(partials, nparts, G, scale, accumulate, zero_from, g);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+// layers beyond the resident kernels: large.cu
+bool grad_reduce_needs_tiled(int N, int Hc, int H, size_t resident_smem);
+size_t grad_reduce_tiled_workspace_bytes(int N, int H, int64_t rows);
+template <int SRC>
+int run_grad_reduce_tiled(const AffineSpec& s, const RowSrc& src, int H, int64_t rows, double scale, double* g, int accumulate, int zero_from,
+                          void* ws, size_t ws_bytes, cudaStream_t st);
+
 static size_t grad_reduce_smem(int N, int Hc, int H) {
   return ((size_t)round_up(Hc * (N | 1), 2) + round_up(Hc, 2) + (size_t)GR * round_up(N, 4) + (size_t)GR * round_up(H, 4) + GR + N) *
          sizeof(double);
@@ -184,7 +197,10 @@ size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows) {
   (void)rows;
   const size_t G = (size_t)nhid * N + N + nhid;
   // partials + the weight image of the tcgen05 kernel + one flag word
-  return align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256) + grad_umma_workspace_bytes() + 256;
+  const size_t resident = align_up((size_t)sm_count() * GR_MAX_CTAS_PER_SM * G * sizeof(double), 256) + grad_umma_workspace_bytes() + 256;
+  if (!grad_reduce_needs_tiled(N, nhid, nhid, grad_reduce_smem(N, nhid, nhid))) return resident;
+  const size_t tiled = grad_reduce_tiled_workspace_bytes(N, nhid, rows);  // row-tiled kernels of large.cu
+  return resident > tiled ? resident : tiled;
 }
 
 template <int SRC>
@@ -192,10 +208,11 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
                               int accumulate, int zero_from, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int N = s.n_in1, Hc = s.n_out;
   const int G = H * N + N + H;
-  if (N + H > ROWS_THREADS) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: N + nh + na = %d > %d", N + H, ROWS_THREADS);
-  if (N > 128) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: N = %d > 128", N);
   const size_t smem = grad_reduce_smem(N, Hc, H);
-  if (smem > SMEM_LIMIT) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: layer %d x %d does not fit in shared memory", H, N);
+  if (grad_reduce_needs_tiled(N, Hc, H, smem)) {  // layers beyond the resident kernels: weights stay in global memory (large.cu)
+    if (src.bits != nullptr) return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: packed rows need the tcgen05 kernel");
+    return run_grad_reduce_tiled<SRC>(s, src, H, rows, scale, g, accumulate, zero_from, ws, ws_bytes, st);
+  }
   const size_t need = grad_reduce_workspace_bytes(N, H, rows);
   if (ws == nullptr || ws_bytes < need) return fail(QCB_ERR_BAD_ARG, "grad_reduce: workspace too small (%zu < %zu)", ws_bytes, need);
   int grid = grad_reduce_grid(rows);

@@ -230,6 +230,48 @@ __global__ void cwf_weights_kernel(const double2* __restrict__ T, const double2*
   wp[r] = -((t.y * d.x - t.x * d.y) * inv);
 }
 
+// ---- layers beyond the fused amplitude kernel (nh > 32, or tables that do not fit in shared memory): the reference's own
+// structure — the energies of the expanded rows from the row-tiled kernel of large.cu, then T_i = Ut_i |psi(v_i)| e^{i phi(v_i)}
+// with |psi| = sqrt(exp(-E_am)), phi = -E_ph / 2 (nn_states/wavefunction.py:33-46, complex_wavefunction.py:129-142) ----
+int run_energy_expanded_tiled(const StackedParams& p, const Expansion& ex, int64_t row0, int64_t rows, double* E, cudaStream_t st);
+
+__global__ void cwf_combine_kernel(const double* __restrict__ Ea, const double* __restrict__ Ep, const double* __restrict__ samples, int N,
+                                   SiteInfo si, const double* __restrict__ U, int64_t rows, double2* __restrict__ T) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int S = si.S;
+  const double* srow = samples + (r >> S) * N;
+  uint32_t sigbits = 0;
+  for (int t = 0; t < S; ++t) sigbits |= (srow[si.site[t]] != 0.0 ? 1u : 0u) << t;
+  double tr, ti, sn, cs;
+  unitary_product(U, si, sigbits, (uint32_t)(r & (((int64_t)1 << S) - 1)), tr, ti);
+  const double amp = exp(-0.5 * Ea[r]);
+  sincos(-0.5 * Ep[r], &sn, &cs);
+  cmul(tr, ti, amp * cs, amp * sn);
+  T[r] = make_double2(tr, ti);
+}
+
+// D_b = sum_i T_bi: one warp per sample, lanes stride the expansion, fixed order
+__global__ void cwf_sum_kernel(const double2* __restrict__ T, int S, int64_t b0, int64_t Bc, double2* __restrict__ D, double* __restrict__ Upsi,
+                               int64_t Btotal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= Bc) return;
+  double sr = 0.0, si_ = 0.0;
+  for (int64_t i = lane; i < ((int64_t)1 << S); i += 32) {
+    const double2 t = T[(b << S) + i];
+    sr += t.x;
+    si_ += t.y;
+  }
+  sr = warp_sum(sr);
+  si_ = warp_sum(si_);
+  if (lane == 0) {
+    D[b] = make_double2(sr, si_);
+    Upsi[b0 + b] = sr;
+    Upsi[Btotal + b0 + b] = si_;
+  }
+}
+
 static int make_sites(const uint8_t* basis_host, int N, int K, SiteInfo& si, Expansion& ex) {
   si.S = 0;
   for (int j = 0; j < N; ++j) {
@@ -237,7 +279,7 @@ static int make_sites(const uint8_t* basis_host, int N, int K, SiteInfo& si, Exp
     if (basis_host[j] >= K) return fail(QCB_ERR_BAD_ARG, "rotated: basis code %d at site %d >= K = %d", basis_host[j], j, K);
     if (basis_host[j] != 0) {
       if (si.S >= ROT_MAX_S) return fail(QCB_ERR_UNSUPPORTED, "rotated: more than %d rotated sites", ROT_MAX_S);
-      si.site[si.S] = (int8_t)j;
+      si.site[si.S] = (int16_t)j;
       si.ucode[si.S] = basis_host[j];
       ex.sitepos[j] = (int8_t)si.S;
       ++si.S;
@@ -275,8 +317,10 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
                     const uint8_t* basis_host, const double* unitaries, int K, double* Upsi, double* g_am, double* g_ph,
                     void* ws, size_t ws_bytes, cudaStream_t st) {
   const int N = am.N, nh = am.nh;
-  if (N > 128) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: N = %d > 128", N);
-  if (nh > 32) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: nh = %d > 32", nh);
+  if (N > ROT_MAX_N) return fail(QCB_ERR_UNSUPPORTED, "cwf_rotated: N = %d > %d", N, ROT_MAX_N);
+  // the fused Gray-walk amplitude kernel keeps six N x NHT tables in shared memory and 2 NHT pre-activations in registers
+  const int NHT = nh <= 8 ? 8 : (nh <= 16 ? 16 : 32);
+  const bool fused_amp = nh <= 32 && ((size_t)6 * N * NHT + 2 * NHT + 2 * round_up(N, 2) + (size_t)K * 8 + 2 * CWF_THREADS + 4 * N) * sizeof(double) <= SMEM_LIMIT;
   SiteInfo si{};
   Expansion ex{};
   int rc = make_sites(basis_host, N, K, si, ex);
@@ -295,7 +339,16 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
   for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
     const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
     const int64_t rows = Bc << S;
-    if (nh <= 8) rc = launch_cwf_amp<8>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
+    if (!fused_amp) {
+      ex.samples = samples + b0 * N;
+      rc = run_energy_expanded_tiled(am, ex, 0, rows, wa, st);  // the weight buffers hold the energies until the weights are formed
+      if (rc == QCB_OK) rc = run_energy_expanded_tiled(ph, ex, 0, rows, wp, st);
+      if (rc != QCB_OK) return rc;
+      cwf_combine_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(wa, wp, samples + b0 * N, N, si, unitaries, rows, T);
+      QCB_LAUNCH_CHECK();
+      cwf_sum_kernel<<<(unsigned)((Bc + 7) / 8), 256, 0, st>>>(T, S, b0, Bc, D, Upsi, B);
+      QCB_LAUNCH_CHECK();
+    } else if (nh <= 8) rc = launch_cwf_amp<8>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
     else if (nh <= 16) rc = launch_cwf_amp<16>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
     else rc = launch_cwf_amp<32>(am, ph, samples, b0, Bc, si, unitaries, K, T, D, Upsi, B, st);
     if (rc != QCB_OK) return rc;
@@ -463,7 +516,7 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
                    const uint8_t* basis_host, const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
   const int N = am.N, nh = am.nh, na = am.na;
-  if (N > 128) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: N = %d > 128", N);
+  if (N > ROT_MAX_N) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: N = %d > %d", N, ROT_MAX_N);
   if (na > DM_MAX_NA) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: na = %d > %d", na, DM_MAX_NA);
   SiteInfo si{};
   Expansion ex{};

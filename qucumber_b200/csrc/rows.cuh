@@ -68,12 +68,14 @@ inline AffineSpec hidden_only_spec(const StackedParams& p) {
   return s;
 }
 
+constexpr int ROT_MAX_N = 512;  // visible units of a state with rotated-basis data (the site tables travel as kernel arguments)
+
 // Expansion of measured samples over their rotated sites (utils/unitaries.py:154-181): row
 // r = b * 2^S + i is sample b with rotated site number t set to bit (i >> (S-1-t)) & 1.
 struct Expansion {
   const double* samples;   // (B, N)
   int N, S;
-  int8_t sitepos[128];     // visible unit -> index among the rotated sites, or -1
+  int8_t sitepos[ROT_MAX_N];  // visible unit -> index among the rotated sites, or -1
   __device__ __forceinline__ double value(int64_t row, int j) const {
     const int64_t b = row >> S;
     const int t = sitepos[j];
@@ -86,7 +88,7 @@ struct Expansion {
 // The rotated sites of a measurement basis (utils/unitaries.py:154-181)
 struct SiteInfo {
   int S;
-  int8_t site[32];    // rotated site t -> visible unit
+  int16_t site[32];   // rotated site t -> visible unit
   uint8_t ucode[32];  // rotated site t -> unitary code
 };
 

@@ -18,7 +18,7 @@ class ComplexWaveFunction(WaveFunctionBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
-    _rotated_limits = (("num_hidden", 32, "num_hidden"), ("num_visible", 128, "num_visible"))
+    _rotated_limits = (("num_visible", 512, "num_visible"),)  # larger hidden layers take the row-tiled kernels (csrc/large.cu)
     _max_rotated_sites = 21
 
     def __init__(self, num_visible, num_hidden=None, unitary_dict=None, gpu=True, module=None):

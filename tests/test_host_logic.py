@@ -393,15 +393,15 @@ def test_rotated_shape_limits_raise_before_training():
     not with QCB_ERR_UNSUPPORTED on the first rotated batch."""
     from qucumber_b200 import ComplexWaveFunction, DensityMatrix
 
-    big = ComplexWaveFunction(40, gpu=False)  # default num_hidden = num_visible = 40 > 32
-    z_only = np.array([["Z"] * 40] * 3)
+    big = ComplexWaveFunction(600, 4, gpu=False)  # the site tables of the rotated-basis kernels hold 512 visible units
+    z_only = np.array([["Z"] * 600] * 3)
     big._validate_rotated_shapes(z_only)  # reference-basis data needs no rotated kernel
     rotated = z_only.copy()
     rotated[1, 5] = "X"
-    with pytest.raises(ValueError, match="num_hidden <= 32"):
+    with pytest.raises(ValueError, match="num_visible <= 512"):
         big._validate_rotated_shapes(rotated)
-    ok = ComplexWaveFunction(40, 32, gpu=False)
-    ok._validate_rotated_shapes(rotated)
+    ok = ComplexWaveFunction(40, gpu=False)  # default num_hidden = 40 > 32: the row-tiled kernels take it
+    ok._validate_rotated_shapes(rotated[:, :40])
     many = np.array([["X"] * 22 + ["Z"] * 18])
     with pytest.raises(ValueError, match="at most 21 non-Z sites"):
         ok._validate_rotated_shapes(many)

@@ -1,0 +1,160 @@
+"""GPU parity of the row-tiled kernels for layers beyond the shared-memory-resident ones (csrc/large.cu): the reference has no
+size limits (rbm/binary_rbm.py:48-72), so energies, conditionals, gradients (reduced and per row), single-flip log-ratios,
+block Gibbs and the rotated-basis gradients of wide layers are held to the same gates as the fused kernels: 1e-10 against the
+CPU oracle, samples bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, load_binary, load_purification, make_binary_params, make_purification_params, random_states
+from oracle import rbm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _binary(n, nh, seed):
+    from qucumber_b200 import BinaryRBM
+
+    W, b, c = make_binary_params(n, nh, seed)
+    return load_binary(BinaryRBM(n, nh, gpu=True), W, b, c), orc.BinaryRBMOracle(W, b, c)
+
+
+@pytest.mark.parametrize("n,nh", [(200, 180), (300, 40), (30, 700), (129, 129), (767, 35)])
+def test_large_binary_rbm_energy_conditionals_gradients(lib, cuda, n, nh):
+    rbm, o = _binary(n, nh, 2001)
+    v = random_states(261, n, 2002)
+    tv = torch.tensor(v, device=cuda)
+    assert_close(rbm.effective_energy(tv), o.effective_energy(v), what="energy")
+    assert_close(rbm.prob_h_given_v(tv), o.prob_h_given_v(v), what="p(h|v)")
+    h = random_states(77, nh, 2003)
+    assert_close(rbm.prob_v_given_h(torch.tensor(h, device=cuda)), o.prob_v_given_h(h), what="p(v|h)")
+    assert_close(rbm.effective_energy_gradient(tv), o.effective_energy_gradient(v), what="reduced gradient")
+    vr = np.random.default_rng(2004).standard_normal((33, n))
+    assert_close(rbm.effective_energy(torch.tensor(vr, device=cuda)), o.effective_energy(vr), what="energy, real rows")
+    assert_close(rbm.effective_energy_gradient(torch.tensor(vr, device=cuda)), o.effective_energy_gradient(vr), what="reduced gradient, real rows")
+    if n * nh <= 40_000:
+        assert_close(rbm.effective_energy_gradient(tv[:5], reduce=False), o.effective_energy_gradient(v[:5], reduce=False), what="per-row gradient")
+
+
+def test_large_reduced_gradient_many_rows_and_accumulate(lib, cuda):
+    """More rows than one chunk's row splits, a ragged tail, and scale / accumulate through the C ABI."""
+    from qucumber_b200 import _lib
+
+    n, nh, rows = 150, 140, 20_011
+    rbm, o = _binary(n, nh, 2011)
+    v = random_states(rows, n, 2012)
+    tv = torch.tensor(v, device=cuda)
+    want = o.effective_energy_gradient(v)
+    assert_close(rbm.effective_energy_gradient(tv), want, what="reduced gradient (20k rows)")
+    args, keep = rbm._param_args()
+    g = torch.full((rbm.num_pars,), 3.0, dtype=torch.double, device=cuda)
+    ws = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_GRAD_REDUCE, n, nh, 0, rows))
+    _lib.check(lib.qcb_rbm_grad_reduce(*args, _lib.ptr(tv), rows, -0.5, _lib.ptr(g), 1, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(cuda)),
+               "qcb_rbm_grad_reduce")
+    assert_close(g, 3.0 - 0.5 * want, what="scale and accumulate")
+
+
+def test_large_purification_rbm(lib, cuda):
+    from qucumber_b200 import PurificationRBM
+
+    n, nh, na = 140, 120, 90
+    pr = make_purification_params(n, nh, na, 2021)
+    rbm, o = load_purification(PurificationRBM(n, nh, na, gpu=True), *pr), orc.PurificationRBMOracle(*pr)
+    v = random_states(101, n, 2022)
+    tv = torch.tensor(v, device=cuda)
+    assert_close(rbm.effective_energy(tv), o.effective_energy(v), what="energy (aux traced out)")
+    assert_close(rbm.prob_h_given_v(tv), o.prob_h_given_v(v), what="p(h|v)")
+    assert_close(rbm.prob_a_given_v(tv), o.prob_a_given_v(v), what="p(a|v)")
+    h, a = random_states(101, nh, 2023), random_states(101, na, 2024)
+    assert_close(rbm.prob_v_given_ha(torch.tensor(h, device=cuda), torch.tensor(a, device=cuda)), o.prob_v_given_ha(h, a), what="p(v|h,a)")
+    assert_close(rbm.effective_energy_gradient(tv), o.effective_energy_gradient(v), what="reduced gradient [W, U, b, c, d]")
+    v0 = random_states(64, n, 2025)
+    got = rbm.gibbs_steps(2, torch.tensor(v0, device=cuda), seed=91, chain_id0=3, sweep0=1)
+    assert np.array_equal(got.cpu().numpy(), o.gibbs_steps_philox(2, v0, seed=91, chain_id0=3, sweep0=1))
+
+
+@pytest.mark.parametrize("n,nh", [(200, 200), (260, 30), (40, 600)])
+def test_large_gibbs_bit_exact(lib, cuda, n, nh):
+    rbm, o = _binary(n, nh, 2031)
+    v0 = random_states(130, n, 2032)
+    got = rbm.gibbs_steps(2, torch.tensor(v0, device=cuda), seed=0xABCDEF, chain_id0=11, sweep0=4)
+    assert np.array_equal(got.cpu().numpy(), o.gibbs_steps_philox(2, v0, seed=0xABCDEF, chain_id0=11, sweep0=4))
+    u = np.random.default_rng(2033).random((2, 130, nh + n))
+    fed = rbm.gibbs_steps(2, torch.tensor(v0, device=cuda), uniforms=torch.tensor(u, device=cuda))
+    assert np.array_equal(fed.cpu().numpy(), o.gibbs_steps_fed(2, v0, u))
+
+
+@pytest.mark.parametrize("n,nh", [(200, 150), (130, 400)])
+def test_large_flip_logratio(lib, cuda, n, nh):
+    from qucumber_b200.observables import flip_logratio
+
+    rbm, o = _binary(n, nh, 2041)
+    v = random_states(23, n, 2042)
+    want = np.zeros_like(v)
+    e0 = o.effective_energy(v)
+    for i in range(n):
+        vf = v.copy()
+        vf[:, i] = 1.0 - vf[:, i]
+        want[:, i] = e0 - o.effective_energy(vf)
+    # a difference of two energies of size ~nh: the 1e-10 gate applies to the energies it is built from
+    terms = np.abs(e0)[:, None] + np.abs(e0[:, None] - want)
+    assert_close(flip_logratio(rbm, torch.tensor(v, device=cuda)), want, what="flip log-ratios", terms=terms)
+
+
+@pytest.mark.parametrize("n,nh,basis_sites", [(6, 40, (0, 3, 5)), (9, 100, (4,)), (140, 5, (1, 77, 139)), (20, 33, (0, 1, 2, 3, 4, 5, 6))])
+def test_large_complex_rotated_gradient(lib, cuda, n, nh, basis_sites):
+    """ComplexWaveFunction with more than 32 hidden units (or more than 128 visible ones): amplitudes from the row-tiled energy
+    kernel, gradients through the expanded-row reduction."""
+    from qucumber_b200 import ComplexWaveFunction
+    from qucumber_b200.utils import unitaries as un
+
+    nn = ComplexWaveFunction(n, nh, gpu=True)
+    pa = make_binary_params(n, nh, 2051, bias_scale=0.3)
+    pp = make_binary_params(n, nh, 2052, bias_scale=0.3)
+    load_binary(nn.rbm_am, *pa)
+    load_binary(nn.rbm_ph, *pp)
+    am, ph = orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp)
+    basis = ["Z"] * n
+    for t, j in enumerate(basis_sites):
+        basis[j] = "XY"[t % 2]
+    samples = random_states(13, n, 2053)
+    rg = nn.rotated_gradient(np.array(basis), torch.tensor(samples, device=cuda))
+    ga, gp = orc.complex_rotated_gradient(am, ph, basis, samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude)")
+    assert_close(rg[1], gp, what="rotated grad (phase)")
+    Upsi = un.rotate_psi_inner_prod(nn, np.array(basis), torch.tensor(samples, device=cuda)).cpu().numpy()
+    want = orc.rotate_psi_inner_prod(lambda x: orc.psi_complex(am, ph, x), basis, samples)
+    assert_close(Upsi[0] + 1j * Upsi[1], want, what="Upsi")
+
+
+def test_large_density_matrix_wide_visible_layer(lib, cuda):
+    """DensityMatrix with more than 128 visible units: the site tables and the expanded-row reduction of large.cu."""
+    from qucumber_b200 import DensityMatrix
+
+    n, nh, na = 135, 6, 4
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    pa = make_purification_params(n, nh, na, 2061, bias_scale=0.3)
+    pp = make_purification_params(n, nh, na, 2062, bias_scale=0.3)
+    load_purification(nn.rbm_am, *pa)
+    load_purification(nn.rbm_ph, *pp)
+    am, ph = orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp)
+    basis = ["Z"] * n
+    basis[2], basis[130] = "X", "Y"
+    samples = random_states(7, n, 2063)
+    rg = nn.rotated_gradient(np.array(basis), torch.tensor(samples, device=cuda))
+    ga, gp = orc.dm_rotated_gradient(am, ph, basis, samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude)")
+    assert_close(rg[1], gp, what="rotated grad (phase)")
+
+
+def test_large_positive_wavefunction_fit_step(lib, cuda):
+    """A CD-k training step on a 200 x 200 PositiveWaveFunction runs end to end (Gibbs through the composed path, both
+    gradient phases through the row-tiled reduction) and moves the parameters by -lr * gradient."""
+    import qucumber_b200 as qb
+
+    n = 200
+    nn = qb.PositiveWaveFunction(n, n, gpu=True)
+    data = torch.tensor(random_states(64, n, 2071))
+    before = nn.rbm_am.weights.detach().clone()
+    nn.fit(data, epochs=1, pos_batch_size=32, neg_batch_size=32, k=2, lr=0.01)
+    assert torch.isfinite(nn.rbm_am.weights).all() and not torch.equal(before, nn.rbm_am.weights)
