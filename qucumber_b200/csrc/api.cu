@@ -69,6 +69,7 @@ int run_exact_grad_range(const StackedParams& p, uint64_t first, uint64_t count,
 int run_grad_batch(const StackedParams& p, const double* v, int64_t rows, double* g_rows, cudaStream_t st);
 int run_flip_logratio(const StackedParams& p, const double* v, int64_t rows, double* out, cudaStream_t st);
 size_t enum_workspace_bytes();
+size_t enum_workspace_bytes_for(int nhid);
 int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
                    cudaStream_t st);
 int run_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -137,9 +138,9 @@ size_t qcb_workspace_bytes(int op, int N, int nh, int na, int64_t rows) {
     case QCB_OP_GIBBS: return gibbs_workspace_bytes_rows(N, nh + na, rows);
     case QCB_OP_ENERGY: return 0;
     case QCB_OP_GRAD_REDUCE: return grad_reduce_workspace_bytes(N, nh + na, rows);
-    case QCB_OP_LOGZ: return enum_workspace_bytes();
+    case QCB_OP_LOGZ: return enum_workspace_bytes_for(nh + na);
     case QCB_OP_EXACT_STATS: {
-      const size_t a = enum_workspace_bytes(), b = grad_reduce_workspace_bytes(N, nh + na, rows);
+      const size_t a = enum_workspace_bytes_for(nh + na), b = grad_reduce_workspace_bytes(N, nh + na, rows);
       return a > b ? a : b;
     }
     case QCB_OP_CWF_ROTATED: return cwf_workspace_bytes(N, nh, rows);

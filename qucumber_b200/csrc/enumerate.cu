@@ -533,6 +533,98 @@ static size_t enum_partials_bytes() { return align_up((size_t)enum_max_grid() * 
 
 size_t enum_workspace_bytes() { return enum_partials_bytes() + 256; }  // + flags
 
+// ---- more than 64 hidden-like units: the reference's own structure (binary_rbm.py:230-241: energies of a block of states, then
+// a log-sum-exp) in chunks of 2^20 states — energies from the row-tiled kernel of large.cu, states still generated from their
+// index, (max, sum) pairs / the five sums merged in a fixed order ----
+int run_energy_enum_tiled(const StackedParams& p, uint64_t first, int64_t rows, double* E, cudaStream_t st);
+constexpr int64_t ENUM_WIDE_CHUNK = (int64_t)1 << 20;
+constexpr int ENUM_WIDE_MAX_CHUNKS = 1 << 14;
+static size_t enum_wide_bytes() { return align_up((size_t)ENUM_WIDE_CHUNK * sizeof(double), 256) + align_up((size_t)ENUM_WIDE_MAX_CHUNKS * 2 * sizeof(double), 256); }
+size_t enum_workspace_bytes_for(int nhid) { return enum_workspace_bytes() + (pick_nht(nhid) == 0 ? enum_wide_bytes() : 0); }
+
+// the five sums of enum_kernel<.., 1> from explicit energies; block partials are stored by the first chunk and added to by the rest
+__global__ void __launch_bounds__(256) stats_from_energy_kernel(const double* __restrict__ E, int64_t n, double logZ, const double* __restrict__ t_re,
+                                                                const double* __restrict__ t_im, double* __restrict__ partials, int first_chunk) {
+  __shared__ double red[8][8];
+  double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const double eps = 0x1.0p-52;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double lp = -E[i] - logZ;
+    const double p = exp(lp);
+    sums[4] += p;
+    if (t_re != nullptr) {
+      const double tr = t_re[i], ti = t_im != nullptr ? t_im[i] : 0.0;
+      const double psi = exp(0.5 * lp);
+      sums[0] = fma(tr, psi, sums[0]);
+      sums[1] = fma(ti, psi, sums[1]);
+      const double pt = tr * tr + ti * ti;
+      sums[2] = fma(pt, log(fmin(fmax(pt, eps), 1.0 - eps)), sums[2]);
+      sums[3] = fma(pt, log(fmin(fmax(p, eps), 1.0 - eps)), sums[3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) sums[q] = warp_sum(sums[q]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int q = 0; q < 5; ++q) red[warp][q] = sums[q];
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
+    double* dst = partials + 8 * blockIdx.x + threadIdx.x;
+    *dst = first_chunk ? tot : *dst + tot;
+  }
+}
+
+static int wide_check(const StackedParams& p, uint64_t first, uint64_t count, size_t ws_bytes, const void* ws) {
+  if (p.N < 1 || p.N > 62) return fail(QCB_ERR_UNSUPPORTED, "enumeration: N=%d outside [1, 62]", p.N);
+  const uint64_t total = 1ull << p.N;
+  if (first > total || count > total - first) return fail(QCB_ERR_BAD_ARG, "enumeration: range exceeds 2^N states");
+  if (count > (uint64_t)ENUM_WIDE_CHUNK * ENUM_WIDE_MAX_CHUNKS)
+    return fail(QCB_ERR_UNSUPPORTED, "enumeration: more than 2^34 states per call with nh + na = %d > 64 (split the range)", p.nhid());
+  if (ws == nullptr || ws_bytes < enum_workspace_bytes_for(p.nhid())) return fail(QCB_ERR_BAD_ARG, "enumeration: workspace too small");
+  return QCB_OK;
+}
+
+static int run_logz_range_wide(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (int rc = wide_check(p, first, count, ws_bytes, ws)) return rc;
+  double* partials = reinterpret_cast<double*>(ws);
+  double* E = reinterpret_cast<double*>(static_cast<char*>(ws) + enum_workspace_bytes());
+  double* pairs = reinterpret_cast<double*>(reinterpret_cast<char*>(E) + align_up((size_t)ENUM_WIDE_CHUNK * sizeof(double), 256));
+  int nchunks = 0;
+  for (uint64_t done = 0; done < count; done += (uint64_t)ENUM_WIDE_CHUNK, ++nchunks) {
+    const int64_t n = (int64_t)(count - done < (uint64_t)ENUM_WIDE_CHUNK ? count - done : (uint64_t)ENUM_WIDE_CHUNK);
+    if (int rc = run_energy_enum_tiled(p, first + done, n, E, st)) return rc;
+    const int64_t need = (n + 255) / 256;
+    const int grid = (int)(need < enum_max_grid() ? need : enum_max_grid());
+    neg_lse_kernel<<<grid, 256, 0, st>>>(E, n, partials);
+    QCB_LAUNCH_CHECK();
+    lse_combine_kernel<<<1, 256, 0, st>>>(partials, grid, pairs + 2 * nchunks);
+    QCB_LAUNCH_CHECK();
+  }
+  lse_combine_kernel<<<1, 256, 0, st>>>(pairs, nchunks, out2);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
+static int run_exact_stats_range_wide(const StackedParams& p, uint64_t first, uint64_t count, double logZ, const double* t_re, const double* t_im,
+                                      double* out8, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (int rc = wide_check(p, first, count, ws_bytes, ws)) return rc;
+  double* partials = reinterpret_cast<double*>(ws);
+  double* E = reinterpret_cast<double*>(static_cast<char*>(ws) + enum_workspace_bytes());
+  const int grid = sm_count() * 4;
+  for (uint64_t done = 0; done < count; done += (uint64_t)ENUM_WIDE_CHUNK) {
+    const int64_t n = (int64_t)(count - done < (uint64_t)ENUM_WIDE_CHUNK ? count - done : (uint64_t)ENUM_WIDE_CHUNK);
+    if (int rc = run_energy_enum_tiled(p, first + done, n, E, st)) return rc;
+    stats_from_energy_kernel<<<grid, 256, 0, st>>>(E, n, logZ, t_re != nullptr ? t_re + done : nullptr, t_im != nullptr ? t_im + done : nullptr,
+                                                   partials, done == 0 ? 1 : 0);
+    QCB_LAUNCH_CHECK();
+  }
+  sums_combine_kernel<<<1, 256, 0, st>>>(partials, count > 0 ? grid : 0, out8);
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
 template <int NHT, int MODE>
 static int launch_enum(const EnumArgs& a, double* partials, int* grid_out, cudaStream_t st, const int* flags = nullptr) {
   const size_t smem = ((size_t)a.p.N * NHT + NHT + round_up(a.p.N, 2) + 8 * (ENUM_THREADS / 32)) * sizeof(double);
@@ -585,6 +677,7 @@ static int setup_enum(const StackedParams& p, uint64_t first, uint64_t count, En
 
 int run_logz_range(const StackedParams& p, uint64_t first, uint64_t count, double* out2, void* ws, size_t ws_bytes,
                    cudaStream_t st) {
+  if (pick_nht(p.nhid()) == 0) return run_logz_range_wide(p, first, count, out2, ws, ws_bytes, st);
   EnumArgs a;
   int rc = setup_enum(p, first, count, a);
   if (rc != QCB_OK) return rc;
@@ -640,6 +733,7 @@ int run_neg_logsumexp(const double* E, int64_t n, double* out2, void* ws, size_t
 
 int run_exact_stats_range(const StackedParams& p, uint64_t first, uint64_t count, double logZ, const double* t_re,
                           const double* t_im, double* out8, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (pick_nht(p.nhid()) == 0) return run_exact_stats_range_wide(p, first, count, logZ, t_re, t_im, out8, ws, ws_bytes, st);
   EnumArgs a;
   int rc = setup_enum(p, first, count, a);
   if (rc != QCB_OK) return rc;

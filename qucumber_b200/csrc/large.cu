@@ -144,6 +144,13 @@ int run_energy_expanded_tiled(const StackedParams& p, const Expansion& ex, int64
   return launch_rows_tiled<0, ROWS_EXPANDED>(stacked_hidden_spec(p), src, nullptr, p.b, row0, rows, E, 1, st);
 }
 
+// energies of the basis states first + [0, rows) (exact enumeration of layers with more than 64 hidden-like units)
+int run_energy_enum_tiled(const StackedParams& p, uint64_t first, int64_t rows, double* E, cudaStream_t st) {
+  RowSrc src{};
+  src.first = first;
+  return launch_rows_tiled<0, ROWS_ENUM>(stacked_hidden_spec(p), src, nullptr, p.b, 0, rows, E, 1, st);
+}
+
 // ---- reduced gradient -------------------------------------------------------------------------------------------------
 // G_ext = A^T B over the chunk's rows with A = [w p | aux | w] (rows x (H + 1)), B = [v | 1] (rows x (N + 1)): the weight block,
 // the hidden-bias sums (column N) and the visible-bias sums (row H) of the flat gradient [Wst (H x N) | vb (N) | hb (H)] in one

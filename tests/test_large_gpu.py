@@ -158,3 +158,45 @@ def test_large_positive_wavefunction_fit_step(lib, cuda):
     before = nn.rbm_am.weights.detach().clone()
     nn.fit(data, epochs=1, pos_batch_size=32, neg_batch_size=32, k=2, lr=0.01)
     assert torch.isfinite(nn.rbm_am.weights).all() and not torch.equal(before, nn.rbm_am.weights)
+
+
+@pytest.mark.parametrize("n,nh", [(10, 100), (12, 65), (21, 70)])
+def test_wide_hidden_layer_exact_enumeration(lib, cuda, n, nh):
+    """Exact enumeration with more than 64 hidden units (energies of index-generated states from the row-tiled kernel, chunked
+    log-sum-exp): log Z against the oracle (N = 21: more than one chunk of 2^20 states, against the chunked oracle), range
+    additivity, and fidelity / KL / exact gradients of a PositiveWaveFunction against the explicit-space evaluation."""
+    import qucumber_b200 as qb
+    from qucumber_b200.utils import training_statistics as ts
+
+    W, b, c = make_binary_params(n, nh, 2081)
+    nn = qb.PositiveWaveFunction(n, nh, gpu=True)
+    load_binary(nn.rbm_am, W, b, c)
+    o = orc.BinaryRBMOracle(W, b, c)
+    out2 = nn.rbm_am.log_partition().cpu().numpy()
+    logz = out2[0] + np.log(out2[1])
+    m, s_ = o.logz_range()
+    want = m + np.log(s_)
+    assert abs(logz - want) <= 1e-10 * abs(want), (logz, want)
+    cut = (1 << n) // 3
+    lo, hi = nn.rbm_am.log_partition(0, cut).cpu().numpy(), nn.rbm_am.log_partition(cut, (1 << n) - cut).cpu().numpy()
+    both = np.logaddexp(lo[0] + np.log(lo[1]), hi[0] + np.log(hi[1]))
+    assert abs(both - want) <= 1e-10 * abs(want)
+    if n > 12:
+        return
+    rng = np.random.default_rng(2082)
+    t = rng.standard_normal((2, 1 << n))
+    t /= np.sqrt((t ** 2).sum())
+    target = torch.tensor(t, device=cuda)
+    space = nn.generate_hilbert_space()
+    psi = np.exp(-0.5 * o.effective_energy(space.cpu().numpy()) - 0.5 * want)
+    fid = (t[0] @ psi) ** 2 + (t[1] @ psi) ** 2
+    assert abs(ts.fidelity(nn, target) - fid) <= 1e-10 * fid
+    pt = t[0] ** 2 + t[1] ** 2
+    eps = 2.0 ** -52
+    kl = np.sum(pt * np.log(np.clip(pt, eps, 1 - eps))) - np.sum(pt * np.log(np.clip(psi ** 2, eps, 1 - eps)))
+    assert abs(ts.KL(nn, target) - kl) <= 1e-10 * abs(kl)
+    data = random_states(50, n, 2083)
+    got = nn.compute_exact_gradients(torch.tensor(data, device=cuda))[0]
+    p = psi ** 2
+    exact = o.effective_energy_gradient(data) / 50 - p @ o.effective_energy_gradient(space.cpu().numpy(), reduce=False)
+    assert_close(got, exact, what="exact gradient (wide hidden layer)")
