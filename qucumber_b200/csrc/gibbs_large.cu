@@ -4,8 +4,8 @@
 // call q0 + 4 (u / 32) + (u % 16) / 4, word u % 4, 16-bit half (u / 16) % 2 of stream 0 and the low bits from two more streams)
 // or the caller's fed uniforms.  Same draws and same exact FP64 decisions as the fused kernels would make — only slower
 // (two launches and two HBM round trips of the state per conditional update, like the reference's own op chain,
-// rbm/binary_rbm.py:129-228, rbm/purification_rbm.py:196-337).  Limit: a layer's weights must fit in shared memory
-// (about 25 000 weights per conditional, e.g. 158 x 158).
+// rbm/binary_rbm.py:129-228, rbm/purification_rbm.py:196-337).  Conditionals whose weights do not fit in shared memory run
+// through the row-tiled kernel of large.cu (weights in global memory); what remains is that kernel's limit of 767 input units.
 #include "rows.cuh"
 
 namespace qcb {
