@@ -404,6 +404,10 @@ static int pick_blocks(int units) {
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 size_t gibbs_umma_workspace_bytes(int N, int nhid);
+size_t gibbs_umma_wide_workspace_bytes(int N, int nhid);
+int64_t gibbs_umma_wide_wave_chains();
+int try_gibbs_umma_wide(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                        void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
 
 size_t gibbs_large_workspace_bytes(int N, int nhid, int64_t C);
 int run_gibbs_large(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
@@ -413,7 +417,10 @@ size_t gibbs_workspace_bytes(int N, int nhid);
 
 // rows: the number of chains (only the composed path for large layers needs scratch that grows with it)
 size_t gibbs_workspace_bytes_rows(int N, int nhid, int64_t rows) {
-  if (!gibbs_fused_shape(N, nhid)) return gibbs_large_workspace_bytes(N, nhid, rows);
+  if (!gibbs_fused_shape(N, nhid)) {
+    const size_t a = gibbs_large_workspace_bytes(N, nhid, rows), w = gibbs_umma_wide_workspace_bytes(N, nhid);
+    return a > w ? a : w;
+  }
   return gibbs_workspace_bytes(N, nhid);
 }
 
@@ -421,7 +428,9 @@ size_t gibbs_workspace_bytes(int N, int nhid) {
   const int HB = pick_blocks(nhid), VB = pick_blocks(N);
   if (HB == 0 || VB == 0) return 0;
   const size_t a = align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256), b = gibbs_imma_workspace_bytes(N, nhid);
-  const size_t c = gibbs_umma_workspace_bytes(N, nhid);
+  size_t c = gibbs_umma_workspace_bytes(N, nhid);
+  const size_t w = gibbs_umma_wide_workspace_bytes(N, nhid);
+  if (w > c) c = w;
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
@@ -453,6 +462,8 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
 int g_gibbs_mode = 0;
 constexpr int GIBBS_UMMA_MIN_K = 3;  // below that the mma.sync kernel's TMA-prefetched state tiles win (k = 1: 0.29 vs 0.35 ms)
 static bool use_umma(int k) { return g_gibbs_mode == 2 || (g_gibbs_mode == 0 && k >= GIBBS_UMMA_MIN_K); }
+// layers of 65..128 units have no mma.sync filter kernel: the tcgen05 kernel (gibbs_umma_wide.cu) takes them in modes 0 and 2
+static bool use_umma_wide(int N, int nhid) { return (g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_wide_workspace_bytes(N, nhid) != 0; }
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
@@ -485,13 +496,14 @@ static int gibbs_shape_check(const StackedParams& p, int* HBo, int* VBo) {
 // integer-filter kernel does not take, one float64 copy of the chain state.
 size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
   const size_t img = gibbs_workspace_bytes_rows(N, nhid, C);
-  const bool imma = gibbs_imma_workspace_bytes(N, nhid) != 0;
+  const bool imma = gibbs_imma_workspace_bytes(N, nhid) != 0 || use_umma_wide(N, nhid);
   return img + (imma && g_gibbs_mode != 1 ? 0 : align_up((size_t)(C > 0 ? C : 0) * N * sizeof(double), 256));
 }
 
 // Chains one full wave of the persistent grid processes (slicing a host pipeline at multiples of it avoids ragged tails)
 int64_t gibbs_wave_chains(int N, int nhid) {
   if ((g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
+  if (use_umma_wide(N, nhid)) return gibbs_umma_wide_wave_chains();
   const int64_t w = gibbs_imma_wave_chains(N, nhid);
   return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
 }
@@ -511,6 +523,11 @@ int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, ui
   if (use_umma(k)) {
     int handled = 0;
     rc = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+    if (rc != QCB_OK || handled) return rc;
+  }
+  if (use_umma_wide(p.N, p.nhid())) {
+    int handled = 0;
+    rc = try_gibbs_umma_wide(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
     if (rc != QCB_OK || handled) return rc;
   }
   if (g_gibbs_mode != 1) {
@@ -548,6 +565,14 @@ int run_gibbs(const StackedParams& p, const double* v_in, double* v, int64_t C, 
 static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                           uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, int allow_imma, cudaStream_t st) {
   const int nhid = p.nhid();
+  if (uniforms == nullptr && allow_imma && k >= 1 && C > 0 && use_umma_wide(p.N, nhid) && sweep0 + (uint64_t)k <= (1ull << 32)) {
+    int handled = 0;
+    ChainIO io;
+    io.v_in = v_in;
+    io.v_out = v;
+    const int rcw = try_gibbs_umma_wide(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+    if (rcw != QCB_OK || handled) return rcw;
+  }
   if (!gibbs_fused_shape(p.N, nhid)) {  // layers beyond the fused kernels: one affine + Bernoulli pass per conditional update
     if (sweep0 + (uint64_t)k > (1ull << 32))
       return fail(QCB_ERR_BAD_ARG, "gibbs: sweep0 + k exceeds the 32-bit sweep counter of the Philox convention (use a new seed)");

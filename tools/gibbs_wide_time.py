@@ -1,0 +1,36 @@
+"""Block Gibbs on layers of 65..128 units: the tcgen05 kernel (gibbs_umma_wide.cu, mode 0) against the path these shapes took
+before (mode 1: FP64 DMMA kernel where one layer is <= 64 units, the composed affine + Bernoulli passes otherwise)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qucumber_b200 import BinaryRBM, _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda")
+C, k = 1 << 20, 10
+for (n, nh) in [(128, 128), (100, 100), (128, 64), (64, 128), (100, 40), (64, 64)]:
+    torch.manual_seed(1)
+    rbm = BinaryRBM(n, nh, gpu=True)
+    v = (torch.rand(C, n, device=dev) < 0.5).double()
+    out = {}
+    for mode in (0, 1):
+        lib.qcb_set_gibbs_mode(mode)
+        reps = 5 if mode == 0 else 2
+        for _ in range(2):
+            rbm.gibbs_steps(k, v, overwrite=True, seed=7)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            rbm.gibbs_steps(k, v, overwrite=True, seed=7)
+        e1.record()
+        torch.cuda.synchronize()
+        out[mode] = e0.elapsed_time(e1) / reps
+    lib.qcb_set_gibbs_mode(0)
+    print(f"N={n:4d} nh={nh:4d}  C=2^20 k={k}: tcgen05 {out[0]:8.3f} ms = {C * k / out[0] / 1e6:7.2f}e9 chain-sweeps/s "
+          f"({C * k * (n + nh) / out[0] / 1e6 / 1e3:6.2f}e12 unit updates/s) | mode 1 {out[1]:9.3f} ms  ({out[1] / out[0]:5.1f} x)", flush=True)
+    del v
+    torch.cuda.empty_cache()
