@@ -68,9 +68,10 @@ constexpr long long GU_WQ_MAX = 127ll * 32768 + 63 * 256 + 127;
 
 // ---- pack: quantise (same fixed point, digits and margins as gibbs_imma.cu), write the B operands ---------------
 constexpr int GU_PACK_LD = 65;
-__global__ void __launch_bounds__(256) gibbs_pack_umma_kernel(StackedParams p, unsigned char* __restrict__ img) {
+constexpr int GU_PACK_THREADS = 1024;
+__global__ void __launch_bounds__(GU_PACK_THREADS) gibbs_pack_umma_kernel(StackedParams p, unsigned char* __restrict__ img) {
   __shared__ double Ws[64 * GU_PACK_LD];
-  __shared__ double red[3][8];
+  __shared__ double red[3][GU_PACK_THREADS / 32];
   const int H = p.nhid(), N = p.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double mw = 0.0;
@@ -81,15 +82,24 @@ __global__ void __launch_bounds__(256) gibbs_pack_umma_kernel(StackedParams p, u
     mw = fmax(mw, fabs(w));
   }
   __syncthreads();
+  // |bias| + sum |w| of every output unit: 8 threads per unit (threads 0..511: hidden-like units, 512..1023: visible units)
   double rm = 0.0, cm = 0.0;
-  if (threadIdx.x < H) {
-    const int i = threadIdx.x;
-    rm = fabs(p.hbias(i));
-    for (int j = 0; j < N; ++j) rm += fabs(Ws[i * GU_PACK_LD + j]);
-  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + N) {
-    const int j = threadIdx.x - 64;
-    cm = fabs(p.b[j]);
-    for (int i = 0; i < H; ++i) cm += fabs(Ws[i * GU_PACK_LD + j]);
+  {
+    const int unit = (threadIdx.x & 511) >> 3, part = threadIdx.x & 7;
+    double acc = 0.0;
+    if (threadIdx.x < 512) {
+      if (unit < H) {
+        for (int j = part; j < N; j += 8) acc += fabs(Ws[unit * GU_PACK_LD + j]);
+        if (part == 0) acc += fabs(p.hbias(unit));
+      }
+    } else if (unit < N) {
+      for (int i = part; i < H; i += 8) acc += fabs(Ws[i * GU_PACK_LD + unit]);
+      if (part == 0) acc += fabs(p.b[unit]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (threadIdx.x < 512) rm = acc; else cm = acc;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(256) gibbs_pack_umma_kernel(StackedParams p, u
   if (lane == 0) { red[0][warp] = mw; red[1][warp] = rm; red[2][warp] = cm; }
   __syncthreads();
   double s_maxw = red[0][0], s_rowmax = red[1][0], s_colmax = red[2][0];
-  for (int w = 1; w < 8; ++w) {
+  for (int w = 1; w < GU_PACK_THREADS / 32; ++w) {
     s_maxw = fmax(s_maxw, red[0][w]);
     s_rowmax = fmax(s_rowmax, red[1][w]);
     s_colmax = fmax(s_colmax, red[2][w]);
@@ -132,25 +142,31 @@ __global__ void __launch_bounds__(256) gibbs_pack_umma_kernel(StackedParams p, u
     biasH[pi] = u < H ? (float)(-1.4426950408889634 * p.hbias(u)) : 0.0f;
     biasV[pi] = u < N ? (float)(-1.4426950408889634 * p.b[u]) : 0.0f;
   }
-  // B operands: one byte per (row n, k).  rows 0..63: output p-index n, k < 64: digit 0 of input p-index k, k >= 64: twice digit 1
-  // of input p-index k - 64 (multiplied by the 128 v copy of the state); rows 64..127: digit 2 for k < 64, zero above.
-  for (int idx = threadIdx.x; idx < 2 * 128 * 128; idx += blockDim.x) {
-    const bool hside = idx < 128 * 128;
-    const int within = hside ? idx : idx - 128 * 128;
-    const int n = within >> 7, k = within & 127;
-    const int outu = gu_unit_of_p(n & 63), inu = gu_unit_of_p(k & 63);
-    const int hid = hside ? outu : inu, vis = hside ? inu : outu;
-    int val = 0;
+  // B operands, one byte per (row n, k): the thread that owns the pair (hidden p-index ph, visible p-index pv) computes the
+  // three digits once and writes them into both images.  Bh (h | v): row ph, k = pv: digit 0; k = 64 + pv: twice digit 1 (it
+  // meets the 128 v copy of the state); row 64 + ph: digit 2 for k = pv, zero above.  Bv (v | h): the transpose.
+  unsigned char* Bh = img + GU_BH_OFF;
+  unsigned char* Bv = img + GU_BV_OFF;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int ph = idx >> 6, pv = idx & 63;
+    const int hid = gu_unit_of_p(ph), vis = gu_unit_of_p(pv);
+    int q0 = 0, q1 = 0, q2 = 0;
     if (!degenerate && hid < H && vis < N) {
       long long wq = llrint(Ws[hid * GU_PACK_LD + vis] * scale);
-      const int q0 = (int)(((wq + 128) & 255) - 128);
+      q0 = (int)(((wq + 128) & 255) - 128);
       wq = (wq - q0) >> 8;
-      const int q1 = (int)(((wq + 64) & 127) - 64);
-      const int q2 = (int)((wq - q1) >> 7);
-      if (n < 64) val = k < 64 ? q0 : 2 * q1;
-      else val = k < 64 ? q2 : 0;
+      q1 = (int)(((wq + 64) & 127) - 64);
+      q2 = (int)((wq - q1) >> 7);
     }
-    img[(hside ? GU_BH_OFF : GU_BV_OFF) + gu_operand_offset(n, k)] = (unsigned char)(val & 255);
+    const unsigned char b0 = (unsigned char)(q0 & 255), b1 = (unsigned char)((2 * q1) & 255), b2 = (unsigned char)(q2 & 255);
+    Bh[gu_operand_offset(ph, pv)] = b0;
+    Bh[gu_operand_offset(ph, 64 + pv)] = b1;
+    Bh[gu_operand_offset(64 + ph, pv)] = b2;
+    Bh[gu_operand_offset(64 + ph, 64 + pv)] = 0;
+    Bv[gu_operand_offset(pv, ph)] = b0;
+    Bv[gu_operand_offset(pv, 64 + ph)] = b1;
+    Bv[gu_operand_offset(64 + pv, ph)] = b2;
+    Bv[gu_operand_offset(64 + pv, 64 + ph)] = 0;
   }
 }
 
@@ -491,7 +507,7 @@ int try_gibbs_umma(const StackedParams& p, const ChainIO& io, int64_t C, int k, 
   const size_t need = gibbs_umma_workspace_bytes(p.N, p.nhid());
   if (need == 0 || ws == nullptr || ws_bytes < need) return QCB_OK;
   unsigned char* img = reinterpret_cast<unsigned char*>(ws);
-  gibbs_pack_umma_kernel<<<1, 256, 0, st>>>(p, img);
+  gibbs_pack_umma_kernel<<<1, GU_PACK_THREADS, 0, st>>>(p, img);
   QCB_LAUNCH_CHECK();
   GibbsUmmaArgs a;
   a.image = img;
