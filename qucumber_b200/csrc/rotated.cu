@@ -371,8 +371,9 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
 }
 
 // ================================= DensityMatrix =================================================
-constexpr int DM_MAX_NA = 16;
-constexpr int DM_MAX_S = 8;
+constexpr int DM_MAX_NA = 16;     // thread-per-row pair kernel (register arrays); wider auxiliary layers: warp per row, DM_WIDE_MAX_NA
+constexpr int DM_WIDE_MAX_NA = 256;
+constexpr int DM_MAX_S = 10;      // 4^S pairs per sample (the reference materialises (2, 2^S, 2^S, B, G) tensors)
 
 // per expanded row: [f_am, f_ph, Ut_re, Ut_im, m_am[na], m_ph[na]]
 // f = b.v + sum softplus(W v + c) (rbm/purification_rbm.py:375-381); m_am = U_am v + d_am,
@@ -477,6 +478,100 @@ __global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__
   for (int k = 0; k < na; ++k) { out[2 + k] = R[k]; out[2 + na + k] = I[k]; }
 }
 
+// The same pair sums for auxiliary layers of more than DM_MAX_NA units: a WARP per expanded row i, lane l owns the auxiliary
+// units k = l + 32 m (m < KPL); Pi is a warp sum, w_ij is formed by every lane, R_ik / I_ik stay with the lane that owns k.
+template <int KPL>
+__global__ void __launch_bounds__(256) dm_pair_wide_kernel(const double* __restrict__ feat, int na, int S, int64_t rows,
+                                                           double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  const int nexp = 1 << S;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    const int64_t b = r >> S;
+    const double* fi = feat + r * FW;
+    double xi[KPL], yi[KPL], R[KPL], I[KPL], Sr[KPL], Si[KPL];
+#pragma unroll
+    for (int m = 0; m < KPL; ++m) {
+      const int k = lane + 32 * m;
+      xi[m] = k < na ? fi[4 + k] : 0.0;
+      yi[m] = k < na ? fi[4 + na + k] : 0.0;
+      R[m] = 0.0;
+      I[m] = 0.0;
+    }
+    const double fi0 = fi[0], fi1 = fi[1], fi2 = fi[2], fi3 = fi[3];
+    double ri = 0.0, si = 0.0;
+    for (int j = 0; j < nexp; ++j) {
+      const double* fj = feat + ((b << S) + j) * FW;
+      const double gp = 0.5 * (fi0 + fj[0]);   // Gamma+ (amplitude RBM)
+      const double gm = 0.5 * (fi1 - fj[1]);   // Gamma- (phase RBM)
+      double pre = 0.0, pim = 0.0;
+#pragma unroll
+      for (int m = 0; m < KPL; ++m) {
+        const int k = lane + 32 * m;
+        Sr[m] = 0.0;
+        Si[m] = 0.0;
+        if (k < na) {
+          const double x = 0.5 * (xi[m] + fj[4 + k]);
+          const double y = 0.5 * (yi[m] - fj[4 + na + k]);
+          double sn, cs;
+          sincos(y, &sn, &cs);
+          const double ex = exp(x);
+          pre += log(sqrt(1.0 + 2.0 * ex * cs + exp(2.0 * x)));   // Pi (nn_states/density_matrix.py:143-155)
+          pim += atan2(ex * sn, 1.0 + ex * cs);
+          const double en = exp(-x);                                // complex sigmoid (utils/cplx.py:319-334)
+          const double dr = 1.0 + en * cs, di = -en * sn;
+          const double inv = 1.0 / (dr * dr + di * di);
+          Sr[m] = dr * inv;
+          Si[m] = -di * inv;
+        }
+      }
+      pre = warp_sum(pre);
+      pim = warp_sum(pim);
+      const double ampl = exp(gp + pre), phs = gm + pim;
+      double sn, cs;
+      sincos(phs, &sn, &cs);
+      double wr = fi2, wi = fi3;   // w = Ut_i conj(Ut_j) rho~
+      cmul(wr, wi, fj[2], -fj[3]);
+      cmul(wr, wi, ampl * cs, ampl * sn);
+      ri += wr;
+      si += wi;
+#pragma unroll
+      for (int m = 0; m < KPL; ++m) {
+        R[m] += wr * Sr[m] - wi * Si[m];
+        I[m] += wr * Si[m] + wi * Sr[m];
+      }
+    }
+    double* out = stats + r * SW;
+    if (lane == 0) {
+      out[0] = ri;
+      out[1] = si;
+    }
+#pragma unroll
+    for (int m = 0; m < KPL; ++m) {
+      const int k = lane + 32 * m;
+      if (k < na) {
+        out[2 + k] = R[m];
+        out[2 + na + k] = I[m];
+      }
+    }
+  }
+}
+
+static int launch_dm_pairs(const double* feat, int na, int S, int64_t rows, double* stats, cudaStream_t st) {
+  if (na <= DM_MAX_NA) {
+    dm_pair_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(feat, na, S, rows, stats);
+  } else {
+    const int64_t want = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (na <= 32) dm_pair_wide_kernel<1><<<grid, 256, 0, st>>>(feat, na, S, rows, stats);
+    else if (na <= 64) dm_pair_wide_kernel<2><<<grid, 256, 0, st>>>(feat, na, S, rows, stats);
+    else if (na <= 128) dm_pair_wide_kernel<4><<<grid, 256, 0, st>>>(feat, na, S, rows, stats);
+    else dm_pair_wide_kernel<8><<<grid, 256, 0, st>>>(feat, na, S, rows, stats);
+  }
+  QCB_LAUNCH_CHECK();
+  return QCB_OK;
+}
+
 // thread per sample: P_b = sum_i r_i (imaginary parts cancel, utils/unitaries.py:274-276)
 __global__ void dm_prob_kernel(const double* __restrict__ stats, int na, int S, int64_t B, int64_t b0, double* __restrict__ UrhoU) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,11 +600,19 @@ __global__ void dm_weights_kernel(const double* __restrict__ stats, const double
 }
 
 constexpr int64_t DM_MAX_ROWS = (int64_t)1 << 18;
+// expanded rows per chunk: 2^18, halved while the per-row scratch of a wide auxiliary layer would exceed 256 MiB
+// (never below one sample's 2^DM_MAX_S rows)
+static int64_t dm_chunk_rows(int na) {
+  const size_t per_row = (size_t)(4 + 2 * na) + (2 + 2 * na) + (2 + 2 * na);
+  int64_t rows = DM_MAX_ROWS;
+  while (rows > ((int64_t)1 << DM_MAX_S) && (size_t)rows * per_row * sizeof(double) > ((size_t)256 << 20)) rows >>= 1;
+  return rows;
+}
 
 size_t dm_workspace_bytes(int N, int nh, int na, int64_t B) {
   (void)B;
   const size_t per_row = (size_t)(4 + 2 * na) + (2 + 2 * na) + (2 + 2 * na);
-  return align_up((size_t)DM_MAX_ROWS * per_row * sizeof(double), 256) + grad_reduce_workspace_bytes(N, nh + na, 0);
+  return align_up((size_t)dm_chunk_rows(na) * per_row * sizeof(double), 256) + grad_reduce_workspace_bytes(N, nh + na, dm_chunk_rows(na));
 }
 
 int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t B,
@@ -517,7 +620,7 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
                    void* ws, size_t ws_bytes, cudaStream_t st) {
   const int N = am.N, nh = am.nh, na = am.na;
   if (N > ROT_MAX_N) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: N = %d > %d", N, ROT_MAX_N);
-  if (na > DM_MAX_NA) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: na = %d > %d", na, DM_MAX_NA);
+  if (na > DM_WIDE_MAX_NA) return fail(QCB_ERR_UNSUPPORTED, "dm_rotated: na = %d > %d", na, DM_WIDE_MAX_NA);
   SiteInfo si{};
   Expansion ex{};
   int rc = make_sites(basis_host, N, K, si, ex);
@@ -527,16 +630,17 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
   if (ws == nullptr || ws_bytes < dm_workspace_bytes(N, nh, na, B)) return fail(QCB_ERR_BAD_ARG, "dm_rotated: workspace too small");
   const int S = si.S;
   const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  const int64_t max_rows = dm_chunk_rows(na);
   double* feat = static_cast<double*>(ws);
-  double* stats = feat + DM_MAX_ROWS * FW;
-  double* wam = stats + DM_MAX_ROWS * SW;
-  double* wph = wam + DM_MAX_ROWS;
-  double* auxam = wph + DM_MAX_ROWS;
-  double* auxph = auxam + DM_MAX_ROWS * na;
+  double* stats = feat + max_rows * FW;
+  double* wam = stats + max_rows * SW;
+  double* wph = wam + max_rows;
+  double* auxam = wph + max_rows;
+  double* auxph = auxam + max_rows * na;
   const size_t per_row = (size_t)FW + SW + SW;
-  void* gws = static_cast<char*>(ws) + align_up((size_t)DM_MAX_ROWS * per_row * sizeof(double), 256);
-  const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh + na, 0);
-  const int64_t chunkB = DM_MAX_ROWS >> S;
+  void* gws = static_cast<char*>(ws) + align_up((size_t)max_rows * per_row * sizeof(double), 256);
+  const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh + na, max_rows);
+  const int64_t chunkB = max_rows >> S;
   for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
     const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
     const int64_t rows = Bc << S;
@@ -544,8 +648,8 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
     const int64_t fgrid = (rows + 7) / 8;
     dm_feat_kernel<<<(unsigned)(fgrid < 65535 ? fgrid : 65535), 256, 0, st>>>(am, ph, ex, si, unitaries, rows, feat);
     QCB_LAUNCH_CHECK();
-    dm_pair_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(feat, na, S, rows, stats);
-    QCB_LAUNCH_CHECK();
+    rc = launch_dm_pairs(feat, na, S, rows, stats, st);
+    if (rc != QCB_OK) return rc;
     dm_prob_kernel<<<(unsigned)((Bc + 127) / 128), 128, 0, st>>>(stats, na, S, Bc, b0, UrhoU);
     QCB_LAUNCH_CHECK();
     if (g_am == nullptr) continue;

@@ -14,8 +14,8 @@ class DensityMatrix(NeuralStateBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
-    _rotated_limits = (("num_aux", 16, "num_aux"), ("num_visible", 512, "num_visible"))
-    _max_rotated_sites = 8  # 4^S pairs per sample
+    _rotated_limits = (("num_aux", 256, "num_aux"), ("num_visible", 512, "num_visible"))
+    _max_rotated_sites = 10  # 4^S pairs per sample
 
     def __init__(self, num_visible, num_hidden=None, num_aux=None, unitary_dict=None, gpu=True, module=None):
         if module is not None:

@@ -405,12 +405,14 @@ def test_rotated_shape_limits_raise_before_training():
     many = np.array([["X"] * 22 + ["Z"] * 18])
     with pytest.raises(ValueError, match="at most 21 non-Z sites"):
         ok._validate_rotated_shapes(many)
-    dm = DensityMatrix(20, gpu=False)  # default num_aux = 20 > 16
-    with pytest.raises(ValueError, match="num_aux <= 16"):
-        dm._validate_rotated_shapes(np.array([["X"] + ["Z"] * 19]))
+    dm = DensityMatrix(20, gpu=False)  # default num_aux = 20 > 16: the warp-per-row pair kernel takes it
+    dm._validate_rotated_shapes(np.array([["X"] + ["Z"] * 19]))
+    dm = DensityMatrix(4, 4, 300, gpu=False)
+    with pytest.raises(ValueError, match="num_aux <= 256"):
+        dm._validate_rotated_shapes(np.array([["X"] + ["Z"] * 3]))
     dm = DensityMatrix(12, 12, 12, gpu=False)
-    with pytest.raises(ValueError, match="at most 8 non-Z sites"):
-        dm._validate_rotated_shapes(np.array([["Y"] * 9 + ["Z"] * 3]))
+    with pytest.raises(ValueError, match="at most 10 non-Z sites"):
+        dm._validate_rotated_shapes(np.array([["Y"] * 11 + ["Z"]]))
 
 
 def test_full_space_fast_path_only_for_the_canonical_enumeration():

@@ -147,6 +147,51 @@ def test_large_density_matrix_wide_visible_layer(lib, cuda):
     assert_close(rg[1], gp, what="rotated grad (phase)")
 
 
+@pytest.mark.parametrize("n,nh,na,sites", [(5, 4, 17, (0, 3)), (6, 5, 40, (1, 2, 4)), (4, 3, 100, (2,)), (3, 2, 200, (0, 1, 2)), (20, 20, 20, (7, 11))])
+def test_density_matrix_wide_auxiliary_layer(lib, cuda, n, nh, na, sites):
+    """DensityMatrix with more than 16 auxiliary units (the default DensityMatrix(N) has num_aux = N): pair sums by the
+    warp-per-row kernel of rotated.cu, weighted reductions with na auxiliary features per expanded row."""
+    from qucumber_b200 import DensityMatrix
+
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    pa = make_purification_params(n, nh, na, 2071, bias_scale=0.3)
+    pp = make_purification_params(n, nh, na, 2072, bias_scale=0.3)
+    load_purification(nn.rbm_am, *pa)
+    load_purification(nn.rbm_ph, *pp)
+    am, ph = orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp)
+    basis = ["Z"] * n
+    for t, s in enumerate(sites):
+        basis[s] = "XY"[t % 2]
+    samples = random_states(9, n, 2073)
+    rg = nn.rotated_gradient(np.array(basis), torch.tensor(samples, device=cuda))
+    ga, gp = orc.dm_rotated_gradient(am, ph, basis, samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude), wide auxiliary layer")
+    assert_close(rg[1], gp, what="rotated grad (phase), wide auxiliary layer")
+
+
+def test_density_matrix_nine_rotated_sites(lib, cuda):
+    """4^9 = 262 144 pairs per sample (the round-1 limit was 8 rotated sites). The case is chosen well-conditioned (all-X basis,
+    outcomes 0...0 and one flipped site, small phase parameters: sum |w_ij| / P_b = 1.0004 and 224), so the 1e-10 gate applies as
+    it stands; with random outcomes and Y sites P_b is a sum of 4^9 terms cancelling to 1e-9 of their magnitude and no float64
+    evaluation order, the reference's included, keeps ten digits."""
+    from qucumber_b200 import DensityMatrix
+
+    n, nh, na = 9, 3, 2
+    nn = DensityMatrix(n, nh, na, gpu=True)
+    pa = make_purification_params(n, nh, na, 2081, bias_scale=0.3)
+    pp = tuple(0.05 * x for x in make_purification_params(n, nh, na, 2082, bias_scale=0.3))
+    load_purification(nn.rbm_am, *pa)
+    load_purification(nn.rbm_ph, *pp)
+    am, ph = orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp)
+    basis = ["X"] * n
+    samples = np.zeros((2, n))
+    samples[1, 4] = 1.0
+    rg = nn.rotated_gradient(np.array(basis), torch.tensor(samples, device=cuda))
+    ga, gp = orc.dm_rotated_gradient(am, ph, basis, samples)
+    assert_close(rg[0], ga, what="rotated grad (amplitude), S = 9")
+    assert_close(rg[1], gp, what="rotated grad (phase), S = 9")
+
+
 def test_large_positive_wavefunction_fit_step(lib, cuda):
     """A CD-k training step on a 200 x 200 PositiveWaveFunction runs end to end (Gibbs through the composed path, both
     gradient phases through the row-tiled reduction) and moves the parameters by -lr * gradient."""
