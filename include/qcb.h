@@ -96,13 +96,17 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
                   void* ws, size_t ws_bytes, void* stream);
 
 /* Kernel selection for qcb_rbm_gibbs / qcb_rbm_sample / the packed and host variants when uniforms == NULL.
- * Layers of up to 64 units use an integer-exact tensor-core filter: W v in exact 24-bit fixed point on the int8 tensor
- * cores, FP64 re-evaluation of the units the rigorous error bound cannot decide.  Two implementations:
- *   csrc/gibbs_umma.cu — tcgen05.mma.kind::i8, accumulators in tensor memory (both layers 33..64 units);
- *   csrc/gibbs_imma.cu — mma.sync.m16n8k32 (any layers up to 64 units).
- * mode 0 (default): automatic — the tcgen05 kernel where its shape fits and k >= 3, else the mma.sync kernel, else the
- * FP64 kernel; mode 1: always the FP64 tensor-core kernel (csrc/gibbs.cu); mode 2: the tcgen05 kernel wherever its shape
- * fits (any k); mode 3: never the tcgen05 kernel.  All kernels draw the same numbers and make the same decisions. */
+ * Layers of up to 128 units use an integer-exact tensor-core filter: W v in exact 24-bit fixed point on the int8 tensor
+ * cores, FP64 re-evaluation of the units the rigorous error bound cannot decide.  Three implementations:
+ *   csrc/gibbs_umma.cu      — tcgen05.mma.kind::i8, accumulators in tensor memory (both layers 33..64 units);
+ *   csrc/gibbs_umma_wide.cu — the same for any two layers of up to 128 units (several 128-chain tiles per CTA around one
+ *                             weight image);
+ *   csrc/gibbs_imma.cu      — mma.sync.m16n8k32 (any layers up to 64 units).
+ * mode 0 (default): automatic — the fastest of them for the shape and k, else the FP64 kernel (fed uniforms), else the
+ * composed path (layers of more than 128 units); mode 1: never the integer filter (FP64 tensor-core kernel of csrc/gibbs.cu
+ * or the composed path); mode 2: the tcgen05 kernels wherever their shapes fit (any k); mode 3: never a tcgen05 kernel;
+ * mode 4: the general tcgen05 kernel for every shape up to 128 units.  All kernels draw the same numbers and make the same
+ * decisions. */
 int qcb_set_gibbs_mode(int mode);
 
 /* Test hook: runs the integer-filter kernel and reports in stats2 (device, two uint64, caller-zeroed)

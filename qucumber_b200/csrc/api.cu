@@ -172,9 +172,9 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
 }
 
 int qcb_set_gibbs_mode(int mode) {
-  if (mode < 0 || mode > 3)
-    return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits) "
-                                 "or 3 (mma.sync integer filter, never tcgen05)");
+  if (mode < 0 || mode > 4)
+    return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits), "
+                                 "3 (mma.sync integer filter, never tcgen05) or 4 (the general tcgen05 kernel for every shape up to 128 units)");
   g_gibbs_mode = mode;
   return QCB_OK;
 }

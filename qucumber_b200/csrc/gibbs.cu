@@ -405,7 +405,7 @@ static int pick_blocks(int units) {
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 size_t gibbs_umma_workspace_bytes(int N, int nhid);
 size_t gibbs_umma_wide_workspace_bytes(int N, int nhid);
-int64_t gibbs_umma_wide_wave_chains();
+int64_t gibbs_umma_wide_wave_chains(int N, int nhid);
 int try_gibbs_umma_wide(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                         void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
 
@@ -462,8 +462,13 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
 int g_gibbs_mode = 0;
 constexpr int GIBBS_UMMA_MIN_K = 3;  // below that the mma.sync kernel's TMA-prefetched state tiles win (k = 1: 0.29 vs 0.35 ms)
 static bool use_umma(int k) { return g_gibbs_mode == 2 || (g_gibbs_mode == 0 && k >= GIBBS_UMMA_MIN_K); }
-// layers of 65..128 units have no mma.sync filter kernel: the tcgen05 kernel (gibbs_umma_wide.cu) takes them in modes 0 and 2
-static bool use_umma_wide(int N, int nhid) { return (g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_wide_workspace_bytes(N, nhid) != 0; }
+// The general tcgen05 kernel (gibbs_umma_wide.cu: any two layers of up to 128 units).  Layers of 65..128 units have no mma.sync
+// filter kernel: it takes them in modes 0 and 2; mode 4 sends every shape it fits through it (measurement / test hook).
+static bool use_umma_wide(int N, int nhid) {
+  if (gibbs_umma_wide_workspace_bytes(N, nhid) == 0) return false;
+  if (g_gibbs_mode == 4) return true;
+  return (g_gibbs_mode == 0 || g_gibbs_mode == 2) && (N > 64 || nhid > 64);
+}
 
 size_t gibbs_imma_workspace_bytes(int N, int nhid);
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
@@ -503,7 +508,7 @@ size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
 // Chains one full wave of the persistent grid processes (slicing a host pipeline at multiples of it avoids ragged tails)
 int64_t gibbs_wave_chains(int N, int nhid) {
   if ((g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
-  if (use_umma_wide(N, nhid)) return gibbs_umma_wide_wave_chains();
+  if (use_umma_wide(N, nhid)) return gibbs_umma_wide_wave_chains(N, nhid);
   const int64_t w = gibbs_imma_wave_chains(N, nhid);
   return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
 }

@@ -20,12 +20,9 @@
 namespace qcb {
 
 constexpr int GW_TILE = 128;            // chains per tile (M of the MMA)
-constexpr int GW_TILE_THREADS = 512;    // 16 warps: 4 TMEM lane quarters x 4 unit groups
-constexpr int GW_TILES = 2;             // tiles per CTA
-constexpr int GW_THREADS = GW_TILE_THREADS * GW_TILES;
+constexpr int GW_THREADS = 1024;        // per CTA: 8 / GMAX tiles of 128 GMAX threads (GMAX = 32-unit groups of the wider layer)
 constexpr int GW_A_LBO = 128 * 16;      // A operand: byte distance of consecutive 16-byte K chunks (128 rows, no swizzle)
-constexpr int GW_A_BYTES = 128 * 256;   // 128 chains x (2 x 128) bytes
-constexpr uint32_t GW_TMEM_COLS = 512;  // 2 tiles x 256 columns
+constexpr uint32_t GW_TMEM_COLS = 512;  // tiles x 64 GMAX columns
 
 struct GwHeader {
   float inv_scale;   // -log2(e) * 2^-s
@@ -211,7 +208,6 @@ __device__ __forceinline__ uint32_t gw_p_to_natural(uint32_t x) {
     for (int h = 0; h < 2; ++h) r |= ((x >> (8 * c + 4 * h)) & 0xFu) << (16 * h + 4 * c);
   return r;
 }
-__device__ __forceinline__ void gw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GW_TILE_THREADS) : "memory"); }
 
 // Cold path (all 32 lanes converged): exact FP64 pre-activation from the original parameters, full 53-bit uniform, exact
 // sigmoid, for every undecided unit of every lane.  in_words: this conditional's input bits of the tile's 128 chains,
@@ -257,23 +253,32 @@ __device__ __noinline__ uint32_t fixup_slow_wide(const GwArgs* a, int hidden_out
   return nib;
 }
 
+// GMAX: 32-unit groups of the wider (padded) layer: 4 (65..128 units), 2 (33..64), 1 (<= 32).  A tile of 128 chains is run by
+// 128 GMAX threads; a CTA of 1 024 threads runs 8 / GMAX tiles around one copy of the weight images.
+// GVT / GHT: the layers' group counts as compile-time constants (0: read them from the arguments).
+template <int GMAX, int GVT = 0, int GHT = 0>
 __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const GwArgs a) {
+  constexpr int TT = 128 * GMAX;              // threads per tile
+  constexpr int TILES = GW_THREADS / TT;      // tiles per CTA
+  constexpr int A_BYTES = 128 * 64 * GMAX;    // 128 chains x 2 x 32 GMAX bytes
+  constexpr uint32_t TCOLS = 64u * GMAX;      // TMEM columns per tile: 2 x 32 GMAX
+  constexpr int RPW = 32 / GMAX;              // rows per warp in the float64 I/O phases
   extern __shared__ __align__(128) unsigned char smem[];
-  const int PV = a.PV, PH = a.PH;
+  const int PV = GVT > 0 ? 32 * GVT : a.PV, PH = GHT > 0 ? 32 * GHT : a.PH;
   const size_t image_bytes = gw_image_bytes(PV, PH), b_bytes = gw_b_bytes(PV, PH);
   const GwHeader* hd = reinterpret_cast<const GwHeader*>(smem);
   const float* biasH = reinterpret_cast<const float*>(smem + GW_BIAS_OFF);
   const float* biasV = biasH + 128;
   const int tid = threadIdx.x;
-  const int tile_slot = tid >> 9;                          // which of the CTA's two tiles
-  const int ttid = tid & (GW_TILE_THREADS - 1), wl = ttid >> 5, lane = tid & 31;
+  const int tile_slot = tid / TT;                          // which of the CTA's tiles
+  const int ttid = tid % TT, wl = ttid >> 5, lane = tid & 31;
   const int g = wl >> 2;                                   // 32-unit group of either layer
   const int row = 32 * (wl & 3) + lane;                    // chain row of the tile = TMEM lane
-  unsigned char* sA = smem + image_bytes + (size_t)tile_slot * GW_A_BYTES;   // this tile's state bytes (A operand)
-  uint32_t* words_all = reinterpret_cast<uint32_t*>(smem + image_bytes + (size_t)GW_TILES * GW_A_BYTES);
-  uint32_t* words = words_all + (size_t)tile_slot * 2 * 4 * GW_TILE;          // [2 buffers][4 groups][128 rows]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(words_all + (size_t)GW_TILES * 2 * 4 * GW_TILE);  // [0]: image, [1 + t]: MMA of tile t
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1 + GW_TILES);
+  unsigned char* sA = smem + image_bytes + (size_t)tile_slot * A_BYTES;      // this tile's state bytes (A operand)
+  uint32_t* words_all = reinterpret_cast<uint32_t*>(smem + image_bytes + (size_t)TILES * A_BYTES);
+  uint32_t* words = words_all + (size_t)tile_slot * 2 * GMAX * GW_TILE;       // [2 buffers][GMAX groups][128 rows]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(words_all + (size_t)TILES * 2 * GMAX * GW_TILE);  // [0]: image, [1 + t]: MMA of tile t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1 + TILES);
   uint32_t* arrive_cnt = tmem_slot + 1 + tile_slot;        // threads of this tile that have published their bits
 
   if (tid < 32) {
@@ -281,9 +286,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   if (tid == 0) {
-    for (int i = 0; i < 1 + GW_TILES; ++i) mbar_init(mbar + i, 1);
-    tmem_slot[1] = 0u;
-    tmem_slot[2] = 0u;
+    for (int i = 0; i < 1 + TILES; ++i) mbar_init(mbar + i, 1);
+    for (int i = 0; i < TILES; ++i) tmem_slot[1 + i] = 0u;
   }
   __syncthreads();
   if (tid == 0) {
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
-  const uint32_t tmem = *tmem_slot + 256u * (uint32_t)tile_slot;
+  const uint32_t tmem = *tmem_slot + TCOLS * (uint32_t)tile_slot;
   const uint32_t taddr = tmem + ((uint32_t)(32 * (wl & 3)) << 16) + 32u * (uint32_t)g;  // this thread's lane, first acc01 column of its group
   const float k1 = hd->inv_scale;
   const int nhid = a.p.nhid(), N = a.p.N;
@@ -320,9 +324,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
   const uint32_t idesc_v = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)((2 * PV) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   uint32_t mma_phase = 0u;
   const int bar_id = 1 + tile_slot;
+  auto tile_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TT) : "memory"); };
 
   const int64_t num_tiles = (a.C + GW_TILE - 1) / GW_TILE;
-  for (int64_t ti = (int64_t)blockIdx.x * GW_TILES + tile_slot; ti < num_tiles; ti += (int64_t)gridDim.x * GW_TILES) {
+  for (int64_t ti = (int64_t)blockIdx.x * TILES + tile_slot; ti < num_tiles; ti += (int64_t)gridDim.x * TILES) {
     const int64_t chain_base = ti * GW_TILE;
     const int64_t ch = chain_base + row;
     const uint64_t id = a.chain_id0 + (uint64_t)ch;
@@ -331,33 +336,35 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
     // ---- initial state of this thread's (chain, visible group), natural bit order -> p-order ----
     uint32_t cur = 0u;
     if (a.in_mode == 0) {
-      // float64 rows: warp wl fetches rows 8 wl .. 8 wl + 7 of the tile, 256 contiguous bytes per load, ballots the bits and
-      // leaves the (up to four) 32-bit words of each row in buffer 0 of `words`
+      // float64 rows: warp wl fetches rows RPW wl .. RPW wl + RPW - 1 of the tile, 256 contiguous bytes per load, ballots the bits
+      // and leaves the (up to GMAX) 32-bit words of each row in buffer 0 of `words`
 #pragma unroll 4
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = 8 * wl + rr;
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int r = RPW * wl + rr;
         const int64_t c = chain_base + r;
-        unsigned long long d[4] = {0ull, 0ull, 0ull, 0ull};
+        unsigned long long d[GMAX];
+#pragma unroll
+        for (int j = 0; j < GMAX; ++j) d[j] = 0ull;
         if (c < a.C) {
           const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(a.v_in) + c * N;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < GMAX; ++j)
             if (lane + 32 * j < N) d[j] = rp[lane + 32 * j];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < GMAX; ++j) {
           const uint32_t bj = __ballot_sync(0xffffffffu, (d[j] << 1) != 0ull);
           if (lane == 0) words[j * GW_TILE + r] = bj;
         }
       }
-      gw_bar(bar_id);
+      tile_bar();
       cur = words[g * GW_TILE + row];
       // pull this tile slot's NEXT tile (one contiguous span of v_in) into L2 while this one is swept
-      const int64_t nbase = (ti + (int64_t)gridDim.x * GW_TILES) * GW_TILE;
+      const int64_t nbase = (ti + (int64_t)gridDim.x * TILES) * GW_TILE;
       if (nbase < a.C) {
         const int64_t nbytes = (a.C - nbase < GW_TILE ? a.C - nbase : (int64_t)GW_TILE) * N * (int64_t)sizeof(double);
         const char* np = reinterpret_cast<const char*>(a.v_in + nbase * N);
-        for (int64_t off = (int64_t)ttid * 128; off < nbytes; off += (int64_t)GW_TILE_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
+        for (int64_t off = (int64_t)ttid * 128; off < nbytes; off += (int64_t)TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
       }
     } else if (a.in_mode == 1) {
       if (ch < a.C) {
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
       const bool back = (hs & 1) != 0;  // false: h | v, true: v | h
       const int GI = back ? GH : GV, GO = back ? GV : GH;   // 32-unit groups of the input / output layer
       // ---- publish this thread's 32 input bits: A operand bytes [v ; 128 v] and the word for the cold path ----
-      uint32_t* in_words = words + (hs & 1) * 4 * GW_TILE;
+      uint32_t* in_words = words + (hs & 1) * GMAX * GW_TILE;
       if (g < GI) {
         in_words[g * GW_TILE + row] = cur;
         uint4 lo, hi4;
@@ -396,10 +403,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
       asm volatile("tcgen05.fence::before_thread_sync;\n");       // ... and this thread's TMEM reads of the previous accumulators are done
-      // every thread of the tile checks in (release); the LAST one (acquire: it sees all 512 publications) issues the MMAs
+      // every thread of the tile checks in (release); the LAST one (acquire: it sees all publications) issues the MMAs
       uint32_t arrived;
       asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(arrived) : "r"(smem_u32(arrive_cnt)) : "memory");
-      if (arrived == GW_TILE_THREADS - 1) {
+      if (arrived == TT - 1) {
         *reinterpret_cast<volatile uint32_t*>(arrive_cnt) = 0u;  // nobody checks in again before this MMA has completed
         asm volatile("tcgen05.fence::after_thread_sync;\n");
         const uint64_t bdesc = back ? bdesc_v : bdesc_h;
@@ -426,6 +433,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
         uint32_t acc1 = 0u, acc0 = 0u;  // bit p: "certainly 1" / "certainly 0"; units are visited from p = 31 down
 #pragma unroll
         for (int c = 3; c >= 0; --c) {
+          const uint32_t vb = (valid >> (8 * c)) & 0xFFu;
+          if (GMAX < 4 && vb == 0u) {   // a Philox call that serves padding only (narrow layers): warp-uniform skip
+            acc1 <<= 8;
+            acc0 = (acc0 << 8) | 0xFFu;
+            continue;
+          }
           int a01[8], a2[8];
           gw_ld8(taddr + 8u * (uint32_t)c, a01);
           gw_ld8(taddr + acc2_off + 8u * (uint32_t)c, a2);
@@ -435,6 +448,22 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
           const float4 b_hi = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
           const float bs[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (GMAX < 4 && (vb & 0xF0u) == 0u) {   // layers of at most 16 units use the high 16-bit halves only (units 16.. are padding)
+            acc1 <<= 4;
+            acc0 = (acc0 << 4) | 0xFu;
+#pragma unroll
+            for (int i = 3; i >= 0; --i) {
+              const int t = a2[i] * 32768 + a01[i];
+              const float y = fmaf((float)t, k1, bs[i]);
+              const float q = 1.0f + gw_ex2(y);
+              const float m = __uint_as_float(__byte_perm(rnd[i], 0x7Fu, 0x5432u) << 7);
+              const float s1 = fmaf(m + c1, q, -1.0f);
+              const float s0 = fmaf(d01, q, -s1);
+              acc1 = __funnelshift_l(__float_as_uint(s1), acc1, 1);
+              acc0 = __funnelshift_l(__float_as_uint(s0), acc0, 1);
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 7; i >= 0; --i) {   // i = 4 h + w
             const int half = i >> 2, w = i & 3;
@@ -463,19 +492,19 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
     const uint32_t nat = gw_p_to_natural(cur & valid_v);
     if (a.v != nullptr) {
       // float64 rows out: the words go through buffer 1 of `words` (free once every thread of the tile has left the last
-      // update's cold path), then warp wl writes rows 8 wl .. 8 wl + 7, 256 contiguous bytes per store
-      gw_bar(bar_id);
-      if (g < GV) words[4 * GW_TILE + g * GW_TILE + row] = nat;
-      gw_bar(bar_id);
+      // update's cold path), then warp wl writes its RPW rows, 256 contiguous bytes per store
+      tile_bar();
+      if (g < GV) words[GMAX * GW_TILE + g * GW_TILE + row] = nat;
+      tile_bar();
 #pragma unroll 4
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = 8 * wl + rr;
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int r = RPW * wl + rr;
         const int64_t c = chain_base + r;
         if (c < a.C) {
           double* rp = a.v + c * N;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < N) rp[lane + 32 * j] = (words[4 * GW_TILE + j * GW_TILE + r] >> lane) & 1u ? 1.0 : 0.0;
+          for (int j = 0; j < GMAX; ++j)
+            if (lane + 32 * j < N) rp[lane + 32 * j] = (words[GMAX * GW_TILE + j * GW_TILE + r] >> lane) & 1u ? 1.0 : 0.0;
         }
       }
     }
@@ -492,20 +521,23 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*tmem_slot), "r"(GW_TMEM_COLS));
 }
 
-static int gw_pad(int units) { return units <= 64 ? 64 : 128; }
+static int gw_pad(int units) { return units <= 32 ? 32 : (units <= 64 ? 64 : 128); }
+static int gw_gmax(int PV, int PH) { return (PV > PH ? PV : PH) / 32; }
 static size_t gw_smem_bytes(int PV, int PH) {
-  return gw_image_bytes(PV, PH) + (size_t)GW_TILES * GW_A_BYTES + (size_t)GW_TILES * 2 * 4 * GW_TILE * sizeof(uint32_t) + (1 + GW_TILES) * 8 + 16;
+  const int gmax = gw_gmax(PV, PH), tiles = 8 / gmax;
+  return gw_image_bytes(PV, PH) + (size_t)tiles * 128 * 64 * gmax + (size_t)tiles * 2 * gmax * GW_TILE * sizeof(uint32_t) + (1 + tiles) * 8 +
+         (1 + tiles) * 4 + 16;
 }
 
-// shapes: at least one layer of 65..128 units, the other of 1..128
+// shapes: both layers of 1..128 units (the dispatcher in gibbs.cu decides which of them come here)
 size_t gibbs_umma_wide_workspace_bytes(int N, int nhid) {
-  if (N < 1 || nhid < 1 || N > 128 || nhid > 128 || (N <= 64 && nhid <= 64)) return 0;
+  if (N < 1 || nhid < 1 || N > 128 || nhid > 128) return 0;
   return align_up(gw_image_bytes(gw_pad(N), gw_pad(nhid)), 256);
 }
 
-int64_t gibbs_umma_wide_wave_chains() { return (int64_t)sm_count() * GW_TILES * GW_TILE; }
+int64_t gibbs_umma_wide_wave_chains(int N, int nhid) { return (int64_t)sm_count() * (8 / gw_gmax(gw_pad(N), gw_pad(nhid))) * GW_TILE; }
 
-// *handled = 1 when this kernel took the call (own Philox draws; one layer of 65..128 units)
+// *handled = 1 when this kernel took the call (own Philox draws; layers of up to 128 units)
 int try_gibbs_umma_wide(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                         void* ws, size_t ws_bytes, int* handled, cudaStream_t st) {
   *handled = 0;
@@ -538,16 +570,24 @@ int try_gibbs_umma_wide(const StackedParams& p, const ChainIO& io, int64_t C, in
     a.rk[2 * r + 1] = a.key1 + (uint32_t)r * 0xBB67AE85u;
   }
   const size_t smem = gw_smem_bytes(PV, PH);
+  const int gmax = gw_gmax(PV, PH), tiles_per_cta = 8 / gmax;
   static bool configured[QCB_MAX_DEVICES] = {false};
   bool& done = configured[device_slot()];
   if (!done) {
-    QCB_CUDA(cudaFuncSetAttribute(gibbs_umma_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(128, 128)));
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_umma_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(128, 128)));
+    QCB_CUDA((cudaFuncSetAttribute(gibbs_umma_wide_kernel<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(128, 128))));
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_umma_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(64, 64)));
+    QCB_CUDA(cudaFuncSetAttribute(gibbs_umma_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(32, 32)));
     done = true;
   }
-  // one CTA per SM (all 512 TMEM columns, up to 201 KB of shared memory), two tiles per CTA
+  // one CTA per SM (all 512 TMEM columns), 8 / GMAX tiles per CTA
   const int64_t tiles = (C + GW_TILE - 1) / GW_TILE;
-  const int64_t want = (tiles + GW_TILES - 1) / GW_TILES, cap = (int64_t)sm_count();
-  gibbs_umma_wide_kernel<<<(int)(want < cap ? want : cap), GW_THREADS, smem, st>>>(a);
+  const int64_t want = (tiles + tiles_per_cta - 1) / tiles_per_cta, cap = (int64_t)sm_count();
+  const int grid = (int)(want < cap ? want : cap);
+  if (PV == 128 && PH == 128) gibbs_umma_wide_kernel<4, 4, 4><<<grid, GW_THREADS, smem, st>>>(a);
+  else if (gmax == 4) gibbs_umma_wide_kernel<4><<<grid, GW_THREADS, smem, st>>>(a);
+  else if (gmax == 2) gibbs_umma_wide_kernel<2><<<grid, GW_THREADS, smem, st>>>(a);
+  else gibbs_umma_wide_kernel<1><<<grid, GW_THREADS, smem, st>>>(a);
   QCB_LAUNCH_CHECK();
   *handled = 1;
   return QCB_OK;
