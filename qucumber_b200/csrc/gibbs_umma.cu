@@ -25,6 +25,9 @@ constexpr int GU_THREADS = 256;
 constexpr int GU_TILE = 128;          // chains per CTA tile (M of the MMA)
 constexpr int GU_MIN_CTAS = 4;        // 4 x 128 TMEM columns = the whole tensor memory of an SM
 constexpr uint32_t GU_TMEM_COLS = 128;
+#ifndef GU_PREFETCH
+#define GU_PREFETCH 1                 // Philox calls of an update drawn before the MMA-completion wait (registers: 4 words each)
+#endif
 constexpr int GU_OPERAND_BYTES = 128 * 128;  // A (128 chains x 128 bytes) and each B image (128 rows x 128 bytes)
 constexpr int GU_LBO = (128 / 8) * 128;      // byte distance of consecutive 16-byte K chunks (no swizzle, K-major)
 
@@ -421,6 +424,11 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
       const uint32_t q0 = (back ? qv0 : 0u) + 4u * (uint32_t)hh;
       const float c1 = (0x1.0p-16f + margin) - 1.0f;   // s1 = (m + c1) q - 1 < 0             => certainly u < p
       const float d01 = 0x1.0p-16f + 2.0f * margin;    // s0 = d01 q - s1 = 1 - (u_f - margin) q < 0 => certainly u >= p
+      // the draws of the first GU_PREFETCH calls are made while the tile's MMAs run (the wait below is where 19 % of all warp
+      // samples sat: the join of the tile's 8 warps plus the MMA latency); the remaining calls overlap the TMEM loads
+      uint32_t pre[GU_PREFETCH > 0 ? GU_PREFETCH : 1][4];
+#pragma unroll
+      for (int j = 0; j < GU_PREFETCH; ++j) gu_philox(cid0, cid1, sweep, q0 + (uint32_t)(3 - j), a.rk, pre[j]);
       mbar_wait(mbar + 1, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -432,7 +440,12 @@ __global__ void __launch_bounds__(GU_THREADS, GU_MIN_CTAS) gibbs_umma_kernel(con
         gu_ld8(taddr + 8u * (uint32_t)c, a01);
         gu_ld8(taddr + 64u + 8u * (uint32_t)c, a2);
         uint32_t rnd[4];
-        gu_philox(cid0, cid1, sweep, q0 + (uint32_t)c, a.rk, rnd);  // stream 0; overlaps the TMEM loads
+        if (3 - c < GU_PREFETCH) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) rnd[w] = pre[3 - c < GU_PREFETCH ? 3 - c : 0][w];
+        } else {
+          gu_philox(cid0, cid1, sweep, q0 + (uint32_t)c, a.rk, rnd);  // stream 0; overlaps the TMEM loads
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const float4 b_lo = *reinterpret_cast<const float4*>(bias + 8 * c);
         const float4 b_hi = *reinterpret_cast<const float4*>(bias + 8 * c + 4);

@@ -23,6 +23,9 @@ constexpr int GW_TILE = 128;            // chains per tile (M of the MMA)
 constexpr int GW_THREADS = 1024;        // per CTA: 8 / GMAX tiles of 128 GMAX threads (GMAX = 32-unit groups of the wider layer)
 constexpr int GW_A_LBO = 128 * 16;      // A operand: byte distance of consecutive 16-byte K chunks (128 rows, no swizzle)
 constexpr uint32_t GW_TMEM_COLS = 512;  // tiles x 64 GMAX columns
+#ifndef GW_PREFETCH
+#define GW_PREFETCH 0                   // Philox calls of an update drawn before the MMA-completion wait (measured: no gain here, spills at 64 registers)
+#endif
 
 struct GwHeader {
   float inv_scale;   // -log2(e) * 2^-s
@@ -425,6 +428,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
       const float c1 = (0x1.0p-16f + margin) - 1.0f;   // s1 = (m + c1) q - 1 < 0             => certainly u < p
       const float d01 = 0x1.0p-16f + 2.0f * margin;    // s0 = d01 q - s1 = 1 - (u_f - margin) q < 0 => certainly u >= p
       const uint32_t acc2_off = 32u * (uint32_t)GO;    // PO columns on
+      // the draws of the first GW_PREFETCH calls are made while the tile's MMAs run; the remaining calls overlap the TMEM loads
+      uint32_t pre[GW_PREFETCH > 0 ? GW_PREFETCH : 1][4];
+      if (valid != 0u) {
+#pragma unroll
+        for (int j = 0; j < GW_PREFETCH; ++j) gw_philox(cid0, cid1, sweep, q0 + (uint32_t)(3 - j), a.rk, pre[j]);
+      }
       mbar_wait(mbar + 1 + tile_slot, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -443,7 +452,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gibbs_umma_wide_kernel(const Gw
           gw_ld8(taddr + 8u * (uint32_t)c, a01);
           gw_ld8(taddr + acc2_off + 8u * (uint32_t)c, a2);
           uint32_t rnd[4];
-          gw_philox(cid0, cid1, sweep, q0 + (uint32_t)c, a.rk, rnd);  // stream 0; overlaps the TMEM loads
+          if (3 - c < GW_PREFETCH) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) rnd[w] = pre[3 - c < GW_PREFETCH ? 3 - c : 0][w];
+          } else {
+            gw_philox(cid0, cid1, sweep, q0 + (uint32_t)c, a.rk, rnd);  // stream 0; overlaps the TMEM loads
+          }
           const float4 b_lo = *reinterpret_cast<const float4*>(bias + 8 * c);
           const float4 b_hi = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
           const float bs[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
