@@ -20,7 +20,12 @@
 
 namespace qcb {
 
-constexpr int GM_THREADS = 256;
+#ifndef GM_SPLIT
+#define GM_SPLIT 4                              // threads per row: each owns 64 / GM_SPLIT hidden units (2: 8 warps, 4: 16 warps per CTA)
+#endif
+constexpr int GM_THREADS = 128 * GM_SPLIT;
+constexpr int GM_UPT = 64 / GM_SPLIT;           // hidden units per thread
+constexpr int GM_RPW = 128 / (4 * GM_SPLIT);    // rows per warp when a tile is loaded
 constexpr int GM_TILE = 128;
 constexpr int GM_LBO = 2048;                    // 16-byte chunk stride of a 128-row operand (K-major view)
 constexpr int GM_A_BYTES = 10 * GM_LBO;         // chunks 0-3: v, 4: ones, 5: zeros, 6-9: 128 v
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
   double* stage = reinterpret_cast<double*>(smem + align_up((size_t)(reinterpret_cast<unsigned char*>(colcnt + 64) - smem), 128));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hh = warp >> 2;
+  const int hh = warp >> 2;                 // which GM_UPT-unit slice of the hidden layer (and of the state bits) this thread owns
   const int row = 32 * (warp & 3) + lane;
   const size_t E = (size_t)H * N + N + H;
 
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
   fill_exp2_table(e2tab);
   // constant chunks of the state tile: chunk 4 = (1, 0, ..., 0) per row (the all-ones column of phase 2), chunk 5 = zeros
   if (tid < 128) reinterpret_cast<uint4*>(sA + 4 * GM_LBO)[tid] = make_uint4(1u, 0u, 0u, 0u);
-  else reinterpret_cast<uint4*>(sA + 5 * GM_LBO)[tid - 128] = make_uint4(0u, 0u, 0u, 0u);
+  else if (tid < 256) reinterpret_cast<uint4*>(sA + 5 * GM_LBO)[tid - 128] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(mbar, (uint32_t)GM_IMAGE_BYTES);
@@ -226,8 +231,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
       // packed rows: lanes 0..15 fetch one row each (one 8-byte load at N > 56), undo the MSB-first bit order of the bytes and
       // publish the two words; the column counts come from 16 broadcasts
       uint32_t w0 = 0u, w1 = 0u;
-      const int64_t gr = r0 + 16 * warp + lane;
-      if (lane < 16 && gr < rows) {
+      const int64_t gr = r0 + GM_RPW * warp + lane;
+      if (lane < GM_RPW && gr < rows) {
         const unsigned char* rp = bits + gr * rowbytes;
         if (bits_wide) {
           const uint2 x = *reinterpret_cast<const uint2*>(rp);
@@ -243,19 +248,19 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
         w0 = __byte_perm(__brev(w0), 0u, 0x0123u);  // unit 8 b + i = bit 7 - i of byte b  ->  bit 8 b + i
         w1 = __byte_perm(__brev(w1), 0u, 0x0123u) & hi_mask;
       }
-      if (lane < 16) {
-        words[16 * warp + lane] = w0;
-        words[GM_TILE + 16 * warp + lane] = w1;
+      if (lane < GM_RPW) {
+        words[GM_RPW * warp + lane] = w0;
+        words[GM_TILE + GM_RPW * warp + lane] = w1;
       }
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
+      for (int rr = 0; rr < GM_RPW; ++rr) {
         cnt0 += (int)((__shfl_sync(0xffffffffu, w0, rr) >> lane) & 1u);
         cnt1 += (int)((__shfl_sync(0xffffffffu, w1, rr) >> lane) & 1u);
       }
     } else {
 #pragma unroll 8
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = 16 * warp + rr;
+    for (int rr = 0; rr < GM_RPW; ++rr) {
+      const int r = GM_RPW * warp + rr;
       const int64_t gr = r0 + r;
       unsigned long long d0 = 0ull, d1 = 0ull;
       if (gr < rows) {
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
       mbar_wait(mbar + 2, ph2);
       ph2 ^= 1u;
     }
-    {  // publish this thread's 32 bits as bytes: [v ; 128 v]
+    if (GM_SPLIT == 2) {  // publish this thread's 32 bits as bytes: [v ; 128 v]
       const uint32_t cur = words[hh * GM_TILE + row];
       uint4 lo, hi4;
       lo.x = gm_spread4(cur & 0xFu); lo.y = gm_spread4((cur >> 4) & 0xFu); lo.z = gm_spread4((cur >> 8) & 0xFu); lo.w = gm_spread4((cur >> 12) & 0xFu);
@@ -297,6 +302,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
       hi4.x <<= 7; hi4.y <<= 7; hi4.z <<= 7; hi4.w <<= 7;
       *reinterpret_cast<uint4*>(base + (6 + 2 * hh) * GM_LBO) = lo;
       *reinterpret_cast<uint4*>(base + (6 + 2 * hh + 1) * GM_LBO) = hi4;
+    } else {              // four threads per row: 16 bits each, one 16-byte chunk of v and one of 128 v
+      const uint32_t cur = (words[(hh >> 1) * GM_TILE + row] >> (16 * (hh & 1))) & 0xFFFFu;
+      uint4 lo;
+      lo.x = gm_spread4(cur & 0xFu); lo.y = gm_spread4((cur >> 4) & 0xFu); lo.z = gm_spread4((cur >> 8) & 0xFu); lo.w = gm_spread4(cur >> 12);
+      unsigned char* base = sA + row * 16;
+      *reinterpret_cast<uint4*>(base + hh * GM_LBO) = lo;
+      lo.x <<= 7; lo.y <<= 7; lo.z <<= 7; lo.w <<= 7;
+      *reinterpret_cast<uint4*>(base + (6 + hh) * GM_LBO) = lo;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -320,9 +333,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
     // ---- theta -> p -> six bytes of rint(p 2^48), written M-major into the digit tiles
     // P = rint(p (2^48 - 1)) fits six bytes for every p in [0, 1] (no clamp); rows beyond the batch get a zero scale
     const double pscale = r0 + row < rows ? 281474976710655.0 : 0.0;
-    const uint32_t tcol = tmem + lane_base + 32u * (uint32_t)hh;
+    const uint32_t tcol = tmem + lane_base + (uint32_t)(GM_UPT * hh);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < GM_UPT / 8; ++c) {
       int h01[8], h2[8], l01[8], l2[8];
       gm_ld8(tcol + 8u * (uint32_t)c, h01);
       gm_ld8(tcol + 64u + 8u * (uint32_t)c, h2);
@@ -332,13 +345,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) grad_reduce_umma_kernel(const u
       unsigned long long P[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int unit = 32 * hh + 8 * c + i;
+        const int unit = GM_UPT * hh + 8 * c + i;
         const double thi = gm_i2d(h2[i] * 32768 + h01[i]), tlo = gm_i2d(l2[i] * 32768 + l01[i]);
         const double theta = fma(fma(tlo, 2.384185791015625e-07, thi), inv_scale, hb[unit]);  // 2^-22
         P[i] = __double2ull_rn(sigmoid_tab(theta, e2tab) * pscale);
       }
       // byte d of the eight values -> eight consecutive bytes of digit d's M-major tile
-      const int u0 = 32 * hh + 8 * c;  // first unit of the chunk: m = (d & 1) * 64 + u0 + i
+      const int u0 = GM_UPT * hh + 8 * c;  // first unit of the chunk: m = (d & 1) * 64 + u0 + i
 #pragma unroll
       for (int d = 0; d < 6; ++d) {
         // byte d of P[0..3] and of P[4..7] -> two words: three byte permutes each (bytes 0..3 live in the low word, 4..5 in the high one)
