@@ -938,9 +938,9 @@ def run_ours(args):
         imma_tops = C * k * IMMA_OPS_PER_SWEEP / (imma_ms_step * 1e-3) / 1e12
         fp64_achieved = C * k * FLOP_PER_SWEEP / (fp64_ms_step * 1e-3) / 1e12
         # issue slots: warp instructions executed per chain-sweep (ncu smsp__inst_executed.sum of one k = 10 launch over C * k,
-        # profiles/gibbs_umma_r02_ncu.txt) against 4 schedulers x SMs x clock; ncu's measured issue-active is quoted beside it
+        # profiles/gibbs_umma_r02e_ncu.txt) against 4 schedulers x SMs x clock; ncu's measured issue-active is quoted beside it
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        instr_per_chain_sweep = 107.2
+        instr_per_chain_sweep = 103.2
         issue_rate = C * k * instr_per_chain_sweep / (ms_step * 1e-3)
         issue_peak = 148 * 4 * sm_mhz * 1e6
         line = {
@@ -957,8 +957,8 @@ def run_ours(args):
                          "frac": issue_rate / issue_peak, "traffic": traffic, "kernel": "gibbs_umma_kernel (tcgen05.mma.kind::i8, TMEM accumulators)",
                          "peak_source": "4 warp schedulers x 148 SMs x the SM clock sampled during the timed region (one warp instruction per "
                                         "scheduler and cycle); MEASURED_PEAKS.json holds HBM and bf16 figures only, neither bounds this kernel",
-                         "warp_instr_per_chain_sweep": instr_per_chain_sweep, "ncu_issue_active": 0.696,
-                         "ncu_source": "profiles/gibbs_umma_r02_ncu.txt (smsp__inst_executed.sum of one k = 10 launch over C * k chain-sweeps)",
+                         "warp_instr_per_chain_sweep": instr_per_chain_sweep, "ncu_issue_active": 0.685,
+                         "ncu_source": "profiles/gibbs_umma_r02e_ncu.txt (smsp__inst_executed.sum = 1 082 292 782 of one k = 10 launch over C * k = 10 485 760 chain-sweeps)",
                          "note": "achieved = warp instructions executed per chain-sweep (ncu) x chain-sweeps per launch / measured launch time. "
                                  "tensor_pipe = the int8 tensor-core work the kernel EXECUTES (two 128x128x128 tile products per 128 chains and "
                                  "sweep) against the measured tcgen05 rate; fp64_equivalent restates the rate in the unit of SURVEY 8(d) and is "
