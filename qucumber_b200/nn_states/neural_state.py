@@ -478,7 +478,10 @@ class NeuralStateBase(abc.ABC):
         return pos, neg, pos_perm
 
     _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
-    device_shuffle_min_rows = 1 << 16  # from this many samples on, fit() shuffles on the device
+    # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
+    # asynchronously (an index tensor drawn on the host has to be copied over first, which makes the host wait for the previous
+    # epoch's kernel: 1.30 -> 1.1 ms per TFIM epoch); set it to a row count to keep host shuffles below that size
+    device_shuffle_min_rows = 0
 
     #: set to False to force one C call per batch even where a whole epoch fits one launch
     fuse_epochs = True
@@ -558,8 +561,9 @@ class NeuralStateBase(abc.ABC):
         # one Philox key per fit() call; under torch.distributed rank 0's key is broadcast and also seeds the host generator of
         # the shuffles, so that every rank walks through the same batches whatever its own seeding was
         self._cd_seed, self._cd_sweep = qd.broadcast_seed(next_seed(), self.device), 0
-        # large data sets without bases are shuffled on the device (a host randperm of 8 M rows takes longer than the epoch's
-        # kernels); the generator is seeded from the fit key, so torch.manual_seed still reproduces the run
+        # data sets without bases are shuffled on the device (nothing for the host to wait on; a host randperm of 8 M rows
+        # also takes longer than the epoch's kernels); the generator is seeded from the fit key, so torch.manual_seed still
+        # reproduces the run
         if input_bases is None and train_samples.is_cuda and train_samples.shape[0] >= self.device_shuffle_min_rows:
             self._shuffle_generator = torch.Generator(device=train_samples.device).manual_seed(self._cd_seed)
         else:
@@ -576,15 +580,40 @@ class NeuralStateBase(abc.ABC):
         fused_epoch = (scheduler is None and max(pos_batch_size, neg_batch_size) <= 4096
                        and self._shards_batches(pos_batch_size, neg_batch_size, input_bases is not None)[1] == 1
                        and self._epoch_fusable(optimizer, cbs, input_bases))
+        # fused epochs with device-side shuffles: the NEXT epoch's permutation and gathers run on a side stream while this
+        # epoch's kernel (one 16-CTA cluster, the rest of the GPU is idle) runs on the caller's stream
+        side = None
+        if fused_epoch and self._shuffle_generator is not None and self._shuffle_generator.device.type == "cuda":
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+
+        def shuffled_epoch():
+            if side is None:
+                return self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None,
+                                             generator=self._shuffle_generator)[:2] + (None,)
+            with torch.cuda.stream(side):
+                p_, n_, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None,
+                                                  generator=self._shuffle_generator)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            return p_, n_, ready
+
+        ahead = shuffled_epoch() if fused_epoch else None
         for ep in epoch_iter:
             if fused_epoch:
-                pos, neg, _ = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, None, None,
-                                                    generator=self._shuffle_generator)
+                pos, neg, ready = ahead
+                if ready is not None:
+                    main = torch.cuda.current_stream(self.device)
+                    main.wait_event(ready)
+                    pos.record_stream(main)
+                    neg.record_stream(main)
                 cbs.fire("on_epoch_start", self, ep)
                 nb = min(num_batches, ceil(neg.shape[0] / neg_batch_size))
                 self._fit_epoch_fused(pos, neg, nb, pos_batch_size, neg_batch_size, k, optimizer.param_groups[0]["lr"],
                                       want_grads=bool(cbs.callbacks))
                 batches = ()
+                if ep != epochs:
+                    ahead = shuffled_epoch()  # queued behind nothing but the previous shuffle: overlaps the kernel just launched
             else:
                 batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
                 cbs.fire("on_epoch_start", self, ep)
