@@ -26,6 +26,7 @@ SIGNATURES = {
                               _P, _P, c_size_t, _P]),
     "qcb_set_gibbs_mode": (c_int, [c_int]),
     "qcb_set_grad_reduce_mode": (c_int, [c_int]),
+    "qcb_set_cd_epoch_mode": (c_int, [c_int]),
     "qcb_debug_gibbs_filter": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, c_int, c_uint64, _P, _P, c_size_t, _P]),
     "qcb_linear_sigmoid": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int64, _P, _P]),
     "qcb_linear": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int64, _P, _P]),

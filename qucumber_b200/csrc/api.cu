@@ -34,6 +34,7 @@ extern int g_gibbs_mode;
 extern int g_grad_mode;
 extern int g_grad_small_hist;
 extern int g_cwf_mode;
+extern int g_cd_epoch_mode;
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
 int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
@@ -176,6 +177,12 @@ int qcb_set_gibbs_mode(int mode) {
     return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits), "
                                  "3 (mma.sync integer filter, never tcgen05) or 4 (the general tcgen05 kernel for every shape up to 128 units)");
   g_gibbs_mode = mode;
+  return QCB_OK;
+}
+
+int qcb_set_cd_epoch_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(QCB_ERR_BAD_ARG, "cd_epoch mode must be 0 (automatic) or 1 (never the warp-specialised kernel)");
+  g_cd_epoch_mode = mode;
   return QCB_OK;
 }
 

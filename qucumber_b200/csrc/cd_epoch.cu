@@ -288,6 +288,344 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
   }
 }
 
+// ---- warp-specialised variant for layers of at most 16 units (round 2) ----------------------------------------------------
+// ncu on cd_epoch_kernel: issue slots 27 % busy, a latency chain — a step is 20 dependent conditional updates of 0.36 us, and
+// half of the instructions a warp issues per update are the Philox rounds of draws that do not depend on the chain's state.
+// Here the CTA has two kinds of warps:
+//  * PRODUCER warps (a) draw the 16-bit cells of every (chain slot, sweep, layer, unit) of the next sweeps into a ring of
+//    shared-memory buffers (one lane per Philox CALL: four / eight units at once, not one call per unit) and (b) after every
+//    parameter update rebuild float NIBBLE TABLES of the pre-activations: T[layer][unit][t][m] = sum of the unit's weights
+//    towards input units 4 t .. 4 t + 3 selected by the bits of m (the bias rides in table 0), plus the unit's filter margin;
+//  * CONSUMER warps run what depends on the state: the pre-activation is SW / 4 table reads and a short add tree (instead of
+//    SW predicated adds), the filter in the division-free form (L q - 1 with q = 1 + 2^(-x log2 e)), two votes.  The float sum
+//    carries a rigorous margin ((n_in + 6) 2^-24 (|bias| + sum |w|): conversions and every float addition, a quarter of it on
+//    top of the 2^-17 of the float sigmoid); a warp with an undecided lane recomputes that lane in FP64 from the shared-memory
+//    weights and takes the exact path.
+// Hand-over by named barriers (full[b]: producers arrive, consumers sync; empty[b]: the reverse; tables: producers arrive,
+// consumers sync).  Same draws, same exact decisions, same reduction order as cd_epoch_kernel — the two kernels return the same
+// parameters bit for bit.
+constexpr int WS_CONS = 256, WS_PROD = 256, WS_THREADS = WS_CONS + WS_PROD;
+constexpr int WS_NBUF = 4;       // ring depth
+constexpr int WS_KC = 2;         // sweeps per ring buffer
+constexpr int WS_BAR_CONS = 1 + 2 * WS_NBUF, WS_BAR_TABLES = 2 + 2 * WS_NBUF, WS_BAR_STEP = 3 + 2 * WS_NBUF;
+__device__ __forceinline__ void ws_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void ws_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// floats behind the FP64 region: cells [WS_NBUF][SPC][2 WS_KC][SW], tables [2 layers][SW units][SW / 4 x 16 + 1 pad], margins [2][SW]
+template <int SW>
+__host__ __device__ inline size_t ws_smem_bytes(int N, int nh) {
+  constexpr int NWC = WS_CONS / 32, SPC = NWC * (32 / SW);
+  return ce_smem_doubles(N, nh, SW, NWC) * sizeof(double) +
+         ((size_t)WS_NBUF * SPC * 2 * WS_KC * SW + (size_t)2 * SW * ((SW / 4) * 16 + 1) + 2 * SW) * sizeof(float);
+}
+
+template <int SW>
+__global__ void __launch_bounds__(WS_THREADS, 1) cd_epoch_ws_kernel(const CdEpochArgs a) {
+  extern __shared__ __align__(16) double ce_smem[];
+  constexpr int NT = WS_CONS, NW = NT / 32, CPW = 32 / SW, SPC = NW * CPW;   // consumer threads / warps, slots per warp / per CTA
+  constexpr int CHUNK_FLOATS = SPC * 2 * WS_KC * SW;
+  constexpr int NT4 = SW / 4;                                                 // nibble tables per unit
+  constexpr int TAB_LD = NT4 * 16 + 1;                                        // a unit's tables, padded: the lanes of a slot read the SAME nibble
+  constexpr int TAB_FLOATS = SW * TAB_LD;                                     // per layer
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int N = a.N, nh = a.nh, LD = N | 1, G = nh * N + N + nh, GP = nh * LD + N + nh;
+  double* Wsm = ce_smem;
+  double* bsm = Wsm + (size_t)SW * LD;  // W region padded to SW rows
+  double* csm = bsm + N;
+  double* partial = csm + nh;
+  double* wpart = partial + 2 * (size_t)G;
+  float* cells = reinterpret_cast<float*>(ce_smem + ce_smem_doubles(N, nh, SW, NW));  // cell * 2^-16
+  float* tabs = cells + (size_t)WS_NBUF * CHUNK_FLOATS;                               // [layer][unit][t][m]
+  float* margins = tabs + 2 * TAB_FLOATS;                                             // [layer][unit]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nranks = (int)cluster.num_blocks();
+  const int nslots = nranks * SPC;
+  const uint32_t qv0 = 4u * (uint32_t)((nh + 31) / 32);
+
+  __shared__ double e2tab[EXP2_TABLE];
+  fill_exp2_table(e2tab);
+  for (int idx = tid; idx < nh * N; idx += WS_THREADS) Wsm[(idx / N) * LD + idx % N] = a.W[idx];
+  for (int idx = tid; idx < N; idx += WS_THREADS) bsm[idx] = a.b[idx];
+  for (int idx = tid; idx < nh; idx += WS_THREADS) csm[idx] = a.c[idx];
+  __syncthreads();
+
+  if (tid >= WS_CONS) {
+    // ================================= producers =================================
+    const int ptid = tid - WS_CONS;
+    // weight of hidden unit i / visible unit j as seen from output unit `unit` of `layer` towards its input `in`
+    auto weight = [&](int layer, int unit, int in) -> double {
+      if (layer == 0) return (unit < nh && in < N) ? Wsm[unit * LD + in] : 0.0;   // h | v: row of W
+      return (unit < N && in < nh) ? Wsm[in * LD + unit] : 0.0;                    // v | h: column of W
+    };
+    auto build_tables = [&]() {
+      // one thread per (layer, unit, nibble t): its four weights once, then the 16 subset sums in a fixed order
+      for (int e = ptid; e < 2 * SW * NT4; e += WS_PROD) {
+        const int t = e % NT4, unit = (e / NT4) % SW, layer = e / (SW * NT4);
+        const int units = layer ? N : nh;
+        float w4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, base = 0.0f;
+        if (unit < units) {
+          if (t == 0) base = (float)(layer ? bsm[unit] : csm[unit]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w4[i] = (float)weight(layer, unit, 4 * t + i);
+        }
+        float* dst = tabs + (size_t)layer * TAB_FLOATS + (size_t)unit * TAB_LD + 16 * t;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          float v = base;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if ((m >> i) & 1) v += w4[i];
+          dst[m] = v;
+        }
+      }
+      // margins: the last warps of the producer group, one unit each
+      for (int e = ptid - (WS_PROD - 2 * SW); e >= 0 && e < 2 * SW; e += WS_PROD) {
+        const int unit = e % SW, layer = e / SW;
+        const int units = layer ? N : nh, n_in = layer ? nh : N;
+        float mg = 4.0f;   // padding lanes, non-finite or huge weights: everything goes to the exact path (or is masked)
+        if (unit < units) {
+          double sabs = fabs(layer ? bsm[unit] : csm[unit]);
+          for (int in = 0; in < n_in; ++in) sabs += fabs(weight(layer, unit, in));
+          const double md = (0.25 * (double)(n_in + 6) * 0x1.0p-24 * sabs + 0x1.0p-17) * 1.001;
+          if (md < 0.25) mg = (float)md;
+        }
+        margins[e] = mg;
+      }
+      __threadfence_block();
+      __syncwarp();
+      ws_bar_arrive(WS_BAR_TABLES, WS_THREADS);
+    };
+    build_tables();
+    int chunk = 0;
+    for (int step = 0; step < a.num_batches; ++step) {
+      const int64_t c0 = (int64_t)step * a.neg_batch;
+      const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
+      for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {
+        for (int s0 = 0; s0 < a.k; s0 += WS_KC, ++chunk) {
+          const int b = chunk % WS_NBUF;
+          if (chunk >= WS_NBUF) ws_bar_sync(1 + WS_NBUF + b, WS_THREADS);  // the consumers have released this buffer
+          const int ns = a.k - s0 < WS_KC ? a.k - s0 : WS_KC;
+          float* buf = cells + (size_t)b * CHUNK_FLOATS;
+          // item = (slot of the CTA, conditional update of the chunk, Philox call c): the call serves units 4 c .. 4 c + 3 (high
+          // 16-bit halves) and 16 + 4 c .. 16 + 4 c + 3 (low halves) of the layer
+          for (int item = ptid; item < SPC * 2 * WS_KC * 4; item += WS_PROD) {
+            const int c = item & 3, cond = (item >> 2) % (2 * WS_KC), sl = (item >> 2) / (2 * WS_KC);
+            const int layer = cond & 1;                       // 0: h | v, 1: v | h
+            const int units = layer ? N : nh;
+            if (4 * c >= units || (cond >> 1) >= ns) continue;
+            const uint32_t ch = (uint32_t)(ch0 + rank * SPC + sl);
+            const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s0 + (cond >> 1));
+            uint32_t r[4];
+            philox4x32_10(ch, 0u, sweep, (layer ? qv0 : 0u) + (uint32_t)c, a.key0, a.key1, r);
+            float* dst = buf + ((size_t)sl * 2 * WS_KC + cond) * SW;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              if (4 * c + w < SW) dst[4 * c + w] = (float)(r[w] >> 16) * 0x1.0p-16f;
+              if (SW > 16 && 16 + 4 * c + w < SW) dst[16 + 4 * c + w] = (float)(r[w] & 0xFFFFu) * 0x1.0p-16f;
+            }
+          }
+          __threadfence_block();
+          __syncwarp();
+          ws_bar_arrive(1 + b, WS_THREADS);                                    // full
+        }
+      }
+      cluster.sync();   // the cluster barriers of the step involve every thread of the cluster
+      cluster.sync();
+      ws_bar_sync(WS_BAR_STEP, WS_THREADS);   // the consumers have applied the update
+      if (step + 1 < a.num_batches) build_tables();
+    }
+    cluster.sync();
+    return;
+  }
+
+  // ================================= consumers =================================
+  const int warp = tid >> 5;
+  const int u = lane % SW, sub = lane / SW;
+  const uint32_t slot_mask = SW == 32 ? 0xffffffffu : ((1u << SW) - 1u);
+  const int slot_in_cta = warp * CPW + sub;
+  const int slot = rank * SPC + slot_in_cta;
+  const int uh = u < nh ? u : nh - 1, uv = u < N ? u : N - 1;
+  auto hidden_pre = [&](uint32_t vm) {
+    const double* row = Wsm + uh * LD;
+    double x[4] = {csm[uh], 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < SW; ++j)
+      if ((vm >> j) & 1u) x[j & 3] += row[j];
+    return (x[0] + x[1]) + (x[2] + x[3]);
+  };
+  auto visible_pre = [&](uint32_t hm) {
+    const double* col = Wsm + uv;
+    double x[4] = {bsm[uv], 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < SW; ++i)
+      if ((hm >> i) & 1u) x[i & 3] += col[i * LD];
+    return (x[0] + x[1]) + (x[2] + x[3]);
+  };
+  auto slot_bits = [&](bool bit) { return (__ballot_sync(0xffffffffu, bit) >> (sub * SW)) & slot_mask; };
+  auto first_row = [&](const double* rows_all, int64_t total, int batch, int step) {
+    const int64_t start = (int64_t)step * batch;
+    const int64_t rows = total - start < batch ? total - start : batch;
+    return (step < a.num_batches && slot < rows && u < N) ? rows_all[(start + slot) * N + u] : 0.0;
+  };
+  double next_pos = first_row(a.pos, a.B_total, a.pos_batch, 0), next_neg = first_row(a.neg, a.C_total, a.neg_batch, 0);
+
+  // float pre-activation of this lane's unit from the nibble tables: SW / 4 independent reads and a short add tree
+  const float* tab_h = tabs + (size_t)u * TAB_LD;
+  const float* tab_v = tabs + TAB_FLOATS + (size_t)u * TAB_LD;
+  auto table_pre = [&](const float* tab, uint32_t mask) {
+    float part[NT4];
+#pragma unroll
+    for (int t = 0; t < NT4; ++t) part[t] = tab[16 * t + ((mask >> (4 * t)) & 15u)];
+#pragma unroll
+    for (int w = 1; w < NT4; w <<= 1)
+#pragma unroll
+      for (int t = 0; t + w < NT4; t += 2 * w) part[t] += part[t + w];
+    return part[0];
+  };
+  // bit 0: u < sigmoid(x) certainly true, bit 1: certainly false (neither: undecided).  lof = cell 2^-16;
+  // L q - 1 < 0  <=>  L < 1 / q = sigmoid
+  auto filter = [&](float xf, float lof, float margin, bool& sure1, bool& sure0) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xf * -1.4426950408889634f));
+    const float q = 1.0f + e;
+    const bool in_range = fabsf(xf) <= 64.0f;
+    sure1 = in_range && fmaf(lof + (0x1.0p-16f + margin), q, -1.0f) < 0.0f;
+    sure0 = in_range && fmaf(lof - margin, q, -1.0f) >= 0.0f;
+  };
+
+  int chunk = 0;
+  for (int step = 0; step < a.num_batches; ++step) {
+    const int64_t p0 = (int64_t)step * a.pos_batch, c0 = (int64_t)step * a.neg_batch;
+    const int Bs = (int)(a.B_total - p0 < a.pos_batch ? a.B_total - p0 : a.pos_batch);
+    const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
+    const double* pos_rows = a.pos + p0 * N;
+    const double* neg_rows = a.neg + c0 * N;
+    const double first_pos = next_pos, first_neg = next_neg;
+    next_pos = first_row(a.pos, a.B_total, a.pos_batch, step + 1);
+    next_neg = first_row(a.neg, a.C_total, a.neg_batch, step + 1);
+    double accW[SW];
+#pragma unroll
+    for (int j = 0; j < SW; ++j) accW[j] = 0.0;
+    double accb = 0.0, accc = 0.0;
+    auto accumulate = [&](uint32_t vm, bool valid, double weight) {
+      const double sg = sigmoid_tab(hidden_pre(vm), e2tab);
+      const double pw = (valid && u < nh) ? weight * sg : 0.0;
+      accc += pw;
+#pragma unroll
+      for (int j = 0; j < SW; ++j)
+        if ((vm >> j) & 1u) accW[j] += pw;
+      if (valid && ((vm >> u) & 1u)) accb += weight;
+    };
+
+    for (int r0 = 0; r0 < Bs; r0 += nslots) {
+      const int r = r0 + slot;
+      const bool valid = r < Bs;
+      const double raw = r0 == 0 ? first_pos : ((valid && u < N) ? pos_rows[(int64_t)r * N + u] : 0.0);
+      const uint32_t vm = slot_bits(raw != 0.0);
+      accumulate(vm, valid, -1.0 / (double)Bs);
+    }
+    ws_bar_sync(WS_BAR_TABLES, WS_THREADS);   // the producers have rebuilt the tables and margins from this step's parameters
+    const float mar_h = margins[u], mar_v = margins[SW + u];
+    for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {
+      const int ch = ch0 + slot;
+      const bool valid = ch < Cs;
+      const double raw = ch0 == 0 ? first_neg : ((valid && u < N) ? neg_rows[(int64_t)ch * N + u] : 0.0);
+      uint32_t vm = slot_bits(raw != 0.0);
+      const uint32_t cid0 = (uint32_t)ch, cid1 = 0u;
+      const bool warp_has_chain = __any_sync(0xffffffffu, valid);
+      for (int s0 = 0; s0 < a.k; s0 += WS_KC, ++chunk) {
+        const int b = chunk % WS_NBUF;
+        ws_bar_sync(1 + b, WS_THREADS);   // full: the producers have drawn this chunk's cells
+        const float* buf = cells + (size_t)b * CHUNK_FLOATS + (size_t)slot_in_cta * 2 * WS_KC * SW + u;
+        const int ns = a.k - s0 < WS_KC ? a.k - s0 : WS_KC;
+        if (warp_has_chain) {
+          for (int ss = 0; ss < ns; ++ss) {
+            const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s0 + ss);
+            const float lof_h = buf[(2 * ss) * SW], lof_v = buf[(2 * ss + 1) * SW];
+            bool s1, s0f;
+            filter(table_pre(tab_h, vm), lof_h, mar_h, s1, s0f);
+            bool one = s1 && u < nh;
+            const bool open_h = !(s1 || s0f) && u < nh;
+            uint32_t hm_all = __ballot_sync(0xffffffffu, one);           // both votes are issued back to back
+            if (__any_sync(0xffffffffu, open_h)) {
+              if (open_h) one = ce_decide_exact(hidden_pre(vm), (uint32_t)(lof_h * 65536.0f), u, 0u, cid0, cid1, sweep, a.key0, a.key1);
+              __syncwarp();
+              hm_all = __ballot_sync(0xffffffffu, one);
+            }
+            const uint32_t hm = (hm_all >> (sub * SW)) & slot_mask;
+            filter(table_pre(tab_v, hm), lof_v, mar_v, s1, s0f);
+            one = s1 && u < N;
+            const bool open_v = !(s1 || s0f) && u < N;
+            uint32_t vm_all = __ballot_sync(0xffffffffu, one);
+            if (__any_sync(0xffffffffu, open_v)) {
+              if (open_v) one = ce_decide_exact(visible_pre(hm), (uint32_t)(lof_v * 65536.0f), u, qv0, cid0, cid1, sweep, a.key0, a.key1);
+              __syncwarp();
+              vm_all = __ballot_sync(0xffffffffu, one);
+            }
+            vm = (vm_all >> (sub * SW)) & slot_mask;
+          }
+        }
+        ws_bar_arrive(1 + WS_NBUF + b, WS_THREADS);   // empty
+      }
+      accumulate(vm, valid, 1.0 / (double)Cs);
+    }
+
+    // the slots of a warp, then the warps of the CTA, in a fixed order (as in cd_epoch_kernel)
+#pragma unroll
+    for (int off = SW; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < SW; ++j) accW[j] += __shfl_xor_sync(0xffffffffu, accW[j], off);
+      accb += __shfl_xor_sync(0xffffffffu, accb, off);
+      accc += __shfl_xor_sync(0xffffffffu, accc, off);
+    }
+    double* mine = wpart + (size_t)warp * GP;
+    if (sub == 0) {
+      if (u < nh) {
+#pragma unroll
+        for (int j = 0; j < SW; ++j)
+          if (j < N) mine[u * LD + j] = accW[j];
+        mine[nh * LD + N + u] = accc;
+      }
+      if (u < N) mine[nh * LD + u] = accb;
+    }
+    ws_bar_sync(WS_BAR_CONS, WS_CONS);
+    double* my_partial = partial;
+    double* my_red = partial + G;
+    for (int idx = tid; idx < G; idx += NT) {
+      const int off = idx < nh * N ? (idx / N) * LD + idx % N : idx - nh * N + nh * LD;
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += wpart[(size_t)w * GP + off];
+      my_partial[idx] = t;
+    }
+    cluster.sync();
+    const int slice = (G + nranks - 1) / nranks;
+    const int lo = rank * slice, hi = lo + slice < G ? lo + slice : G;
+    for (int idx = lo + tid; idx < hi; idx += NT) {
+      double g = 0.0;
+      for (int rk = 0; rk < nranks; ++rk) g += cluster.map_shared_rank(my_partial, rk)[idx];
+      my_red[idx - lo] = g;
+      if (a.g_last != nullptr && step == a.num_batches - 1) a.g_last[idx] = g;
+    }
+    cluster.sync();
+    if (a.lr != 0.0) {
+      for (int idx = tid; idx < G; idx += NT) {
+        const int owner = idx / slice;
+        const double g = cluster.map_shared_rank(my_red, owner)[idx - owner * slice];
+        double* prm = idx < nh * N ? &Wsm[(idx / N) * LD + idx % N] : (idx < nh * N + N ? &bsm[idx - nh * N] : &csm[idx - nh * N - N]);
+        *prm -= a.lr * g;
+      }
+    }
+    ws_bar_sync(WS_BAR_STEP, WS_THREADS);   // parameters final: the producers rebuild the tables, the consumers go on
+  }
+  cluster.sync();  // nobody leaves while its shares may still be read
+  if (rank == 0 && a.lr != 0.0) {
+    for (int idx = tid; idx < nh * N; idx += NT) a.W[idx] = Wsm[(idx / N) * LD + idx % N];
+    for (int idx = tid; idx < N; idx += NT) a.b[idx] = bsm[idx];
+    for (int idx = tid; idx < nh; idx += NT) a.c[idx] = csm[idx];
+  }
+}
+
 // ---- layers of 33 .. 64 units ------------------------------------------------------------------------
 // Same scheme with one chain per warp and two units per lane (u and u + 32).  A lane cannot keep a row of the
 // gradient in registers any more, so after every round the warps park (w p, v, w) of their row in shared memory
@@ -597,6 +935,15 @@ static int launch_cd_epoch(const CdEpochArgs& a, cudaStream_t st) {
   return launch_one_cluster(cd_epoch_kernel<SW>, NT, ce_smem_doubles(a.N, a.nh, SW, NT / 32) * sizeof(double), a, st, cluster_on);
 }
 
+template <int SW>
+static int launch_cd_epoch_ws(const CdEpochArgs& a, cudaStream_t st) {
+  static int cluster_on[QCB_MAX_DEVICES] = {0};
+  return launch_one_cluster(cd_epoch_ws_kernel<SW>, WS_THREADS, ws_smem_bytes<SW>(a.N, a.nh), a, st, cluster_on);
+}
+
+// 0: automatic (the warp-specialised kernel for layers of at most 16 units), 1: never the warp-specialised kernel
+int g_cd_epoch_mode = 0;
+
 static int launch_cd_epoch_wide(const CdEpochArgs& a, cudaStream_t st) {
   static int cluster_on[QCB_MAX_DEVICES] = {0};
   return launch_one_cluster(cd_epoch_wide_kernel, CEW_THREADS, cew_smem_doubles() * sizeof(double), a, st, cluster_on);
@@ -628,6 +975,11 @@ int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* p
   a.sweep0 = (uint32_t)sweep0;
   a.g_last = g_last;
   const int m = N > nh ? N : nh;
+  if (g_cd_epoch_mode == 0 && k >= 1) {
+    if (m <= 8) return launch_cd_epoch_ws<8>(a, st);
+    if (m <= 16) return launch_cd_epoch_ws<16>(a, st);
+    // 17..32 units: measured slower than the single-role kernel (8 table reads per update, 32 gradient accumulators per lane: spills)
+  }
   if (m <= 8) return launch_cd_epoch<8>(a, st);
   if (m <= 16) return launch_cd_epoch<16>(a, st);
   if (m <= 32) return launch_cd_epoch<32>(a, st);

@@ -330,6 +330,39 @@ def test_cd_epoch_matches_oracle(lib, cuda, n, nh, B, C, pb, nb_, k):
     assert np.array_equal(tn.cpu().numpy(), neg) and np.array_equal(tp.cpu().numpy(), pos)
 
 
+@pytest.mark.parametrize("n,nh,B,C,pb,nb_,k,scale", [(10, 10, 1000, 2000, 100, 200, 10, None), (7, 5, 53, 90, 10, 17, 3, None),
+                                                      (16, 16, 700, 1300, 350, 650, 1, None), (3, 12, 64, 64, 16, 16, 5, None),
+                                                      (12, 9, 120, 150, 120, 150, 3, 3.0), (16, 10, 90, 90, 30, 30, 4, 40.0),
+                                                      (1, 1, 10, 10, 5, 5, 2, None), (8, 8, 2000, 4096, 1000, 2048, 2, None)])
+def test_cd_epoch_warp_specialised_equals_single_role_kernel(lib, cuda, n, nh, B, C, pb, nb_, k, scale):
+    """Layers of at most 16 units run the warp-specialised epoch kernel (producer warps draw the Philox cells into a ring and
+    rebuild float nibble tables of the pre-activations after every update, consumer warps run the chain from those tables
+    with a rigorous margin and the exact FP64 path behind it): same
+    decisions and the same summation order as the single-role kernel — identical parameters and gradients, bit for bit; more
+    chains than slots (several rounds per step), sweeps that do not fill a ring buffer, short last batches, strong couplings."""
+    from qucumber_b200 import _lib
+
+    W, b, c = make_binary_params(n, nh, 900 + n, bias_scale=0.1 if scale is None else 1.0, weight_scale=scale)
+    pos, neg = random_states(B, n, 901), random_states(C, n, 902)
+    num_batches = min(-(-B // pb), -(-C // nb_))
+    outs = []
+    for mode in (0, 1):
+        tW, tb, tc = (torch.tensor(x, device=cuda) for x in (W, b, c))
+        tp, tn = torch.tensor(pos, device=cuda), torch.tensor(neg, device=cuda)
+        g_last = torch.empty(nh * n + n + nh, dtype=torch.double, device=cuda)
+        _lib.check(lib.qcb_set_cd_epoch_mode(mode), "mode")
+        try:
+            _lib.check(lib.qcb_rbm_cd_epoch(_lib.ptr(tW), _lib.ptr(tb), _lib.ptr(tc), n, nh, _lib.ptr(tp), B, pb, _lib.ptr(tn), C, nb_,
+                                            num_batches, k, 0.05, 4711, 9, _lib.ptr(g_last), _lib.stream_ptr(cuda)), "qcb_rbm_cd_epoch")
+            torch.cuda.synchronize()
+        finally:
+            _lib.check(lib.qcb_set_cd_epoch_mode(0), "mode")
+        outs.append([t.cpu() for t in (tW, tb, tc, g_last)])
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert lib.qcb_set_cd_epoch_mode(2) != 0
+
+
 def test_cd_epoch_rejects_large_layers(lib, cuda):
     from qucumber_b200 import _lib
 

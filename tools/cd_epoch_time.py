@@ -24,13 +24,16 @@ def run():
                                     100, k, 0.01, 1, 0, None, _lib.stream_ptr(dev)), "cd_epoch")
 
 
-for _ in range(3):
-    run()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-torch.cuda.synchronize()
-e0.record()
-for _ in range(10):
-    run()
-e1.record()
-torch.cuda.synchronize()
-print(f"fused epoch kernel N = nh = {n}: {e0.elapsed_time(e1) / 10:.3f} ms per epoch of 100 steps (k = {k})")
+for mode in (0, 1):  # 0: warp-specialised kernel where it applies (layers <= 16 units), 1: single-role kernel
+    lib.qcb_set_cd_epoch_mode(mode)
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"fused epoch kernel N = nh = {n}, mode {mode}: {e0.elapsed_time(e1) / 10:.3f} ms per epoch of 100 steps (k = {k})")
+lib.qcb_set_cd_epoch_mode(0)
