@@ -305,8 +305,16 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
 // consumers sync).  Same draws, same exact decisions, same reduction order as cd_epoch_kernel — the two kernels return the same
 // parameters bit for bit.
 constexpr int WS_CONS = 256, WS_PROD = 256, WS_THREADS = WS_CONS + WS_PROD;
-constexpr int WS_NBUF = 4;       // ring depth
-constexpr int WS_KC = 2;         // sweeps per ring buffer
+// ring depth x sweeps per buffer, measured at N = nh = 10, k = 10: 4 x 2: 0.657 ms per epoch, 6 x 2: 0.643, 3 x 5: 0.610, 2 x 10: 0.594
+// (every hand-over is a 512-thread named barrier that also couples the consumer warps to each other)
+#ifndef WS_NBUF_V
+#define WS_NBUF_V 2
+#endif
+#ifndef WS_KC_V
+#define WS_KC_V 10
+#endif
+constexpr int WS_NBUF = WS_NBUF_V;       // ring depth
+constexpr int WS_KC = WS_KC_V;         // sweeps per ring buffer
 constexpr int WS_BAR_CONS = 1 + 2 * WS_NBUF, WS_BAR_TABLES = 2 + 2 * WS_NBUF, WS_BAR_STEP = 3 + 2 * WS_NBUF;
 __device__ __forceinline__ void ws_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void ws_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -353,6 +361,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cd_epoch_ws_kernel(const CdEpoc
   if (tid >= WS_CONS) {
     // ================================= producers =================================
     const int ptid = tid - WS_CONS;
+    int ring_next = 0;   // chunks drawn so far = the ring position of the next one
     // weight of hidden unit i / visible unit j as seen from output unit `unit` of `layer` towards its input `in`
     auto weight = [&](int layer, int unit, int in) -> double {
       if (layer == 0) return (unit < nh && in < N) ? Wsm[unit * LD + in] : 0.0;   // h | v: row of W
@@ -397,39 +406,56 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cd_epoch_ws_kernel(const CdEpoc
       ws_bar_arrive(WS_BAR_TABLES, WS_THREADS);
     };
     build_tables();
-    int chunk = 0;
-    for (int step = 0; step < a.num_batches; ++step) {
+    // Chunks are numbered through the whole epoch: chunk q belongs to step q / cps (cps chunks per full step; a short last
+    // negative batch has fewer rounds, its surplus chunks are never drawn).  Before the cluster barriers of step t the
+    // producers have drawn all of step t's chunks and up to WS_NBUF chunks of step t + 1: the ring slots those need were last
+    // used by chunks of step <= t, which the consumers release before they reach the same barriers — no producer ever waits for
+    // something that happens behind a barrier it has not joined.
+    auto draw_chunk = [&](int step, int local) {   // local = round * chunks_per_round + sweep chunk, within the step
+      const int cpr = (a.k + WS_KC - 1) / WS_KC;
+      const int ch0 = (local / cpr) * nslots, s0 = (local % cpr) * WS_KC;
+      const int ns = a.k - s0 < WS_KC ? a.k - s0 : WS_KC;
+      for (int item = ptid; item < SPC * 2 * WS_KC * 4; item += WS_PROD) {
+        // item = (slot of the CTA, conditional update of the chunk, Philox call c): the call serves units 4 c .. 4 c + 3 (high
+        // 16-bit halves) and 16 + 4 c .. 16 + 4 c + 3 (low halves) of the layer
+        const int c = item & 3, cond = (item >> 2) % (2 * WS_KC), sl = (item >> 2) / (2 * WS_KC);
+        const int layer = cond & 1;                       // 0: h | v, 1: v | h
+        const int units = layer ? N : nh;
+        if (4 * c >= units || (cond >> 1) >= ns) continue;
+        const uint32_t ch = (uint32_t)(ch0 + rank * SPC + sl);
+        const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s0 + (cond >> 1));
+        uint32_t r[4];
+        philox4x32_10(ch, 0u, sweep, (layer ? qv0 : 0u) + (uint32_t)c, a.key0, a.key1, r);
+        float* dst = cells + (size_t)(ring_next % WS_NBUF) * CHUNK_FLOATS + ((size_t)sl * 2 * WS_KC + cond) * SW;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          if (4 * c + w < SW) dst[4 * c + w] = (float)(r[w] >> 16) * 0x1.0p-16f;
+          if (SW > 16 && 16 + 4 * c + w < SW) dst[16 + 4 * c + w] = (float)(r[w] & 0xFFFFu) * 0x1.0p-16f;
+        }
+      }
+    };
+    auto chunks_of_step = [&](int step) {
+      if (step >= a.num_batches) return 0;
       const int64_t c0 = (int64_t)step * a.neg_batch;
       const int Cs = (int)(a.C_total - c0 < a.neg_batch ? a.C_total - c0 : a.neg_batch);
-      for (int ch0 = 0; ch0 < Cs; ch0 += nslots) {
-        for (int s0 = 0; s0 < a.k; s0 += WS_KC, ++chunk) {
-          const int b = chunk % WS_NBUF;
-          if (chunk >= WS_NBUF) ws_bar_sync(1 + WS_NBUF + b, WS_THREADS);  // the consumers have released this buffer
-          const int ns = a.k - s0 < WS_KC ? a.k - s0 : WS_KC;
-          float* buf = cells + (size_t)b * CHUNK_FLOATS;
-          // item = (slot of the CTA, conditional update of the chunk, Philox call c): the call serves units 4 c .. 4 c + 3 (high
-          // 16-bit halves) and 16 + 4 c .. 16 + 4 c + 3 (low halves) of the layer
-          for (int item = ptid; item < SPC * 2 * WS_KC * 4; item += WS_PROD) {
-            const int c = item & 3, cond = (item >> 2) % (2 * WS_KC), sl = (item >> 2) / (2 * WS_KC);
-            const int layer = cond & 1;                       // 0: h | v, 1: v | h
-            const int units = layer ? N : nh;
-            if (4 * c >= units || (cond >> 1) >= ns) continue;
-            const uint32_t ch = (uint32_t)(ch0 + rank * SPC + sl);
-            const uint32_t sweep = a.sweep0 + (uint32_t)(step * a.k + s0 + (cond >> 1));
-            uint32_t r[4];
-            philox4x32_10(ch, 0u, sweep, (layer ? qv0 : 0u) + (uint32_t)c, a.key0, a.key1, r);
-            float* dst = buf + ((size_t)sl * 2 * WS_KC + cond) * SW;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              if (4 * c + w < SW) dst[4 * c + w] = (float)(r[w] >> 16) * 0x1.0p-16f;
-              if (SW > 16 && 16 + 4 * c + w < SW) dst[16 + 4 * c + w] = (float)(r[w] & 0xFFFFu) * 0x1.0p-16f;
-            }
-          }
+      return ((Cs + nslots - 1) / nslots) * ((a.k + WS_KC - 1) / WS_KC);
+    };
+    int done_in_next = 0;   // chunks of the coming step that were drawn ahead
+    for (int step = 0; step < a.num_batches; ++step) {
+      const int mine = chunks_of_step(step), next = chunks_of_step(step + 1);
+      const int ahead = next < WS_NBUF ? next : WS_NBUF;
+      for (int phase = 0; phase < 2; ++phase) {          // 0: the rest of this step, 1: the first chunks of the next one
+        const int from = phase == 0 ? done_in_next : 0, to = phase == 0 ? mine : ahead;
+        for (int local = from; local < to; ++local, ++ring_next) {
+          const int b = ring_next % WS_NBUF;
+          if (ring_next >= WS_NBUF) ws_bar_sync(1 + WS_NBUF + b, WS_THREADS);  // the consumers have released this buffer
+          draw_chunk(step + phase, local);
           __threadfence_block();
           __syncwarp();
           ws_bar_arrive(1 + b, WS_THREADS);                                    // full
         }
       }
+      done_in_next = ahead;
       cluster.sync();   // the cluster barriers of the step involve every thread of the cluster
       cluster.sync();
       ws_bar_sync(WS_BAR_STEP, WS_THREADS);   // the consumers have applied the update
@@ -598,6 +624,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cd_epoch_ws_kernel(const CdEpoc
       for (int w = 0; w < NW; ++w) t += wpart[(size_t)w * GP + off];
       my_partial[idx] = t;
     }
+    // the exchange of cd_epoch_kernel (reduce-scatter and all-gather by remote READS, two cluster barriers).  Measured against
+    // it in this kernel and not faster: an all-to-all push of every share with one barrier (0.661 vs 0.652 ms per epoch at
+    // N = 10, 0.770 vs 0.723 at N = 16), and pushes to the slice owner / from the owner to everybody (0.679 vs 0.658 ms) —
+    // the barrier's release waits for the remote stores, which costs what the remote reads' latency costs.
     cluster.sync();
     const int slice = (G + nranks - 1) / nranks;
     const int lo = rank * slice, hi = lo + slice < G ? lo + slice : G;

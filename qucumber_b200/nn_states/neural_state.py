@@ -86,6 +86,17 @@ def stored_attribute(slot):
     return property(lambda self: getattr(self, slot), lambda self, value: setattr(self, slot, value))
 
 
+_SHUFFLE_STREAMS = {}
+
+
+def _shuffle_stream(device):
+    """The side stream fit() draws the next epoch's shuffle on (created once per device)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SHUFFLE_STREAMS:
+        _SHUFFLE_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return _SHUFFLE_STREAMS[idx]
+
+
 class NeuralStateBase(abc.ABC):
     """Abstract base class for neural-network quantum states backed by CUDA RBMs."""
 
@@ -584,7 +595,7 @@ class NeuralStateBase(abc.ABC):
         # epoch's kernel (one 16-CTA cluster, the rest of the GPU is idle) runs on the caller's stream
         side = None
         if fused_epoch and self._shuffle_generator is not None and self._shuffle_generator.device.type == "cuda":
-            side = torch.cuda.Stream(device=self.device)
+            side = _shuffle_stream(self.device)  # one per device for the process: the caching allocator pools blocks per stream
             side.wait_stream(torch.cuda.current_stream(self.device))
 
         def shuffled_epoch():
@@ -599,6 +610,7 @@ class NeuralStateBase(abc.ABC):
             return p_, n_, ready
 
         ahead = shuffled_epoch() if fused_epoch else None
+        in_flight = []
         for ep in epoch_iter:
             if fused_epoch:
                 pos, neg, ready = ahead
@@ -614,6 +626,14 @@ class NeuralStateBase(abc.ABC):
                 batches = ()
                 if ep != epochs:
                     ahead = shuffled_epoch()  # queued behind nothing but the previous shuffle: overlaps the kernel just launched
+                if side is not None:
+                    # nothing above makes the host wait, so bound its lead: with hundreds of epochs queued, every epoch's
+                    # shuffled copy of the data would be alive at once (and the caching allocator would have to grow for it)
+                    done = torch.cuda.Event()
+                    done.record(torch.cuda.current_stream(self.device))
+                    in_flight.append(done)
+                    if len(in_flight) > 3:
+                        in_flight.pop(0).synchronize()
             else:
                 batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
                 cbs.fire("on_epoch_start", self, ep)
