@@ -105,7 +105,9 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
  * mode 0 (default): automatic — the fastest of them for the shape and k, else the FP64 kernel (fed uniforms), else the
  * composed path (layers of more than 128 units); mode 1: never the integer filter (FP64 tensor-core kernel of csrc/gibbs.cu
  * or the composed path); mode 2: the tcgen05 kernels wherever their shapes fit (any k); mode 3: never a tcgen05 kernel;
- * mode 4: the general tcgen05 kernel for every shape up to 128 units.  All kernels draw the same numbers and make the same
+ * mode 4: the general tcgen05 kernel for every shape up to 128 units; mode 5: the table kernel (csrc/gibbs_table.cu: one
+ * thread per chain, float nibble tables of the pre-activations in shared memory, no tensor cores) for every shape up to 16
+ * units — the automatic choice for such layers.  All kernels draw the same numbers and make the same
  * decisions. */
 int qcb_set_gibbs_mode(int mode);
 

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libqucumber_b200.so")
-SOURCES = ["api.cu", "gibbs.cu", "gibbs_imma.cu", "gibbs_umma.cu", "gibbs_umma_wide.cu", "gibbs_large.cu", "cd_epoch.cu", "energy_grad.cu", "grad_reduce.cu", "grad_reduce_dmma.cu", "grad_reduce_small.cu", "grad_reduce_umma.cu", "enumerate.cu", "rotated.cu", "rotated_gray.cu", "fullspace.cu", "states.cu", "large.cu"]
+SOURCES = ["api.cu", "gibbs.cu", "gibbs_imma.cu", "gibbs_umma.cu", "gibbs_umma_wide.cu", "gibbs_table.cu", "gibbs_large.cu", "cd_epoch.cu", "energy_grad.cu", "grad_reduce.cu", "grad_reduce_dmma.cu", "grad_reduce_small.cu", "grad_reduce_umma.cu", "enumerate.cu", "rotated.cu", "rotated_gray.cu", "fullspace.cu", "states.cu", "large.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",

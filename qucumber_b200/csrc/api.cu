@@ -173,9 +173,10 @@ int qcb_rbm_gibbs(const double* W, const double* U, const double* b, const doubl
 }
 
 int qcb_set_gibbs_mode(int mode) {
-  if (mode < 0 || mode > 4)
+  if (mode < 0 || mode > 5)
     return fail(QCB_ERR_BAD_ARG, "gibbs mode must be 0 (automatic), 1 (FP64 tensor cores only), 2 (tcgen05 integer filter wherever it fits), "
-                                 "3 (mma.sync integer filter, never tcgen05) or 4 (the general tcgen05 kernel for every shape up to 128 units)");
+                                 "3 (mma.sync integer filter, never tcgen05), 4 (the general tcgen05 kernel for every shape up to 128 units) or "
+                                 "5 (the table kernel for every shape up to 16 units)");
   g_gibbs_mode = mode;
   return QCB_OK;
 }

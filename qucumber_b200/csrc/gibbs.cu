@@ -409,6 +409,11 @@ int64_t gibbs_umma_wide_wave_chains(int N, int nhid);
 int try_gibbs_umma_wide(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
                         void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
 
+size_t gibbs_table_workspace_bytes(int N, int nhid);
+int64_t gibbs_table_wave_chains();
+int try_gibbs_table(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0, uint64_t sweep0,
+                    void* ws, size_t ws_bytes, int* handled, cudaStream_t st);
+
 size_t gibbs_large_workspace_bytes(int N, int nhid, int64_t C);
 int run_gibbs_large(const StackedParams& p, const double* v_in, double* v, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                     uint64_t sweep0, const double* uniforms, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -429,8 +434,9 @@ size_t gibbs_workspace_bytes(int N, int nhid) {
   if (HB == 0 || VB == 0) return 0;
   const size_t a = align_up(gibbs_image_doubles(HB, VB) * sizeof(double), 256), b = gibbs_imma_workspace_bytes(N, nhid);
   size_t c = gibbs_umma_workspace_bytes(N, nhid);
-  const size_t w = gibbs_umma_wide_workspace_bytes(N, nhid);
+  const size_t w = gibbs_umma_wide_workspace_bytes(N, nhid), tb = gibbs_table_workspace_bytes(N, nhid);
   if (w > c) c = w;
+  if (tb > c) c = tb;
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
@@ -462,6 +468,13 @@ static int launch_gibbs(const GibbsArgs& a, cudaStream_t st) {
 int g_gibbs_mode = 0;
 constexpr int GIBBS_UMMA_MIN_K = 3;  // below that the mma.sync kernel's TMA-prefetched state tiles win (k = 1: 0.29 vs 0.35 ms)
 static bool use_umma(int k) { return g_gibbs_mode == 2 || (g_gibbs_mode == 0 && k >= GIBBS_UMMA_MIN_K); }
+// The table kernel (gibbs_table.cu: one thread per chain, nibble tables in shared memory) takes layers of at most 16 units in
+// the automatic mode; mode 5 sends every shape it fits through it whatever the mode's other choices.
+constexpr int GIBBS_TABLE_MIN_K = 1;  // measured faster than the mma.sync kernel from one sweep on (2^20 chains, N = nh = 10: 0.084 vs 0.141 ms)
+static bool use_table(int N, int nhid, int k) {
+  if (gibbs_table_workspace_bytes(N, nhid) == 0) return false;
+  return g_gibbs_mode == 5 || (g_gibbs_mode == 0 && k >= GIBBS_TABLE_MIN_K);
+}
 // The general tcgen05 kernel (gibbs_umma_wide.cu: any two layers of up to 128 units).  Layers of 65..128 units have no mma.sync
 // filter kernel: it takes them in modes 0 and 2; mode 4 sends every shape it fits through it (measurement / test hook).
 static bool use_umma_wide(int N, int nhid) {
@@ -509,6 +522,7 @@ size_t gibbs_io_workspace_bytes(int N, int nhid, int64_t C) {
 int64_t gibbs_wave_chains(int N, int nhid) {
   if ((g_gibbs_mode == 0 || g_gibbs_mode == 2) && gibbs_umma_workspace_bytes(N, nhid) != 0) return gibbs_umma_wave_chains();
   if (use_umma_wide(N, nhid)) return gibbs_umma_wide_wave_chains(N, nhid);
+  if (use_table(N, nhid, GIBBS_TABLE_MIN_K)) return gibbs_table_wave_chains();
   const int64_t w = gibbs_imma_wave_chains(N, nhid);
   return w > 0 ? w : (int64_t)sm_count() * 2 * GIBBS_WARPS * CHAINS_PER_WARP;
 }
@@ -533,6 +547,11 @@ int run_gibbs_io(const StackedParams& p, const ChainIO& io, int64_t C, int k, ui
   if (use_umma_wide(p.N, p.nhid())) {
     int handled = 0;
     rc = try_gibbs_umma_wide(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+    if (rc != QCB_OK || handled) return rc;
+  }
+  if (use_table(p.N, p.nhid(), k)) {
+    int handled = 0;
+    rc = try_gibbs_table(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
     if (rc != QCB_OK || handled) return rc;
   }
   if (g_gibbs_mode != 1) {
@@ -603,6 +622,10 @@ static int run_gibbs_rows(const StackedParams& p, const double* v_in, double* v,
     if (use_umma(k)) {
       const int rcu = try_gibbs_umma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
       if (rcu != QCB_OK || handled) return rcu;
+    }
+    if (use_table(p.N, nhid, k)) {
+      const int rct = try_gibbs_table(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, &handled, st);
+      if (rct != QCB_OK || handled) return rct;
     }
     const int rc = try_gibbs_imma(p, io, C, k, seed, chain_id0, sweep0, ws, ws_bytes, nullptr, &handled, st);
     if (rc != QCB_OK || handled) return rc;

@@ -475,7 +475,7 @@ def test_integer_filter_kernel_equals_fp64_kernel(lib, cuda):
             ref = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
         finally:
             _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
-        for mode in (0, 2, 3, 4):  # automatic, tcgen05 / TMEM kernel (where the shape fits), mma.sync kernel, general tcgen05 kernel
+        for mode in (0, 2, 3, 4, 5):  # automatic, tcgen05 / TMEM kernel (where the shape fits), mma.sync kernel, general tcgen05 kernel
             try:
                 _lib.check(lib.qcb_set_gibbs_mode(mode), "mode")
                 got = rbm.gibbs_steps(3, v0, seed=2718, chain_id0=11, sweep0=5)
@@ -528,7 +528,7 @@ def _run_extreme_case(lib, cuda, case, n, nh):
         ref = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
     finally:
         _lib.check(lib.qcb_set_gibbs_mode(0), "mode")
-    for mode in (0, 2, 3, 4):
+    for mode in (0, 2, 3, 4, 5):
         try:
             _lib.check(lib.qcb_set_gibbs_mode(mode), "mode")
             got = rbm.gibbs_steps(4, v0, seed=99, chain_id0=3, sweep0=1)
@@ -537,7 +537,7 @@ def _run_extreme_case(lib, cuda, case, n, nh):
         assert torch.equal(got, ref), (case, n, nh, mode)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n,nh,C", [(7, 5, 37), (33, 20, 50), (64, 64, 19), (10, 10, 1), (63, 41, 300)])
 def test_gibbs_ragged_and_unaligned_state_tiles(lib, cuda, mode, n, nh, C):
     """State tiles reach the kernels by TMA bulk copies when the span is 16-byte aligned and a multiple of 16 bytes;

@@ -41,7 +41,7 @@ def test_pack_unpack_equals_numpy_packbits(lib, cuda, n):
 
 
 @pytest.mark.parametrize("n,nh", SHAPES)
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_sample_chains_bit_exact_vs_oracle(lib, cuda, n, nh, mode):
     """v0 drawn in the kernel (Philox stream 5) + k sweeps == the oracle's restatement, for every kernel (mode 0 automatic,
     1 forces the FP64 kernel, which goes through the separate init / pack kernels, 2 the tcgen05 / TMEM kernel where the
