@@ -86,6 +86,20 @@ def stored_attribute(slot):
     return property(lambda self: getattr(self, slot), lambda self, value: setattr(self, slot, value))
 
 
+class _IndexedRows:
+    """Rows ``source[index]`` that have not been gathered yet: fit() hands the batches of a large data set to
+    compute_batch_gradients in this form, so that a rank gathers only the rows of its own shard (under torch.distributed
+    every rank would otherwise copy the whole shuffled data set every epoch) and no data-set sized temporary exists."""
+
+    def __init__(self, source, index):
+        self.source, self.index = source, index
+        self.shape = (index.shape[0],) + tuple(source.shape[1:])
+
+    def rows(self, first=0, count=None):
+        idx = self.index if count is None else self.index[first:first + count]
+        return self.source.index_select(0, idx)
+
+
 _SHUFFLE_STREAMS = {}
 
 
@@ -427,6 +441,22 @@ class NeuralStateBase(abc.ABC):
         lib = _lib.load()
         na = getattr(rbm, "num_aux", 0)
         seed, sweep0 = self._next_cd_stream(k)
+        if isinstance(samples_batch, _IndexedRows):  # batches of fit() that are still (data, index) pairs: shard first, gather after
+            B, C = samples_batch.shape[0], neg_batch.shape[0]
+            rank, world_size = self._shards_batches(B, C, False)
+            # equal batch sizes reuse the positive permutation for the chains' starting rows (neural_state.py:449-498): one gather
+            # serves both (the CD step does not modify its negative batch)
+            same = (B == C and neg_batch.source is samples_batch.source and neg_batch.index.data_ptr() == samples_batch.index.data_ptr())
+            if world_size > 1:
+                pf, pc = qd.shard_range(B, rank, world_size)
+                nf, nc = qd.shard_range(C, rank, world_size)
+                pos_rows = samples_batch.rows(pf, pc)
+                grad = self._cd_gradients_local(k, pos_rows, pos_rows if same else neg_batch.rows(nf, nc), None, 1.0 / float(B),
+                                                -1.0 / float(C), nf, seed, sweep0)
+                qd.allreduce_sum_(grad)
+                return grad
+            samples_batch = samples_batch.rows()
+            neg_batch = samples_batch if same else neg_batch.rows()
         neg = neg_batch.to(device=self.device, dtype=torch.double).contiguous()
         pos = samples_batch.to(device=self.device, dtype=torch.double).contiguous()
         B, C = pos.shape[0], neg.shape[0]
@@ -458,6 +488,17 @@ class NeuralStateBase(abc.ABC):
         """Per-epoch batching (neural_state.py:449-498): positive batches are a permutation of the
         data; negative batches reuse it when the sizes match, otherwise they are drawn with
         replacement (from the all-Z samples when bases are given)."""
+        gen = self._shuffle_generator
+        if (input_bases is None and gen is not None and gen.device.type == "cuda" and train_samples.is_cuda
+                and train_samples.shape[0] >= self.lazy_batches_min_rows):
+            # large data: only the permutations are drawn now, the rows are gathered batch by batch (and shard by shard)
+            n = train_samples.shape[0]
+            pos_perm = torch.randperm(n, generator=gen, device=train_samples.device)
+            neg_perm = pos_perm if neg_batch_size == pos_batch_size else torch.randint(
+                n, size=(num_batches * neg_batch_size,), dtype=torch.long, generator=gen, device=train_samples.device)
+            pos_b = [_IndexedRows(train_samples, pos_perm[s:s + pos_batch_size]) for s in range(0, n, pos_batch_size)]
+            neg_b = [_IndexedRows(train_samples, neg_perm[s:s + neg_batch_size]) for s in range(0, neg_perm.shape[0], neg_batch_size)]
+            return zip(pos_b, neg_b)
         pos, neg, pos_perm = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples,
                                                    generator=self._shuffle_generator)
         pos_batches = [pos[s:s + pos_batch_size] for s in range(0, len(pos), pos_batch_size)]
@@ -493,6 +534,8 @@ class NeuralStateBase(abc.ABC):
     # asynchronously (an index tensor drawn on the host has to be copied over first, which makes the host wait for the previous
     # epoch's kernel: 1.30 -> 1.1 ms per TFIM epoch); set it to a row count to keep host shuffles below that size
     device_shuffle_min_rows = 0
+    #: from this many samples on, fit() hands batches to compute_batch_gradients as (data, index) pairs (see _IndexedRows)
+    lazy_batches_min_rows = 1 << 16
 
     #: set to False to force one C call per batch even where a whole epoch fits one launch
     fuse_epochs = True
