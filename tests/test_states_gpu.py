@@ -367,6 +367,30 @@ def test_fit_fused_epoch_equals_per_batch_path(lib, cuda):
     assert hook.n == 11
 
 
+@pytest.mark.parametrize("pos_b,neg_b", [(35000, 35000), (20000, 30000)])
+def test_fit_lazy_batches_equal_gathered_batches(lib, cuda, pos_b, neg_b):
+    """From 65 536 samples on fit() hands the batches to compute_batch_gradients as (data, index) pairs (gathered per batch and,
+    under torch.distributed, per shard; one gather for both phases when the batch sizes match): same permutations, same rows,
+    same kernels as the epoch-wide gather — identical parameters."""
+    from qucumber_b200 import PositiveWaveFunction
+
+    n = 12
+    gen = torch.Generator().manual_seed(77)
+    train = (torch.rand(70000, n, generator=gen) < 0.4).double()
+    W, b, c = make_binary_params(n, n, 78)
+    out = []
+    for lazy in (True, False):
+        torch.manual_seed(99)
+        nn = PositiveWaveFunction(n, n, gpu=True)
+        load_binary(nn.rbm_am, W, b, c)
+        nn.lazy_batches_min_rows = (1 << 16) if lazy else (1 << 40)
+        nn.fit(train, epochs=2, pos_batch_size=pos_b, neg_batch_size=neg_b, k=2, lr=0.05)
+        out.append([p.detach().cpu().clone() for p in nn.rbm_am.parameters()])
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
+    assert not torch.equal(out[0][0], torch.as_tensor(W))
+
+
 @pytest.mark.parametrize("kind", ["complex", "density"])
 def test_fit_reaches_reference_training_targets(lib, cuda, kind):
     """The reference's own training regression for states with rotated bases (tests/test_training.py:143-279, `slow`):
