@@ -79,9 +79,9 @@ __host__ __device__ inline int imma_unit(int nb, int c) { return 32 * (nb >> 2) 
 // One CTA (the global maximum fixes the scale); the parameters are staged in shared memory once so that
 // every later pass (maxima, abs-sums, the three digit images) reads them from there.
 constexpr int GI_PACK_LD = 65;  // row stride of the staged weights (odd: column walks are conflict-free)
-__global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, int HB, int VB, unsigned char* __restrict__ img) {
+__global__ void __launch_bounds__(1024) gibbs_pack_imma_kernel(StackedParams p, int HB, int VB, unsigned char* __restrict__ img) {
   __shared__ double Ws[64 * GI_PACK_LD];
-  __shared__ double red[3][8];
+  __shared__ double red[3][32];
   const int H = p.nhid(), N = p.N;
   const int Hpad = 16 * HB, Npad = 16 * VB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) gibbs_pack_imma_kernel(StackedParams p, i
   if (lane == 0) { red[0][warp] = mw; red[1][warp] = rm; red[2][warp] = cm; }
   __syncthreads();
   double s_maxw = red[0][0], s_rowmax = red[1][0], s_colmax = red[2][0];
-  for (int w = 1; w < 8; ++w) {
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
     s_maxw = fmax(s_maxw, red[0][w]);
     s_rowmax = fmax(s_rowmax, red[1][w]);
     s_colmax = fmax(s_colmax, red[2][w]);
@@ -594,7 +594,7 @@ int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, 
   const size_t need = gibbs_imma_workspace_bytes(p.N, p.nhid());
   if (ws == nullptr || ws_bytes < need) return QCB_OK;
   unsigned char* img = reinterpret_cast<unsigned char*>(ws);
-  gibbs_pack_imma_kernel<<<1, 256, 0, st>>>(p, HB, VB, img);
+  gibbs_pack_imma_kernel<<<1, 1024, 0, st>>>(p, HB, VB, img);  // one CTA; the word loop below is what takes the time
   QCB_LAUNCH_CHECK();
   GibbsImmaArgs a;
   a.image = img;

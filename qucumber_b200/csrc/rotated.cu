@@ -448,15 +448,17 @@ __global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__
       double sn, cs;
       sincos(y, &sn, &cs);
       const double ex = exp(x);
-      // Pi (nn_states/density_matrix.py:143-155)
-      pre += log(sqrt(1.0 + 2.0 * ex * cs + exp(2.0 * x)));
-      pim += atan2(ex * sn, 1.0 + ex * cs);
-      // complex sigmoid 1 / (1 + exp(-(x + iy)))  (utils/cplx.py:319-334)
-      const double en = exp(-x);
-      const double dr = 1.0 + en * cs, di = -en * sn;
-      const double inv = 1.0 / (dr * dr + di * di);
-      Sr[k] = dr * inv;
-      Si[k] = -di * inv;
+      // Pi (nn_states/density_matrix.py:143-155): log sqrt(1 + 2 e^x cos y + e^2x) = log|1 + e^(x + iy)|, one exponential for
+      // e^x, e^2x = (e^x)^2 and e^-x = 1 / e^x (x is an affine function of bounded parameters: no overflow concerns beyond exp's own)
+      const double zr = 1.0 + ex * cs, zi = ex * sn;       // 1 + e^(x + iy)
+      const double mod2 = zr * zr + zi * zi;               // = 1 + 2 e^x cos y + e^2x
+      pre += 0.5 * log(mod2);
+      pim += atan2(zi, zr);
+      // complex sigmoid 1 / (1 + exp(-(x + iy))) = e^(x + iy) / (1 + e^(x + iy)) = conj(z) e^(x + iy) / |z|^2  (utils/cplx.py:319-334)
+      const double inv = 1.0 / mod2;
+      const double er = ex * cs, ei = zi;                  // e^(x + iy)
+      Sr[k] = (er * zr + ei * zi) * inv;
+      Si[k] = (ei * zr - er * zi) * inv;
     }
     const double ampl = exp(gp + pre), phs = gm + pim;
     double sn, cs;
@@ -516,13 +518,14 @@ __global__ void __launch_bounds__(256) dm_pair_wide_kernel(const double* __restr
           double sn, cs;
           sincos(y, &sn, &cs);
           const double ex = exp(x);
-          pre += log(sqrt(1.0 + 2.0 * ex * cs + exp(2.0 * x)));   // Pi (nn_states/density_matrix.py:143-155)
-          pim += atan2(ex * sn, 1.0 + ex * cs);
-          const double en = exp(-x);                                // complex sigmoid (utils/cplx.py:319-334)
-          const double dr = 1.0 + en * cs, di = -en * sn;
-          const double inv = 1.0 / (dr * dr + di * di);
-          Sr[m] = dr * inv;
-          Si[m] = -di * inv;
+          const double zr = 1.0 + ex * cs, zi = ex * sn;            // 1 + e^(x + iy); Pi (nn_states/density_matrix.py:143-155)
+          const double mod2 = zr * zr + zi * zi;
+          pre += 0.5 * log(mod2);
+          pim += atan2(zi, zr);
+          const double inv = 1.0 / mod2;                            // complex sigmoid e^(x + iy) / (1 + e^(x + iy)) (utils/cplx.py:319-334)
+          const double er = ex * cs, ei = zi;
+          Sr[m] = (er * zr + ei * zi) * inv;
+          Si[m] = (ei * zr - er * zi) * inv;
         }
       }
       pre = warp_sum(pre);
