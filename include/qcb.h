@@ -197,6 +197,17 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
                     uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale,
                     double* g, void* ws, size_t ws_bytes, void* stream);
 
+/* The same step with both batches as PACKED rows (see "Compact states": ceil(N / 8) bytes per row, numpy.packbits order) — the
+ * form in which fit() keeps large binary data sets: the positive-phase reduction, the Gibbs kernel and the negative-phase
+ * reduction all read and write bits (8 bytes per row at N = 64 instead of 512), nothing is expanded to float64 unless the
+ * tcgen05 gradient kernel hands a batch to its FP64 stand-in.  Same arithmetic, same Philox draws and the same result as
+ * qcb_rbm_cd_step on the unpacked rows.  Shapes: both layers of 33..64 units and at least 16384 rows per phase, k >= 1;
+ * anything else returns QCB_ERR_UNSUPPORTED.  Workspace: qcb_workspace_bytes(QCB_OP_CD_STEP, N, nh, na, max(B, C)). */
+int qcb_rbm_cd_step_packed(const double* W, const double* U, const double* b, const double* c, const double* d,
+                           int N, int nh, int na, const uint8_t* pos_bits, int64_t B, const uint8_t* neg_bits, int64_t C, int k,
+                           uint64_t seed, uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale,
+                           double* g, void* ws, size_t ws_bytes, void* stream);
+
 /* A whole CD-k epoch with plain SGD in ONE launch, for a small BinaryRBM (1 <= N, nh <= 64): the batch loop of
  * NeuralStateBase.fit (nn_states/neural_state.py:611-627).  For step i = 0 .. num_batches-1:
  *   g = qcb_rbm_cd_step(pos[i*pos_batch : (i+1)*pos_batch], neg[i*neg_batch : (i+1)*neg_batch], k, seed,

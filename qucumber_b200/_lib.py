@@ -40,6 +40,8 @@ SIGNATURES = {
                                 _P, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_cd_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_uint64, c_uint64,
                                 c_uint64, c_double, c_double, _P, _P, c_size_t, _P]),
+    "qcb_rbm_cd_step_packed": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_uint64, c_uint64,
+                                c_uint64, c_double, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_cd_epoch": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_double, c_uint64,
                                  c_uint64, _P, _P]),
     "qcb_rbm_logz_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, _P, _P, c_size_t, _P]),

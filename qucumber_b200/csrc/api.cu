@@ -333,6 +333,40 @@ int qcb_rbm_cd_step(const double* W, const double* U, const double* b, const dou
   return run_grad_reduce(p, vk, C, neg_scale, g, 1, base + gb, rb, st);
 }
 
+int qcb_rbm_cd_step_packed(const double* W, const double* U, const double* b, const double* c, const double* d, int N, int nh,
+                           int na, const uint8_t* pos_bits, int64_t B, const uint8_t* neg_bits, int64_t C, int k, uint64_t seed,
+                           uint64_t chain_id0, uint64_t sweep0, double pos_scale, double neg_scale, double* g, void* ws,
+                           size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W);
+  StackedParams p;
+  int rc = make_params(p, W, U, b, c, d, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (B < 1 || C < 1 || k < 1 || g == nullptr || pos_bits == nullptr || neg_bits == nullptr)
+    return fail(QCB_ERR_BAD_ARG, "cd_step_packed: bad arguments (needs B, C, k >= 1)");
+  if (g_gibbs_mode == 1 || gibbs_imma_workspace_bytes(N, nh + na) == 0 || !grad_reduce_bits_supported(N, nh + na, B) ||
+      !grad_reduce_bits_supported(N, nh + na, C))
+    return fail(QCB_ERR_UNSUPPORTED, "cd_step_packed: packed rows need both layers of 33..64 units and at least 16384 rows per phase "
+                                     "(use qcb_rbm_cd_step with float64 rows)");
+  const int64_t R = B > C ? B : C;
+  const size_t gb = gibbs_workspace_bytes_rows(N, nh + na, R);
+  const size_t rb = grad_reduce_workspace_bytes(N, nh + na, R);
+  const size_t vb = align_up((size_t)R * N * sizeof(double), 256);
+  const size_t pb = align_up((size_t)R * packed_row_bytes(N), 256);
+  if (ws == nullptr || ws_bytes < gb + rb + vb + pb) return fail(QCB_ERR_BAD_ARG, "cd_step_packed: workspace too small (size it as QCB_OP_CD_STEP for max(B, C) rows)");
+  char* base = static_cast<char*>(ws);
+  double* rows = reinterpret_cast<double*>(base + gb + rb);   // float64 stand-in rows, only written if the tcgen05 kernel gives a batch up
+  uint8_t* vk_bits = reinterpret_cast<uint8_t*>(base + gb + rb + vb);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_grad_reduce_bits(p, pos_bits, rows, B, pos_scale, g, 0, base + gb, rb, st);
+  if (rc != QCB_OK) return rc;
+  ChainIO io;
+  io.bits_in = neg_bits;
+  io.bits_out = vk_bits;
+  rc = run_gibbs_io(p, io, C, k, seed, chain_id0, sweep0, base, gb, st);
+  if (rc != QCB_OK) return rc;
+  return run_grad_reduce_bits(p, vk_bits, rows, C, neg_scale, g, 1, base + gb, rb, st);
+}
+
 int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* pos, int64_t B_total, int pos_batch,
                      const double* neg, int64_t C_total, int neg_batch, int num_batches, int k, double lr, uint64_t seed,
                      uint64_t sweep0, double* g_last, void* stream) {

@@ -429,6 +429,36 @@ class NeuralStateBase(abc.ABC):
                                            _lib.ptr(grad[0]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self.device)), "qcb_rbm_cdk_neg")
         return grad
 
+    #: rows per phase from which qcb_rbm_cd_step_packed applies (the tcgen05 gradient kernel's threshold)
+    packed_min_rows = 16384
+
+    def _packed_training_shape(self):
+        """Whether fit() may keep the data as packed rows: a BinaryRBM with both layers of 33..64 units."""
+        rbm = self.rbm_am
+        return (len(self.networks) == 1 and hasattr(rbm, "weights") and getattr(rbm, "num_aux", 0) == 0
+                and 33 <= rbm.num_visible <= 64 and 33 <= rbm.num_hidden <= 64)
+
+    def _cd_gradients_packed(self, k, pos_bits, neg_bits, bases, pos_scale, neg_scale, chain_id0, seed, sweep0):
+        """_cd_gradients_local for batches that arrive as PACKED rows (uint8, ceil(N / 8) bytes per row): ONE call,
+        qcb_rbm_cd_step_packed — both reductions and the sweeps read and write bits. Phases of fewer than ``packed_min_rows``
+        rows (a short last batch) are unpacked and take the float64 call."""
+        from ..rbm._sampling import unpack_states
+
+        rbm = self.rbm_am
+        B, C = pos_bits.shape[0], neg_bits.shape[0]
+        if min(B, C) < self.packed_min_rows or int(k) < 1:
+            pos = unpack_states(pos_bits, rbm.num_visible)
+            neg = pos if neg_bits is pos_bits else unpack_states(neg_bits, rbm.num_visible)
+            return self._cd_gradients_local(k, pos, neg, None, pos_scale, neg_scale, chain_id0, seed, sweep0)
+        lib = _lib.load()
+        args, keep = rbm._param_args()
+        g = torch.empty(rbm.num_pars, dtype=torch.double, device=self.device)
+        ws = _lib.workspace(self.device, _lib.workspace_bytes(_lib.OP_CD_STEP, rbm.num_visible, rbm.num_hidden, 0, max(B, C)))
+        _lib.check(lib.qcb_rbm_cd_step_packed(*args, _lib.ptr(pos_bits), B, _lib.ptr(neg_bits), C, int(k), seed, int(chain_id0), sweep0,
+                                              float(pos_scale), float(neg_scale), _lib.ptr(g), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(self.device)), "qcb_rbm_cd_step_packed")
+        return [g]
+
     def compute_batch_gradients(self, k, samples_batch, neg_batch, bases_batch=None):
         """CD-k gradient of one batch (neural_state.py:417-447): positive phase from the data, negative phase from k
         Gibbs sweeps started at ``neg_batch``. Under torch.distributed a large batch is sharded: each rank reduces its
@@ -447,13 +477,16 @@ class NeuralStateBase(abc.ABC):
             # equal batch sizes reuse the positive permutation for the chains' starting rows (neural_state.py:449-498): one gather
             # serves both (the CD step does not modify its negative batch)
             same = (B == C and neg_batch.source is samples_batch.source and neg_batch.index.data_ptr() == samples_batch.index.data_ptr())
-            if world_size > 1:
-                pf, pc = qd.shard_range(B, rank, world_size)
-                nf, nc = qd.shard_range(C, rank, world_size)
+            packed = samples_batch.source.dtype == torch.uint8   # fit() keeps large binary data sets as packed rows
+            if world_size > 1 or packed:
+                pf, pc = qd.shard_range(B, rank, world_size) if world_size > 1 else (0, B)
+                nf, nc = qd.shard_range(C, rank, world_size) if world_size > 1 else (0, C)
                 pos_rows = samples_batch.rows(pf, pc)
-                grad = self._cd_gradients_local(k, pos_rows, pos_rows if same else neg_batch.rows(nf, nc), None, 1.0 / float(B),
-                                                -1.0 / float(C), nf, seed, sweep0)
-                qd.allreduce_sum_(grad)
+                neg_rows = pos_rows if same else neg_batch.rows(nf, nc)
+                local = self._cd_gradients_packed if packed else self._cd_gradients_local
+                grad = local(k, pos_rows, neg_rows, None, 1.0 / float(B), -1.0 / float(C), nf, seed, sweep0)
+                if world_size > 1:
+                    qd.allreduce_sum_(grad)
                 return grad
             samples_batch = samples_batch.rows()
             neg_batch = samples_batch if same else neg_batch.rows()
@@ -496,8 +529,9 @@ class NeuralStateBase(abc.ABC):
             pos_perm = torch.randperm(n, generator=gen, device=train_samples.device)
             neg_perm = pos_perm if neg_batch_size == pos_batch_size else torch.randint(
                 n, size=(num_batches * neg_batch_size,), dtype=torch.long, generator=gen, device=train_samples.device)
-            pos_b = [_IndexedRows(train_samples, pos_perm[s:s + pos_batch_size]) for s in range(0, n, pos_batch_size)]
-            neg_b = [_IndexedRows(train_samples, neg_perm[s:s + neg_batch_size]) for s in range(0, neg_perm.shape[0], neg_batch_size)]
+            rows = self._train_bits if self._train_bits is not None else train_samples
+            pos_b = [_IndexedRows(rows, pos_perm[s:s + pos_batch_size]) for s in range(0, n, pos_batch_size)]
+            neg_b = [_IndexedRows(rows, neg_perm[s:s + neg_batch_size]) for s in range(0, neg_perm.shape[0], neg_batch_size)]
             return zip(pos_b, neg_b)
         pos, neg, pos_perm = self._shuffle_tensors(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples,
                                                    generator=self._shuffle_generator)
@@ -530,6 +564,9 @@ class NeuralStateBase(abc.ABC):
         return pos, neg, pos_perm
 
     _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
+    _train_bits = None         # set by fit(): the packed copy of a large binary data set (see _cd_gradients_packed)
+    #: set to False to keep fit() on float64 rows whatever the data
+    pack_training_data = True
     # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
     # asynchronously (an index tensor drawn on the host has to be copied over first, which makes the host wait for the previous
     # epoch's kernel: 1.30 -> 1.1 ms per TFIM epoch); set it to a row count to keep host shuffles below that size
@@ -622,6 +659,17 @@ class NeuralStateBase(abc.ABC):
             self._shuffle_generator = torch.Generator(device=train_samples.device).manual_seed(self._cd_seed)
         else:
             self._shuffle_generator = torch.Generator().manual_seed(self._cd_seed) if qd.world()[1] > 1 else None
+        # large binary data for a 33..64-unit BinaryRBM: keep a packed copy (1 bit per unit) and hand the batches out as
+        # packed rows — the shuffle gathers 8 bytes per sample instead of 512 and the whole CD step runs on bits
+        self._train_bits = None
+        if (self.pack_training_data and input_bases is None and self._shuffle_generator is not None
+                and self._shuffle_generator.device.type == "cuda" and train_samples.shape[0] >= self.lazy_batches_min_rows
+                and self._packed_training_shape() and int(k) >= 1
+                and min(pos_batch_size, neg_batch_size) // max(1, qd.world()[1]) >= self.packed_min_rows
+                and bool(((train_samples == 0) | (train_samples == 1)).all())):
+            from ..rbm._sampling import pack_states
+
+            self._train_bits = pack_states(train_samples)
         cbs.fire("on_train_start", self)
         num_batches = ceil(train_samples.shape[0] / pos_batch_size)
         epoch_iter = range(starting_epoch, epochs + 1)
@@ -711,4 +759,5 @@ class NeuralStateBase(abc.ABC):
                 break
         self._cd_seed = None
         self._shuffle_generator = None
+        self._train_bits = None
         cbs.fire("on_train_end", self)

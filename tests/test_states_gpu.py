@@ -391,6 +391,66 @@ def test_fit_lazy_batches_equal_gathered_batches(lib, cuda, pos_b, neg_b):
     assert not torch.equal(out[0][0], torch.as_tensor(W))
 
 
+@pytest.mark.parametrize("n,nh,pos_b,neg_b", [(40, 36, 35000, 35000), (64, 64, 20000, 30000), (64, 33, 70000, 17000)])
+def test_fit_packed_training_data_equals_float64_rows(lib, cuda, n, nh, pos_b, neg_b):
+    """Large binary data for a 33..64-unit BinaryRBM is kept as packed rows and every batch runs through
+    qcb_rbm_cd_step_packed: same bits into the same kernels as the float64 rows — identical parameters; a short last batch
+    (fewer than 16 384 rows) is unpacked and takes the float64 call."""
+    from qucumber_b200 import PositiveWaveFunction
+
+    gen = torch.Generator().manual_seed(177)
+    train = (torch.rand(70000 + 5000, n, generator=gen) < 0.4).double()
+    W, b, c = make_binary_params(n, nh, 178)
+    out = []
+    for packed in (True, False):
+        torch.manual_seed(199)
+        nn = PositiveWaveFunction(n, nh, gpu=True)
+        load_binary(nn.rbm_am, W, b, c)
+        nn.pack_training_data = packed
+        launches0 = lib.qcb_launch_count()
+        nn.fit(train, epochs=1, pos_batch_size=pos_b, neg_batch_size=neg_b, k=2, lr=0.05)
+        out.append(([p.detach().cpu().clone() for p in nn.rbm_am.parameters()], lib.qcb_launch_count() - launches0))
+    (pp, lp), (pf, lf) = out
+    for x, y in zip(pp, pf):
+        assert torch.equal(x, y)
+    assert not torch.equal(pp[0], torch.as_tensor(W))
+    # non-binary data keeps the float64 path
+    nn = PositiveWaveFunction(n, nh, gpu=True)
+    soft = train.clone()
+    soft[5, 3] = 0.5
+    nn.fit(soft, epochs=1, pos_batch_size=pos_b, neg_batch_size=neg_b, k=1, lr=0.01)
+    assert nn._train_bits is None
+
+
+def test_cd_step_packed_equals_cd_step(lib, cuda):
+    """qcb_rbm_cd_step_packed == qcb_rbm_cd_step on the unpacked rows (same kernels on the same bits), and its shape limits."""
+    import qucumber_b200 as qb
+    from qucumber_b200 import BinaryRBM, _lib
+
+    n, nh, B, C, k = 50, 64, 20000, 17000, 3
+    W, b, c = make_binary_params(n, nh, 211)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    pos = torch.tensor(random_states(B, n, 212), device=cuda)
+    neg = torch.tensor(random_states(C, n, 213), device=cuda)
+    args, keep = rbm._param_args()
+    ws = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_CD_STEP, n, nh, 0, max(B, C)))
+    g1 = torch.empty(rbm.num_pars, dtype=torch.double, device=cuda)
+    g2 = torch.empty_like(g1)
+    _lib.check(lib.qcb_rbm_cd_step(*args, _lib.ptr(pos), B, _lib.ptr(neg), C, k, 77, 5, 2, 1.0 / B, -1.0 / C, _lib.ptr(g1), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream_ptr(cuda)), "qcb_rbm_cd_step")
+    pb, nb = qb.pack_states(pos), qb.pack_states(neg)
+    _lib.check(lib.qcb_rbm_cd_step_packed(*args, _lib.ptr(pb), B, _lib.ptr(nb), C, k, 77, 5, 2, 1.0 / B, -1.0 / C, _lib.ptr(g2), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr(cuda)), "qcb_rbm_cd_step_packed")
+    assert torch.equal(g1, g2)
+    o = orc.BinaryRBMOracle(W, b, c)
+    vk = o.gibbs_steps_philox(k, neg.cpu().numpy(), seed=77, chain_id0=5, sweep0=2)
+    want = o.effective_energy_gradient(pos.cpu().numpy()) / B - o.effective_energy_gradient(vk) / C
+    assert_close(g2, want, what="packed CD step vs oracle")
+    rc = lib.qcb_rbm_cd_step_packed(*args, _lib.ptr(pb), 1000, _lib.ptr(nb), C, k, 77, 5, 2, 1.0, -1.0, _lib.ptr(g2), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr(cuda))
+    assert rc != 0 and b"16384" in lib.qcb_last_error()
+
+
 @pytest.mark.parametrize("kind", ["complex", "density"])
 def test_fit_reaches_reference_training_targets(lib, cuda, kind):
     """The reference's own training regression for states with rotated bases (tests/test_training.py:143-279, `slow`):
