@@ -223,11 +223,11 @@ int qcb_rbm_cd_epoch(double* W, double* b, double* c, int N, int nh,
                      const double* neg, int64_t C_total, int neg_batch, int num_batches,
                      int k, double lr, uint64_t seed, uint64_t sweep0, double* g_last, void* stream);
 
-/* Kernel selection for qcb_rbm_cd_epoch (process-wide; for tests and measurements).  0 (default): layers of at most 16
+/* Kernel selection for qcb_rbm_cd_epoch (process-wide; for tests and measurements).  0 (default): layers of at most 32
  * units run the warp-specialised kernel (producer warps draw the Philox cells of the coming sweeps into a shared-memory ring,
  * consumer warps run the state-dependent chain from float weight copies in registers, exact FP64 path for what the float
- * filter leaves open); 1: always the single-role kernels of round 1.  Both make the same decisions and add the gradients in
- * the same order: identical parameters bit for bit. */
+ * filter leaves open); 1: always the single-role kernels of round 1.  Both make the same decisions; up to 16 units they also
+ * add the gradients in the same order (identical parameters bit for bit), from 17 units on the sums agree to rounding. */
 int qcb_set_cd_epoch_mode(int mode);
 
 /* ---- Exact enumeration ---------------------------------------------------------------

@@ -21,6 +21,8 @@
 //    identical update to its copy.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
   }
 }
 
-// ---- warp-specialised variant for layers of at most 16 units (round 2) ----------------------------------------------------
+// ---- warp-specialised variant for layers of at most 32 units (round 2) ----------------------------------------------------
 // ncu on cd_epoch_kernel: issue slots 27 % busy, a latency chain — a step is 20 dependent conditional updates of 0.36 us, and
 // half of the instructions a warp issues per update are the Philox rounds of draws that do not depend on the chain's state.
 // Here the CTA has two kinds of warps:
@@ -302,8 +304,9 @@ __global__ void __launch_bounds__(ce_threads(SW), 1) cd_epoch_kernel(const CdEpo
 //    top of the 2^-17 of the float sigmoid); a warp with an undecided lane recomputes that lane in FP64 from the shared-memory
 //    weights and takes the exact path.
 // Hand-over by named barriers (full[b]: producers arrive, consumers sync; empty[b]: the reverse; tables: producers arrive,
-// consumers sync).  Same draws, same exact decisions, same reduction order as cd_epoch_kernel — the two kernels return the same
-// parameters bit for bit.
+// consumers sync).  Same draws and the same exact decisions as cd_epoch_kernel; up to 16 units also the same reduction order —
+// the two kernels return the same parameters bit for bit there (17..32 units: 8 consumer warps of one chain each against the
+// 16 warps of cd_epoch_kernel<32>, so the rows are dealt to different slots and the sums agree to rounding).
 constexpr int WS_CONS = 256, WS_PROD = 256, WS_THREADS = WS_CONS + WS_PROD;
 // ring depth x sweeps per buffer, measured at N = nh = 10, k = 10: 4 x 2: 0.657 ms per epoch, 6 x 2: 0.643, 3 x 5: 0.610, 2 x 10: 0.594
 // (every hand-over is a 512-thread named barrier that also couples the consumer warps to each other)
@@ -971,7 +974,7 @@ static int launch_cd_epoch_ws(const CdEpochArgs& a, cudaStream_t st) {
   return launch_one_cluster(cd_epoch_ws_kernel<SW>, WS_THREADS, ws_smem_bytes<SW>(a.N, a.nh), a, st, cluster_on);
 }
 
-// 0: automatic (the warp-specialised kernel for layers of at most 16 units), 1: never the warp-specialised kernel
+// 0: automatic (the warp-specialised kernel for layers of at most 32 units), 1: never the warp-specialised kernel
 int g_cd_epoch_mode = 0;
 
 static int launch_cd_epoch_wide(const CdEpochArgs& a, cudaStream_t st) {
@@ -1008,7 +1011,10 @@ int run_cd_epoch(double* W, double* b, double* c, int N, int nh, const double* p
   if (g_cd_epoch_mode == 0 && k >= 1) {
     if (m <= 8) return launch_cd_epoch_ws<8>(a, st);
     if (m <= 16) return launch_cd_epoch_ws<16>(a, st);
-    // 17..32 units: measured slower than the single-role kernel (8 table reads per update, 32 gradient accumulators per lane: spills)
+    // 17..32 units: one chain per consumer warp, i.e. 128 slots against the single-role kernel's 256 (rows and chains are dealt
+    // differently, so the sums are associated differently: agreement to rounding, not bit for bit); 1.48 against 2.09 ms per epoch at
+    // N = nh = 32 all the same
+    if (m <= 32) return launch_cd_epoch_ws<32>(a, st);
   }
   if (m <= 8) return launch_cd_epoch<8>(a, st);
   if (m <= 16) return launch_cd_epoch<16>(a, st);

@@ -333,12 +333,15 @@ def test_cd_epoch_matches_oracle(lib, cuda, n, nh, B, C, pb, nb_, k):
 @pytest.mark.parametrize("n,nh,B,C,pb,nb_,k,scale", [(10, 10, 1000, 2000, 100, 200, 10, None), (7, 5, 53, 90, 10, 17, 3, None),
                                                       (16, 16, 700, 1300, 350, 650, 1, None), (3, 12, 64, 64, 16, 16, 5, None),
                                                       (12, 9, 120, 150, 120, 150, 3, 3.0), (16, 10, 90, 90, 30, 30, 4, 40.0),
-                                                      (1, 1, 10, 10, 5, 5, 2, None), (8, 8, 2000, 4096, 1000, 2048, 2, None)])
+                                                      (1, 1, 10, 10, 5, 5, 2, None), (8, 8, 2000, 4096, 1000, 2048, 2, None),
+                                                      (32, 32, 300, 300, 100, 100, 3, None), (20, 30, 64, 64, 16, 16, 2, 2.0),
+                                                      (31, 17, 500, 700, 250, 350, 1, None), (24, 24, 1000, 2000, 100, 200, 10, None)])
 def test_cd_epoch_warp_specialised_equals_single_role_kernel(lib, cuda, n, nh, B, C, pb, nb_, k, scale):
-    """Layers of at most 16 units run the warp-specialised epoch kernel (producer warps draw the Philox cells into a ring and
+    """Layers of at most 32 units run the warp-specialised epoch kernel (producer warps draw the Philox cells into a ring and
     rebuild float nibble tables of the pre-activations after every update, consumer warps run the chain from those tables
     with a rigorous margin and the exact FP64 path behind it): same
-    decisions and the same summation order as the single-role kernel — identical parameters and gradients, bit for bit; more
+    decisions and (up to 16 units) the same summation order as the single-role kernel — identical parameters and gradients, bit for
+    bit there, to rounding for 17..32 units; more
     chains than slots (several rounds per step), sweeps that do not fill a ring buffer, short last batches, strong couplings."""
     from qucumber_b200 import _lib
 
@@ -359,7 +362,10 @@ def test_cd_epoch_warp_specialised_equals_single_role_kernel(lib, cuda, n, nh, B
             _lib.check(lib.qcb_set_cd_epoch_mode(0), "mode")
         outs.append([t.cpu() for t in (tW, tb, tc, g_last)])
     for x, y in zip(*outs):
-        assert torch.equal(x, y)
+        if max(n, nh) <= 16:
+            assert torch.equal(x, y)
+        else:  # 17..32 units: the rows are dealt to different slots, the sums agree to rounding
+            assert_close(x, y.numpy(), rtol=1e-12, what="warp-specialised vs single-role epoch kernel")
     assert lib.qcb_set_cd_epoch_mode(2) != 0
 
 
