@@ -666,13 +666,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cd_epoch_ws_kernel(const CdEpoc
 // gradient is reduce-scattered and all-gathered across the cluster through distributed shared memory
 // (two cluster barriers per step), and every CTA applies the identical update to its copy of W, b, c.
 constexpr int CEW_THREADS = 512, CEW_WARPS = CEW_THREADS / 32, CEW_LD = 65, CEW_GMAX = 64 * 64 + 128;
+constexpr int CEW_TLD = 16 * 16 + 1;  // floats of one unit's nibble tables (+ 1: bank padding)
 constexpr int CEW_EPT = (CEW_GMAX + CEW_THREADS - 1) / CEW_THREADS;  // gradient entries owned by a thread
 static_assert(CEW_EPT * CEW_THREADS >= CEW_GMAX, "every gradient entry needs an owner");
 
 __host__ __device__ inline size_t cew_smem_doubles() {
   // W (64 x 65) | b (64) | c (64) | parked rows (warps x 64) | row weights | row masks | own share (G) | reduced slice (<= G / 8)
-  // ... | float copies of W, b, c and the per-unit filter margins (64 x 65 + 4 x 64 floats)
-  return (size_t)64 * CEW_LD + 64 + 64 + CEW_WARPS * 64 + CEW_WARPS + CEW_WARPS + CEW_GMAX + (CEW_GMAX + 7) / 8 + 8 + (64 * CEW_LD + 4 * 64 + 1) / 2;
+  // ... | float nibble tables of both layers and the per-unit filter margins (2 x 64 x 257 + 2 x 64 floats)
+  return (size_t)64 * CEW_LD + 64 + 64 + CEW_WARPS * 64 + CEW_WARPS + CEW_WARPS + CEW_GMAX + (CEW_GMAX + 7) / 8 + 8 + (2 * 64 * CEW_TLD + 2 * 64 + 1) / 2;
 }
 
 __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdEpochArgs a) {
@@ -688,10 +689,12 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
   unsigned long long* masks = reinterpret_cast<unsigned long long*>(wts + CEW_WARPS);
   double* Gpart = reinterpret_cast<double*>(masks + CEW_WARPS);
   double* Gred = Gpart + CEW_GMAX;
-  float* Wf = reinterpret_cast<float*>(Gred + (CEW_GMAX + 7) / 8 + 8);  // float image of W for the filter
-  float* bf = Wf + 64 * CEW_LD;
-  float* cf = bf + 64;
-  float* mrg_h = cf + 64;  // filter margins per hidden / visible unit
+  // float NIBBLE TABLES of the pre-activations for the filter: T[unit][t][m] = (bias if t = 0) + the unit's weights towards
+  // inputs 4 t .. 4 t + 3 selected by the bits of m; a unit's 16 tables are padded by one float (the 32 lanes of a warp read the
+  // same (t, m) of 32 different units)
+  float* Th = reinterpret_cast<float*>(Gred + (CEW_GMAX + 7) / 8 + 8);
+  float* Tv = Th + 64 * CEW_TLD;
+  float* mrg_h = Tv + 64 * CEW_TLD;  // filter margins per hidden / visible unit
   float* mrg_v = mrg_h + 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = rank * CEW_WARPS + warp, nslots = nranks * CEW_WARPS;
@@ -746,52 +749,57 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
   // |x~ - x| <= (n_in + 3) 2^-24 (|bias| + sum |w|) =: dx, so |sigmoid(x~) - sigmoid(x)| <= dx / 4; 2^-17 covers the
   // float evaluation of the sigmoid itself (ce_filter).  Units the filter leaves open are redone in FP64.
   auto refresh_float = [&]() {
-    for (int idx = tid; idx < 64 * CEW_LD; idx += CEW_THREADS) Wf[idx] = (float)Wsm[idx];
-    for (int idx = tid; idx < 64; idx += CEW_THREADS) { bf[idx] = (float)bsm[idx]; cf[idx] = (float)csm[idx]; }
+    // one thread per (layer, unit, nibble): its four weights once, then the 16 subset sums in a fixed order
+    for (int e = tid; e < 2 * 64 * 16; e += CEW_THREADS) {
+      const int t = e & 15, unit = (e >> 4) & 63, layer = e >> 10;
+      float w4[4], base = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w4[i] = (float)(layer ? Wsm[(4 * t + i) * CEW_LD + unit] : Wsm[unit * CEW_LD + 4 * t + i]);
+      if (t == 0) base = (float)(layer ? bsm[unit] : csm[unit]);
+      float* dst = (layer ? Tv : Th) + unit * CEW_TLD + 16 * t;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        float v = base;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((m >> i) & 1) v += w4[i];
+        dst[m] = v;
+      }
+    }
+    // |x~ - x| <= (n_in + 20) 2^-24 (|bias| + sum |w|): the conversions, at most four additions per table and the 15 of the tree
     if (tid < 64) {
       double S = fabs(csm[tid]);
       for (int j = 0; j < 64; ++j) S += fabs(Wsm[tid * CEW_LD + j]);
-      mrg_h[tid] = (float)(((N + 3) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
+      mrg_h[tid] = (float)(((N + 20) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
     } else if (tid < 128) {
       const int j = tid - 64;
       double S = fabs(bsm[j]);
       for (int i = 0; i < 64; ++i) S += fabs(Wsm[i * CEW_LD + j]);
-      mrg_v[j] = (float)(((nh + 3) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
+      mrg_v[j] = (float)(((nh + 20) * 0x1.0p-24 * S * 0.25 + 0x1.0p-17) * 1.001);
     }
     __syncthreads();
   };
-  auto hidden_pre2_f = [&](unsigned long long vm, float& x0, float& x1) {
-    const float* r0 = Wf + u0 * CEW_LD;
-    const float* r1 = Wf + u1 * CEW_LD;
-    const uint32_t lo = (uint32_t)vm, hi = (uint32_t)(vm >> 32);
-    float s0[4] = {cf[u0], 0.0f, 0.0f, 0.0f}, s1[4] = {cf[u1], 0.0f, 0.0f, 0.0f};
+  // float pre-activations of this lane's two units from the tables: 16 reads and a four-level add tree per unit (the
+  // predicated load-add pairs per weight of the first version were 256 instructions per conditional update)
+  auto table_pre2 = [&](const float* tab, unsigned long long m, float& x0, float& x1) {
+    const float* t0 = tab + u0 * CEW_TLD;
+    const float* t1 = tab + u1 * CEW_TLD;
+    float p0[16], p1[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if ((lo >> j) & 1u) { s0[j & 3] += r0[j]; s1[j & 3] += r1[j]; }
+    for (int t = 0; t < 16; ++t) {
+      const int idx = 16 * t + (int)((m >> (4 * t)) & 15ull);
+      p0[t] = t0[idx];
+      p1[t] = t1[idx];
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if ((hi >> j) & 1u) { s0[j & 3] += r0[32 + j]; s1[j & 3] += r1[32 + j]; }
-    }
-    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
-    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+    for (int w = 1; w < 16; w <<= 1)
+#pragma unroll
+      for (int t = 0; t + w < 16; t += 2 * w) { p0[t] += p0[t + w]; p1[t] += p1[t + w]; }
+    x0 = p0[0];
+    x1 = p1[0];
   };
-  auto visible_pre2_f = [&](unsigned long long hm, float& x0, float& x1) {
-    const float* c0 = Wf + u0;
-    const float* c1 = Wf + u1;
-    const uint32_t lo = (uint32_t)hm, hi = (uint32_t)(hm >> 32);
-    float s0[4] = {bf[u0], 0.0f, 0.0f, 0.0f}, s1[4] = {bf[u1], 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if ((lo >> i) & 1u) { s0[i & 3] += c0[i * CEW_LD]; s1[i & 3] += c1[i * CEW_LD]; }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if ((hi >> i) & 1u) { s0[i & 3] += c0[(32 + i) * CEW_LD]; s1[i & 3] += c1[(32 + i) * CEW_LD]; }
-    }
-    x0 = (s0[0] + s0[1]) + (s0[2] + s0[3]);
-    x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-  };
+  auto hidden_pre2_f = [&](unsigned long long vm, float& x0, float& x1) { table_pre2(Th, vm, x0, x1); };
+  auto visible_pre2_f = [&](unsigned long long hm, float& x0, float& x1) { table_pre2(Tv, hm, x0, x1); };
   auto mask64 = [&](bool b0, bool b1) {
     return (unsigned long long)__ballot_sync(0xffffffffu, b0) | ((unsigned long long)__ballot_sync(0xffffffffu, b1) << 32);
   };
@@ -929,7 +937,8 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
 // One cluster per launch: 16 CTAs (non-portable size) when the device can co-schedule them, else the portable 8.
 template <typename Kernel>
 static int launch_one_cluster(Kernel kernel, int threads, size_t smem, const CdEpochArgs& a, cudaStream_t st, int* cluster_cache) {
-  if (smem > 200 * 1024) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: layer too large for the fused epoch kernel");
+  constexpr size_t SMEM_MAX = 226 * 1024;  // 227 KB per block on sm_100 includes the kernels' 512 bytes of static shared memory
+  if (smem > SMEM_MAX) return fail(QCB_ERR_UNSUPPORTED, "cd_epoch: layer too large for the fused epoch kernel");
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
@@ -942,13 +951,13 @@ static int launch_one_cluster(Kernel kernel, int threads, size_t smem, const CdE
   cfg.numAttrs = 1;
   int& cluster_size = cluster_cache[device_slot()];  // cached per device
   if (cluster_size == 0) {
-    QCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     cluster_size = CE_CLUSTER_PORTABLE;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       int nclusters = 0;
       cfg.gridDim = dim3(CE_CLUSTER_MAX, 1, 1);
       attr[0].val.clusterDim.x = CE_CLUSTER_MAX;
-      cfg.dynamicSmemBytes = 200 * 1024;
+      cfg.dynamicSmemBytes = SMEM_MAX;
       if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) == cudaSuccess && nclusters >= 1) cluster_size = CE_CLUSTER_MAX;
       cfg.dynamicSmemBytes = smem;
     }
