@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(CEW_THREADS, 1) cd_epoch_wide_kernel(const CdE
     x1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
   };
   // Float image and margins, rebuilt whenever the parameters change.  x~ (float sum of float-rounded weights) obeys
-  // |x~ - x| <= (n_in + 3) 2^-24 (|bias| + sum |w|) =: dx, so |sigmoid(x~) - sigmoid(x)| <= dx / 4; 2^-17 covers the
+  // |x~ - x| <= (n_in + 20) 2^-24 (|bias| + sum |w|) =: dx (see below), so |sigmoid(x~) - sigmoid(x)| <= dx / 4; 2^-17 covers the
   // float evaluation of the sigmoid itself (ce_filter).  Units the filter leaves open are redone in FP64.
   auto refresh_float = [&]() {
     // one thread per (layer, unit, nibble): its four weights once, then the 16 subset sums in a fixed order
