@@ -121,3 +121,42 @@ def test_wide_statistics_vs_conditional(lib, cuda):
     pv = orc.prob_v_given_h(h).mean(0)
     sigma = np.sqrt(0.25 / 200_000) * 2  # two independent Monte-Carlo estimates
     assert np.all(np.abs(vk.mean(0) - pv) < 5 * sigma)
+
+
+@pytest.mark.parametrize("n,nh", [(10, 10), (16, 16), (3, 12), (13, 5)])
+def test_table_kernel_full_size_properties(lib, cuda, n, nh):
+    """Layers of at most 16 units run the thread-per-chain table kernel (csrc/gibbs_table.cu).  At the Tutorial-4 size (2^20
+    chains) it makes the decisions of the all-FP64 path, halves sampled separately (by global chain id) equal one call, and
+    two calls of k / 2 sweeps equal one of k; packed rows and chains started in the kernel agree with the float64 rows."""
+    import qucumber_b200 as qb
+    from qucumber_b200 import BinaryRBM
+
+    W, b, c = make_binary_params(n, nh, 741, bias_scale=0.4, weight_scale=1.3)
+    rbm = load_binary(BinaryRBM(n, nh, gpu=True), W, b, c)
+    C = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(6)
+    v0 = (torch.rand(C, n, generator=g, device=cuda) < 0.5).double()
+    launches0 = lib.qcb_launch_count()
+    whole = rbm.gibbs_steps(6, v0, seed=31415, chain_id0=1 << 33, sweep0=2)
+    assert lib.qcb_launch_count() - launches0 == 2  # table build + one kernel
+    lib.qcb_set_gibbs_mode(1)
+    try:
+        ref = rbm.gibbs_steps(6, v0, seed=31415, chain_id0=1 << 33, sweep0=2)
+    finally:
+        lib.qcb_set_gibbs_mode(0)
+    assert torch.equal(whole, ref)
+    half = C // 2 + 77
+    lo = rbm.gibbs_steps(6, v0[:half], seed=31415, chain_id0=1 << 33, sweep0=2)
+    hi = rbm.gibbs_steps(6, v0[half:], seed=31415, chain_id0=(1 << 33) + half, sweep0=2)
+    assert torch.equal(torch.cat([lo, hi]), whole)
+    two = rbm.gibbs_steps(3, rbm.gibbs_steps(3, v0, seed=31415, chain_id0=1 << 33, sweep0=2), seed=31415, chain_id0=1 << 33, sweep0=5)
+    assert torch.equal(two, whole)
+    bits = rbm.gibbs_steps_packed(6, qb.pack_states(v0), seed=31415, chain_id0=1 << 33, sweep0=2)
+    assert torch.equal(qb.unpack_states(bits, n), whole)
+    started = rbm.sample_chains(4, 100_000, seed=99, chain_id0=5)
+    lib.qcb_set_gibbs_mode(1)
+    try:
+        started_ref = rbm.sample_chains(4, 100_000, seed=99, chain_id0=5)
+    finally:
+        lib.qcb_set_gibbs_mode(0)
+    assert torch.equal(started, started_ref)
