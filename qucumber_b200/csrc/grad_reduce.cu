@@ -18,6 +18,7 @@
 namespace qcb {
 
 constexpr int GR = 32;  // rows per tile
+constexpr int64_t GR_DIRECT_MAX_ROWS = 8 * GR;  // up to this many rows one CTA does the whole reduction and finalises in place
 constexpr int GR_MAX_CTAS_PER_SM = 4;  // partial-sum slots per SM in the workspace (tensor-core kernel: up to 4 CTAs/SM)
 
 int try_grad_reduce_small(const AffineSpec& s, const RowSrc& src, int mode, int H, int64_t rows, double* partials, int max_grid,
@@ -27,9 +28,27 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
                          int* grid_out, int* flag, unsigned char* umma_img, cudaStream_t st);
 size_t grad_umma_workspace_bytes();
 
+// Tiny batches (one CTA): the kernel applies what grad_finalize_kernel would — g[e] = (accumulate ? g[e] : 0) - scale * sum[e],
+// nothing for e >= zero_from — instead of writing a partial for a second launch to pick up (a rotated-basis batch of the
+// two-qubit tutorials is up to nine bases x two reductions: the launches were the cost).  Same value bit for bit.
+struct GradDirect {
+  double* g;        // NULL: write the CTA's partial
+  double scale;
+  int accumulate;
+  int zero_from;
+  __device__ __forceinline__ void put(double* partial_out, size_t e, double sum) const {
+    if (g == nullptr) {
+      partial_out[e] = sum;
+    } else {
+      const double val = (long long)e >= (long long)zero_from ? 0.0 : -scale * sum;
+      g[e] = accumulate ? g[e] + val : val;
+    }
+  }
+};
+
 template <int TPT, int SRC>  // TPT = 4x4 tiles per thread
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s, RowSrc src, int64_t rows,
-                                                                   double* __restrict__ partials) {
+                                                                   double* __restrict__ partials, GradDirect direct) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ws = reinterpret_cast<double*>(smem_raw);
   const int N = s.n_in1, Hc = s.n_out;             // Hc: units whose p is computed here
@@ -148,11 +167,11 @@ __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s,
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int i = 4 * ib + a, j = 4 * jb + b;
-          if (i < H && j < N) out[(size_t)i * N + j] = acc[m][a * 4 + b];
+          if (i < H && j < N) direct.put(out, (size_t)i * N + j, acc[m][a * 4 + b]);
         }
     }
   }
-  if (threadIdx.x < N + H) out[(size_t)H * N + threadIdx.x] = bsum;
+  if (threadIdx.x < N + H) direct.put(out, (size_t)H * N + threadIdx.x, bsum);
 }
 
 // g[e] = (accumulate ? g[e] : 0) + scale * (-(sum over CTAs of partial[e])); entries >= zero_from are
@@ -231,21 +250,27 @@ static int launch_grad_reduce(const AffineSpec& s, const RowSrc& src, int H, int
     const int rc = try_grad_reduce_dmma(s, src, SRC, H, rows, partials, sm_count() * GR_MAX_CTAS_PER_SM, &grid_dmma, flag, umma_img, st);
     if (rc != QCB_OK) return rc;
   }
+  GradDirect direct{nullptr, scale, accumulate, zero_from};
   if (grid_dmma > 0) {
     grid = grid_dmma;
   } else if (rows > 0) {
+    if (rows <= GR_DIRECT_MAX_ROWS) {  // one CTA walks the few row tiles and finalises in place
+      grid = 1;
+      direct.g = g;
+    }
     const int ntiles = (round_up(H, 4) / 4) * (round_up(N, 4) / 4);
     const int tpt = (ntiles + ROWS_THREADS - 1) / ROWS_THREADS;
 #define QCB_GR_CASE(T)                                                                                                       \
   if (tpt <= T) {                                                                                                            \
     QCB_CUDA(cudaFuncSetAttribute(grad_reduce_kernel<T, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT)); \
-    grad_reduce_kernel<T, SRC><<<grid, ROWS_THREADS, smem, st>>>(s, src, rows, partials);                                    \
+    grad_reduce_kernel<T, SRC><<<grid, ROWS_THREADS, smem, st>>>(s, src, rows, partials, direct);                            \
     QCB_LAUNCH_CHECK();                                                                                                      \
   } else
     QCB_GR_CASE(1) QCB_GR_CASE(2) QCB_GR_CASE(4)
     return fail(QCB_ERR_UNSUPPORTED, "grad_reduce: %d x %d weight matrix too large", H, N);
 #undef QCB_GR_CASE
   }
+  if (direct.g != nullptr) return QCB_OK;  // the single CTA has written g itself
   grad_finalize_kernel<<<(G + 255) / 256, 256, 0, st>>>(partials, rows > 0 ? grid : 0, G, scale, accumulate, zero_from, g);
   QCB_LAUNCH_CHECK();
   return QCB_OK;
