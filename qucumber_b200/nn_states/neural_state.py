@@ -100,6 +100,23 @@ class _IndexedRows:
         return self.source.index_select(0, idx)
 
 
+class _GroupedBases:
+    """The bases of one batch together with the group every row belongs to: fit() groups the whole data set by basis ONCE
+    (np.unique over string rows costs more than the kernels of a two-qubit batch) and hands each batch its slice."""
+
+    def __init__(self, strings, ids, unique):
+        self.strings, self.ids, self.unique = strings, ids, unique
+
+    def __len__(self):
+        return len(self.strings)
+
+    def __getitem__(self, item):  # row slices (the shards of compute_batch_gradients)
+        return _GroupedBases(self.strings[item], self.ids[item], self.unique)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.strings, dtype=dtype)
+
+
 _SHUFFLE_STREAMS = {}
 
 
@@ -311,7 +328,10 @@ class NeuralStateBase(abc.ABC):
             bases = np.array(list(bases)).reshape(1, -1)
         # group the rows by basis on the host, gather them ONCE on the device (a boolean-mask index per basis would
         # synchronise the stream every time): after the gather each basis owns a contiguous slice
-        unique_bases, indices = np.unique(bases, axis=0, return_inverse=True)
+        if isinstance(bases, _GroupedBases):
+            unique_bases, indices = bases.unique, bases.ids
+        else:
+            unique_bases, indices = np.unique(bases, axis=0, return_inverse=True)
         indices = np.asarray(indices).reshape(-1)
         order = np.argsort(indices, kind="stable")
         counts = np.bincount(indices, minlength=unique_bases.shape[0])
@@ -497,7 +517,8 @@ class NeuralStateBase(abc.ABC):
         if world_size > 1:
             pf, pc = qd.shard_range(B, rank, world_size)
             nf, nc = qd.shard_range(C, rank, world_size)
-            bases = None if bases_batch is None else np.asarray(bases_batch)[pf:pf + pc]
+            bases = None if bases_batch is None else (bases_batch[pf:pf + pc] if isinstance(bases_batch, _GroupedBases)
+                                                      else np.asarray(bases_batch)[pf:pf + pc])
             grad = self._cd_gradients_local(k, pos[pf:pf + pc], neg[nf:nf + nc], bases, 1.0 / float(B), -1.0 / float(C), nf, seed, sweep0)
             qd.allreduce_sum_(grad)
             return grad
@@ -539,7 +560,13 @@ class NeuralStateBase(abc.ABC):
         neg_batches = [neg[s:s + neg_batch_size] for s in range(0, len(neg), neg_batch_size)]
         if input_bases is not None:
             pos_bases = input_bases[pos_perm]
-            bases_batches = [pos_bases[s:s + pos_batch_size] for s in range(0, len(train_samples), pos_batch_size)]
+            if self._basis_groups is not None:
+                uniq, ids_all = self._basis_groups
+                pos_ids = ids_all[np.asarray(pos_perm)]
+                bases_batches = [_GroupedBases(pos_bases[s:s + pos_batch_size], pos_ids[s:s + pos_batch_size], uniq)
+                                 for s in range(0, len(train_samples), pos_batch_size)]
+            else:
+                bases_batches = [pos_bases[s:s + pos_batch_size] for s in range(0, len(train_samples), pos_batch_size)]
             return zip(pos_batches, neg_batches, bases_batches)
         return zip(pos_batches, neg_batches)
 
@@ -565,6 +592,7 @@ class NeuralStateBase(abc.ABC):
 
     _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
     _train_bits = None         # set by fit(): the packed copy of a large binary data set (see _cd_gradients_packed)
+    _basis_groups = None       # set by fit(): (unique bases, group id of every sample) of the data set
     #: set to False to keep fit() on float64 rows whatever the data
     pack_training_data = True
     # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
@@ -646,6 +674,9 @@ class NeuralStateBase(abc.ABC):
         if input_bases is not None:
             self._validate_rotated_shapes(input_bases)  # a clear error now instead of QCB_ERR_UNSUPPORTED on the first rotated batch
             z_samples = extract_refbasis_samples(train_samples, input_bases).to(device=self.device)
+            input_bases = np.asarray(input_bases)
+            uniq, ids_all = np.unique(input_bases, axis=0, return_inverse=True)
+            self._basis_groups = (uniq, np.asarray(ids_all).reshape(-1))
 
         from .. import distributed as qd
 
@@ -760,4 +791,5 @@ class NeuralStateBase(abc.ABC):
         self._cd_seed = None
         self._shuffle_generator = None
         self._train_bits = None
+        self._basis_groups = None
         cbs.fire("on_train_end", self)

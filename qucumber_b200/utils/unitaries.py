@@ -28,9 +28,24 @@ def create_dict(**kwargs):
     return out
 
 
+_encode_cache = {}
+
+
 def encode_basis(basis, unitary_dict):
     """basis (sequence of names) -> (uint8 codes on the host, (K, 2, 2, 2) table, names).
-    Code 0 is the identity "Z"; every other name in the dictionary gets its own code."""
+    Code 0 is the identity "Z"; every other name in the dictionary gets its own code. The training loop asks for the same
+    few bases in every batch: the result is cached per (names of the dictionary, basis)."""
+    key = (tuple(unitary_dict), tuple(str(b) for b in basis))
+    hit = _encode_cache.get(key)
+    if hit is not None:
+        return hit
+    if len(_encode_cache) > 4096:
+        _encode_cache.clear()
+    _encode_cache[key] = out = _encode_basis(basis, unitary_dict)
+    return out
+
+
+def _encode_basis(basis, unitary_dict):
     names = ["Z"] + sorted(k for k in unitary_dict if k != "Z")
     if len(names) > 255:
         raise ValueError("too many unitaries")
