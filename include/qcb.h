@@ -289,6 +289,24 @@ int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, c
                    const double* unitaries, int K, double* UrhoU, double* g_am, double* g_ph,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* A batch grouped by measurement basis in ONE call (the loop over np.unique(bases) of NeuralStateBase.gradient,
+ * nn_states/neural_state.py:326-369): group gi = rows offsets[gi] .. offsets[gi + 1] of `samples`, measured in basis
+ * bases[gi * N .. gi * N + N) (codes as above; offsets (ngroups + 1) and bases are HOST arrays).  An all-Z group adds the
+ * plain gradient of the amplitude RBM (scale 1), the others add their rotated-basis gradients — the same kernels in the same
+ * order as one qcb_rbm_grad_reduce / qcb_cwf_rotated / qcb_dm_rotated call per group.  scratch: device doubles for the
+ * per-group amplitudes / probabilities (2 x the largest group for cwf, 1 x for dm).  Workspace: that of the single-basis
+ * call for the largest group. */
+int qcb_cwf_rotated_groups(const double* W_am, const double* b_am, const double* c_am,
+                           const double* W_ph, const double* b_ph, const double* c_ph, int N, int nh,
+                           const double* samples, const int64_t* offsets, const uint8_t* bases, int ngroups,
+                           const double* unitaries, int K, double* scratch, double* g_am, double* g_ph,
+                           void* ws, size_t ws_bytes, void* stream);
+int qcb_dm_rotated_groups(const double* W_am, const double* U_am, const double* b_am, const double* c_am, const double* d_am,
+                          const double* W_ph, const double* U_ph, const double* b_ph, const double* c_ph, const double* d_ph,
+                          int N, int nh, int na, const double* samples, const int64_t* offsets, const uint8_t* bases, int ngroups,
+                          const double* unitaries, int K, double* scratch, double* g_am, double* g_ph,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Full-space rotated metrics --------------------------------------------------------
  * qcb_kron_rotate: x <- (U_0 (x) U_1 (x) ... (x) U_{n-1}) x on the leading index of a planar complex array
  * x[i * batch + t], i in [0, 2^n), in place (re and im planes).  basis is a HOST array of n codes into

@@ -50,6 +50,9 @@ SIGNATURES = {
     "qcb_kl_terms": (c_int, [_P, _P, _P, _P, c_int64, c_double, _P, _P, c_size_t, _P]),
     "qcb_rbm_exact_stats_range": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint64, c_uint64, c_double, _P, _P,
                                           _P, _P, _P, c_size_t, _P]),
+    "qcb_cwf_rotated_groups": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "qcb_dm_rotated_groups": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P,
+                                      _P, _P, c_size_t, _P]),
     "qcb_cwf_rotated": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, c_int, _P, _P, _P, _P,
                                 c_size_t, _P]),
     "qcb_dm_rotated": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P, c_int,

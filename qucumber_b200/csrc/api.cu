@@ -450,6 +450,66 @@ int qcb_dm_rotated(const double* W_am, const double* U_am, const double* b_am, c
   return run_dm_rotated(am, ph, samples, B, basis, unitaries, K, UrhoU, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// A batch whose rows are grouped by measurement basis, every group in ONE call: group gi holds rows offsets[gi] .. offsets[gi + 1]
+// of `samples` and was measured in basis bases[gi * N ..]; an all-Z group adds the plain positive-phase gradient of the
+// amplitude RBM, the others their rotated-basis gradients — what NeuralStateBase.gradient (nn_states/neural_state.py:326-369)
+// does with one Python iteration and one C call per basis.  offsets and bases are HOST arrays.
+int qcb_cwf_rotated_groups(const double* W_am, const double* b_am, const double* c_am, const double* W_ph, const double* b_ph,
+                           const double* c_ph, int N, int nh, const double* samples, const int64_t* offsets, const uint8_t* bases,
+                           int ngroups, const double* unitaries, int K, double* scratch, double* g_am, double* g_ph, void* ws,
+                           size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W_am);
+  StackedParams am, ph;
+  int rc = make_params(am, W_am, nullptr, b_am, c_am, nullptr, N, nh, 0);
+  if (rc != QCB_OK) return rc;
+  rc = make_params(ph, W_ph, nullptr, b_ph, c_ph, nullptr, N, nh, 0);
+  if (rc != QCB_OK) return rc;
+  if (ngroups < 0 || offsets == nullptr || bases == nullptr || unitaries == nullptr || K < 1 || g_am == nullptr || g_ph == nullptr ||
+      samples == nullptr || scratch == nullptr)
+    return fail(QCB_ERR_BAD_ARG, "cwf_rotated_groups: bad arguments");
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int64_t first = offsets[gi], B = offsets[gi + 1] - first;
+    if (B < 0) return fail(QCB_ERR_BAD_ARG, "cwf_rotated_groups: offsets must not decrease");
+    if (B == 0) continue;
+    const uint8_t* basis = bases + (size_t)gi * N;
+    bool plain = true;
+    for (int j = 0; j < N; ++j) plain = plain && basis[j] == 0;
+    if (plain) rc = run_grad_reduce(am, samples + first * N, B, 1.0, g_am, 1, ws, ws_bytes, (cudaStream_t)stream);
+    else rc = run_cwf_rotated(am, ph, samples + first * N, B, basis, unitaries, K, scratch, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
+    if (rc != QCB_OK) return rc;
+  }
+  return QCB_OK;
+}
+
+int qcb_dm_rotated_groups(const double* W_am, const double* U_am, const double* b_am, const double* c_am, const double* d_am,
+                          const double* W_ph, const double* U_ph, const double* b_ph, const double* c_ph, const double* d_ph,
+                          int N, int nh, int na, const double* samples, const int64_t* offsets, const uint8_t* bases, int ngroups,
+                          const double* unitaries, int K, double* scratch, double* g_am, double* g_ph, void* ws, size_t ws_bytes,
+                          void* stream) {
+  StreamDeviceGuard device_guard(stream, W_am);
+  StackedParams am, ph;
+  if (na < 1) return fail(QCB_ERR_BAD_ARG, "dm_rotated_groups: na must be >= 1");
+  int rc = make_params(am, W_am, U_am, b_am, c_am, d_am, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  rc = make_params(ph, W_ph, U_ph, b_ph, c_ph, d_ph, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (ngroups < 0 || offsets == nullptr || bases == nullptr || unitaries == nullptr || K < 1 || g_am == nullptr || g_ph == nullptr ||
+      samples == nullptr || scratch == nullptr)
+    return fail(QCB_ERR_BAD_ARG, "dm_rotated_groups: bad arguments");
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int64_t first = offsets[gi], B = offsets[gi + 1] - first;
+    if (B < 0) return fail(QCB_ERR_BAD_ARG, "dm_rotated_groups: offsets must not decrease");
+    if (B == 0) continue;
+    const uint8_t* basis = bases + (size_t)gi * N;
+    bool plain = true;
+    for (int j = 0; j < N; ++j) plain = plain && basis[j] == 0;
+    if (plain) rc = run_grad_reduce(am, samples + first * N, B, 1.0, g_am, 1, ws, ws_bytes, (cudaStream_t)stream);
+    else rc = run_dm_rotated(am, ph, samples + first * N, B, basis, unitaries, K, scratch, g_am, g_ph, ws, ws_bytes, (cudaStream_t)stream);
+    if (rc != QCB_OK) return rc;
+  }
+  return QCB_OK;
+}
+
 // ---- compact states -------------------------------------------------------------------------------
 int qcb_pack_states(const double* v, int64_t rows, int N, uint8_t* bits, void* stream) {
   StreamDeviceGuard device_guard(stream, v);

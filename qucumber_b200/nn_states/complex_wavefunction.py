@@ -18,6 +18,7 @@ class ComplexWaveFunction(WaveFunctionBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
+    _grouped_call = "cwf"
     _rotated_limits = (("num_visible", 512, "num_visible"),)  # larger hidden layers take the row-tiled kernels (csrc/large.cu)
     _max_rotated_sites = 21
 

@@ -14,6 +14,7 @@ class DensityMatrix(NeuralStateBase):
     rbm_am = stored_attribute("_rbm_am")
     rbm_ph = stored_attribute("_rbm_ph")
     device = stored_attribute("_device")
+    _grouped_call = "dm"
     _rotated_limits = (("num_aux", 256, "num_aux"), ("num_visible", 512, "num_visible"))
     _max_rotated_sites = 10  # 4^S pairs per sample
 

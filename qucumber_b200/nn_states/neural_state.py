@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..utils import unitaries
 from ..hilbert import HilbertSpace
 from ..rng import next_seed
 from ..utils import cplx
@@ -297,6 +298,9 @@ class NeuralStateBase(abc.ABC):
         """Subclasses with measurement bases accumulate the rotated-basis gradient of ``samples``."""
         raise NotImplementedError
 
+    #: "cwf" / "dm": the grouped C entry point that serves a whole batch of this state type (None: one call per basis)
+    _grouped_call = None
+
     #: shape limits of the fused rotated-basis kernels: (attribute of the state, largest supported value, what it is)
     _rotated_limits = ()
     _max_rotated_sites = 21
@@ -336,6 +340,11 @@ class NeuralStateBase(abc.ABC):
         order = np.argsort(indices, kind="stable")
         counts = np.bincount(indices, minlength=unique_bases.shape[0])
         grouped = samples.index_select(0, torch.as_tensor(order, device=samples.device))
+        if self._grouped_call is not None and grouped.is_cuda:
+            # every basis of the batch in ONE C call (the per-basis loop, plain all-Z groups included, runs in C)
+            unitaries._call_groups(self._grouped_call, self.rbm_am, self.rbm_ph, unique_bases, counts, grouped, self.unitary_dict,
+                                   grad[0], grad[1])
+            return grad
         start = 0
         for i in range(unique_bases.shape[0]):
             basis = unique_bases[i, :]

@@ -209,3 +209,42 @@ def _call_dm(rbm_am, rbm_ph, basis, states, unitary_dict, g_am=None, g_ph=None):
                             _lib.ptr(g_am), _lib.ptr(g_ph), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "qcb_dm_rotated")
     return out
+
+
+def _call_groups(kind, rbm_am, rbm_ph, unique_bases, counts, grouped, unitary_dict, g_am, g_ph):
+    """qcb_cwf_rotated_groups / qcb_dm_rotated_groups: the rows of ``grouped`` (already sorted by basis: ``counts[i]`` rows
+    of ``unique_bases[i]`` each) in ONE call that accumulates into g_am / g_ph — the per-basis loop runs in C."""
+    lib = _lib.load()
+    dev = grouped.device
+    B, N = grouped.shape
+    grouped = grouped.contiguous()
+    counts = np.asarray(counts, dtype=np.int64)
+    offsets = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    codes = None
+    names = None
+    rows = []
+    for basis in unique_bases:
+        c, names = encode_basis(basis, unitary_dict)
+        rows.append(c)
+    codes = np.ascontiguousarray(np.stack(rows).astype(np.uint8))
+    table = unitary_table(unitary_dict, names, dev)
+    bmax = int(counts.max()) if len(counts) else 0
+    scratch = torch.empty(2 * max(bmax, 1), dtype=torch.double, device=dev)
+    if kind == "cwf":
+        ws = _lib.workspace(dev, lib.qcb_workspace_bytes(_lib.OP_CWF_ROTATED, N, rbm_am.num_hidden, 0, bmax))
+        wa, ba, ca = rbm_am._params()
+        wp, bp, cp = rbm_ph._params()
+        rc = lib.qcb_cwf_rotated_groups(_lib.ptr(wa), _lib.ptr(ba), _lib.ptr(ca), _lib.ptr(wp), _lib.ptr(bp), _lib.ptr(cp), N,
+                                        rbm_am.num_hidden, _lib.ptr(grouped), offsets.ctypes.data, codes.ctypes.data, len(counts),
+                                        _lib.ptr(table), len(names), _lib.ptr(scratch), _lib.ptr(g_am), _lib.ptr(g_ph), _lib.ptr(ws),
+                                        ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "qcb_cwf_rotated_groups")
+    else:
+        ws = _lib.workspace(dev, lib.qcb_workspace_bytes(_lib.OP_DM_ROTATED, N, rbm_am.num_hidden, rbm_am.num_aux, bmax))
+        ta, tp = rbm_am._tensors(), rbm_ph._tensors()
+        rc = lib.qcb_dm_rotated_groups(*[_lib.ptr(t) for t in ta], *[_lib.ptr(t) for t in tp], N, rbm_am.num_hidden, rbm_am.num_aux,
+                                       _lib.ptr(grouped), offsets.ctypes.data, codes.ctypes.data, len(counts), _lib.ptr(table),
+                                       len(names), _lib.ptr(scratch), _lib.ptr(g_am), _lib.ptr(g_ph), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(dev))
+        _lib.check(rc, "qcb_dm_rotated_groups")

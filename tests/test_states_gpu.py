@@ -452,6 +452,44 @@ def test_cd_step_packed_equals_cd_step(lib, cuda):
 
 
 @pytest.mark.parametrize("kind", ["complex", "density"])
+def test_gradient_grouped_call_equals_per_basis_calls(lib, cuda, kind):
+    """NeuralStateBase.gradient with bases: every basis of the batch goes through ONE C call (qcb_cwf_rotated_groups /
+    qcb_dm_rotated_groups, all-Z groups included) — the same kernels in the same order as one call per basis: identical
+    gradients; and both equal the oracle's gradient of the batch."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+    n = 5
+    rng = np.random.default_rng(321)
+    bases_pool = ["ZZZZZ", "XZZZZ", "ZYZXZ", "XYXYX", "ZZZZY", "YYZZZ"]
+    bases = np.array([list(bases_pool[i]) for i in rng.integers(0, len(bases_pool), size=300)])
+    samples = random_states(300, n, 322)
+    if kind == "complex":
+        nn = ComplexWaveFunction(n, 4, gpu=True)
+        pa, pp = make_binary_params(n, 4, 323, bias_scale=0.3), make_binary_params(n, 4, 324, bias_scale=0.3)
+        load_binary(nn.rbm_am, *pa)
+        load_binary(nn.rbm_ph, *pp)
+        want = orc.complex_gradient(orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp), samples, bases)
+    else:
+        nn = DensityMatrix(n, 4, 3, gpu=True)
+        pa, pp = make_purification_params(n, 4, 3, 325, bias_scale=0.3), make_purification_params(n, 4, 3, 326, bias_scale=0.3)
+        load_purification(nn.rbm_am, *pa)
+        load_purification(nn.rbm_ph, *pp)
+        want = orc.dm_gradient(orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp), samples, bases)
+    ts = torch.tensor(samples, device=cuda)
+    launches0 = lib.qcb_launch_count()
+    grouped = nn.gradient(ts, bases=bases)
+    launched_grouped = lib.qcb_launch_count() - launches0
+    nn._grouped_call = None
+    launches0 = lib.qcb_launch_count()
+    single = nn.gradient(ts, bases=bases)
+    assert lib.qcb_launch_count() - launches0 == launched_grouped
+    for a, b_ in zip(grouped, single):
+        assert torch.equal(a, b_)
+    assert_close(grouped[0], want[0], what="gradient with bases (amplitude)")
+    assert_close(grouped[1], want[1], what="gradient with bases (phase)")
+
+
+@pytest.mark.parametrize("kind", ["complex", "density"])
 def test_fit_reaches_reference_training_targets(lib, cuda, kind):
     """The reference's own training regression for states with rotated bases (tests/test_training.py:143-279, `slow`):
     5 epochs of CD-10 at lr = 0.1 on the Tutorial-2 / Tutorial-3 data, fidelity and KL averaged over repeated runs must
