@@ -564,6 +564,31 @@ def extra_metrics(dev, lib_mod):
                                    "density_ms_per_epoch": ms_d, "density_samples": int(d3.shape[0]),
                                    "note": "pos = neg = 100, CD-10, SGD; notebook timings of the reference (unknown CPU): "
                                            "98 ms/epoch (1000 samples) and 350 ms/epoch (900 samples, Adadelta)"}
+        # the unmodified reference on the same data and settings: host cores, and its torch-CUDA path on this GPU
+        if load_reference() is not None:
+            from qucumber.nn_states import ComplexWaveFunction as RefComplex, DensityMatrix as RefDensity
+
+            def ref_epoch(make, data, bases, gpu):
+                st = make(gpu)
+                st.fit(data, epochs=1, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=bases)
+                if gpu:
+                    torch.cuda.synchronize(dev)
+                t0 = _time.perf_counter()
+                st.fit(data, epochs=2, pos_batch_size=100, neg_batch_size=100, k=10, lr=0.1, input_bases=bases)
+                if gpu:
+                    torch.cuda.synchronize(dev)
+                return (_time.perf_counter() - t0) / 2 * 1e3
+
+            ref = {}
+            for name, make, data, bases in (("complex", lambda gpu: RefComplex(2, 2, gpu=gpu), d2, b2),
+                                            ("density", lambda gpu: RefDensity(2, 2, 2, gpu=gpu), d3, b3)):
+                for gpu in (False, True):
+                    try:
+                        ref[f"{name}_ms_per_epoch_{'torch_cuda' if gpu else 'cpu'}"] = ref_epoch(make, data, bases, gpu)
+                    except Exception as exc:  # pragma: no cover
+                        ref[f"{name}_{'torch_cuda' if gpu else 'cpu'}_error"] = str(exc)[:200]
+            ref["cores"] = torch.get_num_threads()
+            out["two_qubit_epochs"]["reference"] = ref
     except Exception as exc:  # pragma: no cover
         out["two_qubit_epochs"] = {"error": str(exc)}
 
