@@ -307,6 +307,26 @@ int qcb_dm_rotated_groups(const double* W_am, const double* U_am, const double* 
                           const double* unitaries, int K, double* scratch, double* g_am, double* g_ph,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ---- One training epoch on data with measurement bases ------------------------------------------
+ * The batch loop of NeuralStateBase.fit (nn_states/neural_state.py:593-623) for a ComplexWaveFunction (na == 0; U_*, d_*
+ * NULL) or a DensityMatrix (na >= 1) with the reference's default optimizer (vanilla SGD), in ONE call.  Batch t holds the
+ * rows offsets[t * ngroups] .. offsets[(t + 1) * ngroups] of `pos`, grouped by basis: group gi (basis bases[gi * N ..], codes
+ * into `unitaries` as for qcb_cwf_rotated) owns rows offsets[t * ngroups + gi] .. offsets[t * ngroups + gi + 1].  offsets
+ * (nbatches * ngroups + 1 entries) and bases are HOST arrays.  Per batch: g = [g_am ; g_ph] <- (1 / B_t) * the grouped
+ * positive phase (compute_batch_gradients, neural_state.py:417-447; same kernels and order as qcb_*_rotated_groups), then k
+ * sweeps from rows t * neg_batch_size .. of `neg` with Philox key `seed`, chains 0 .. neg_batch_size - 1 and sweeps
+ * sweep0 + t * k .., g_am -= (1 / neg_batch_size) * sum grad E(v_k) (as qcb_rbm_cdk_neg), then p <- p - lr * g on the ten
+ * (six) parameter tensors IN PLACE; lr == 0 leaves them untouched.  On return g holds the last batch's gradient.  Each RBM's
+ * part of g is ordered [W ; U ; b ; c ; d].  scratch: 2 x (largest group) doubles; vk: neg_batch_size * N doubles;
+ * workspace: max of qcb_workspace_bytes(QCB_OP_CWF_ROTATED / QCB_OP_DM_ROTATED, largest group) and (QCB_OP_CDK_NEG,
+ * neg_batch_size). */
+int qcb_fit_epoch_bases(double* W_am, double* U_am, double* b_am, double* c_am, double* d_am,
+                        double* W_ph, double* U_ph, double* b_ph, double* c_ph, double* d_ph, int N, int nh, int na,
+                        const double* pos, const int64_t* offsets, const uint8_t* bases, int ngroups, int nbatches,
+                        const double* unitaries, int K, const double* neg, int64_t neg_batch_size, int k, double lr,
+                        uint64_t seed, uint64_t sweep0, double* scratch, double* g, double* vk,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Full-space rotated metrics --------------------------------------------------------
  * qcb_kron_rotate: x <- (U_0 (x) U_1 (x) ... (x) U_{n-1}) x on the leading index of a planar complex array
  * x[i * batch + t], i in [0, 2^n), in place (re and im planes).  basis is a HOST array of n codes into

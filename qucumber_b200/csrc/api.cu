@@ -122,6 +122,75 @@ struct StreamDeviceGuard {
   }
 };
 
+// ---- one training epoch over data with measurement bases (qcb_fit_epoch_bases) ----------------------
+constexpr int FE_MAX_SEGS = 10;
+struct FitEpochSegs {  // the parameter tensors of both RBMs and where their gradients sit in the flat vector [g_am ; g_ph]
+  double* p[FE_MAX_SEGS];
+  long long first[FE_MAX_SEGS + 1];
+  int count;
+};
+
+__global__ void fit_epoch_scale_kernel(double* __restrict__ g, long long n, double scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] *= scale;
+}
+
+// p <- p + (-lr) g, the arithmetic of the vanilla SGD step (torch.optim.SGD without momentum / weight decay)
+__global__ void fit_epoch_sgd_kernel(FitEpochSegs segs, const double* __restrict__ g, double lr) {
+  const long long n = segs.first[segs.count];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (i >= segs.first[s + 1]) ++s;
+    double* q = segs.p[s] + (i - segs.first[s]);
+    *q = fma(-lr, g[i], *q);
+  }
+}
+
+int run_fit_epoch_bases(const StackedParams& am, const StackedParams& ph, const FitEpochSegs& segs, bool density, const double* pos,
+                        const int64_t* offsets, const uint8_t* bases, int ngroups, int nbatches, const double* unitaries, int K,
+                        const double* neg, int64_t C, int k, double lr, uint64_t seed, uint64_t sweep0, double* scratch, double* g,
+                        double* vk, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int N = am.N, nhid = am.nhid();
+  const long long n_am = segs.first[segs.count / 2], n_all = segs.first[segs.count];
+  double* g_am = g;
+  double* g_ph = g + n_am;
+  const size_t gb = gibbs_workspace_bytes_rows(N, nhid, C);
+  if (C > 0 && ws_bytes < gb + grad_reduce_workspace_bytes(N, nhid, C)) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: workspace too small");
+  const int blocks = (int)((n_all + 255) / 256 < 148 ? (n_all + 255) / 256 : 148);
+  for (int b = 0; b < nbatches; ++b) {
+    const int64_t* off = offsets + (size_t)b * ngroups;
+    const int64_t B = off[ngroups] - off[0];
+    QCB_CUDA(cudaMemsetAsync(g, 0, (size_t)n_all * sizeof(double), st));
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int64_t first = off[gi], rows = off[gi + 1] - first;
+      if (rows < 0) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: offsets must not decrease");
+      if (rows == 0) continue;
+      const uint8_t* basis = bases + (size_t)gi * N;
+      bool plain = true;
+      for (int j = 0; j < N; ++j) plain = plain && basis[j] == 0;
+      int rc;
+      if (plain) rc = run_grad_reduce(am, pos + first * N, rows, 1.0, g_am, 1, ws, ws_bytes, st);
+      else if (density) rc = run_dm_rotated(am, ph, pos + first * N, rows, basis, unitaries, K, scratch, g_am, g_ph, ws, ws_bytes, st);
+      else rc = run_cwf_rotated(am, ph, pos + first * N, rows, basis, unitaries, K, scratch, g_am, g_ph, ws, ws_bytes, st);
+      if (rc != QCB_OK) return rc;
+    }
+    if (B > 0) {
+      fit_epoch_scale_kernel<<<blocks, 256, 0, st>>>(g, n_all, 1.0 / (double)B);
+      QCB_LAUNCH_CHECK();
+    }
+    if (C > 0) {
+      int rc = run_gibbs(am, neg + (size_t)b * C * N, vk, C, k, seed, 0, sweep0 + (uint64_t)b * (uint64_t)k, nullptr, ws, gb, st);
+      if (rc != QCB_OK) return rc;
+      rc = run_grad_reduce(am, vk, C, -1.0 / (double)C, g_am, 1, static_cast<char*>(ws) + gb, ws_bytes - gb, st);
+      if (rc != QCB_OK) return rc;
+    }
+    if (lr != 0.0) {
+      fit_epoch_sgd_kernel<<<blocks, 256, 0, st>>>(segs, g, lr);
+      QCB_LAUNCH_CHECK();
+    }
+  }
+  return QCB_OK;
+}
+
 }  // namespace qcb
 
 using namespace qcb;
@@ -508,6 +577,46 @@ int qcb_dm_rotated_groups(const double* W_am, const double* U_am, const double* 
     if (rc != QCB_OK) return rc;
   }
   return QCB_OK;
+}
+
+// One epoch of CD-k training on data with measurement bases in ONE call: per batch the grouped positive phase (as
+// qcb_cwf_rotated_groups / qcb_dm_rotated_groups), the k sweeps and the negative phase of the amplitude RBM (as qcb_rbm_cdk_neg)
+// and the vanilla SGD step p <- p - lr g on both RBMs — the batch loop of NeuralStateBase.fit (nn_states/neural_state.py:593-623)
+// with the reference's default optimizer.  na == 0: ComplexWaveFunction (U_*, d_* NULL); na >= 1: DensityMatrix.
+int qcb_fit_epoch_bases(double* W_am, double* U_am, double* b_am, double* c_am, double* d_am, double* W_ph, double* U_ph, double* b_ph,
+                        double* c_ph, double* d_ph, int N, int nh, int na, const double* pos, const int64_t* offsets,
+                        const uint8_t* bases, int ngroups, int nbatches, const double* unitaries, int K, const double* neg,
+                        int64_t neg_batch_size, int k, double lr, uint64_t seed, uint64_t sweep0, double* scratch, double* g,
+                        double* vk, void* ws, size_t ws_bytes, void* stream) {
+  StreamDeviceGuard device_guard(stream, W_am);
+  StackedParams am, ph;
+  if (na < 0) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: na must be >= 0");
+  int rc = make_params(am, W_am, na ? U_am : nullptr, b_am, c_am, na ? d_am : nullptr, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  rc = make_params(ph, W_ph, na ? U_ph : nullptr, b_ph, c_ph, na ? d_ph : nullptr, N, nh, na);
+  if (rc != QCB_OK) return rc;
+  if (ngroups < 1 || nbatches < 0 || offsets == nullptr || bases == nullptr || unitaries == nullptr || K < 1 || g == nullptr ||
+      pos == nullptr || scratch == nullptr || neg_batch_size < 0 || k < 0 || (neg_batch_size > 0 && (neg == nullptr || vk == nullptr)) ||
+      ws == nullptr)
+    return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: bad arguments");
+  FitEpochSegs segs;
+  long long at = 0;
+  int n = 0;
+  for (int net = 0; net < 2; ++net) {  // the flat gradient of an RBM is [W ; U ; b ; c ; d], as its parameters() are ordered
+    double* const t[5] = {net ? W_ph : W_am, net ? U_ph : U_am, net ? b_ph : b_am, net ? c_ph : c_am, net ? d_ph : d_am};
+    const long long len[5] = {(long long)nh * N, (long long)na * N, N, nh, na};
+    for (int j = 0; j < 5; ++j) {
+      if (len[j] == 0) continue;
+      segs.p[n] = t[j];
+      segs.first[n] = at;
+      at += len[j];
+      ++n;
+    }
+  }
+  segs.first[n] = at;
+  segs.count = n;
+  return run_fit_epoch_bases(am, ph, segs, na > 0, pos, offsets, bases, ngroups, nbatches, unitaries, K, neg, neg_batch_size, k, lr, seed,
+                             sweep0, scratch, g, vk, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---- compact states -------------------------------------------------------------------------------

@@ -602,6 +602,7 @@ class NeuralStateBase(abc.ABC):
     _shuffle_generator = None  # set by fit() under torch.distributed: every rank must draw the same batches
     _train_bits = None         # set by fit(): the packed copy of a large binary data set (see _cd_gradients_packed)
     _basis_groups = None       # set by fit(): (unique bases, group id of every sample) of the data set
+    _basis_codes = None        # set by fit(): (codes of the unique bases, names of the unitaries they index)
     #: set to False to keep fit() on float64 rows whatever the data
     pack_training_data = True
     # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
@@ -632,6 +633,63 @@ class NeuralStateBase(abc.ABC):
         # hooks are resolved exactly as fire() resolves them (instance attributes included: the reference's
         # LambdaCallback installs its hooks on the instance, callbacks/lambda_callback.py:84-97)
         return all(_is_noop_hook(getattr(cb, hook, None)) for cb in cbs.callbacks for hook in ("on_batch_start", "on_batch_end"))
+
+    def _bases_epoch_fusable(self, plain_sgd, cbs):
+        """True when the batch loop of an epoch over data WITH bases can run as one C call (qcb_fit_epoch_bases): a state type
+        with a grouped entry point on a CUDA device, vanilla SGD, and no callback that acts per batch."""
+        if not (self.fuse_epochs and plain_sgd and self._grouped_call is not None and self.device.type == "cuda"
+                and list(self.networks) == ["rbm_am", "rbm_ph"]):
+            return False
+        if not all(prm.is_contiguous() and prm.is_cuda for net in self.networks for prm in getattr(self, net).parameters()):
+            return False
+        return all(_is_noop_hook(getattr(cb, hook, None)) for cb in cbs.callbacks for hook in ("on_batch_start", "on_batch_end"))
+
+    def _fit_epoch_bases(self, train_samples, z_samples, pos_batch_size, neg_batch_size, num_batches, k, lr, want_grads):
+        """All batches of one epoch over data with bases in one call; parameters are updated in place. Draws the permutations
+        exactly as _shuffle_tensors does and hands every batch over grouped by basis (stable within a group), so the
+        batches, their row order and the chains' Philox streams are those of the per-batch loop."""
+        lib = _lib.load()
+        dev = self.device
+        am, ph = self.rbm_am, self.rbm_ph
+        uniq, ids_all = self._basis_groups
+        n, N = train_samples.shape
+        G = int(uniq.shape[0])
+        gen = self._shuffle_generator
+        pos_perm = torch.randperm(n, generator=gen).numpy()
+        neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long, generator=gen)
+        key = (np.arange(n, dtype=np.int64) // int(pos_batch_size)) * G + ids_all[pos_perm]
+        order = np.argsort(key, kind="stable")
+        counts = np.bincount(key, minlength=num_batches * G)
+        offsets = np.zeros(num_batches * G + 1, dtype=np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        pos = train_samples.index_select(0, torch.as_tensor(pos_perm[order], device=dev)).contiguous()
+        neg = z_samples.index_select(0, neg_perm.to(dev)).contiguous()
+        codes, names = self._basis_codes
+        table = unitaries.unitary_table(self.unitary_dict, names, dev)
+        na = int(getattr(am, "num_aux", 0))
+        bmax = int(counts.max()) if counts.size else 0
+        C = int(neg_batch_size)
+        op = _lib.OP_DM_ROTATED if na else _lib.OP_CWF_ROTATED
+        ws = _lib.workspace(dev, max(lib.qcb_workspace_bytes(op, N, am.num_hidden, na, bmax),
+                                     lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, N, am.num_hidden, na, C), 256))
+        scratch = torch.empty(2 * max(bmax, 1), dtype=torch.double, device=dev)
+        g = torch.empty(am.num_pars + ph.num_pars, dtype=torch.double, device=dev)
+        vk = torch.empty(max(C, 1) * N, dtype=torch.double, device=dev)
+        if self._cd_sweep + num_batches * int(k) >= (1 << 31):
+            self._cd_seed, self._cd_sweep = next_seed(), 0
+        if na:
+            ptrs = [_lib.ptr(t.data) for r in (am, ph) for t in (r.weights_W, r.weights_U, r.visible_bias, r.hidden_bias, r.aux_bias)]
+        else:
+            ptrs = [_lib.ptr(t.data) if t is not None else None
+                    for r in (am, ph) for t in (r.weights, None, r.visible_bias, r.hidden_bias, None)]
+        _lib.check(lib.qcb_fit_epoch_bases(*ptrs, N, am.num_hidden, na, _lib.ptr(pos), offsets.ctypes.data, codes.ctypes.data, G,
+                                           int(num_batches), _lib.ptr(table), len(names), _lib.ptr(neg), C, int(k), float(lr),
+                                           self._cd_seed, self._cd_sweep, _lib.ptr(scratch), _lib.ptr(g), _lib.ptr(vk), _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr(dev)), "qcb_fit_epoch_bases")
+        self._cd_sweep += num_batches * int(k)
+        if want_grads:
+            vector_to_grads(g[:am.num_pars], am.parameters())
+            vector_to_grads(g[am.num_pars:], ph.parameters())
 
     def _fit_epoch_fused(self, pos, neg, num_batches, pos_batch_size, neg_batch_size, k, lr, want_grads):
         """All batches of one epoch in one launch; parameters are updated in place."""
@@ -686,6 +744,11 @@ class NeuralStateBase(abc.ABC):
             input_bases = np.asarray(input_bases)
             uniq, ids_all = np.unique(input_bases, axis=0, return_inverse=True)
             self._basis_groups = (uniq, np.asarray(ids_all).reshape(-1))
+            rows, names = [], None
+            for basis in uniq:
+                c_, names = unitaries.encode_basis(basis, self.unitary_dict)
+                rows.append(c_)
+            self._basis_codes = (np.ascontiguousarray(np.stack(rows).astype(np.uint8)), names)
 
         from .. import distributed as qd
 
@@ -722,6 +785,10 @@ class NeuralStateBase(abc.ABC):
         fused_epoch = (scheduler is None and max(pos_batch_size, neg_batch_size) <= 4096
                        and self._shards_batches(pos_batch_size, neg_batch_size, input_bases is not None)[1] == 1
                        and self._epoch_fusable(optimizer, cbs, input_bases))
+        # data with bases: the whole batch loop of an epoch in one C call (the kernels of the per-batch path in the same order,
+        # the SGD step included; at two qubits the per-batch loop was host time)
+        fused_bases = (input_bases is not None and scheduler is None and self._bases_epoch_fusable(plain_sgd, cbs)
+                       and self._shards_batches(pos_batch_size, neg_batch_size, True)[1] == 1 and train_samples.shape[0] > 0)
         # fused epochs with device-side shuffles: the NEXT epoch's permutation and gathers run on a side stream while this
         # epoch's kernel (one 16-CTA cluster, the rest of the GPU is idle) runs on the caller's stream
         side = None
@@ -765,6 +832,11 @@ class NeuralStateBase(abc.ABC):
                     in_flight.append(done)
                     if len(in_flight) > 3:
                         in_flight.pop(0).synchronize()
+            elif fused_bases:
+                cbs.fire("on_epoch_start", self, ep)
+                self._fit_epoch_bases(train_samples, z_samples, pos_batch_size, neg_batch_size, num_batches, k,
+                                      optimizer.param_groups[0]["lr"], want_grads=bool(cbs.callbacks))
+                batches = ()
             else:
                 batches = self._shuffle_data(pos_batch_size, neg_batch_size, num_batches, train_samples, input_bases, z_samples)
                 cbs.fire("on_epoch_start", self, ep)
@@ -801,4 +873,5 @@ class NeuralStateBase(abc.ABC):
         self._shuffle_generator = None
         self._train_bits = None
         self._basis_groups = None
+        self._basis_codes = None
         cbs.fire("on_train_end", self)

@@ -632,6 +632,66 @@ def test_hilbert_space_guard_and_rotations_cross_check(lib, cuda):
             assert_close(un.rotate_rho_probs(dm, basis, space), np.diag(want).real, rtol=1e-12, what=f"rotate_rho_probs, N={n}")
 
 
+@pytest.mark.parametrize("kind,n,nh,na,samples,pos_b,neg_b,k", [("complex", 2, 2, 0, 500, 100, 100, 10), ("complex", 5, 4, 0, 230, 50, 30, 3),
+                                                                 ("complex", 3, 6, 0, 64, 64, 7, 0), ("density", 2, 2, 2, 900, 100, 100, 10),
+                                                                 ("density", 4, 3, 3, 170, 60, 25, 2)])
+def test_fit_bases_epoch_call_equals_per_batch_path(lib, cuda, kind, n, nh, na, samples, pos_b, neg_b, k):
+    """Data with measurement bases: fit() runs the batch loop of an epoch as ONE C call (qcb_fit_epoch_bases: grouped positive
+    phase, k sweeps + negative phase, SGD step, per batch). With the same torch seed it walks through the batches, row
+    orders and Philox streams of the per-batch path (compute_batch_gradients + the fused multi-tensor SGD update) and must land
+    on its parameters; .grad holds the last batch's gradient when a callback can look; a callback with batch hooks, another
+    optimizer or fuse_epochs = False keep the per-batch loop."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix
+
+    rng = np.random.default_rng(4100 + n)
+    names = np.array(["X", "Y", "Z", "Z"])
+    bases = names[rng.integers(0, 4, size=(6, n))]
+    bases[0, :] = "Z"
+    bases = bases[rng.integers(0, 6, size=samples)]
+    data = torch.tensor((rng.random((samples, n)) < 0.5).astype(np.float64))
+
+    def make():
+        torch.manual_seed(4243)
+        return ComplexWaveFunction(n, nh, gpu=True) if kind == "complex" else DensityMatrix(n, nh, na, gpu=True)
+
+    class EpochHook:
+        def on_epoch_end(self, s, ep):
+            self.grads = [p.grad.clone() for net in s.networks for p in getattr(s, net).parameters()]
+
+    out = []
+    for fuse in (True, False):
+        nn = make()
+        nn.fuse_epochs = fuse
+        hook = EpochHook()
+        launches0 = lib.qcb_launch_count()
+        nn.fit(data, epochs=3, pos_batch_size=pos_b, neg_batch_size=neg_b, k=k, lr=0.07, input_bases=bases, callbacks=[hook])
+        out.append(([p.detach().cpu().numpy().copy() for net in nn.networks for p in getattr(nn, net).parameters()],
+                    [g.cpu().numpy() for g in hook.grads], lib.qcb_launch_count() - launches0))
+    (pf, gf, lf), (pu, gu, lu) = out
+    for i, (a, b) in enumerate(zip(pf, pu)):
+        assert_close(a, b, rtol=1e-12, what=f"parameter {i}: one call per epoch vs per-batch path")
+    for i, (a, b) in enumerate(zip(gf, gu)):
+        assert_close(a, b, rtol=1e-11, what=f"gradient {i} of the last batch")
+    assert any(np.abs(g).max() > 0 for g in gf)
+    # the same kernels, plus one scaling and one update launch per batch on our side (the per-batch path does those with torch)
+    nb = -(-samples // pos_b)
+    assert lu < lf <= lu + 3 * nb * 3
+
+    class BatchHook:
+        n = 0
+
+        def on_batch_end(self, s, ep, b):
+            BatchHook.n += 1
+
+    nn = make()
+    nn.fit(data, epochs=1, pos_batch_size=pos_b, neg_batch_size=neg_b, k=k, lr=0.07, input_bases=bases, callbacks=[BatchHook()])
+    assert BatchHook.n == nb
+    for i, (a, b) in enumerate(zip([p for net in nn.networks for p in getattr(nn, net).parameters()], pu)):
+        assert a.shape == b.shape
+    nn = make()
+    nn.fit(data, epochs=1, pos_batch_size=pos_b, neg_batch_size=neg_b, k=k, lr=0.01, input_bases=bases, optimizer=torch.optim.Adam)
+
+
 def test_fit_complex_and_density_smoke(lib, cuda):
     """Parameters move after one epoch with mixed bases (reference tests/test_training.py:40-70)."""
     from qucumber_b200 import ComplexWaveFunction, DensityMatrix
