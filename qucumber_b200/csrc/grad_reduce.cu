@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s,
 // hundreds (profiles/two_qubit_launches_r02.txt).  Here the loads of all rows are in flight at once; phase 2 adds the rows in
 // ascending order with the same fused multiply-adds, so g is bit for bit what the one-CTA walk of grad_reduce_kernel writes.
 template <int SRC>
-__global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_kernel(AffineSpec s, RowSrc src, int rows, GradDirect direct) {
+__device__ __forceinline__ void grad_reduce_tiny_body(const AffineSpec& s, const RowSrc& src, int rows, const GradDirect& direct) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ws = reinterpret_cast<double*>(smem_raw);
   const int N = s.n_in1, Hc = s.n_out;
@@ -228,6 +228,23 @@ __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_kernel(AffineSp
     }
     direct.put(nullptr, (size_t)e, acc);
   }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_kernel(AffineSpec s, RowSrc src, int rows, GradDirect direct) {
+  grad_reduce_tiny_body<SRC>(s, src, rows, direct);
+}
+
+// The amplitude and the phase RBM of a rotated-basis gradient take the same expanded rows with their own weights: two CTAs
+// of ONE launch (each what grad_reduce_tiny_kernel<ROWS_EXPANDED> does for its RBM).
+struct TinyJob {
+  AffineSpec s;
+  RowSrc src;
+  GradDirect direct;
+};
+__global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_pair_kernel(TinyJob j0, TinyJob j1, int rows) {
+  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct);
+  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct);
 }
 
 static size_t grad_reduce_tiny_smem(int N, int Hc, int H, int64_t rows) {
@@ -391,6 +408,32 @@ int run_grad_reduce_expanded(const StackedParams& p, const Expansion& ex, int64_
   const int H = p.nh + n_aux;
   const int G = H * p.N + p.N + H;
   return launch_grad_reduce<ROWS_EXPANDED>(hidden_only_spec(p), src, H, rows, scale, g, 1, G - zero_tail, ws, ws_bytes, st);
+}
+
+// Both RBMs of a rotated-basis gradient over the same expanded rows: g_am += scale * (...) with (w_am, aux_am), g_ph likewise
+// with (w_ph, aux_ph) and its last zero_tail_ph entries untouched.  A handful of rows of a small layer: one launch for both
+// (values as from two run_grad_reduce_expanded calls); otherwise those two calls.
+int run_grad_reduce_expanded_pair(const StackedParams& am, const StackedParams& ph, const Expansion& ex, int64_t rows, const double* w_am,
+                                  const double* aux_am, const double* w_ph, const double* aux_ph, int n_aux, int zero_tail_ph,
+                                  double scale, double* g_am, double* g_ph, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int N = am.N, Hc = am.nh, H = am.nh + n_aux;
+  const int G = H * N + N + H;
+  if (rows > 0 && rows <= GR_DIRECT_MAX_ROWS && N <= 16 && H <= 16 && ph.N == N && ph.nh == Hc &&
+      grad_reduce_tiny_smem(N, Hc, H, rows) <= 48 * 1024) {
+    TinyJob j0{}, j1{};
+    j0.s = hidden_only_spec(am);
+    j1.s = hidden_only_spec(ph);
+    j0.src.ex = ex; j0.src.wrow = w_am; j0.src.aux = aux_am; j0.src.n_aux = n_aux;
+    j1.src.ex = ex; j1.src.wrow = w_ph; j1.src.aux = aux_ph; j1.src.n_aux = n_aux;
+    j0.direct = GradDirect{g_am, scale, 1, G};
+    j1.direct = GradDirect{g_ph, scale, 1, G - zero_tail_ph};
+    grad_reduce_tiny_pair_kernel<<<2, ROWS_THREADS, grad_reduce_tiny_smem(N, Hc, H, rows), st>>>(j0, j1, (int)rows);
+    QCB_LAUNCH_CHECK();
+    return QCB_OK;
+  }
+  int rc = run_grad_reduce_expanded(am, ex, rows, w_am, aux_am, n_aux, 0, scale, g_am, ws, ws_bytes, st);
+  if (rc != QCB_OK) return rc;
+  return run_grad_reduce_expanded(ph, ex, rows, w_ph, aux_ph, n_aux, zero_tail_ph, scale, g_ph, ws, ws_bytes, st);
 }
 
 }  // namespace qcb

@@ -25,6 +25,9 @@ namespace qcb {
 int run_grad_reduce_expanded(const StackedParams& p, const Expansion& ex, int64_t rows, const double* wrow,
                              const double* aux, int n_aux, int zero_tail, double scale, double* g, void* ws, size_t ws_bytes,
                              cudaStream_t st);
+int run_grad_reduce_expanded_pair(const StackedParams& am, const StackedParams& ph, const Expansion& ex, int64_t rows, const double* w_am,
+                                  const double* aux_am, const double* w_ph, const double* aux_ph, int n_aux, int zero_tail_ph,
+                                  double scale, double* g_am, double* g_ph, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t grad_reduce_workspace_bytes(int N, int nhid, int64_t rows);
 size_t cwf_gray_workspace_bytes(int N);
 int run_cwf_grad_gray(const StackedParams& am, const StackedParams& ph, const double* samples, int64_t Bc, const SiteInfo& si,
@@ -362,9 +365,7 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
     cwf_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(T, D, S, rows, wa, wp);
     QCB_LAUNCH_CHECK();
     ex.samples = samples + b0 * N;
-    rc = run_grad_reduce_expanded(am, ex, rows, wa, nullptr, 0, 0, 1.0, g_am, gws, gws_bytes, st);
-    if (rc != QCB_OK) return rc;
-    rc = run_grad_reduce_expanded(ph, ex, rows, wp, nullptr, 0, 0, 1.0, g_ph, gws, gws_bytes, st);
+    rc = run_grad_reduce_expanded_pair(am, ph, ex, rows, wa, nullptr, wp, nullptr, 0, 0, 1.0, g_am, g_ph, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
   }
   return QCB_OK;
@@ -658,9 +659,7 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
     if (g_am == nullptr) continue;
     dm_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, UrhoU, na, S, rows, b0, wam, auxam, wph, auxph);
     QCB_LAUNCH_CHECK();
-    rc = run_grad_reduce_expanded(am, ex, rows, wam, auxam, na, 0, -1.0, g_am, gws, gws_bytes, st);
-    if (rc != QCB_OK) return rc;
-    rc = run_grad_reduce_expanded(ph, ex, rows, wph, auxph, na, na, -1.0, g_ph, gws, gws_bytes, st);
+    rc = run_grad_reduce_expanded_pair(am, ph, ex, rows, wam, auxam, wph, auxph, na, na, -1.0, g_am, g_ph, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
   }
   return QCB_OK;
