@@ -164,7 +164,9 @@ int qcb_rbm_grad_reduce(const double* W, const double* U, const double* b, const
  * below when a row is not binary or the weights do not fit; mode 3: never tcgen05 (integer theta on mma.sync + FP64
  * tensor-core outer products, csrc/grad_reduce_dmma.cu); mode 1: FP64 tensor cores only.  Modes 1 and 3 also make
  * qcb_cwf_rotated reduce the expanded rows through those kernels instead of the Gray-walk subset sums of
- * csrc/rotated_gray.cu (same results to rounding; for tests and measurements).
+ * csrc/rotated_gray.cu, and make qcb_cwf_rotated / qcb_dm_rotated send small basis groups (at most 256 expanded rows, layers
+ * of at most 16 units) through the general kernels instead of the one-launch kernels (same results to rounding; for tests
+ * and measurements).
  * Small layers (N <= 12, nh + na <= 16) with >= 16 * 2^N binary rows are COUNTED in mode 0 (csrc/grad_reduce_small.cu: a
  * histogram of the at most 2^N distinct rows — one coalesced read of the batch — then one weighted pass over the states);
  * a non-binary row hands the batch to the streaming kernel on the device.  Modes 1 and 3 always stream. */

@@ -34,6 +34,7 @@ extern int g_gibbs_mode;
 extern int g_grad_mode;
 extern int g_grad_small_hist;
 extern int g_cwf_mode;
+extern int g_rotated_tiny;
 extern int g_cd_epoch_mode;
 int try_gibbs_imma(const StackedParams& p, const ChainIO& io, int64_t C, int k, uint64_t seed, uint64_t chain_id0,
                    uint64_t sweep0, void* ws, size_t ws_bytes, unsigned long long* dbg, int* handled, cudaStream_t st);
@@ -262,6 +263,7 @@ int qcb_set_grad_reduce_mode(int mode) {
   g_grad_mode = mode;
   g_grad_small_hist = mode == 0 ? 1 : 0;  // the histogram path of small binary layers is part of the automatic selection
   g_cwf_mode = mode != 0 ? 1 : 0;  // modes 1 and 3 also send the rotated-basis gradients through the expanded-row reduction
+  g_rotated_tiny = mode == 0 ? 1 : 0;  // ... and small basis groups through the general kernels instead of the one-launch kernels
   return QCB_OK;
 }
 

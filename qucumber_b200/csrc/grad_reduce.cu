@@ -28,24 +28,6 @@ int try_grad_reduce_dmma(const AffineSpec& s, const RowSrc& src, int mode, int H
                          int* grid_out, int* flag, unsigned char* umma_img, cudaStream_t st);
 size_t grad_umma_workspace_bytes();
 
-// Tiny batches (one CTA): the kernel applies what grad_finalize_kernel would — g[e] = (accumulate ? g[e] : 0) - scale * sum[e],
-// nothing for e >= zero_from — instead of writing a partial for a second launch to pick up (a rotated-basis batch of the
-// two-qubit tutorials is up to nine bases x two reductions: the launches were the cost).  Same value bit for bit.
-struct GradDirect {
-  double* g;        // NULL: write the CTA's partial
-  double scale;
-  int accumulate;
-  int zero_from;
-  __device__ __forceinline__ void put(double* partial_out, size_t e, double sum) const {
-    if (g == nullptr) {
-      partial_out[e] = sum;
-    } else {
-      const double val = (long long)e >= (long long)zero_from ? 0.0 : -scale * sum;
-      g[e] = accumulate ? g[e] + val : val;
-    }
-  }
-};
-
 template <int TPT, int SRC>  // TPT = 4x4 tiles per thread
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s, RowSrc src, int64_t rows,
                                                                    double* __restrict__ partials, GradDirect direct) {
@@ -174,82 +156,20 @@ __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_kernel(AffineSpec s,
   if (threadIdx.x < N + H) direct.put(out, (size_t)H * N + threadIdx.x, bsum);
 }
 
-// The same reduction for a handful of rows of a small layer (rows <= GR_DIRECT_MAX_ROWS, a few KB of tiles), one CTA, one
-// THREAD per row in phase 1: in grad_reduce_kernel a warp walks its rows one after the other and every row waits for its own
-// global loads — 16 us per launch for the 20..80 expanded rows of a two-qubit basis group, of which a training epoch has
-// hundreds (profiles/two_qubit_launches_r02.txt).  Here the loads of all rows are in flight at once; phase 2 adds the rows in
-// ascending order with the same fused multiply-adds, so g is bit for bit what the one-CTA walk of grad_reduce_kernel writes.
-template <int SRC>
-__device__ __forceinline__ void grad_reduce_tiny_body(const AffineSpec& s, const RowSrc& src, int rows, const GradDirect& direct) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Ws = reinterpret_cast<double*>(smem_raw);
-  const int N = s.n_in1, Hc = s.n_out;
-  const int H = Hc + (SRC == ROWS_EXPANDED ? src.n_aux : 0);
-  const int LD = N | 1;
-  double* bs = Ws + round_up(Hc * LD, 2);
-  double* Vt = bs + round_up(Hc, 2);        // [rows][N]
-  double* Pt = Vt + (size_t)rows * N;       // [rows][H]
-  double* wts = Pt + (size_t)rows * H;      // [rows]
-  stage_affine(s, Ws, LD, bs);
-  __syncthreads();
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-    double* vrow = Vt + r * N;
-    double* prow = Pt + r * H;
-    for (int i = 0; i < N; ++i) vrow[i] = SRC == ROWS_EXPANDED ? src.ex.value(r, i) : src.v[(size_t)r * N + i];
-    const double wgt = SRC == ROWS_EXPANDED ? src.wrow[r] : 1.0;
-    for (int o = 0; o < Hc; ++o) {
-      const double* wrow = Ws + (size_t)o * LD;
-      double th = bs[o];
-      for (int i = 0; i < N; ++i) th = fma(wrow[i], vrow[i], th);
-      const double pr = fmin(fmax(sigmoid_exact(th), 0.0), 1.0);
-      prow[o] = SRC == ROWS_EXPANDED ? pr * wgt : pr;
-    }
-    if (SRC == ROWS_EXPANDED) {
-      for (int o = 0; o < src.n_aux; ++o) prow[Hc + o] = src.aux[(size_t)r * src.n_aux + o];
-      wts[r] = wgt;
-    }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < H * N + N + H; e += blockDim.x) {
-    double acc = 0.0;
-    if (e < H * N) {
-      const int i = e / N, j = e - i * N;
-      for (int r = 0; r < rows; ++r) acc = fma(Pt[r * H + i], Vt[r * N + j], acc);
-    } else if (e < H * N + N) {
-      const int j = e - H * N;
-      if (SRC == ROWS_EXPANDED) {
-        for (int r = 0; r < rows; ++r) acc = fma(wts[r], Vt[r * N + j], acc);
-      } else {
-        for (int r = 0; r < rows; ++r) acc += Vt[r * N + j];
-      }
-    } else {
-      const int i = e - H * N - N;
-      for (int r = 0; r < rows; ++r) acc += Pt[r * H + i];
-    }
-    direct.put(nullptr, (size_t)e, acc);
-  }
-}
-
 template <int SRC>
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_kernel(AffineSpec s, RowSrc src, int rows, GradDirect direct) {
-  grad_reduce_tiny_body<SRC>(s, src, rows, direct);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  grad_reduce_tiny_body<SRC>(s, src, rows, direct, smem_raw);
 }
 
 // The amplitude and the phase RBM of a rotated-basis gradient take the same expanded rows with their own weights: two CTAs
 // of ONE launch (each what grad_reduce_tiny_kernel<ROWS_EXPANDED> does for its RBM).
-struct TinyJob {
-  AffineSpec s;
-  RowSrc src;
-  GradDirect direct;
-};
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_pair_kernel(TinyJob j0, TinyJob j1, int rows) {
-  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct);
-  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
+  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
 }
 
-static size_t grad_reduce_tiny_smem(int N, int Hc, int H, int64_t rows) {
-  return ((size_t)round_up(Hc * (N | 1), 2) + round_up(Hc, 2) + (size_t)rows * (N + H + 1)) * sizeof(double);
-}
 
 // g[e] = (accumulate ? g[e] : 0) + scale * (-(sum over CTAs of partial[e])); entries >= zero_from are
 // forced to contribute nothing (the phase RBM's aux bias never receives a gradient,

@@ -275,6 +275,85 @@ __global__ void cwf_sum_kernel(const double2* __restrict__ T, int S, int64_t b0,
   }
 }
 
+// ---- a whole basis group of a SMALL state in one launch -----------------------------------------------------------------
+// At most TINY_MAX_ROWS expanded rows, layers of at most 16 units (the two-qubit trainings of the reference's Tutorials 2 / 3:
+// a batch is up to nine groups of ~10 samples x 4 rows): the three to five kernels of the general path are microseconds of
+// work each and a training epoch launched hundreds of them.  Here CTA 0 serves the amplitude RBM and CTA 1 the phase RBM;
+// both evaluate the (cheap) per-row quantities, thread per expanded row, and each reduces its own RBM's gradient with
+// grad_reduce_tiny_body.  Same formulas as the general kernels; sums over a sample's rows run in ascending order.
+constexpr int TINY_MAX_ROWS = ROWS_THREADS;
+
+__global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
+                                                                     int rows, int64_t Btotal, double* __restrict__ Upsi, double* w_am,
+                                                                     double* w_ph, TinyJob j0, TinyJob j1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double2 Tsm[TINY_MAX_ROWS];
+  const Expansion& ex = j0.src.ex;
+  const int N = am.N, nh = am.nh, S = si.S;
+  const int r = threadIdx.x;
+  const int mask = (1 << S) - 1;
+  if (r < rows) {
+    // T_i = Ut_i |psi(v_i)| e^{i phi(v_i)}, |psi| = sqrt(exp(-E_am)), phi = -E_ph / 2 (complex_wavefunction.py:129-142)
+    double xa = 0.0, xp = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double vj = ex.value(r, j);
+      xa = fma(am.b[j], vj, xa);
+      xp = fma(ph.b[j], vj, xp);
+    }
+    for (int i = 0; i < nh; ++i) {
+      double ta = am.c[i], tp = ph.c[i];
+      for (int j = 0; j < N; ++j) {
+        const double vj = ex.value(r, j);
+        ta = fma(am.W[(size_t)i * N + j], vj, ta);
+        tp = fma(ph.W[(size_t)i * N + j], vj, tp);
+      }
+      xa += softplus20(ta);
+      xp += softplus20(tp);
+    }
+    const double amp = exp(0.5 * xa);
+    double sn, cs;
+    sincos(0.5 * xp, &sn, &cs);
+    const int b = r >> S;
+    uint32_t sigbits = 0;
+    for (int t = 0; t < S; ++t) sigbits |= (ex.samples[(size_t)b * N + si.site[t]] != 0.0 ? 1u : 0u) << t;
+    double tr, ti;
+    unitary_product(U, si, sigbits, (uint32_t)(r & mask), tr, ti);
+    cmul(tr, ti, amp * cs, amp * sn);
+    Tsm[r] = make_double2(tr, ti);
+  }
+  __syncthreads();
+  if (r < rows) {
+    const int b = r >> S;
+    double dr = 0.0, di = 0.0;
+    for (int i = 0; i <= mask; ++i) { dr += Tsm[(b << S) + i].x; di += Tsm[(b << S) + i].y; }
+    if (blockIdx.x == 0 && (r & mask) == 0) {
+      Upsi[b] = dr;
+      Upsi[Btotal + b] = di;
+    }
+    const double2 t = Tsm[r];
+    const double inv = 1.0 / (dr * dr + di * di);
+    if (blockIdx.x == 0) w_am[r] = (t.x * dr + t.y * di) * inv;   // Re(T / D)
+    else w_ph[r] = -((t.y * dr - t.x * di) * inv);                // -Im(T / D)
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
+  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
+}
+
+static void make_tiny_jobs(const StackedParams& am, const StackedParams& ph, const Expansion& ex, const double* w_am, const double* aux_am,
+                           const double* w_ph, const double* aux_ph, int n_aux, int zero_tail_ph, double scale, double* g_am, double* g_ph,
+                           TinyJob& j0, TinyJob& j1) {
+  const int G = (am.nh + n_aux) * am.N + am.N + am.nh + n_aux;
+  j0.s = hidden_only_spec(am);
+  j1.s = hidden_only_spec(ph);
+  j0.src.ex = ex; j0.src.wrow = w_am; j0.src.aux = aux_am; j0.src.n_aux = n_aux;
+  j1.src.ex = ex; j1.src.wrow = w_ph; j1.src.aux = aux_ph; j1.src.n_aux = n_aux;
+  j0.direct = GradDirect{g_am, scale, 1, G};
+  j1.direct = GradDirect{g_ph, scale, 1, G - zero_tail_ph};
+}
+
+int g_rotated_tiny = 1;  // 0: small groups take the general kernels too (test / measurement hook, qcb_set_rotated_mode bit 1)
+
 static int make_sites(const uint8_t* basis_host, int N, int K, SiteInfo& si, Expansion& ex) {
   si.S = 0;
   for (int j = 0; j < N; ++j) {
@@ -338,6 +417,16 @@ int run_cwf_rotated(const StackedParams& am, const StackedParams& ph, const doub
   void* gws = base + align_up((size_t)ROT_MAX_ROWS * 32, 256) + align_up((size_t)B * 16, 256);
   const size_t gws_bytes = ws_bytes - (size_t)(static_cast<char*>(gws) - base);
   const int S = si.S;
+  if (g_rotated_tiny && g_am != nullptr && S <= 8 && (B << S) <= TINY_MAX_ROWS && N <= 16 && nh <= 16 &&
+      grad_reduce_tiny_smem(N, nh, nh, B << S) <= 40 * 1024) {  // a small group: amplitudes, weights and both reductions in one launch
+    const int rows = (int)(B << S);
+    ex.samples = samples;
+    TinyJob j0{}, j1{};
+    make_tiny_jobs(am, ph, ex, wa, nullptr, wp, nullptr, 0, 0, 1.0, g_am, g_ph, j0, j1);
+    cwf_group_tiny_kernel<<<2, ROWS_THREADS, grad_reduce_tiny_smem(N, nh, nh, rows), st>>>(am, ph, si, unitaries, rows, B, Upsi, wa, wp, j0, j1);
+    QCB_LAUNCH_CHECK();
+    return QCB_OK;
+  }
   const int64_t chunkB = ROT_MAX_ROWS >> S;
   for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
     const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
@@ -427,19 +516,14 @@ __global__ void __launch_bounds__(256) dm_feat_kernel(StackedParams am, StackedP
 
 // thread per expanded row i of sample b: loops over the partner index j
 // stats row: [r_i, s_i, R_i[na], I_i[na]]
-__global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__ feat, int na, int S, int64_t rows,
-                                                      double* __restrict__ stats) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
-  const int64_t b = r >> S;
-  const double* fi = feat + r * FW;
+__device__ __forceinline__ void dm_pair_row(const double* fi, const double* fsample, int na, int S, double* out) {
+  const int FW = 4 + 2 * na;
   double ri = 0.0, si = 0.0;
   double R[DM_MAX_NA], I[DM_MAX_NA], Sr[DM_MAX_NA], Si[DM_MAX_NA];
   for (int k = 0; k < na; ++k) { R[k] = 0.0; I[k] = 0.0; }
   const int nexp = 1 << S;
   for (int j = 0; j < nexp; ++j) {
-    const double* fj = feat + ((b << S) + j) * FW;
+    const double* fj = fsample + (size_t)j * FW;
     const double gp = 0.5 * (fi[0] + fj[0]);   // Gamma+ (amplitude RBM)
     const double gm = 0.5 * (fi[1] - fj[1]);   // Gamma- (phase RBM)
     double pre = 0.0, pim = 0.0;
@@ -475,10 +559,17 @@ __global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__
       I[k] += wr * Si[k] + wi * Sr[k];
     }
   }
-  double* out = stats + r * SW;
   out[0] = ri;
   out[1] = si;
   for (int k = 0; k < na; ++k) { out[2 + k] = R[k]; out[2 + na + k] = I[k]; }
+}
+
+__global__ void __launch_bounds__(128) dm_pair_kernel(const double* __restrict__ feat, int na, int S, int64_t rows,
+                                                      double* __restrict__ stats) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  dm_pair_row(feat + r * FW, feat + ((r >> S) << S) * FW, na, S, stats + r * SW);
 }
 
 // The same pair sums for auxiliary layers of more than DM_MAX_NA units: a WARP per expanded row i, lane l owns the auxiliary
@@ -603,6 +694,104 @@ __global__ void dm_weights_kernel(const double* __restrict__ stats, const double
   }
 }
 
+// DensityMatrix: features, pair sums, probabilities, row weights and (want_grad) the two reductions
+__global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
+                                                                    int rows, double* __restrict__ UrhoU, double* w_am, double* aux_am,
+                                                                    double* w_ph, double* aux_ph, int want_grad, size_t body_bytes,
+                                                                    TinyJob j0, TinyJob j1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Expansion& ex = j0.src.ex;
+  const int N = am.N, nh = am.nh, na = am.na, S = si.S;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  double* feat = reinterpret_cast<double*>(smem_raw + body_bytes);  // [rows][FW]
+  double* stats = feat + (size_t)rows * FW;                          // [rows][SW]
+  const int r = threadIdx.x;
+  const int mask = (1 << S) - 1;
+  if (r < rows) {
+    double fa = 0.0, fp = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double vj = ex.value(r, j);
+      fa = fma(am.b[j], vj, fa);
+      fp = fma(ph.b[j], vj, fp);
+    }
+    for (int i = 0; i < nh; ++i) {
+      double ta = am.c[i], tp = ph.c[i];
+      for (int j = 0; j < N; ++j) {
+        const double vj = ex.value(r, j);
+        ta = fma(am.W[(size_t)i * N + j], vj, ta);
+        tp = fma(ph.W[(size_t)i * N + j], vj, tp);
+      }
+      fa += softplus20(ta);
+      fp += softplus20(tp);
+    }
+    double* out = feat + (size_t)r * FW;
+    for (int k = 0; k < na; ++k) {
+      double ma = am.d[k], mp = 0.0;
+      for (int j = 0; j < N; ++j) {
+        const double vj = ex.value(r, j);
+        ma = fma(am.U[(size_t)k * N + j], vj, ma);
+        mp = fma(ph.U[(size_t)k * N + j], vj, mp);
+      }
+      out[4 + k] = ma;
+      out[4 + na + k] = mp;
+    }
+    const int b = r >> S;
+    uint32_t sigbits = 0;
+    for (int t = 0; t < S; ++t) sigbits |= (ex.samples[(size_t)b * N + si.site[t]] != 0.0 ? 1u : 0u) << t;
+    double ur, ui;
+    unitary_product(U, si, sigbits, (uint32_t)(r & mask), ur, ui);
+    out[0] = fa; out[1] = fp; out[2] = ur; out[3] = ui;
+  }
+  __syncthreads();
+  if (r < rows) dm_pair_row(feat + (size_t)r * FW, feat + (size_t)((r >> S) << S) * FW, na, S, stats + (size_t)r * SW);
+  __syncthreads();
+  if (r < rows) {
+    const int b = r >> S;
+    double p = 0.0;
+    for (int i = 0; i <= mask; ++i) p += stats[(size_t)((b << S) + i) * SW];
+    if (blockIdx.x == 0 && (r & mask) == 0) UrhoU[b] = p;
+    if (want_grad) {
+      const double f = -1.0 / (p + 1e-8);  // nn_states/density_matrix.py:296,300
+      const double* st = stats + (size_t)r * SW;
+      if (blockIdx.x == 0) {
+        w_am[r] = f * st[0];
+        for (int k = 0; k < na; ++k) aux_am[(size_t)r * na + k] = f * st[2 + k];
+      } else {
+        w_ph[r] = -f * st[1];
+        for (int k = 0; k < na; ++k) aux_ph[(size_t)r * na + k] = -f * st[2 + na + k];
+      }
+    }
+  }
+  if (!want_grad) return;
+  __syncthreads();
+  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
+  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
+}
+
+// both of the above in one launch for few rotated sites (every row thread re-adds its sample's 2^S terms in the same order:
+// same P_b, same weights; one launch less per basis group of a two-qubit training batch)
+constexpr int DM_PW_MAX_S = 4;
+__global__ void dm_prob_weights_kernel(const double* __restrict__ stats, int na, int S, int64_t rows, int64_t b0, double* __restrict__ UrhoU,
+                                       double* __restrict__ wam, double* __restrict__ auxam, double* __restrict__ wph,
+                                       double* __restrict__ auxph, int want_weights) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int SW = 2 + 2 * na;
+  const int64_t b = r >> S;
+  double p = 0.0;
+  for (int i = 0; i < (1 << S); ++i) p += stats[((b << S) + i) * SW];
+  if ((r & (((int64_t)1 << S) - 1)) == 0) UrhoU[b0 + b] = p;
+  if (!want_weights) return;
+  const double f = -1.0 / (p + 1e-8);  // nn_states/density_matrix.py:296,300
+  const double* s = stats + r * SW;
+  wam[r] = f * s[0];
+  wph[r] = -f * s[1];
+  for (int k = 0; k < na; ++k) {
+    auxam[r * na + k] = f * s[2 + k];
+    auxph[r * na + k] = -f * s[2 + na + k];
+  }
+}
+
 constexpr int64_t DM_MAX_ROWS = (int64_t)1 << 18;
 // expanded rows per chunk: 2^18, halved while the per-row scratch of a wide auxiliary layer would exceed 256 MiB
 // (never below one sample's 2^DM_MAX_S rows)
@@ -644,6 +833,20 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
   const size_t per_row = (size_t)FW + SW + SW;
   void* gws = static_cast<char*>(ws) + align_up((size_t)max_rows * per_row * sizeof(double), 256);
   const size_t gws_bytes = grad_reduce_workspace_bytes(N, nh + na, max_rows);
+  if (g_rotated_tiny && S <= 8 && (B << S) <= TINY_MAX_ROWS && N <= 16 && nh + na <= 16 && na <= DM_MAX_NA) {
+    const int rows = (int)(B << S);
+    const size_t body = align_up(grad_reduce_tiny_smem(N, nh, nh + na, rows), 16);
+    const size_t smem = body + (size_t)rows * (FW + SW) * sizeof(double);
+    if (smem <= 44 * 1024) {  // a small group: features, pair sums, probabilities, weights and both reductions in one launch
+      ex.samples = samples;
+      TinyJob j0{}, j1{};
+      make_tiny_jobs(am, ph, ex, wam, auxam, wph, auxph, na, na, -1.0, g_am, g_ph, j0, j1);
+      dm_group_tiny_kernel<<<g_am != nullptr ? 2 : 1, ROWS_THREADS, smem, st>>>(am, ph, si, unitaries, rows, UrhoU, wam, auxam, wph, auxph,
+                                                                             g_am != nullptr ? 1 : 0, body, j0, j1);
+      QCB_LAUNCH_CHECK();
+      return QCB_OK;
+    }
+  }
   const int64_t chunkB = max_rows >> S;
   for (int64_t b0 = 0; b0 < B; b0 += chunkB) {
     const int64_t Bc = B - b0 < chunkB ? B - b0 : chunkB;
@@ -654,11 +857,18 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
     QCB_LAUNCH_CHECK();
     rc = launch_dm_pairs(feat, na, S, rows, stats, st);
     if (rc != QCB_OK) return rc;
-    dm_prob_kernel<<<(unsigned)((Bc + 127) / 128), 128, 0, st>>>(stats, na, S, Bc, b0, UrhoU);
-    QCB_LAUNCH_CHECK();
-    if (g_am == nullptr) continue;
-    dm_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, UrhoU, na, S, rows, b0, wam, auxam, wph, auxph);
-    QCB_LAUNCH_CHECK();
+    if (S <= DM_PW_MAX_S && rows <= 4096) {
+      dm_prob_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, na, S, rows, b0, UrhoU, wam, auxam, wph, auxph,
+                                                                           g_am != nullptr ? 1 : 0);
+      QCB_LAUNCH_CHECK();
+      if (g_am == nullptr) continue;
+    } else {
+      dm_prob_kernel<<<(unsigned)((Bc + 127) / 128), 128, 0, st>>>(stats, na, S, Bc, b0, UrhoU);
+      QCB_LAUNCH_CHECK();
+      if (g_am == nullptr) continue;
+      dm_weights_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, UrhoU, na, S, rows, b0, wam, auxam, wph, auxph);
+      QCB_LAUNCH_CHECK();
+    }
     rc = run_grad_reduce_expanded_pair(am, ph, ex, rows, wam, auxam, wph, auxph, na, na, -1.0, g_am, g_ph, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
   }

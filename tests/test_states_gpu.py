@@ -1185,3 +1185,64 @@ def test_complex_rotated_gradient_gray_walk(lib, cuda, n, nh, S, B, scale):
         ga, gp = orc.complex_rotated_gradient(am, ph, list(basis), samples)
         assert_close(new[0], ga, what="Gray-walk vs oracle (amplitude)")
         assert_close(new[1], gp, what="Gray-walk vs oracle (phase)")
+
+
+@pytest.mark.parametrize("kind,n,nh,na,S,B", [("complex", 2, 2, 0, 1, 20), ("complex", 2, 2, 0, 2, 64), ("complex", 6, 5, 0, 3, 32),
+                                              ("complex", 16, 16, 0, 4, 8), ("complex", 9, 3, 0, 8, 1), ("complex", 3, 7, 0, 1, 128),
+                                              ("density", 2, 2, 2, 2, 64), ("density", 2, 2, 2, 1, 11), ("density", 5, 4, 3, 3, 16),
+                                              ("density", 8, 6, 10, 2, 12), ("density", 4, 1, 15, 4, 3)])
+def test_small_basis_groups_one_launch_equal_general_kernels(lib, cuda, kind, n, nh, na, S, B):
+    """A basis group of at most 256 expanded rows of a state with layers of at most 16 units is ONE launch (cwf_group_tiny_kernel /
+    dm_group_tiny_kernel: per-row quantities, weights and both RBMs' reductions). Same formulas as the general kernels
+    (qcb_set_grad_reduce_mode(1) sends the group through them): gradients and rotated amplitudes / probabilities agree to
+    rounding, and both agree with the oracle."""
+    from qucumber_b200 import ComplexWaveFunction, DensityMatrix, _lib
+    from qucumber_b200.utils import unitaries as qu
+
+    rng = np.random.default_rng(7000 + 10 * n + S)
+    if kind == "complex":
+        nn = ComplexWaveFunction(n, nh, gpu=True)
+        pa, pp = make_binary_params(n, nh, 51, bias_scale=0.4), make_binary_params(n, nh, 52, bias_scale=0.4)
+        load_binary(nn.rbm_am, *pa)
+        load_binary(nn.rbm_ph, *pp)
+    else:
+        nn = DensityMatrix(n, nh, na, gpu=True)
+        pa, pp = make_purification_params(n, nh, na, 53), make_purification_params(n, nh, na, 54)
+        load_purification(nn.rbm_am, *pa)
+        load_purification(nn.rbm_ph, *pp)
+    sites = np.sort(rng.choice(n, S, replace=False))
+    basis = np.array(["Z"] * n)
+    basis[sites] = rng.choice(["X", "Y"], S)
+    samples = random_states(B, n, 55)
+    ts = torch.tensor(samples, device=cuda)
+    call = qu._call_cwf if kind == "complex" else qu._call_dm
+
+    def run():
+        g_am = torch.zeros(nn.rbm_am.num_pars, dtype=torch.double, device=cuda)
+        g_ph = torch.zeros(nn.rbm_ph.num_pars, dtype=torch.double, device=cuda)
+        l0 = lib.qcb_launch_count()
+        out = call(nn.rbm_am, nn.rbm_ph, basis, ts, nn.unitary_dict, g_am, g_ph)
+        return out.cpu().numpy(), g_am.cpu().numpy(), g_ph.cpu().numpy(), lib.qcb_launch_count() - l0
+
+    out_t, ga_t, gp_t, launches = run()
+    assert launches == 1
+    _lib.check(lib.qcb_set_grad_reduce_mode(1), "mode")
+    try:
+        out_g, ga_g, gp_g, launches_g = run()
+    finally:
+        _lib.check(lib.qcb_set_grad_reduce_mode(0), "mode")
+    assert launches_g >= 3
+    assert_close(out_t, out_g, rtol=1e-12, what="rotated amplitudes / probabilities: one launch vs general kernels")
+    # entries are sums of terms of both signs: the two paths add the same terms in different orders (cf. the Gray-walk test)
+    assert_close(ga_t, ga_g, rtol=1e-11, elementwise=False, what="amplitude gradient: one launch vs general kernels")
+    assert_close(gp_t, gp_g, rtol=1e-11, elementwise=False, what="phase gradient: one launch vs general kernels")
+    if kind == "density":
+        assert np.all(gp_t[-na:] == 0.0)  # the phase RBM's aux bias never receives a gradient
+        assert np.array_equal(call(nn.rbm_am, nn.rbm_ph, basis, ts, nn.unitary_dict).cpu().numpy(), out_t)  # probabilities only: one CTA
+    got = [g.cpu().numpy() for g in nn.rotated_gradient(basis, ts)]
+    if kind == "complex":
+        want = orc.complex_rotated_gradient(orc.BinaryRBMOracle(*pa), orc.BinaryRBMOracle(*pp), list(basis), samples)
+    else:
+        want = orc.dm_rotated_gradient(orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp), list(basis), samples)
+    assert_close(got[0], want[0], elementwise=S < 4, what="one launch vs oracle (amplitude)")
+    assert_close(got[1], want[1], elementwise=S < 4, what="one launch vs oracle (phase)")
