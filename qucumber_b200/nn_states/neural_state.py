@@ -603,6 +603,7 @@ class NeuralStateBase(abc.ABC):
     _train_bits = None         # set by fit(): the packed copy of a large binary data set (see _cd_gradients_packed)
     _basis_groups = None       # set by fit(): (unique bases, group id of every sample) of the data set
     _basis_codes = None        # set by fit(): (codes of the unique bases, names of the unitaries they index)
+    _index_staging = None      # set by _fit_epoch_bases(): two pinned index buffers with the events of their last copies
     #: set to False to keep fit() on float64 rows whatever the data
     pack_training_data = True
     # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
@@ -662,8 +663,23 @@ class NeuralStateBase(abc.ABC):
         counts = np.bincount(key, minlength=num_batches * G)
         offsets = np.zeros(num_batches * G + 1, dtype=np.int64)
         np.cumsum(counts, out=offsets[1:])
-        pos = train_samples.index_select(0, torch.as_tensor(pos_perm[order], device=dev)).contiguous()
-        neg = z_samples.index_select(0, neg_perm.to(dev)).contiguous()
+        # both index vectors go over in ONE asynchronous copy from a pinned staging buffer (a pageable copy would make the host
+        # wait for the previous epoch's kernels before it could prepare this one); two buffers alternate, each guarded by an event
+        stage = self._index_staging
+        if stage is None or stage[0][0].numel() < n + neg_perm.numel():
+            stage = self._index_staging = [[torch.empty(n + neg_perm.numel(), dtype=torch.long).pin_memory(), None] for _ in range(2)]
+        stage.reverse()
+        buf, busy = stage[0]
+        if busy is not None:
+            busy.synchronize()
+        host = buf[:n + neg_perm.numel()]
+        host[:n] = torch.from_numpy(pos_perm[order])
+        host[n:] = neg_perm
+        index = host.to(dev, non_blocking=True)
+        stage[0][1] = torch.cuda.Event()
+        stage[0][1].record(torch.cuda.current_stream(dev))
+        pos = train_samples.index_select(0, index[:n])
+        neg = z_samples.index_select(0, index[n:])
         codes, names = self._basis_codes
         table = unitaries.unitary_table(self.unitary_dict, names, dev)
         na = int(getattr(am, "num_aux", 0))
@@ -874,4 +890,5 @@ class NeuralStateBase(abc.ABC):
         self._train_bits = None
         self._basis_groups = None
         self._basis_codes = None
+        self._index_staging = None
         cbs.fire("on_train_end", self)
