@@ -1246,3 +1246,64 @@ def test_small_basis_groups_one_launch_equal_general_kernels(lib, cuda, kind, n,
         want = orc.dm_rotated_gradient(orc.PurificationRBMOracle(*pa), orc.PurificationRBMOracle(*pp), list(basis), samples)
     assert_close(got[0], want[0], elementwise=S < 4, what="one launch vs oracle (amplitude)")
     assert_close(got[1], want[1], elementwise=S < 4, what="one launch vs oracle (phase)")
+
+
+def test_fit_epoch_bases_rejects_bad_arguments(lib, cuda):
+    """qcb_fit_epoch_bases reports bad arguments through its return code and qcb_last_error (nothing is launched); with lr = 0 and
+    one batch it leaves the parameters alone and returns the batch's CD gradient: the one of compute_batch_gradients."""
+    from qucumber_b200 import ComplexWaveFunction, _lib
+    from qucumber_b200.utils import unitaries as qu
+
+    torch.manual_seed(8)
+    nn = ComplexWaveFunction(3, 2, gpu=True)
+    am, ph = nn.rbm_am, nn.rbm_ph
+    rng = np.random.default_rng(81)
+    bases = np.array([list("XZZ")] * 6 + [list("ZZZ")] * 5 + [list("ZYX")] * 9)
+    pos = torch.tensor((rng.random((20, 3)) < 0.5).astype(np.float64), device=cuda)
+    neg = torch.tensor((rng.random((7, 3)) < 0.5).astype(np.float64), device=cuda)
+    uniq, ids = np.unique(bases, axis=0, return_inverse=True)
+    order = np.argsort(ids, kind="stable")
+    offsets = np.zeros(len(uniq) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ids, minlength=len(uniq)), out=offsets[1:])
+    rows, names = [], None
+    for b in uniq:
+        c_, names = qu.encode_basis(b, nn.unitary_dict)
+        rows.append(c_)
+    codes = np.ascontiguousarray(np.stack(rows).astype(np.uint8))
+    table = qu.unitary_table(nn.unitary_dict, names, cuda)
+    grouped = pos.index_select(0, torch.as_tensor(order, device=cuda)).contiguous()
+    ws = _lib.workspace(cuda, max(lib.qcb_workspace_bytes(_lib.OP_CWF_ROTATED, 3, 2, 0, 20), lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, 3, 2, 0, 7)))
+    scratch = torch.empty(40, dtype=torch.double, device=cuda)
+    g = torch.full((am.num_pars + ph.num_pars,), 7.0, dtype=torch.double, device=cuda)
+    vk = torch.empty(7 * 3, dtype=torch.double, device=cuda)
+    ptrs = [_lib.ptr(t.data) if t is not None else None for r in (am, ph) for t in (r.weights, None, r.visible_bias, r.hidden_bias, None)]
+
+    def call(ngroups=len(uniq), nbatches=1, ws_bytes=ws.numel(), na=0, k=4, gptr=_lib.ptr(g)):
+        return lib.qcb_fit_epoch_bases(*ptrs, 3, 2, na, _lib.ptr(grouped), offsets.ctypes.data, codes.ctypes.data, ngroups, nbatches,
+                                       _lib.ptr(table), len(names), _lib.ptr(neg), 7, k, 0.0, 1234, 5, _lib.ptr(scratch), gptr,
+                                       _lib.ptr(vk), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(cuda))
+
+    before = [p.detach().clone() for r in (am, ph) for p in r.parameters()]
+    launches0 = lib.qcb_launch_count()
+    assert call(ngroups=0) != 0 and b"fit_epoch_bases" in lib.qcb_last_error()
+    assert call(nbatches=-1) != 0 and b"fit_epoch_bases" in lib.qcb_last_error()
+    assert call(na=-1) != 0 and b"fit_epoch_bases" in lib.qcb_last_error()
+    assert call(k=-1) != 0 and b"fit_epoch_bases" in lib.qcb_last_error()
+    assert call(gptr=None) != 0 and b"fit_epoch_bases" in lib.qcb_last_error()
+    assert call(ws_bytes=64) != 0 and b"workspace" in lib.qcb_last_error()
+    assert lib.qcb_launch_count() == launches0
+    assert call() == 0
+    for a, b in zip(before, [p for r in (am, ph) for p in r.parameters()]):
+        assert torch.equal(a, b)  # lr = 0: gradient out, parameters untouched
+    # the same batch through the per-batch entry points with the same Philox stream
+    want = nn.gradient(pos, bases=bases)
+    for gr in want:
+        gr.mul_(1.0 / 20)
+    args, keep = am._param_args()
+    v2 = neg.clone()
+    ws2 = _lib.workspace(cuda, lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, 3, 2, 0, 7))
+    _lib.check(lib.qcb_rbm_cdk_neg(*args, _lib.ptr(v2), 7, 4, 1234, 0, 5, None, -1.0 / 7, _lib.ptr(want[0]), _lib.ptr(ws2), ws2.numel(),
+                                   _lib.stream_ptr(cuda)), "cdk_neg")
+    assert_close(g[:am.num_pars], want[0].cpu().numpy(), rtol=1e-12, what="amplitude gradient of the batch")
+    assert_close(g[am.num_pars:], want[1].cpu().numpy(), rtol=1e-12, what="phase gradient of the batch")
+    assert torch.equal(vk.view(7, 3), v2)
