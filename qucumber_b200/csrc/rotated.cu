@@ -282,6 +282,7 @@ __global__ void cwf_sum_kernel(const double2* __restrict__ T, int S, int64_t b0,
 // both evaluate the (cheap) per-row quantities, thread per expanded row, and each reduces its own RBM's gradient with
 // grad_reduce_tiny_body.  Same formulas as the general kernels; sums over a sample's rows run in ascending order.
 constexpr int TINY_MAX_ROWS = ROWS_THREADS;
+constexpr size_t DM_TINY_SMEM_MAX = 96 * 1024;
 
 __global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
                                                                      int rows, int64_t Btotal, double* __restrict__ Upsi, double* w_am,
@@ -698,7 +699,7 @@ __global__ void dm_weights_kernel(const double* __restrict__ stats, const double
 __global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
                                                                     int rows, double* __restrict__ UrhoU, double* w_am, double* aux_am,
                                                                     double* w_ph, double* aux_ph, int want_grad, size_t body_bytes,
-                                                                    TinyJob j0, TinyJob j1) {
+                                                                    int pair_parallel, TinyJob j0, TinyJob j1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Expansion& ex = j0.src.ex;
   const int N = am.N, nh = am.nh, na = am.na, S = si.S;
@@ -743,7 +744,73 @@ __global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedPara
     out[0] = fa; out[1] = fp; out[2] = ur; out[3] = ui;
   }
   __syncthreads();
-  if (r < rows) dm_pair_row(feat + (size_t)r * FW, feat + (size_t)((r >> S) << S) * FW, na, S, stats + (size_t)r * SW);
+  if (pair_parallel) {
+    // the pair sums of dm_pair_row with the terms spread over the CTA: a row's 2^S pair terms x na auxiliary units are each a
+    // chain of FP64 exp / sincos / log / atan2, and a two-qubit group has three warps' worth of rows.  Stage A: one
+    // (row, partner, auxiliary unit) per thread; stage B: one (row, partner); stage C: a thread per row adds in dm_pair_row's order.
+    const int nexp = 1 << S;
+    double* pk = stats + (size_t)rows * SW;                // [rows * nexp * na][4]: Pi terms (re, im), complex sigmoid (re, im)
+    double* wbuf = pk + (size_t)rows * nexp * na * 4;      // [rows * nexp][2]
+    for (int item = threadIdx.x; item < rows * nexp * na; item += blockDim.x) {
+      const int k = item % na, rj = item / na, ri_ = rj >> S, j = rj & mask;
+      const double* fi = feat + (size_t)ri_ * FW;
+      const double* fj = feat + (size_t)(((ri_ >> S) << S) + j) * FW;
+      const double x = 0.5 * (fi[4 + k] + fj[4 + k]);
+      const double y = 0.5 * (fi[4 + na + k] - fj[4 + na + k]);
+      double sn, cs;
+      sincos(y, &sn, &cs);
+      const double ex_ = exp(x);
+      const double zr = 1.0 + ex_ * cs, zi = ex_ * sn;
+      const double mod2 = zr * zr + zi * zi;
+      const double inv = 1.0 / mod2;
+      const double er = ex_ * cs, ei = zi;
+      double* o = pk + (size_t)item * 4;
+      o[0] = 0.5 * log(mod2);
+      o[1] = atan2(zi, zr);
+      o[2] = (er * zr + ei * zi) * inv;
+      o[3] = (ei * zr - er * zi) * inv;
+    }
+    __syncthreads();
+    for (int rj = threadIdx.x; rj < rows * nexp; rj += blockDim.x) {
+      const int ri_ = rj >> S, j = rj & mask;
+      const double* fi = feat + (size_t)ri_ * FW;
+      const double* fj = feat + (size_t)(((ri_ >> S) << S) + j) * FW;
+      const double gp = 0.5 * (fi[0] + fj[0]);
+      const double gm = 0.5 * (fi[1] - fj[1]);
+      double pre = 0.0, pim = 0.0;
+      for (int k = 0; k < na; ++k) { pre += pk[((size_t)rj * na + k) * 4]; pim += pk[((size_t)rj * na + k) * 4 + 1]; }
+      const double ampl = exp(gp + pre), phs = gm + pim;
+      double sn, cs;
+      sincos(phs, &sn, &cs);
+      double wr = fi[2], wi = fi[3];
+      cmul(wr, wi, fj[2], -fj[3]);
+      cmul(wr, wi, ampl * cs, ampl * sn);
+      wbuf[2 * rj] = wr;
+      wbuf[2 * rj + 1] = wi;
+    }
+    __syncthreads();
+    if (r < rows) {
+      double ri = 0.0, si_ = 0.0, R[DM_MAX_NA], I[DM_MAX_NA];
+      for (int k = 0; k < na; ++k) { R[k] = 0.0; I[k] = 0.0; }
+      for (int j = 0; j < nexp; ++j) {
+        const int rj = (r << S) + j;
+        const double wr = wbuf[2 * rj], wi = wbuf[2 * rj + 1];
+        ri += wr;
+        si_ += wi;
+        for (int k = 0; k < na; ++k) {
+          const double Sr = pk[((size_t)rj * na + k) * 4 + 2], Si = pk[((size_t)rj * na + k) * 4 + 3];
+          R[k] += wr * Sr - wi * Si;
+          I[k] += wr * Si + wi * Sr;
+        }
+      }
+      double* out = stats + (size_t)r * SW;
+      out[0] = ri;
+      out[1] = si_;
+      for (int k = 0; k < na; ++k) { out[2 + k] = R[k]; out[2 + na + k] = I[k]; }
+    }
+  } else if (r < rows) {
+    dm_pair_row(feat + (size_t)r * FW, feat + (size_t)((r >> S) << S) * FW, na, S, stats + (size_t)r * SW);
+  }
   __syncthreads();
   if (r < rows) {
     const int b = r >> S;
@@ -841,8 +908,18 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
       ex.samples = samples;
       TinyJob j0{}, j1{};
       make_tiny_jobs(am, ph, ex, wam, auxam, wph, auxph, na, na, -1.0, g_am, g_ph, j0, j1);
-      dm_group_tiny_kernel<<<g_am != nullptr ? 2 : 1, ROWS_THREADS, smem, st>>>(am, ph, si, unitaries, rows, UrhoU, wam, auxam, wph, auxph,
-                                                                             g_am != nullptr ? 1 : 0, body, j0, j1);
+      // room for the pair terms of all rows (stage A / B of the kernel): spread over the CTA when they fit
+      const size_t pair_bytes = (size_t)rows * ((size_t)1 << S) * ((size_t)na * 4 + 2) * sizeof(double);
+      const int pair_parallel = smem + pair_bytes <= DM_TINY_SMEM_MAX ? 1 : 0;
+      static std::atomic<uint64_t> attr_done{0};  // per device: cudaFuncSetAttribute applies to the current device only
+      int dev = 0;
+      QCB_CUDA(cudaGetDevice(&dev));
+      if (!((attr_done.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
+        QCB_CUDA(cudaFuncSetAttribute(dm_group_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_TINY_SMEM_MAX));
+        attr_done.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+      }
+      dm_group_tiny_kernel<<<g_am != nullptr ? 2 : 1, ROWS_THREADS, smem + (pair_parallel ? pair_bytes : 0), st>>>(
+          am, ph, si, unitaries, rows, UrhoU, wam, auxam, wph, auxph, g_am != nullptr ? 1 : 0, body, pair_parallel, j0, j1);
       QCB_LAUNCH_CHECK();
       return QCB_OK;
     }

@@ -18,4 +18,4 @@ for name, make, n_samples in (("complex", lambda: ComplexWaveFunction(2, 2, gpu=
     t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
     print(f"{name}: host {(t1-t0)*100:.2f} ms/epoch, with sync {(t2-t0)*100:.2f}; launches/epoch {(L.qcb_launch_count()-l0)/10}")
     pr = cProfile.Profile(); pr.enable(); nn.fit(data, epochs=10, **kw); torch.cuda.synchronize(); pr.disable()
-    s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18); print(s.getvalue()[:4500])
+    s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30); print(s.getvalue()[:7000])
