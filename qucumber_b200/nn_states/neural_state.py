@@ -87,6 +87,20 @@ def stored_attribute(slot):
     return property(lambda self: getattr(self, slot), lambda self, value: setattr(self, slot, value))
 
 
+def _group_epoch_by_basis(ids, num_groups, batch_size, num_batches):
+    """Rows of an epoch (``ids[i]``: basis group of the i-th row of the shuffled data set; batch t = rows t * batch_size ..)
+    sorted by (batch, group), stable within a group — per batch the order ``np.argsort(ids_of_batch, kind="stable")`` gives, which
+    is what NeuralStateBase.gradient does with one batch. Returns (order, offsets, counts): row ``order[p]`` goes to position
+    p; group g of batch t owns positions offsets[t * num_groups + g] .. offsets[t * num_groups + g + 1]."""
+    ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+    key = (np.arange(ids.shape[0], dtype=np.int64) // batch_size) * num_groups + ids
+    order = np.argsort(key, kind="stable")
+    counts = np.bincount(key, minlength=num_batches * num_groups)
+    offsets = np.zeros(num_batches * num_groups + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return order, offsets, counts
+
+
 class _IndexedRows:
     """Rows ``source[index]`` that have not been gathered yet: fit() hands the batches of a large data set to
     compute_batch_gradients in this form, so that a rank gathers only the rows of its own shard (under torch.distributed
@@ -658,11 +672,7 @@ class NeuralStateBase(abc.ABC):
         gen = self._shuffle_generator
         pos_perm = torch.randperm(n, generator=gen).numpy()
         neg_perm = torch.randint(z_samples.shape[0], size=(num_batches * neg_batch_size,), dtype=torch.long, generator=gen)
-        key = (np.arange(n, dtype=np.int64) // int(pos_batch_size)) * G + ids_all[pos_perm]
-        order = np.argsort(key, kind="stable")
-        counts = np.bincount(key, minlength=num_batches * G)
-        offsets = np.zeros(num_batches * G + 1, dtype=np.int64)
-        np.cumsum(counts, out=offsets[1:])
+        order, offsets, counts = _group_epoch_by_basis(ids_all[pos_perm], G, int(pos_batch_size), int(num_batches))
         # both index vectors go over in ONE asynchronous copy from a pinned staging buffer (a pageable copy would make the host
         # wait for the previous epoch's kernels before it could prepare this one); two buffers alternate, each guarded by an event
         stage = self._index_staging

@@ -478,3 +478,29 @@ def test_mixed_state_fidelity_formula():
     truth = (psi.conj().T @ rho @ psi).real.item()
     assert abs(_mixed_state_fidelity(planes(psi @ psi.conj().T), planes(rho)) - truth) <= 1e-13 * truth
     assert abs(_mixed_state_fidelity(planes(rho), planes(rho)) - 1.0) <= 1e-12
+
+
+@pytest.mark.parametrize("n,groups,batch", [(500, 5, 100), (900, 9, 100), (230, 6, 50), (64, 3, 64), (7, 4, 3), (1, 1, 1)])
+def test_epoch_grouping_matches_per_batch_grouping(n, groups, batch):
+    """fit() over data with bases sorts the whole epoch by (batch, basis) once (qcb_fit_epoch_bases takes the offsets table): per
+    batch that must be the stable grouping NeuralStateBase.gradient applies to a single batch (neural_state.py:326-369), group
+    after group, including empty groups and a short last batch."""
+    from qucumber_b200.nn_states.neural_state import _group_epoch_by_basis
+
+    rng = np.random.default_rng(n + groups)
+    ids = rng.integers(0, groups, size=n)
+    if n > 10:
+        ids[ids == groups - 1] = 0  # one basis never measured: an empty group in every batch
+    nb = -(-n // batch)
+    order, offsets, counts = _group_epoch_by_basis(ids, groups, batch, nb)
+    assert sorted(order.tolist()) == list(range(n))
+    assert offsets[0] == 0 and offsets[-1] == n and np.all(np.diff(offsets) == counts)
+    for t in range(nb):
+        rows = np.arange(t * batch, min((t + 1) * batch, n))
+        want = rows[np.argsort(ids[rows], kind="stable")]
+        first, last = offsets[t * groups], offsets[(t + 1) * groups]
+        assert np.array_equal(order[first:last], want)
+        assert np.array_equal(counts[t * groups:(t + 1) * groups], np.bincount(ids[rows], minlength=groups))
+        for g in range(groups):
+            seg = order[offsets[t * groups + g]:offsets[t * groups + g + 1]]
+            assert np.all(ids[seg] == g) and np.all(np.diff(seg) > 0)
