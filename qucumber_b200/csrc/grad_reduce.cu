@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_kernel(AffineSp
 // of ONE launch (each what grad_reduce_tiny_kernel<ROWS_EXPANDED> does for its RBM).
 __global__ void __launch_bounds__(ROWS_THREADS) grad_reduce_tiny_pair_kernel(TinyJob j0, TinyJob j1, int rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
-  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
+  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;
+  grad_reduce_tiny_body<ROWS_EXPANDED>(job.s, job.src, rows, job.direct, smem_raw);
 }
 
 

@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedPar
     else w_ph[r] = -((t.y * dr - t.x * di) * inv);                // -Im(T / D)
   }
   __syncthreads();
-  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
-  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
+  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
+  grad_reduce_tiny_body<ROWS_EXPANDED>(job.s, job.src, rows, job.direct, smem_raw);
 }
 
 static void make_tiny_jobs(const StackedParams& am, const StackedParams& ph, const Expansion& ex, const double* w_am, const double* aux_am,
@@ -831,8 +831,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedPara
   }
   if (!want_grad) return;
   __syncthreads();
-  if (blockIdx.x == 0) grad_reduce_tiny_body<ROWS_EXPANDED>(j0.s, j0.src, rows, j0.direct, smem_raw);
-  else grad_reduce_tiny_body<ROWS_EXPANDED>(j1.s, j1.src, rows, j1.direct, smem_raw);
+  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
+  grad_reduce_tiny_body<ROWS_EXPANDED>(job.s, job.src, rows, job.direct, smem_raw);
 }
 
 // both of the above in one launch for few rotated sites (every row thread re-adds its sample's 2^S terms in the same order:
