@@ -703,11 +703,10 @@ class NeuralStateBase(abc.ABC):
         vk = torch.empty(max(C, 1) * N, dtype=torch.double, device=dev)
         if self._cd_sweep + num_batches * int(k) >= (1 << 31):
             self._cd_seed, self._cd_sweep = next_seed(), 0
-        if na:
-            ptrs = [_lib.ptr(t.data) for r in (am, ph) for t in (r.weights_W, r.weights_U, r.visible_bias, r.hidden_bias, r.aux_bias)]
-        else:
-            ptrs = [_lib.ptr(t.data) if t is not None else None
-                    for r in (am, ph) for t in (r.weights, None, r.visible_bias, r.hidden_bias, None)]
+        # parameters straight from the modules' dictionaries (nn.Module.__getattr__ is the slow path, and this runs every epoch)
+        names_p = ("weights_W", "weights_U", "visible_bias", "hidden_bias", "aux_bias") if na else ("weights", None, "visible_bias",
+                                                                                                   "hidden_bias", None)
+        ptrs = [r._parameters[name].data_ptr() if name is not None else None for r in (am, ph) for name in names_p]
         _lib.check(lib.qcb_fit_epoch_bases(*ptrs, N, am.num_hidden, na, _lib.ptr(pos), offsets.ctypes.data, codes.ctypes.data, G,
                                            int(num_batches), _lib.ptr(table), len(names), _lib.ptr(neg), C, int(k), float(lr),
                                            self._cd_seed, self._cd_sweep, _lib.ptr(scratch), _lib.ptr(g), _lib.ptr(vk), _lib.ptr(ws),
