@@ -319,15 +319,21 @@ int qcb_dm_rotated_groups(const double* W_am, const double* U_am, const double* 
  * sweeps from rows t * neg_batch_size .. of `neg` with Philox key `seed`, chains 0 .. neg_batch_size - 1 and sweeps
  * sweep0 + t * k .., g_am -= (1 / neg_batch_size) * sum grad E(v_k) (as qcb_rbm_cdk_neg), then p <- p - lr * g on the ten
  * (six) parameter tensors IN PLACE; lr == 0 leaves them untouched.  On return g holds the last batch's gradient.  Each RBM's
- * part of g is ordered [W ; U ; b ; c ; d].  scratch: 2 x (largest group) doubles; vk: neg_batch_size * N doubles;
+ * part of g is ordered [W ; U ; b ; c ; d].  scratch: 2 x (rows of the largest batch) doubles; vk: neg_batch_size * N doubles;
  * workspace: max of qcb_workspace_bytes(QCB_OP_CWF_ROTATED / QCB_OP_DM_ROTATED, largest group) and (QCB_OP_CDK_NEG,
- * neg_batch_size). */
+ * neg_batch_size).
+ * desc_host (PINNED host memory) / desc_dev (device memory), desc_bytes >= qcb_fit_epoch_desc_bytes(ngroups, nbatches) each,
+ * or NULL: with them, a batch all of whose basis groups are small (at most 256 expanded rows each, layers of at most 16 units)
+ * takes ONE launch for its positive phase — the call writes one descriptor per group into desc_host, copies them to desc_dev
+ * on `stream`, and every group's CTA pair writes a partial gradient that is added in group order (the sums of the
+ * group-by-group path, bit for bit).  desc_host must stay untouched until the work queued by the call has run. */
 int qcb_fit_epoch_bases(double* W_am, double* U_am, double* b_am, double* c_am, double* d_am,
                         double* W_ph, double* U_ph, double* b_ph, double* c_ph, double* d_ph, int N, int nh, int na,
                         const double* pos, const int64_t* offsets, const uint8_t* bases, int ngroups, int nbatches,
                         const double* unitaries, int K, const double* neg, int64_t neg_batch_size, int k, double lr,
                         uint64_t seed, uint64_t sweep0, double* scratch, double* g, double* vk,
-                        void* ws, size_t ws_bytes, void* stream);
+                        void* ws, size_t ws_bytes, void* desc_host, void* desc_dev, size_t desc_bytes, void* stream);
+size_t qcb_fit_epoch_desc_bytes(int ngroups, int nbatches);
 
 /* ---- Full-space rotated metrics --------------------------------------------------------
  * qcb_kron_rotate: x <- (U_0 (x) U_1 (x) ... (x) U_{n-1}) x on the leading index of a planar complex array

@@ -54,7 +54,8 @@ SIGNATURES = {
     "qcb_dm_rotated_groups": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P,
                                       _P, _P, c_size_t, _P]),
     "qcb_fit_epoch_bases": (c_int, [_P] * 10 + [c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_int, _P, c_int64, c_int, c_double,
-                                               c_uint64, c_uint64, _P, _P, _P, _P, c_size_t, _P]),
+                                               c_uint64, c_uint64, _P, _P, _P, _P, c_size_t, _P, _P, c_size_t, _P]),
+    "qcb_fit_epoch_desc_bytes": (c_size_t, [c_int, c_int]),
     "qcb_cwf_rotated": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, c_int, _P, _P, _P, _P,
                                 c_size_t, _P]),
     "qcb_dm_rotated": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P, _P, c_int,

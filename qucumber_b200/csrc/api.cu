@@ -3,6 +3,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace qcb {
 
@@ -131,6 +132,24 @@ struct FitEpochSegs {  // the parameter tensors of both RBMs and where their gra
   int count;
 };
 
+size_t rotated_tiny_group_bytes();
+size_t rotated_batch_tiny_scratch_bytes(int ngroups, long long n_all, int na);
+int prepare_rotated_batch_tiny(bool density, const StackedParams& am, const StackedParams& ph, const double* pos, const int64_t* off,
+                               const uint8_t* bases, int ngroups, int K, double* out, double* gpart, long long n_all, void* scratch,
+                               void* host_slots, int* n_used, size_t* smem_out);
+int launch_rotated_batch_tiny(bool density, const StackedParams& am, const StackedParams& ph, const double* unitaries, const void* dev_slots,
+                              int n_used, size_t smem, cudaStream_t st);
+
+// g <- scale * (p_0 + p_1 + ... ) over the per-group partial gradients of a batch, added in group order (what accumulating group
+// after group into a cleared g and scaling it gives)
+__global__ void fit_epoch_sum_kernel(double* __restrict__ g, const double* __restrict__ gpart, int nparts, long long n, double scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int u = 0; u < nparts; ++u) acc += gpart[(size_t)u * n + i];
+    g[i] = acc * scale;
+  }
+}
+
 __global__ void fit_epoch_scale_kernel(double* __restrict__ g, long long n, double scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] *= scale;
 }
@@ -149,7 +168,7 @@ __global__ void fit_epoch_sgd_kernel(FitEpochSegs segs, const double* __restrict
 int run_fit_epoch_bases(const StackedParams& am, const StackedParams& ph, const FitEpochSegs& segs, bool density, const double* pos,
                         const int64_t* offsets, const uint8_t* bases, int ngroups, int nbatches, const double* unitaries, int K,
                         const double* neg, int64_t C, int k, double lr, uint64_t seed, uint64_t sweep0, double* scratch, double* g,
-                        double* vk, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        double* vk, void* ws, size_t ws_bytes, void* desc_host, void* desc_dev, size_t desc_bytes, cudaStream_t st) {
   const int N = am.N, nhid = am.nhid();
   const long long n_am = segs.first[segs.count / 2], n_all = segs.first[segs.count];
   double* g_am = g;
@@ -157,9 +176,41 @@ int run_fit_epoch_bases(const StackedParams& am, const StackedParams& ph, const 
   const size_t gb = gibbs_workspace_bytes_rows(N, nhid, C);
   if (C > 0 && ws_bytes < gb + grad_reduce_workspace_bytes(N, nhid, C)) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: workspace too small");
   const int blocks = (int)((n_all + 255) / 256 < 148 ? (n_all + 255) / 256 : 148);
+  // One launch per batch for the positive phase where every basis group of the batch is small (descriptors for the whole epoch
+  // are written into the caller's pinned buffer now and cross in one copy); its device scratch sits at the END of the workspace,
+  // past what the sweeps and the negative-phase reduction use.
+  std::vector<int> used(nbatches > 0 ? nbatches : 0, 0);
+  std::vector<size_t> smem_of(nbatches > 0 ? nbatches : 0, 0);
+  const size_t slot = rotated_tiny_group_bytes();
+  const size_t carve = rotated_batch_tiny_scratch_bytes(ngroups, n_all, density ? am.na : 0);
+  char* carve_base = nullptr;
+  if (desc_host != nullptr && desc_dev != nullptr && nbatches > 0 && desc_bytes >= (size_t)nbatches * ngroups * slot &&
+      ws_bytes >= carve + 256 + (C > 0 ? gb + grad_reduce_workspace_bytes(N, nhid, C) : 0)) {
+    carve_base = static_cast<char*>(ws) + ((ws_bytes - carve) / 256) * 256;
+    double* gpart = reinterpret_cast<double*>(carve_base);
+    void* wscratch = carve_base + align_up((size_t)ngroups * n_all * sizeof(double), 256);
+    bool any = false;
+    for (int b = 0; b < nbatches; ++b) {
+      const int64_t* off = offsets + (size_t)b * ngroups;
+      int rc = prepare_rotated_batch_tiny(density, am, ph, pos, off, bases, ngroups, K, scratch, gpart, n_all, wscratch,
+                                          static_cast<char*>(desc_host) + (size_t)b * ngroups * slot, &used[b], &smem_of[b]);
+      if (rc != QCB_OK) return rc;
+      any = any || used[b] > 0;
+    }
+    if (any) QCB_CUDA(cudaMemcpyAsync(desc_dev, desc_host, (size_t)nbatches * ngroups * slot, cudaMemcpyHostToDevice, st));
+  }
   for (int b = 0; b < nbatches; ++b) {
     const int64_t* off = offsets + (size_t)b * ngroups;
     const int64_t B = off[ngroups] - off[0];
+    if (used[b] > 0) {
+      double* gpart = reinterpret_cast<double*>(carve_base);
+      QCB_CUDA(cudaMemsetAsync(gpart, 0, (size_t)used[b] * n_all * sizeof(double), st));
+      int rc = launch_rotated_batch_tiny(density, am, ph, unitaries, static_cast<char*>(desc_dev) + (size_t)b * ngroups * slot, used[b],
+                                         smem_of[b], st);
+      if (rc != QCB_OK) return rc;
+      fit_epoch_sum_kernel<<<blocks, 256, 0, st>>>(g, gpart, used[b], n_all, 1.0 / (double)B);
+      QCB_LAUNCH_CHECK();
+    } else {
     QCB_CUDA(cudaMemsetAsync(g, 0, (size_t)n_all * sizeof(double), st));
     for (int gi = 0; gi < ngroups; ++gi) {
       const int64_t first = off[gi], rows = off[gi + 1] - first;
@@ -177,6 +228,7 @@ int run_fit_epoch_bases(const StackedParams& am, const StackedParams& ph, const 
     if (B > 0) {
       fit_epoch_scale_kernel<<<blocks, 256, 0, st>>>(g, n_all, 1.0 / (double)B);
       QCB_LAUNCH_CHECK();
+    }
     }
     if (C > 0) {
       int rc = run_gibbs(am, neg + (size_t)b * C * N, vk, C, k, seed, 0, sweep0 + (uint64_t)b * (uint64_t)k, nullptr, ws, gb, st);
@@ -589,7 +641,7 @@ int qcb_fit_epoch_bases(double* W_am, double* U_am, double* b_am, double* c_am, 
                         double* c_ph, double* d_ph, int N, int nh, int na, const double* pos, const int64_t* offsets,
                         const uint8_t* bases, int ngroups, int nbatches, const double* unitaries, int K, const double* neg,
                         int64_t neg_batch_size, int k, double lr, uint64_t seed, uint64_t sweep0, double* scratch, double* g,
-                        double* vk, void* ws, size_t ws_bytes, void* stream) {
+                        double* vk, void* ws, size_t ws_bytes, void* desc_host, void* desc_dev, size_t desc_bytes, void* stream) {
   StreamDeviceGuard device_guard(stream, W_am);
   StackedParams am, ph;
   if (na < 0) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: na must be >= 0");
@@ -618,7 +670,12 @@ int qcb_fit_epoch_bases(double* W_am, double* U_am, double* b_am, double* c_am, 
   segs.first[n] = at;
   segs.count = n;
   return run_fit_epoch_bases(am, ph, segs, na > 0, pos, offsets, bases, ngroups, nbatches, unitaries, K, neg, neg_batch_size, k, lr, seed,
-                             sweep0, scratch, g, vk, ws, ws_bytes, (cudaStream_t)stream);
+                             sweep0, scratch, g, vk, ws, ws_bytes, desc_host, desc_dev, desc_bytes, (cudaStream_t)stream);
+}
+
+size_t qcb_fit_epoch_desc_bytes(int ngroups, int nbatches) {
+  if (ngroups < 1 || nbatches < 1) return 0;
+  return (size_t)ngroups * (size_t)nbatches * rotated_tiny_group_bytes();
 }
 
 // ---- compact states -------------------------------------------------------------------------------

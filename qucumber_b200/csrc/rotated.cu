@@ -284,12 +284,11 @@ __global__ void cwf_sum_kernel(const double2* __restrict__ T, int S, int64_t b0,
 constexpr int TINY_MAX_ROWS = ROWS_THREADS;
 constexpr size_t DM_TINY_SMEM_MAX = 96 * 1024;
 
-__global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
-                                                                     int rows, int64_t Btotal, double* __restrict__ Upsi, double* w_am,
-                                                                     double* w_ph, TinyJob j0, TinyJob j1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void cwf_group_tiny_body(const StackedParams& am, const StackedParams& ph, const SiteInfo& si, const double* __restrict__ U,
+                                                    int rows, int64_t Btotal, double* __restrict__ Upsi, double* w_am, double* w_ph,
+                                                    const TinyJob& job, int cta, unsigned char* smem_raw) {
   __shared__ double2 Tsm[TINY_MAX_ROWS];
-  const Expansion& ex = j0.src.ex;
+  const Expansion& ex = job.src.ex;
   const int N = am.N, nh = am.nh, S = si.S;
   const int r = threadIdx.x;
   const int mask = (1 << S) - 1;
@@ -327,19 +326,63 @@ __global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedPar
     const int b = r >> S;
     double dr = 0.0, di = 0.0;
     for (int i = 0; i <= mask; ++i) { dr += Tsm[(b << S) + i].x; di += Tsm[(b << S) + i].y; }
-    if (blockIdx.x == 0 && (r & mask) == 0) {
+    if (cta == 0 && (r & mask) == 0) {
       Upsi[b] = dr;
       Upsi[Btotal + b] = di;
     }
     const double2 t = Tsm[r];
     const double inv = 1.0 / (dr * dr + di * di);
-    if (blockIdx.x == 0) w_am[r] = (t.x * dr + t.y * di) * inv;   // Re(T / D)
+    if (cta == 0) w_am[r] = (t.x * dr + t.y * di) * inv;   // Re(T / D)
     else w_ph[r] = -((t.y * dr - t.x * di) * inv);                // -Im(T / D)
   }
   __syncthreads();
-  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
   grad_reduce_tiny_body<ROWS_EXPANDED>(job.s, job.src, rows, job.direct, smem_raw);
 }
+
+__global__ void __launch_bounds__(ROWS_THREADS) cwf_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
+                                                                     int rows, int64_t Btotal, double* __restrict__ Upsi, double* w_am,
+                                                                     double* w_ph, TinyJob j0, TinyJob j1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
+  cwf_group_tiny_body(am, ph, si, U, rows, Btotal, Upsi, w_am, w_ph, job, (int)blockIdx.x, smem_raw);
+}
+
+// ---- all basis groups of a BATCH in one launch: CTA pair g serves the g-th non-empty group (descriptors in global memory,
+// written by the host for the whole epoch and copied over once); an all-Z group is the plain positive-phase reduction of the
+// amplitude RBM (its second CTA has nothing to do).  Every pair writes its group's gradient to its own partial vector; the
+// caller adds the partials in group order (fit_epoch_sum_kernel in api.cu): the sums of the group-by-group path, bit for bit.
+struct alignas(16) TinyGroup {
+  SiteInfo si;
+  int rows, kind, pair_parallel, want_grad;   // kind 0: rotated group, 1: all-Z group
+  unsigned long long body_bytes;
+  long long Btotal;
+  double* out;        // Upsi (2 x samples of the group) / UrhoU (samples of the group)
+  double* w[2];
+  double* aux[2];
+  TinyJob job[2];
+};
+
+__device__ __forceinline__ const TinyGroup* load_tiny_group(const TinyGroup* __restrict__ groups, unsigned char* slot) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(groups + (blockIdx.x >> 1));
+  uint32_t* dst = reinterpret_cast<uint32_t*>(slot);
+  for (int i = threadIdx.x; i < (int)(sizeof(TinyGroup) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return reinterpret_cast<const TinyGroup*>(slot);
+}
+
+__global__ void __launch_bounds__(ROWS_THREADS) cwf_batch_tiny_kernel(StackedParams am, StackedParams ph, const double* __restrict__ U,
+                                                                     const TinyGroup* __restrict__ groups) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) unsigned char slot[sizeof(TinyGroup)];
+  const TinyGroup& grp = *load_tiny_group(groups, slot);
+  const int cta = blockIdx.x & 1;
+  if (grp.kind == 1) {
+    if (cta == 0) grad_reduce_tiny_body<ROWS_EXPLICIT>(grp.job[0].s, grp.job[0].src, grp.rows, grp.job[0].direct, smem_raw);
+    return;
+  }
+  cwf_group_tiny_body(am, ph, grp.si, U, grp.rows, grp.Btotal, grp.out, grp.w[0], grp.w[1], grp.job[cta], cta, smem_raw);
+}
+
 
 static void make_tiny_jobs(const StackedParams& am, const StackedParams& ph, const Expansion& ex, const double* w_am, const double* aux_am,
                            const double* w_ph, const double* aux_ph, int n_aux, int zero_tail_ph, double scale, double* g_am, double* g_ph,
@@ -696,12 +739,11 @@ __global__ void dm_weights_kernel(const double* __restrict__ stats, const double
 }
 
 // DensityMatrix: features, pair sums, probabilities, row weights and (want_grad) the two reductions
-__global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
-                                                                    int rows, double* __restrict__ UrhoU, double* w_am, double* aux_am,
-                                                                    double* w_ph, double* aux_ph, int want_grad, size_t body_bytes,
-                                                                    int pair_parallel, TinyJob j0, TinyJob j1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Expansion& ex = j0.src.ex;
+__device__ __forceinline__ void dm_group_tiny_body(const StackedParams& am, const StackedParams& ph, const SiteInfo& si, const double* __restrict__ U,
+                                                   int rows, double* __restrict__ UrhoU, double* w_am, double* aux_am, double* w_ph,
+                                                   double* aux_ph, int want_grad, size_t body_bytes, int pair_parallel, const TinyJob& job,
+                                                   int cta, unsigned char* smem_raw) {
+  const Expansion& ex = job.src.ex;
   const int N = am.N, nh = am.nh, na = am.na, S = si.S;
   const int FW = 4 + 2 * na, SW = 2 + 2 * na;
   double* feat = reinterpret_cast<double*>(smem_raw + body_bytes);  // [rows][FW]
@@ -816,11 +858,11 @@ __global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedPara
     const int b = r >> S;
     double p = 0.0;
     for (int i = 0; i <= mask; ++i) p += stats[(size_t)((b << S) + i) * SW];
-    if (blockIdx.x == 0 && (r & mask) == 0) UrhoU[b] = p;
+    if (cta == 0 && (r & mask) == 0) UrhoU[b] = p;
     if (want_grad) {
       const double f = -1.0 / (p + 1e-8);  // nn_states/density_matrix.py:296,300
       const double* st = stats + (size_t)r * SW;
-      if (blockIdx.x == 0) {
+      if (cta == 0) {
         w_am[r] = f * st[0];
         for (int k = 0; k < na; ++k) aux_am[(size_t)r * na + k] = f * st[2 + k];
       } else {
@@ -831,9 +873,32 @@ __global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedPara
   }
   if (!want_grad) return;
   __syncthreads();
-  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
   grad_reduce_tiny_body<ROWS_EXPANDED>(job.s, job.src, rows, job.direct, smem_raw);
 }
+
+__global__ void __launch_bounds__(ROWS_THREADS) dm_group_tiny_kernel(StackedParams am, StackedParams ph, SiteInfo si, const double* __restrict__ U,
+                                                                    int rows, double* __restrict__ UrhoU, double* w_am, double* aux_am,
+                                                                    double* w_ph, double* aux_ph, int want_grad, size_t body_bytes,
+                                                                    int pair_parallel, TinyJob j0, TinyJob j1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TinyJob& job = blockIdx.x == 0 ? j0 : j1;  // one inlined copy of the body: these kernels' time is instruction fetch
+  dm_group_tiny_body(am, ph, si, U, rows, UrhoU, w_am, aux_am, w_ph, aux_ph, want_grad, body_bytes, pair_parallel, job, (int)blockIdx.x, smem_raw);
+}
+
+__global__ void __launch_bounds__(ROWS_THREADS) dm_batch_tiny_kernel(StackedParams am, StackedParams ph, const double* __restrict__ U,
+                                                                    const TinyGroup* __restrict__ groups) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) unsigned char slot[sizeof(TinyGroup)];
+  const TinyGroup& grp = *load_tiny_group(groups, slot);
+  const int cta = blockIdx.x & 1;
+  if (grp.kind == 1) {
+    if (cta == 0) grad_reduce_tiny_body<ROWS_EXPLICIT>(grp.job[0].s, grp.job[0].src, grp.rows, grp.job[0].direct, smem_raw);
+    return;
+  }
+  dm_group_tiny_body(am, ph, grp.si, U, grp.rows, grp.out, grp.w[0], grp.aux[0], grp.w[1], grp.aux[1], 1, (size_t)grp.body_bytes,
+                     grp.pair_parallel, grp.job[cta], cta, smem_raw);
+}
+
 
 // both of the above in one launch for few rotated sites (every row thread re-adds its sample's 2^S terms in the same order:
 // same P_b, same weights; one launch less per basis group of a two-qubit training batch)
@@ -949,6 +1014,123 @@ int run_dm_rotated(const StackedParams& am, const StackedParams& ph, const doubl
     rc = run_grad_reduce_expanded_pair(am, ph, ex, rows, wam, auxam, wph, auxph, na, na, -1.0, g_am, g_ph, gws, gws_bytes, st);
     if (rc != QCB_OK) return rc;
   }
+  return QCB_OK;
+}
+
+// ---- host side of the one-launch-per-batch path (used by qcb_fit_epoch_bases) ----------------------------------------------
+size_t rotated_tiny_group_bytes() { return sizeof(TinyGroup); }
+
+// Device memory one batch needs beside the descriptors: the groups' partial gradients and their row weights / aux features.
+size_t rotated_batch_tiny_scratch_bytes(int ngroups, long long n_all, int na) {
+  return align_up((size_t)ngroups * n_all * sizeof(double), 256) +
+         align_up((size_t)ngroups * TINY_MAX_ROWS * (2 + 2 * (size_t)na) * sizeof(double), 256);
+}
+
+// Fills `host` (ngroups slots) with the descriptors of one batch if EVERY non-empty group qualifies for the small-group kernels;
+// *n_used = number of descriptors written (0: the batch takes the group-by-group path), *smem = dynamic shared memory of the launch.
+// Group u writes its gradient to gpart + u * n_all ([g_am ; g_ph] layout; the caller clears gpart first: an all-Z group leaves the
+// phase part alone).  out: 2 doubles per sample of the batch (cwf) / 1 (dm); scratch: rotated_batch_tiny_scratch_bytes() minus gpart.
+int prepare_rotated_batch_tiny(bool density, const StackedParams& am, const StackedParams& ph, const double* pos, const int64_t* off,
+                               const uint8_t* bases, int ngroups, int K, double* out, double* gpart, long long n_all, void* scratch,
+                               void* host_slots, int* n_used, size_t* smem_out) {
+  *n_used = 0;
+  *smem_out = 0;
+  if (!g_rotated_tiny) return QCB_OK;
+  const int N = am.N, nh = am.nh, na = density ? am.na : 0;
+  const int H = nh + na;
+  if (N > 16 || H > 16 || na > DM_MAX_NA) return QCB_OK;
+  const long long n_am = (long long)H * N + N + H;
+  const int G = (int)n_am;
+  TinyGroup* slots = static_cast<TinyGroup*>(host_slots);
+  const size_t cap = (size_t)ngroups * TINY_MAX_ROWS;
+  double* w_am = static_cast<double*>(scratch);
+  double* w_ph = w_am + cap;
+  double* aux_am = w_ph + cap;
+  double* aux_ph = aux_am + cap * na;
+  const int FW = 4 + 2 * na, SW = 2 + 2 * na;
+  size_t smem = 0, row_at = 0;
+  int u = 0;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int64_t first = off[gi], B = off[gi + 1] - first;
+    if (B < 0) return fail(QCB_ERR_BAD_ARG, "fit_epoch_bases: offsets must not decrease");
+    if (B == 0) continue;
+    const uint8_t* basis = bases + (size_t)gi * N;
+    TinyGroup grp{};
+    bool plain = true;
+    for (int j = 0; j < N; ++j) plain = plain && basis[j] == 0;
+    size_t need;
+    if (plain) {
+      if (B > TINY_MAX_ROWS) return QCB_OK;
+      need = grad_reduce_tiny_smem(N, H, H, B);
+      if (need > 40 * 1024) return QCB_OK;
+      grp.kind = 1;
+      grp.rows = (int)B;
+      grp.job[0].s = stacked_hidden_spec(am);
+      grp.job[0].src.v = pos + first * N;
+      grp.job[0].direct = GradDirect{gpart + (size_t)u * n_all, 1.0, 0, G};
+    } else {
+      SiteInfo si{};
+      Expansion ex{};
+      int rc = make_sites(basis, N, K, si, ex);
+      if (rc != QCB_OK) return rc;
+      const int S = si.S;
+      if (S > 8 || (B << S) > TINY_MAX_ROWS) return QCB_OK;
+      const int rows = (int)(B << S);
+      ex.samples = pos + first * N;
+      grp.kind = 0;
+      grp.si = si;
+      grp.rows = rows;
+      grp.want_grad = 1;
+      grp.Btotal = B;
+      grp.w[0] = w_am + row_at;
+      grp.w[1] = w_ph + row_at;
+      double* gu = gpart + (size_t)u * n_all;
+      if (!density) {
+        need = grad_reduce_tiny_smem(N, nh, nh, rows);
+        if (need > 40 * 1024) return QCB_OK;
+        grp.out = out + 2 * (first - off[0]);
+        make_tiny_jobs(am, ph, ex, grp.w[0], nullptr, grp.w[1], nullptr, 0, 0, 1.0, gu, gu + n_am, grp.job[0], grp.job[1]);
+      } else {
+        const size_t body = align_up(grad_reduce_tiny_smem(N, nh, H, rows), 16);
+        need = body + (size_t)rows * (FW + SW) * sizeof(double);
+        if (need > 44 * 1024) return QCB_OK;
+        const size_t pair_bytes = (size_t)rows * ((size_t)1 << S) * ((size_t)na * 4 + 2) * sizeof(double);
+        grp.pair_parallel = need + pair_bytes <= DM_TINY_SMEM_MAX ? 1 : 0;
+        if (grp.pair_parallel) need += pair_bytes;
+        grp.body_bytes = body;
+        grp.out = out + (first - off[0]);
+        grp.aux[0] = aux_am + row_at * na;
+        grp.aux[1] = aux_ph + row_at * na;
+        make_tiny_jobs(am, ph, ex, grp.w[0], grp.aux[0], grp.w[1], grp.aux[1], na, na, -1.0, gu, gu + n_am, grp.job[0], grp.job[1]);
+      }
+      grp.job[0].direct.accumulate = 0;
+      grp.job[1].direct.accumulate = 0;
+      row_at += (size_t)rows;
+    }
+    smem = need > smem ? need : smem;
+    slots[u++] = grp;
+  }
+  *n_used = u;
+  *smem_out = smem;
+  return QCB_OK;
+}
+
+int launch_rotated_batch_tiny(bool density, const StackedParams& am, const StackedParams& ph, const double* unitaries, const void* dev_slots,
+                              int n_used, size_t smem, cudaStream_t st) {
+  const TinyGroup* groups = static_cast<const TinyGroup*>(dev_slots);
+  if (density) {
+    static std::atomic<uint64_t> attr_done{0};  // per device: cudaFuncSetAttribute applies to the current device only
+    int dev = 0;
+    QCB_CUDA(cudaGetDevice(&dev));
+    if (!((attr_done.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
+      QCB_CUDA(cudaFuncSetAttribute(dm_batch_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_TINY_SMEM_MAX));
+      attr_done.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+    }
+    dm_batch_tiny_kernel<<<2 * n_used, ROWS_THREADS, smem, st>>>(am, ph, unitaries, groups);
+  } else {
+    cwf_batch_tiny_kernel<<<2 * n_used, ROWS_THREADS, smem, st>>>(am, ph, unitaries, groups);
+  }
+  QCB_LAUNCH_CHECK();
   return QCB_OK;
 }
 

@@ -617,7 +617,8 @@ class NeuralStateBase(abc.ABC):
     _train_bits = None         # set by fit(): the packed copy of a large binary data set (see _cd_gradients_packed)
     _basis_groups = None       # set by fit(): (unique bases, group id of every sample) of the data set
     _basis_codes = None        # set by fit(): (codes of the unique bases, names of the unitaries they index)
-    _index_staging = None      # set by _fit_epoch_bases(): two pinned index buffers with the events of their last copies
+    _index_staging = None      # set by _fit_epoch_bases(): two pinned staging slots (indices, event of the last use, descriptors)
+    _desc_dev = None           # set by _fit_epoch_bases(): device copy of the per-group descriptors
     #: set to False to keep fit() on float64 rows whatever the data
     pack_training_data = True
     # data without bases is shuffled on the device: the permutation, the gathers and the epoch's kernels are then all queued
@@ -675,19 +676,21 @@ class NeuralStateBase(abc.ABC):
         order, offsets, counts = _group_epoch_by_basis(ids_all[pos_perm], G, int(pos_batch_size), int(num_batches))
         # both index vectors go over in ONE asynchronous copy from a pinned staging buffer (a pageable copy would make the host
         # wait for the previous epoch's kernels before it could prepare this one); two buffers alternate, each guarded by an event
+        # (the same pair of staging slots carries the per-group descriptors qcb_fit_epoch_bases writes for its one-launch batches)
         stage = self._index_staging
-        if stage is None or stage[0][0].numel() < n + neg_perm.numel():
-            stage = self._index_staging = [[torch.empty(n + neg_perm.numel(), dtype=torch.long).pin_memory(), None] for _ in range(2)]
+        desc_bytes = int(lib.qcb_fit_epoch_desc_bytes(G, int(num_batches)))
+        if stage is None or stage[0][0].numel() < n + neg_perm.numel() or stage[0][2].numel() < desc_bytes:
+            stage = self._index_staging = [[torch.empty(n + neg_perm.numel(), dtype=torch.long).pin_memory(), None,
+                                            torch.empty(max(desc_bytes, 16), dtype=torch.uint8).pin_memory()] for _ in range(2)]
+            self._desc_dev = torch.empty(max(desc_bytes, 16), dtype=torch.uint8, device=dev)
         stage.reverse()
-        buf, busy = stage[0]
+        buf, busy, desc_host = stage[0]
         if busy is not None:
             busy.synchronize()
         host = buf[:n + neg_perm.numel()]
         host[:n] = torch.from_numpy(pos_perm[order])
         host[n:] = neg_perm
         index = host.to(dev, non_blocking=True)
-        stage[0][1] = torch.cuda.Event()
-        stage[0][1].record(torch.cuda.current_stream(dev))
         pos = train_samples.index_select(0, index[:n])
         neg = z_samples.index_select(0, index[n:])
         codes, names = self._basis_codes
@@ -698,7 +701,7 @@ class NeuralStateBase(abc.ABC):
         op = _lib.OP_DM_ROTATED if na else _lib.OP_CWF_ROTATED
         ws = _lib.workspace(dev, max(lib.qcb_workspace_bytes(op, N, am.num_hidden, na, bmax),
                                      lib.qcb_workspace_bytes(_lib.OP_CDK_NEG, N, am.num_hidden, na, C), 256))
-        scratch = torch.empty(2 * max(bmax, 1), dtype=torch.double, device=dev)
+        scratch = torch.empty(2 * max(int(pos_batch_size), 1), dtype=torch.double, device=dev)
         g = torch.empty(am.num_pars + ph.num_pars, dtype=torch.double, device=dev)
         vk = torch.empty(max(C, 1) * N, dtype=torch.double, device=dev)
         if self._cd_sweep + num_batches * int(k) >= (1 << 31):
@@ -710,7 +713,10 @@ class NeuralStateBase(abc.ABC):
         _lib.check(lib.qcb_fit_epoch_bases(*ptrs, N, am.num_hidden, na, _lib.ptr(pos), offsets.ctypes.data, codes.ctypes.data, G,
                                            int(num_batches), _lib.ptr(table), len(names), _lib.ptr(neg), C, int(k), float(lr),
                                            self._cd_seed, self._cd_sweep, _lib.ptr(scratch), _lib.ptr(g), _lib.ptr(vk), _lib.ptr(ws),
-                                           ws.numel(), _lib.stream_ptr(dev)), "qcb_fit_epoch_bases")
+                                           ws.numel(), desc_host.data_ptr(), self._desc_dev.data_ptr(), desc_bytes,
+                                           _lib.stream_ptr(dev)), "qcb_fit_epoch_bases")
+        stage[0][1] = torch.cuda.Event()   # this slot's index vector and descriptors have crossed once this has happened
+        stage[0][1].record(torch.cuda.current_stream(dev))
         self._cd_sweep += num_batches * int(k)
         if want_grads:
             vector_to_grads(g[:am.num_pars], am.parameters())
@@ -900,4 +906,5 @@ class NeuralStateBase(abc.ABC):
         self._basis_groups = None
         self._basis_codes = None
         self._index_staging = None
+        self._desc_dev = None
         cbs.fire("on_train_end", self)
