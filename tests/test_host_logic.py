@@ -504,3 +504,41 @@ def test_epoch_grouping_matches_per_batch_grouping(n, groups, batch):
         for g in range(groups):
             seg = order[offsets[t * groups + g]:offsets[t * groups + g + 1]]
             assert np.all(ids[seg] == g) and np.all(np.diff(seg) > 0)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/qcb.h against the ctypes table of qucumber_b200/_lib.py: same number of parameters, and each
+    parameter's C type maps to the ctypes type listed for it (pointers -> c_void_p, int -> c_int, int64_t -> c_int64, uint64_t ->
+    c_uint64, size_t -> c_size_t, double -> c_double) — an argument added on one side only would shift every later one."""
+    import ctypes
+
+    from qucumber_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "qcb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", "", header)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(qcb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+
+    def ctype_of(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return ctypes.c_void_p
+        words = [w for w in re.split(r"\s+", decl) if w not in ("const", "unsigned", "long")]
+        base = decl if decl.startswith("unsigned long long") else words[0]
+        table = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t,
+                 "double": ctypes.c_double, "unsigned long long": ctypes.c_uint64}
+        for key, val in table.items():
+            if base.startswith(key) and (len(base) == len(key) or not (base[len(key)].isalnum() or base[len(key)] == "_")):
+                return val
+        raise AssertionError(f"unmapped C type in {decl!r}")
+
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        params = params.strip()
+        plist = [] if params in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(argtypes), f"{name}: {len(plist)} parameters in qcb.h, {len(argtypes)} in _lib.SIGNATURES"
+        for i, (p, a) in enumerate(zip(plist, argtypes)):
+            want = ctype_of(p)
+            same = want is a or (ctypes.sizeof(want) == ctypes.sizeof(a) and {want, a} <= {ctypes.c_void_p, ctypes.c_char_p})
+            assert same, f"{name}: parameter {i} is {p.strip()!r} in qcb.h but {a.__name__} in _lib.SIGNATURES"
